@@ -1,0 +1,31 @@
+/*
+ * oracle.h -- CPU oracle for the Caracal RPMD hot path (TEST INFRASTRUCTURE ONLY).
+ *
+ * A literal C restatement of the reference's Fortran routines, used exclusively as
+ * the parity checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs.  The product (caracal_b200/) never links or loads it.
+ * Parity status: UNPINNED by the reference (no Fortran toolchain here,
+ * reference ships no tests or golden outputs) -- see DESIGN.md "Oracle".
+ *
+ * Layout everywhere: Fortran X(3,natoms,nbeads) column-major == C [bead][atom][xyz].
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include "oracle_real.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- `real`-typed internals (double in the checker build, counting type otherwise) ---- */
+void oracle_egrad_h3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_h3_pote_real(const real R[3], real *pe, real dpe[3]);
+void oracle_egrad_oh3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_oh3_pot_real(const real R[6], real *V, real dVdR[6]);
+void oracle_egrad_ch4h_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_ch4h_parts_real(const real *q18, real parts[3], real *V);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+/*
+ * rpmd.h -- state struct + entry points of the CPU oracle's integrator part
+ * (TEST INFRASTRUCTURE ONLY, see oracle.h).  The struct makes explicit the module
+ * globals of the reference (evb_mod.f90:243-291 q_i,p_i,nbeads,beta,andersen_step,...;
+ * general.f90 bath block vnh,qnh,gnh,nfree; mass(:), at_move(:)).
+ */
+#ifndef ORACLE_RPMD_H
+#define ORACLE_RPMD_H
+#include <stdint.h>
+
+#define ORC_MAXBEADS 1024 /* fftw_mod.f90:6 Nmax */
+#define ORC_MAXBOND 8
+#define ORC_MAXREAC 4
+#define ORC_MAXREACAT 200 /* calc_rate_read.f90:540 */
+
+#define ORC_PES_NONE 0
+#define ORC_PES_H3 1
+#define ORC_PES_OH3 2
+#define ORC_PES_CH4H 3
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void (*orc_custom_grad_fn)(const double *xyz, double *e, double *g, int natoms);
+
+typedef struct orc_sys {
+    int natoms, nbeads, pes;
+    double *mass;
+    int *at_move;
+    double beta, dt, kelvin;
+    int thermostat; /* 0 none, 1 Andersen, 2 NHC (dynamic.f90:463-465) */
+    int andersen_step, nve;
+    double nose_q, vnh[4], qnh[4], gnh[4];
+    int nfree;
+    /* reaction-coordinate mechanism (0-based atom indices) */
+    int form_num, break_num;
+    int bond_form[ORC_MAXBOND][2], bond_break[ORC_MAXBOND][2];
+    double form_ref[ORC_MAXBOND], break_ref[ORC_MAXBOND];
+    int sum_reacs, n_reac[ORC_MAXREAC], at_reac[ORC_MAXREAC][ORC_MAXREACAT];
+    double mass_reac[ORC_MAXREAC], R_inf;
+    double k_force; /* k_force(um_window_act) */
+    double *q, *p;  /* [bead][atom][xyz] */
+    /* normal-deviate source */
+    uint64_t seed;
+    uint32_t traj, event;
+    const double *inject;
+    long inject_len, inject_pos;
+    orc_custom_grad_fn custom_grad;
+} orc_sys;
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void oracle_rng_normal_pair(uint64_t seed, uint32_t traj, uint32_t event, uint32_t bead,
+                            uint32_t pair, double z[2]);
+
+orc_sys *oracle_sys_create(int natoms, int nbeads, const double *mass, const int *at_move,
+                           double beta, double dt, int pes);
+void oracle_sys_free(orc_sys *s);
+void oracle_sys_set_mecha(orc_sys *s, int form_num, const int *bond_form, int break_num,
+                          const int *bond_break, const double *form_ref, const double *break_ref,
+                          int sum_reacs, const int *n_reac, const int *at_reac, double R_inf);
+void oracle_sys_set_thermostat(orc_sys *s, int thermostat, int andersen_step, double kelvin,
+                               double nose_q);
+void oracle_sys_set_kforce(orc_sys *s, double k_force);
+void oracle_sys_set_rng(orc_sys *s, uint64_t seed, uint32_t traj, uint32_t event);
+void oracle_sys_inject_normals(orc_sys *s, const double *z, long n);
+void oracle_sys_set_custom_grad(orc_sys *s, orc_custom_grad_fn fn);
+double *oracle_sys_q(orc_sys *s);
+double *oracle_sys_p(orc_sys *s);
+void oracle_sys_get_nhc(orc_sys *s, double *v4q4);
+
+void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g);
+void orc_get_centroid(orc_sys *s, double *centroid);
+void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double *xi_act,
+                 double *dxi_act, double *d2xi_act, int mode);
+void orc_umbrella(orc_sys *s, const double *centroid, double xi_ideal, double *xi_real,
+                  double *dxi_act, double *grad_xyz, int mode);
+int orc_constrain_q(orc_sys *s, const double *centroid, double xi_ideal, const double *dxi_act,
+                    double dt);
+void orc_constrain_p(orc_sys *s, const double *dxi_act);
+void orc_andersen(orc_sys *s);
+void orc_nhc(orc_sys *s, double dt);
+int orc_transrot(orc_sys *s);
+void orc_mdinit(orc_sys *s, double *derivs, double xi_ideal, double *dxi_act, int bias_mode);
+int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_ideal,
+               double *xi_real, double *dxi_act, int constrain);
+int orc_recross_pair(orc_sys *s, double xi_ideal, int child_evol, double *num, double *denom);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
