@@ -1,0 +1,17 @@
+"""caracal_b200 -- B200-native (sm_100a) RPMD hot path for Trebonius91/Caracal.
+
+The product is the C-ABI shared library caracal_b200/libcaracal_gpu.so
+(include/caracal_gpu.h).  This package only loads it (lib.py) and mirrors the reference's
+operator interface for the path (api.py): egrad_<pes>(q,Natoms,Nbeads) -> V,dVdq,info ;
+mdinit / verlet / recross / umbrella work units on batches of ring polymers.
+"""
+from .lib import (CaracalGpuError, LIB_PATH, PES_CH4H, PES_H3, PES_IDS, PES_OH3, TRANSFORM_EXACT,  # noqa: F401
+                  TRANSFORM_REFERENCE, load)
+from .api import (RPMD, Mechanism, atomic_mass_au, beta_calc_rate, beta_dynamic, dt_au, egrad, egrad_ch4h,  # noqa: F401
+                  egrad_h3, egrad_oh3)
+
+
+def build_if_needed(force=False):
+    """Compile libcaracal_gpu.so in-tree if it is missing or stale (nvcc, sm_100a)."""
+    from . import build as _b
+    return _b.build(force=force)

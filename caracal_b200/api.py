@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference's interface for the RPMD hot path, over the C-ABI.
+
+Names and argument meaning follow the reference:
+  egrad_h3 / egrad_oh3 / egrad_ch4h (q, Natoms, Nbeads) -> V, dVdq, info   (egrad_*.f)
+  RPMD.mdinit / RPMD.verlet                                                  (mdinit.f90, verlet.f90)
+  RPMD.recross_children                                                      (recross.f90 worker body)
+  RPMD.umbrella_window                                                       (calc_rate.f90 worker body)
+Arrays are numpy float64 in the reference's layout [traj][bead][atom][xyz]
+(= Fortran X(3,natoms,nbeads) per trajectory).  Everything computes on the GPU through
+libcaracal_gpu.so; there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+
+from . import lib as _l
+
+# ---- unit helpers: the literal semantics of the reference's drivers ----------
+_F32 = np.float32
+EMASS = 5.485799095e-4  # general.f90:252
+AMU = {"H": 1.00782503207, "D": 2.0141017778, "C": 12.00000, "N": 14.0030740048, "O": 15.99491461956}
+
+
+def atomic_mass_au(symbol):
+    """atommass.f90:58-216: isotope mass in amu divided by emass."""
+    return AMU[symbol.upper()] / EMASS
+
+
+def dt_au(dt_fs):
+    """dt = dt/2.41888428E-2 with a REAL*4 literal (dynamic.f90:589, calc_rate.f90:466)."""
+    return float(dt_fs) / float(_F32(2.41888428e-2))
+
+
+def beta_calc_rate(kelvin):
+    """beta = 1/(kelvin*k_B), k_B = 3.16681517576e-06 as REAL*4 (calc_rate.f90:144,476)."""
+    return 1.0 / (float(kelvin) * float(_F32(3.16681517576e-06)))
+
+
+def beta_dynamic(kelvin):
+    """beta = 1/(kelvin*0.316679D-5) (dynamic.f90:584)."""
+    return 1.0 / (float(kelvin) * 0.316679e-5)
+
+
+def _dp(a):
+    return a.ctypes.data_as(_l.c_double_p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(_l.c_int_p) if a is not None else None
+
+
+def _up(a):
+    return a.ctypes.data_as(_l.c_u32_p) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Mechanism:
+    """MECHA{} section, BIMOLEC family: 1-based atom indices as in the key file."""
+
+    def __init__(self, bond_form, bond_break, reactants, dist_inf, ts_struc):
+        self.bond_form = np.asarray(bond_form, dtype=np.int32).reshape(-1, 2)
+        self.bond_break = np.asarray(bond_break, dtype=np.int32).reshape(-1, 2)
+        self.reactants = [np.asarray(r, dtype=np.int32) for r in reactants]
+        self.R_inf = float(dist_inf)
+        ts = _f64(ts_struc)
+        # bonds_ref.f90:39-62: reference bond lengths from the TS structure
+        self.form_ref = np.array([np.linalg.norm(ts[a - 1] - ts[b - 1]) for a, b in self.bond_form])
+        self.break_ref = np.array([np.linalg.norm(ts[a - 1] - ts[b - 1]) for a, b in self.bond_break])
+
+
+class RPMD:
+    """One handle per process/GPU: the explicit form of the reference's module globals."""
+
+    def __init__(self, pes, nbeads, mass, beta, dt, device=0, at_move=None):
+        self._lib = _l.load()
+        self.pes_id = _l.PES_IDS[pes] if isinstance(pes, str) else int(pes)
+        self.mass = _f64(mass)
+        self.natoms = len(self.mass)
+        self.nbeads = int(nbeads)
+        self.beta, self.dt = float(beta), float(dt)
+        am = None if at_move is None else np.ascontiguousarray(at_move, dtype=np.int32)
+        self._h = ctypes.c_void_p()
+        rc = self._lib.crcl_create(ctypes.byref(self._h), device, self.natoms, self.nbeads, _dp(self.mass), _ip(am),
+                                   self.beta, self.dt, self.pes_id)
+        _l.check(rc, None, "crcl_create")
+
+    def close(self):
+        if self._h:
+            self._lib.crcl_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        _l.check(rc, self._h, what)
+
+    # -- configuration ------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._ck(self._lib.crcl_set_stream(self._h, ctypes.c_void_p(cuda_stream)), "crcl_set_stream")
+
+    def synchronize(self):
+        self._ck(self._lib.crcl_synchronize(self._h), "crcl_synchronize")
+
+    def set_beta_dt(self, beta, dt):
+        self.beta, self.dt = float(beta), float(dt)
+        self._ck(self._lib.crcl_set_beta_dt(self._h, self.beta, self.dt), "crcl_set_beta_dt")
+
+    def set_transform(self, mode):
+        self._ck(self._lib.crcl_set_transform(self._h, int(mode)), "crcl_set_transform")
+
+    def set_mechanism(self, m):
+        bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
+        bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)
+        nr = np.array([len(r) for r in m.reactants], dtype=np.int32)
+        ar = np.ascontiguousarray(np.concatenate(m.reactants), dtype=np.int32)
+        fr, br = _f64(m.form_ref), _f64(m.break_ref)
+        self._ck(self._lib.crcl_set_mechanism(self._h, len(bf), _ip(bf), len(bb), _ip(bb), _dp(fr), _dp(br), len(nr),
+                                              _ip(nr), _ip(ar), m.R_inf), "crcl_set_mechanism")
+
+    def set_thermostat(self, thermostat, andersen_step=0, kelvin=0.0, nose_q=0.0):
+        self._ck(self._lib.crcl_set_thermostat(self._h, int(thermostat), int(andersen_step), float(kelvin),
+                                               float(nose_q)), "crcl_set_thermostat")
+
+    def set_seed(self, seed):
+        self._ck(self._lib.crcl_set_seed(self._h, int(seed)), "crcl_set_seed")
+
+    # -- PES seam -------------------------------------------------------------------------------
+    def egrad(self, q, pes_id=None):
+        q = _f64(q)
+        nimg = q.size // (3 * self.natoms)
+        V = np.empty(nimg)
+        g = np.empty_like(q)
+        info = ctypes.c_int(0)
+        self._ck(self._lib.crcl_egrad(self._h, pes_id or self.pes_id, _dp(q), self.natoms, nimg, _dp(V), _dp(g),
+                                      ctypes.byref(info)), "crcl_egrad")
+        return V, g, info.value
+
+    # -- integrator seam ------------------------------------------------------------------------
+    def _shape(self, q):
+        q = _f64(q)
+        per = self.nbeads * self.natoms * 3
+        if q.size % per:
+            raise ValueError("q size is not a multiple of nbeads*natoms*3")
+        return q.reshape(-1, self.nbeads, self.natoms, 3)
+
+    def mdinit(self, q, bias_mode=0, xi_ideal=None, k_force=None, traj_id=None, event=None):
+        q = self._shape(q)
+        nt = q.shape[0]
+        p = np.zeros_like(q)
+        g = np.zeros_like(q)
+        dxi = np.zeros((nt, self.natoms, 3))
+        xi = None if xi_ideal is None else _f64(np.broadcast_to(xi_ideal, (nt,)))
+        kf = None if k_force is None else _f64(np.broadcast_to(k_force, (nt,)))
+        tid = None if traj_id is None else np.ascontiguousarray(traj_id, dtype=np.uint32)
+        ev = np.zeros(nt, dtype=np.uint32) if event is None else np.ascontiguousarray(event, dtype=np.uint32)
+        self._ck(self._lib.crcl_mdinit(self._h, nt, bias_mode, _dp(xi), _dp(kf), _dp(q), _dp(p), _dp(g), _dp(dxi),
+                                       _up(tid), _up(ev)), "crcl_mdinit")
+        return p, g, dxi, ev
+
+    def verlet(self, q, p, derivs, nsteps=1, istep0=0, constrain=-1, xi_ideal=None, k_force=None, dxi=None,
+               status=None, traj_id=None, event=None):
+        """Advance in place; returns (epot, xi_real, status)."""
+        for a in (q, p, derivs):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous):
+                raise ValueError("q, p, derivs must be C-contiguous float64 arrays (updated in place)")
+        nt = q.size // (self.nbeads * self.natoms * 3)
+        xi = None if xi_ideal is None else _f64(np.broadcast_to(xi_ideal, (nt,)))
+        kf = None if k_force is None else _f64(np.broadcast_to(k_force, (nt,)))
+        epot = np.zeros(nt)
+        xr = np.zeros(nt)
+        st = np.zeros(nt, dtype=np.int32) if status is None else status
+        tid = None if traj_id is None else np.ascontiguousarray(traj_id, dtype=np.uint32)
+        self._ck(self._lib.crcl_verlet(self._h, nt, int(nsteps), int(istep0), int(constrain), _dp(xi), _dp(kf),
+                                       _dp(q), _dp(p), _dp(derivs), _dp(epot), _dp(xr), _dp(dxi), _ip(st), _up(tid),
+                                       _up(event)), "crcl_verlet")
+        return epot, xr, st
+
+    def calc_xi(self, coords, xi_ideal=0.0, mode=1, hams=False):
+        c = _f64(coords).reshape(-1, self.natoms, 3)
+        n = c.shape[0]
+        xid = _f64(np.broadcast_to(xi_ideal, (n,)))
+        xi = np.empty(n)
+        dxi = np.empty_like(c)
+        hh = np.empty_like(c) if hams else None
+        self._ck(self._lib.crcl_calc_xi(self._h, n, _dp(c), _dp(xid), int(mode), _dp(xi), _dp(dxi), _dp(hh)),
+                 "crcl_calc_xi")
+        return (xi, dxi, hh) if hams else (xi, dxi)
+
+    # -- work units -----------------------------------------------------------------------------
+    def recross_children(self, q_parents, npairs, child_evol, xi_ideal, pair0=0):
+        qp = self._shape(q_parents)
+        num = np.zeros(child_evol)
+        den = ctypes.c_double(0.0)
+        st = np.zeros(max(npairs, 1), dtype=np.int32)
+        self._ck(self._lib.crcl_recross_children(self._h, _dp(qp), qp.shape[0], int(pair0), int(npairs),
+                                                 int(child_evol), float(xi_ideal), _dp(num), ctypes.byref(den),
+                                                 _ip(st)), "crcl_recross_children")
+        return num, den.value, st[:npairs]
+
+    def recross_children_dev(self, d_q_parents, nparent, npairs, child_evol, xi_ideal, d_num, d_denom, pair0=0,
+                             d_status=None):
+        """Device-pointer variant (ints from torch.Tensor.data_ptr()); asynchronous on the handle's stream."""
+        self._ck(self._lib.crcl_recross_children_dev(self._h, ctypes.c_void_p(d_q_parents), int(nparent), int(pair0),
+                                                     int(npairs), int(child_evol), float(xi_ideal),
+                                                     ctypes.c_void_p(d_num), ctypes.c_void_p(d_denom),
+                                                     ctypes.c_void_p(d_status) if d_status else None),
+                 "crcl_recross_children_dev")
+
+    def umbrella_window(self, q0, xi0, k_force, ntraj, equi_steps, sample_steps, traj_id0=0):
+        q0 = _f64(q0)
+        avg = np.zeros(ntraj)
+        var = np.zeros(ntraj)
+        st = np.zeros(ntraj, dtype=np.int32)
+        self._ck(self._lib.crcl_umbrella_window(self._h, _dp(q0), float(xi0), float(k_force), int(ntraj),
+                                                int(equi_steps), int(sample_steps), int(traj_id0), _dp(avg),
+                                                _dp(var), _ip(st)), "crcl_umbrella_window")
+        return avg, var, st
+
+    # -- hooks ------------------------------------------------------------------------------------
+    def rng_normals(self, seed, traj, event, bead, n):
+        out = np.empty(n)
+        self._ck(self._lib.crcl_rng_normals(self._h, int(seed), int(traj), int(event), int(bead), int(n), _dp(out)),
+                 "crcl_rng_normals")
+        return out
+
+    def launch_count(self):
+        return int(self._lib.crcl_launch_count(self._h))
+
+    def last_kernel_ms(self):
+        return float(self._lib.crcl_last_kernel_ms(self._h))
+
+    def kernel_timings(self, max_n=256):
+        """ms of each trajectory/egrad kernel launched since the previous call (syncs the stream)"""
+        buf = np.zeros(max_n)
+        n = self._lib.crcl_kernel_timings(self._h, _dp(buf), max_n)
+        if n < 0:
+            self._ck(n, "crcl_kernel_timings")
+        return buf[:n].copy()
+
+    def measure_fp64_tflops(self, iters=8192):
+        return float(self._lib.crcl_measure_fp64_tflops(self._h, int(iters)))
+
+
+# ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
+_PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"]}
+_egrad_handles = {}
+
+
+def egrad(pes, q, natoms=None, nbeads=None, device=0):
+    pes_id = _l.PES_IDS[pes] if isinstance(pes, str) else int(pes)
+    key = (pes_id, device)
+    if key not in _egrad_handles:
+        m = [atomic_mass_au(s) for s in _PES_MASS[pes_id]]
+        _egrad_handles[key] = RPMD(pes_id, 1, m, 1.0, 1.0, device=device)
+    q = _f64(q)
+    if natoms is not None and natoms != _l.PES_NATOMS[pes_id]:
+        raise ValueError("Natoms does not match the surface")
+    V, g, info = _egrad_handles[key].egrad(q)
+    return V, g.reshape(q.shape), info
+
+
+def egrad_h3(q, Natoms=3, Nbeads=None):
+    return egrad(_l.PES_H3, q, Natoms, Nbeads)
+
+
+def egrad_oh3(q, Natoms=4, Nbeads=None):
+    return egrad(_l.PES_OH3, q, Natoms, Nbeads)
+
+
+def egrad_ch4h(q, Natoms=6, Nbeads=None):
+    return egrad(_l.PES_CH4H, q, Natoms, Nbeads)

@@ -1,0 +1,847 @@
+// api.cu -- C-ABI of libcaracal_gpu.so (include/caracal_gpu.h): handle management, host-side
+// set-up that the Fortran drivers do once (free ring-polymer kernels, mechanism tables), and
+// kernel dispatch.  No CPU compute path exists behind these entry points.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "crcl_common.cuh"
+#include "pes_h3.cuh"
+#include "pes_oh3.cuh"
+#include "pes_ch4h.cuh"
+#include "traj_inst.cuh"
+
+using namespace crcl;
+
+struct crcl_handle_s {
+    int device = 0, natoms = 0, nbeads = 0, pes = 0;
+    double beta = 0, dt = 0, kelvin = 0, nose_q = 0;
+    int thermostat = 0, andersen_step = 0, transform = CRCL_TRANSFORM_REFERENCE;
+    uint64_t seed = 0;
+    std::vector<double> mass;
+    std::vector<int> at_move;
+    Mech mech{};
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    // ring of CUDA-event pairs bracketing every trajectory/egrad kernel launch on h->stream
+    static constexpr int NEV = 256;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // the pair of the most recent launch
+    cudaEvent_t evs[2 * NEV] = {nullptr};
+    int ev_head = 0, ev_count = 0;
+    bool timed = false;
+    double* d_fker = nullptr;
+    bool fker_dirty = true;
+    crcl_host_grad_fn cb = nullptr;
+    void* cb_user = nullptr;
+    long long launches = 0;
+    std::string err;
+    // grow-only device scratch
+    void* scratch[12] = {nullptr};
+    size_t scratch_sz[12] = {0};
+};
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+            return CRCL_ECUDA;                                                       \
+        }                                                                            \
+    } while (0)
+
+static void next_event_pair(crcl_handle h)
+{
+    const int i = h->ev_head;
+    h->ev0 = h->evs[2 * i];
+    h->ev1 = h->evs[2 * i + 1];
+    h->ev_head = (i + 1) % crcl_handle_s::NEV;
+    if (h->ev_count < crcl_handle_s::NEV) h->ev_count++;
+}
+
+static int fail(crcl_handle h, int code, const char* msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+
+template <class T>
+static int scratch(crcl_handle h, int slot, size_t n, T** out)
+{
+    const size_t bytes = n * sizeof(T);
+    if (h->scratch_sz[slot] < bytes) {
+        if (h->scratch[slot]) cudaFree(h->scratch[slot]);
+        h->scratch[slot] = nullptr;
+        h->scratch_sz[slot] = 0;
+        if (cudaMalloc(&h->scratch[slot], bytes ? bytes : 8) != cudaSuccess) {
+            h->err = "cudaMalloc failed";
+            return CRCL_ENOMEM;
+        }
+        h->scratch_sz[slot] = bytes;
+    }
+    *out = static_cast<T*>(h->scratch[slot]);
+    return CRCL_OK;
+}
+
+// ---- free ring-polymer kernels f_c, f_a, f_b (see traj_kernel.cuh header) ------------------
+// d_k as verlet.f90:405-433: w_k = (2 nbeads/beta) sin(k pi/nbeads), mirrored k <-> N-k.
+static void build_fker(int N, double beta, double dt, std::vector<double>& f)
+{
+    f.assign((size_t)3 * N, 0.0);
+    std::vector<double> dc(N), da(N), db(N);
+    dc[0] = 1.0;
+    da[0] = 0.0;
+    db[0] = dt;
+    const double beta_n = beta / N, twown = 2.0 / beta_n, pi_n = PI_QMDFF / N;
+    for (int k = 1; k <= N / 2; k++) {
+        const double wk = twown * std::sin(k * pi_n), wt = wk * dt;
+        dc[k] = std::cos(wt);
+        da[k] = -wk * std::sin(wt);
+        db[k] = std::sin(wt) / wk;
+    }
+    for (int k = 1; k <= (N - 1) / 2; k++) {
+        dc[N - k] = dc[k];
+        da[N - k] = da[k];
+        db[N - k] = db[k];
+    }
+    for (int j = 0; j < N; j++) {
+        long double sc = 0, sa = 0, sb = 0;
+        for (int k = 0; k < N; k++) {
+            const long double c = cosl(2.0L * 3.14159265358979323846264338327950288L * ((k * j) % N) / N);
+            sc += dc[k] * c;
+            sa += da[k] * c;
+            sb += db[k] * c;
+        }
+        f[j] = (double)(sc / N);
+        f[N + j] = (double)(sa / N);
+        f[2 * N + j] = (double)(sb / N);
+    }
+}
+
+static int ensure_fker(crcl_handle h)
+{
+    if (!h->fker_dirty) return CRCL_OK;
+    std::vector<double> f;
+    build_fker(h->nbeads, h->beta, h->dt, f);
+    if (h->d_fker) cudaFree(h->d_fker);
+    CK(cudaMalloc(&h->d_fker, f.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(h->d_fker, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->fker_dirty = false;
+    return CRCL_OK;
+}
+
+// ---- small kernels ---------------------------------------------------------------------------
+template <class PES>
+__global__ void egrad_kernel(const double* __restrict__ q, int nimg, double* __restrict__ V,
+                             double* __restrict__ g, int* __restrict__ info)
+{
+    constexpr int NC = 3 * PES::NATOMS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nimg) return;
+    double x[NC], gr[NC], e;
+#pragma unroll
+    for (int c = 0; c < NC; c++) x[c] = q[(size_t)i * NC + c];
+    const int w = PES::eval(x, e, gr);
+    V[i] = e;
+#pragma unroll
+    for (int c = 0; c < NC; c++) g[(size_t)i * NC + c] = gr[c];
+    if (w && info) atomicOr(info, w);
+}
+
+template <int NAT>
+__global__ void calc_xi_kernel(const __grid_constant__ TrajArgs A, int n, const double* coords,
+                               const double* xi_ideal, int mode, double* xi, double* dxi, double* hams)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x[3 * NAT], d[3 * NAT], hh[3 * NAT], v;
+#pragma unroll
+    for (int c = 0; c < 3 * NAT; c++) x[c] = coords[(size_t)i * 3 * NAT + c];
+    calc_xi<NAT>(A.mech, A.mass, x, xi_ideal[i], mode, v, d, (hams && mode == 1) ? hh : nullptr, A.beta);
+    xi[i] = v;
+#pragma unroll
+    for (int c = 0; c < 3 * NAT; c++) {
+        dxi[(size_t)i * 3 * NAT + c] = d[c];
+        if (hams && mode == 1) hams[(size_t)i * 3 * NAT + c] = hh[c];
+    }
+}
+
+__global__ void rng_kernel(uint64_t seed, uint32_t traj, uint32_t event, uint32_t bead, int n, double* out)
+{
+    const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * pr >= n) return;
+    double z0, z1;
+    normal_pair(seed, traj, event, bead, (uint32_t)pr, z0, z1);
+    out[2 * pr] = z0;
+    if (2 * pr + 1 < n) out[2 * pr + 1] = z1;
+}
+
+// DFMA throughput probe: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b);
+        x1 = fma(x1, a, b);
+        x2 = fma(x2, a, b);
+        x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b);
+        x5 = fma(x5, a, b);
+        x6 = fma(x6, a, b);
+        x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+namespace crcl {
+// kappa_num[l] = sum_t weight[t]*theta[l][t], kappa_denom = sum_t denom_part[t]; fixed
+// summation order -> bit-reproducible for a given (pair0, npairs) regardless of launch shape.
+__global__ void reduce_kappa_kernel(const unsigned char* theta, const double* weight,
+                                    const double* denom_part, int ntraj, int nsteps,
+                                    double* kappa_num, double* kappa_denom)
+{
+    __shared__ double sh[256];
+    const int l = blockIdx.x;  // l == nsteps -> denominator
+    double s = 0.0;
+    if (l < nsteps) {
+        for (int t = threadIdx.x; t < ntraj; t += 256)
+            if (theta[(size_t)l * ntraj + t]) s += weight[t];
+    } else {
+        for (int t = threadIdx.x; t < ntraj; t += 256) s += denom_part[t];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if (l < nsteps)
+            kappa_num[l] = sh[0];
+        else
+            *kappa_denom = sh[0];
+    }
+}
+
+}  // namespace crcl
+
+// ---- dispatch --------------------------------------------------------------------------------
+static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode = 0)
+{
+    static const traj_launch_fn table[3][3] = {
+        {launch_h3_verlet, launch_h3_mdinit, launch_h3_recross},
+        {launch_oh3_verlet, launch_oh3_mdinit, launch_oh3_recross},
+        {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross}};
+    int row;
+    switch (h->pes) {
+    case CRCL_PES_H3: row = 0; break;
+    case CRCL_PES_OH3: row = 1; break;
+    case CRCL_PES_CH4H: row = 2; break;
+    default: return fail(h, CRCL_ENOSUP, "no device trajectory kernel for this PES id");
+    }
+    if (A.ntraj <= 0) return CRCL_OK;
+    int nosup = 0;
+    if (h->timed) {
+        next_event_pair(h);
+        cudaEventRecord(h->ev0, h->stream);
+    }
+    cudaError_t e = table[row][kind](h->nbeads, A, bias_mode, h->nose_q, h->stream, &nosup);
+    if (nosup) return fail(h, CRCL_ENOSUP, "fused trajectory kernel: nbeads must be a power of two <= 128");
+    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    h->launches++;
+    if (e != cudaSuccess) {
+        h->err = std::string("trajectory kernel launch: ") + cudaGetErrorString(e);
+        return CRCL_ECUDA;
+    }
+    return CRCL_OK;
+}
+
+static void fill_args(crcl_handle h, TrajArgs& A)
+{
+    memset(&A, 0, sizeof(A));
+    A.nbeads = h->nbeads;
+    A.beta = h->beta;
+    A.dt = h->dt;
+    A.kelvin = h->kelvin;
+    A.thermostat = h->thermostat;
+    A.andersen_step = h->andersen_step;
+    A.symmetrize = (h->transform == CRCL_TRANSFORM_REFERENCE) ? 1 : 0;
+    for (int i = 0; i < h->natoms && i < TRAJ_MAXNAT; i++) {
+        A.mass[i] = h->mass[i];
+        A.at_move[i] = h->at_move[i];
+    }
+    A.mech = h->mech;
+    A.seed = h->seed;
+    A.fker = h->d_fker;
+}
+
+static int pes_natoms(int pes)
+{
+    switch (pes) {
+    case CRCL_PES_H3: return 3;
+    case CRCL_PES_OH3: return 4;
+    case CRCL_PES_CH4H: return 6;
+    }
+    return -1;
+}
+
+// ---- C-ABI -----------------------------------------------------------------------------------
+extern "C" {
+
+int crcl_create(crcl_handle* out, int device, int natoms, int nbeads, const double* mass,
+                const int* at_move, double beta, double dt, int pes_id)
+{
+    if (!out || !mass || natoms <= 0 || nbeads <= 0) return CRCL_EINVAL;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CRCL_ENODEV;
+    if (device < 0 || device >= ndev) return CRCL_EINVAL;
+    if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE) {
+        const int n = pes_natoms(pes_id);
+        if (n < 0 || n != natoms) return CRCL_EINVAL;
+    }
+    crcl_handle h = new crcl_handle_s();
+    h->device = device;
+    h->natoms = natoms;
+    h->nbeads = nbeads;
+    h->pes = pes_id;
+    h->beta = beta;
+    h->dt = dt;
+    h->mass.assign(mass, mass + natoms);
+    h->at_move.assign(natoms, 1);
+    if (at_move)
+        for (int i = 0; i < natoms; i++) h->at_move[i] = at_move[i] ? 1 : 0;
+    h->mech.valid = 0;
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2 * crcl_handle_s::NEV; i++) ok = cudaEventCreate(&h->evs[i]) == cudaSuccess;
+    if (!ok) {
+        delete h;
+        return CRCL_ECUDA;
+    }
+    h->ev0 = h->evs[0];
+    h->ev1 = h->evs[1];
+    h->stream = h->own_stream;
+    h->timed = true;
+    *out = h;
+    return CRCL_OK;
+}
+
+int crcl_destroy(crcl_handle h)
+{
+    if (!h) return CRCL_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& s : h->scratch)
+        if (s) cudaFree(s);
+    if (h->d_fker) cudaFree(h->d_fker);
+    for (auto& e : h->evs)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(h->own_stream);
+    delete h;
+    return CRCL_OK;
+}
+
+const char* crcl_last_error(crcl_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int crcl_set_stream(crcl_handle h, void* s)
+{
+    if (!h) return CRCL_EINVAL;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return CRCL_OK;
+}
+
+int crcl_synchronize(crcl_handle h)
+{
+    if (!h) return CRCL_EINVAL;
+    CK(cudaStreamSynchronize(h->stream));
+    return CRCL_OK;
+}
+
+int crcl_set_beta_dt(crcl_handle h, double beta, double dt)
+{
+    if (!h) return CRCL_EINVAL;
+    if (beta != h->beta || dt != h->dt) h->fker_dirty = true;
+    h->beta = beta;
+    h->dt = dt;
+    return CRCL_OK;
+}
+
+int crcl_set_transform(crcl_handle h, int mode)
+{
+    if (!h || (mode != CRCL_TRANSFORM_REFERENCE && mode != CRCL_TRANSFORM_EXACT)) return CRCL_EINVAL;
+    h->transform = mode;
+    return CRCL_OK;
+}
+
+int crcl_set_host_gradient_cb(crcl_handle h, crcl_host_grad_fn fn, void* user)
+{
+    if (!h) return CRCL_EINVAL;
+    h->cb = fn;
+    h->cb_user = user;
+    return CRCL_OK;
+}
+
+int crcl_set_mechanism(crcl_handle h, int form_num, const int* bond_form, int break_num,
+                       const int* bond_break, const double* form_ref, const double* break_ref,
+                       int sum_reacs, const int* n_reac, const int* at_reac, double R_inf)
+{
+    if (!h) return CRCL_EINVAL;
+    const int rc = build_mech(h->mech, h->natoms, h->mass.data(), form_num, bond_form, break_num, bond_break,
+                              form_ref, break_ref, sum_reacs, n_reac, at_reac, R_inf);
+    if (rc == -1)
+        return fail(h, CRCL_ENOSUP, "mechanism exceeds the in-register limits (bonds<=4, fragments<=4, atoms<=8)");
+    if (rc == -2) return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    return CRCL_OK;
+}
+
+int crcl_set_thermostat(crcl_handle h, int thermostat, int andersen_step, double kelvin, double nose_q)
+{
+    if (!h || thermostat < 0 || thermostat > 2) return CRCL_EINVAL;
+    h->thermostat = thermostat;
+    h->andersen_step = andersen_step;
+    h->kelvin = kelvin;
+    h->nose_q = nose_q;
+    return CRCL_OK;
+}
+
+int crcl_set_seed(crcl_handle h, uint64_t seed)
+{
+    if (!h) return CRCL_EINVAL;
+    h->seed = seed;
+    return CRCL_OK;
+}
+
+// ---- PES seam ---------------------------------------------------------------------------------
+int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int nimg, double* d_V,
+                   double* d_dVdq, int* d_info)
+{
+    if (!h || !d_q || !d_V || !d_dVdq || nimg < 0) return CRCL_EINVAL;
+    if (pes_natoms(pes_id) != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the PES");
+    if (nimg == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    const int tpb = 128, grid = (nimg + tpb - 1) / tpb;
+    if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
+    if (h->timed) {
+        next_event_pair(h);
+        cudaEventRecord(h->ev0, h->stream);
+    }
+    switch (pes_id) {
+    case CRCL_PES_H3: egrad_kernel<PesH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_OH3: egrad_kernel<PesOH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_CH4H: egrad_kernel<PesCH4H><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    default: return fail(h, CRCL_ENOSUP, "unknown PES id");
+    }
+    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
+int crcl_egrad(crcl_handle h, int pes_id, const double* q, int natoms, int nimg, double* V,
+               double* dVdq, int* info)
+{
+    if (!h || !q || !V || !dVdq || nimg < 0) return CRCL_EINVAL;
+    if (info) *info = 0;
+    if (nimg == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)nimg * 3 * natoms;
+    double *dq, *dg, *dV;
+    int* di;
+    int rc;
+    if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, (size_t)nimg, &dV)) ||
+        (rc = scratch(h, 3, (size_t)1, &di)))
+        return rc;
+    CK(cudaMemcpyAsync(dq, q, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = crcl_egrad_dev(h, pes_id, dq, natoms, nimg, dV, dg, di))) return rc;
+    CK(cudaMemcpyAsync(V, dV, (size_t)nimg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(dVdq, dg, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    int hi = 0;
+    CK(cudaMemcpyAsync(&hi, di, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (info) *info = hi;
+    return CRCL_OK;
+}
+
+// ---- integrator seam --------------------------------------------------------------------------
+static int check_traj_call(crcl_handle h, int constrain)
+{
+    if (!h) return CRCL_EINVAL;
+    if (h->natoms > TRAJ_MAXNAT) return fail(h, CRCL_ENOSUP, "natoms exceeds the in-register trajectory path");
+    if (constrain < -1 || constrain > 3) return fail(h, CRCL_EINVAL, "constrain must be -1..3");
+    if (constrain >= 0 && !h->mech.valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    return CRCL_OK;
+}
+
+int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain, const double* xi_ideal,
+                const double* k_force, double* q, double* p, double* derivs, double* epot,
+                double* xi_real, double* dxi, int* status, const uint32_t* traj_id, uint32_t* event0)
+{
+    int rc = check_traj_call(h, constrain);
+    if (rc) return rc;
+    if (!q || !p || !derivs || ntraj < 0 || nsteps < 0) return CRCL_EINVAL;
+    if (ntraj == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    const size_t n = (size_t)ntraj * h->nbeads * h->natoms * 3, nd = (size_t)ntraj * h->natoms * 3;
+    double *dq, *dp, *dg, *ddxi, *dep, *dxr, *dxid, *dkf, *dnhc;
+    int* dst;
+    uint32_t *dtid, *dev;
+    if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
+        (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntraj * 4, &dep)) ||
+        (rc = scratch(h, 5, (size_t)ntraj, &dst)) || (rc = scratch(h, 6, (size_t)ntraj * 2, &dtid)) ||
+        (rc = scratch(h, 7, (size_t)ntraj * 8, &dnhc)))
+        return rc;
+    dxr = dep + ntraj;
+    dxid = dep + 2 * ntraj;
+    dkf = dep + 3 * ntraj;
+    dev = dtid + ntraj;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dq, q, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dp, p, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dg, derivs, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (dxi) CK(cudaMemcpyAsync(ddxi, dxi, nd * sizeof(double), cudaMemcpyHostToDevice, s));
+    else CK(cudaMemsetAsync(ddxi, 0, nd * sizeof(double), s));
+    if (xi_ideal) CK(cudaMemcpyAsync(dxid, xi_ideal, ntraj * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (k_force) CK(cudaMemcpyAsync(dkf, k_force, ntraj * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (traj_id) CK(cudaMemcpyAsync(dtid, traj_id, ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (event0) CK(cudaMemcpyAsync(dev, event0, ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    else CK(cudaMemsetAsync(dev, 0, ntraj * sizeof(uint32_t), s));
+    if (status) CK(cudaMemcpyAsync(dst, status, ntraj * sizeof(int), cudaMemcpyHostToDevice, s));
+    else CK(cudaMemsetAsync(dst, 0, ntraj * sizeof(int), s));
+    TrajArgs A;
+    fill_args(h, A);
+    A.ntraj = ntraj;
+    A.nsteps = nsteps;
+    A.istep0 = istep0;
+    A.constrain = constrain;
+    A.xi_ideal = xi_ideal ? dxid : nullptr;
+    A.k_force = k_force ? dkf : nullptr;
+    A.q = dq;
+    A.p = dp;
+    A.g = dg;
+    A.dxi = ddxi;
+    A.epot = dep;
+    A.xi_real = dxr;
+    A.status = dst;
+    A.nhc = dnhc;  // NHC chain state persists on the device between calls of one handle
+    A.traj_id = traj_id ? dtid : nullptr;
+    A.event = dev;
+    if ((rc = launch_traj(h, K_VERLET, A))) return rc;
+    CK(cudaMemcpyAsync(q, dq, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p, dp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(derivs, dg, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dxi) CK(cudaMemcpyAsync(dxi, ddxi, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (epot) CK(cudaMemcpyAsync(epot, dep, ntraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (xi_real) CK(cudaMemcpyAsync(xi_real, dxr, ntraj * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (status) CK(cudaMemcpyAsync(status, dst, ntraj * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (event0) CK(cudaMemcpyAsync(event0, dev, ntraj * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CRCL_OK;
+}
+
+int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double* xi_ideal, const double* k_force,
+                const double* q, double* p, double* derivs, double* dxi, const uint32_t* traj_id,
+                uint32_t* event0)
+{
+    int rc = check_traj_call(h, bias_mode ? 0 : -1);
+    if (rc) return rc;
+    if (!q || !p || !derivs || ntraj < 0 || bias_mode < 0 || bias_mode > 2) return CRCL_EINVAL;
+    if (ntraj == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    const size_t n = (size_t)ntraj * h->nbeads * h->natoms * 3, nd = (size_t)ntraj * h->natoms * 3;
+    double *dq, *dp, *dg, *ddxi, *dep, *dxid, *dkf, *dnhc;
+    uint32_t *dtid, *dev;
+    if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
+        (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntraj * 4, &dep)) ||
+        (rc = scratch(h, 6, (size_t)ntraj * 2, &dtid)) || (rc = scratch(h, 7, (size_t)ntraj * 8, &dnhc)))
+        return rc;
+    dxid = dep + 2 * ntraj;
+    dkf = dep + 3 * ntraj;
+    dev = dtid + ntraj;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dq, q, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dp, p, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (xi_ideal) CK(cudaMemcpyAsync(dxid, xi_ideal, ntraj * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (k_force) CK(cudaMemcpyAsync(dkf, k_force, ntraj * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (traj_id) CK(cudaMemcpyAsync(dtid, traj_id, ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    if (event0) CK(cudaMemcpyAsync(dev, event0, ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    else CK(cudaMemsetAsync(dev, 0, ntraj * sizeof(uint32_t), s));
+    TrajArgs A;
+    fill_args(h, A);
+    A.ntraj = ntraj;
+    A.xi_ideal = xi_ideal ? dxid : nullptr;
+    A.k_force = k_force ? dkf : nullptr;
+    A.q = dq;
+    A.p = dp;
+    A.g = dg;
+    A.dxi = ddxi;
+    A.nhc = dnhc;
+    A.traj_id = traj_id ? dtid : nullptr;
+    A.event = dev;
+    if ((rc = launch_traj(h, K_MDINIT, A, bias_mode))) return rc;
+    CK(cudaMemcpyAsync(p, dp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(derivs, dg, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dxi && bias_mode) CK(cudaMemcpyAsync(dxi, ddxi, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (event0) CK(cudaMemcpyAsync(event0, dev, ntraj * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CRCL_OK;
+}
+
+int crcl_calc_xi(crcl_handle h, int ncoord, const double* coords, const double* xi_ideal, int mode,
+                 double* xi, double* dxi, double* hams)
+{
+    if (!h || !coords || !xi || !dxi || ncoord < 0 || (mode != 1 && mode != 2)) return CRCL_EINVAL;
+    if (!h->mech.valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    if (ncoord == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)ncoord * h->natoms * 3;
+    double *dc, *dd, *dh, *dx;
+    int rc;
+    if ((rc = scratch(h, 0, n, &dc)) || (rc = scratch(h, 1, n, &dd)) || (rc = scratch(h, 2, n, &dh)) ||
+        (rc = scratch(h, 4, (size_t)ncoord * 2, &dx)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dc, coords, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    std::vector<double> xid(ncoord, 0.0);
+    if (xi_ideal) xid.assign(xi_ideal, xi_ideal + ncoord);
+    CK(cudaMemcpyAsync(dx + ncoord, xid.data(), ncoord * sizeof(double), cudaMemcpyHostToDevice, s));
+    TrajArgs A;
+    fill_args(h, A);
+    const int tpb = 64, grid = (ncoord + tpb - 1) / tpb;
+    double* hp = hams ? dh : nullptr;
+    switch (h->natoms) {
+    case 3: calc_xi_kernel<3><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    case 4: calc_xi_kernel<4><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    case 5: calc_xi_kernel<5><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    case 6: calc_xi_kernel<6><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    case 7: calc_xi_kernel<7><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    case 8: calc_xi_kernel<8><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
+    default: return fail(h, CRCL_ENOSUP, "calc_xi: natoms must be 3..8 on the in-register path");
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(xi, dx, ncoord * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(dxi, dd, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (hams) CK(cudaMemcpyAsync(hams, dh, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return CRCL_OK;
+}
+
+// ---- work-unit seam ---------------------------------------------------------------------------
+int crcl_recross_children_dev(crcl_handle h, const double* d_q_parents, int nparent, int pair0, int npairs,
+                              int child_evol, double xi_ideal, double* d_kappa_num, double* d_kappa_denom,
+                              int* d_status)
+{
+    int rc = check_traj_call(h, 2);
+    if (rc) return rc;
+    if (!d_q_parents || !d_kappa_num || !d_kappa_denom || nparent <= 0 || npairs < 0 || child_evol < 0)
+        return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    const int ntraj = 2 * npairs;
+    unsigned char* dth;
+    double* dw;
+    int* dst;
+    if ((rc = scratch(h, 8, (size_t)ntraj * (child_evol > 0 ? child_evol : 1), &dth)) ||
+        (rc = scratch(h, 9, (size_t)ntraj * 2 + 2, &dw)) || (rc = scratch(h, 10, (size_t)ntraj + 1, &dst)))
+        return rc;
+    TrajArgs A;
+    fill_args(h, A);
+    A.ntraj = ntraj;
+    A.nsteps = child_evol;
+    A.constrain = 2;
+    A.thermostat = 0;
+    A.andersen_step = 0;
+    A.xi_ideal_s = xi_ideal;
+    A.k_force_s = 0.0;
+    A.q_parents = d_q_parents;
+    A.nparent = nparent;
+    A.pair0 = pair0;
+    A.theta = dth;
+    A.weight = dw;
+    A.denom_part = dw + ntraj;
+    A.status = d_status ? d_status : dst;
+    if (ntraj > 0 && (rc = launch_traj(h, K_RECROSS, A))) return rc;
+    reduce_kappa_kernel<<<child_evol + 1, 256, 0, h->stream>>>(dth, dw, dw + ntraj, ntraj, child_evol,
+                                                            d_kappa_num, d_kappa_denom);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
+int crcl_recross_children(crcl_handle h, const double* q_parents, int nparent, int pair0, int npairs,
+                          int child_evol, double xi_ideal, double* kappa_num, double* kappa_denom, int* status)
+{
+    if (!h || !q_parents || !kappa_num || !kappa_denom || nparent <= 0 || npairs < 0 || child_evol < 0)
+        return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    const size_t np = (size_t)nparent * h->nbeads * h->natoms * 3;
+    double *dqp, *dk;
+    int* dst;
+    int rc;
+    if ((rc = scratch(h, 0, np, &dqp)) || (rc = scratch(h, 4, (size_t)child_evol + 2, &dk)) ||
+        (rc = scratch(h, 5, (size_t)2 * npairs + 1, &dst)))
+        return rc;
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(dqp, q_parents, np * sizeof(double), cudaMemcpyHostToDevice, s));
+    if ((rc = crcl_recross_children_dev(h, dqp, nparent, pair0, npairs, child_evol, xi_ideal, dk,
+                                        dk + child_evol, dst)))
+        return rc;
+    if (child_evol) CK(cudaMemcpyAsync(kappa_num, dk, child_evol * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(kappa_denom, dk + child_evol, sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (status && npairs) {
+        std::vector<int> st(2 * (size_t)npairs);
+        CK(cudaMemcpyAsync(st.data(), dst, st.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int g = 0; g < npairs; g++) status[g] = st[2 * g] | st[2 * g + 1];
+    }
+    CK(cudaStreamSynchronize(s));
+    return CRCL_OK;
+}
+
+int crcl_umbrella_window(crcl_handle h, const double* q0, double xi0, double k_force, int ntraj,
+                         int equi_steps, int sample_steps, uint32_t traj_id0, double* avg, double* var,
+                         int* status)
+{
+    int rc = check_traj_call(h, 0);
+    if (rc) return rc;
+    if (!q0 || !avg || !var || ntraj < 0 || equi_steps < 0 || sample_steps <= 0) return CRCL_EINVAL;
+    if (ntraj == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    const size_t per = (size_t)h->nbeads * h->natoms * 3, n = per * ntraj, nd = (size_t)ntraj * h->natoms * 3;
+    double *dq, *dp, *dg, *ddxi, *dep, *dnhc;
+    int* dst;
+    uint32_t* dev;
+    if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
+        (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntraj * 4, &dep)) ||
+        (rc = scratch(h, 5, (size_t)ntraj, &dst)) || (rc = scratch(h, 6, (size_t)ntraj * 2, &dev)) ||
+        (rc = scratch(h, 7, (size_t)ntraj * 8, &dnhc)))
+        return rc;
+    cudaStream_t s = h->stream;
+    // every trajectory starts from the window's equilibrated structure (calc_rate.f90:1523-1535)
+    std::vector<double> rep(n);
+    for (int t = 0; t < ntraj; t++) memcpy(rep.data() + t * per, q0, per * sizeof(double));
+    CK(cudaMemcpyAsync(dq, rep.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(dp, 0, n * sizeof(double), s));
+    CK(cudaMemsetAsync(dev, 0, ntraj * 2 * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(dst, 0, ntraj * sizeof(int), s));
+    CK(cudaMemsetAsync(dep, 0, ntraj * 4 * sizeof(double), s));
+    TrajArgs A;
+    fill_args(h, A);
+    A.ntraj = ntraj;
+    A.constrain = 0;
+    A.xi_ideal_s = xi0;
+    A.k_force_s = k_force;
+    A.q = dq;
+    A.p = dp;
+    A.g = dg;
+    A.dxi = ddxi;
+    A.epot = dep;
+    A.xi_real = dep + ntraj;
+    A.status = dst;
+    A.nhc = dnhc;
+    A.traj_id0 = traj_id0;
+    A.event = dev;
+    if ((rc = launch_traj(h, K_MDINIT, A, 2))) return rc;
+    A.nsteps = equi_steps;
+    A.istep0 = 0;
+    if (equi_steps > 0 && (rc = launch_traj(h, K_VERLET, A))) return rc;
+    // calc_rate.f90:1619-1623 recomputes the gradient before sampling: the forces in g are
+    // already those of the current positions, so nothing to do; the step counter restarts.
+    A.nsteps = sample_steps;
+    A.istep0 = 0;
+    A.xi_sum = dep + 2 * ntraj;
+    A.xi_sum2 = dep + 3 * ntraj;
+    if ((rc = launch_traj(h, K_VERLET, A))) return rc;
+    std::vector<double> sums(2 * (size_t)ntraj);
+    CK(cudaMemcpyAsync(sums.data(), dep + 2 * ntraj, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<int> st(ntraj);
+    CK(cudaMemcpyAsync(st.data(), dst, ntraj * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int t = 0; t < ntraj; t++) {
+        // calc_rate.f90:1660-1664: av = sum/n, var = sum2/n - av^2
+        const double a = sums[t] / sample_steps;
+        avg[t] = a;
+        var[t] = sums[ntraj + t] / sample_steps - a * a;
+        if (status) status[t] = st[t];
+    }
+    return CRCL_OK;
+}
+
+// ---- hooks ------------------------------------------------------------------------------------
+int crcl_rng_normals(crcl_handle h, uint64_t seed, uint32_t traj, uint32_t event, uint32_t bead, int n,
+                     double* out)
+{
+    if (!h || !out || n < 0) return CRCL_EINVAL;
+    if (n == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    double* d;
+    int rc;
+    if ((rc = scratch(h, 0, (size_t)n + 1, &d))) return rc;
+    const int pairs = (n + 1) / 2;
+    rng_kernel<<<(pairs + 127) / 128, 128, 0, h->stream>>>(seed, traj, event, bead, n, d);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CRCL_OK;
+}
+
+long long crcl_launch_count(crcl_handle h) { return h ? h->launches : -1; }
+
+double crcl_last_kernel_ms(crcl_handle h)
+{
+    if (!h) return -1.0;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int crcl_kernel_timings(crcl_handle h, double* ms_out, int max_n)
+{
+    if (!h || (!ms_out && max_n > 0)) return CRCL_EINVAL;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return CRCL_ECUDA;
+    const int n = h->ev_count < max_n ? h->ev_count : max_n;
+    // oldest first among the last n launches
+    for (int k = 0; k < n; k++) {
+        const int i = ((h->ev_head - n + k) % crcl_handle_s::NEV + crcl_handle_s::NEV) % crcl_handle_s::NEV;
+        float ms = -1.0f;
+        if (cudaEventElapsedTime(&ms, h->evs[2 * i], h->evs[2 * i + 1]) != cudaSuccess) ms = -1.0f;
+        ms_out[k] = (double)ms;
+    }
+    h->ev_count = 0;
+    return n;
+}
+
+double crcl_measure_fp64_tflops(crcl_handle h, int iters)
+{
+    if (!h) return -1.0;
+    if (iters <= 0) iters = 4096;
+    cudaSetDevice(h->device);
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, h->device) != cudaSuccess) return -1.0;
+    const int tpb = 256, grid = pr.multiProcessorCount * 8;
+    double* d;
+    if (scratch(h, 11, (size_t)grid * tpb, &d)) return -1.0;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(h->ev0, h->stream);
+        fp64_peak_kernel<<<grid, tpb, 0, h->stream>>>(d, iters, 1.0000001, 1e-9);
+        cudaEventRecord(h->ev1, h->stream);
+        h->launches++;
+        if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        const double flops = 2.0 * 8.0 * (double)iters * grid * tpb;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,379 @@
+// pes_ch4h.cuh -- CBE-2009 CH4 + H -> CH3 + H2 surface (Corchado, Bravo, Espinosa-Garcia,
+// J. Chem. Phys. 130, 184314), one thread per image, FP64.
+//
+// Replaces /root/reference/src/egrad_ch4h.f: egrad_ch4h :74-132, POT_ch4h :161-285,
+// coorden :287, refangles :367, stretch :506, opbend :713, ipbend :865, calcdelta :986,
+// opforce :1240, ipforce :1350, switchf :1545, constants :1852-1886 scaled once as
+// PREPOT_ch4h :1781-1793 does.  The POTLIB wrappers in util_ch4h.f are identity maps for the
+// flags Caracal sets (NFLAG(1)=NFLAG(2)=1, ICARTR=1) and have no counterpart here.
+//
+// This is a re-derivation for the GPU, not a transcription.  The reference scatters
+// Cartesian derivatives term by term into pdot(150) through index tables and re-evaluates
+// the same exponentials inside triple loops (~370 libm calls per image).  Here every term
+// is differentiated once with respect to the eleven distances it depends on
+// (rch[4], rbh[4], rcb) plus explicit vector parts for the two angle types, and the chain
+// rule to Cartesians is applied once at the end (~40 libm calls per image).  Results agree
+// with the literal oracle to rounding (tests/test_pes_parity.py).
+//
+// Units as in the reference: bohr -> Angstrom by *0.52918 (:231); energy 1e5 J/mol ->
+// hartree by *0.03812 (:267); gradient by *0.0201723 (:276).  NB 0.03812*0.52918 =
+// 0.02017234..., so the reference's gradient is 2e-6 (relative) inconsistent with its
+// energy; reproduced, not fixed.  No clamps on acos / 1/sqrt(1-x^2) arguments (:939-947,
+// :1088, :1218): collinear/planar arrangements give NaN as in the reference.
+#pragma once
+#include "crcl_common.cuh"
+
+namespace crcl {
+namespace ch4h {
+
+// BLOCK DATA PTPACM_ch4h after PREPOT scaling (fact1 = 0.041840, fact2 = 6.022045)
+constexpr double R0CH = 1.08898, A1CH = 1.78374, B1CH = 0.14201, C1CH = 2.21773;
+constexpr double R0HH = 0.74239, AHH = 1.9589, R0CB = 1.08898, ACB = 1.4173200;
+constexpr double D1CH = 111.266 * 0.041840, D3CH = 48.96226 * 0.041840;
+constexpr double D1HH = 108.382 * 0.041840, D3HH = 38.42657 * 0.041840;
+constexpr double D1CB = 56.505 * 0.041840, D3CB = 19.612 * 0.041840;
+constexpr double A3S = 0.1475300, B3S = -2.9926300;
+constexpr double APHI = 0.5307000, BPHI = 0.4012200, CPHI = 1.9235100;
+constexpr double ATHETA = 0.9119800, BTHETA = 0.3537500, CTHETA = 1.8970500;
+constexpr double FCH3 = 0.0693700 * 6.022045, HCH3 = 0.1387400 * 6.022045;
+constexpr double FKINF = 0.4291400 * 6.022045, AK = 0.1353000 * 6.022045;
+constexpr double AA1 = 1.265960, AA2 = 0.000710, AA3 = 0.985920, AA4 = 2.785060;
+// switchf_ch4h :1598-1601
+constexpr double A1S = 1.5132681e-7, B1S = -4.3792246, A2S = 1.9202402e-7, B2S = -12.323018;
+constexpr double PI = 3.141592653589793;
+
+// Morse-like singlet/triplet pair for one bond: vq, vj and their r- and a-derivatives
+struct Leps {
+    double vq, vj, dvq, dvj;  // d/dr
+};
+CRCL_HD __forceinline__ Leps leps(double d1, double d3, double a, double dr)
+{
+    const double X1 = exp(-a * dr), X2 = X1 * X1;
+    Leps o;
+    o.vq = 0.5 * ((d1 + d3) * X2 - 2.0 * (d1 - d3) * X1);
+    o.vj = 0.5 * ((d1 - d3) * X2 - 2.0 * (d1 + d3) * X1);
+    o.dvq = -a * ((d1 + d3) * X2 - (d1 - d3) * X1);
+    o.dvj = -a * ((d1 - d3) * X2 - (d1 + d3) * X1);
+    return o;
+}
+
+CRCL_HD __forceinline__ void cross(const double a[3], const double b[3], double c[3])
+{
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+CRCL_HD __forceinline__ double dot(const double a[3], const double b[3])
+{
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+
+}  // namespace ch4h
+
+struct PesCH4H {
+    static constexpr int NATOMS = 6;
+    static constexpr int ID = CRCL_PES_CH4H;
+
+    // q, g: [atom][xyz] in bohr / hartree bohr^-1, atom order H, C, H, H, H, H_b
+    // (nnc=2, nnb=6, nnh=3,4,5,1; egrad_ch4h.f:1852-1854)
+    CRCL_HD static __forceinline__ int eval(const double* __restrict__ q, double& V,
+                                               double* __restrict__ g)
+    {
+        using namespace ch4h;
+        constexpr int HA[4] = {2, 3, 4, 0};  // 0-based atom index of methane hydrogen x
+        constexpr int CA = 1, BA = 5;
+        double c[4][3], ubh[4][3], ucb[3];  // unit vectors H-C, H-Hb, Hb-C
+        double rch[4], rbh[4], rcb;
+        {
+            double t[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) t[d] = q[3 * BA + d] * 0.52918 - q[3 * CA + d] * 0.52918;
+            rcb = sqrt(dot(t, t));
+#pragma unroll
+            for (int d = 0; d < 3; d++) ucb[d] = t[d] / rcb;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                double tc[3], tb[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    // the reference converts each coordinate first (q(I)=R(I)*0.52918) and
+                    // differences afterwards; do the same so near-cancelling differences agree
+                    const double h = q[3 * HA[x] + d] * 0.52918;
+                    tc[d] = h - q[3 * CA + d] * 0.52918;
+                    tb[d] = h - q[3 * BA + d] * 0.52918;
+                }
+                rch[x] = sqrt(dot(tc, tc));
+                rbh[x] = sqrt(dot(tb, tb));
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    c[x][d] = tc[d] / rch[x];
+                    ubh[x][d] = tb[d] / rbh[x];
+                }
+            }
+        }
+        // accumulators: dV/d(distance) and explicit vector parts
+        double Dch[4] = {0, 0, 0, 0}, Dbh[4] = {0, 0, 0, 0}, Dcb = 0.0;
+        double gH[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, gC[3] = {0, 0, 0};
+        double en = 0.0;
+
+        // ---- switching functions (switchf_ch4h) ----
+        double s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            const double r = rch[x], dr = r - R0CH;
+            double omt, ms2;
+            {
+                const double u = r - B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
+                const double arg = A1S * dr * u8;
+                if (arg < 19.0) {
+                    one_minus_tanh(arg, omt, ms2);
+                    s1[x] = omt;
+                    ds1[x] = A1S * (u8 + 8.0 * dr * u7) * ms2;
+                } else {
+                    s1[x] = 0.0;
+                    ds1[x] = 0.0;
+                }
+            }
+            {
+                const double u = r - B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
+                const double arg = A2S * dr * u6;
+                if (arg < 19.0) {
+                    one_minus_tanh(arg, omt, ms2);
+                    s2[x] = omt;
+                    ds2[x] = A2S * (u6 + 6.0 * dr * u5) * ms2;
+                } else {
+                    s2[x] = 0.0;
+                    ds2[x] = 0.0;
+                }
+            }
+            {
+                const double u = r - B3S;
+                const double arg = A3S * dr * u * u;
+                if (arg < 19.0) {
+                    one_minus_tanh(arg, omt, ms2);
+                    s3[x] = omt;
+                    ds3[x] = A3S * (3.0 * r * r - 2.0 * r * (R0CH + 2.0 * B3S) + B3S * (B3S + 2.0 * R0CH)) * ms2;
+                } else {
+                    s3[x] = 0.0;
+                    ds3[x] = 0.0;
+                }
+            }
+            if (r < 3.8) {
+                const double u = r - CPHI, ex = exp(BPHI * u * u * u);
+                one_minus_tanh(APHI * dr * ex, omt, ms2);
+                sphi[x] = omt;
+                dsphi[x] = APHI * (1.0 + 3.0 * BPHI * dr * u * u) * ex * ms2;
+                const double v = r - CTHETA, ev = exp(BTHETA * v * v * v);
+                one_minus_tanh(ATHETA * dr * ev, omt, ms2);
+                sth[x] = omt;
+                dsth[x] = ATHETA * (1.0 + 3.0 * BTHETA * dr * v * v) * ev * ms2;
+            } else {
+                sphi[x] = 0.0;
+                dsphi[x] = 0.0;
+                sth[x] = 0.0;
+                dsth[x] = 0.0;
+            }
+        }
+        // reference angles theta0(i,j) = tau + ta (sphi_i sphi_j - 1) + tb (sth_k sth_l - 1)
+        // with {k,l} the complement of {i,j} (refangles_ch4h)
+        const double tau = acos(-1.0 / 3.0);
+        const double ta = tau - 0.5 * PI, tb = tau - 2.0 * PI / 3.0;
+        auto theta0 = [&](int i, int j, int k, int l) {
+            return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
+        };
+
+        // ---- stretching (stretch_ch4h): LEPS for each (C-H_i, C-H_b, H_b-H_i) triple ----
+        {
+            const double rav = (rch[0] + rch[1] + rch[2] + rch[3]) / 4.0;
+            const double arga = C1CH * (rav - R0CH);
+            double ach, dach;  // dach = d ach / d rch_x (same for every x)
+            if (arga < 19.0) {
+                double omt, ms2;
+                one_minus_tanh(arga, omt, ms2);
+                ach = A1CH + B1CH * (2.0 - omt) * 0.5;
+                dach = -B1CH * C1CH * 0.5 * ms2 * 0.25;
+            } else {
+                ach = A1CH + B1CH;
+                dach = 0.0;
+            }
+            const Leps cb = leps(D1CB, D3CB, ACB, rcb - R0CB);
+            double Dach = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double dr = rch[i] - R0CH;
+                const Leps ch = leps(D1CH, D3CH, ach, dr);
+                const Leps bh = leps(D1HH, D3HH, AHH, rbh[i] - R0HH);
+                const double a = ch.vj, b = cb.vj, cc = bh.vj;
+                const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
+                en += ch.vq + cb.vq + bh.vq + vj;
+                const double h = 0.5 / vj;
+                const double wa = (2.0 * a - b - cc) * h, wb = (2.0 * b - a - cc) * h,
+                             wc = (2.0 * cc - a - b) * h;
+                const double dch = ch.dvq + wa * ch.dvj;
+                Dch[i] += dch;
+                Dbh[i] += bh.dvq + wc * bh.dvj;
+                Dcb += cb.dvq + wb * cb.dvj;
+                // d/d(ach): exp(-a dr) depends on a exactly as on r with dr/a swapped
+                Dach += dch * (dr / ach);
+            }
+            const double t = Dach * dach;
+#pragma unroll
+            for (int x = 0; x < 4; x++) Dch[x] += t;
+        }
+
+        // ---- out-of-plane bending (opbend_ch4h, calcdelta_ch4h, opforce_ch4h) ----
+        {
+            const double s3p = s3[0] * s3[1] * s3[2] * s3[3];
+            (void)s3p;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int j = (i + 1) & 3, k = (i + 2) & 3, l = (i + 3) & 3;
+                const double pj = s3[j], pk = s3[k], pl = s3[l];
+                const double sw = (1.0 - s3[i]) * pj * pk * pl;
+                const double fd = sw * FCH3, hd = sw * HCH3;
+                // a = H_k - H_j, b = H_l - H_j (Angstrom), from unit vectors and lengths
+                double a[3], b[3], n[3];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double hj = c[j][d] * rch[j];
+                    a[d] = c[k][d] * rch[k] - hj;
+                    b[d] = c[l][d] * rch[l] - hj;
+                }
+                cross(a, b, n);
+                const double nn = sqrt(dot(n, n));
+                const double inn = 1.0 / nn;
+                double u[3];
+                u[0] = dot(n, c[j]) * inn;
+                u[1] = dot(n, c[k]) * inn;
+                u[2] = dot(n, c[l]) * inn;
+                // right-handedness: each positive argd toggles k<->l (:821-833); an odd count
+                // leaves them swapped, which flips the sign of a x b
+                const int npos = (u[0] > 0.0) + (u[1] > 0.0) + (u[2] > 0.0);
+                const double sg = (npos & 1) ? -1.0 : 1.0;
+                double nh[3] = {sg * n[0] * inn, sg * n[1] * inn, sg * n[2] * inn};
+                const int m3[3] = {j, k, l};
+                // complement pairs of (i,m): for m=j -> (k,l), m=k -> (j,l), m=l -> (j,k)
+                const int ca[3] = {k, j, j}, cb2[3] = {l, l, k};
+                double sum2 = 0.0, sum4 = 0.0;
+                double G[3] = {0, 0, 0};
+#pragma unroll
+                for (int t = 0; t < 3; t++) {
+                    const int m = m3[t];
+                    const double um = sg * u[t];
+                    const double del = acos(um) - theta0(i, m, ca[t], cb2[t]);
+                    const double d2 = del * del;
+                    sum2 += d2;
+                    sum4 += d2 * d2;
+                    const double w = 2.0 * fd * del + 4.0 * hd * d2 * del;
+                    const double wu = -w / sqrt(1.0 - um * um);  // dV/du_m
+                    // u_m = nhat . chat_m : direct part through chat_m
+                    const double f = wu / rch[m];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        const double v = f * (nh[d] - um * c[m][d]);
+                        gH[m][d] += v;
+                        gC[d] -= v;
+                        G[d] += wu * (c[m][d] - um * nh[d]);
+                    }
+                    // through theta0(i,m): -w * dtheta0(i,m,x)
+                    Dch[i] -= w * ta * dsphi[i] * sphi[m];
+                    Dch[m] -= w * ta * sphi[i] * dsphi[m];
+                    Dch[ca[t]] -= w * tb * dsth[ca[t]] * sth[cb2[t]];
+                    Dch[cb2[t]] -= w * tb * sth[ca[t]] * dsth[cb2[t]];
+                }
+                // through nhat: d(n_eff)/dH_k = sg * (b x .), dH_l = sg * (. x a)
+                {
+                    const double s = sg * inn;
+                    double gk[3], gl[3];
+                    cross(b, G, gk);
+                    cross(G, a, gl);
+#pragma unroll
+                    for (int d = 0; d < 3; d++) {
+                        gH[k][d] += s * gk[d];
+                        gH[l][d] += s * gl[d];
+                        gH[j][d] -= s * (gk[d] + gl[d]);
+                    }
+                }
+                en += fd * sum2 + hd * sum4;
+                // force-constant derivatives (opforce_ch4h)
+                const double fs = FCH3 * sum2 + HCH3 * sum4;
+                Dch[i] -= fs * ds3[i] * pj * pk * pl;
+                Dch[j] += fs * (1.0 - s3[i]) * ds3[j] * pk * pl;
+                Dch[k] += fs * (1.0 - s3[i]) * pj * ds3[k] * pl;
+                Dch[l] += fs * (1.0 - s3[i]) * pj * pk * ds3[l];
+            }
+        }
+
+        // ---- in-plane bending (ipbend_ch4h, ipforce_ch4h) ----
+        {
+            constexpr double f0 = FKINF + AK, f2 = FKINF;
+            double f1[4], df1c[4], df1h[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const double dr = rch[x] - R0CH, dh = rbh[x] - R0HH;
+                const double e1 = exp(-AA1 * rbh[x] * rbh[x]);
+                const double e2 = exp(-AA4 * dh * dh);
+                const double a1 = 1.0 - e1;
+                const double a2 = AA2 + AA3 * e2;
+                const double E = exp(-a2 * dr * dr);
+                f1[x] = a1 * E;
+                df1c[x] = -2.0 * dr * a1 * a2 * E;
+                df1h[x] = 2.0 * AA1 * rbh[x] * e1 * E + 2.0 * AA3 * AA4 * dh * e2 * dr * dr * a1 * E;
+            }
+            constexpr int PI_[6] = {0, 0, 0, 1, 1, 2}, PJ_[6] = {1, 2, 3, 2, 3, 3};
+            constexpr int PK_[6] = {2, 1, 1, 0, 0, 0}, PL_[6] = {3, 3, 2, 3, 2, 1};
+#pragma unroll
+            for (int p = 0; p < 6; p++) {
+                const int i = PI_[p], j = PJ_[p], k = PK_[p], l = PL_[p];
+                const double fk0 = f0 + f0 * (s1[i] * s1[j] - 1.0) + (f0 - f2) * (s2[k] * s2[l] - 1.0);
+                const double ff = f1[i] * f1[j];
+                const double K = fk0 * ff;
+                const double cs = dot(c[i], c[j]);
+                const double del = acos(cs) - theta0(i, j, k, l);
+                en += 0.5 * K * del * del;
+                const double w = K * del;                  // dV/d(delta)
+                const double wc = -w / sqrt(1.0 - cs * cs);  // dV/d(cos)
+                const double fi = wc / rch[i], fj = wc / rch[j];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double vi = fi * (c[j][d] - cs * c[i][d]);
+                    const double vj = fj * (c[i][d] - cs * c[j][d]);
+                    gH[i][d] += vi;
+                    gH[j][d] += vj;
+                    gC[d] -= vi + vj;
+                }
+                const double hd2 = 0.5 * del * del;
+                // theta0 and force-constant dependence on rch
+                Dch[i] += -w * ta * dsphi[i] * sphi[j] + hd2 * (f0 * ds1[i] * s1[j] * ff + fk0 * df1c[i] * f1[j]);
+                Dch[j] += -w * ta * sphi[i] * dsphi[j] + hd2 * (f0 * s1[i] * ds1[j] * ff + fk0 * f1[i] * df1c[j]);
+                Dch[k] += -w * tb * dsth[k] * sth[l] + hd2 * (f0 - f2) * ds2[k] * s2[l] * ff;
+                Dch[l] += -w * tb * sth[k] * dsth[l] + hd2 * (f0 - f2) * s2[k] * ds2[l] * ff;
+                Dbh[i] += hd2 * fk0 * df1h[i] * f1[j];
+                Dbh[j] += hd2 * fk0 * f1[i] * df1h[j];
+            }
+        }
+
+        // ---- chain rule to Cartesians, unit conversion ----
+        V = en * 0.03812;
+        constexpr double GF = 0.0201723;
+        double gB[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            double cC = gC[d] - Dcb * ucb[d];
+            double cB = Dcb * ucb[d];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const double vc = Dch[x] * c[x][d], vb = Dbh[x] * ubh[x][d];
+                g[3 * HA[x] + d] = (gH[x][d] + vc + vb) * GF;
+                cC -= vc;
+                cB -= vb;
+            }
+            g[3 * CA + d] = cC * GF;
+            gB[d] = cB * GF;
+            g[3 * BA + d] = gB[d];
+        }
+        return 0;
+    }
+};
+
+}  // namespace crcl

@@ -1,0 +1,6 @@
+// traj_h3_mdinit.cu -- instantiates the mdinit trajectory kernels for the "h3" surface.
+#include "pes_h3.cuh"
+#include "traj_inst.cuh"
+namespace crcl {
+CRCL_DECLARE_TRAJ(launch_h3_mdinit) { return launch_traj_pes<PesH3, K_MDINIT>(nbeads, A, bias_mode, nose_q, s, nosup); }
+}  // namespace crcl

@@ -1,0 +1,776 @@
+// traj_kernel.cuh -- fused ring-polymer trajectory kernels for small analytic systems.
+//
+// One launch advances a whole batch of independent ring polymers by many steps; positions,
+// forces and all per-trajectory scalars stay in registers / shared memory for the whole
+// launch, so HBM traffic per step is zero (state is read once and written once).
+//
+// Replaces, per step, the reference's verlet.f90:65-1308 (operation order: SURVEY.md 3.5)
+// with everything it calls on the graded paths: rfft/irfft (rfft.f90, irfft.f90),
+// get_centroid.f90, gradient.f90 -> egrad_*, umbrella.f90 + calc_xi.f90, constrain_q.f90,
+// constrain_p.f90, nhc.f90, andersen.f90, transrot.f90 + invert.f90; and, for the
+// recrossing work unit, the child-pair body recross.f90:515-628 / recross_serial.f90:172-229.
+//
+// Mapping: one thread per (trajectory, bead).  The NB beads of a trajectory form a
+// "group": a sub-warp segment for NB <= 32 (32/NB trajectories per warp, synchronised with
+// masked __syncwarp / shuffles, so trajectories in the same warp never wait on each other),
+// the whole CTA for NB > 32.
+//
+// Free ring-polymer step (verlet.f90:377-463).  rfft and irfft are the same map
+// T = Re(DFT)/sqrt(N), so the reference applies T.D.T with D the per-mode
+// 2x2 propagator; T.T = (I+J)/2 with J the bead reversal a -> N-a, hence
+//     T.D.T = Circ(f) . (I+J)/2 ,   f(j) = (1/N) sum_k d_k cos(2 pi k j / N),
+// i.e. "symmetrise over a <-> N-a, then apply the exact circulant propagator".  The three
+// kernels f_c (cos wt), f_a (-w sin wt) and f_b (sin wt / w) depend only on (N, beta, dt)
+// and are built once on the host (api.cu); masses enter as p' = Fc p + m Fa q,
+// q' = Fb p / m + Fc q.  CRCL_TRANSFORM_EXACT skips the symmetrisation.
+#pragma once
+#include "crcl_common.cuh"
+#include "rng.cuh"
+#include "xi.cuh"
+
+namespace crcl {
+
+constexpr int TRAJ_MAXNAT = XI_MAXAT;
+
+struct TrajArgs {
+    int ntraj, nsteps, istep0, constrain, thermostat, andersen_step, symmetrize, nbeads;
+    double beta, dt, kelvin;
+    double mass[TRAJ_MAXNAT];
+    int at_move[TRAJ_MAXNAT];
+    Mech mech;
+    // per-trajectory inputs; if the pointer is null the scalar is used for every trajectory
+    const double* xi_ideal;
+    const double* k_force;
+    double xi_ideal_s, k_force_s;
+    // state, reference layout [traj][bead][atom][xyz]
+    double* q;
+    double* p;
+    double* g;
+    double* dxi;      // [traj][atom][xyz] (in/out)
+    double* epot;     // [traj]
+    double* xi_real;  // [traj]
+    int* status;      // [traj]
+    double* nhc;      // [traj][8]: vnh[4], qnh[4]
+    const uint32_t* traj_id;
+    uint32_t traj_id0;
+    uint32_t* event;  // [traj]
+    uint64_t seed;
+    const double* fker;  // [3][NB]
+    // umbrella sampling accumulators (may be null): sum xi, sum xi^2 over the steps of this launch
+    double* xi_sum;
+    double* xi_sum2;
+    // recrossing work unit
+    const double* q_parents;  // [nparent][bead][atom][xyz]
+    int nparent, pair0;
+    unsigned char* theta;  // [nsteps][ntraj]: xi_real > 0 after step l
+    double* weight;        // [ntraj]: v_s/f_s of the child
+    double* denom_part;    // [ntraj]: v_s/f_s if v_s > 0 else 0
+};
+
+template <int NB>
+struct Group {
+    static constexpr bool WARP = (NB <= 32);
+    static constexpr int TPB = WARP ? 32 : NB;   // threads per block
+    static constexpr int GPB = WARP ? 32 / NB : 1;  // groups (trajectories) per block
+    int bead, gib;                               // bead index, group index in block
+    unsigned mask;
+    double* red;  // CTA-wide scratch (NB > 32): [TPB/32]
+
+    __device__ __forceinline__ Group(double* red_)
+    {
+        bead = threadIdx.x % NB;
+        gib = threadIdx.x / NB;
+        if (WARP) {
+            const unsigned m = (NB == 32) ? 0xffffffffu : ((1u << NB) - 1u);
+            mask = m << ((threadIdx.x & 31) / NB * NB);
+        } else {
+            mask = 0xffffffffu;
+        }
+        red = red_;
+    }
+    __device__ __forceinline__ void sync() const
+    {
+        if (WARP)
+            __syncwarp(mask);
+        else
+            __syncthreads();
+    }
+    // all-reduce sum over the beads of the trajectory; every bead gets the same bits
+    __device__ __forceinline__ double sum(double v) const
+    {
+        if (WARP) {
+#pragma unroll
+            for (int o = NB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+            return v;
+        } else {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            double t = 0.0;
+            for (int w = 0; w < NB / 32; w++) t += red[w];
+            return t;
+        }
+    }
+    __device__ __forceinline__ int any(int pred) const
+    {
+        if (WARP)
+            return __any_sync(mask, pred);
+        else
+            return __syncthreads_or(pred);
+    }
+};
+
+// shared-memory footprint (doubles) of one group and of the block-wide part
+template <int NAT, int NB>
+struct SmemLayout {
+    static constexpr int NC = 3 * NAT;
+    static constexpr int PER_GROUP = 2 * NC * NB + 2 * NC;  // {p,q}[c][b] interleaved, cen, dxi
+    static constexpr int BLOCK = (3 * NB + 32 + 1) & ~1;    // fker, reduction scratch (even: double2 alignment)
+    static constexpr size_t bytes() { return sizeof(double) * (BLOCK + Group<NB>::GPB * PER_GROUP); }
+};
+
+// 3x3 inverse by Gauss-Jordan with full pivoting, as invert.f90:38-123; returns 1 if singular
+__device__ __forceinline__ int invert3(double a[3][3])
+{
+    int ipivot[3] = {0, 0, 0}, indxr[3], indxc[3];
+    int irow = 0, icol = 0;
+    for (int i = 0; i < 3; i++) {
+        double big = 0.0;
+        for (int j = 0; j < 3; j++)
+            if (ipivot[j] != 1)
+                for (int k = 0; k < 3; k++) {
+                    if (ipivot[k] == 0) {
+                        if (fabs(a[j][k]) >= big) {
+                            big = fabs(a[j][k]);
+                            irow = j;
+                            icol = k;
+                        }
+                    } else if (ipivot[k] > 1)
+                        return 1;
+                }
+        ipivot[icol]++;
+        if (irow != icol)
+            for (int j = 0; j < 3; j++) {
+                const double t = a[irow][j];
+                a[irow][j] = a[icol][j];
+                a[icol][j] = t;
+            }
+        indxr[i] = irow;
+        indxc[i] = icol;
+        if (a[icol][icol] == 0.0) return 1;
+        const double pivot = a[icol][icol];
+        a[icol][icol] = 1.0;
+        for (int j = 0; j < 3; j++) a[icol][j] /= pivot;
+        for (int j = 0; j < 3; j++)
+            if (j != icol) {
+                const double t = a[j][icol];
+                a[j][icol] = 0.0;
+                for (int k = 0; k < 3; k++) a[j][k] -= a[icol][k] * t;
+            }
+    }
+    for (int i = 2; i >= 0; i--)
+        if (indxr[i] != indxc[i])
+            for (int k = 0; k < 3; k++) {
+                const double t = a[k][indxr[i]];
+                a[k][indxr[i]] = a[k][indxc[i]];
+                a[k][indxc[i]] = t;
+            }
+    return 0;
+}
+
+// Per-thread view of one bead of one trajectory plus the group's shared staging.
+template <class PES, int NB>
+struct Traj {
+    static constexpr int NAT = PES::NATOMS;
+    static constexpr int NC = 3 * NAT;
+    const TrajArgs& A;
+    const Group<NB>& G;
+    double q[NC], g[NC];  // this bead's positions and forces (registers)
+    double2* pq;          // shared {p,q}[c][b] of the trajectory
+    double* cen;          // shared centroid [NC]
+    double* dxi;          // shared dxi [NC]
+    const double* fk;     // shared free-RP kernels [3][NB]
+    double xi_ideal, k_force, xi_real, epot;
+    double vnh[4], qnh[4];
+    int nfree, status;
+    uint32_t tid, event;
+
+    __device__ __forceinline__ Traj(const TrajArgs& a, const Group<NB>& grp, double* smem)
+        : A(a), G(grp)
+    {
+        using L = SmemLayout<NAT, NB>;
+        fk = smem;
+        double* base = smem + L::BLOCK + grp.gib * L::PER_GROUP;
+        pq = reinterpret_cast<double2*>(base);
+        cen = base + 2 * NC * NB;
+        dxi = cen + NC;
+        status = 0;
+        xi_real = 0.0;
+        epot = 0.0;
+        nfree = 0;
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+            if (A.at_move[j]) nfree += 3;
+    }
+    __device__ __forceinline__ double& P(int c) { return pq[c * NB + G.bead].x; }
+
+    // verlet.f90:225-231
+    __device__ __forceinline__ void mask_p()
+    {
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+            if (!A.at_move[j]) {
+                P(3 * j) = 0.0;
+                P(3 * j + 1) = 0.0;
+                P(3 * j + 2) = 0.0;
+            }
+    }
+    // p <- p - dt/2 * g  (verlet.f90:216-218, 1060-1062) followed by the fixed-atom mask
+    __device__ __forceinline__ void half_kick()
+    {
+        const double h = 0.5 * A.dt;
+#pragma unroll
+        for (int c = 0; c < NC; c++) P(c) = P(c) - h * g[c];
+        mask_p();
+    }
+    // centroid of q (get_centroid.f90:67-82), left in shared cen[]; summed in bead order
+    __device__ __forceinline__ void centroid()
+    {
+#pragma unroll
+        for (int c = 0; c < NC; c++) pq[c * NB + G.bead].y = q[c];
+        G.sync();
+        for (int c = G.bead; c < NC; c += NB) {
+            double s = 0.0;
+            for (int b = 0; b < NB; b++) s += pq[c * NB + b].y;
+            cen[c] = s / NB;
+        }
+        G.sync();
+    }
+    // free ring-polymer propagation (verlet.f90:353-357 for one bead, :377-463 otherwise)
+    __device__ __forceinline__ void free_rp()
+    {
+        if (NB == 1) {
+#pragma unroll
+            for (int j = 0; j < NAT; j++)
+#pragma unroll
+                for (int d = 0; d < 3; d++) q[3 * j + d] = q[3 * j + d] + P(3 * j + d) * A.dt / A.mass[j];
+            return;
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) pq[c * NB + G.bead].y = q[c];
+        G.sync();
+        if (A.symmetrize) {
+            // (I+J)/2: x_a <- (x_a + x_{N-a})/2, what T.T does
+            const int rb = (NB - G.bead) & (NB - 1);
+            double2 t[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const double2 u = pq[c * NB + G.bead], w = pq[c * NB + rb];
+                t[c].x = 0.5 * (u.x + w.x);
+                t[c].y = 0.5 * (u.y + w.y);
+            }
+            G.sync();
+#pragma unroll
+            for (int c = 0; c < NC; c++) pq[c * NB + G.bead] = t[c];
+            G.sync();
+        }
+        double pn[NC];
+#pragma unroll
+        for (int j = 0; j < NAT; j++) {
+            const double m = A.mass[j], im = 1.0 / m;
+            double p0 = 0, p1 = 0, p2 = 0, q0 = 0, q1 = 0, q2 = 0;
+#pragma unroll 4
+            for (int b = 0; b < NB; b++) {
+                const int idx = (G.bead - b) & (NB - 1);
+                const double fc = fk[idx], fa = m * fk[NB + idx], fb = im * fk[2 * NB + idx];
+                const double2 u0 = pq[(3 * j) * NB + b], u1 = pq[(3 * j + 1) * NB + b],
+                              u2 = pq[(3 * j + 2) * NB + b];
+                p0 = fma(fc, u0.x, fma(fa, u0.y, p0));
+                q0 = fma(fb, u0.x, fma(fc, u0.y, q0));
+                p1 = fma(fc, u1.x, fma(fa, u1.y, p1));
+                q1 = fma(fb, u1.x, fma(fc, u1.y, q1));
+                p2 = fma(fc, u2.x, fma(fa, u2.y, p2));
+                q2 = fma(fb, u2.x, fma(fc, u2.y, q2));
+            }
+            pn[3 * j] = p0;
+            pn[3 * j + 1] = p1;
+            pn[3 * j + 2] = p2;
+            q[3 * j] = q0;
+            q[3 * j + 1] = q1;
+            q[3 * j + 2] = q2;
+        }
+        G.sync();
+#pragma unroll
+        for (int c = 0; c < NC; c++) P(c) = pn[c];
+    }
+    // gradient.f90 -> egrad_<pes> for this bead; epot = sum over beads (verlet.f90:772-777)
+    __device__ __forceinline__ double forces()
+    {
+        double e;
+        const int w = PES::eval(q, e, g);
+        if (w) status |= CRCL_TRAJ_PESWARN;
+        return G.sum(e);
+    }
+    // umbrella.f90:66-175 on the shared centroid.  mode 0: bias + hams force added to g,
+    // xi in umbrella form; mode 1: xi in recrossing form, nothing added.
+    __device__ __forceinline__ void umbrella(int mode)
+    {
+        double x[NC], d[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) x[c] = cen[c];
+        G.sync();
+        if (mode == 1) {
+            calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 2, xi_real, d, nullptr, A.beta);
+        } else {
+            double h[NC];
+            calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 1, xi_real, d, h, A.beta);
+            const double kd = k_force * (xi_real - xi_ideal);
+#pragma unroll
+            for (int c = 0; c < NC; c++) g[c] = (g[c] + kd * d[c]) + h[c];
+        }
+        if (G.bead == 0) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) dxi[c] = d[c];
+        }
+        G.sync();
+    }
+    // constrain_q.f90:30-112 (SHAKE on the centroid with the previous step's dxi)
+    __device__ __forceinline__ int constrain_q()
+    {
+        double x[NC], d[NC], dn[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            x[c] = cen[c];
+            d[c] = dxi[c];
+        }
+        const double dt = A.dt;
+        double mult = 0.0, coeff = 0.0;
+        int ok = 0;
+        for (int iter = 1; iter <= 200; iter++) {
+            coeff = mult * dt * dt / NB;
+            double xt[NC], xin;
+#pragma unroll
+            for (int j = 0; j < NAT; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) xt[3 * j + k] = x[3 * j + k] + coeff * d[3 * j + k] / A.mass[j];
+            calc_xi<NAT>(A.mech, A.mass, xt, xi_ideal, 2, xin, dn, nullptr, A.beta);
+            double dsigma = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int j = 0; j < NAT; j++)
+                    dsigma += dn[3 * j + k] * dt * dt * d[3 * j + k] / (A.mass[j] * NB);
+            const double dx = xin / dsigma;
+            mult -= dx;
+            // 1.0E-8 / 1.0E-10 are REAL*4 literals in constrain_q.f90:93
+            if (fabs(dx) < FL(1.0E-8) || fabs(xin) < FL(1.0E-10)) {
+                ok = 1;
+                break;
+            }
+        }
+        if (!ok) return 1;
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int c = 3 * j + k;
+                q[c] = q[c] + coeff / A.mass[j] * d[c];
+                P(c) = P(c) + mult * dt / NB * d[c];
+            }
+        return 0;
+    }
+    // constrain_p.f90:30-75 (RATTLE)
+    __device__ __forceinline__ void constrain_p()
+    {
+        double c1 = 0.0, c2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int c = 3 * j + k;
+                c1 += dxi[c] * P(c) / A.mass[j];
+                c2 += dxi[c] * dxi[c] / A.mass[j];
+            }
+        c1 = G.sum(c1);
+        const double lam = -c1 / c2 / NB;
+#pragma unroll
+        for (int c = 0; c < NC; c++) P(c) = P(c) + lam * dxi[c];
+    }
+    // andersen.f90:36-74: full resample p = N(0,1) sqrt(m/beta_n)
+    __device__ __forceinline__ void andersen()
+    {
+        const double beta_n = A.beta / NB;
+#pragma unroll
+        for (int m = 0; m < NC; m += 2) {
+            double z0, z1;
+            normal_pair(A.seed, tid, event, (uint32_t)G.bead, (uint32_t)(m >> 1), z0, z1);
+            P(m) = z0 * sqrt(A.mass[m / 3] / beta_n);
+            if (m + 1 < NC) P(m + 1) = z1 * sqrt(A.mass[(m + 1) / 3] / beta_n);
+        }
+        event++;
+    }
+    // nhc.f90:34-170
+    __device__ __forceinline__ void nhc()
+    {
+        constexpr float ektf = 1.380649E-23f / 4.3597447E-18f;  // REAL*4 division, nhc.f90:51
+        const double ekt = (double)ektf * A.kelvin;
+        const double dtc = A.dt / 5.0;
+        double w[3];
+        w[0] = 1.0 / (2.0 - cbrt(2.0));
+        w[1] = 1.0 - 2.0 * w[0];
+        w[2] = w[0];
+        double ek = 0.0;
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+            if (A.at_move[j]) {
+                const double d = P(3 * j) * P(3 * j) + P(3 * j + 1) * P(3 * j + 1) + P(3 * j + 2) * P(3 * j + 2);
+                ek += d / (2.0 * A.mass[j]) / NB / NB;
+            }
+        double eksum = G.sum(ek);
+        double scale = 1.0, gn;
+        const double nf = (double)nfree;
+        for (int i = 0; i < 5; i++)
+            for (int j = 0; j < 3; j++) {
+                const double dts = w[j] * dtc, dt2 = 0.5 * dts, dt4 = 0.25 * dts, dt8 = 0.125 * dts;
+                double ex;
+                gn = (qnh[2] * vnh[2] * vnh[2] - ekt) / qnh[3];
+                vnh[3] = vnh[3] + gn * dt4;
+                gn = (qnh[1] * vnh[1] * vnh[1] - ekt) / qnh[2];
+                ex = exp(-vnh[3] * dt8);
+                vnh[2] = ex * (vnh[2] * ex + gn * dt4);
+                gn = (qnh[0] * vnh[0] * vnh[0] - ekt) / qnh[1];
+                ex = exp(-vnh[2] * dt8);
+                vnh[1] = ex * (vnh[1] * ex + gn * dt4);
+                gn = (2.0 * eksum - nf * ekt) / qnh[0];
+                ex = exp(-vnh[1] * dt8);
+                vnh[0] = ex * (vnh[0] * ex + gn * dt4);
+                ex = exp(-vnh[0] * dt2);
+                scale = scale * ex;
+                eksum = eksum * ex * ex;
+                gn = (2.0 * eksum - nf * ekt) / qnh[0];
+                ex = exp(-vnh[1] * dt8);
+                vnh[0] = ex * (vnh[0] * ex + gn * dt4);
+                gn = (qnh[0] * vnh[0] * vnh[0] - ekt) / qnh[1];
+                ex = exp(-vnh[2] * dt8);
+                vnh[1] = ex * (vnh[1] * ex + gn * dt4);
+                gn = (qnh[1] * vnh[1] * vnh[1] - ekt) / qnh[2];
+                ex = exp(-vnh[3] * dt8);
+                vnh[2] = ex * (vnh[2] * ex + gn * dt4);
+                gn = (qnh[2] * vnh[2] * vnh[2] - ekt) / qnh[3];
+                vnh[3] = vnh[3] + gn * dt4;
+            }
+#pragma unroll
+        for (int j = 0; j < NAT; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) P(3 * j + k) = A.at_move[j] ? scale * P(3 * j + k) : 0.0;
+    }
+    // NHC masses and zeroed chain (mdinit.f90:126-146)
+    __device__ __forceinline__ void nhc_init(double nose_q)
+    {
+        const double ekt = 0.316679e-5 * A.kelvin;
+        const double qterm = ekt * nose_q * nose_q;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            qnh[j] = qterm;
+            vnh[j] = 0.0;
+        }
+        qnh[0] = (double)nfree * qnh[0];
+    }
+    // transrot.f90:36-236, including the totmass*nbeads double count
+    __device__ __forceinline__ int transrot()
+    {
+        double s[15];
+#pragma unroll
+        for (int i = 0; i < 15; i++) s[i] = 0.0;
+        double mt = 0.0;
+        double v[NC];
+#pragma unroll
+        for (int j = 0; j < NAT; j++) {
+            const double w = A.mass[j];
+            mt += w;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                v[3 * j + d] = P(3 * j + d) / w;
+                s[d] += v[3 * j + d] * w;
+                s[3 + d] += q[3 * j + d] * w;
+            }
+            s[6] += (q[3 * j + 1] * v[3 * j + 2] - q[3 * j + 2] * v[3 * j + 1]) * w;
+            s[7] += (q[3 * j + 2] * v[3 * j + 0] - q[3 * j + 0] * v[3 * j + 2]) * w;
+            s[8] += (q[3 * j + 0] * v[3 * j + 1] - q[3 * j + 1] * v[3 * j + 0]) * w;
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) s[i] = G.sum(s[i]);
+        const double totmass = (mt * NB) * NB;
+        double vtot[3], ctr[3], mang[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            vtot[d] = s[d] / totmass;
+            ctr[d] = s[3 + d] / totmass;
+        }
+        mang[0] = s[6] - (ctr[1] * vtot[2] - ctr[2] * vtot[1]) * totmass;
+        mang[1] = s[7] - (ctr[2] * vtot[0] - ctr[0] * vtot[2]) * totmass;
+        mang[2] = s[8] - (ctr[0] * vtot[1] - ctr[1] * vtot[0]) * totmass;
+        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+#pragma unroll
+        for (int j = 0; j < NAT; j++) {
+            const double w = A.mass[j];
+            const double xd = q[3 * j] - ctr[0], yd = q[3 * j + 1] - ctr[1], zd = q[3 * j + 2] - ctr[2];
+            xx += xd * xd * w;
+            xy += xd * yd * w;
+            xz += xd * zd * w;
+            yy += yd * yd * w;
+            yz += yd * zd * w;
+            zz += zd * zd * w;
+        }
+        xx = G.sum(xx);
+        xy = G.sum(xy);
+        xz = G.sum(xz);
+        yy = G.sum(yy);
+        yz = G.sum(yz);
+        zz = G.sum(zz);
+        double t[3][3] = {{yy + zz, -xy, -xz}, {-xy, xx + zz, -yz}, {-xz, -yz, xx + yy}};
+        if (NAT <= 2) {
+            t[0][0] += 0.000001;
+            t[1][1] += 0.000001;
+            t[2][2] += 0.000001;
+        }
+        if (invert3(t)) return 1;
+        double vang[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
+#pragma unroll
+        for (int j = 0; j < NAT; j++) {
+            const double xd = q[3 * j] - ctr[0], yd = q[3 * j + 1] - ctr[1], zd = q[3 * j + 2] - ctr[2];
+            const double v0 = (v[3 * j] - vtot[0]) - vang[1] * zd + vang[2] * yd;
+            const double v1 = (v[3 * j + 1] - vtot[1]) - vang[2] * xd + vang[0] * zd;
+            const double v2 = (v[3 * j + 2] - vtot[2]) - vang[0] * yd + vang[1] * xd;
+            P(3 * j) = v0 * A.mass[j];
+            P(3 * j + 1) = v1 * A.mass[j];
+            P(3 * j + 2) = v2 * A.mass[j];
+        }
+        mask_p();
+        return 0;
+    }
+
+    // one verlet step (SURVEY.md 3.5 numbering)
+    __device__ __forceinline__ void step(int istep)
+    {
+        const int c = A.constrain, th = A.thermostat;
+        if (c != 2 && th == 2) nhc();                          // 1
+        half_kick();                                           // 2,3
+        free_rp();                                             // 4
+        centroid();                                            // 6
+        mask_p();                                              // 7
+        int bad = 0;
+        if (c == 1) bad = constrain_q();                       // 9
+        epot = forces();                                       // 10
+        if (bad) {
+            epot += 100000.0;
+            status |= CRCL_TRAJ_SHAKE_FAIL;
+        }
+        if (c == 0 || c == 3)                                  // 12
+            umbrella(0);
+        else if (c == 1 || c == 2)
+            umbrella(1);
+        half_kick();                                           // 13
+        if (c == 1) constrain_p();                             // 14
+        if (c != 2 && th == 2) nhc();                          // 15
+        if (c != 2 && th == 1 && A.andersen_step > 0 && (istep % A.andersen_step) == 0)
+            andersen();                                        // 16
+        int nan = 0;                                           // 18
+#pragma unroll
+        for (int k = 0; k < NC; k++) nan |= (q[k] != q[k]) || (q[k] > 1.79769313486231570815e308);
+        if (G.any(nan)) status |= CRCL_TRAJ_NAN;
+        if (c <= 0)                                            // 19
+            if (transrot()) status |= CRCL_TRAJ_SINGULAR;
+    }
+};
+
+template <int NB>
+__device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
+{
+    for (int i = threadIdx.x; i < 3 * NB; i += blockDim.x) smem[i] = A.fker[i];
+    __syncthreads();
+}
+
+// ---- generic batched verlet: state in HBM in, nsteps steps, state out --------------------
+template <class PES, int NB>
+__global__ void __launch_bounds__(Group<NB>::TPB)
+verlet_kernel(const __grid_constant__ TrajArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NC = 3 * PES::NATOMS;
+    using L = SmemLayout<PES::NATOMS, NB>;
+    load_fker<NB>(A, smem);
+    Group<NB> G(smem + 3 * NB);
+    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    if (traj >= A.ntraj) return;
+    Traj<PES, NB> T(A, G, smem);
+    const size_t off = ((size_t)traj * NB + G.bead) * NC;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        T.q[c] = A.q[off + c];
+        T.g[c] = A.g[off + c];
+        T.P(c) = A.p[off + c];
+    }
+    T.xi_ideal = A.xi_ideal ? A.xi_ideal[traj] : A.xi_ideal_s;
+    T.k_force = A.k_force ? A.k_force[traj] : A.k_force_s;
+    T.tid = A.traj_id ? A.traj_id[traj] : A.traj_id0 + (uint32_t)traj;
+    T.event = A.event ? A.event[traj] : 0u;
+    if (A.dxi) {
+        for (int c = G.bead; c < NC; c += NB) T.dxi[c] = A.dxi[(size_t)traj * NC + c];
+    }
+    if (A.nhc) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            T.vnh[i] = A.nhc[(size_t)traj * 8 + i];
+            T.qnh[i] = A.nhc[(size_t)traj * 8 + 4 + i];
+        }
+    }
+    T.status = A.status ? A.status[traj] : 0;
+    G.sync();
+    double sx = 0.0, sx2 = 0.0;
+    for (int s = 1; s <= A.nsteps; s++) {
+        // a failed trajectory is frozen (the reference aborts or restarts it)
+        if (T.status & (CRCL_TRAJ_SHAKE_FAIL | CRCL_TRAJ_NAN | CRCL_TRAJ_SINGULAR)) break;
+        T.step(A.istep0 + s);
+        sx += T.xi_real;
+        sx2 += T.xi_real * T.xi_real;
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        A.q[off + c] = T.q[c];
+        A.g[off + c] = T.g[c];
+        A.p[off + c] = T.P(c);
+    }
+    if (A.dxi)
+        for (int c = G.bead; c < NC; c += NB) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
+    if (G.bead == 0) {
+        if (A.epot) A.epot[traj] = T.epot;
+        if (A.xi_real) A.xi_real[traj] = T.xi_real;
+        if (A.status) A.status[traj] = T.status;
+        if (A.event) A.event[traj] = T.event;
+        if (A.xi_sum) A.xi_sum[traj] += sx;
+        if (A.xi_sum2) A.xi_sum2[traj] += sx2;
+        if (A.nhc) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                A.nhc[(size_t)traj * 8 + i] = T.vnh[i];
+                A.nhc[(size_t)traj * 8 + 4 + i] = T.qnh[i];
+            }
+        }
+    }
+}
+
+// ---- mdinit (mdinit.f90:40-172) -------------------------------------------------------------
+// bias_mode: 0 no umbrella call, 1 xi only (umbrella mode 1), 2 bias applied (umbrella mode 0).
+template <class PES, int NB>
+__global__ void __launch_bounds__(Group<NB>::TPB)
+mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const double nose_q)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NC = 3 * PES::NATOMS;
+    load_fker<NB>(A, smem);
+    Group<NB> G(smem + 3 * NB);
+    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    if (traj >= A.ntraj) return;
+    Traj<PES, NB> T(A, G, smem);
+    const size_t off = ((size_t)traj * NB + G.bead) * NC;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        T.q[c] = A.q[off + c];
+        T.P(c) = A.p[off + c];
+    }
+    T.xi_ideal = A.xi_ideal ? A.xi_ideal[traj] : A.xi_ideal_s;
+    T.k_force = A.k_force ? A.k_force[traj] : A.k_force_s;
+    T.tid = A.traj_id ? A.traj_id[traj] : A.traj_id0 + (uint32_t)traj;
+    T.event = A.event ? A.event[traj] : 0u;
+    G.sync();
+    T.epot = T.forces();
+    T.centroid();
+    if (bias_mode == 1)
+        T.umbrella(1);
+    else if (bias_mode == 2)
+        T.umbrella(0);
+    if (A.thermostat == 0 || A.thermostat == 1) T.andersen();
+    if (A.thermostat == 2) {
+        T.andersen();
+        T.nhc_init(nose_q);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        A.g[off + c] = T.g[c];
+        A.p[off + c] = T.P(c);
+    }
+    if (A.dxi && bias_mode != 0)
+        for (int c = G.bead; c < NC; c += NB) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
+    if (G.bead == 0) {
+        if (A.event) A.event[traj] = T.event;
+        if (A.nhc && A.thermostat == 2) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                A.nhc[(size_t)traj * 8 + i] = T.vnh[i];
+                A.nhc[(size_t)traj * 8 + 4 + i] = T.qnh[i];
+            }
+        }
+    }
+}
+
+// ---- recrossing child trajectories (recross.f90:515-628 / recross_serial.f90:172-229) ------
+// trajectory t = 2*g + k is child k (0: +p, 1: -p) of pair pair0+g.  Both children of a pair
+// draw the same momenta (RNG stream keyed by the pair index).  Writes weight = v_s/f_s,
+// denom_part and, per step, theta = [xi_real > 0]; kappa sums are formed by reduce_kappa.
+template <class PES, int NB>
+__global__ void __launch_bounds__(Group<NB>::TPB)
+recross_kernel(const __grid_constant__ TrajArgs A)
+{
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NAT = PES::NATOMS, NC = 3 * NAT;
+    load_fker<NB>(A, smem);
+    Group<NB> G(smem + 3 * NB);
+    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    if (traj >= A.ntraj) return;
+    Traj<PES, NB> T(A, G, smem);
+    const int pair = A.pair0 + (traj >> 1);
+    const int sign = (traj & 1) ? -1 : 1;
+    const size_t poff = ((size_t)(pair % A.nparent) * NB + G.bead) * NC;
+#pragma unroll
+    for (int c = 0; c < NC; c++) T.q[c] = A.q_parents[poff + c];
+    T.xi_ideal = A.xi_ideal_s;
+    T.k_force = 0.0;
+    T.tid = (uint32_t)pair;
+    T.event = 0u;
+    T.andersen();
+    if (sign < 0) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) T.P(c) = -T.P(c);
+    }
+    T.centroid();
+    T.umbrella(1);  // calc_xi(mode 2) on the centroid -> dxi (recross_serial.f90:186-187)
+    T.epot = T.forces();
+    double vs = 0.0, fs = 0.0;
+#pragma unroll
+    for (int j = 0; j < NAT; j++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int c = 3 * j + d;
+            vs += T.dxi[c] * T.P(c) / A.mass[j];
+            fs += T.dxi[c] * T.dxi[c] / A.mass[j];
+        }
+    vs = G.sum(vs) / NB;
+    fs = sqrt(fs / (2.0 * PI_UMBR * A.beta));
+    const double w = vs / fs;
+    if (G.bead == 0) {
+        A.weight[traj] = w;
+        A.denom_part[traj] = (vs > 0) ? w : 0.0;
+    }
+    for (int l = 1; l <= A.nsteps; l++) {
+        if (!(T.status & CRCL_TRAJ_NAN)) T.step(l);
+        if (G.bead == 0) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
+    }
+    if (G.bead == 0 && A.status) A.status[traj] = T.status;
+}
+
+}  // namespace crcl

@@ -1,0 +1,260 @@
+// xi.cuh -- reaction coordinate of the BIMOLEC mechanism family on one structure
+// (the ring-polymer centroid), its gradient, and the umbrella "hams" force.
+//
+// Replaces calc_xi.f90:108-502 (+ calc_com.f90:36-58) and the contraction of
+// umbrella.f90:144-174.  The reference assembles the dense (3N)^2 Hessians d2s0/d2s1 on
+// every call, including the calls that discard them (modes used by SHAKE and by child
+// trajectories), and umbrella contracts d2xi with dxi/m in O((3N)^2).  Here the Hessian is
+// never formed: each bond / fragment-pair block is (+-)(r^2 I - r r^T)/r^3, so the
+// contraction H.v collapses to one 3-vector per bond and per fragment pair, O(N).
+#pragma once
+#include "crcl_common.cuh"
+
+namespace crcl {
+
+constexpr int XI_MAXBOND = 4;
+constexpr int XI_MAXREAC = 4;
+constexpr int XI_MAXAT = 8;  // in-register path; larger systems use the split path
+
+struct Mech {
+    int form_num, break_num;
+    int bf[XI_MAXBOND][2], bb[XI_MAXBOND][2];  // 0-based
+    double fref[XI_MAXBOND], bref[XI_MAXBOND];
+    int sum_reacs;
+    int frag[XI_MAXAT];  // fragment of each atom, -1 = none
+    double mass_reac[XI_MAXREAC];
+    double R_inf;
+    int valid;
+};
+
+// Host-side construction from the MECHA{} tables (1-based atom indices as in the key file,
+// calc_rate_read.f90:430-870).  Returns 0, or a negative code: -1 limits exceeded, -2 bad index.
+inline int build_mech(Mech& M, int natoms, const double* mass, int form_num, const int* bond_form,
+                      int break_num, const int* bond_break, const double* form_ref,
+                      const double* break_ref, int sum_reacs, const int* n_reac, const int* at_reac,
+                      double R_inf)
+{
+    if (form_num < 0 || break_num < 0 || form_num > XI_MAXBOND || break_num > XI_MAXBOND ||
+        sum_reacs < 2 || sum_reacs > XI_MAXREAC || natoms > XI_MAXAT)
+        return -1;
+    M = Mech();
+    M.form_num = form_num;
+    M.break_num = break_num;
+    for (int i = 0; i < form_num; i++) {
+        M.bf[i][0] = bond_form[2 * i] - 1;
+        M.bf[i][1] = bond_form[2 * i + 1] - 1;
+        M.fref[i] = form_ref[i];
+        if (M.bf[i][0] < 0 || M.bf[i][0] >= natoms || M.bf[i][1] < 0 || M.bf[i][1] >= natoms) return -2;
+    }
+    for (int i = 0; i < break_num; i++) {
+        M.bb[i][0] = bond_break[2 * i] - 1;
+        M.bb[i][1] = bond_break[2 * i + 1] - 1;
+        M.bref[i] = break_ref[i];
+        if (M.bb[i][0] < 0 || M.bb[i][0] >= natoms || M.bb[i][1] < 0 || M.bb[i][1] >= natoms) return -2;
+    }
+    M.sum_reacs = sum_reacs;
+    for (int a = 0; a < XI_MAXAT; a++) M.frag[a] = -1;
+    int off = 0;
+    for (int k = 0; k < sum_reacs; k++) {
+        M.mass_reac[k] = 0.0;
+        for (int i = 0; i < n_reac[k]; i++) {
+            const int a = at_reac[off + i] - 1;
+            if (a < 0 || a >= natoms) return -2;
+            M.frag[a] = k;
+            M.mass_reac[k] += mass[a];  // calc_rate_read.f90: fragment mass = sum of its atoms
+        }
+        off += n_reac[k];
+    }
+    M.R_inf = R_inf;
+    M.valid = 1;
+    return 0;
+}
+
+// M w with M = (r^2 I - r r^T)/r^3
+CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w[3], double o[3])
+{
+    const double r3 = rinv * rinv * rinv;
+    const double rr = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double rw = r[0] * w[0] + r[1] * w[1] + r[2] * w[2];
+#pragma unroll
+    for (int d = 0; d < 3; d++) o[d] = (rr * w[d] - r[d] * rw) * r3;
+}
+
+// mode 1: xi = s0/(s0-s1) (umbrella form); mode 2: xi = xi_ideal*s1 + (1-xi_ideal)*s0.
+// x, dxi: [atom][xyz].  If hams != nullptr (mode 1 only) it receives the force of
+// umbrella.f90:144-174, -(1/beta) d/dx log f_s with f_s^2 = sum (dxi)^2/m / (2 pi beta).
+template <int NAT>
+CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const double* x,
+                                     double xi_ideal, int mode, double& xi, double* dxi,
+                                     double* hams, double beta)
+{
+    double ds0[3 * NAT], ds1[3 * NAT];
+#pragma unroll
+    for (int t = 0; t < 3 * NAT; t++) {
+        ds0[t] = 0.0;
+        ds1[t] = 0.0;
+    }
+    double Rf[XI_MAXBOND][3], Rb[XI_MAXBOND][3], fi[XI_MAXBOND], bi[XI_MAXBOND];
+    double s1 = 0.0;
+    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+    for (int i = 0; i < M.break_num; i++) {
+        const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+#pragma unroll
+        for (int d = 0; d < 3; d++) Rb[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
+        const double r = sqrt(Rb[i][0] * Rb[i][0] + Rb[i][1] * Rb[i][1] + Rb[i][2] * Rb[i][2]);
+        bi[i] = 1.0 / r;
+        s1 += (r - M.bref[i]) / bnum;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double v = Rb[i][d] * bi[i] / bnum;
+            ds1[3 * a1 + d] += v;
+            ds1[3 * a2 + d] -= v;
+        }
+    }
+    for (int i = 0; i < M.form_num; i++) {
+        const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+#pragma unroll
+        for (int d = 0; d < 3; d++) Rf[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
+        const double r = sqrt(Rf[i][0] * Rf[i][0] + Rf[i][1] * Rf[i][1] + Rf[i][2] * Rf[i][2]);
+        fi[i] = 1.0 / r;
+        s1 -= (r - M.fref[i]) / fnum;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double v = Rf[i][d] * fi[i] / fnum;
+            ds1[3 * a1 + d] -= v;
+            ds1[3 * a2 + d] += v;
+        }
+    }
+    // centres of mass of the reactant fragments (calc_com.f90)
+    double com[XI_MAXREAC][3];
+#pragma unroll
+    for (int k = 0; k < XI_MAXREAC; k++) com[k][0] = com[k][1] = com[k][2] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NAT; a++) {
+        const int k = M.frag[a];
+        if (k >= 0) {
+            const double w = mass[a];
+#pragma unroll
+            for (int d = 0; d < 3; d++) com[k][d] += w * x[3 * a + d] / M.mass_reac[k];
+        }
+    }
+    const int nterms = (M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2;
+    const double fterms = (double)nterms;
+    double s0 = 0.0;
+    double Red[XI_MAXREAC * (XI_MAXREAC - 1) / 2][3], ri[XI_MAXREAC * (XI_MAXREAC - 1) / 2];
+    int np = 0;
+    for (int i = 0; i < M.sum_reacs; i++)
+        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) Red[np][d] = com[j][d] - com[i][d];
+            const double r =
+                sqrt(Red[np][0] * Red[np][0] + Red[np][1] * Red[np][1] + Red[np][2] * Red[np][2]);
+            ri[np] = 1.0 / r;
+            s0 += M.R_inf - r;
+#pragma unroll
+            for (int a = 0; a < NAT; a++) {
+                const int k = M.frag[a];
+                if (k == i || k == j) {
+                    const double sg = (k == i) ? 1.0 : -1.0;
+                    const double w = sg * ri[np] * mass[a] / M.mass_reac[k] / fterms;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) ds0[3 * a + d] += Red[np][d] * w;
+                }
+            }
+        }
+    s0 = s0 / fterms;
+
+    if (mode == 1) {
+        const double D = s0 - s1;
+        xi = s0 / D;
+        const double iD2 = 1.0 / (D * D);
+#pragma unroll
+        for (int t = 0; t < 3 * NAT; t++) dxi[t] = (s0 * ds1[t] - s1 * ds0[t]) * iD2;
+    } else {
+        xi = xi_ideal * s1 + (1 - xi_ideal) * s0;
+#pragma unroll
+        for (int t = 0; t < 3 * NAT; t++) dxi[t] = xi_ideal * ds1[t] + (1 - xi_ideal) * ds0[t];
+    }
+    if (!hams) return;
+
+    // ---- hams[b] = coeff2/(coeff1 fs2) * sum_a d2xi(a,b) v_a,  v_a = dxi_a / m_a ----
+    double v[3 * NAT], H1v[3 * NAT], H0v[3 * NAT];
+    double fs2 = 0.0, d1v = 0.0, d0v = 0.0;
+#pragma unroll
+    for (int a = 0; a < NAT; a++)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const int t = 3 * a + d;
+            v[t] = dxi[t] / mass[a];
+            fs2 += dxi[t] * v[t];
+            d1v += ds1[t] * v[t];
+            d0v += ds0[t] * v[t];
+            H1v[t] = 0.0;
+            H0v[t] = 0.0;
+        }
+    for (int i = 0; i < M.form_num; i++) {  // forming bonds: block = -(r^2 I - r r^T)/r^3
+        const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+        double w[3], o[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) w[d] = v[3 * a1 + d] - v[3 * a2 + d];
+        proj(Rf[i], fi[i], w, o);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            H1v[3 * a1 + d] -= o[d] / fnum;
+            H1v[3 * a2 + d] += o[d] / fnum;
+        }
+    }
+    for (int i = 0; i < M.break_num; i++) {  // breaking bonds: block = +(r^2 I - r r^T)/r^3
+        const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+        double w[3], o[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) w[d] = v[3 * a1 + d] - v[3 * a2 + d];
+        proj(Rb[i], bi[i], w, o);
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            H1v[3 * a1 + d] += o[d] / bnum;
+            H1v[3 * a2 + d] -= o[d] / bnum;
+        }
+    }
+    np = 0;
+    for (int i = 0; i < M.sum_reacs; i++)
+        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+            double W[3] = {0, 0, 0}, o[3];
+#pragma unroll
+            for (int a = 0; a < NAT; a++) {
+                const int k = M.frag[a];
+                if (k == i || k == j) {
+                    const double sg = (k == i) ? 1.0 : -1.0;
+                    const double w = sg * mass[a] / M.mass_reac[k];
+#pragma unroll
+                    for (int d = 0; d < 3; d++) W[d] += w * v[3 * a + d];
+                }
+            }
+            proj(Red[np], ri[np], W, o);
+#pragma unroll
+            for (int a = 0; a < NAT; a++) {
+                const int k = M.frag[a];
+                if (k == i || k == j) {
+                    const double sg = (k == i) ? 1.0 : -1.0;
+                    const double w = -sg * mass[a] / M.mass_reac[k] / fterms;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) H0v[3 * a + d] += w * o[d];
+                }
+            }
+        }
+    const double coeff1 = 2.0 * PI_UMBR * beta;
+    fs2 = fs2 / coeff1;
+    const double pref = (-1.0 / beta) / (coeff1 * fs2);
+    const double D = s0 - s1;
+    const double iD3 = 1.0 / (D * D * D);
+    const double cross2 = 2.0 * (s0 * d1v - s1 * d0v);
+#pragma unroll
+    for (int t = 0; t < 3 * NAT; t++) {
+        const double h = ((s0 * H1v[t] + ds0[t] * d1v - ds1[t] * d0v - s1 * H0v[t]) * D -
+                          cross2 * (ds0[t] - ds1[t])) *
+                         iD3;
+        hams[t] = h * pref;
+    }
+}
+
+}  // namespace crcl

@@ -1,0 +1,97 @@
+"""ctypes loader for libcaracal_gpu.so (the C-ABI in include/caracal_gpu.h).
+
+There is no fallback: if the library is missing or no CUDA device is present the calls fail
+loudly.  Nothing under oracle/ is ever imported from here.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcaracal_gpu.so")
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_u32_p = ctypes.POINTER(ctypes.c_uint32)
+
+PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_HOSTCB = 0, 1, 2, 3, 100
+PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H}
+PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6}
+TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
+ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM", -4: "CRCL_ECUDA",
+          -5: "CRCL_ENOSUP", -6: "CRCL_ESTATE"}
+TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_PESWARN = 0, 1, 2, 5, 16
+
+# every symbol include/caracal_gpu.h declares: (restype, argtypes)
+_H = ctypes.c_void_p
+SIGNATURES = {
+    "crcl_create": (ctypes.c_int, [ctypes.POINTER(_H), ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p,
+                                   c_int_p, ctypes.c_double, ctypes.c_double, ctypes.c_int]),
+    "crcl_destroy": (ctypes.c_int, [_H]),
+    "crcl_last_error": (ctypes.c_char_p, [_H]),
+    "crcl_set_stream": (ctypes.c_int, [_H, ctypes.c_void_p]),
+    "crcl_synchronize": (ctypes.c_int, [_H]),
+    "crcl_set_beta_dt": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double]),
+    "crcl_set_transform": (ctypes.c_int, [_H, ctypes.c_int]),
+    "crcl_set_host_gradient_cb": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
+                                          ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),
+    "crcl_set_thermostat": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
+    "crcl_set_seed": (ctypes.c_int, [_H, ctypes.c_uint64]),
+    "crcl_egrad": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+                                  c_int_p]),
+    "crcl_egrad_dev": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
+    "crcl_verlet": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
+                                   c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p,
+                                   c_u32_p, c_u32_p]),
+    "crcl_mdinit": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
+                                   c_double_p, c_double_p, c_u32_p, c_u32_p]),
+    "crcl_calc_xi": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, c_double_p, c_double_p,
+                                    c_double_p]),
+    "crcl_recross_children": (ctypes.c_int, [_H, c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_double, c_double_p, c_double_p, c_int_p]),
+    "crcl_recross_children_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                 ctypes.c_void_p]),
+    "crcl_umbrella_window": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_uint32, c_double_p, c_double_p,
+                                            c_int_p]),
+    "crcl_rng_normals": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                        ctypes.c_int, c_double_p]),
+    "crcl_launch_count": (ctypes.c_longlong, [_H]),
+    "crcl_last_kernel_ms": (ctypes.c_double, [_H]),
+    "crcl_kernel_timings": (ctypes.c_int, [_H, c_double_p, ctypes.c_int]),
+    "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
+}
+
+_lib = None
+
+
+class CaracalGpuError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcaracal_gpu.so and bind every declared symbol; raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CaracalGpuError(
+            "%s not found: build it with `python -m caracal_b200.build` (no CPU fallback exists)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, handle=None, what=""):
+    if rc == 0:
+        return
+    msg = ""
+    if handle:
+        msg = (load().crcl_last_error(handle) or b"").decode()
+    raise CaracalGpuError("%s failed: %s %s" % (what, ERRORS.get(rc, str(rc)), msg))

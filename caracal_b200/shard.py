@@ -1,0 +1,47 @@
+"""Multi-GPU decomposition of the RPMD work units (one process per GPU).
+
+The reference parallelises only whole work units with an MPI master/worker scheme
+(recross.f90:334-417: child +/- pairs; calc_rate.f90:1351-1376: umbrella windows) and ships
+results through files or point-to-point messages.  Here every rank takes a contiguous block of
+the global unit range -- units are independent, so the data path has no collective -- and the
+only exchange is the sum of the kappa(t) numerators and the denominator (child_evol+1 doubles),
+all-reduced with torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
+RNG streams are keyed by the GLOBAL pair index, so the reduced sums do not depend on the
+number of ranks beyond floating-point summation order.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [start, start+count) of n units for this rank; blocks differ by at most 1."""
+    base, rem = divmod(int(n), int(world))
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def reduce_sums(t, group=None):
+    """In-place sum over ranks of a tensor holding [kappa_num(0..child_evol-1), kappa_denom]."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def recross_sharded(compute, total_pairs, child_evol, rank=None, world=None, device="cpu", group=None):
+    """Runs compute(pair0, npairs) -> (num[child_evol], denom) on this rank's block and reduces.
+
+    `compute` is the rank-local work unit: RPMD.recross_children on a GPU (or, in the CPU tests,
+    the oracle).  Returns (kappa_num tensor, kappa_denom float) of the whole job on every rank.
+    """
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    start, count = shard_range(total_pairs, rank, world)
+    num, den = compute(start, count)
+    t = torch.zeros(child_evol + 1, dtype=torch.float64, device=device)
+    t[:child_evol] = torch.as_tensor(num, dtype=torch.float64)
+    t[child_evol] = float(den)
+    reduce_sums(t, group)
+    return t[:child_evol], float(t[child_evol])

@@ -1,0 +1,173 @@
+/*
+ * caracal_gpu.h -- C-ABI of the B200 (sm_100a) RPMD hot path for Trebonius91/Caracal.
+ *
+ * Drop-in boundary for ONE path of the reference: propagation of a batch of ring-polymer
+ * trajectories together with the per-bead PES gradient.  Plain C, plain pointers and
+ * sizes; bind from Fortran with iso_c_binding exactly the way the reference binds its only
+ * other native component (src/inter_mace.f90:34-67 -> src/C_API/wrap_mace.c); the module
+ * a maintainer would add is fortran/caracal_gpu_mod.f90.
+ *
+ * Conventions (the reference's own):
+ *   - arrays are Fortran column-major X(3,natoms,nbeads[,ntraj]) == C [traj][bead][atom][xyz];
+ *   - bohr, hartree, electron masses, atomic time units (dt = fs / 2.41888428E-2);
+ *   - atom indices passed in mechanism tables are 1-based, as in the key file;
+ *   - every function returns 0 on success or a negative CRCL_E* code; nothing aborts the
+ *     process (the reference's `call fatal`, fatal.f90, becomes a per-trajectory status).
+ *   - "host" entry points take host pointers and copy H<->D inside the call on the
+ *     handle's stream; "_dev" entry points take device pointers, are asynchronous on the
+ *     handle's stream and move nothing over PCIe.
+ *
+ * There is no CPU fallback: without a CUDA device crcl_create fails with CRCL_ENODEV.
+ */
+#ifndef CARACAL_GPU_H
+#define CARACAL_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRCL_VERSION 100
+
+/* PES ids: pot_type strings of gradient.f90:154-207 that are implemented on the device */
+#define CRCL_PES_NONE 0
+#define CRCL_PES_H3 1    /* "h3"   egrad_h3.f   BKMP2 H + H2, 3 atoms                 */
+#define CRCL_PES_OH3 2   /* "oh3"  egrad_oh3.f  Schatz-Elgersma OH + H2, atoms O,H,H,H */
+#define CRCL_PES_CH4H 3  /* "ch4h" egrad_ch4h.f CBE CH4 + H, atoms H,C,H,H,H,H         */
+#define CRCL_PES_HOSTCB 100 /* custom_grad / external_grad stay on the host (callback)  */
+
+/* error codes */
+#define CRCL_OK 0
+#define CRCL_ENODEV (-1)   /* no CUDA device / driver                              */
+#define CRCL_EINVAL (-2)   /* bad argument (sizes, ids, null pointers)             */
+#define CRCL_ENOMEM (-3)   /* device allocation failed                             */
+#define CRCL_ECUDA (-4)    /* CUDA runtime error (crcl_last_error gives the text)  */
+#define CRCL_ENOSUP (-5)   /* combination not implemented on the device path       */
+#define CRCL_ESTATE (-6)   /* call order (e.g. no mechanism set, no resident state) */
+
+/* per-trajectory status written by the integrator (verlet.f90 / rpmd_check.f90 outcomes) */
+#define CRCL_TRAJ_OK 0
+#define CRCL_TRAJ_SHAKE_FAIL 1 /* constrain_q.f90:95-98 const_good=1 (epot += 1e5)       */
+#define CRCL_TRAJ_NAN 2        /* verlet.f90:1256-1275 NaN/Inf coordinate (reference: fatal) */
+#define CRCL_TRAJ_SINGULAR 5   /* invert.f90 singular inertia tensor (reference: fatal)  */
+#define CRCL_TRAJ_PESWARN 16   /* PES printed a geometry warning (egrad_h3.f:1465,1471)  */
+
+/* bead-transform flavour */
+#define CRCL_TRANSFORM_REFERENCE 0 /* rfft.f90/irfft.f90 as written: Re(DFT)/sqrt(N) both ways */
+#define CRCL_TRANSFORM_EXACT 1     /* orthonormal normal-mode transform (physics)             */
+
+typedef struct crcl_handle_s *crcl_handle;
+
+/* replaces custom_grad(xyz2,e_evb,g_evb) (custom_grad.f90:35) / external_grad as the
+ * host-side PES plug-in: one image per call, (3,natoms) in, energy and (3,natoms) out */
+typedef void (*crcl_host_grad_fn)(const double *xyz, double *e, double *g, int natoms, void *user);
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+
+/* Makes explicit the module globals the path reads (evb_mod.f90:243-291 nbeads, beta;
+ * general.f90 mass(:), at_move(:); dt as passed to verlet).  One handle per MPI rank / GPU. */
+int crcl_create(crcl_handle *h, int device, int natoms, int nbeads, const double *mass,
+                const int *at_move /* may be NULL = all movable */, double beta, double dt,
+                int pes_id);
+int crcl_destroy(crcl_handle h);
+const char *crcl_last_error(crcl_handle h);
+/* use an existing CUDA stream (cudaStream_t as void*); NULL = the handle's own stream */
+int crcl_set_stream(crcl_handle h, void *cuda_stream);
+int crcl_synchronize(crcl_handle h);
+
+/* beta, dt, nbeads are mutated mid-run by the drivers (calc_rate.f90:651,1253) */
+int crcl_set_beta_dt(crcl_handle h, double beta, double dt);
+int crcl_set_transform(crcl_handle h, int mode);
+int crcl_set_host_gradient_cb(crcl_handle h, crcl_host_grad_fn fn, void *user);
+
+/* MECHA{} section, BIMOLEC family (calc_rate_read.f90:430-870, bonds_ref.f90): 1-based
+ * atom pairs bond_form(form_num,2), bond_break(break_num,2) flattened row-wise; reference
+ * lengths from the TS structure; reactant fragments at_reac (concatenated, n_reac each);
+ * R_inf = dist_inf in bohr. */
+int crcl_set_mechanism(crcl_handle h, int form_num, const int *bond_form, int break_num,
+                       const int *bond_break, const double *form_ref, const double *break_ref,
+                       int sum_reacs, const int *n_reac, const int *at_reac, double R_inf);
+
+/* NVT{} section: thermostat 0 none, 1 Andersen, 2 Nose-Hoover chain (dynamic.f90:463-465);
+ * andersen_step as evb_mod.f90:289; kelvin and nose_q for nhc.f90 / mdinit.f90:138-146 */
+int crcl_set_thermostat(crcl_handle h, int thermostat, int andersen_step, double kelvin,
+                        double nose_q);
+/* counter-based RNG (replaces random_init_local, andersen.f90:131) */
+int crcl_set_seed(crcl_handle h, uint64_t seed);
+
+/* ---- PES seam: egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info) --------------------------------
+ * Same argument order and layout as egrad_h3.f:29 / egrad_ch4h.f:74 / egrad_oh3.f:33;
+ * Nbeads generalises to nimg = ntraj*nbeads images.  info = OR of warning bits. */
+int crcl_egrad(crcl_handle h, int pes_id, const double *q, int natoms, int nimg, double *V,
+               double *dVdq, int *info);
+int crcl_egrad_dev(crcl_handle h, int pes_id, const double *d_q, int natoms, int nimg,
+                   double *d_V, double *d_dVdq, int *d_info /* one int, may be NULL */);
+
+/* ---- integrator seam: verlet(istep,dt,derivs,epot,...,constrain,...) (verlet.f90:65) ----
+ * Advances ntraj independent ring polymers by nsteps steps, istep = istep0+1..istep0+nsteps.
+ * constrain: -1 plain MD (dynamic.x), 0 umbrella, 1 SHAKE/RATTLE on xi, 2 child trajectory.
+ * q, p, derivs: [ntraj][nbeads][natoms][3], in/out.  xi_ideal, k_force: per trajectory
+ * (k_force = k_force(um_window_act)).  Outputs per trajectory from the LAST step: epot,
+ * xi_real; dxi [ntraj][natoms][3] is in/out (SHAKE uses the previous step's, verlet.f90:744).
+ * status: CRCL_TRAJ_* of the first failing step (trajectory is frozen from then on).
+ * traj_id: global trajectory numbers keying the RNG streams (NULL = 0..ntraj-1);
+ * event0 [ntraj]: in/out count of Andersen redraws consumed (NULL = start at 0). */
+int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
+                const double *xi_ideal, const double *k_force, double *q, double *p,
+                double *derivs, double *epot, double *xi_real, double *dxi, int *status,
+                const uint32_t *traj_id, uint32_t *event0);
+
+/* mdinit(derivs,xi_ideal,dxi_act,bias_mode,rank) (mdinit.f90:40): gradient of all beads,
+ * umbrella (bias_mode 1 -> xi only, 2 -> bias applied, 0 -> none), fresh momenta, NHC reset. */
+int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double *xi_ideal,
+                const double *k_force, const double *q, double *p, double *derivs, double *dxi,
+                const uint32_t *traj_id, uint32_t *event0);
+
+/* calc_xi(coords,xi_ideal,xi_act,dxi_act,d2xi_act,mode) (calc_xi.f90:63) on ncoord
+ * structures [ncoord][natoms][3]; mode 1 umbrella form, 2 recrossing form; d2xi may be NULL */
+int crcl_calc_xi(crcl_handle h, int ncoord, const double *coords, const double *xi_ideal,
+                 int mode, double *xi, double *dxi, double *d2xi);
+
+/* ---- work-unit seam --------------------------------------------------------------------
+ * Recrossing children (recross.f90:515-628 worker body / recross_serial.f90:172-229):
+ * pairs pair0..pair0+npairs-1; pair g starts from parent snapshot (g mod nparent), draws
+ * momenta with RNG stream (seed, traj=g), runs the +p and -p child for child_evol free
+ * steps.  kappa_num[child_evol] and *kappa_denom receive this call's sums (reduce across
+ * ranks/GPUs by plain addition).  status[npairs] may be NULL. */
+int crcl_recross_children(crcl_handle h, const double *q_parents, int nparent, int pair0,
+                          int npairs, int child_evol, double xi_ideal, double *kappa_num,
+                          double *kappa_denom, int *status);
+/* same with q_parents / outputs resident in device memory (async on the stream) */
+int crcl_recross_children_dev(crcl_handle h, const double *d_q_parents, int nparent, int pair0,
+                              int npairs, int child_evol, double xi_ideal, double *d_kappa_num,
+                              double *d_kappa_denom, int *d_status);
+
+/* Umbrella window worker body (calc_rate.f90:1387-1700): ntraj trajectories started from
+ * q0 [nbeads][natoms][3] in window (xi0, k): mdinit, equi_steps, then sample_steps while
+ * accumulating xi.  avg/var [ntraj] as written to statistics/bias_<xi> (:1690-1700). */
+int crcl_umbrella_window(crcl_handle h, const double *q0, double xi0, double k_force, int ntraj,
+                         int equi_steps, int sample_steps, uint32_t traj_id0, double *avg,
+                         double *var, int *status);
+
+/* ---- test / introspection hooks ---------------------------------------------------- */
+/* n standard normals of stream (seed, traj, event, bead), elements 0..n-1 (DESIGN.md "RNG") */
+int crcl_rng_normals(crcl_handle h, uint64_t seed, uint32_t traj, uint32_t event, uint32_t bead,
+                     int n, double *out);
+/* number of kernel launches issued through this handle since creation */
+long long crcl_launch_count(crcl_handle h);
+/* duration in ms of the most recent trajectory-kernel launch (CUDA events on the handle's
+ * stream; valid after crcl_synchronize or any host-pointer call) */
+double crcl_last_kernel_ms(crcl_handle h);
+/* durations (ms, CUDA events on the handle's stream around each launch) of the trajectory /
+ * egrad kernels launched since the previous call, oldest first, at most max_n (ring of 256);
+ * synchronises the stream; returns the number written */
+int crcl_kernel_timings(crcl_handle h, double *ms_out, int max_n);
+/* sustained FP64 FMA throughput of the device in TFLOP/s (DFMA microbenchmark, used as the
+ * roofline denominator because MEASURED_PEAKS.json has no FP64 entry) */
+double crcl_measure_fp64_tflops(crcl_handle h, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,50 @@
+// count_flops.cpp -- dynamic operation census of the three reference surfaces:
+// compiles the oracle's PES sources with `real` = counting type and evaluates them at
+// TS-neighbourhood geometries.  Output: one JSON object on stdout.  TEST INFRASTRUCTURE.
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include "count_real.hpp"
+cnt_counters g_cnt = {0, 0, 0, 0, 0, 0};
+#include "pes_h3.c"
+#include "pes_oh3.c"
+#include "pes_ch4h.c"
+
+typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
+
+static void census(const char* name, egrad_fn fn, int nat, const double* ts, int n, bool last)
+{
+    std::mt19937_64 gen(20261017);
+    std::normal_distribution<double> nd(0.0, 0.15);
+    cnt_counters z = {0, 0, 0, 0, 0, 0};
+    g_cnt = z;
+    for (int s = 0; s < n; s++) {
+        real q[18], V[1], g[18];
+        int info;
+        for (int i = 0; i < 3 * nat; i++) q[i] = cnt_real(ts[i] + nd(gen));
+        fn(q, nat, 1, V, g, &info);
+    }
+    printf("  \"%s\": {\"samples\": %d, \"add\": %.1f, \"mul\": %.1f, \"div\": %.1f, \"sqrt\": %.1f, \"libm\": %.1f, "
+           "\"arith\": %.1f, \"flops\": %.1f}%s\n",
+           name, n, (double)g_cnt.add / n, (double)g_cnt.mul / n, (double)g_cnt.div / n, (double)g_cnt.sqrt_ / n,
+           (double)g_cnt.libm / n, (double)g_cnt.arith() / n, (double)g_cnt.total() / n, last ? "" : ",");
+}
+
+int main()
+{
+    const double b = 0.52917721092;
+    const double h3[9] = {0, 0, -0.929764359586 / b, 0, 0, 0, 0, 0, 0.929764359586 / b};
+    const double oh3[12] = {0, 0, 0, 0.97 * -0.2272020946930871 / b, 0.97 * 0.9738476308781951 / b, 0,
+                            1.35 / b, 0, 0, 2.11 / b, 0, 0};
+    const double s3 = 0.5773502691896258;
+    const double ch5[18] = {1.39 * s3 / b, 1.39 * s3 / b, 1.39 * s3 / b, 0, 0, 0,
+                            1.09 * s3 / b, -1.09 * s3 / b, -1.09 * s3 / b, -1.09 * s3 / b, 1.09 * s3 / b, -1.09 * s3 / b,
+                            -1.09 * s3 / b, -1.09 * s3 / b, 1.09 * s3 / b,
+                            2.263 * s3 / b, 2.263 * s3 / b, 2.263 * s3 / b};
+    printf("{\n");
+    census("h3", oracle_egrad_h3_real, 3, h3, 2000, false);
+    census("oh3", oracle_egrad_oh3_real, 4, oh3, 2000, false);
+    census("ch4h", oracle_egrad_ch4h_real, 6, ch5, 2000, true);
+    printf("}\n");
+    return 0;
+}

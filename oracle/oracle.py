@@ -1,0 +1,209 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+never by caracal_b200.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+PES = {"h3": 1, "oh3": 2, "ch4h": 3}
+
+
+def build(force=False):
+    """Compile the C restatement (gcc; see oracle/Makefile)."""
+    need = force or not all(os.path.exists(os.path.join(HERE, f)) for f in ("liboracle.so", "liboracle_exact.so"))
+    if not need:
+        so = os.path.getmtime(os.path.join(HERE, "liboracle.so"))
+        need = any(os.path.getmtime(os.path.join(HERE, f)) > so for f in os.listdir(HERE)
+                   if f.endswith((".c", ".h")) or f == "Makefile")
+    if need:
+        subprocess.run(["make", "-C", HERE, "-s", "all"], check=True, capture_output=True)
+    return os.path.join(HERE, "liboracle.so")
+
+
+_libs = {}
+
+
+def lib(exact=False):
+    name = "liboracle_exact.so" if exact else "liboracle.so"
+    if name not in _libs:
+        build()
+        L = ctypes.CDLL(os.path.join(HERE, name))
+        L.oracle_sys_create.restype = ctypes.c_void_p
+        L.oracle_sys_create.argtypes = [ctypes.c_int, ctypes.c_int, dp, ip, ctypes.c_double, ctypes.c_double,
+                                        ctypes.c_int]
+        L.oracle_sys_q.restype = dp
+        L.oracle_sys_p.restype = dp
+        for f in ("oracle_sys_q", "oracle_sys_p", "oracle_sys_free"):
+            getattr(L, f).argtypes = [ctypes.c_void_p]
+        L.oracle_sys_set_mecha.argtypes = [ctypes.c_void_p, ctypes.c_int, ip, ctypes.c_int, ip, dp, dp, ctypes.c_int,
+                                           ip, ip, ctypes.c_double]
+        L.oracle_sys_set_thermostat.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                ctypes.c_double]
+        L.oracle_sys_set_kforce.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        L.oracle_sys_set_rng.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
+        L.oracle_sys_inject_normals.argtypes = [ctypes.c_void_p, dp, ctypes.c_long]
+        L.oracle_sys_get_nhc.argtypes = [ctypes.c_void_p, dp]
+        L.orc_verlet.restype = ctypes.c_int
+        L.orc_verlet.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp, ctypes.c_double, dp, dp, ctypes.c_int]
+        L.orc_mdinit.argtypes = [ctypes.c_void_p, dp, ctypes.c_double, dp, ctypes.c_int]
+        L.orc_calc_xi.argtypes = [ctypes.c_void_p, dp, ctypes.c_double, dp, dp, dp, ctypes.c_int]
+        L.orc_umbrella.argtypes = [ctypes.c_void_p, dp, ctypes.c_double, dp, dp, dp, ctypes.c_int]
+        L.orc_get_centroid.argtypes = [ctypes.c_void_p, dp]
+        L.orc_andersen.argtypes = [ctypes.c_void_p]
+        L.orc_transrot.argtypes = [ctypes.c_void_p]
+        L.orc_transrot.restype = ctypes.c_int
+        L.orc_recross_pair.restype = ctypes.c_int
+        L.orc_recross_pair.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_int, dp, dp]
+        L.oracle_recross_children.restype = ctypes.c_int
+        L.oracle_recross_children.argtypes = [ctypes.c_void_p, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, dp, dp]
+        L.oracle_egrad.restype = ctypes.c_int
+        L.oracle_egrad.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, dp, dp]
+        L.oracle_rng_normal_pair.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_uint32, dp]
+        L.oracle_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
+        L.oracle_h3_pote.argtypes = [dp, dp, dp]
+        L.oracle_oh3_pot.argtypes = [dp, dp, dp]
+        L.oracle_ch4h_parts.argtypes = [dp, dp, dp]
+        _libs[name] = L
+    return _libs[name]
+
+
+def _d(a):
+    return a.ctypes.data_as(dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(ip)
+
+
+def egrad(pes, q, exact=False):
+    """Oracle of egrad_<pes> on [nimg][natoms][3]; loops images the way gradient.f90 does."""
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    pid = PES[pes] if isinstance(pes, str) else pes
+    nat = {1: 3, 2: 4, 3: 6}[pid]
+    qq = q.reshape(-1, nat, 3)
+    V = np.zeros(qq.shape[0])
+    g = np.zeros_like(qq)
+    info = lib(exact).oracle_egrad(pid, _d(qq), nat, qq.shape[0], _d(V), _d(g))
+    return V, g.reshape(q.shape), info
+
+
+def normals(seed, traj, event, bead, n):
+    out = np.empty(n)
+    z = (ctypes.c_double * 2)()
+    L = lib()
+    for pr in range((n + 1) // 2):
+        L.oracle_rng_normal_pair(seed, traj, event, bead, pr, z)
+        out[2 * pr] = z[0]
+        if 2 * pr + 1 < n:
+            out[2 * pr + 1] = z[1]
+    return out
+
+
+def philox(ctr, key):
+    c = (ctypes.c_uint32 * 4)(*ctr)
+    k = (ctypes.c_uint32 * 2)(*key)
+    o = (ctypes.c_uint32 * 4)()
+    lib().oracle_philox4x32_10(c, k, o)
+    return list(o)
+
+
+class System:
+    """One ring polymer with the oracle's explicit copy of the reference's module state."""
+
+    def __init__(self, pes, nbeads, mass, beta, dt, at_move=None, exact=False):
+        self.L = lib(exact)
+        self.mass = np.ascontiguousarray(mass, dtype=np.float64)
+        self.natoms = len(self.mass)
+        self.nbeads = nbeads
+        am = np.ones(self.natoms, dtype=np.int32) if at_move is None else np.ascontiguousarray(at_move, np.int32)
+        pid = PES[pes] if isinstance(pes, str) else pes
+        self.h = ctypes.c_void_p(self.L.oracle_sys_create(self.natoms, nbeads, _d(self.mass), _i(am), beta, dt, pid))
+        n = 3 * self.natoms * nbeads
+        self.q = np.ctypeslib.as_array(self.L.oracle_sys_q(self.h), shape=(n,)).reshape(nbeads, self.natoms, 3)
+        self.p = np.ctypeslib.as_array(self.L.oracle_sys_p(self.h), shape=(n,)).reshape(nbeads, self.natoms, 3)
+        self.derivs = np.zeros((nbeads, self.natoms, 3))
+        self.dxi = np.zeros((self.natoms, 3))
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.L.oracle_sys_free(self.h)
+        except Exception:
+            pass
+
+    def set_mechanism(self, m):
+        """m: caracal_b200.api.Mechanism-like (1-based indices) -> 0-based for the oracle."""
+        bf = np.ascontiguousarray(m.bond_form - 1, dtype=np.int32)
+        bb = np.ascontiguousarray(m.bond_break - 1, dtype=np.int32)
+        nr = np.array([len(r) for r in m.reactants], dtype=np.int32)
+        ar = np.ascontiguousarray(np.concatenate(m.reactants) - 1, dtype=np.int32)
+        fr = np.ascontiguousarray(m.form_ref, dtype=np.float64)
+        br = np.ascontiguousarray(m.break_ref, dtype=np.float64)
+        self.L.oracle_sys_set_mecha(self.h, len(bf), _i(bf), len(bb), _i(bb), _d(fr), _d(br), len(nr), _i(nr), _i(ar),
+                                    m.R_inf)
+
+    def set_thermostat(self, thermostat, andersen_step=0, kelvin=0.0, nose_q=0.0):
+        self.L.oracle_sys_set_thermostat(self.h, thermostat, andersen_step, kelvin, nose_q)
+
+    def set_kforce(self, k):
+        self.L.oracle_sys_set_kforce(self.h, k)
+
+    def set_rng(self, seed, traj, event=0):
+        self.L.oracle_sys_set_rng(self.h, seed, traj, event)
+
+    def inject_normals(self, z):
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        self._keep.append(z)
+        self.L.oracle_sys_inject_normals(self.h, _d(z), z.size)
+
+    def nhc(self):
+        out = np.zeros(8)
+        self.L.oracle_sys_get_nhc(self.h, _d(out))
+        return out
+
+    def mdinit(self, xi_ideal=0.0, bias_mode=0):
+        self.L.orc_mdinit(self.h, _d(self.derivs), xi_ideal, _d(self.dxi), bias_mode)
+
+    def verlet(self, istep, xi_ideal=0.0, constrain=-1):
+        epot = ctypes.c_double(0.0)
+        xr = ctypes.c_double(0.0)
+        st = self.L.orc_verlet(self.h, istep, _d(self.derivs), ctypes.byref(epot), xi_ideal, ctypes.byref(xr),
+                               _d(self.dxi), constrain)
+        return epot.value, xr.value, st
+
+    def calc_xi(self, coords, xi_ideal, mode, hessian=False):
+        c = np.ascontiguousarray(coords, dtype=np.float64)
+        xi = ctypes.c_double(0.0)
+        dxi = np.zeros((self.natoms, 3))
+        d2 = np.zeros((self.natoms, 3, self.natoms, 3)) if hessian else None
+        self.L.orc_calc_xi(self.h, _d(c), xi_ideal, ctypes.byref(xi), _d(dxi), _d(d2) if hessian else None, mode)
+        return (xi.value, dxi, d2) if hessian else (xi.value, dxi)
+
+    def umbrella(self, centroid, xi_ideal, grad, mode):
+        c = np.ascontiguousarray(centroid, dtype=np.float64)
+        xr = ctypes.c_double(0.0)
+        dxi = np.zeros((self.natoms, 3))
+        self.L.orc_umbrella(self.h, _d(c), xi_ideal, ctypes.byref(xr), _d(dxi), _d(grad), mode)
+        return xr.value, dxi
+
+    def recross_pair(self, xi_ideal, child_evol):
+        num = np.zeros(child_evol)
+        den = ctypes.c_double(0.0)
+        st = self.L.orc_recross_pair(self.h, xi_ideal, child_evol, _d(num), ctypes.byref(den))
+        return num, den.value, st
+
+    def recross_children(self, q_parents, pair0, npairs, child_evol, xi_ideal, seed, nthreads=1):
+        qp = np.ascontiguousarray(q_parents, dtype=np.float64).reshape(-1, self.nbeads, self.natoms, 3)
+        num = np.zeros(child_evol)
+        den = ctypes.c_double(0.0)
+        st = self.L.oracle_recross_children(self.h, _d(qp), qp.shape[0], pair0, npairs, child_evol, xi_ideal, seed,
+                                            nthreads, _d(num), ctypes.byref(den))
+        return num, den.value, st

@@ -1,0 +1,94 @@
+"""Shared systems, geometries and tolerances for the parity tests."""
+import numpy as np
+
+from caracal_b200.api import Mechanism, atomic_mass_au, beta_calc_rate, dt_au
+
+BOHR = 0.52917721092  # general.f90:256
+SEED = 20261017
+
+# tolerances of BASELINE.json north_star
+TOL_EG = 1e-10   # energies / gradients per bead, relative
+TOL_QP = 1e-8    # positions / momenta after 100 steps
+
+
+def h3_ts():
+    """examples/calc_rate/h+h2/ts.xyz (collinear, 0.929764 A)."""
+    return np.array([[0, 0, -0.929764359586], [0, 0, 0], [0, 0, 0.929764359586]]) / BOHR
+
+
+def oh3_ts():
+    """O at origin, r(OH)=0.97 A, H2 (0.76 A) approaching at r(O-H')=1.35 A."""
+    return np.array([[0, 0, 0], [0.97 * np.cos(1.8), 0.97 * np.sin(1.8), 0], [1.35, 0, 0], [1.35 + 0.76, 0, 0]]) / BOHR
+
+
+def ch5_ts():
+    """CBE saddle point neighbourhood: atom order H,C,H,H,H,H_b; r(C-H')=1.39 A, r(H'-Hb)=0.873 A."""
+    t = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]]) / np.sqrt(3)
+    q = np.zeros((6, 3))
+    q[0] = t[0] * 1.39
+    q[2], q[3], q[4] = t[1] * 1.09, t[2] * 1.09, t[3] * 1.09
+    q[5] = t[0] * (1.39 + 0.873)
+    return q / BOHR
+
+
+SYSTEMS = {
+    "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
+               # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
+               mecha=dict(bond_form=[[2, 3]], bond_break=[[1, 2]], reactants=[[1, 2], [3]], dist_inf=16.0)),
+    "oh3": dict(pes="oh3", symbols=["O", "H", "H", "H"], ts=oh3_ts,
+                mecha=dict(bond_form=[[1, 3]], bond_break=[[3, 4]], reactants=[[1, 2], [3, 4]], dist_inf=16.0)),
+    "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
+                 # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
+                 mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),
+}
+
+
+def masses(name):
+    return np.array([atomic_mass_au(s) for s in SYSTEMS[name]["symbols"]])
+
+
+def mechanism(name):
+    s = SYSTEMS[name]
+    return Mechanism(ts_struc=s["ts"](), **s["mecha"])
+
+
+def make_pair(name, nbeads, kelvin=300.0, dt_fs=0.1, **kw):
+    """(product RPMD handle, oracle System) configured identically."""
+    import caracal_b200
+    from oracle import oracle as O
+    m = masses(name)
+    beta, dt = beta_calc_rate(kelvin), dt_au(dt_fs)
+    g = caracal_b200.RPMD(SYSTEMS[name]["pes"], nbeads, m, beta, dt)
+    o = O.System(SYSTEMS[name]["pes"], nbeads, m, beta, dt)
+    mech = mechanism(name)
+    g.set_mechanism(mech)
+    o.set_mechanism(mech)
+    return g, o
+
+
+def ts_cloud(name, n, sigma, rng, min_dist=0.6):
+    """TS + N(0, sigma) Cartesian noise, rejecting pair distances < min_dist."""
+    ts = SYSTEMS[name]["ts"]()
+    out = []
+    while len(out) < n:
+        q = ts[None] + rng.normal(0, sigma, (n,) + ts.shape)
+        d = np.linalg.norm(q[:, :, None, :] - q[:, None, :, :], axis=-1)
+        d += np.eye(ts.shape[0])[None] * 1e3
+        out.extend(q[d.min(axis=(1, 2)) > min_dist])
+    return np.array(out[:n])
+
+
+def ring_polymer(name, nbeads, rng, spread=0.05):
+    ts = SYSTEMS[name]["ts"]()
+    return ts[None] + rng.normal(0, spread, (nbeads,) + ts.shape)
+
+
+def rel_err_E(a, ref, floor=1e-3):
+    return np.abs(a - ref) / np.maximum(np.abs(ref), floor)
+
+
+def rel_err_G(a, ref, floor=1e-3):
+    """max-norm error of each image's gradient relative to that image's largest component."""
+    a = a.reshape(ref.shape)
+    ax = tuple(range(1, ref.ndim))
+    return np.abs(a - ref).max(axis=ax) / np.maximum(np.abs(ref).max(axis=ax), floor)

@@ -1,0 +1,73 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic: pair-range sharding + all-reduce of
+the kappa sums reproduces the single-process result.  The rank-local compute is the oracle here
+(no GPU in this container); on the GPU box the same code path runs with RPMD.recross_children."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from caracal_b200.shard import recross_sharded, shard_range  # noqa: E402
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 512, 1000):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert sum(c for _, c in blocks) == n
+            pos = 0
+            for s, c in blocks:
+                assert s == pos
+                pos += c
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+
+
+NPAIRS, EVOL, XI = 6, 25, 0.98
+
+
+def _compute_factory():
+    from oracle import oracle as O
+    from tests import common as C
+    name, nb = "h3", 4
+    o = O.System(name, nb, C.masses(name), C.beta_calc_rate(300.0), C.dt_au(0.1))
+    o.set_mechanism(C.mechanism(name))
+    qp = np.array([C.ring_polymer(name, nb, np.random.default_rng(k), 0.02) for k in range(2)])
+
+    def compute(pair0, npairs):
+        if npairs == 0:
+            return np.zeros(EVOL), 0.0
+        num, den, st = o.recross_children(qp, pair0, npairs, EVOL, XI, C.SEED, nthreads=1)
+        assert st == 0
+        return num, den
+    return compute
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    num, den = recross_sharded(_compute_factory(), NPAIRS, EVOL, rank, world)
+    if rank == 0:
+        torch.save((num.clone(), den), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_reduction_equals_single_process(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    num2, den2 = torch.load(out)
+    num1, den1 = recross_sharded(_compute_factory(), NPAIRS, EVOL, 0, 1)
+    assert abs(den1 - den2) < 1e-12 * abs(den1)
+    assert (num1 - num2).abs().max().item() < 1e-12 * max(1.0, num1.abs().max().item())

@@ -1,0 +1,101 @@
+"""GPU parity of the PES seam (crcl_egrad == egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info)) against
+the oracle and the golden fixtures, through the C-ABI.  Tolerance: 1e-10 relative per image
+(BASELINE.json north_star), energies relative to max(|E|,1e-3 Eh), gradients relative to the
+image's largest gradient component."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,sigma,n", [("h3", 0.15, 100000), ("h3", 0.5, 30000), ("oh3", 0.15, 100000),
+                                          ("oh3", 0.5, 30000), ("ch4h", 0.15, 100000), ("ch4h", 0.4, 30000)])
+def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
+    rng = np.random.default_rng(C.SEED)
+    q = C.ts_cloud(name, n, sigma, rng)
+    Vo, go, _ = oracle.egrad(name, q)
+    Vd, gd, info = gpu.egrad(name, q)
+    ok = np.isfinite(Vo)
+    assert ok.mean() > 0.999
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+
+
+def test_egrad_golden(gpu):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "pes_golden.json")) as f:
+        G = json.load(f)
+    for name, rec in G.items():
+        q = np.array(rec["q"])
+        V, g, _ = gpu.egrad(name, q)
+        assert C.rel_err_E(V, np.array(rec["V"])).max() < C.TOL_EG
+        assert C.rel_err_G(g, np.array(rec["g"])).max() < C.TOL_EG
+
+
+def test_reference_signature_wrappers(gpu, oracle):
+    q = C.ts_cloud("h3", 16, 0.1, np.random.default_rng(1))        # q(3,Natoms,Nbeads) with Nbeads=16
+    V, dVdq, info = gpu.egrad_h3(q, 3, 16)
+    assert V.shape == (16,) and dVdq.shape == q.shape and info == 0
+    assert C.rel_err_E(V, oracle.egrad("h3", q)[0]).max() < C.TOL_EG
+    V, dVdq, info = gpu.egrad_ch4h(C.ts_cloud("ch4h", 5, 0.1, np.random.default_rng(2)), 6, 5)
+    assert V.shape == (5,)
+    V, dVdq, info = gpu.egrad_oh3(C.ts_cloud("oh3", 3, 0.1, np.random.default_rng(3)), 4, 3)
+    assert V.shape == (3,)
+
+
+def test_edge_sizes(gpu, oracle):
+    # empty, single image, sizes straddling the 128-thread block
+    for n in (0, 1, 127, 128, 129, 1000003 % 4099):
+        q = C.ts_cloud("oh3", max(n, 1), 0.1, np.random.default_rng(n))[:n]
+        V, g, info = gpu.egrad("oh3", q)
+        assert V.shape == (n,)
+        if n:
+            Vo, go, _ = oracle.egrad("oh3", q)
+            assert C.rel_err_E(V, Vo).max() < C.TOL_EG
+
+
+def test_h3_compact_branch_and_warning_bits(gpu, oracle):
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-1.6, 1.6, (40000, 3, 3))
+    d = np.linalg.norm(q[:, [0, 0, 1]] - q[:, [1, 2, 2]], axis=-1)
+    q = q[(d.min(axis=1) > 0.6) & (d.min(axis=1) < 1.15)][:5000]
+    Vo, go, _ = oracle.egrad("h3", q)
+    Vd, gd, info = gpu.egrad("h3", q)
+    assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
+    assert C.rel_err_G(gd, go).max() < C.TOL_EG
+    # CHGEOM prints "INVALID GEOMETRY RLO" for R < 0.2 a0 (egrad_h3.f:1468-1472) -> info bit 2
+    bad = np.array([[[0, 0, 0], [0, 0, 0.15], [0, 0, 3.0]]])
+    _, _, info = gpu.egrad("h3", bad)
+    _, _, oinfo = oracle.egrad("h3", bad)
+    assert info == oinfo == 2
+
+
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h"])
+def test_invariances_at_scale(gpu, name):
+    """size-independent properties on 1e6 images: rigid motions and permutations of equivalent
+    hydrogens leave E unchanged and rotate/permute the gradient."""
+    rng = np.random.default_rng(11)
+    n = 1000000
+    q = C.ts_cloud(name, 20000, 0.15, rng)
+    q = np.tile(q, (n // len(q), 1, 1))
+    q += rng.normal(0, 1e-3, q.shape)
+    V, g, _ = gpu.egrad(name, q)
+    assert np.isfinite(V).all()
+    # random rotation + translation
+    A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    if np.linalg.det(A) < 0:
+        A[:, 0] *= -1
+    q2 = q @ A.T + rng.normal(size=3)
+    V2, g2, _ = gpu.egrad(name, q2)
+    assert C.rel_err_E(V2, V, 1e-2).max() < 1e-9
+    assert C.rel_err_G(g2, g @ A.T, 1e-2).max() < 1e-8
+    # net force and torque vanish
+    assert np.abs(g.sum(axis=1)).max() < 1e-10
+    perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5]}[name]
+    V3, g3, _ = gpu.egrad(name, q[:, perm])
+    assert C.rel_err_E(V3, V, 1e-2).max() < 1e-9
+    assert C.rel_err_G(g3, g[:, perm], 1e-2).max() < 1e-8

@@ -1,0 +1,148 @@
+"""GPU parity of the integrator seam (crcl_mdinit / crcl_verlet) against the oracle: positions
+and momenta after 100 steps from identical initial state within 1e-8 (BASELINE.json north_star),
+for every constrain mode and thermostat of the graded paths, several bead counts (1 bead,
+sub-warp groups, full warp, multi-warp) and ragged batch sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import common as C
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, nbeads, constrain, thermostat, andersen_step, bias_mode, xi_ideal, k_force, ntraj
+    ("h3", 16, -1, 1, 70, 0, 0.0, 0.0, 5),        # config 1: dynamic.x NVT Andersen
+    ("h3", 16, -1, 1, 7, 0, 0.0, 0.0, 3),         # several Andersen redraws inside 100 steps
+    ("h3", 8, 0, 1, 80, 2, 0.9, 15.0, 9),         # umbrella window (rate.key: 8 beads)
+    ("h3", 8, 1, 1, 31, 2, 0.98, 15.0, 4),        # constrained parent (SHAKE/RATTLE)
+    ("h3", 8, 2, 0, 0, 2, 0.98, 0.0, 6),          # child trajectory
+    ("h3", 1, 0, 1, 50, 2, 0.95, 15.0, 33),       # nbeads=1 (start-structure generation phase)
+    ("h3", 4, -1, 2, 0, 0, 0.0, 0.0, 3),          # Nose-Hoover chain
+    ("h3", 32, 2, 0, 0, 2, 0.98, 0.0, 3),         # full-warp group
+    ("h3", 64, 2, 0, 0, 2, 0.98, 0.0, 2),         # CTA-wide group
+    ("oh3", 64, 2, 0, 0, 2, 0.97, 0.0, 2),        # config 3 shape
+    ("oh3", 4, 0, 2, 0, 2, 0.8, 15.0, 5),
+    ("ch4h", 16, 2, 0, 0, 2, 0.97, 0.0, 5),       # config 2: child trajectories
+    ("ch4h", 16, 1, 1, 31, 2, 0.97, 15.0, 3),     # config 2: parent
+    ("ch4h", 16, 0, 1, 80, 2, 0.5, 15.0, 3),      # config 2: umbrella window
+    ("ch4h", 2, -1, 0, 0, 0, 0.0, 0.0, 17),
+]
+
+
+def run_case(gpu, oracle, name, nb, constrain, thermo, astep, bias_mode, xi_ideal, kf, ntraj, nsteps=100,
+             chunks=(100,)):
+    rng = np.random.default_rng(abs(hash((name, nb, constrain, thermo))) % 2 ** 31)
+    g, _ = C.make_pair(name, nb)
+    g.set_seed(C.SEED)
+    g.set_thermostat(thermo, astep, 300.0, 100.0)
+    q0 = np.array([C.ring_polymer(name, nb, rng, 0.03) for _ in range(ntraj)])
+    tid = np.arange(100, 100 + ntraj, dtype=np.uint32)
+    # product
+    q = q0.copy()
+    p, d, dxi, ev = g.mdinit(q, bias_mode, xi_ideal, kf, traj_id=tid)
+    st = np.zeros(ntraj, dtype=np.int32)
+    done = 0
+    for ch in chunks:
+        ep, xr, st = g.verlet(q, p, d, nsteps=ch, istep0=done, constrain=constrain, xi_ideal=xi_ideal, k_force=kf,
+                              dxi=dxi, status=st, traj_id=tid, event=ev)
+        done += ch
+    assert done == nsteps
+    # oracle, one trajectory at a time
+    worst_q = worst_p = 0.0
+    for t in range(ntraj):
+        _, o = C.make_pair(name, nb)
+        o.q[:] = q0[t]
+        o.set_rng(C.SEED, int(tid[t]))
+        o.set_thermostat(thermo, astep, 300.0, 100.0)
+        o.set_kforce(kf)
+        o.mdinit(xi_ideal, bias_mode)
+        for i in range(1, nsteps + 1):
+            epo, xro, sto = o.verlet(i, xi_ideal, constrain)
+            assert sto == 0
+        assert st[t] in (0, 16)
+        worst_q = max(worst_q, np.abs(q[t] - o.q).max())
+        worst_p = max(worst_p, (np.abs(p[t] - o.p) / np.abs(o.p).max()).max())
+        assert abs(ep[t] - epo) < 1e-9 * max(1.0, abs(epo))
+        if constrain >= 0:
+            assert abs(xr[t] - xro) < 1e-9
+    return worst_q, worst_p
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-nb%d-c%d-th%d" % (c[0], c[1], c[2], c[3]))
+def test_100_steps_match_oracle(gpu, oracle, case):
+    wq, wp = run_case(gpu, oracle, *case)
+    assert wq < C.TOL_QP, "positions differ by %g" % wq
+    assert wp < C.TOL_QP, "momenta differ by %g (relative to max |p|)" % wp
+
+
+def test_chunked_calls_equal_single_call(gpu, oracle):
+    """the drivers call verlet one step at a time: 100 x 1 step == 1 x 100 steps (incl. Andersen phase)"""
+    wq, wp = run_case(gpu, oracle, "h3", 8, 0, 1, 7, 2, 0.9, 15.0, 3, chunks=(1,) * 20 + (30, 50))
+    assert wq < C.TOL_QP and wp < C.TOL_QP
+
+
+def test_golden_trajectories(gpu):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "traj_golden.json")) as f:
+        T = json.load(f)
+    for rec in T:
+        g, _ = C.make_pair(rec["name"], rec["nbeads"])
+        g.set_seed(C.SEED)
+        g.set_thermostat(rec["thermostat"], rec["andersen_step"], 300.0, rec.get("nose_q", 0.0))
+        q = np.array(rec["q0"])[None].copy()
+        tid = np.array([rec["traj"]], dtype=np.uint32)
+        p, d, dxi, ev = g.mdinit(q, rec["bias_mode"], rec["xi_ideal"], rec["k_force"], traj_id=tid)
+        g.verlet(q, p, d, nsteps=rec["nsteps"], constrain=rec["constrain"], xi_ideal=rec["xi_ideal"],
+                 k_force=rec["k_force"], dxi=dxi, traj_id=tid, event=ev)
+        assert np.abs(q[0] - np.array(rec["q"])).max() < C.TOL_QP
+        pr = np.array(rec["p"])
+        assert (np.abs(p[0] - pr) / np.abs(pr).max()).max() < C.TOL_QP
+
+
+def test_bead_symmetry_and_exact_transform(gpu):
+    """F2 at scale: in REFERENCE mode beads a and N-a coincide after step 1; in EXACT mode they do
+    not and the ring-polymer Hamiltonian is conserved."""
+    name, nb, ntraj = "h3", 16, 4096
+    rng = np.random.default_rng(3)
+    g, _ = C.make_pair(name, nb)
+    g.set_seed(1)
+    q0 = C.h3_ts()[None, None] + rng.normal(0, 0.02, (ntraj, nb, 3, 3))
+    m = C.masses(name)[None, None, :, None]
+    beta_n = C.beta_calc_rate(300.0) / nb
+
+    def ham(q, p):
+        V = gpu.egrad(name, q.reshape(-1, 3, 3))[0].reshape(ntraj, nb).sum(axis=1)
+        spring = 0.5 * (m * (q - np.roll(q, 1, axis=1)) ** 2).sum(axis=(1, 2, 3)) / beta_n ** 2
+        return (p ** 2 / (2 * m)).sum(axis=(1, 2, 3)) + spring + V
+    for mode in (gpu.TRANSFORM_REFERENCE, gpu.TRANSFORM_EXACT):
+        g.set_transform(mode)
+        q = q0.copy()
+        p, d, dxi, ev = g.mdinit(q, 2, 0.98, 0.0)
+        if mode == gpu.TRANSFORM_EXACT:
+            e0 = ham(q, p)
+        g.verlet(q, p, d, nsteps=200, constrain=2, xi_ideal=0.98, dxi=dxi)
+        asym = max(np.abs(q[:, a] - q[:, nb - a]).max() for a in range(1, nb))
+        if mode == gpu.TRANSFORM_REFERENCE:
+            assert asym < 1e-12
+        else:
+            assert asym > 1e-3
+            assert np.abs(ham(q, p) - e0).max() < 5e-5
+
+
+def test_nan_status_is_reported_not_fatal(gpu):
+    g, _ = C.make_pair("h3", 4)
+    q = np.array([C.ring_polymer("h3", 4, np.random.default_rng(1)) for _ in range(3)])
+    p, d, dxi, ev = g.mdinit(q, 2, 0.98, 0.0)
+    p[1, 0, 0, 0] = np.nan
+    ep, xr, st = g.verlet(q, p, d, nsteps=5, constrain=2, xi_ideal=0.98, dxi=dxi)
+    assert st[1] & 2 and st[0] == 0 and st[2] == 0
+    assert np.isfinite(q[0]).all() and np.isfinite(q[2]).all()
+
+
+def test_unsupported_bead_count_is_an_error(gpu):
+    g = gpu.RPMD("h3", 12, C.masses("h3"), C.beta_calc_rate(300.0), C.dt_au(0.1))
+    q = np.zeros((1, 12, 3, 3))
+    with pytest.raises(gpu.CaracalGpuError, match="ENOSUP"):
+        g.mdinit(q)

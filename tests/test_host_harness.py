@@ -1,0 +1,100 @@
+"""CPU checks of the PRODUCT's device code: the __host__ __device__ PES functors, the reaction
+coordinate / umbrella-hams routine and the counter-based RNG are compiled for the host
+(tests/host_harness/pes_host.cu) and compared with the literal oracle.  These are independent
+derivations (see the headers of caracal_b200/csrc/pes_*.cuh, xi.cuh), so agreement to rounding
+validates both; the same comparisons run on the GPU under -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import common as C
+
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+PID = {"h3": 1, "oh3": 2, "ch4h": 3}
+
+
+def hh_egrad(H, name, q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    V = np.zeros(q.shape[0])
+    g = np.zeros_like(q)
+    H.hh_egrad(PID[name], q.ctypes.data_as(dp), q.shape[0], V.ctypes.data_as(dp), g.ctypes.data_as(dp))
+    return V, g
+
+
+@pytest.mark.parametrize("name,sigma", [("h3", 0.15), ("h3", 0.5), ("oh3", 0.15), ("oh3", 0.5),
+                                        ("ch4h", 0.15), ("ch4h", 0.4)])
+def test_pes_functor_matches_oracle(oracle, host_harness, name, sigma):
+    rng = np.random.default_rng(C.SEED)
+    q = C.ts_cloud(name, 20000, sigma, rng)
+    Vo, go, _ = oracle.egrad(name, q)
+    Vd, gd = hh_egrad(host_harness, name, q)
+    ok = np.isfinite(Vo)
+    assert ok.mean() > 0.999
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+
+
+def test_h3_compact_geometries(oracle, host_harness):
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-1.6, 1.6, (40000, 3, 3))
+    d = np.linalg.norm(q[:, [0, 0, 1]] - q[:, [1, 2, 2]], axis=-1)
+    q = q[(d.min(axis=1) > 0.6) & (d.min(axis=1) < 1.15)][:5000]   # compact branch (R < 1.15 a0)
+    assert len(q) > 1000
+    Vo, go, _ = oracle.egrad("h3", q)
+    Vd, gd = hh_egrad(host_harness, "h3", q)
+    assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
+    assert C.rel_err_G(gd, go).max() < C.TOL_EG
+
+
+def _hh_xi(H, name, x, xi_ideal, mode, beta, hams):
+    m = C.masses(name)
+    mech = C.mechanism(name)
+    bf = np.ascontiguousarray(mech.bond_form, dtype=np.int32)
+    bb = np.ascontiguousarray(mech.bond_break, dtype=np.int32)
+    nr = np.array([len(r) for r in mech.reactants], dtype=np.int32)
+    ar = np.ascontiguousarray(np.concatenate(mech.reactants), dtype=np.int32)
+    xi = ctypes.c_double(0.0)
+    dxi = np.zeros_like(x)
+    hh = np.zeros_like(x)
+    rc = H.hh_calc_xi(len(m), m.ctypes.data_as(dp), len(bf), bf.ctypes.data_as(ip), len(bb), bb.ctypes.data_as(ip),
+                      mech.form_ref.ctypes.data_as(dp), mech.break_ref.ctypes.data_as(dp), len(nr),
+                      nr.ctypes.data_as(ip), ar.ctypes.data_as(ip), ctypes.c_double(mech.R_inf),
+                      x.ctypes.data_as(dp), ctypes.c_double(xi_ideal), mode, ctypes.c_double(beta),
+                      ctypes.byref(xi), dxi.ctypes.data_as(dp), hh.ctypes.data_as(dp) if hams else None)
+    assert rc == 0
+    return xi.value, dxi, hh
+
+
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h"])
+def test_xi_and_hams_match_oracle(oracle, host_harness, name):
+    rng = np.random.default_rng(6)
+    beta = C.beta_calc_rate(300.0)
+    s = oracle.System(name, 2, C.masses(name), beta, C.dt_au(0.1))
+    s.set_mechanism(C.mechanism(name))
+    kf = 0.05 * 300.0
+    s.set_kforce(kf)
+    nat = len(C.masses(name))
+    for x in C.ts_cloud(name, 50, 0.1, rng):
+        x = np.ascontiguousarray(x)
+        for mode in (1, 2):
+            xo, dxo = s.calc_xi(x, 0.93, mode)
+            xd, dxd, _ = _hh_xi(host_harness, name, x, 0.93, mode, beta, False)
+            assert abs(xd - xo) < 1e-13 * max(1, abs(xo))
+            assert np.abs(dxd - dxo).max() < 1e-13
+        # umbrella mode 0 adds k*(xi-xi0)*dxi + hams to every bead's gradient
+        grad = np.zeros((2, nat, 3))
+        xr, dxo = s.umbrella(x, 0.93, grad, 0)
+        xd, dxd, hams = _hh_xi(host_harness, name, x, 0.93, 1, beta, True)
+        want = kf * (xd - 0.93) * dxd + hams
+        assert np.abs(want - grad[0]).max() < 1e-10 * max(1.0, np.abs(grad).max())
+        assert np.array_equal(grad[0], grad[1])
+
+
+def test_rng_matches_oracle(oracle, host_harness):
+    z = (ctypes.c_double * 2)()
+    for traj, event, bead, pair in [(0, 0, 0, 0), (5, 2, 3, 7), (2 ** 31, 9, 15, 8), (123456, 1, 63, 0)]:
+        host_harness.hh_normal_pair(ctypes.c_ulonglong(C.SEED), traj, event, bead, pair, z)
+        ref = oracle.normals(C.SEED, traj, event, bead, 2 * pair + 2)[-2:]
+        assert abs(z[0] - ref[0]) < 1e-14 and abs(z[1] - ref[1]) < 1e-14
