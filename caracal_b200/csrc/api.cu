@@ -348,7 +348,7 @@ const char* crcl_last_error(crcl_handle h) { return h ? h->err.c_str() : "null h
 int crcl_set_stream(crcl_handle h, void* s)
 {
     if (!h) return CRCL_EINVAL;
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = (cudaStream_t)s;   // used as given; NULL is CUDA's (legacy) default stream
     return CRCL_OK;
 }
 

@@ -72,7 +72,9 @@ int crcl_create(crcl_handle *h, int device, int natoms, int nbeads, const double
                 int pes_id);
 int crcl_destroy(crcl_handle h);
 const char *crcl_last_error(crcl_handle h);
-/* use an existing CUDA stream (cudaStream_t as void*); NULL = the handle's own stream */
+/* launch on an existing CUDA stream (cudaStream_t passed as void*, used as given: NULL is CUDA's
+ * default stream, e.g. torch.cuda.current_stream().cuda_stream == 0).  Until this is called the
+ * handle uses a private non-blocking stream created by crcl_create. */
 int crcl_set_stream(crcl_handle h, void *cuda_stream);
 int crcl_synchronize(crcl_handle h);
 

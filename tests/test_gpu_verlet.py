@@ -103,32 +103,38 @@ def test_golden_trajectories(gpu):
 
 def test_bead_symmetry_and_exact_transform(gpu):
     """F2 at scale: in REFERENCE mode beads a and N-a coincide after step 1; in EXACT mode they do
-    not and the ring-polymer Hamiltonian is conserved."""
-    name, nb, ntraj = "h3", 16, 4096
+    not, and the ring-polymer Hamiltonian is conserved with the O(dt^2) error of velocity Verlet
+    (halving dt over the same time span quarters the energy error)."""
+    name, nb, ntraj = "h3", 16, 2048
     rng = np.random.default_rng(3)
-    g, _ = C.make_pair(name, nb)
-    g.set_seed(1)
     q0 = C.h3_ts()[None, None] + rng.normal(0, 0.02, (ntraj, nb, 3, 3))
     m = C.masses(name)[None, None, :, None]
-    beta_n = C.beta_calc_rate(300.0) / nb
+    beta = C.beta_calc_rate(300.0)
+    beta_n = beta / nb
 
     def ham(q, p):
         V = gpu.egrad(name, q.reshape(-1, 3, 3))[0].reshape(ntraj, nb).sum(axis=1)
         spring = 0.5 * (m * (q - np.roll(q, 1, axis=1)) ** 2).sum(axis=(1, 2, 3)) / beta_n ** 2
         return (p ** 2 / (2 * m)).sum(axis=(1, 2, 3)) + spring + V
-    for mode in (gpu.TRANSFORM_REFERENCE, gpu.TRANSFORM_EXACT):
-        g.set_transform(mode)
-        q = q0.copy()
-        p, d, dxi, ev = g.mdinit(q, 2, 0.98, 0.0)
-        if mode == gpu.TRANSFORM_EXACT:
-            e0 = ham(q, p)
-        g.verlet(q, p, d, nsteps=200, constrain=2, xi_ideal=0.98, dxi=dxi)
-        asym = max(np.abs(q[:, a] - q[:, nb - a]).max() for a in range(1, nb))
-        if mode == gpu.TRANSFORM_REFERENCE:
-            assert asym < 1e-12
-        else:
-            assert asym > 1e-3
-            assert np.abs(ham(q, p) - e0).max() < 5e-5
+    g, _ = C.make_pair(name, nb)
+    g.set_seed(1)
+    q = q0.copy()
+    p0, d0, dxi, ev = g.mdinit(q, 2, 0.98, 0.0)
+    p, d = p0.copy(), d0.copy()
+    g.verlet(q, p, d, nsteps=50, constrain=2, xi_ideal=0.98, dxi=dxi)
+    assert max(np.abs(q[:, a] - q[:, nb - a]).max() for a in range(1, nb)) < 1e-12
+    errs = []
+    for fac in (1, 2):
+        g.set_transform(gpu.TRANSFORM_EXACT)
+        g.set_beta_dt(beta, C.dt_au(0.1) / fac)
+        q, p, d = q0.copy(), p0.copy(), d0.copy()
+        e0 = ham(q, p)
+        g.verlet(q, p, d, nsteps=100 * fac, constrain=2, xi_ideal=0.98, dxi=dxi.copy())
+        assert max(np.abs(q[:, a] - q[:, nb - a]).max() for a in range(1, nb)) > 1e-3
+        errs.append(np.abs(ham(q, p) - e0))
+    assert errs[0].max() < 2e-3
+    ratio = np.median(errs[0] / np.maximum(errs[1], 1e-14))
+    assert 2.5 < ratio < 6.0, ratio
 
 
 def test_nan_status_is_reported_not_fatal(gpu):
