@@ -377,3 +377,313 @@ struct PesCH4H {
 };
 
 }  // namespace crcl
+
+// =================================================================================================
+// Four-lane cooperative evaluation (device only).
+//
+// ncu on the one-thread-per-bead kernel (profiles/r1_recross_ch4h_nb16.md) shows the BASELINE
+// batch (1024 trajectories x 16 beads = 512 warps on 148 SMs) is bound by instruction-cache misses
+// and dependent-issue latency at 3.5 warps/SM, not by the FP64 pipe.  The surface is a sum over
+// the four methane hydrogens, so four adjacent lanes evaluate one image: lane x owns hydrogen x,
+// works in a frame rotated by x (local index t <-> hydrogen (x+t)&3, all register indices stay
+// compile-time), exchanges the per-hydrogen scalars with width-4 shuffles, and the partial
+// derivative accumulators are reduce-scattered back to the owner lane by the inverse rotation.
+// 4x the warps, ~1/4 of the instruction stream per warp.
+// =================================================================================================
+#ifdef __CUDACC__
+namespace crcl {
+
+struct PesCH4H4 {
+    static constexpr int NATOMS = 6;
+    static constexpr int ID = CRCL_PES_CH4H;
+    static constexpr int LANES = 4;
+    static constexpr int NOWN = 5;  // components owned per lane (5,5,4,4 of 18)
+
+    // component (atom*3+xyz) number k owned by lane x, or -1: the lane's hydrogen, then C and H_b
+    // spread as lane0: Cx,Cy  lane1: Cz,Bx  lane2: By  lane3: Bz
+    __device__ static __forceinline__ int owned(int x, int k)
+    {
+        if (k < 3) return 3 * ((x == 3) ? 0 : x + 2) + k;
+        if (k == 3) return (x == 0) ? 3 : (x == 1) ? 5 : (x == 2) ? 16 : 17;
+        return (x == 0) ? 4 : (x == 1) ? 15 : -1;
+    }
+
+    // q(c): position component c of this image (any callable); x: lane 0..3; mask: shuffle mask.
+    // Returns the energy on lane 0 (0 on the others) and the gradient of the owned components.
+    template <class QF>
+    __device__ static __forceinline__ int eval_coop(QF q, int x, unsigned mask, double& V, double gown[NOWN])
+    {
+        using namespace ch4h;
+        auto shf = [&](double v, int src) { return __shfl_sync(mask, v, src & 3, 4); };
+        const int ha = (x == 3) ? 0 : x + 2;
+        double co[3], ubo[3], ucb[3], rcho, rbho, rcb;
+        {
+            double tc[3], tb[3], t[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double C = q(3 + d) * 0.52918, B = q(15 + d) * 0.52918, h = q(3 * ha + d) * 0.52918;
+                t[d] = B - C;
+                tc[d] = h - C;
+                tb[d] = h - B;
+            }
+            rcb = sqrt(dot(t, t));
+            rcho = sqrt(dot(tc, tc));
+            rbho = sqrt(dot(tb, tb));
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                ucb[d] = t[d] / rcb;
+                co[d] = tc[d] / rcho;
+                ubo[d] = tb[d] / rbho;
+            }
+        }
+        // own switching functions
+        double sw[10];  // s1,ds1,s2,ds2,s3,ds3,sphi,dsphi,sth,dsth
+        {
+            const double r = rcho, dr = r - R0CH;
+            double omt, ms2;
+            {
+                const double u = r - B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
+                const double arg = A1S * dr * u8;
+                one_minus_tanh(arg, omt, ms2);
+                const bool on = arg < 19.0;
+                sw[0] = on ? omt : 0.0;
+                sw[1] = on ? A1S * (u8 + 8.0 * dr * u7) * ms2 : 0.0;
+            }
+            {
+                const double u = r - B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
+                const double arg = A2S * dr * u6;
+                one_minus_tanh(arg, omt, ms2);
+                const bool on = arg < 19.0;
+                sw[2] = on ? omt : 0.0;
+                sw[3] = on ? A2S * (u6 + 6.0 * dr * u5) * ms2 : 0.0;
+            }
+            {
+                const double u = r - B3S;
+                const double arg = A3S * dr * u * u;
+                one_minus_tanh(arg, omt, ms2);
+                const bool on = arg < 19.0;
+                sw[4] = on ? omt : 0.0;
+                sw[5] = on ? A3S * (3.0 * r * r - 2.0 * r * (R0CH + 2.0 * B3S) + B3S * (B3S + 2.0 * R0CH)) * ms2 : 0.0;
+            }
+            {
+                const bool on = r < 3.8;
+                const double u = r - CPHI, ex = exp(BPHI * u * u * u);
+                one_minus_tanh(APHI * dr * ex, omt, ms2);
+                sw[6] = on ? omt : 0.0;
+                sw[7] = on ? APHI * (1.0 + 3.0 * BPHI * dr * u * u) * ex * ms2 : 0.0;
+                const double v = r - CTHETA, ev = exp(BTHETA * v * v * v);
+                one_minus_tanh(ATHETA * dr * ev, omt, ms2);
+                sw[8] = on ? omt : 0.0;
+                sw[9] = on ? ATHETA * (1.0 + 3.0 * BTHETA * dr * v * v) * ev * ms2 : 0.0;
+            }
+        }
+        // own f1 and derivatives (ipforce_ch4h)
+        double f1o, df1co, df1ho;
+        {
+            const double dr = rcho - R0CH, dh = rbho - R0HH;
+            const double e1 = exp(-AA1 * rbho * rbho);
+            const double e2 = exp(-AA4 * dh * dh);
+            const double a1 = 1.0 - e1, a2 = AA2 + AA3 * e2;
+            const double E = exp(-a2 * dr * dr);
+            f1o = a1 * E;
+            df1co = -2.0 * dr * a1 * a2 * E;
+            df1ho = 2.0 * AA1 * rbho * e1 * E + 2.0 * AA3 * AA4 * dh * e2 * dr * dr * a1 * E;
+        }
+        // rotated gathers: local t <-> hydrogen (x+t)&3
+        double c[4][3], rch[4], s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
+        double f1[3], df1c[3], df1h[3];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int src = x + t;
+#pragma unroll
+            for (int d = 0; d < 3; d++) c[t][d] = t ? shf(co[d], src) : co[d];
+            rch[t] = t ? shf(rcho, src) : rcho;
+            s1[t] = t ? shf(sw[0], src) : sw[0];
+            ds1[t] = t ? shf(sw[1], src) : sw[1];
+            s2[t] = t ? shf(sw[2], src) : sw[2];
+            ds2[t] = t ? shf(sw[3], src) : sw[3];
+            s3[t] = t ? shf(sw[4], src) : sw[4];
+            ds3[t] = t ? shf(sw[5], src) : sw[5];
+            sphi[t] = t ? shf(sw[6], src) : sw[6];
+            dsphi[t] = t ? shf(sw[7], src) : sw[7];
+            sth[t] = t ? shf(sw[8], src) : sw[8];
+            dsth[t] = t ? shf(sw[9], src) : sw[9];
+            if (t < 3) {
+                f1[t] = t ? shf(f1o, src) : f1o;
+                df1c[t] = t ? shf(df1co, src) : df1co;
+                df1h[t] = t ? shf(df1ho, src) : df1ho;
+            }
+        }
+        const double tau = acos(-1.0 / 3.0);
+        const double ta = tau - 0.5 * PI, tb = tau - 2.0 * PI / 3.0;
+        auto theta0 = [&](int i, int j, int k, int l) {
+            return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
+        };
+        // partial accumulators in the local frame
+        double Dch[4] = {0, 0, 0, 0}, Dbh[3] = {0, 0, 0}, Dcb = 0.0;
+        double gH[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, gC[3] = {0, 0, 0};
+        double en = 0.0;
+
+        // ---- stretching, own triple (C-H_x, C-H_b, H_b-H_x) ----
+        {
+            const double rav = (rch[0] + rch[1] + rch[2] + rch[3]) / 4.0;
+            const double arga = C1CH * (rav - R0CH);
+            double omt, ms2;
+            one_minus_tanh(arga, omt, ms2);
+            const bool on = arga < 19.0;
+            const double ach = on ? A1CH + B1CH * (2.0 - omt) * 0.5 : A1CH + B1CH;
+            const double dach = on ? -B1CH * C1CH * 0.5 * ms2 * 0.25 : 0.0;
+            const Leps cb = leps(D1CB, D3CB, ACB, rcb - R0CB);
+            const double dr = rcho - R0CH;
+            const Leps ch = leps(D1CH, D3CH, ach, dr);
+            const Leps bh = leps(D1HH, D3HH, AHH, rbho - R0HH);
+            const double a = ch.vj, b = cb.vj, cc = bh.vj;
+            const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
+            en += ch.vq + cb.vq + bh.vq + vj;
+            const double h = 0.5 / vj;
+            const double wa = (2.0 * a - b - cc) * h, wb = (2.0 * b - a - cc) * h, wc = (2.0 * cc - a - b) * h;
+            const double dch = ch.dvq + wa * ch.dvj;
+            Dbh[0] += bh.dvq + wc * bh.dvj;
+            Dcb += cb.dvq + wb * cb.dvj;
+            const double tt = dch * (dr / ach) * dach;
+            Dch[0] += dch + tt;
+            Dch[1] += tt;
+            Dch[2] += tt;
+            Dch[3] += tt;
+        }
+        // ---- out-of-plane bending, centre = own hydrogen (local 0), (j,k,l) = local (1,2,3) ----
+        {
+            const double pj = s3[1], pk = s3[2], pl = s3[3];
+            const double swi = (1.0 - s3[0]) * pj * pk * pl;
+            const double fd = swi * FCH3, hd = swi * HCH3;
+            double a[3], b[3], n[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double hj = c[1][d] * rch[1];
+                a[d] = c[2][d] * rch[2] - hj;
+                b[d] = c[3][d] * rch[3] - hj;
+            }
+            cross(a, b, n);
+            const double nn = sqrt(dot(n, n));
+            const double inn = 1.0 / nn;
+            double u[3] = {dot(n, c[1]) * inn, dot(n, c[2]) * inn, dot(n, c[3]) * inn};
+            const int npos = (u[0] > 0.0) + (u[1] > 0.0) + (u[2] > 0.0);
+            const double sg = (npos & 1) ? -1.0 : 1.0;
+            const double nh[3] = {sg * n[0] * inn, sg * n[1] * inn, sg * n[2] * inn};
+            double sum2 = 0.0, sum4 = 0.0, G[3] = {0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+                const int m = t + 1;
+                const int ca = (t == 0) ? 2 : 1, cb2 = (t == 2) ? 2 : 3;
+                const double um = sg * u[t];
+                const double del = acos(um) - theta0(0, m, ca, cb2);
+                const double d2 = del * del;
+                sum2 += d2;
+                sum4 += d2 * d2;
+                const double w = 2.0 * fd * del + 4.0 * hd * d2 * del;
+                const double wu = -w / sqrt(1.0 - um * um);
+                const double f = wu / rch[m];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double v = f * (nh[d] - um * c[m][d]);
+                    gH[m][d] += v;
+                    gC[d] -= v;
+                    G[d] += wu * (c[m][d] - um * nh[d]);
+                }
+                Dch[0] -= w * ta * dsphi[0] * sphi[m];
+                Dch[m] -= w * ta * sphi[0] * dsphi[m];
+                Dch[ca] -= w * tb * dsth[ca] * sth[cb2];
+                Dch[cb2] -= w * tb * sth[ca] * dsth[cb2];
+            }
+            {
+                const double s = sg * inn;
+                double gk[3], gl[3];
+                cross(b, G, gk);
+                cross(G, a, gl);
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    gH[2][d] += s * gk[d];
+                    gH[3][d] += s * gl[d];
+                    gH[1][d] -= s * (gk[d] + gl[d]);
+                }
+            }
+            en += fd * sum2 + hd * sum4;
+            const double fs = FCH3 * sum2 + HCH3 * sum4;
+            Dch[0] -= fs * ds3[0] * pj * pk * pl;
+            Dch[1] += fs * (1.0 - s3[0]) * ds3[1] * pk * pl;
+            Dch[2] += fs * (1.0 - s3[0]) * pj * ds3[2] * pl;
+            Dch[3] += fs * (1.0 - s3[0]) * pj * pk * ds3[3];
+        }
+        // ---- in-plane bending: pair local (0,1) on every lane, local (0,2) on lanes 0 and 1 ----
+        {
+            constexpr double f0 = FKINF + AK, f2 = FKINF;
+#pragma unroll
+            for (int pp = 0; pp < 2; pp++) {
+                const int j = pp + 1, k = pp ? 1 : 2, l = 3;
+                if (pp == 1 && x >= 2) break;
+                const double fk0 = f0 + f0 * (s1[0] * s1[j] - 1.0) + (f0 - f2) * (s2[k] * s2[l] - 1.0);
+                const double ff = f1[0] * f1[j];
+                const double K = fk0 * ff;
+                const double cs = dot(c[0], c[j]);
+                const double del = acos(cs) - theta0(0, j, k, l);
+                en += 0.5 * K * del * del;
+                const double w = K * del;
+                const double wc = -w / sqrt(1.0 - cs * cs);
+                const double fi = wc / rch[0], fj = wc / rch[j];
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double vi = fi * (c[j][d] - cs * c[0][d]);
+                    const double vj = fj * (c[0][d] - cs * c[j][d]);
+                    gH[0][d] += vi;
+                    gH[j][d] += vj;
+                    gC[d] -= vi + vj;
+                }
+                const double hd2 = 0.5 * del * del;
+                Dch[0] += -w * ta * dsphi[0] * sphi[j] + hd2 * (f0 * ds1[0] * s1[j] * ff + fk0 * df1c[0] * f1[j]);
+                Dch[j] += -w * ta * sphi[0] * dsphi[j] + hd2 * (f0 * s1[0] * ds1[j] * ff + fk0 * f1[0] * df1c[j]);
+                Dch[k] += -w * tb * dsth[k] * sth[l] + hd2 * (f0 - f2) * ds2[k] * s2[l] * ff;
+                Dch[l] += -w * tb * sth[k] * dsth[l] + hd2 * (f0 - f2) * s2[k] * ds2[l] * ff;
+                Dbh[0] += hd2 * fk0 * df1h[0] * f1[j];
+                Dbh[j] += hd2 * fk0 * f1[0] * df1h[j];
+            }
+        }
+        // ---- reduce-scatter to the owner lane: hydrogen y collects local t from lane y-t ----
+        double DchT = Dch[0], DbhT = Dbh[0], gHT[3] = {gH[0][0], gH[0][1], gH[0][2]};
+#pragma unroll
+        for (int t = 1; t < 4; t++) {
+            DchT += shf(Dch[t], x - t + 4);
+            if (t < 3) DbhT += shf(Dbh[t], x - t + 4);
+#pragma unroll
+            for (int d = 0; d < 3; d++) gHT[d] += shf(gH[t][d], x - t + 4);
+        }
+        // own hydrogen's chain rule; its share of the C and H_b gradients; all-reduce those
+        double gB[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double vc = DchT * co[d], vb = DbhT * ubo[d], vcb = Dcb * ucb[d];
+            gHT[d] += vc + vb;
+            gC[d] -= vc + vcb;
+            gB[d] = vcb - vb;
+        }
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                gC[d] += __shfl_xor_sync(mask, gC[d], o, 4);
+                gB[d] += __shfl_xor_sync(mask, gB[d], o, 4);
+            }
+            en += __shfl_xor_sync(mask, en, o, 4);
+        }
+        constexpr double GF = 0.0201723;
+        V = (x == 0) ? en * 0.03812 : 0.0;
+        gown[0] = gHT[0] * GF;
+        gown[1] = gHT[1] * GF;
+        gown[2] = gHT[2] * GF;
+        gown[3] = ((x == 0) ? gC[0] : (x == 1) ? gC[2] : (x == 2) ? gB[1] : gB[2]) * GF;
+        gown[4] = ((x == 0) ? gC[1] : (x == 1) ? gB[0] : 0.0) * GF;
+        return 0;
+    }
+};
+
+}  // namespace crcl
+#endif

@@ -444,6 +444,18 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
 struct PesH3 {
     static constexpr int NATOMS = 3;
     static constexpr int ID = CRCL_PES_H3;
+    // one thread per image in the trajectory kernels (LANES cooperating threads per bead)
+    static constexpr int LANES = 1;
+    static constexpr int NOWN = 3 * NATOMS;
+    CRCL_HD static __forceinline__ int owned(int, int k) { return k; }
+    template <class QF>
+    CRCL_HD static __forceinline__ int eval_coop(QF qf, int, unsigned, double& V, double* gown)
+    {
+        double x[NOWN];
+#pragma unroll
+        for (int c = 0; c < NOWN; c++) x[c] = qf(c);
+        return eval(x, V, gown);
+    }
     // q, g: [atom][xyz] of one image.  Returns warning bits (0 = clean).
     CRCL_HD static __forceinline__ int eval(const double* __restrict__ q, double& V,
                                                double* __restrict__ g)

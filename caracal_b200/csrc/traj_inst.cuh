@@ -15,8 +15,8 @@ typedef cudaError_t (*traj_launch_fn)(int nbeads, const TrajArgs& A, int bias_mo
 template <class PES, int KIND, int NB>
 static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, cudaStream_t s)
 {
-    using L = SmemLayout<PES::NATOMS, NB>;
-    constexpr int gpb = Group<NB>::GPB, tpb = Group<NB>::TPB;
+    using L = SmemLayout<PES::NATOMS, NB, PES::LANES>;
+    constexpr int gpb = Group<NB, PES::LANES>::GPB, tpb = Group<NB, PES::LANES>::TPB;
     const int grid = (A.ntraj + gpb - 1) / gpb;
     const size_t smem = L::bytes();
     if (grid <= 0) return cudaSuccess;

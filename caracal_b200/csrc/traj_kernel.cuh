@@ -67,22 +67,28 @@ struct TrajArgs {
     double* denom_part;    // [ntraj]: v_s/f_s if v_s > 0 else 0
 };
 
-template <int NB>
+// The T = NB*LANES threads of one trajectory: a sub-warp segment when T <= 32 (32/T trajectories
+// per warp, masked shuffles / __syncwarp so trajectories sharing a warp never wait on each
+// other), otherwise one whole CTA.
+template <int NB, int LANES>
 struct Group {
-    static constexpr bool WARP = (NB <= 32);
-    static constexpr int TPB = WARP ? 32 : NB;   // threads per block
-    static constexpr int GPB = WARP ? 32 / NB : 1;  // groups (trajectories) per block
-    int bead, gib;                               // bead index, group index in block
+    static constexpr int T = NB * LANES;
+    static constexpr bool WARP = (T <= 32);
+    static constexpr int TPB = WARP ? 32 : T;      // threads per block
+    static constexpr int GPB = WARP ? 32 / T : 1;  // trajectories per block
+    int tig, bead, lane, gib;                      // thread in group, bead, lane of the bead, group in block
     unsigned mask;
-    double* red;  // CTA-wide scratch (NB > 32): [TPB/32]
+    double* red;  // CTA-wide scratch (T > 32): [T/32]
 
     __device__ __forceinline__ Group(double* red_)
     {
-        bead = threadIdx.x % NB;
-        gib = threadIdx.x / NB;
+        tig = threadIdx.x % T;
+        bead = tig / LANES;
+        lane = tig % LANES;
+        gib = threadIdx.x / T;
         if (WARP) {
-            const unsigned m = (NB == 32) ? 0xffffffffu : ((1u << NB) - 1u);
-            mask = m << ((threadIdx.x & 31) / NB * NB);
+            const unsigned m = (T == 32) ? 0xffffffffu : ((1u << T) - 1u);
+            mask = m << ((threadIdx.x & 31) / T * T);
         } else {
             mask = 0xffffffffu;
         }
@@ -95,12 +101,12 @@ struct Group {
         else
             __syncthreads();
     }
-    // all-reduce sum over the beads of the trajectory; every bead gets the same bits
+    // all-reduce sum over the threads of the trajectory; every thread gets the same bits
     __device__ __forceinline__ double sum(double v) const
     {
         if (WARP) {
 #pragma unroll
-            for (int o = NB / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+            for (int o = T / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
             return v;
         } else {
 #pragma unroll
@@ -109,7 +115,8 @@ struct Group {
             if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
             __syncthreads();
             double t = 0.0;
-            for (int w = 0; w < NB / 32; w++) t += red[w];
+#pragma unroll
+            for (int w = 0; w < T / 32; w++) t += red[w];
             return t;
         }
     }
@@ -122,13 +129,16 @@ struct Group {
     }
 };
 
-// shared-memory footprint (doubles) of one group and of the block-wide part
-template <int NAT, int NB>
+// shared-memory footprint (doubles) of one trajectory and of the block-wide part
+template <int NAT, int NB, int LANES>
 struct SmemLayout {
     static constexpr int NC = 3 * NAT;
-    static constexpr int PER_GROUP = 2 * NC * NB + 2 * NC;  // {p,q}[c][b] interleaved, cen, dxi
+    static constexpr int PER_GROUP = 2 * NC * NB + 4 * NC;  // {p,q}[c][b] interleaved, cen, dxi, add, ham
     static constexpr int BLOCK = (3 * NB + 32 + 1) & ~1;    // fker, reduction scratch (even: double2 alignment)
-    static constexpr size_t bytes() { return sizeof(double) * (BLOCK + Group<NB>::GPB * PER_GROUP); }
+    static constexpr size_t bytes()
+    {
+        return sizeof(double) * (BLOCK + Group<NB, LANES>::GPB * PER_GROUP);
+    }
 };
 
 // 3x3 inverse by Gauss-Jordan with full pivoting, as invert.f90:38-123; returns 1 if singular
@@ -180,32 +190,41 @@ __device__ __forceinline__ int invert3(double a[3][3])
     return 0;
 }
 
-// Per-thread view of one bead of one trajectory plus the group's shared staging.
+// Per-thread view of a trajectory.  Every thread owns up to NOWN components c = atom*3+xyz of
+// its bead (all of them when LANES == 1); momenta and positions of the whole trajectory live in
+// shared memory as {p,q}[c][bead], the forces of the owned components in registers.
 template <class PES, int NB>
 struct Traj {
     static constexpr int NAT = PES::NATOMS;
     static constexpr int NC = 3 * NAT;
+    static constexpr int L = PES::LANES;
+    static constexpr int NO = PES::NOWN;
+    using Grp = Group<NB, L>;
     const TrajArgs& A;
-    const Group<NB>& G;
-    double q[NC], g[NC];  // this bead's positions and forces (registers)
-    double2* pq;          // shared {p,q}[c][b] of the trajectory
-    double* cen;          // shared centroid [NC]
-    double* dxi;          // shared dxi [NC]
-    const double* fk;     // shared free-RP kernels [3][NB]
+    const Grp& G;
+    double g[NO];   // forces of the owned components
+    int oc[NO];     // owned component numbers (-1: none)
+    double2* pq;    // shared {p,q}[c][b]
+    double* cen;    // shared centroid [NC]
+    double* dxi;    // shared dxi [NC]
+    double* add;    // shared k (xi - xi0) dxi, the umbrella force added to every bead [NC]
+    double* ham;    // shared hams force (umbrella.f90:144-174) [NC]
+    const double* fk;
     double xi_ideal, k_force, xi_real, epot;
     double vnh[4], qnh[4];
     int nfree, status;
     uint32_t tid, event;
 
-    __device__ __forceinline__ Traj(const TrajArgs& a, const Group<NB>& grp, double* smem)
-        : A(a), G(grp)
+    __device__ __forceinline__ Traj(const TrajArgs& a, const Grp& grp, double* smem) : A(a), G(grp)
     {
-        using L = SmemLayout<NAT, NB>;
+        using Lay = SmemLayout<NAT, NB, L>;
         fk = smem;
-        double* base = smem + L::BLOCK + grp.gib * L::PER_GROUP;
+        double* base = smem + Lay::BLOCK + grp.gib * Lay::PER_GROUP;
         pq = reinterpret_cast<double2*>(base);
         cen = base + 2 * NC * NB;
         dxi = cen + NC;
+        add = dxi + NC;
+        ham = add + NC;
         status = 0;
         xi_real = 0.0;
         epot = 0.0;
@@ -213,35 +232,36 @@ struct Traj {
 #pragma unroll
         for (int j = 0; j < NAT; j++)
             if (A.at_move[j]) nfree += 3;
+#pragma unroll
+        for (int k = 0; k < NO; k++) {
+            oc[k] = PES::owned(grp.lane, k);
+            g[k] = 0.0;
+        }
     }
     __device__ __forceinline__ double& P(int c) { return pq[c * NB + G.bead].x; }
+    __device__ __forceinline__ double& Q(int c) { return pq[c * NB + G.bead].y; }
+    __device__ __forceinline__ double mass_of(int c) const { return A.mass[c / 3]; }
+    __device__ __forceinline__ bool moves(int c) const { return A.at_move[c / 3] != 0; }
 
-    // verlet.f90:225-231
-    __device__ __forceinline__ void mask_p()
-    {
-#pragma unroll
-        for (int j = 0; j < NAT; j++)
-            if (!A.at_move[j]) {
-                P(3 * j) = 0.0;
-                P(3 * j + 1) = 0.0;
-                P(3 * j + 2) = 0.0;
-            }
-    }
-    // p <- p - dt/2 * g  (verlet.f90:216-218, 1060-1062) followed by the fixed-atom mask
+    // p <- p - dt/2 * g (verlet.f90:216-218, 1060-1062) followed by the fixed-atom mask (:225-231)
     __device__ __forceinline__ void half_kick()
     {
         const double h = 0.5 * A.dt;
 #pragma unroll
-        for (int c = 0; c < NC; c++) P(c) = P(c) - h * g[c];
-        mask_p();
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) P(oc[k]) = moves(oc[k]) ? P(oc[k]) - h * g[k] : 0.0;
     }
-    // centroid of q (get_centroid.f90:67-82), left in shared cen[]; summed in bead order
-    __device__ __forceinline__ void centroid()
+    __device__ __forceinline__ void mask_p()
     {
 #pragma unroll
-        for (int c = 0; c < NC; c++) pq[c * NB + G.bead].y = q[c];
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0 && !moves(oc[k])) P(oc[k]) = 0.0;
+    }
+    // centroid of q (get_centroid.f90:67-82) into shared cen[]; beads summed in order
+    __device__ __forceinline__ void centroid()
+    {
         G.sync();
-        for (int c = G.bead; c < NC; c += NB) {
+        for (int c = G.tig; c < NC; c += Grp::T) {
             double s = 0.0;
             for (int b = 0; b < NB; b++) s += pq[c * NB + b].y;
             cen[c] = s / NB;
@@ -253,86 +273,96 @@ struct Traj {
     {
         if (NB == 1) {
 #pragma unroll
-            for (int j = 0; j < NAT; j++)
-#pragma unroll
-                for (int d = 0; d < 3; d++) q[3 * j + d] = q[3 * j + d] + P(3 * j + d) * A.dt / A.mass[j];
+            for (int k = 0; k < NO; k++)
+                if (oc[k] >= 0) Q(oc[k]) = Q(oc[k]) + P(oc[k]) * A.dt / mass_of(oc[k]);
             return;
         }
-#pragma unroll
-        for (int c = 0; c < NC; c++) pq[c * NB + G.bead].y = q[c];
         G.sync();
         if (A.symmetrize) {
             // (I+J)/2: x_a <- (x_a + x_{N-a})/2, what T.T does
             const int rb = (NB - G.bead) & (NB - 1);
-            double2 t[NC];
+            double2 t[NO];
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const double2 u = pq[c * NB + G.bead], w = pq[c * NB + rb];
-                t[c].x = 0.5 * (u.x + w.x);
-                t[c].y = 0.5 * (u.y + w.y);
-            }
+            for (int k = 0; k < NO; k++)
+                if (oc[k] >= 0) {
+                    const double2 u = pq[oc[k] * NB + G.bead], w = pq[oc[k] * NB + rb];
+                    t[k].x = 0.5 * (u.x + w.x);
+                    t[k].y = 0.5 * (u.y + w.y);
+                }
             G.sync();
 #pragma unroll
-            for (int c = 0; c < NC; c++) pq[c * NB + G.bead] = t[c];
+            for (int k = 0; k < NO; k++)
+                if (oc[k] >= 0) pq[oc[k] * NB + G.bead] = t[k];
             G.sync();
         }
-        double pn[NC];
+        double pn[NO], qn[NO], ms[NO], ims[NO];
 #pragma unroll
-        for (int j = 0; j < NAT; j++) {
-            const double m = A.mass[j], im = 1.0 / m;
-            double p0 = 0, p1 = 0, p2 = 0, q0 = 0, q1 = 0, q2 = 0;
-#pragma unroll 4
-            for (int b = 0; b < NB; b++) {
-                const int idx = (G.bead - b) & (NB - 1);
-                const double fc = fk[idx], fa = m * fk[NB + idx], fb = im * fk[2 * NB + idx];
-                const double2 u0 = pq[(3 * j) * NB + b], u1 = pq[(3 * j + 1) * NB + b],
-                              u2 = pq[(3 * j + 2) * NB + b];
-                p0 = fma(fc, u0.x, fma(fa, u0.y, p0));
-                q0 = fma(fb, u0.x, fma(fc, u0.y, q0));
-                p1 = fma(fc, u1.x, fma(fa, u1.y, p1));
-                q1 = fma(fb, u1.x, fma(fc, u1.y, q1));
-                p2 = fma(fc, u2.x, fma(fa, u2.y, p2));
-                q2 = fma(fb, u2.x, fma(fc, u2.y, q2));
+        for (int k = 0; k < NO; k++) {
+            pn[k] = 0.0;
+            qn[k] = 0.0;
+            ms[k] = (oc[k] >= 0) ? mass_of(oc[k]) : 1.0;
+            ims[k] = 1.0 / ms[k];
+        }
+#pragma unroll 2
+        for (int b = 0; b < NB; b++) {
+            const int idx = (G.bead - b) & (NB - 1);
+            const double fc = fk[idx], fa = fk[NB + idx], fb = fk[2 * NB + idx];
+#pragma unroll
+            for (int k = 0; k < NO; k++) {
+                const double2 u = pq[(oc[k] >= 0 ? oc[k] : 0) * NB + b];
+                pn[k] = fma(fc, u.x, fma(fa * ms[k], u.y, pn[k]));
+                qn[k] = fma(fb * ims[k], u.x, fma(fc, u.y, qn[k]));
             }
-            pn[3 * j] = p0;
-            pn[3 * j + 1] = p1;
-            pn[3 * j + 2] = p2;
-            q[3 * j] = q0;
-            q[3 * j + 1] = q1;
-            q[3 * j + 2] = q2;
         }
         G.sync();
 #pragma unroll
-        for (int c = 0; c < NC; c++) P(c) = pn[c];
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) pq[oc[k] * NB + G.bead] = make_double2(pn[k], qn[k]);
     }
-    // gradient.f90 -> egrad_<pes> for this bead; epot = sum over beads (verlet.f90:772-777)
+    // gradient.f90 -> egrad_<pes> for this bead; returns epot = sum over beads (verlet.f90:772-777)
     __device__ __forceinline__ double forces()
     {
+        G.sync();
         double e;
-        const int w = PES::eval(q, e, g);
+        const double2* base = pq + G.bead;
+        const int w = PES::eval_coop([&](int c) { return base[c * NB].y; }, G.lane, G.mask, e, g);
         if (w) status |= CRCL_TRAJ_PESWARN;
         return G.sum(e);
     }
-    // umbrella.f90:66-175 on the shared centroid.  mode 0: bias + hams force added to g,
+    // umbrella.f90:66-175 on the shared centroid.  mode 0: bias + hams force added to the forces,
     // xi in umbrella form; mode 1: xi in recrossing form, nothing added.
     __device__ __forceinline__ void umbrella(int mode)
     {
         double x[NC], d[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) x[c] = cen[c];
-        G.sync();
         if (mode == 1) {
             calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 2, xi_real, d, nullptr, A.beta);
+            G.sync();
+            if (G.tig == 0) {
+#pragma unroll
+                for (int c = 0; c < NC; c++) dxi[c] = d[c];
+            }
         } else {
             double h[NC];
             calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 1, xi_real, d, h, A.beta);
             const double kd = k_force * (xi_real - xi_ideal);
+            G.sync();
+            if (G.tig == 0) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) g[c] = (g[c] + kd * d[c]) + h[c];
-        }
-        if (G.bead == 0) {
+                for (int c = 0; c < NC; c++) {
+                    dxi[c] = d[c];
+                    add[c] = kd * d[c];
+                }
+            }
+            if (G.tig == 0) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) dxi[c] = d[c];
+                for (int c = 0; c < NC; c++) ham[c] = h[c];
+            }
+            G.sync();
+#pragma unroll
+            for (int k = 0; k < NO; k++)
+                if (oc[k] >= 0) g[k] = (g[k] + add[oc[k]]) + ham[oc[k]];
         }
         G.sync();
     }
@@ -372,12 +402,11 @@ struct Traj {
         }
         if (!ok) return 1;
 #pragma unroll
-        for (int j = 0; j < NAT; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int c = 3 * j + k;
-                q[c] = q[c] + coeff / A.mass[j] * d[c];
-                P(c) = P(c) + mult * dt / NB * d[c];
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const int c = oc[k];
+                Q(c) = Q(c) + coeff / mass_of(c) * dxi[c];
+                P(c) = P(c) + mult * dt / NB * dxi[c];
             }
         return 0;
     }
@@ -386,29 +415,31 @@ struct Traj {
     {
         double c1 = 0.0, c2 = 0.0;
 #pragma unroll
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) c1 += dxi[oc[k]] * P(oc[k]) / mass_of(oc[k]);
+#pragma unroll
         for (int j = 0; j < NAT; j++)
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int c = 3 * j + k;
-                c1 += dxi[c] * P(c) / A.mass[j];
-                c2 += dxi[c] * dxi[c] / A.mass[j];
-            }
+            for (int k = 0; k < 3; k++) c2 += dxi[3 * j + k] * dxi[3 * j + k] / A.mass[j];
         c1 = G.sum(c1);
         const double lam = -c1 / c2 / NB;
 #pragma unroll
-        for (int c = 0; c < NC; c++) P(c) = P(c) + lam * dxi[c];
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) P(oc[k]) = P(oc[k]) + lam * dxi[oc[k]];
     }
-    // andersen.f90:36-74: full resample p = N(0,1) sqrt(m/beta_n)
+    // andersen.f90:36-74: full resample p = N(0,1) sqrt(m/beta_n); component m of the bead takes
+    // element m&1 of Box-Muller pair m>>1 (rng.cuh)
     __device__ __forceinline__ void andersen()
     {
         const double beta_n = A.beta / NB;
 #pragma unroll
-        for (int m = 0; m < NC; m += 2) {
-            double z0, z1;
-            normal_pair(A.seed, tid, event, (uint32_t)G.bead, (uint32_t)(m >> 1), z0, z1);
-            P(m) = z0 * sqrt(A.mass[m / 3] / beta_n);
-            if (m + 1 < NC) P(m + 1) = z1 * sqrt(A.mass[(m + 1) / 3] / beta_n);
-        }
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const int m = oc[k];
+                double z0, z1;
+                normal_pair(A.seed, tid, event, (uint32_t)G.bead, (uint32_t)(m >> 1), z0, z1);
+                P(m) = ((m & 1) ? z1 : z0) * sqrt(mass_of(m) / beta_n);
+            }
         event++;
     }
     // nhc.f90:34-170
@@ -423,11 +454,8 @@ struct Traj {
         w[2] = w[0];
         double ek = 0.0;
 #pragma unroll
-        for (int j = 0; j < NAT; j++)
-            if (A.at_move[j]) {
-                const double d = P(3 * j) * P(3 * j) + P(3 * j + 1) * P(3 * j + 1) + P(3 * j + 2) * P(3 * j + 2);
-                ek += d / (2.0 * A.mass[j]) / NB / NB;
-            }
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0 && moves(oc[k])) ek += P(oc[k]) * P(oc[k]) / (2.0 * mass_of(oc[k])) / NB / NB;
         double eksum = G.sum(ek);
         double scale = 1.0, gn;
         const double nf = (double)nfree;
@@ -462,9 +490,8 @@ struct Traj {
                 vnh[3] = vnh[3] + gn * dt4;
             }
 #pragma unroll
-        for (int j = 0; j < NAT; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) P(3 * j + k) = A.at_move[j] ? scale * P(3 * j + k) : 0.0;
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) P(oc[k]) = moves(oc[k]) ? scale * P(oc[k]) : 0.0;
     }
     // NHC masses and zeroed chain (mdinit.f90:126-146)
     __device__ __forceinline__ void nhc_init(double nose_q)
@@ -478,28 +505,42 @@ struct Traj {
         }
         qnh[0] = (double)nfree * qnh[0];
     }
-    // transrot.f90:36-236, including the totmass*nbeads double count
+    // transrot.f90:36-236, including the totmass*nbeads double count.  A thread
+    // contributes, per owned component (atom j, direction d) with velocity v:
+    //   linear momentum m v e_d, angular momentum m (q x e_d) v; the thread owning (j,0) also adds
+    //   atom j's m q and inertia terms.
     __device__ __forceinline__ int transrot()
     {
+        G.sync();
         double s[15];
 #pragma unroll
         for (int i = 0; i < 15; i++) s[i] = 0.0;
         double mt = 0.0;
-        double v[NC];
 #pragma unroll
-        for (int j = 0; j < NAT; j++) {
-            const double w = A.mass[j];
-            mt += w;
+        for (int j = 0; j < NAT; j++) mt += A.mass[j];
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                v[3 * j + d] = P(3 * j + d) / w;
-                s[d] += v[3 * j + d] * w;
-                s[3 + d] += q[3 * j + d] * w;
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const int c = oc[k], j = c / 3, d = c - 3 * j;
+                const double w = A.mass[j];
+                const double v = P(c) / w;
+                const double qx = Q(3 * j), qy = Q(3 * j + 1), qz = Q(3 * j + 2);
+                s[d] += v * w;
+                // (q x e_d) v w
+                if (d == 0) {
+                    s[7] += qz * v * w;
+                    s[8] -= qy * v * w;
+                    s[3] += qx * w;
+                    s[4] += qy * w;
+                    s[5] += qz * w;
+                } else if (d == 1) {
+                    s[6] -= qz * v * w;
+                    s[8] += qx * v * w;
+                } else {
+                    s[6] += qy * v * w;
+                    s[7] -= qx * v * w;
+                }
             }
-            s[6] += (q[3 * j + 1] * v[3 * j + 2] - q[3 * j + 2] * v[3 * j + 1]) * w;
-            s[7] += (q[3 * j + 2] * v[3 * j + 0] - q[3 * j + 0] * v[3 * j + 2]) * w;
-            s[8] += (q[3 * j + 0] * v[3 * j + 1] - q[3 * j + 1] * v[3 * j + 0]) * w;
-        }
 #pragma unroll
         for (int i = 0; i < 9; i++) s[i] = G.sum(s[i]);
         const double totmass = (mt * NB) * NB;
@@ -514,16 +555,18 @@ struct Traj {
         mang[2] = s[8] - (ctr[0] * vtot[1] - ctr[1] * vtot[0]) * totmass;
         double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
 #pragma unroll
-        for (int j = 0; j < NAT; j++) {
-            const double w = A.mass[j];
-            const double xd = q[3 * j] - ctr[0], yd = q[3 * j + 1] - ctr[1], zd = q[3 * j + 2] - ctr[2];
-            xx += xd * xd * w;
-            xy += xd * yd * w;
-            xz += xd * zd * w;
-            yy += yd * yd * w;
-            yz += yd * zd * w;
-            zz += zd * zd * w;
-        }
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0 && (oc[k] % 3) == 0) {
+                const int j = oc[k] / 3;
+                const double w = A.mass[j];
+                const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
+                xx += xd * xd * w;
+                xy += xd * yd * w;
+                xz += xd * zd * w;
+                yy += yd * yd * w;
+                yz += yd * zd * w;
+                zz += zd * zd * w;
+            }
         xx = G.sum(xx);
         xy = G.sum(xy);
         xz = G.sum(xz);
@@ -541,16 +584,20 @@ struct Traj {
 #pragma unroll
         for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
 #pragma unroll
-        for (int j = 0; j < NAT; j++) {
-            const double xd = q[3 * j] - ctr[0], yd = q[3 * j + 1] - ctr[1], zd = q[3 * j + 2] - ctr[2];
-            const double v0 = (v[3 * j] - vtot[0]) - vang[1] * zd + vang[2] * yd;
-            const double v1 = (v[3 * j + 1] - vtot[1]) - vang[2] * xd + vang[0] * zd;
-            const double v2 = (v[3 * j + 2] - vtot[2]) - vang[0] * yd + vang[1] * xd;
-            P(3 * j) = v0 * A.mass[j];
-            P(3 * j + 1) = v1 * A.mass[j];
-            P(3 * j + 2) = v2 * A.mass[j];
-        }
-        mask_p();
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const int c = oc[k], j = c / 3, d = c - 3 * j;
+                const double w = A.mass[j];
+                const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
+                double v = P(c) / w - vtot[d];
+                if (d == 0)
+                    v = v - vang[1] * zd + vang[2] * yd;
+                else if (d == 1)
+                    v = v - vang[2] * xd + vang[0] * zd;
+                else
+                    v = v - vang[0] * yd + vang[1] * xd;
+                P(c) = moves(c) ? v * w : 0.0;
+            }
         return 0;
     }
 
@@ -581,10 +628,23 @@ struct Traj {
             andersen();                                        // 16
         int nan = 0;                                           // 18
 #pragma unroll
-        for (int k = 0; k < NC; k++) nan |= (q[k] != q[k]) || (q[k] > 1.79769313486231570815e308);
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const double v = Q(oc[k]);
+                nan |= (v != v) || (v > 1.79769313486231570815e308);
+            }
         if (G.any(nan)) status |= CRCL_TRAJ_NAN;
         if (c <= 0)                                            // 19
             if (transrot()) status |= CRCL_TRAJ_SINGULAR;
+    }
+
+    // state <-> HBM in the reference layout [traj][bead][atom][xyz]
+    __device__ __forceinline__ void load_qp(const double* qsrc, size_t qoff, const double* psrc, size_t poff)
+    {
+#pragma unroll
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0)
+                pq[oc[k] * NB + G.bead] = make_double2(psrc ? psrc[poff + oc[k]] : 0.0, qsrc[qoff + oc[k]]);
     }
 };
 
@@ -597,31 +657,28 @@ __device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
 
 // ---- generic batched verlet: state in HBM in, nsteps steps, state out --------------------
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB>::TPB)
+__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
 verlet_kernel(const __grid_constant__ TrajArgs A)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int NC = 3 * PES::NATOMS;
-    using L = SmemLayout<PES::NATOMS, NB>;
+    constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
+    using Grp = Group<NB, PES::LANES>;
     load_fker<NB>(A, smem);
-    Group<NB> G(smem + 3 * NB);
-    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    Grp G(smem + 3 * NB);
+    const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
     const size_t off = ((size_t)traj * NB + G.bead) * NC;
+    T.load_qp(A.q, off, A.p, off);
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        T.q[c] = A.q[off + c];
-        T.g[c] = A.g[off + c];
-        T.P(c) = A.p[off + c];
-    }
+    for (int k = 0; k < NO; k++)
+        if (T.oc[k] >= 0) T.g[k] = A.g[off + T.oc[k]];
     T.xi_ideal = A.xi_ideal ? A.xi_ideal[traj] : A.xi_ideal_s;
     T.k_force = A.k_force ? A.k_force[traj] : A.k_force_s;
     T.tid = A.traj_id ? A.traj_id[traj] : A.traj_id0 + (uint32_t)traj;
     T.event = A.event ? A.event[traj] : 0u;
-    if (A.dxi) {
-        for (int c = G.bead; c < NC; c += NB) T.dxi[c] = A.dxi[(size_t)traj * NC + c];
-    }
+    if (A.dxi)
+        for (int c = G.tig; c < NC; c += Grp::T) T.dxi[c] = A.dxi[(size_t)traj * NC + c];
     if (A.nhc) {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -639,15 +696,18 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
         sx += T.xi_real;
         sx2 += T.xi_real * T.xi_real;
     }
+    G.sync();
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        A.q[off + c] = T.q[c];
-        A.g[off + c] = T.g[c];
-        A.p[off + c] = T.P(c);
-    }
+    for (int k = 0; k < NO; k++)
+        if (T.oc[k] >= 0) {
+            const int c = T.oc[k];
+            A.q[off + c] = T.Q(c);
+            A.p[off + c] = T.P(c);
+            A.g[off + c] = T.g[k];
+        }
     if (A.dxi)
-        for (int c = G.bead; c < NC; c += NB) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
-    if (G.bead == 0) {
+        for (int c = G.tig; c < NC; c += Grp::T) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
+    if (G.tig == 0) {
         if (A.epot) A.epot[traj] = T.epot;
         if (A.xi_real) A.xi_real[traj] = T.xi_real;
         if (A.status) A.status[traj] = T.status;
@@ -667,27 +727,23 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
 // ---- mdinit (mdinit.f90:40-172) -------------------------------------------------------------
 // bias_mode: 0 no umbrella call, 1 xi only (umbrella mode 1), 2 bias applied (umbrella mode 0).
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB>::TPB)
+__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
 mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const double nose_q)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int NC = 3 * PES::NATOMS;
+    constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
+    using Grp = Group<NB, PES::LANES>;
     load_fker<NB>(A, smem);
-    Group<NB> G(smem + 3 * NB);
-    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    Grp G(smem + 3 * NB);
+    const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
     const size_t off = ((size_t)traj * NB + G.bead) * NC;
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-        T.q[c] = A.q[off + c];
-        T.P(c) = A.p[off + c];
-    }
+    T.load_qp(A.q, off, A.p, off);
     T.xi_ideal = A.xi_ideal ? A.xi_ideal[traj] : A.xi_ideal_s;
     T.k_force = A.k_force ? A.k_force[traj] : A.k_force_s;
     T.tid = A.traj_id ? A.traj_id[traj] : A.traj_id0 + (uint32_t)traj;
     T.event = A.event ? A.event[traj] : 0u;
-    G.sync();
     T.epot = T.forces();
     T.centroid();
     if (bias_mode == 1)
@@ -700,13 +756,14 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
         T.nhc_init(nose_q);
     }
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-        A.g[off + c] = T.g[c];
-        A.p[off + c] = T.P(c);
-    }
+    for (int k = 0; k < NO; k++)
+        if (T.oc[k] >= 0) {
+            A.g[off + T.oc[k]] = T.g[k];
+            A.p[off + T.oc[k]] = T.P(T.oc[k]);
+        }
     if (A.dxi && bias_mode != 0)
-        for (int c = G.bead; c < NC; c += NB) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
-    if (G.bead == 0) {
+        for (int c = G.tig; c < NC; c += Grp::T) A.dxi[(size_t)traj * NC + c] = T.dxi[c];
+    if (G.tig == 0) {
         if (A.event) A.event[traj] = T.event;
         if (A.nhc && A.thermostat == 2) {
 #pragma unroll
@@ -723,54 +780,50 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
 // draw the same momenta (RNG stream keyed by the pair index).  Writes weight = v_s/f_s,
 // denom_part and, per step, theta = [xi_real > 0]; kappa sums are formed by reduce_kappa.
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB>::TPB)
+__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
 recross_kernel(const __grid_constant__ TrajArgs A)
 {
     extern __shared__ __align__(16) double smem[];
-    constexpr int NAT = PES::NATOMS, NC = 3 * NAT;
+    constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
+    using Grp = Group<NB, PES::LANES>;
     load_fker<NB>(A, smem);
-    Group<NB> G(smem + 3 * NB);
-    const int traj = blockIdx.x * Group<NB>::GPB + G.gib;
+    Grp G(smem + 3 * NB);
+    const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
     const int pair = A.pair0 + (traj >> 1);
-    const int sign = (traj & 1) ? -1 : 1;
+    const double sign = (traj & 1) ? -1.0 : 1.0;
     const size_t poff = ((size_t)(pair % A.nparent) * NB + G.bead) * NC;
-#pragma unroll
-    for (int c = 0; c < NC; c++) T.q[c] = A.q_parents[poff + c];
+    T.load_qp(A.q_parents, poff, nullptr, 0);
     T.xi_ideal = A.xi_ideal_s;
     T.k_force = 0.0;
     T.tid = (uint32_t)pair;
     T.event = 0u;
     T.andersen();
-    if (sign < 0) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) T.P(c) = -T.P(c);
-    }
+    for (int k = 0; k < NO; k++)
+        if (T.oc[k] >= 0) T.P(T.oc[k]) = sign * T.P(T.oc[k]);
     T.centroid();
     T.umbrella(1);  // calc_xi(mode 2) on the centroid -> dxi (recross_serial.f90:186-187)
     T.epot = T.forces();
     double vs = 0.0, fs = 0.0;
 #pragma unroll
-    for (int j = 0; j < NAT; j++)
+    for (int k = 0; k < NO; k++)
+        if (T.oc[k] >= 0) vs += T.dxi[T.oc[k]] * T.P(T.oc[k]) / T.mass_of(T.oc[k]);
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const int c = 3 * j + d;
-            vs += T.dxi[c] * T.P(c) / A.mass[j];
-            fs += T.dxi[c] * T.dxi[c] / A.mass[j];
-        }
+    for (int c = 0; c < NC; c++) fs += T.dxi[c] * T.dxi[c] / A.mass[c / 3];
     vs = G.sum(vs) / NB;
     fs = sqrt(fs / (2.0 * PI_UMBR * A.beta));
     const double w = vs / fs;
-    if (G.bead == 0) {
+    if (G.tig == 0) {
         A.weight[traj] = w;
         A.denom_part[traj] = (vs > 0) ? w : 0.0;
     }
     for (int l = 1; l <= A.nsteps; l++) {
         if (!(T.status & CRCL_TRAJ_NAN)) T.step(l);
-        if (G.bead == 0) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
+        if (G.tig == 0) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
     }
-    if (G.bead == 0 && A.status) A.status[traj] = T.status;
+    if (G.tig == 0 && A.status) A.status[traj] = T.status;
 }
 
 }  // namespace crcl
