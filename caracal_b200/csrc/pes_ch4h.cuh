@@ -416,7 +416,7 @@ struct PesCH4H4 {
         using namespace ch4h;
         auto shf = [&](double v, int src) { return __shfl_sync(mask, v, src & 3, 4); };
         const int ha = (x == 3) ? 0 : x + 2;
-        double co[3], ubo[3], ucb[3], rcho, rbho, rcb;
+        double co[3], ubo[3], ucb[3], rcho, rbho, rcb, ircho;
         {
             double tc[3], tb[3], t[3];
 #pragma unroll
@@ -429,11 +429,13 @@ struct PesCH4H4 {
             rcb = sqrt(dot(t, t));
             rcho = sqrt(dot(tc, tc));
             rbho = sqrt(dot(tb, tb));
+            ircho = 1.0 / rcho;
+            const double ircb = 1.0 / rcb, irbho = 1.0 / rbho;
 #pragma unroll
             for (int d = 0; d < 3; d++) {
-                ucb[d] = t[d] / rcb;
-                co[d] = tc[d] / rcho;
-                ubo[d] = tb[d] / rbho;
+                ucb[d] = t[d] * ircb;
+                co[d] = tc[d] * ircho;
+                ubo[d] = tb[d] * irbho;
             }
         }
         // own switching functions
@@ -490,7 +492,7 @@ struct PesCH4H4 {
             df1ho = 2.0 * AA1 * rbho * e1 * E + 2.0 * AA3 * AA4 * dh * e2 * dr * dr * a1 * E;
         }
         // rotated gathers: local t <-> hydrogen (x+t)&3
-        double c[4][3], rch[4], s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
+        double c[4][3], rch[4], irch[4], s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
         double f1[3], df1c[3], df1h[3];
 #pragma unroll
         for (int t = 0; t < 4; t++) {
@@ -498,6 +500,7 @@ struct PesCH4H4 {
 #pragma unroll
             for (int d = 0; d < 3; d++) c[t][d] = t ? shf(co[d], src) : co[d];
             rch[t] = t ? shf(rcho, src) : rcho;
+            irch[t] = t ? shf(ircho, src) : ircho;
             s1[t] = t ? shf(sw[0], src) : sw[0];
             ds1[t] = t ? shf(sw[1], src) : sw[1];
             s2[t] = t ? shf(sw[2], src) : sw[2];
@@ -581,8 +584,8 @@ struct PesCH4H4 {
                 sum2 += d2;
                 sum4 += d2 * d2;
                 const double w = 2.0 * fd * del + 4.0 * hd * d2 * del;
-                const double wu = -w / sqrt(1.0 - um * um);
-                const double f = wu / rch[m];
+                const double wu = -w * rsqrt(1.0 - um * um);
+                const double f = wu * irch[m];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
                     const double v = f * (nh[d] - um * c[m][d]);
@@ -628,8 +631,8 @@ struct PesCH4H4 {
                 const double del = acos(cs) - theta0(0, j, k, l);
                 en += 0.5 * K * del * del;
                 const double w = K * del;
-                const double wc = -w / sqrt(1.0 - cs * cs);
-                const double fi = wc / rch[0], fj = wc / rch[j];
+                const double wc = -w * rsqrt(1.0 - cs * cs);
+                const double fi = wc * irch[0], fj = wc * irch[j];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
                     const double vi = fi * (c[j][d] - cs * c[0][d]);

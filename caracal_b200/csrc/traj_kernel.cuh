@@ -133,7 +133,10 @@ struct Group {
 template <int NAT, int NB, int LANES>
 struct SmemLayout {
     static constexpr int NC = 3 * NAT;
-    static constexpr int PER_GROUP = 2 * NC * NB + 4 * NC;  // {p,q}[c][b] interleaved, cen, dxi, add, ham
+    // bead stride of the {p,q}[c][b] staging in double2 units: +1 when several lanes of a bead
+    // address different components of the same bead slot (keeps them in different banks)
+    static constexpr int NBP = (LANES > 1 && NB > 1) ? NB + 1 : NB;
+    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC;  // {p,q}[c][b] interleaved, cen, dxi, add, ham
     static constexpr int BLOCK = (3 * NB + 32 + 1) & ~1;    // fker, reduction scratch (even: double2 alignment)
     static constexpr size_t bytes()
     {
@@ -199,11 +202,16 @@ struct Traj {
     static constexpr int NC = 3 * NAT;
     static constexpr int L = PES::LANES;
     static constexpr int NO = PES::NOWN;
+    static constexpr int NBP = SmemLayout<NAT, NB, L>::NBP;
     using Grp = Group<NB, L>;
     const TrajArgs& A;
     const Grp& G;
     double g[NO];   // forces of the owned components
+    double ms[NO];  // mass of the owned components' atoms
+    double ims[NO]; // and its reciprocal
     int oc[NO];     // owned component numbers (-1: none)
+    int ob[NO];     // their row offset in pq (component 0's row for unowned slots)
+    unsigned mv;    // bit k: owned component k exists and its atom is movable
     double2* pq;    // shared {p,q}[c][b]
     double* cen;    // shared centroid [NC]
     double* dxi;    // shared dxi [NC]
@@ -221,7 +229,7 @@ struct Traj {
         fk = smem;
         double* base = smem + Lay::BLOCK + grp.gib * Lay::PER_GROUP;
         pq = reinterpret_cast<double2*>(base);
-        cen = base + 2 * NC * NB;
+        cen = base + 2 * NC * NBP;
         dxi = cen + NC;
         add = dxi + NC;
         ham = add + NC;
@@ -232,16 +240,23 @@ struct Traj {
 #pragma unroll
         for (int j = 0; j < NAT; j++)
             if (A.at_move[j]) nfree += 3;
+        mv = 0u;
 #pragma unroll
         for (int k = 0; k < NO; k++) {
             oc[k] = PES::owned(grp.lane, k);
+            ob[k] = (oc[k] >= 0 ? oc[k] : 0) * NBP;
+            ms[k] = (oc[k] >= 0) ? A.mass[oc[k] / 3] : 1.0;
+            ims[k] = 1.0 / ms[k];
+            if (oc[k] >= 0 && A.at_move[oc[k] / 3]) mv |= 1u << k;
             g[k] = 0.0;
         }
     }
-    __device__ __forceinline__ double& P(int c) { return pq[c * NB + G.bead].x; }
-    __device__ __forceinline__ double& Q(int c) { return pq[c * NB + G.bead].y; }
-    __device__ __forceinline__ double mass_of(int c) const { return A.mass[c / 3]; }
-    __device__ __forceinline__ bool moves(int c) const { return A.at_move[c / 3] != 0; }
+    __device__ __forceinline__ double& P(int c) { return pq[c * NBP + G.bead].x; }
+    __device__ __forceinline__ double& Q(int c) { return pq[c * NBP + G.bead].y; }
+    __device__ __forceinline__ double& Pk(int k) { return pq[ob[k] + G.bead].x; }
+    __device__ __forceinline__ double& Qk(int k) { return pq[ob[k] + G.bead].y; }
+    __device__ __forceinline__ bool own(int k) const { return oc[k] >= 0; }
+    __device__ __forceinline__ bool mov(int k) const { return (mv >> k) & 1u; }
 
     // p <- p - dt/2 * g (verlet.f90:216-218, 1060-1062) followed by the fixed-atom mask (:225-231)
     __device__ __forceinline__ void half_kick()
@@ -249,13 +264,13 @@ struct Traj {
         const double h = 0.5 * A.dt;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) P(oc[k]) = moves(oc[k]) ? P(oc[k]) - h * g[k] : 0.0;
+            if (own(k)) Pk(k) = mov(k) ? Pk(k) - h * g[k] : 0.0;
     }
     __device__ __forceinline__ void mask_p()
     {
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0 && !moves(oc[k])) P(oc[k]) = 0.0;
+            if (own(k) && !mov(k)) Pk(k) = 0.0;
     }
     // centroid of q (get_centroid.f90:67-82) into shared cen[]; beads summed in order
     __device__ __forceinline__ void centroid()
@@ -263,18 +278,19 @@ struct Traj {
         G.sync();
         for (int c = G.tig; c < NC; c += Grp::T) {
             double s = 0.0;
-            for (int b = 0; b < NB; b++) s += pq[c * NB + b].y;
+            for (int b = 0; b < NB; b++) s += pq[c * NBP + b].y;
             cen[c] = s / NB;
         }
         G.sync();
     }
-    // free ring-polymer propagation (verlet.f90:353-357 for one bead, :377-463 otherwise)
+    // free ring-polymer propagation (verlet.f90:353-357 for one bead, :377-463 otherwise):
+    // p' = Fc p + m Fa q, q' = Fb p / m + Fc q with the circulant kernels of the header comment
     __device__ __forceinline__ void free_rp()
     {
         if (NB == 1) {
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (oc[k] >= 0) Q(oc[k]) = Q(oc[k]) + P(oc[k]) * A.dt / mass_of(oc[k]);
+                if (own(k)) Qk(k) = Qk(k) + Pk(k) * A.dt / ms[k];
             return;
         }
         G.sync();
@@ -283,41 +299,37 @@ struct Traj {
             const int rb = (NB - G.bead) & (NB - 1);
             double2 t[NO];
 #pragma unroll
-            for (int k = 0; k < NO; k++)
-                if (oc[k] >= 0) {
-                    const double2 u = pq[oc[k] * NB + G.bead], w = pq[oc[k] * NB + rb];
-                    t[k].x = 0.5 * (u.x + w.x);
-                    t[k].y = 0.5 * (u.y + w.y);
-                }
+            for (int k = 0; k < NO; k++) {
+                const double2 u = pq[ob[k] + G.bead], w = pq[ob[k] + rb];
+                t[k].x = 0.5 * (u.x + w.x);
+                t[k].y = 0.5 * (u.y + w.y);
+            }
             G.sync();
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (oc[k] >= 0) pq[oc[k] * NB + G.bead] = t[k];
+                if (own(k)) pq[ob[k] + G.bead] = t[k];
             G.sync();
         }
-        double pn[NO], qn[NO], ms[NO], ims[NO];
+        double cp[NO], aq[NO], bp[NO], cq[NO];
 #pragma unroll
-        for (int k = 0; k < NO; k++) {
-            pn[k] = 0.0;
-            qn[k] = 0.0;
-            ms[k] = (oc[k] >= 0) ? mass_of(oc[k]) : 1.0;
-            ims[k] = 1.0 / ms[k];
-        }
+        for (int k = 0; k < NO; k++) cp[k] = aq[k] = bp[k] = cq[k] = 0.0;
 #pragma unroll 2
         for (int b = 0; b < NB; b++) {
             const int idx = (G.bead - b) & (NB - 1);
             const double fc = fk[idx], fa = fk[NB + idx], fb = fk[2 * NB + idx];
 #pragma unroll
             for (int k = 0; k < NO; k++) {
-                const double2 u = pq[(oc[k] >= 0 ? oc[k] : 0) * NB + b];
-                pn[k] = fma(fc, u.x, fma(fa * ms[k], u.y, pn[k]));
-                qn[k] = fma(fb * ims[k], u.x, fma(fc, u.y, qn[k]));
+                const double2 u = pq[ob[k] + b];
+                cp[k] = fma(fc, u.x, cp[k]);
+                aq[k] = fma(fa, u.y, aq[k]);
+                bp[k] = fma(fb, u.x, bp[k]);
+                cq[k] = fma(fc, u.y, cq[k]);
             }
         }
         G.sync();
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) pq[oc[k] * NB + G.bead] = make_double2(pn[k], qn[k]);
+            if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
     }
     // gradient.f90 -> egrad_<pes> for this bead; returns epot = sum over beads (verlet.f90:772-777)
     __device__ __forceinline__ double forces()
@@ -325,7 +337,7 @@ struct Traj {
         G.sync();
         double e;
         const double2* base = pq + G.bead;
-        const int w = PES::eval_coop([&](int c) { return base[c * NB].y; }, G.lane, G.mask, e, g);
+        const int w = PES::eval_coop([&](int c) { return base[c * NBP].y; }, G.lane, G.mask, e, g);
         if (w) status |= CRCL_TRAJ_PESWARN;
         return G.sum(e);
     }
@@ -336,6 +348,11 @@ struct Traj {
         double x[NC], d[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) x[c] = cen[c];
+        if (mode == 2) {
+            // child trajectory: only the value of xi is ever used (recross.f90:597-602)
+            xi_real = xi_value<NAT>(A.mech, x, xi_ideal, 2);
+            return;
+        }
         if (mode == 1) {
             calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 2, xi_real, d, nullptr, A.beta);
             G.sync();
@@ -362,7 +379,7 @@ struct Traj {
             G.sync();
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (oc[k] >= 0) g[k] = (g[k] + add[oc[k]]) + ham[oc[k]];
+                if (own(k)) g[k] = (g[k] + add[oc[k]]) + ham[oc[k]];
         }
         G.sync();
     }
@@ -403,10 +420,9 @@ struct Traj {
         if (!ok) return 1;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) {
-                const int c = oc[k];
-                Q(c) = Q(c) + coeff / mass_of(c) * dxi[c];
-                P(c) = P(c) + mult * dt / NB * dxi[c];
+            if (own(k)) {
+                Qk(k) = Qk(k) + coeff / ms[k] * dxi[oc[k]];
+                Pk(k) = Pk(k) + mult * dt / NB * dxi[oc[k]];
             }
         return 0;
     }
@@ -416,7 +432,7 @@ struct Traj {
         double c1 = 0.0, c2 = 0.0;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) c1 += dxi[oc[k]] * P(oc[k]) / mass_of(oc[k]);
+            if (own(k)) c1 += dxi[oc[k]] * Pk(k) / ms[k];
 #pragma unroll
         for (int j = 0; j < NAT; j++)
 #pragma unroll
@@ -425,7 +441,7 @@ struct Traj {
         const double lam = -c1 / c2 / NB;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) P(oc[k]) = P(oc[k]) + lam * dxi[oc[k]];
+            if (own(k)) Pk(k) = Pk(k) + lam * dxi[oc[k]];
     }
     // andersen.f90:36-74: full resample p = N(0,1) sqrt(m/beta_n); component m of the bead takes
     // element m&1 of Box-Muller pair m>>1 (rng.cuh)
@@ -438,7 +454,7 @@ struct Traj {
                 const int m = oc[k];
                 double z0, z1;
                 normal_pair(A.seed, tid, event, (uint32_t)G.bead, (uint32_t)(m >> 1), z0, z1);
-                P(m) = ((m & 1) ? z1 : z0) * sqrt(mass_of(m) / beta_n);
+                Pk(k) = ((m & 1) ? z1 : z0) * sqrt(ms[k] / beta_n);
             }
         event++;
     }
@@ -455,7 +471,7 @@ struct Traj {
         double ek = 0.0;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0 && moves(oc[k])) ek += P(oc[k]) * P(oc[k]) / (2.0 * mass_of(oc[k])) / NB / NB;
+            if (mov(k)) ek += Pk(k) * Pk(k) / (2.0 * ms[k]) / NB / NB;
         double eksum = G.sum(ek);
         double scale = 1.0, gn;
         const double nf = (double)nfree;
@@ -491,7 +507,7 @@ struct Traj {
             }
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) P(oc[k]) = moves(oc[k]) ? scale * P(oc[k]) : 0.0;
+            if (own(k)) Pk(k) = mov(k) ? scale * Pk(k) : 0.0;
     }
     // NHC masses and zeroed chain (mdinit.f90:126-146)
     __device__ __forceinline__ void nhc_init(double nose_q)
@@ -596,7 +612,7 @@ struct Traj {
                     v = v - vang[2] * xd + vang[0] * zd;
                 else
                     v = v - vang[0] * yd + vang[1] * xd;
-                P(c) = moves(c) ? v * w : 0.0;
+                P(c) = mov(k) ? v * w : 0.0;
             }
         return 0;
     }
@@ -619,8 +635,10 @@ struct Traj {
         }
         if (c == 0 || c == 3)                                  // 12
             umbrella(0);
-        else if (c == 1 || c == 2)
+        else if (c == 1)
             umbrella(1);
+        else if (c == 2)
+            umbrella(2);
         half_kick();                                           // 13
         if (c == 1) constrain_p();                             // 14
         if (c != 2 && th == 2) nhc();                          // 15
@@ -644,8 +662,20 @@ struct Traj {
 #pragma unroll
         for (int k = 0; k < NO; k++)
             if (oc[k] >= 0)
-                pq[oc[k] * NB + G.bead] = make_double2(psrc ? psrc[poff + oc[k]] : 0.0, qsrc[qoff + oc[k]]);
+                pq[ob[k] + G.bead] = make_double2(psrc ? psrc[poff + oc[k]] : 0.0, qsrc[qoff + oc[k]]);
     }
+};
+
+// minimum resident CTAs per SM requested from ptxas (register cap = 64K / (MINB * threads)).
+// The lane-split CH4+H kernels need 7 CTAs of 64 threads per SM to hold the BASELINE batch
+// (1024 trajectories on 148 SMs) in a single wave; see profiles/ for the measured trade-off.
+#ifndef CRCL_MINB_L4
+#define CRCL_MINB_L4 7
+#endif
+template <class PES, int NB>
+struct LaunchCfg {
+    static constexpr int TPB = Group<NB, PES::LANES>::TPB;
+    static constexpr int MINB = (PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : 1;
 };
 
 template <int NB>
@@ -657,7 +687,7 @@ __device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
 
 // ---- generic batched verlet: state in HBM in, nsteps steps, state out --------------------
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
+__global__ void __launch_bounds__(LaunchCfg<PES, NB>::TPB, LaunchCfg<PES, NB>::MINB)
 verlet_kernel(const __grid_constant__ TrajArgs A)
 {
     extern __shared__ __align__(16) double smem[];
@@ -696,6 +726,8 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
         sx += T.xi_real;
         sx2 += T.xi_real * T.xi_real;
     }
+    // child steps only evaluate the value of xi; leave dxi as verlet.f90:1049-1050 would
+    if (A.constrain == 2 && A.nsteps > 0) T.umbrella(1);
     G.sync();
 #pragma unroll
     for (int k = 0; k < NO; k++)
@@ -727,7 +759,7 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
 // ---- mdinit (mdinit.f90:40-172) -------------------------------------------------------------
 // bias_mode: 0 no umbrella call, 1 xi only (umbrella mode 1), 2 bias applied (umbrella mode 0).
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
+__global__ void __launch_bounds__(LaunchCfg<PES, NB>::TPB, LaunchCfg<PES, NB>::MINB)
 mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const double nose_q)
 {
     extern __shared__ __align__(16) double smem[];
@@ -780,7 +812,7 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
 // draw the same momenta (RNG stream keyed by the pair index).  Writes weight = v_s/f_s,
 // denom_part and, per step, theta = [xi_real > 0]; kappa sums are formed by reduce_kappa.
 template <class PES, int NB>
-__global__ void __launch_bounds__(Group<NB, PES::LANES>::TPB)
+__global__ void __launch_bounds__(LaunchCfg<PES, NB>::TPB, LaunchCfg<PES, NB>::MINB)
 recross_kernel(const __grid_constant__ TrajArgs A)
 {
     extern __shared__ __align__(16) double smem[];
@@ -809,7 +841,7 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     double vs = 0.0, fs = 0.0;
 #pragma unroll
     for (int k = 0; k < NO; k++)
-        if (T.oc[k] >= 0) vs += T.dxi[T.oc[k]] * T.P(T.oc[k]) / T.mass_of(T.oc[k]);
+        if (T.own(k)) vs += T.dxi[T.oc[k]] * T.Pk(k) / T.ms[k];
 #pragma unroll
     for (int c = 0; c < NC; c++) fs += T.dxi[c] * T.dxi[c] / A.mass[c / 3];
     vs = G.sum(vs) / NB;

@@ -23,6 +23,7 @@ struct Mech {
     int sum_reacs;
     int frag[XI_MAXAT];  // fragment of each atom, -1 = none
     double mass_reac[XI_MAXREAC];
+    double wfrag[XI_MAXAT];  // mass[a] / mass_reac[frag[a]] (0 if the atom is in no fragment)
     double R_inf;
     int valid;
 };
@@ -65,6 +66,8 @@ inline int build_mech(Mech& M, int natoms, const double* mass, int form_num, con
         }
         off += n_reac[k];
     }
+    for (int a = 0; a < XI_MAXAT; a++)
+        M.wfrag[a] = (a < natoms && M.frag[a] >= 0) ? mass[a] / M.mass_reac[M.frag[a]] : 0.0;
     M.R_inf = R_inf;
     M.valid = 1;
     return 0;
@@ -78,6 +81,44 @@ CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w
     const double rw = r[0] * w[0] + r[1] * w[1] + r[2] * w[2];
 #pragma unroll
     for (int d = 0; d < 3; d++) o[d] = (rr * w[d] - r[d] * rw) * r3;
+}
+
+// xi only (no gradient): what a child trajectory needs every step (verlet.f90:1049-1050 calls
+// umbrella mode 1 only to learn the sign of xi_real, recross.f90:597-602).
+template <int NAT>
+CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double xi_ideal, int mode)
+{
+    double s1 = 0.0;
+    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+    for (int i = 0; i < M.break_num; i++) {
+        const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+        s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) / bnum;
+    }
+    for (int i = 0; i < M.form_num; i++) {
+        const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+        s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) / fnum;
+    }
+    double com[XI_MAXREAC][3];
+#pragma unroll
+    for (int k = 0; k < XI_MAXREAC; k++) com[k][0] = com[k][1] = com[k][2] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NAT; a++) {
+        const int k = M.frag[a];
+        if (k >= 0) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
+        }
+    }
+    double s0 = 0.0;
+    for (int i = 0; i < M.sum_reacs; i++)
+        for (int j = i + 1; j < M.sum_reacs; j++) {
+            const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
+            s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
+        }
+    s0 = s0 / (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
+    return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
 }
 
 // mode 1: xi = s0/(s0-s1) (umbrella form); mode 2: xi = xi_ideal*s1 + (1-xi_ideal)*s0.
@@ -133,9 +174,8 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
     for (int a = 0; a < NAT; a++) {
         const int k = M.frag[a];
         if (k >= 0) {
-            const double w = mass[a];
 #pragma unroll
-            for (int d = 0; d < 3; d++) com[k][d] += w * x[3 * a + d] / M.mass_reac[k];
+            for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
         }
     }
     const int nterms = (M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2;
@@ -156,7 +196,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
                 const int k = M.frag[a];
                 if (k == i || k == j) {
                     const double sg = (k == i) ? 1.0 : -1.0;
-                    const double w = sg * ri[np] * mass[a] / M.mass_reac[k] / fterms;
+                    const double w = sg * ri[np] * M.wfrag[a] / fterms;
 #pragma unroll
                     for (int d = 0; d < 3; d++) ds0[3 * a + d] += Red[np][d] * w;
                 }
@@ -225,7 +265,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
                 const int k = M.frag[a];
                 if (k == i || k == j) {
                     const double sg = (k == i) ? 1.0 : -1.0;
-                    const double w = sg * mass[a] / M.mass_reac[k];
+                    const double w = sg * M.wfrag[a];
 #pragma unroll
                     for (int d = 0; d < 3; d++) W[d] += w * v[3 * a + d];
                 }
@@ -236,7 +276,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
                 const int k = M.frag[a];
                 if (k == i || k == j) {
                     const double sg = (k == i) ? 1.0 : -1.0;
-                    const double w = -sg * mass[a] / M.mass_reac[k] / fterms;
+                    const double w = -sg * M.wfrag[a] / fterms;
 #pragma unroll
                     for (int d = 0; d < 3; d++) H0v[3 * a + d] += w * o[d];
                 }

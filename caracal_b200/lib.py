@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcaracal_gpu.so")
+# CRCL_LIB_PATH selects an alternative build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("CRCL_LIB_PATH", os.path.join(_HERE, "libcaracal_gpu.so"))
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
