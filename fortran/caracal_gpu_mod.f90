@@ -1,0 +1,208 @@
+!
+!     module caracal_gpu: iso_c_binding interface to libcaracal_gpu.so (include/caracal_gpu.h)
+!     and thin shims that keep the call sites of the reference drivers unchanged.
+!
+!     Written in the style of src/inter_mace.f90:34-67 (the reference's only other bind(C)
+!     interface).  NOT compiled in this repository's CI: the build image has no Fortran compiler
+!     (SURVEY.md F1).  See INTEGRATION.md for where each shim is called from.
+!
+module caracal_gpu
+use, intrinsic :: iso_c_binding
+implicit none
+
+integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 3
+type(c_ptr), save :: crcl_h = c_null_ptr        ! one handle per MPI rank / GPU
+
+interface
+   function crcl_create(h, device, natoms, nbeads, mass, at_move, beta, dt, pes_id) bind(C, name="crcl_create")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), intent(out) :: h
+      integer(c_int), value :: device, natoms, nbeads, pes_id
+      real(c_double), dimension(*), intent(in) :: mass
+      integer(c_int), dimension(*), intent(in) :: at_move
+      real(c_double), value :: beta, dt
+      integer(c_int) :: crcl_create
+   end function crcl_create
+
+   function crcl_destroy(h) bind(C, name="crcl_destroy")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int) :: crcl_destroy
+   end function crcl_destroy
+
+   function crcl_set_beta_dt(h, beta, dt) bind(C, name="crcl_set_beta_dt")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: beta, dt
+      integer(c_int) :: crcl_set_beta_dt
+   end function crcl_set_beta_dt
+
+   function crcl_set_mechanism(h, form_num, bond_form, break_num, bond_break, form_ref, break_ref, &
+                               sum_reacs, n_reac, at_reac, r_inf) bind(C, name="crcl_set_mechanism")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: form_num, break_num, sum_reacs
+      integer(c_int), dimension(*), intent(in) :: bond_form, bond_break, n_reac, at_reac
+      real(c_double), dimension(*), intent(in) :: form_ref, break_ref
+      real(c_double), value :: r_inf
+      integer(c_int) :: crcl_set_mechanism
+   end function crcl_set_mechanism
+
+   function crcl_set_thermostat(h, thermostat, andersen_step, kelvin, nose_q) bind(C, name="crcl_set_thermostat")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: thermostat, andersen_step
+      real(c_double), value :: kelvin, nose_q
+      integer(c_int) :: crcl_set_thermostat
+   end function crcl_set_thermostat
+
+   function crcl_set_seed(h, seed) bind(C, name="crcl_set_seed")
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: h
+      integer(c_int64_t), value :: seed
+      integer(c_int) :: crcl_set_seed
+   end function crcl_set_seed
+
+   ! egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info)  (egrad_h3.f:29, egrad_ch4h.f:74, egrad_oh3.f:33)
+   function crcl_egrad(h, pes_id, q, natoms, nimg, V, dVdq, info) bind(C, name="crcl_egrad")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: pes_id, natoms, nimg
+      real(c_double), dimension(*), intent(in) :: q
+      real(c_double), dimension(*), intent(out) :: V, dVdq
+      integer(c_int), intent(out) :: info
+      integer(c_int) :: crcl_egrad
+   end function crcl_egrad
+
+   ! verlet (verlet.f90:65) on ntraj ring polymers
+   function crcl_verlet(h, ntraj, nsteps, istep0, constrain, xi_ideal, k_force, q, p, derivs, epot, &
+                        xi_real, dxi, status, traj_id, event0) bind(C, name="crcl_verlet")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: ntraj, nsteps, istep0, constrain
+      real(c_double), dimension(*), intent(in) :: xi_ideal, k_force
+      real(c_double), dimension(*), intent(inout) :: q, p, derivs, dxi
+      real(c_double), dimension(*), intent(out) :: epot, xi_real
+      integer(c_int), dimension(*), intent(inout) :: status
+      type(c_ptr), value :: traj_id, event0          ! c_null_ptr or c_loc of uint32 arrays
+      integer(c_int) :: crcl_verlet
+   end function crcl_verlet
+
+   ! mdinit (mdinit.f90:40)
+   function crcl_mdinit(h, ntraj, bias_mode, xi_ideal, k_force, q, p, derivs, dxi, traj_id, event0) &
+                        bind(C, name="crcl_mdinit")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: ntraj, bias_mode
+      real(c_double), dimension(*), intent(in) :: xi_ideal, k_force, q
+      real(c_double), dimension(*), intent(inout) :: p, derivs, dxi
+      type(c_ptr), value :: traj_id, event0
+      integer(c_int) :: crcl_mdinit
+   end function crcl_mdinit
+
+   ! recross worker body (recross.f90:515-628)
+   function crcl_recross_children(h, q_parents, nparent, pair0, npairs, child_evol, xi_ideal, &
+                                  kappa_num, kappa_denom, status) bind(C, name="crcl_recross_children")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), dimension(*), intent(in) :: q_parents
+      integer(c_int), value :: nparent, pair0, npairs, child_evol
+      real(c_double), value :: xi_ideal
+      real(c_double), dimension(*), intent(out) :: kappa_num
+      real(c_double), intent(out) :: kappa_denom
+      integer(c_int), dimension(*), intent(out) :: status
+      integer(c_int) :: crcl_recross_children
+   end function crcl_recross_children
+
+   ! umbrella worker body (calc_rate.f90:1387-1700)
+   function crcl_umbrella_window(h, q0, xi0, k_force, ntraj, equi_steps, sample_steps, traj_id0, &
+                                 avg, var, status) bind(C, name="crcl_umbrella_window")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), dimension(*), intent(in) :: q0
+      real(c_double), value :: xi0, k_force
+      integer(c_int), value :: ntraj, equi_steps, sample_steps, traj_id0
+      real(c_double), dimension(*), intent(out) :: avg, var
+      integer(c_int), dimension(*), intent(out) :: status
+      integer(c_int) :: crcl_umbrella_window
+   end function crcl_umbrella_window
+end interface
+
+contains
+
+!
+!     gpu_init: call once after read_pes / calc_rate_read (all globals below are set by then)
+!
+subroutine gpu_init(rank, pes_id)
+use general      ! natoms, mass(:), at_move(:), kelvin, thermostat, nose_q
+use evb_mod      ! nbeads, beta, andersen_step, bond_form, bond_break, form_ref, break_ref, ...
+integer, intent(in) :: rank, pes_id
+integer(c_int) :: rc, i, k, n
+integer(c_int), allocatable :: amove(:), bf(:), bb(:), atr(:)
+real(kind=8) :: dt_dummy
+allocate(amove(natoms))
+amove = 0
+do i = 1, natoms
+   if (at_move(i)) amove(i) = 1
+end do
+dt_dummy = 0.d0   ! the time step is passed per call through gpu_set_dt (drivers convert units late)
+rc = crcl_create(crcl_h, int(mod(rank, 8), c_int), int(natoms, c_int), int(nbeads, c_int), &
+                 mass(1:natoms), amove, beta, dt_dummy, int(pes_id, c_int))
+if (rc .ne. 0) then
+   write(*,*) "caracal_gpu: crcl_create failed with code", rc
+   call fatal
+end if
+! MECHA{} tables: bond_form(form_num,2) -> flattened pairs, at_reac(sum_reacs,200) -> concatenated
+allocate(bf(2*form_num), bb(2*break_num))
+do i = 1, form_num
+   bf(2*i-1) = bond_form(i,1); bf(2*i) = bond_form(i,2)
+end do
+do i = 1, break_num
+   bb(2*i-1) = bond_break(i,1); bb(2*i) = bond_break(i,2)
+end do
+n = sum(n_reac(1:sum_reacs))
+allocate(atr(n))
+n = 0
+do k = 1, sum_reacs
+   do i = 1, n_reac(k)
+      n = n + 1
+      atr(n) = at_reac(k,i)
+   end do
+end do
+rc = crcl_set_mechanism(crcl_h, int(form_num, c_int), bf, int(break_num, c_int), bb, form_ref, break_ref, &
+                        int(sum_reacs, c_int), int(n_reac(1:sum_reacs), c_int), atr, R_inf)
+rc = crcl_set_thermostat(crcl_h, int(thermostat, c_int), int(andersen_step, c_int), kelvin, nose_q)
+end subroutine gpu_init
+
+!
+!     verlet_gpu: same argument list as verlet (verlet.f90:65); operates on the module globals
+!     q_i, p_i like the original.  Drop-in for the call sites listed in INTEGRATION.md.
+!
+subroutine verlet_gpu(istep, dt, derivs, epot, ekin, afm_force, xi_ideal, xi_real, dxi_act, round, &
+                      constrain, analyze, rank)
+use general
+use evb_mod
+integer :: istep, round, constrain, rank
+real(kind=8) :: dt, epot, ekin, afm_force, xi_ideal, xi_real
+real(kind=8) :: derivs(3,natoms,nbeads), dxi_act(3,natoms)
+logical :: analyze
+integer(c_int) :: rc, st(1)
+real(c_double) :: xi1(1), kf1(1), ep1(1), xr1(1)
+rc = crcl_set_beta_dt(crcl_h, beta, dt)
+rc = crcl_set_thermostat(crcl_h, int(thermostat, c_int), int(andersen_step, c_int), kelvin, nose_q)
+xi1(1) = xi_ideal
+kf1(1) = 0.d0
+if (constrain .ge. 0) kf1(1) = k_force(um_window_act)
+st(1) = 0
+rc = crcl_verlet(crcl_h, 1_c_int, 1_c_int, int(istep-1, c_int), int(constrain, c_int), xi1, kf1, &
+                 q_i, p_i, derivs, ep1, xr1, dxi_act, st, c_null_ptr, c_null_ptr)
+epot = ep1(1)
+xi_real = xr1(1)
+if (rc .ne. 0 .or. iand(st(1), 2+4) .ne. 0) then
+   ! verlet.f90:1256-1275: NaN/Inf coordinate is fatal in the reference
+   write(*,*) "Something went wrong during the dynamics (GPU status", st(1), ")"
+   call fatal
+end if
+end subroutine verlet_gpu
+
+end module caracal_gpu
