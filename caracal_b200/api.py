@@ -115,6 +115,23 @@ class RPMD:
     def set_transform(self, mode):
         self._ck(self._lib.crcl_set_transform(self._h, int(mode)), "crcl_set_transform")
 
+    def set_path(self, path):
+        self._ck(self._lib.crcl_set_path(self._h, int(path)), "crcl_set_path")
+
+    def set_host_gradient(self, fn):
+        """fn(xyz[natoms,3]) -> (e, g[natoms,3]): the custom_grad / external_grad plug-in seam."""
+        natoms = self.natoms
+        CB = ctypes.CFUNCTYPE(None, _l.c_double_p, _l.c_double_p, _l.c_double_p, ctypes.c_int, ctypes.c_void_p)
+
+        def tramp(xyz, e, g, n, user):
+            x = np.ctypeslib.as_array(xyz, shape=(natoms, 3))
+            ev, gv = fn(x)
+            e[0] = float(ev)
+            np.ctypeslib.as_array(g, shape=(natoms, 3))[:] = gv
+        self._cb = CB(tramp)   # keep alive
+        self._ck(self._lib.crcl_set_host_gradient_cb(self._h, ctypes.cast(self._cb, ctypes.c_void_p), None),
+                 "crcl_set_host_gradient_cb")
+
     def set_mechanism(self, m):
         bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
         bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)
@@ -243,6 +260,13 @@ class RPMD:
         if n < 0:
             self._ck(n, "crcl_kernel_timings")
         return buf[:n].copy()
+
+    def bench_propagate(self, ntraj, reps=10):
+        """(mean ms, best ms, GB/s at the mean) of the split path's propagation kernel on resident data"""
+        out = np.zeros(2)
+        self._ck(self._lib.crcl_bench_propagate(self._h, int(ntraj), int(reps), _dp(out)), "crcl_bench_propagate")
+        gbs = 120.0 * ntraj * self.nbeads * self.natoms / (out[0] * 1e-3) / 1e9
+        return out[0], out[1], gbs
 
     def measure_fp64_tflops(self, iters=8192):
         return float(self._lib.crcl_measure_fp64_tflops(self._h, int(iters)))

@@ -1,6 +1,7 @@
 // api.cu -- C-ABI of libcaracal_gpu.so (include/caracal_gpu.h): handle management, host-side
 // set-up that the Fortran drivers do once (free ring-polymer kernels, mechanism tables), and
 // kernel dispatch.  No CPU compute path exists behind these entry points.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,7 @@
 #include "pes_oh3.cuh"
 #include "pes_ch4h.cuh"
 #include "traj_inst.cuh"
+#include "split_kernels.cuh"
 
 using namespace crcl;
 
@@ -34,6 +36,15 @@ struct crcl_handle_s {
     bool fker_dirty = true;
     crcl_host_grad_fn cb = nullptr;
     void* cb_user = nullptr;
+    int path = CRCL_PATH_AUTO;
+    // split path: per-atom tables on the device, generic-size mechanism
+    double *d_mass = nullptr, *d_wfrag = nullptr;
+    int *d_atmove = nullptr, *d_frag = nullptr;
+    MechDev mechd{};
+    bool mechd_valid = false;
+    std::vector<int> frag_h;
+    std::vector<double> wfrag_h;
+    std::vector<double> hostbuf_q, hostbuf_g, hostbuf_v;
     long long launches = 0;
     std::string err;
     // grow-only device scratch
@@ -287,6 +298,246 @@ static int pes_natoms(int pes)
     return -1;
 }
 
+// ---- split (HBM-resident) path ----------------------------------------------------------------
+namespace crcl {
+__global__ void sp_transrot_apply(const SplitArgs A, double mt, const double* sums)
+{
+    const int na = A.natoms, nb = A.nbeads, t = blockIdx.y;
+    const size_t nab = (size_t)na * nb;
+    const double* s = sums + (size_t)t * 16;
+    double totmass, vtot[3], ctr[3];
+    sp_centre(A, s, mt, totmass, vtot, ctr);
+    double mang[3];
+    mang[0] = s[6] - (ctr[1] * vtot[2] - ctr[2] * vtot[1]) * totmass;
+    mang[1] = s[7] - (ctr[2] * vtot[0] - ctr[0] * vtot[2]) * totmass;
+    mang[2] = s[8] - (ctr[0] * vtot[1] - ctr[1] * vtot[0]) * totmass;
+    const double xx = s[9], xy = s[10], xz = s[11], yy = s[12], yz = s[13], zz = s[14];
+    double ten[3][3] = {{yy + zz, -xy, -xz}, {-xy, xx + zz, -yz}, {-xz, -yz, xx + yy}};
+    if (na <= 2) {
+        ten[0][0] += 0.000001;
+        ten[1][1] += 0.000001;
+        ten[2][2] += 0.000001;
+    }
+    if (invert3(ten)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&A.status[t], CRCL_TRAJ_SINGULAR);
+        return;
+    }
+    double vang[3];
+    for (int i = 0; i < 3; i++) vang[i] = ten[i][0] * mang[0] + ten[i][1] * mang[1] + ten[i][2] * mang[2];
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nab; e += (size_t)gridDim.x * blockDim.x) {
+        const int atom = (int)(e % na);
+        const size_t k = ((size_t)t * nab + e) * 3;
+        const double w = A.mass[atom];
+        const bool mv = A.at_move[atom] != 0;
+        const double xd = A.q[k] - ctr[0], yd = A.q[k + 1] - ctr[1], zd = A.q[k + 2] - ctr[2];
+        const double v0 = (A.p[k] / w - vtot[0]) - vang[1] * zd + vang[2] * yd;
+        const double v1 = (A.p[k + 1] / w - vtot[1]) - vang[2] * xd + vang[0] * zd;
+        const double v2 = (A.p[k + 2] / w - vtot[2]) - vang[0] * yd + vang[1] * xd;
+        A.p[k] = mv ? v0 * w : 0.0;
+        A.p[k + 1] = mv ? v1 * w : 0.0;
+        A.p[k + 2] = mv ? v2 * w : 0.0;
+    }
+}
+}  // namespace crcl
+
+static bool fused_ok(crcl_handle h)
+{
+    const int nb = h->nbeads;
+    const bool pow2 = (nb & (nb - 1)) == 0 && nb <= 128;
+    return h->natoms <= TRAJ_MAXNAT && pow2 && pes_natoms(h->pes) == h->natoms;
+}
+static bool use_split(crcl_handle h)
+{
+    if (h->path == CRCL_PATH_SPLIT) return true;
+    if (h->path == CRCL_PATH_FUSED) return false;
+    return !fused_ok(h);
+}
+
+static int ensure_split_tables(crcl_handle h)
+{
+    if (h->d_mass) return CRCL_OK;
+    CK(cudaMalloc(&h->d_mass, h->natoms * sizeof(double)));
+    CK(cudaMalloc(&h->d_atmove, h->natoms * sizeof(int)));
+    CK(cudaMemcpy(h->d_mass, h->mass.data(), h->natoms * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_atmove, h->at_move.data(), h->natoms * sizeof(int), cudaMemcpyHostToDevice));
+    return CRCL_OK;
+}
+
+static int upload_mechd(crcl_handle h)
+{
+    if (!h->mechd_valid) return CRCL_OK;
+    if (h->d_frag) cudaFree(h->d_frag);
+    if (h->d_wfrag) cudaFree(h->d_wfrag);
+    CK(cudaMalloc(&h->d_frag, h->natoms * sizeof(int)));
+    CK(cudaMalloc(&h->d_wfrag, h->natoms * sizeof(double)));
+    CK(cudaMemcpy(h->d_frag, h->frag_h.data(), h->natoms * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_wfrag, h->wfrag_h.data(), h->natoms * sizeof(double), cudaMemcpyHostToDevice));
+    h->mechd.frag = h->d_frag;
+    h->mechd.wfrag = h->d_wfrag;
+    return CRCL_OK;
+}
+
+// PES for all images of the split path: device kernel for the analytic surfaces, otherwise the host
+// callback (custom_grad.f90:35 / external_grad.f90:33 seam): D2H positions, one call per image as
+// gradient.f90 does per bead (verlet.f90:772-777), H2D gradients.
+static int split_forces(crcl_handle h, int nimg, const double* dq, double* dg, double* dV)
+{
+    if (h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE)
+        return crcl_egrad_dev(h, h->pes, dq, h->natoms, nimg, dV, dg, nullptr);
+    if (!h->cb) return fail(h, CRCL_ESTATE, "PES is CRCL_PES_HOSTCB but crcl_set_host_gradient_cb was not called");
+    const size_t n = (size_t)nimg * 3 * h->natoms;
+    h->hostbuf_q.resize(n);
+    h->hostbuf_g.resize(n);
+    h->hostbuf_v.resize(nimg);
+    CK(cudaMemcpyAsync(h->hostbuf_q.data(), dq, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < nimg; i++)
+        h->cb(h->hostbuf_q.data() + (size_t)i * 3 * h->natoms, &h->hostbuf_v[i],
+              h->hostbuf_g.data() + (size_t)i * 3 * h->natoms, h->natoms, h->cb_user);
+    CK(cudaMemcpyAsync(dg, h->hostbuf_g.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dV, h->hostbuf_v.data(), nimg * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return CRCL_OK;
+}
+
+template <int NB>
+static void launch_kfr_reg(const SplitArgs& A, dim3 grid, cudaStream_t s)
+{
+    sp_kick_freerp_reg<NB><<<grid, 128, 0, s>>>(A);
+}
+
+static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
+{
+    const int nc = 3 * A.natoms;
+    dim3 grid((nc + 127) / 128, A.ntraj);
+    if (h->timed) {
+        next_event_pair(h);
+        cudaEventRecord(h->ev0, h->stream);
+    }
+    switch (A.nbeads) {
+    case 1: launch_kfr_reg<1>(A, grid, h->stream); break;
+    case 2: launch_kfr_reg<2>(A, grid, h->stream); break;
+    case 3: launch_kfr_reg<3>(A, grid, h->stream); break;
+    case 4: launch_kfr_reg<4>(A, grid, h->stream); break;
+    case 6: launch_kfr_reg<6>(A, grid, h->stream); break;
+    case 8: launch_kfr_reg<8>(A, grid, h->stream); break;
+    case 12: launch_kfr_reg<12>(A, grid, h->stream); break;
+    case 16: launch_kfr_reg<16>(A, grid, h->stream); break;
+    default: {
+        int bd = 128;
+        while (bd > 32 && (size_t)(3 * A.nbeads + 2 * (size_t)A.nbeads * bd) * sizeof(double) > 200 * 1024) bd >>= 1;
+        const size_t smem = (size_t)(3 * A.nbeads + 2 * (size_t)A.nbeads * bd) * sizeof(double);
+        if (smem > 200 * 1024) return fail(h, CRCL_ENOSUP, "split path: nbeads too large for the shared-memory transform");
+        CK(cudaFuncSetAttribute(sp_kick_freerp_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 g2((nc + bd - 1) / bd, A.ntraj);
+        sp_kick_freerp_smem<<<g2, bd, smem, h->stream>>>(A);
+    }
+    }
+    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    h->launches++;
+    CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
+// nsteps verlet steps on device-resident state (split path).  Supported this round: constrain -1
+// (plain MD incl. transrot) and 2 (child trajectory); thermostat 0 / 1.
+static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain, const double* d_xi_ideal,
+                        double xi_ideal_s, double* dq, double* dp, double* dg, double* dep, double* dxr, int* dst,
+                        const uint32_t* dtid, uint32_t* dev)
+{
+    if (constrain != -1 && constrain != 2)
+        return fail(h, CRCL_ENOSUP, "split path: constrain 0/1 (umbrella, SHAKE) not implemented yet");
+    if (h->thermostat == 2) return fail(h, CRCL_ENOSUP, "split path: Nose-Hoover chain not implemented yet");
+    if (constrain == 2 && !h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    int rc;
+    if ((rc = ensure_split_tables(h)) || (rc = ensure_fker(h))) return rc;
+    const int na = h->natoms, nb = h->nbeads, nc = 3 * na;
+    const size_t per = (size_t)nb * nc;
+    double *dcen, *dV, *dsums;
+    if ((rc = scratch(h, 8, (size_t)ntraj * nc, &dcen)) || (rc = scratch(h, 9, (size_t)ntraj * nb, &dV)) ||
+        (rc = scratch(h, 10, (size_t)ntraj * 16, &dsums)))
+        return rc;
+    SplitArgs A;
+    A.ntraj = ntraj;
+    A.natoms = na;
+    A.nbeads = nb;
+    A.symmetrize = (h->transform == CRCL_TRANSFORM_REFERENCE) ? 1 : 0;
+    A.dt = h->dt;
+    A.beta = h->beta;
+    A.mass = h->d_mass;
+    A.at_move = h->d_atmove;
+    A.fker = h->d_fker;
+    A.q = dq;
+    A.p = dp;
+    A.g = dg;
+    A.cen = dcen;
+    A.status = dst;
+    A.seed = h->seed;
+    A.traj_id = dtid;
+    A.traj_id0 = 0;
+    A.event = dev;
+    double mt = 0.0;
+    for (int i = 0; i < na; i++) mt += h->mass[i];
+    cudaStream_t s = h->stream;
+    const dim3 gel((unsigned)((per + 255) / 256), ntraj);
+    const int rblocks = (int)std::min<size_t>(64, ((size_t)na * nb + 255) / 256);
+    for (int st = 1; st <= nsteps; st++) {
+        const int istep = istep0 + st;
+        if ((rc = launch_kick_freerp(h, A))) return rc;                       // 2,3,4,6,7
+        if ((rc = split_forces(h, ntraj * nb, dq, dg, dV))) return rc;        // 10
+        sp_epot<<<(ntraj + 127) / 128, 128, 0, s>>>(dV, nb, ntraj, dep);
+        if (constrain == 2)                                                   // 12
+            sp_xi_value<<<(ntraj + 63) / 64, 64, 0, s>>>(h->mechd, na, ntraj, dcen, d_xi_ideal, xi_ideal_s, 2, dxr);
+        sp_kick<<<gel, 256, 0, s>>>(A);                                       // 13, 18
+        h->launches += 2 + (constrain == 2);
+        if (constrain != 2 && h->thermostat == 1 && h->andersen_step > 0 && (istep % h->andersen_step) == 0) {
+            sp_andersen<<<gel, 256, 0, s>>>(A);                               // 16
+            sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(dev, ntraj);
+            h->launches += 2;
+        }
+        if (constrain <= 0) {                                                 // 19
+            CK(cudaMemsetAsync(dsums, 0, (size_t)ntraj * 16 * sizeof(double), s));
+            sp_transrot_sums1<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, dsums);
+            sp_transrot_sums2<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, mt, dsums);
+            sp_transrot_apply<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, mt, dsums);
+            h->launches += 3;
+        }
+        CK(cudaGetLastError());
+    }
+    return CRCL_OK;
+}
+
+// mdinit on the split path (bias_mode 0 only): forces of all beads + Andersen draw
+static int mdinit_split(crcl_handle h, int ntraj, int bias_mode, double* dq, double* dp, double* dg,
+                        const uint32_t* dtid, uint32_t* dev)
+{
+    if (bias_mode != 0) return fail(h, CRCL_ENOSUP, "split path: mdinit bias_mode 1/2 not implemented yet");
+    if (h->thermostat == 2) return fail(h, CRCL_ENOSUP, "split path: Nose-Hoover chain not implemented yet");
+    int rc;
+    if ((rc = ensure_split_tables(h))) return rc;
+    const int na = h->natoms, nb = h->nbeads;
+    const size_t per = (size_t)nb * 3 * na;
+    double* dV;
+    if ((rc = scratch(h, 9, (size_t)ntraj * nb, &dV))) return rc;
+    if ((rc = split_forces(h, ntraj * nb, dq, dg, dV))) return rc;
+    SplitArgs A{};
+    A.ntraj = ntraj;
+    A.natoms = na;
+    A.nbeads = nb;
+    A.beta = h->beta;
+    A.mass = h->d_mass;
+    A.at_move = h->d_atmove;
+    A.p = dp;
+    A.seed = h->seed;
+    A.traj_id = dtid;
+    A.event = dev;
+    const dim3 gel((unsigned)((per + 255) / 256), ntraj);
+    sp_andersen<<<gel, 256, 0, h->stream>>>(A);
+    sp_bump_event<<<(ntraj + 127) / 128, 128, 0, h->stream>>>(dev, ntraj);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
 // ---- C-ABI -----------------------------------------------------------------------------------
 extern "C" {
 
@@ -336,6 +587,10 @@ int crcl_destroy(crcl_handle h)
     for (auto& s : h->scratch)
         if (s) cudaFree(s);
     if (h->d_fker) cudaFree(h->d_fker);
+    if (h->d_mass) cudaFree(h->d_mass);
+    if (h->d_atmove) cudaFree(h->d_atmove);
+    if (h->d_frag) cudaFree(h->d_frag);
+    if (h->d_wfrag) cudaFree(h->d_wfrag);
     for (auto& e : h->evs)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(h->own_stream);
@@ -388,11 +643,65 @@ int crcl_set_mechanism(crcl_handle h, int form_num, const int* bond_form, int br
                        int sum_reacs, const int* n_reac, const int* at_reac, double R_inf)
 {
     if (!h) return CRCL_EINVAL;
-    const int rc = build_mech(h->mech, h->natoms, h->mass.data(), form_num, bond_form, break_num, bond_break,
-                              form_ref, break_ref, sum_reacs, n_reac, at_reac, R_inf);
-    if (rc == -1)
-        return fail(h, CRCL_ENOSUP, "mechanism exceeds the in-register limits (bonds<=4, fragments<=4, atoms<=8)");
-    if (rc == -2) return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    if (!bond_form && form_num > 0) return CRCL_EINVAL;
+    // generic-size tables for the split path (any natoms; <= 8 bonds of each kind, <= 4 fragments)
+    if (form_num < 0 || break_num < 0 || form_num > 8 || break_num > 8 || sum_reacs < 2 || sum_reacs > 4)
+        return fail(h, CRCL_ENOSUP, "mechanism limits: <= 8 forming / breaking bonds, 2..4 reactant fragments");
+    MechDev& D = h->mechd;
+    D = MechDev();
+    D.form_num = form_num;
+    D.break_num = break_num;
+    D.sum_reacs = sum_reacs;
+    for (int i = 0; i < form_num; i++) {
+        D.bf[i][0] = bond_form[2 * i] - 1;
+        D.bf[i][1] = bond_form[2 * i + 1] - 1;
+        D.fref[i] = form_ref[i];
+        if (D.bf[i][0] < 0 || D.bf[i][0] >= h->natoms || D.bf[i][1] < 0 || D.bf[i][1] >= h->natoms)
+            return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    }
+    for (int i = 0; i < break_num; i++) {
+        D.bb[i][0] = bond_break[2 * i] - 1;
+        D.bb[i][1] = bond_break[2 * i + 1] - 1;
+        D.bref[i] = break_ref[i];
+        if (D.bb[i][0] < 0 || D.bb[i][0] >= h->natoms || D.bb[i][1] < 0 || D.bb[i][1] >= h->natoms)
+            return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    }
+    h->frag_h.assign(h->natoms, -1);
+    h->wfrag_h.assign(h->natoms, 0.0);
+    {
+        int off = 0;
+        double mr[4] = {0, 0, 0, 0};
+        for (int k = 0; k < sum_reacs; k++) {
+            for (int i = 0; i < n_reac[k]; i++) {
+                const int a = at_reac[off + i] - 1;
+                if (a < 0 || a >= h->natoms) return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+                h->frag_h[a] = k;
+                mr[k] += h->mass[a];
+            }
+            off += n_reac[k];
+        }
+        for (int a = 0; a < h->natoms; a++)
+            if (h->frag_h[a] >= 0) h->wfrag_h[a] = h->mass[a] / mr[h->frag_h[a]];
+    }
+    D.R_inf = R_inf;
+    h->mechd_valid = true;
+    CK(cudaSetDevice(h->device));
+    int rc2 = upload_mechd(h);
+    if (rc2) return rc2;
+    // in-register tables of the fused kernels (small systems only)
+    h->mech.valid = 0;
+    if (h->natoms <= XI_MAXAT && form_num <= XI_MAXBOND && break_num <= XI_MAXBOND) {
+        const int rc = build_mech(h->mech, h->natoms, h->mass.data(), form_num, bond_form, break_num, bond_break,
+                                  form_ref, break_ref, sum_reacs, n_reac, at_reac, R_inf);
+        if (rc == -2) return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    }
+    return CRCL_OK;
+}
+
+int crcl_set_path(crcl_handle h, int path)
+{
+    if (!h || path < CRCL_PATH_AUTO || path > CRCL_PATH_SPLIT) return CRCL_EINVAL;
+    h->path = path;
     return CRCL_OK;
 }
 
@@ -468,9 +777,11 @@ int crcl_egrad(crcl_handle h, int pes_id, const double* q, int natoms, int nimg,
 static int check_traj_call(crcl_handle h, int constrain)
 {
     if (!h) return CRCL_EINVAL;
-    if (h->natoms > TRAJ_MAXNAT) return fail(h, CRCL_ENOSUP, "natoms exceeds the in-register trajectory path");
     if (constrain < -1 || constrain > 3) return fail(h, CRCL_EINVAL, "constrain must be -1..3");
-    if (constrain >= 0 && !h->mech.valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    if (h->path == CRCL_PATH_FUSED && !fused_ok(h))
+        return fail(h, CRCL_ENOSUP, "fused trajectory kernels need <= 8 atoms, a device PES and power-of-two nbeads <= 128");
+    if (constrain >= 0 && !use_split(h) && !h->mech.valid)
+        return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
     return CRCL_OK;
 }
 
@@ -528,7 +839,18 @@ int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
     A.nhc = dnhc;  // NHC chain state persists on the device between calls of one handle
     A.traj_id = traj_id ? dtid : nullptr;
     A.event = dev;
-    if ((rc = launch_traj(h, K_VERLET, A))) return rc;
+    if (use_split(h)) {
+        if (!traj_id) {
+            std::vector<uint32_t> ids(ntraj);
+            for (int t = 0; t < ntraj; t++) ids[t] = (uint32_t)t;
+            CK(cudaMemcpyAsync(dtid, ids.data(), ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if ((rc = verlet_split(h, ntraj, nsteps, istep0, constrain, xi_ideal ? dxid : nullptr,
+                               xi_ideal ? 0.0 : 0.0, dq, dp, dg, dep, dxr, dst, dtid, dev)))
+            return rc;
+    } else if ((rc = launch_traj(h, K_VERLET, A)))
+        return rc;
     CK(cudaMemcpyAsync(q, dq, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(p, dp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(derivs, dg, n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -581,7 +903,16 @@ int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double* xi_ideal,
     A.nhc = dnhc;
     A.traj_id = traj_id ? dtid : nullptr;
     A.event = dev;
-    if ((rc = launch_traj(h, K_MDINIT, A, bias_mode))) return rc;
+    if (use_split(h)) {
+        if (!traj_id) {
+            std::vector<uint32_t> ids(ntraj);
+            for (int t = 0; t < ntraj; t++) ids[t] = (uint32_t)t;
+            CK(cudaMemcpyAsync(dtid, ids.data(), ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        if ((rc = mdinit_split(h, ntraj, bias_mode, dq, dp, dg, dtid, dev))) return rc;
+    } else if ((rc = launch_traj(h, K_MDINIT, A, bias_mode)))
+        return rc;
     CK(cudaMemcpyAsync(p, dp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(derivs, dg, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dxi && bias_mode) CK(cudaMemcpyAsync(dxi, ddxi, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -788,6 +1119,54 @@ int crcl_rng_normals(crcl_handle h, uint64_t seed, uint32_t traj, uint32_t event
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return CRCL_OK;
+}
+
+int crcl_bench_propagate(crcl_handle h, int ntraj, int reps, double* ms_out)
+{
+    if (!h || ntraj <= 0 || reps <= 0 || !ms_out) return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_split_tables(h)) || (rc = ensure_fker(h))) return rc;
+    const int na = h->natoms, nb = h->nbeads, nc = 3 * na;
+    const size_t n = (size_t)ntraj * nb * nc;
+    double *dq, *dp, *dg, *dcen;
+    int* dst;
+    if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
+        (rc = scratch(h, 8, (size_t)ntraj * nc, &dcen)) || (rc = scratch(h, 5, (size_t)ntraj, &dst)))
+        return rc;
+    // finite, non-trivial contents: zero momenta/forces, positions = byte pattern 0x3f (1.2e-4 ...)
+    CK(cudaMemsetAsync(dq, 0x3f, n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(dp, 0, n * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(dg, 0, n * sizeof(double), h->stream));
+    SplitArgs A{};
+    A.ntraj = ntraj;
+    A.natoms = na;
+    A.nbeads = nb;
+    A.symmetrize = (h->transform == CRCL_TRANSFORM_REFERENCE) ? 1 : 0;
+    A.dt = h->dt;
+    A.beta = h->beta;
+    A.mass = h->d_mass;
+    A.at_move = h->d_atmove;
+    A.fker = h->d_fker;
+    A.q = dq;
+    A.p = dp;
+    A.g = dg;
+    A.cen = dcen;
+    A.status = dst;
+    double best = 1e30, sum = 0.0;
+    for (int r = 0; r < reps + 2; r++) {
+        if ((rc = launch_kick_freerp(h, A))) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (r >= 2) {
+            sum += ms;
+            if (ms < best) best = ms;
+        }
+    }
+    ms_out[0] = sum / reps;
+    ms_out[1] = best;
     return CRCL_OK;
 }
 

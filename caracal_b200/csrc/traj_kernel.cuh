@@ -144,55 +144,6 @@ struct SmemLayout {
     }
 };
 
-// 3x3 inverse by Gauss-Jordan with full pivoting, as invert.f90:38-123; returns 1 if singular
-__device__ __forceinline__ int invert3(double a[3][3])
-{
-    int ipivot[3] = {0, 0, 0}, indxr[3], indxc[3];
-    int irow = 0, icol = 0;
-    for (int i = 0; i < 3; i++) {
-        double big = 0.0;
-        for (int j = 0; j < 3; j++)
-            if (ipivot[j] != 1)
-                for (int k = 0; k < 3; k++) {
-                    if (ipivot[k] == 0) {
-                        if (fabs(a[j][k]) >= big) {
-                            big = fabs(a[j][k]);
-                            irow = j;
-                            icol = k;
-                        }
-                    } else if (ipivot[k] > 1)
-                        return 1;
-                }
-        ipivot[icol]++;
-        if (irow != icol)
-            for (int j = 0; j < 3; j++) {
-                const double t = a[irow][j];
-                a[irow][j] = a[icol][j];
-                a[icol][j] = t;
-            }
-        indxr[i] = irow;
-        indxc[i] = icol;
-        if (a[icol][icol] == 0.0) return 1;
-        const double pivot = a[icol][icol];
-        a[icol][icol] = 1.0;
-        for (int j = 0; j < 3; j++) a[icol][j] /= pivot;
-        for (int j = 0; j < 3; j++)
-            if (j != icol) {
-                const double t = a[j][icol];
-                a[j][icol] = 0.0;
-                for (int k = 0; k < 3; k++) a[j][k] -= a[icol][k] * t;
-            }
-    }
-    for (int i = 2; i >= 0; i--)
-        if (indxr[i] != indxc[i])
-            for (int k = 0; k < 3; k++) {
-                const double t = a[k][indxr[i]];
-                a[k][indxr[i]] = a[k][indxc[i]];
-                a[k][indxc[i]] = t;
-            }
-    return 0;
-}
-
 // Per-thread view of a trajectory.  Every thread owns up to NOWN components c = atom*3+xyz of
 // its bead (all of them when LANES == 1); momenta and positions of the whole trajectory live in
 // shared memory as {p,q}[c][bead], the forces of the owned components in registers.

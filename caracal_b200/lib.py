@@ -18,6 +18,7 @@ PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_HOSTCB = 0, 1, 2, 3, 100
 PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H}
 PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6}
 TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
+PATH_AUTO, PATH_FUSED, PATH_SPLIT = 0, 1, 2
 ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM", -4: "CRCL_ECUDA",
           -5: "CRCL_ENOSUP", -6: "CRCL_ESTATE"}
 TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_PESWARN = 0, 1, 2, 5, 16
@@ -34,6 +35,7 @@ SIGNATURES = {
     "crcl_set_beta_dt": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double]),
     "crcl_set_transform": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_host_gradient_cb": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "crcl_set_path": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                           ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),
     "crcl_set_thermostat": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "crcl_launch_count": (ctypes.c_longlong, [_H]),
     "crcl_last_kernel_ms": (ctypes.c_double, [_H]),
     "crcl_kernel_timings": (ctypes.c_int, [_H, c_double_p, ctypes.c_int]),
+    "crcl_bench_propagate": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p]),
     "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
 }
 

@@ -57,6 +57,12 @@ extern "C" {
 #define CRCL_TRANSFORM_REFERENCE 0 /* rfft.f90/irfft.f90 as written: Re(DFT)/sqrt(N) both ways */
 #define CRCL_TRANSFORM_EXACT 1     /* orthonormal normal-mode transform (physics)             */
 
+/* integrator code path */
+#define CRCL_PATH_AUTO 0  /* fused in-register kernels when the system fits, else split */
+#define CRCL_PATH_FUSED 1 /* <= 8 atoms, device PES, power-of-two nbeads <= 128           */
+#define CRCL_PATH_SPLIT 2 /* HBM-resident state, one kernel per stage, any natoms/nbeads,
+                             device PES or host callback; constrain -1 / 2, thermostat 0 / 1 */
+
 typedef struct crcl_handle_s *crcl_handle;
 
 /* replaces custom_grad(xyz2,e_evb,g_evb) (custom_grad.f90:35) / external_grad as the
@@ -82,6 +88,7 @@ int crcl_synchronize(crcl_handle h);
 int crcl_set_beta_dt(crcl_handle h, double beta, double dt);
 int crcl_set_transform(crcl_handle h, int mode);
 int crcl_set_host_gradient_cb(crcl_handle h, crcl_host_grad_fn fn, void *user);
+int crcl_set_path(crcl_handle h, int path);
 
 /* MECHA{} section, BIMOLEC family (calc_rate_read.f90:430-870, bonds_ref.f90): 1-based
  * atom pairs bond_form(form_num,2), bond_break(break_num,2) flattened row-wise; reference
@@ -165,6 +172,10 @@ double crcl_last_kernel_ms(crcl_handle h);
  * egrad kernels launched since the previous call, oldest first, at most max_n (ring of 256);
  * synchronises the stream; returns the number written */
 int crcl_kernel_timings(crcl_handle h, double *ms_out, int max_n);
+/* times the split path's propagation kernel (half kick + free ring polymer + centroid) alone on
+ * ntraj synthetic trajectories resident in HBM: ms_out[0] = mean, ms_out[1] = best of reps launches.
+ * Algorithmic traffic is 120 B per (trajectory, bead, atom). */
+int crcl_bench_propagate(crcl_handle h, int ntraj, int reps, double *ms_out);
 /* sustained FP64 FMA throughput of the device in TFLOP/s (DFMA microbenchmark, used as the
  * roofline denominator because MEASURED_PEAKS.json has no FP64 entry) */
 double crcl_measure_fp64_tflops(crcl_handle h, int iters);

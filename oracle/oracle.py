@@ -153,6 +153,20 @@ class System:
     def set_thermostat(self, thermostat, andersen_step=0, kelvin=0.0, nose_q=0.0):
         self.L.oracle_sys_set_thermostat(self.h, thermostat, andersen_step, kelvin, nose_q)
 
+    def set_custom_grad(self, fn):
+        """fn(xyz[natoms,3]) -> (e, g[natoms,3]); the custom_grad.f90:35 plug-in slot"""
+        natoms = self.natoms
+        CB = ctypes.CFUNCTYPE(None, dp, dp, dp, ctypes.c_int)
+
+        def tramp(xyz, e, g, n):
+            x = np.ctypeslib.as_array(xyz, shape=(natoms, 3))
+            ev, gv = fn(x)
+            e[0] = float(ev)
+            np.ctypeslib.as_array(g, shape=(natoms, 3))[:] = gv
+        self._cb = CB(tramp)
+        self.L.oracle_sys_set_custom_grad.argtypes = [ctypes.c_void_p, CB]
+        self.L.oracle_sys_set_custom_grad(self.h, self._cb)
+
     def set_kforce(self, k):
         self.L.oracle_sys_set_kforce(self.h, k)
 
