@@ -302,7 +302,7 @@ static int pes_natoms(int pes)
 namespace crcl {
 __global__ void sp_transrot_apply(const SplitArgs A, double mt, const double* sums)
 {
-    const int na = A.natoms, nb = A.nbeads, t = blockIdx.y;
+    const int na = A.natoms, nb = A.nbeads, rb = gridDim.x / A.ntraj, t = blockIdx.x / rb, bx = blockIdx.x - t * rb;
     const size_t nab = (size_t)na * nb;
     const double* s = sums + (size_t)t * 16;
     double totmass, vtot[3], ctr[3];
@@ -319,12 +319,12 @@ __global__ void sp_transrot_apply(const SplitArgs A, double mt, const double* su
         ten[2][2] += 0.000001;
     }
     if (invert3(ten)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&A.status[t], CRCL_TRAJ_SINGULAR);
+        if (bx == 0 && threadIdx.x == 0) atomicOr(&A.status[t], CRCL_TRAJ_SINGULAR);
         return;
     }
     double vang[3];
     for (int i = 0; i < 3; i++) vang[i] = ten[i][0] * mang[0] + ten[i][1] * mang[1] + ten[i][2] * mang[2];
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nab; e += (size_t)gridDim.x * blockDim.x) {
+    for (size_t e = (size_t)bx * blockDim.x + threadIdx.x; e < nab; e += (size_t)rb * blockDim.x) {
         const int atom = (int)(e % na);
         const size_t k = ((size_t)t * nab + e) * 3;
         const double w = A.mass[atom];
@@ -408,7 +408,7 @@ static void launch_kfr_reg(const SplitArgs& A, dim3 grid, cudaStream_t s)
 static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
 {
     const int nc = 3 * A.natoms;
-    dim3 grid((nc + 127) / 128, A.ntraj);
+    dim3 grid((unsigned)((size_t)((nc + 127) / 128) * A.ntraj));
     if (h->timed) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
@@ -428,7 +428,7 @@ static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
         const size_t smem = (size_t)(3 * A.nbeads + 2 * (size_t)A.nbeads * bd) * sizeof(double);
         if (smem > 200 * 1024) return fail(h, CRCL_ENOSUP, "split path: nbeads too large for the shared-memory transform");
         CK(cudaFuncSetAttribute(sp_kick_freerp_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 g2((nc + bd - 1) / bd, A.ntraj);
+        dim3 g2((unsigned)((size_t)((nc + bd - 1) / bd) * A.ntraj));
         sp_kick_freerp_smem<<<g2, bd, smem, h->stream>>>(A);
     }
     }
@@ -478,7 +478,7 @@ static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int co
     double mt = 0.0;
     for (int i = 0; i < na; i++) mt += h->mass[i];
     cudaStream_t s = h->stream;
-    const dim3 gel((unsigned)((per + 255) / 256), ntraj);
+    const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
     const int rblocks = (int)std::min<size_t>(64, ((size_t)na * nb + 255) / 256);
     for (int st = 1; st <= nsteps; st++) {
         const int istep = istep0 + st;
@@ -496,9 +496,9 @@ static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int co
         }
         if (constrain <= 0) {                                                 // 19
             CK(cudaMemsetAsync(dsums, 0, (size_t)ntraj * 16 * sizeof(double), s));
-            sp_transrot_sums1<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, dsums);
-            sp_transrot_sums2<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, mt, dsums);
-            sp_transrot_apply<<<dim3(rblocks, ntraj), 128, 0, s>>>(A, mt, dsums);
+            sp_transrot_sums1<<<rblocks * ntraj, 128, 0, s>>>(A, dsums);
+            sp_transrot_sums2<<<rblocks * ntraj, 128, 0, s>>>(A, mt, dsums);
+            sp_transrot_apply<<<rblocks * ntraj, 128, 0, s>>>(A, mt, dsums);
             h->launches += 3;
         }
         CK(cudaGetLastError());
@@ -530,7 +530,7 @@ static int mdinit_split(crcl_handle h, int ntraj, int bias_mode, double* dq, dou
     A.seed = h->seed;
     A.traj_id = dtid;
     A.event = dev;
-    const dim3 gel((unsigned)((per + 255) / 256), ntraj);
+    const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
     sp_andersen<<<gel, 256, 0, h->stream>>>(A);
     sp_bump_event<<<(ntraj + 127) / 128, 128, 0, h->stream>>>(dev, ntraj);
     h->launches += 2;

@@ -44,8 +44,9 @@ template <int NB>
 __global__ void __launch_bounds__(128) sp_kick_freerp_reg(const SplitArgs A)
 {
     const int nc = 3 * A.natoms;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int tiles = gridDim.x / A.ntraj;   // 1-D grid: block = traj * tiles + tile
+    const int t = blockIdx.x / tiles;
+    const int c = (blockIdx.x - t * tiles) * blockDim.x + threadIdx.x;
     if (c >= nc) return;
     const int atom = c / 3;
     const double m = A.mass[atom];
@@ -120,8 +121,9 @@ __global__ void sp_kick_freerp_smem(const SplitArgs A)
     for (int i = threadIdx.x; i < 3 * NB; i += BD) fk[i] = A.fker[i];
     __syncthreads();
     const int nc = 3 * A.natoms;
-    const int c = blockIdx.x * BD + threadIdx.x;
-    const int t = blockIdx.y;
+    const int tiles = gridDim.x / A.ntraj;
+    const int t = blockIdx.x / tiles;
+    const int c = (blockIdx.x - t * tiles) * BD + threadIdx.x;
     if (c >= nc) return;
     const int atom = c / 3, x = threadIdx.x;
     const double m = A.mass[atom], im = 1.0 / m;
@@ -175,8 +177,9 @@ __global__ void sp_kick(const SplitArgs A)
 {
     const int nc = 3 * A.natoms;
     const size_t per = (size_t)A.nbeads * nc;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int tiles = gridDim.x / A.ntraj;
+    const int t = blockIdx.x / tiles;
+    const size_t i = (size_t)(blockIdx.x - t * tiles) * blockDim.x + threadIdx.x;
     if (i >= per) return;
     const int atom = (int)(i % nc) / 3;
     const size_t k = (size_t)t * per + i;
@@ -191,8 +194,9 @@ __global__ void sp_andersen(const SplitArgs A)
 {
     const int nc = 3 * A.natoms;
     const size_t per = (size_t)A.nbeads * nc;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y;
+    const int tiles = gridDim.x / A.ntraj;
+    const int t = blockIdx.x / tiles;
+    const size_t i = (size_t)(blockIdx.x - t * tiles) * blockDim.x + threadIdx.x;
     if (i >= per) return;
     const int bead = (int)(i / nc), mcomp = (int)(i % nc);
     const uint32_t tid = A.traj_id ? A.traj_id[t] : A.traj_id0 + (uint32_t)t;
@@ -266,10 +270,10 @@ __global__ void sp_xi_value(MechDev M, int natoms, int ntraj, const double* cen,
 // pass 3: apply
 __global__ void sp_transrot_sums1(const SplitArgs A, double* sums)
 {
-    const int na = A.natoms, nb = A.nbeads, t = blockIdx.y;
+    const int na = A.natoms, nb = A.nbeads, rb = gridDim.x / A.ntraj, t = blockIdx.x / rb, bx = blockIdx.x - t * rb;
     const size_t nab = (size_t)na * nb;
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nab; e += (size_t)gridDim.x * blockDim.x) {
+    for (size_t e = (size_t)bx * blockDim.x + threadIdx.x; e < nab; e += (size_t)rb * blockDim.x) {
         const int atom = (int)(e % na);
         const size_t k = ((size_t)t * nab + e) * 3;
         const double w = A.mass[atom];
@@ -310,12 +314,12 @@ __device__ __forceinline__ void sp_centre(const SplitArgs& A, const double* s, d
 }
 __global__ void sp_transrot_sums2(const SplitArgs A, double mt, double* sums)
 {
-    const int na = A.natoms, nb = A.nbeads, t = blockIdx.y;
+    const int na = A.natoms, nb = A.nbeads, rb = gridDim.x / A.ntraj, t = blockIdx.x / rb, bx = blockIdx.x - t * rb;
     const size_t nab = (size_t)na * nb;
     double totmass, vtot[3], ctr[3];
     sp_centre(A, sums + (size_t)t * 16, mt, totmass, vtot, ctr);
     double s[6] = {0, 0, 0, 0, 0, 0};
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nab; e += (size_t)gridDim.x * blockDim.x) {
+    for (size_t e = (size_t)bx * blockDim.x + threadIdx.x; e < nab; e += (size_t)rb * blockDim.x) {
         const int atom = (int)(e % na);
         const size_t k = ((size_t)t * nab + e) * 3;
         const double w = A.mass[atom];

@@ -148,7 +148,16 @@ def test_nan_status_is_reported_not_fatal(gpu):
 
 
 def test_unsupported_bead_count_is_an_error(gpu):
+    """12 beads do not fit the fused kernels: an explicit error when that path is forced, the split
+    path when the choice is left to the library"""
     g = gpu.RPMD("h3", 12, C.masses("h3"), C.beta_calc_rate(300.0), C.dt_au(0.1))
-    q = np.zeros((1, 12, 3, 3))
+    q = np.array([C.ring_polymer("h3", 12, np.random.default_rng(0))])
+    g.set_path(gpu.PATH_FUSED)
     with pytest.raises(gpu.CaracalGpuError, match="ENOSUP"):
         g.mdinit(q)
+    g.set_path(gpu.PATH_AUTO)
+    p, d, dxi, ev = g.mdinit(q)
+    assert np.isfinite(p).all() and np.abs(p).max() > 0
+    # stages the split path does not cover yet are refused, not silently skipped
+    with pytest.raises(gpu.CaracalGpuError, match="ENOSUP"):
+        g.verlet(q, p, d, nsteps=1, constrain=1, xi_ideal=0.9, k_force=1.0)
