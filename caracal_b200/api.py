@@ -132,6 +132,33 @@ class RPMD:
         self._ck(self._lib.crcl_set_host_gradient_cb(self._h, ctypes.cast(self._cb, ctypes.c_void_p), None),
                  "crcl_set_host_gradient_cb")
 
+    def set_qmdff(self, T):
+        """T: dict of QMDFF tables named as in the reference's module qmdff (see crcl_qmdff_tables)."""
+        keep = {}
+
+        def arr(key, dtype):
+            order = "F" if key in ("c6xy", "r0ab", "zab", "r094", "sr42") else "C"
+            keep[key] = np.array(T[key], dtype=dtype, order=order)
+            return keep[key]
+        S = _l.QmdffTables()
+        S.n, S.nmols = int(T["n"]), int(T["nmols"])
+        S.at, S.q, S.molnum = _ip(arr("at", np.int32)), _dp(arr("q", np.float64)), _ip(arr("molnum", np.int32))
+        S.nbond, S.nangl, S.ntors, S.nnci = len(T["bond"]), len(T["angl"]), len(T["tors"]), len(T["nci"])
+        S.nhb, S.ldvt = int(T.get("nhb", 0)), int(T["ldvt"])
+        S.bond, S.vbond = _ip(arr("bond", np.int32)), _dp(arr("vbond", np.float64))
+        S.angl, S.vangl = _ip(arr("angl", np.int32)), _dp(arr("vangl", np.float64))
+        S.tors, S.vtors = _ip(arr("tors", np.int32)), _dp(arr("vtors", np.float64))
+        S.nci = _ip(arr("nci", np.int32))
+        for k in ("c6xy", "r0ab", "zab", "r094", "sr42", "rad"):
+            setattr(S, k, _dp(arr(k, np.float64)))
+        S.eps1 = (ctypes.c_double * 6)(*T["eps1"])
+        S.eps2 = (ctypes.c_double * 6)(*T["eps2"])
+        S.periodic, S.zahn = int(T["periodic"]), int(T["zahn"])
+        S.box = (ctypes.c_double * 3)(*T["box"])
+        S.coul_cut, S.vdw_cut, S.cut_low = float(T["coul_cut"]), float(T["vdw_cut"]), float(T["cut_low"])
+        S.zahn_a, S.zahn_par, S.e_zero = float(T["zahn_a"]), float(T["zahn_par"]), float(T["e_zero"])
+        self._ck(self._lib.crcl_set_qmdff(self._h, ctypes.byref(S)), "crcl_set_qmdff")
+
     def set_mechanism(self, m):
         bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
         bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)

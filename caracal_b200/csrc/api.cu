@@ -14,6 +14,7 @@
 #include "pes_ch4h.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
+#include "qmdff.cuh"
 
 using namespace crcl;
 
@@ -37,6 +38,7 @@ struct crcl_handle_s {
     crcl_host_grad_fn cb = nullptr;
     void* cb_user = nullptr;
     int path = CRCL_PATH_AUTO;
+    QmdffDev* qmdff = nullptr;
     // split path: per-atom tables on the device, generic-size mechanism
     double *d_mass = nullptr, *d_wfrag = nullptr;
     int *d_atmove = nullptr, *d_frag = nullptr;
@@ -548,7 +550,7 @@ int crcl_create(crcl_handle* out, int device, int natoms, int nbeads, const doub
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CRCL_ENODEV;
     if (device < 0 || device >= ndev) return CRCL_EINVAL;
-    if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE) {
+    if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE && pes_id != CRCL_PES_QMDFF) {
         const int n = pes_natoms(pes_id);
         if (n < 0 || n != natoms) return CRCL_EINVAL;
     }
@@ -587,6 +589,7 @@ int crcl_destroy(crcl_handle h)
     for (auto& s : h->scratch)
         if (s) cudaFree(s);
     if (h->d_fker) cudaFree(h->d_fker);
+    qmdff_free(h->qmdff);
     if (h->d_mass) cudaFree(h->d_mass);
     if (h->d_atmove) cudaFree(h->d_atmove);
     if (h->d_frag) cudaFree(h->d_frag);
@@ -698,6 +701,19 @@ int crcl_set_mechanism(crcl_handle h, int form_num, const int* bond_form, int br
     return CRCL_OK;
 }
 
+int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables* T)
+{
+    if (!h || !T) return CRCL_EINVAL;
+    if (T->n != h->natoms) return fail(h, CRCL_EINVAL, "crcl_set_qmdff: T->n differs from the handle's natoms");
+    CK(cudaSetDevice(h->device));
+    qmdff_free(h->qmdff);
+    h->qmdff = nullptr;
+    const char* msg = "";
+    const int rc = qmdff_upload(T, &h->qmdff, &msg);
+    if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
 int crcl_set_path(crcl_handle h, int path)
 {
     if (!h || path < CRCL_PATH_AUTO || path > CRCL_PATH_SPLIT) return CRCL_EINVAL;
@@ -727,6 +743,24 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
                    double* d_dVdq, int* d_info)
 {
     if (!h || !d_q || !d_V || !d_dVdq || nimg < 0) return CRCL_EINVAL;
+    if (pes_id == CRCL_PES_QMDFF) {
+        if (!h->qmdff) return fail(h, CRCL_ESTATE, "crcl_set_qmdff has not been called");
+        if (h->qmdff->n != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the QMDFF tables");
+        if (nimg == 0) return CRCL_OK;
+        CK(cudaSetDevice(h->device));
+        if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
+        if (h->timed) {
+            next_event_pair(h);
+            cudaEventRecord(h->ev0, h->stream);
+        }
+        cudaError_t e = qmdff_egrad(h->qmdff, d_q, nimg, d_V, d_dVdq, h->stream, &h->launches);
+        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (e != cudaSuccess) {
+            h->err = std::string("qmdff kernels: ") + cudaGetErrorString(e);
+            return CRCL_ECUDA;
+        }
+        return CRCL_OK;
+    }
     if (pes_natoms(pes_id) != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the PES");
     if (nimg == 0) return CRCL_OK;
     CK(cudaSetDevice(h->device));

@@ -1,0 +1,43 @@
+// qmdff.cuh -- device tables and launch interface of the QMDFF force-field kernels
+// (qmdff_kernels.cu).  Replaces ff_eg.f90, ff_nonb.f90:33-512 and the QMDFF1 branch of
+// gradient.f90:341-362 for one QMDFF (nqmdff = 1).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/caracal_gpu.h"
+
+namespace crcl {
+
+constexpr int QM_MAXTYPE = 12;  // distinct elements in one force field
+
+struct QmdffDev {
+    int n, nbond, nangl, ntors, nnci, ldvt, nmols, ntype;
+    // per atom
+    int* type;      // element type index 0..ntype-1
+    int* molnum;
+    double* q;
+    double* radsum2;  // unused placeholder (abdamp uses rad per type)
+    // lists, 0-based atom indices
+    int* bond;
+    double* vbond;
+    int* angl;
+    double* vangl;
+    int* tors;
+    double* vtors;
+    int* nci;
+    double* c6;  // [n][n] symmetric: c6xy(max,min) of the reference
+    // per element-type tables
+    double rad[QM_MAXTYPE];
+    double r0ab[QM_MAXTYPE][QM_MAXTYPE], zab[QM_MAXTYPE][QM_MAXTYPE], r094[QM_MAXTYPE][QM_MAXTYPE],
+        sr42[QM_MAXTYPE][QM_MAXTYPE];
+    double eps1[6], eps2[6];
+    int periodic, zahn;
+    double box[3], coul_cut, vdw_cut, cut_low, zahn_a, zahn_par, e_zero;
+};
+
+// host: build / free the device copy; evaluate nimg images (AoS [img][atom][xyz])
+int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err);
+void qmdff_free(QmdffDev* D);
+cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g,
+                        cudaStream_t s, long long* launches);
+
+}  // namespace crcl

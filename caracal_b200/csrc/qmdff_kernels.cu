@@ -1,0 +1,673 @@
+// qmdff_kernels.cu -- QMDFF energy and gradient on the device.
+//
+// Replaces, for one QMDFF (gradient.f90:341-362, nqmdff = 1):
+//   ff_eg.f90:40-629    bonds, angles (cosine / linear form, abdamp.f90 damping), proper torsions
+//                       (<= 4 cosine terms, erf switch, valijkl.f90 + dphidr.f90) and inversions
+//                       (omega.f90 + domegadr.f90)                      -> qm_bonded_kernel
+//   ff_nonb.f90:88-193,339-417   nci pair list: D3-BJ-like dispersion, exponential repulsion,
+//                       Coulomb (Zahn / cut-off + exp_switch.f90 / plain)  -> qm_nci_kernel
+//   ff_nonb.f90:198-332,421-512  inter-molecular O(N^2) loops             -> qm_inter_kernel
+// The SPME/Ewald branch of ff_nonb is dead code in the reference (ewald=.false., :337) and has
+// no counterpart.  ff_hb (H/X-bond terms) is not implemented yet: crcl_set_qmdff refuses tables
+// with nhb > 0.
+//
+// Mapping: one thread per (image, term) for the lists, gradients accumulated with FP64
+// atomics (red.global.add.f64; a term touches 2-4 atoms, contention is negligible).  The
+// inter-molecular part is an all-pairs sweep: a CTA owns 128 atoms i of one image, streams all
+// atoms j through shared memory in tiles (positions, charge, type, molecule), every thread
+// accumulates the gradient of its own atom in registers -- each pair is visited from both sides,
+// so no atomics and fully coalesced traffic; energies are halved.  With the 10 A cut-offs of the
+// periodic case ~20 % of the pairs of a 27 A box survive the distance test.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "qmdff.cuh"
+
+namespace crcl {
+
+__device__ __forceinline__ void box_image(const QmdffDev& D, double v[3])
+{
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const double L = D.box[d], L2 = 0.5 * L;
+        while (fabs(v[d]) > L2) v[d] -= (v[d] >= 0.0) ? L : -L;
+    }
+}
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3])
+{
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double a[3], const double b[3])
+{
+    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+}
+// abdamp.f90:35-50; rcut = 3.0*3.5710642*(rad_i+rad_j)^2 with REAL*4 literals (F3)
+__device__ __forceinline__ void abdamp(const QmdffDev& D, int ti, int tj, double r2, double& damp, double& ddamp)
+{
+    const double rs = D.rad[ti] + D.rad[tj];
+    const double rcut = (double)(3.0f * 3.5710642f) * (rs * rs);
+    const double rr = (r2 / rcut) * (r2 / rcut);
+    damp = 1.0 / (1.0 + rr);
+    ddamp = -4.0 * rr / (r2 * ((1.0 + rr) * (1.0 + rr)));
+}
+__device__ __forceinline__ void ld3(const double* x, int a, double v[3])
+{
+    v[0] = x[3 * a];
+    v[1] = x[3 * a + 1];
+    v[2] = x[3 * a + 2];
+}
+__device__ __forceinline__ void add3(double* g, int a, const double v[3])
+{
+    atomicAdd(&g[3 * a], v[0]);
+    atomicAdd(&g[3 * a + 1], v[1]);
+    atomicAdd(&g[3 * a + 2], v[2]);
+}
+__device__ __forceinline__ double block_sum_to(double v, double* dst)
+{
+    __shared__ double sh[8];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+        if (t != 0.0) atomicAdd(dst, t);
+    }
+    __syncthreads();
+    return v;
+}
+
+// ---- bonded terms: term index t in [0, nbond+nangl+ntors) -------------------------------------------
+__global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const double* __restrict__ xyz,
+                                                        double* __restrict__ V, double* __restrict__ g)
+{
+    constexpr double PI = 3.1415926535897932384626433832795029, PI2 = 6.28318530717958623199592693708837,
+                     SPI = 1.77245385090551599275151910313925;
+    const int nterm = D.nbond + D.nangl + D.ntors;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    const double* x = xyz + (size_t)img * 3 * D.n;
+    double* gi = g + (size_t)img * 3 * D.n;
+    double e = 0.0;
+    if (t < D.nbond) {
+        const int i = D.bond[2 * t], j = D.bond[2 * t + 1];
+        double a[3], b[3], rb[3];
+        ld3(x, i, a);
+        ld3(x, j, b);
+        for (int c = 0; c < 3; c++) rb[c] = a[c] - b[c];
+        if (D.periodic) box_image(D, rb);
+        const double r2 = dot3(rb, rb), r = sqrt(r2);
+        const double rij = D.vbond[3 * t], kij = D.vbond[3 * t + 1], aai = D.vbond[3 * t + 2];
+        const double ph = pow(rij / r, 0.5 * aai), pf = ph * ph;   // (rij/r)^(a/2), (rij/r)^a
+        e = kij * (1.0 + pf - 2.0 * ph);
+        const double fac = aai * kij * (-pf + ph) / r2;
+        double v[3] = {fac * rb[0], fac * rb[1], fac * rb[2]};
+        add3(gi, i, v);
+        v[0] = -v[0];
+        v[1] = -v[1];
+        v[2] = -v[2];
+        add3(gi, j, v);
+    } else if (t < D.nbond + D.nangl) {
+        const int m = t - D.nbond;
+        const int j = D.angl[3 * m], i = D.angl[3 * m + 1], k = D.angl[3 * m + 2];
+        const double c0 = D.vangl[2 * m], kijk = D.vangl[2 * m + 1];
+        double va[3], vb[3], vc[3], vab[3], vcb[3], vp[3];
+        ld3(x, i, va);
+        ld3(x, j, vb);
+        ld3(x, k, vc);
+        for (int c = 0; c < 3; c++) {
+            vab[c] = va[c] - vb[c];
+            vcb[c] = vc[c] - vb[c];
+        }
+        if (D.periodic) {
+            box_image(D, vab);
+            box_image(D, vcb);
+        }
+        const double rab2 = dot3(vab, vab), rcb2 = dot3(vcb, vcb);
+        cross3(vcb, vab, vp);
+        const double rp = sqrt(dot3(vp, vp)) + 1.e-14;
+        const double al = sqrt(rab2), bl = sqrt(rcb2);
+        double cosa = (al > 0.0 && bl > 0.0) ? dot3(vab, vcb) / (al * bl) : 0.0;
+        cosa = fmin(1.0, fmax(-1.0, cosa));
+        const double theta = acos(cosa);
+        double dij, d2ij, djk, d2jk;
+        abdamp(D, D.type[i], D.type[j], rab2, dij, d2ij);
+        abdamp(D, D.type[k], D.type[j], rcb2, djk, d2jk);
+        const double damp = dij * djk;
+        double ea, deddt;
+        if (PI - c0 < 1.e-6) {
+            const double dt = theta - c0;
+            ea = kijk * dt * dt;
+            deddt = 2.0 * kijk * dt;
+        } else {
+            const double cc = cos(c0);
+            ea = kijk * (cosa - cc) * (cosa - cc);
+            deddt = 2.0 * kijk * sin(theta) * (cc - cosa);
+        }
+        e = ea * damp;
+        double deda[3], dedc[3];
+        cross3(vab, vp, deda);
+        cross3(vcb, vp, dedc);
+        const double rm1 = -deddt / (rab2 * rp), rm2 = deddt / (rcb2 * rp);
+        double ga[3], gb[3], gc[3];
+        for (int c = 0; c < 3; c++) {
+            const double da = deda[c] * rm1, dc = dedc[c] * rm2;
+            const double t1 = ea * d2ij * djk * vab[c], t2 = ea * d2jk * dij * vcb[c];
+            ga[c] = da * damp + t1;
+            gc[c] = dc * damp + t2;
+            gb[c] = -(da + dc) * damp - t1 - t2;
+        }
+        add3(gi, i, ga);
+        add3(gi, j, gb);
+        add3(gi, k, gc);
+    } else if (t < nterm) {
+        const int m = t - D.nbond - D.nangl;
+        const int* tr = D.tors + 6 * m;
+        const double* vt = D.vtors + (size_t)D.ldvt * m;
+        const int i = tr[0], j = tr[1], k = tr[2], l = tr[3], nt = tr[4];
+        const double phi0 = vt[0];
+        double xi[3], xj[3], xk[3], xl[3];
+        ld3(x, i, xi);
+        ld3(x, j, xj);
+        ld3(x, k, xk);
+        ld3(x, l, xl);
+        double gA[3], gB[3], gC[3], gD[3];
+        if (tr[5] != 2) {
+            // proper torsion: ra = j-i, rb = k-j, rc = l-k (valijkl.f90, dphidr.f90)
+            double ra[3], rb[3], rc[3];
+            for (int c = 0; c < 3; c++) {
+                ra[c] = xj[c] - xi[c];
+                rb[c] = xk[c] - xj[c];
+                rc[c] = xl[c] - xk[c];
+            }
+            if (D.periodic) {
+                box_image(D, ra);
+                box_image(D, rb);
+                box_image(D, rc);
+            }
+            const double rij = dot3(ra, ra), rjk = dot3(rb, rb), rkl = dot3(rc, rc);
+            double dij, d2ij, djk, d2jk, dkl, d2kl;
+            abdamp(D, D.type[i], D.type[j], rij, dij, d2ij);
+            abdamp(D, D.type[k], D.type[j], rjk, djk, d2jk);
+            abdamp(D, D.type[k], D.type[l], rkl, dkl, d2kl);
+            const double damp = djk * dij * dkl;
+            double na[3], nb[3];
+            cross3(ra, rb, na);
+            cross3(rb, rc, nb);
+            const double nan_ = sqrt(dot3(na, na)), nbn = sqrt(dot3(nb, nb));
+            double sn = dot3(na, nb);
+            if (nan_ > 1.e-14) sn /= nan_;
+            if (nbn > 1.e-14) sn /= nbn;
+            if (fabs(fabs(sn) - 1.0) < 1.0e-14) sn = (sn >= 0.0) ? 1.0 : -1.0;
+            const double phi = acos(sn);
+            const double cosphi = cos(phi), sinphi = sin(phi);
+            double dda[3] = {0, 0, 0}, ddb[3] = {0, 0, 0}, ddc[3] = {0, 0, 0}, ddd[3] = {0, 0, 0};
+            const double nenner = nan_ * nbn * sinphi;
+            if (!(fabs(nenner) < 1.e-14)) {
+                const double on = 1.0 / nenner;
+                double rapb[3], rbpc[3], rab[3], rba[3], rac[3], rbb[3], rbc[3], raa[3], rapba[3], rapbb[3],
+                    rbpca[3], rbpcb[3];
+                for (int c = 0; c < 3; c++) {
+                    rapb[c] = ra[c] + rb[c];
+                    rbpc[c] = rb[c] + rc[c];
+                }
+                cross3(na, rb, rab);
+                cross3(nb, ra, rba);
+                cross3(na, rc, rac);
+                cross3(nb, rb, rbb);
+                cross3(nb, rc, rbc);
+                cross3(na, ra, raa);
+                cross3(rapb, na, rapba);
+                cross3(rapb, nb, rapbb);
+                cross3(rbpc, na, rbpca);
+                cross3(rbpc, nb, rbpcb);
+                const double ba = nbn / nan_, ab = nan_ / nbn;
+                for (int c = 0; c < 3; c++) {
+                    dda[c] = on * (cosphi * ba * rab[c] - rbb[c]);
+                    ddb[c] = on * (cosphi * (ba * rapba[c] + ab * rbc[c]) - (rac[c] + rapbb[c]));
+                    ddc[c] = on * (cosphi * (ba * raa[c] + ab * rbpcb[c]) - (rba[c] + rbpca[c]));
+                    ddd[c] = on * (cosphi * ab * rbb[c] - rab[c]);
+                }
+            }
+            double et = 0.0, dd = 0.0;
+            const double phipi = phi - PI, ef = erf(phipi), expo = exp(-phipi * phipi) / SPI;
+            for (int it = 0; it < nt; it++) {
+                const double rn = vt[2 + 3 * it], ph = vt[3 + 3 * it], vv = vt[4 + 3 * it];
+                const double c1 = rn * (phi - phi0) + ph, c2 = rn * (phi + phi0 - PI2) + ph;
+                double s1, co1, s2, co2;
+                sincos(c1, &s1, &co1);
+                sincos(c2, &s2, &co2);
+                const double e1 = vv * (1.0 + co1), e2 = vv * (1.0 + co2);
+                et += 0.5 * (1.0 - ef) * e1 + (0.5 + 0.5 * ef) * e2;
+                dd += -expo * e1 - 0.5 * (1.0 - ef) * vv * s1 * rn + expo * e2 - (0.5 + 0.5 * ef) * vv * s2 * rn;
+            }
+            et *= vt[1];
+            dd *= vt[1] * damp;
+            e = et * damp;
+            // the reference's vab = i-j = -ra, vcb = j-k = -rb, vdc = k-l = -rc
+            for (int c = 0; c < 3; c++) {
+                const double t1 = et * d2ij * djk * dkl * (-ra[c]);
+                const double t2 = et * d2jk * dij * dkl * (-rb[c]);
+                const double t3 = et * d2kl * dij * djk * (-rc[c]);
+                gA[c] = dd * dda[c] + t1;
+                gB[c] = dd * ddb[c] - t1 + t2;
+                gC[c] = dd * ddc[c] + t3 - t2;
+                gD[c] = dd * ddd[c] - t3;
+            }
+        } else {
+            // inversion at centre j (omega.f90, domegadr.f90): re = i-j, rd = k-j, rv = l-i
+            double re[3], rd[3], rv[3], vdl[3];
+            for (int c = 0; c < 3; c++) {
+                re[c] = xi[c] - xj[c];
+                rd[c] = xk[c] - xj[c];
+                rv[c] = xl[c] - xi[c];
+                vdl[c] = xj[c] - xl[c];
+            }
+            if (D.periodic) {
+                box_image(D, re);
+                box_image(D, rd);
+                box_image(D, rv);
+                box_image(D, vdl);
+            }
+            const double rij = dot3(re, re), rjk = dot3(rd, rd), rjl = dot3(vdl, vdl);
+            double dij, d2ij, djk, d2jk, djl, d2jl;
+            abdamp(D, D.type[i], D.type[j], rij, dij, d2ij);
+            abdamp(D, D.type[k], D.type[j], rjk, djk, d2jk);
+            abdamp(D, D.type[j], D.type[l], rjl, djl, d2jl);
+            const double damp = djk * dij * djl;
+            double rn[3];
+            cross3(re, rd, rn);
+            const double rnn = sqrt(dot3(rn, rn)), rvn = sqrt(dot3(rv, rv));
+            double sarg = dot3(rn, rv);
+            if (rnn > 1.e-14) sarg /= rnn;
+            if (rvn > 1.e-14) sarg /= rvn;
+            const double om = asin(sarg);
+            const double sinom = sin(om);
+            double dda[3] = {0, 0, 0}, ddb[3] = {0, 0, 0}, ddc[3] = {0, 0, 0}, ddd[3] = {0, 0, 0};
+            const double nenner = rnn * rvn * cos(om);
+            if (fabs(nenner) > 1.e-14) {
+                const double on = 1.0 / nenner;
+                double rdme[3], rve[3], rne[3], rdv[3], rdn[3], rvdme[3], rndme[3];
+                for (int c = 0; c < 3; c++) rdme[c] = rd[c] - re[c];
+                cross3(rv, re, rve);
+                cross3(rn, re, rne);
+                cross3(rd, rv, rdv);
+                cross3(rd, rn, rdn);
+                cross3(rv, rdme, rvdme);
+                cross3(rn, rdme, rndme);
+                const double vn = rvn / rnn, nv = rnn / rvn;
+                for (int c = 0; c < 3; c++) {
+                    dda[c] = on * (rdv[c] - rn[c] - sinom * (vn * rdn[c] - nv * rv[c]));
+                    ddb[c] = on * (rvdme[c] - sinom * vn * rndme[c]);
+                    ddc[c] = on * (rve[c] - sinom * vn * rne[c]);
+                    ddd[c] = on * (rn[c] - sinom * nv * rv[c]);
+                }
+            }
+            double et, dd;
+            if (vt[2] > 1.e-6) {
+                const double c1 = (om - phi0) + PI;
+                et = (1.0 + cos(c1)) * vt[1];
+                dd = -sin(c1) * vt[1] * damp;
+            } else {
+                const double cd = cos(om) - cos(phi0);
+                et = vt[1] * cd * cd;
+                dd = 2.0 * vt[1] * sin(om) * (-cd) * damp;
+            }
+            e = et * damp;
+            // the reference's vab = j-i = -re, vcb = j-k = -rd, vdc = j-l = vdl
+            for (int c = 0; c < 3; c++) {
+                const double t1 = et * d2ij * djk * djl * (-re[c]);
+                const double t2 = et * d2jk * dij * djl * (-rd[c]);
+                const double t3 = et * d2jl * dij * djk * vdl[c];
+                gA[c] = dd * dda[c] - t1;
+                gB[c] = dd * ddb[c] + t1 + t2 + t3;
+                gC[c] = dd * ddc[c] - t2;
+                gD[c] = dd * ddd[c] - t3;
+            }
+        }
+        add3(gi, i, gA);
+        add3(gi, j, gB);
+        add3(gi, k, gC);
+        add3(gi, l, gD);
+    }
+    block_sum_to(e, &V[img]);
+}
+
+// dispersion + repulsion of one pair (ff_nonb.f90:120-160): returns the energy, dr = gradient factor
+// such that g_i1 += vab*dr, g_i2 -= vab*dr
+__device__ __forceinline__ double vdw_pair(const QmdffDev& D, int t1, int t2, double c6, double r2, double r,
+                                           double eps, double& dr)
+{
+    const double R0 = D.r094[t1][t2];
+    const double r4 = r2 * r2, r6 = r4 * r2;
+    const double R02 = R0 * R0, r06 = R02 * R02 * R02;
+    const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
+    const double c6t6 = c6 / t6, c6t8 = c6 / t8;
+    const double t27 = D.sr42[t1][t2] * c6t8;
+    double e = -(c6t6 + t27) * eps;
+    dr = eps * (c6t6 * 6.0 * r4 / t6 + 8.0 * t27 * r6 / t8);
+    if (r < 25.0) {
+        const double alpha = D.r0ab[t1][t2];
+        const double tt = D.zab[t1][t2] * exp(-alpha * r);
+        const double oner = 1.0 / r;
+        e += tt * oner * eps;
+        dr -= eps * tt * (alpha * r + 1.0) * oner / r2;
+    }
+    return e;
+}
+// Coulomb of one pair (ff_nonb.f90:339-417): energy; gradient factor dr (g_i1 += vab*dr)
+__device__ __forceinline__ double coul_pair(const QmdffDev& D, double qq, double r2, double r, double eps, double& dr)
+{
+    dr = 0.0;
+    double sw = 1.0;
+    if (D.periodic) {
+        if (r > D.coul_cut) return 0.0;
+        if (!D.zahn && r > D.cut_low) {
+            const double xv = (r - D.cut_low) / (D.coul_cut - D.cut_low);
+            sw = exp(1.0) * exp(1.0 / (xv - 1.0));
+        }
+    }
+    if (r > D.coul_cut) return 0.0;
+    const double oner = 1.0 / r;
+    const double e0 = D.zahn ? qq * (erfc(D.zahn_a * r) * oner - D.zahn_par * (r - D.coul_cut)) : qq * oner * eps * sw;
+    dr = -e0 / r2;   // the reference uses e0/r^2 for every Coulomb form (ff_nonb.f90:384,470)
+    return e0;
+}
+
+__global__ void __launch_bounds__(128) qm_nci_kernel(const QmdffDev D, const double* __restrict__ xyz,
+                                                     double* __restrict__ V, double* __restrict__ g)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int img = blockIdx.y;
+    const double* x = xyz + (size_t)img * 3 * D.n;
+    double* gi = g + (size_t)img * 3 * D.n;
+    double e = 0.0;
+    if (k < D.nnci) {
+        const int i1 = D.nci[3 * k], i2 = D.nci[3 * k + 1], nk = D.nci[3 * k + 2] - 1;
+        double a[3], b[3], vab[3];
+        ld3(x, i1, a);
+        ld3(x, i2, b);
+        for (int c = 0; c < 3; c++) vab[c] = a[c] - b[c];
+        if (D.periodic) box_image(D, vab);
+        const double r2 = dot3(vab, vab), r = sqrt(r2);
+        double dr = 0.0, d1, d2;
+        if (!(D.periodic && r > D.vdw_cut)) {
+            const int lo = min(i1, i2), hi = max(i1, i2);
+            e += vdw_pair(D, D.type[i1], D.type[i2], D.c6[(size_t)lo * D.n + hi], r2, r, D.eps2[nk], d1);
+            dr += d1;
+        }
+        e += coul_pair(D, D.q[i1] * D.q[i2], r2, r, D.eps1[nk], d2);
+        dr += d2;
+        double v[3] = {vab[0] * dr, vab[1] * dr, vab[2] * dr};
+        add3(gi, i1, v);
+        v[0] = -v[0];
+        v[1] = -v[1];
+        v[2] = -v[2];
+        add3(gi, i2, v);
+    }
+    block_sum_to(e, &V[img]);
+}
+
+// inter-molecular all-pairs sweep; thread = atom i of image blockIdx.y, tiles of 128 atoms j
+__global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const double* __restrict__ xyz,
+                                                       double* __restrict__ V, double* __restrict__ g)
+{
+    __shared__ double sx[128], sy[128], sz[128], sq[128];
+    __shared__ int st[128], sm[128];
+    const int img = blockIdx.y, n = D.n;
+    const double* x = xyz + (size_t)img * 3 * n;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const bool act = i < n;
+    double xi = 0, yi = 0, zi = 0, qi = 0, gx = 0, gy = 0, gz = 0, e = 0.0;
+    int ti = 0, mi = -1;
+    if (act) {
+        xi = x[3 * i];
+        yi = x[3 * i + 1];
+        zi = x[3 * i + 2];
+        qi = D.q[i];
+        ti = D.type[i];
+        mi = D.molnum[i];
+    }
+    for (int j0 = 0; j0 < n; j0 += 128) {
+        const int j = j0 + threadIdx.x;
+        __syncthreads();
+        if (j < n) {
+            sx[threadIdx.x] = x[3 * j];
+            sy[threadIdx.x] = x[3 * j + 1];
+            sz[threadIdx.x] = x[3 * j + 2];
+            sq[threadIdx.x] = D.q[j];
+            st[threadIdx.x] = D.type[j];
+            sm[threadIdx.x] = D.molnum[j];
+        }
+        __syncthreads();
+        if (!act) continue;
+        const int cnt = min(128, n - j0);
+        for (int jj = 0; jj < cnt; jj++) {
+            if (sm[jj] == mi) continue;
+            // orientation as the reference: vab = x(i1) - x(i2) with i1 < i2
+            const int jg = j0 + jj;
+            const double sgn = (i < jg) ? 1.0 : -1.0;
+            double vab[3] = {sgn * (xi - sx[jj]), sgn * (yi - sy[jj]), sgn * (zi - sz[jj])};
+            if (D.periodic) box_image(D, vab);
+            const double r2 = dot3(vab, vab), r = sqrt(r2);
+            double dr = 0.0, d1, d2, ep = 0.0;
+            if (!(D.periodic && r > D.vdw_cut)) {
+                const int lo = min(i, jg), hi = max(i, jg);
+                ep += vdw_pair(D, ti, st[jj], __ldg(&D.c6[(size_t)lo * n + hi]), r2, r, 1.0, d1);
+                dr += d1;
+            }
+            ep += coul_pair(D, qi * sq[jj], r2, r, 1.0, d2);
+            dr += d2;
+            e += 0.5 * ep;
+            gx += sgn * vab[0] * dr;
+            gy += sgn * vab[1] * dr;
+            gz += sgn * vab[2] * dr;
+        }
+    }
+    if (act) {
+        double* gi = g + (size_t)img * 3 * n;
+        atomicAdd(&gi[3 * i], gx);
+        atomicAdd(&gi[3 * i + 1], gy);
+        atomicAdd(&gi[3 * i + 2], gz);
+    }
+    block_sum_to(e, &V[img]);
+}
+
+__global__ void qm_init_kernel(double* V, int nimg, double e_zero)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nimg) V[i] = e_zero;
+}
+
+cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g, cudaStream_t s,
+                        long long* launches)
+{
+    if (nimg <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_g, 0, (size_t)nimg * 3 * D->n * sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    qm_init_kernel<<<(nimg + 127) / 128, 128, 0, s>>>(d_V, nimg, D->e_zero);
+    int nl = 1;
+    // blockIdx.y carries the image: at most 65535 images per launch
+    for (int i0 = 0; i0 < nimg; i0 += 65535) {
+        const int ni = std::min(65535, nimg - i0);
+        const double* x = d_xyz + (size_t)i0 * 3 * D->n;
+        double* g = d_g + (size_t)i0 * 3 * D->n;
+        double* V = d_V + i0;
+        const int nterm = D->nbond + D->nangl + D->ntors;
+        if (nterm > 0) {
+            qm_bonded_kernel<<<dim3((nterm + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+            nl++;
+        }
+        if (!(D->nnci <= 1 && D->nmols == 0)) {   // ff_nonb.f90:74 early return
+            if (D->nnci > 0) {
+                qm_nci_kernel<<<dim3((D->nnci + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                nl++;
+            }
+            if (D->nmols > 1) {
+                qm_inter_kernel<<<dim3((D->n + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                nl++;
+            }
+        }
+    }
+    if (launches) *launches += nl;
+    return cudaGetLastError();
+}
+
+template <class T>
+static T* up(const T* h, size_t n, bool& ok)
+{
+    T* d = nullptr;
+    if (!ok) return nullptr;
+    if (cudaMalloc(&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) {
+        ok = false;
+        return nullptr;
+    }
+    if (n && cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+    return d;
+}
+
+int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err)
+{
+    *out = nullptr;
+    if (T->nhb > 0) {
+        *err = "QMDFF H/X-bond terms (ff_hb) are not implemented on the device yet";
+        return CRCL_ENOSUP;
+    }
+    const int n = T->n;
+    QmdffDev* D = new QmdffDev();
+    memset(D, 0, sizeof(*D));
+    D->n = n;
+    D->nbond = T->nbond;
+    D->nangl = T->nangl;
+    D->ntors = T->ntors;
+    D->nnci = T->nnci;
+    D->ldvt = T->ldvt;
+    D->nmols = T->nmols;
+    // element types
+    int zmap[95];
+    for (int z = 0; z < 95; z++) zmap[z] = -1;
+    int ztab[QM_MAXTYPE];
+    std::vector<int> type(n), mol(n);
+    for (int a = 0; a < n; a++) {
+        const int z = T->at[a];
+        if (z < 1 || z > 94) {
+            *err = "atomic number out of range 1..94";
+            delete D;
+            return CRCL_EINVAL;
+        }
+        if (zmap[z] < 0) {
+            if (D->ntype == QM_MAXTYPE) {
+                *err = "more than 12 distinct elements in one QMDFF";
+                delete D;
+                return CRCL_ENOSUP;
+            }
+            ztab[D->ntype] = z;
+            zmap[z] = D->ntype++;
+        }
+        type[a] = zmap[z];
+        mol[a] = T->molnum ? T->molnum[a] : 1;
+    }
+    for (int a = 0; a < D->ntype; a++) {
+        D->rad[a] = T->rad[ztab[a] - 1];
+        for (int b = 0; b < D->ntype; b++) {
+            const size_t ix = (size_t)(ztab[a] - 1) + 94 * (size_t)(ztab[b] - 1);   // Fortran (94,94)
+            D->r0ab[a][b] = T->r0ab[ix];
+            D->zab[a][b] = T->zab[ix];
+            D->r094[a][b] = T->r094[ix];
+            D->sr42[a][b] = T->sr42[ix];
+        }
+    }
+    for (int k = 0; k < 6; k++) {
+        D->eps1[k] = T->eps1[k];
+        D->eps2[k] = T->eps2[k];
+    }
+    D->periodic = T->periodic;
+    D->zahn = T->zahn;
+    for (int d = 0; d < 3; d++) D->box[d] = T->box[d];
+    D->coul_cut = T->coul_cut;
+    D->vdw_cut = T->vdw_cut;
+    D->cut_low = T->cut_low;
+    D->zahn_a = T->zahn_a;
+    D->zahn_par = T->zahn_par;
+    D->e_zero = T->e_zero;
+    // lists -> 0-based
+    auto idx_ok = [&](int v) { return v >= 1 && v <= n; };
+    std::vector<int> bond(2 * (size_t)T->nbond), angl(3 * (size_t)T->nangl), tors(6 * (size_t)T->ntors),
+        nci(3 * (size_t)T->nnci);
+    bool good = true;
+    for (size_t k = 0; k < bond.size(); k++) {
+        good &= idx_ok(T->bond[k]);
+        bond[k] = T->bond[k] - 1;
+    }
+    for (size_t k = 0; k < angl.size(); k++) {
+        good &= idx_ok(T->angl[k]);
+        angl[k] = T->angl[k] - 1;
+    }
+    for (int m = 0; m < T->ntors; m++) {
+        for (int c = 0; c < 4; c++) {
+            good &= idx_ok(T->tors[6 * m + c]);
+            tors[6 * m + c] = T->tors[6 * m + c] - 1;
+        }
+        tors[6 * m + 4] = T->tors[6 * m + 4];
+        tors[6 * m + 5] = T->tors[6 * m + 5];
+        good &= T->tors[6 * m + 4] >= 0 && 2 + 3 * T->tors[6 * m + 4] <= T->ldvt;
+    }
+    for (int k = 0; k < T->nnci; k++) {
+        good &= idx_ok(T->nci[3 * k]) && idx_ok(T->nci[3 * k + 1]) && T->nci[3 * k + 2] >= 1 && T->nci[3 * k + 2] <= 6;
+        nci[3 * k] = T->nci[3 * k] - 1;
+        nci[3 * k + 1] = T->nci[3 * k + 1] - 1;
+        nci[3 * k + 2] = T->nci[3 * k + 2];
+    }
+    if (!good) {
+        *err = "QMDFF list entry out of range";
+        delete D;
+        return CRCL_EINVAL;
+    }
+    // c6: the reference reads c66ab(i2,i1) with i1 < i2, i.e. element (max,min) of the Fortran array
+    std::vector<double> c6((size_t)n * n);
+    for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) {
+            const int lo = a < b ? a : b, hi = a < b ? b : a;
+            c6[(size_t)a * n + b] = T->c6xy[(size_t)hi + (size_t)n * lo];
+        }
+    bool ok = true;
+    D->type = up(type.data(), n, ok);
+    D->molnum = up(mol.data(), n, ok);
+    D->q = up(T->q, n, ok);
+    D->bond = up(bond.data(), bond.size(), ok);
+    D->vbond = up(T->vbond, 3 * (size_t)T->nbond, ok);
+    D->angl = up(angl.data(), angl.size(), ok);
+    D->vangl = up(T->vangl, 2 * (size_t)T->nangl, ok);
+    D->tors = up(tors.data(), tors.size(), ok);
+    D->vtors = up(T->vtors, (size_t)T->ldvt * T->ntors, ok);
+    D->nci = up(nci.data(), nci.size(), ok);
+    D->c6 = up(c6.data(), c6.size(), ok);
+    if (!ok) {
+        qmdff_free(D);
+        *err = "device allocation / upload of the QMDFF tables failed";
+        return CRCL_ENOMEM;
+    }
+    *out = D;
+    return CRCL_OK;
+}
+
+void qmdff_free(QmdffDev* D)
+{
+    if (!D) return;
+    cudaFree(D->type);
+    cudaFree(D->molnum);
+    cudaFree(D->q);
+    cudaFree(D->bond);
+    cudaFree(D->vbond);
+    cudaFree(D->angl);
+    cudaFree(D->vangl);
+    cudaFree(D->tors);
+    cudaFree(D->vtors);
+    cudaFree(D->nci);
+    cudaFree(D->c6);
+    delete D;
+}
+
+}  // namespace crcl

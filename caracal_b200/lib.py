@@ -14,7 +14,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_u32_p = ctypes.POINTER(ctypes.c_uint32)
 
-PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_HOSTCB = 0, 1, 2, 3, 100
+PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_QMDFF, PES_HOSTCB = 0, 1, 2, 3, 10, 100
 PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H}
 PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6}
 TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
@@ -35,6 +35,7 @@ SIGNATURES = {
     "crcl_set_beta_dt": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double]),
     "crcl_set_transform": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_host_gradient_cb": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
+    "crcl_set_qmdff": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),
     "crcl_set_path": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                           ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),
@@ -67,6 +68,22 @@ SIGNATURES = {
     "crcl_bench_propagate": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p]),
     "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
 }
+
+
+
+class QmdffTables(ctypes.Structure):
+    """crcl_qmdff_tables of include/caracal_gpu.h"""
+    _fields_ = [("n", ctypes.c_int), ("at", c_int_p), ("q", c_double_p), ("molnum", c_int_p), ("nmols", ctypes.c_int),
+                ("nbond", ctypes.c_int), ("nangl", ctypes.c_int), ("ntors", ctypes.c_int), ("nhb", ctypes.c_int),
+                ("nnci", ctypes.c_int), ("ldvt", ctypes.c_int),
+                ("bond", c_int_p), ("vbond", c_double_p), ("angl", c_int_p), ("vangl", c_double_p),
+                ("tors", c_int_p), ("vtors", c_double_p), ("nci", c_int_p), ("c6xy", c_double_p),
+                ("r0ab", c_double_p), ("zab", c_double_p), ("r094", c_double_p), ("sr42", c_double_p),
+                ("rad", c_double_p), ("eps1", ctypes.c_double * 6), ("eps2", ctypes.c_double * 6),
+                ("periodic", ctypes.c_int), ("zahn", ctypes.c_int), ("box", ctypes.c_double * 3),
+                ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double), ("cut_low", ctypes.c_double),
+                ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double), ("e_zero", ctypes.c_double)]
+
 
 _lib = None
 

@@ -35,6 +35,7 @@ extern "C" {
 #define CRCL_PES_H3 1    /* "h3"   egrad_h3.f   BKMP2 H + H2, 3 atoms                 */
 #define CRCL_PES_OH3 2   /* "oh3"  egrad_oh3.f  Schatz-Elgersma OH + H2, atoms O,H,H,H */
 #define CRCL_PES_CH4H 3  /* "ch4h" egrad_ch4h.f CBE CH4 + H, atoms H,C,H,H,H,H         */
+#define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_HOSTCB 100 /* custom_grad / external_grad stay on the host (callback)  */
 
 /* error codes */
@@ -97,6 +98,37 @@ int crcl_set_path(crcl_handle h, int path);
 int crcl_set_mechanism(crcl_handle h, int form_num, const int *bond_form, int break_num,
                        const int *bond_break, const double *form_ref, const double *break_ref,
                        int sum_reacs, const int *n_reac, const int *at_reac, double R_inf);
+
+/* Tables of one QMDFF exactly as the reference holds them after prepare.f90 / rdsolvff.f90 /
+ * setnonb.f90 / set_periodic.f90 (module qmdff, qmdff.f90:49-110; pbc_mod): the library receives
+ * them, it does not rebuild them.  Index lists are 1-based as in the .qmdff file;
+ * (94,94) and (n,n) arrays are in Fortran order.  All pointers are host pointers, copied by
+ * crcl_set_qmdff. */
+typedef struct crcl_qmdff_tables {
+    int n;                /* atoms */
+    const int *at;        /* at(n) atomic numbers */
+    const double *q;      /* q(n) charges */
+    const int *molnum;    /* molnum(n); may be NULL when nmols <= 1 */
+    int nmols;
+    int nbond, nangl, ntors, nhb, nnci, ldvt; /* ldvt = leading dimension of vtors (14) */
+    const int *bond;      /* bond(2,nbond) */
+    const double *vbond;  /* vbond(3,nbond): r0, k, a */
+    const int *angl;      /* angl(3,nangl): centre first (ff_eg.f90:168-176) */
+    const double *vangl;  /* vangl(2,nangl): theta0, k */
+    const int *tors;      /* tors(6,ntors): i,j,k,l,nt,type (type 2 = inversion, ff_eg.f90:316) */
+    const double *vtors;  /* vtors(ldvt,ntors): phi0, k, nt x (n, phase, V) */
+    const int *nci;       /* nci(3,nnci): i, j, screening class 1..6 */
+    const double *c6xy;   /* c6xy(n,n) */
+    const double *r0ab, *zab, *r094, *sr42; /* (94,94): r0ab, zab, r094_mod, sr42 */
+    const double *rad;    /* rad(94) */
+    double eps1[6], eps2[6];
+    int periodic, zahn;   /* pbc_mod: periodic, zahn */
+    double box[3];        /* boxlen_x, boxlen_y, boxlen_z */
+    double coul_cut, vdw_cut, cut_low, zahn_a, zahn_par;
+    double e_zero;        /* E_zero1 (ESHIFT keyword) */
+} crcl_qmdff_tables;
+/* handle must have been created with pes_id = CRCL_PES_QMDFF and natoms = T->n */
+int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables *T);
 
 /* NVT{} section: thermostat 0 none, 1 Andersen, 2 Nose-Hoover chain (dynamic.f90:463-465);
  * andersen_step as evb_mod.f90:289; kelvin and nose_q for nhc.f90 / mdinit.f90:138-146 */

@@ -221,3 +221,66 @@ class System:
         st = self.L.oracle_recross_children(self.h, _d(qp), qp.shape[0], pair0, npairs, child_evol, xi_ideal, seed,
                                             nthreads, _d(num), ctypes.byref(den))
         return num, den.value, st
+
+
+class _QmdffStruct(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int), ("at", ip), ("q", dp),
+                ("nbond", ctypes.c_int), ("nangl", ctypes.c_int), ("ntors", ctypes.c_int), ("nnci", ctypes.c_int),
+                ("ldvt", ctypes.c_int), ("nmols", ctypes.c_int),
+                ("bond", ip), ("vbond", dp), ("angl", ip), ("vangl", dp), ("tors", ip), ("vtors", dp), ("nci", ip),
+                ("molnum", ip), ("c6xy", dp), ("r0ab", dp), ("zab", dp), ("r094", dp), ("sr42", dp), ("rad", dp),
+                ("eps1", ctypes.c_double * 6), ("eps2", ctypes.c_double * 6),
+                ("periodic", ctypes.c_int), ("zahn", ctypes.c_int),
+                ("box", ctypes.c_double * 3), ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double),
+                ("cut_low", ctypes.c_double), ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double),
+                ("e_zero", ctypes.c_double)]
+
+
+class Qmdff:
+    """Oracle of gradient.f90:341-362 (nqmdff = 1): ff_eg + ff_nonb + E_zero1 on the given tables."""
+
+    def __init__(self, T):
+        self.L = lib()
+        self.keep = {}
+
+        def arr(key, dtype):
+            order = "F" if key in ("c6xy", "r0ab", "zab", "r094", "sr42") else "C"
+            a = np.array(T[key], dtype=dtype, order=order)
+            self.keep[key] = a
+            return a
+        S = _QmdffStruct()
+        S.n = int(T["n"])
+        S.at = _i(arr("at", np.int32))
+        S.q = _d(arr("q", np.float64))
+        S.nbond, S.nangl, S.ntors, S.nnci = len(T["bond"]), len(T["angl"]), len(T["tors"]), len(T["nci"])
+        S.ldvt, S.nmols = int(T["ldvt"]), int(T["nmols"])
+        S.bond, S.vbond = _i(arr("bond", np.int32)), _d(arr("vbond", np.float64))
+        S.angl, S.vangl = _i(arr("angl", np.int32)), _d(arr("vangl", np.float64))
+        S.tors, S.vtors = _i(arr("tors", np.int32)), _d(arr("vtors", np.float64))
+        S.nci, S.molnum = _i(arr("nci", np.int32)), _i(arr("molnum", np.int32))
+        for k in ("c6xy", "r0ab", "zab", "r094", "sr42", "rad"):
+            setattr(S, k, _d(arr(k, np.float64)))
+        S.eps1 = (ctypes.c_double * 6)(*T["eps1"])
+        S.eps2 = (ctypes.c_double * 6)(*T["eps2"])
+        S.periodic, S.zahn = int(T["periodic"]), int(T["zahn"])
+        S.box = (ctypes.c_double * 3)(*T["box"])
+        S.coul_cut, S.vdw_cut, S.cut_low = float(T["coul_cut"]), float(T["vdw_cut"]), float(T["cut_low"])
+        S.zahn_a, S.zahn_par, S.e_zero = float(T["zahn_a"]), float(T["zahn_par"]), float(T["e_zero"])
+        self.S = S
+        self.n = S.n
+        self.L.orc_qmdff_egrad.argtypes = [ctypes.POINTER(_QmdffStruct), dp, ctypes.c_int, dp, dp]
+        self.L.orc_ff_eg.argtypes = [ctypes.POINTER(_QmdffStruct), dp, dp, dp]
+
+    def egrad(self, xyz):
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, self.n, 3)
+        V = np.zeros(x.shape[0])
+        g = np.zeros_like(x)
+        self.L.orc_qmdff_egrad(ctypes.byref(self.S), _d(x), x.shape[0], _d(V), _d(g))
+        return V, g
+
+    def ff_eg(self, xyz):
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(self.n, 3)
+        e = ctypes.c_double(0.0)
+        g = np.zeros_like(x)
+        self.L.orc_ff_eg(ctypes.byref(self.S), _d(x), ctypes.byref(e), _d(g))
+        return e.value, g

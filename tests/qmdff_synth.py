@@ -1,0 +1,143 @@
+"""Synthetic, well-formed QMDFF systems for the parity tests of the force-field kernels.
+
+The real tables come from qmdffgen / prepare.f90 / setnonb.f90 / copyc6.f90 (D3 reference data),
+which are out of scope: the GPU library RECEIVES tables.  These generators produce
+random but physically shaped tables (ethanol-like and formaldehyde-like molecules: bonds, angles,
+proper torsions with 1-3 cosine terms, an inversion centre, intramolecular nci pairs of screening
+classes 3..6, inter-molecular pairs through molnum) so that every branch of ff_eg / ff_nonb runs.
+"""
+import numpy as np
+
+BOHR = 0.52917721092
+
+# templates: (Z, xyz in Angstrom), bonds (1-based within molecule)
+ETHANOL = dict(
+    Z=[6, 6, 8, 1, 1, 1, 1, 1, 1],
+    xyz=np.array([[0.00, 0.00, 0.00], [1.52, 0.00, 0.00], [2.00, 1.34, 0.00], [-0.40, 1.02, 0.00],
+                  [-0.38, -0.52, 0.88], [-0.38, -0.52, -0.88], [1.90, -0.52, 0.88], [1.90, -0.52, -0.88],
+                  [2.96, 1.30, 0.05]]),
+    bonds=[(1, 2), (2, 3), (1, 4), (1, 5), (1, 6), (2, 7), (2, 8), (3, 9)], inversions=[])
+FORMALDEHYDE = dict(
+    Z=[6, 8, 1, 1],
+    xyz=np.array([[0.0, 0.0, 0.0], [1.21, 0.0, 0.0], [-0.58, 0.94, 0.05], [-0.58, -0.94, 0.05]]),
+    bonds=[(1, 2), (1, 3), (1, 4)], inversions=[(2, 1, 3, 4)])   # (i, centre j, k, l)
+
+
+def _topology(tpl):
+    n = len(tpl["Z"])
+    nb = {i: set() for i in range(1, n + 1)}
+    for a, b in tpl["bonds"]:
+        nb[a].add(b)
+        nb[b].add(a)
+    angles = [(j, i, k) for j in nb for i in sorted(nb[j]) for k in sorted(nb[j]) if i < k]   # centre first
+    tors = []
+    for j, k in tpl["bonds"]:
+        for i in sorted(nb[j] - {k}):
+            for l in sorted(nb[k] - {j}):
+                tors.append((i, j, k, l))
+    dist = np.full((n + 1, n + 1), 99)
+    for a in range(1, n + 1):
+        dist[a, a] = 0
+        frontier, d = {a}, 0
+        seen = {a}
+        while frontier:
+            d += 1
+            nxt = set()
+            for u in frontier:
+                for v in nb[u]:
+                    if v not in seen:
+                        seen.add(v)
+                        dist[a, v] = d
+                        nxt.add(v)
+            frontier = nxt
+    nci = [(a, b, min(6, int(dist[a, b]))) for a in range(1, n + 1) for b in range(a + 1, n + 1) if dist[a, b] >= 3]
+    return angles, tors, nci
+
+
+def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_formaldehyde=0.25):
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(nmol ** (1 / 3)))
+    spacing = 5.2  # Angstrom
+    box_A = box_A or side * spacing
+    Z, xyz, q, molnum = [], [], [], []
+    bond, vbond, angl, vangl, tors, vtors, nci = [], [], [], [], [], [], []
+    ldvt = 14
+    off = 0
+    for m in range(nmol):
+        tpl = FORMALDEHYDE if rng.random() < frac_formaldehyde else ETHANOL
+        n = len(tpl["Z"])
+        A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        cell = np.array([m % side, (m // side) % side, m // (side * side)]) * spacing + spacing / 2
+        x = (tpl["xyz"] - tpl["xyz"].mean(axis=0)) @ A.T + cell + rng.normal(0, 0.03, (n, 3))
+        xyz.append(x / BOHR)
+        Z += tpl["Z"]
+        ch = rng.normal(0, 0.25, n)
+        q += list(ch - ch.mean())
+        molnum += [m + 1] * n
+        angles, torsl, ncil = _topology(tpl)
+        for a, b in tpl["bonds"]:
+            r0 = np.linalg.norm(tpl["xyz"][a - 1] - tpl["xyz"][b - 1]) / BOHR
+            bond.append((a + off, b + off))
+            vbond.append((r0 * rng.uniform(0.97, 1.03), rng.uniform(0.05, 0.25), rng.uniform(2.0, 6.0)))
+        for t_i, (j, i, k) in enumerate(angles):
+            v1 = tpl["xyz"][i - 1] - tpl["xyz"][j - 1]
+            v2 = tpl["xyz"][k - 1] - tpl["xyz"][j - 1]
+            th = np.arccos(v1 @ v2 / np.linalg.norm(v1) / np.linalg.norm(v2))
+            # one (near-)linear reference angle to reach the pi - c0 < 1e-6 branch of ff_eg.f90:206
+            th0 = np.pi if (m == 0 and t_i == 0) else th + rng.normal(0, 0.05)
+            angl.append((j + off, i + off, k + off))
+            vangl.append((th0, rng.uniform(0.02, 0.12)))
+        for (i, j, k, l) in torsl:
+            nt = int(rng.integers(1, 4))
+            row = np.zeros(ldvt)
+            row[0] = rng.uniform(0, np.pi)
+            row[1] = rng.uniform(0.2, 1.0)
+            for it in range(nt):
+                row[2 + 3 * it:5 + 3 * it] = (float(rng.integers(1, 4)), np.pi * rng.integers(0, 2), rng.uniform(0.001, 0.01))
+            tors.append((i + off, j + off, k + off, l + off, nt, 1))
+            vtors.append(row)
+        for t_i, (i, j, k, l) in enumerate(tpl["inversions"]):
+            row = np.zeros(ldvt)
+            row[0] = rng.uniform(0.0, 0.2)
+            row[1] = rng.uniform(0.005, 0.03)
+            row[2] = 0.0 if (m % 2 == 0) else 1.0          # both inversion forms (ff_eg.f90:560-570)
+            tors.append((i + off, j + off, k + off, l + off, 1, 2))
+            vtors.append(row)
+        nci += [(a + off, b + off, c) for a, b, c in ncil]
+        off += n
+    n = off
+    xyz = np.concatenate(xyz)
+    T = lambda: np.zeros((94, 94))   # noqa: E731
+    r0ab, zab, r094, sr42 = T(), T(), T(), T()
+    els = [1, 6, 8]
+    for a in els:
+        for b in els:
+            if a <= b:
+                v = (rng.uniform(1.6, 2.4), rng.uniform(5.0, 60.0), rng.uniform(4.0, 6.0), rng.uniform(2.0, 9.0))
+                for tab, val in zip((r0ab, zab, r094, sr42), v):
+                    tab[a - 1, b - 1] = tab[b - 1, a - 1] = val
+    rad = np.zeros(94)
+    rad[0], rad[5], rad[7] = 0.32, 0.75, 0.63
+    c6 = rng.uniform(5.0, 40.0, (n, n))
+    c6 = 0.5 * (c6 + c6.T)
+    eps1 = np.array([0, 0, 0.85, 1, 1, 1.0])      # setnonb.f90:164-169
+    eps2 = np.array([0, 0, 0.5, 1, 1, 1.0])       # setnonb.f90:173-178
+    L = box_A / BOHR
+    coul_cut = 10.0 / BOHR if periodic else 50.0 / BOHR
+    if periodic:
+        coul_cut = min(coul_cut, L / 2 - 0.1)
+    zahn_a = 0.2 * BOHR
+    from math import erfc, exp, sqrt, pi
+    zac = zahn_a * coul_cut
+    zahn_par = erfc(zac) / coul_cut ** 2 + 2 * zahn_a / sqrt(pi) * exp(-zac ** 2) / coul_cut
+    return dict(
+        n=n, at=np.array(Z, dtype=np.int32), q=np.array(q), xyz=xyz, molnum=np.array(molnum, dtype=np.int32), nmols=nmol,
+        bond=np.array(bond, dtype=np.int32).reshape(-1, 2), vbond=np.array(vbond).reshape(-1, 3),
+        angl=np.array(angl, dtype=np.int32).reshape(-1, 3), vangl=np.array(vangl).reshape(-1, 2),
+        tors=np.array(tors, dtype=np.int32).reshape(-1, 6), vtors=np.array(vtors).reshape(-1, ldvt), ldvt=ldvt,
+        nci=np.array(nci, dtype=np.int32).reshape(-1, 3),
+        c6xy=np.asfortranarray(c6), r0ab=np.asfortranarray(r0ab), zab=np.asfortranarray(zab),
+        r094=np.asfortranarray(r094), sr42=np.asfortranarray(sr42), rad=rad, eps1=eps1, eps2=eps2,
+        periodic=int(periodic), zahn=int(zahn and periodic), box=np.array([L, L, L]), coul_cut=coul_cut,
+        vdw_cut=min(10.0 / BOHR, L / 2 - 0.1) if periodic else 10.0 / BOHR, cut_low=0.8 * coul_cut, zahn_a=zahn_a,
+        zahn_par=zahn_par, e_zero=-1.2345)
