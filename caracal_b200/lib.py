@@ -23,6 +23,20 @@ ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM",
           -5: "CRCL_ENOSUP", -6: "CRCL_ESTATE"}
 TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_PESWARN = 0, 1, 2, 5, 16
 
+class QmdffTables(ctypes.Structure):
+    """crcl_qmdff_tables of include/caracal_gpu.h"""
+    _fields_ = [("n", ctypes.c_int), ("at", c_int_p), ("q", c_double_p), ("molnum", c_int_p), ("nmols", ctypes.c_int),
+                ("nbond", ctypes.c_int), ("nangl", ctypes.c_int), ("ntors", ctypes.c_int), ("nhb", ctypes.c_int),
+                ("nnci", ctypes.c_int), ("ldvt", ctypes.c_int),
+                ("bond", c_int_p), ("vbond", c_double_p), ("angl", c_int_p), ("vangl", c_double_p),
+                ("tors", c_int_p), ("vtors", c_double_p), ("nci", c_int_p), ("c6xy", c_double_p),
+                ("r0ab", c_double_p), ("zab", c_double_p), ("r094", c_double_p), ("sr42", c_double_p),
+                ("rad", c_double_p), ("eps1", ctypes.c_double * 6), ("eps2", ctypes.c_double * 6),
+                ("periodic", ctypes.c_int), ("zahn", ctypes.c_int), ("box", ctypes.c_double * 3),
+                ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double), ("cut_low", ctypes.c_double),
+                ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double), ("e_zero", ctypes.c_double)]
+
+
 # every symbol include/caracal_gpu.h declares: (restype, argtypes)
 _H = ctypes.c_void_p
 SIGNATURES = {
@@ -69,20 +83,6 @@ SIGNATURES = {
     "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
 }
 
-
-
-class QmdffTables(ctypes.Structure):
-    """crcl_qmdff_tables of include/caracal_gpu.h"""
-    _fields_ = [("n", ctypes.c_int), ("at", c_int_p), ("q", c_double_p), ("molnum", c_int_p), ("nmols", ctypes.c_int),
-                ("nbond", ctypes.c_int), ("nangl", ctypes.c_int), ("ntors", ctypes.c_int), ("nhb", ctypes.c_int),
-                ("nnci", ctypes.c_int), ("ldvt", ctypes.c_int),
-                ("bond", c_int_p), ("vbond", c_double_p), ("angl", c_int_p), ("vangl", c_double_p),
-                ("tors", c_int_p), ("vtors", c_double_p), ("nci", c_int_p), ("c6xy", c_double_p),
-                ("r0ab", c_double_p), ("zab", c_double_p), ("r094", c_double_p), ("sr42", c_double_p),
-                ("rad", c_double_p), ("eps1", ctypes.c_double * 6), ("eps2", ctypes.c_double * 6),
-                ("periodic", ctypes.c_int), ("zahn", ctypes.c_int), ("box", ctypes.c_double * 3),
-                ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double), ("cut_low", ctypes.c_double),
-                ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double), ("e_zero", ctypes.c_double)]
 
 
 _lib = None
