@@ -17,6 +17,27 @@ def handle(gpu, T, nbeads=1, dt_fs=0.5):
     return g, mass
 
 
+def torsion_conditioning(T, x):
+    """min |sin phi| over the proper torsions of each image.  dphidr.f90:74-84 divides by
+    |na||nb| sin(phi) with phi = acos(na.nb) (valijkl.f90:80-98): near phi = 0 or pi a one-ulp libm
+    difference in acos is amplified by 1/sin^2(phi) in that torsion's gradient, in the reference as
+    much as here, so the comparison tolerance follows the conditioning of the reference formula."""
+    out = np.ones(x.shape[0])
+    tr = np.array([t[:4] - 1 for t in T["tors"] if t[5] != 2])
+    if len(tr) == 0:
+        return out
+    L = T["box"] if T["periodic"] else None
+
+    def img(v):
+        return v - L * np.round(v / L) if L is not None else v
+    ra = img(x[:, tr[:, 1]] - x[:, tr[:, 0]])
+    rb = img(x[:, tr[:, 2]] - x[:, tr[:, 1]])
+    rc = img(x[:, tr[:, 3]] - x[:, tr[:, 2]])
+    na, nb = np.cross(ra, rb), np.cross(rb, rc)
+    cs = (na * nb).sum(-1) / np.linalg.norm(na, axis=-1) / np.linalg.norm(nb, axis=-1)
+    return np.sqrt(np.maximum(1 - cs ** 2, 1e-30)).min(axis=1)
+
+
 @pytest.mark.parametrize("periodic,zahn,nmol,nimg", [(True, True, 8, 48), (True, False, 8, 48), (False, False, 8, 48),
                                                      (True, True, 125, 3), (False, False, 1, 16)])
 def test_egrad_matches_oracle(gpu, oracle, periodic, zahn, nmol, nimg):
@@ -28,7 +49,10 @@ def test_egrad_matches_oracle(gpu, oracle, periodic, zahn, nmol, nimg):
     Vo, go = Q.egrad(x)
     Vd, gd, _ = g.egrad(x)
     assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
-    assert C.rel_err_G(gd.reshape(go.shape), go).max() < C.TOL_EG
+    tol = np.maximum(C.TOL_EG, 4e-16 / torsion_conditioning(T, x) ** 2)
+    err = C.rel_err_G(gd.reshape(go.shape), go)
+    assert (err < tol).all(), (err / tol).max()
+    assert (tol == C.TOL_EG).mean() > 0.7     # the relaxed bound is the exception, not the rule
 
 
 def test_rpmd_with_qmdff_on_split_path(gpu, oracle):
