@@ -49,10 +49,10 @@ def test_egrad_matches_oracle(gpu, oracle, periodic, zahn, nmol, nimg):
     Vo, go = Q.egrad(x)
     Vd, gd, _ = g.egrad(x)
     assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
-    tol = np.maximum(C.TOL_EG, 4e-16 / torsion_conditioning(T, x) ** 2)
+    tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T, x) ** 2)
     err = C.rel_err_G(gd.reshape(go.shape), go)
     assert (err < tol).all(), (err / tol).max()
-    assert (tol == C.TOL_EG).mean() > 0.7     # the relaxed bound is the exception, not the rule
+    assert (tol == C.TOL_EG).mean() > 0.5     # the relaxed bound is the exception, not the rule
 
 
 def test_rpmd_with_qmdff_on_split_path(gpu, oracle):
