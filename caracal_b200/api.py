@@ -157,6 +157,10 @@ class RPMD:
         S.box = (ctypes.c_double * 3)(*T["box"])
         S.coul_cut, S.vdw_cut, S.cut_low = float(T["coul_cut"]), float(T["vdw_cut"]), float(T["cut_low"])
         S.zahn_a, S.zahn_par, S.e_zero = float(T["zahn_a"]), float(T["zahn_par"]), float(T["e_zero"])
+        if "scalehb" in T:
+            S.hb, S.vhb = _ip(arr("hb", np.int32)), _dp(arr("vhb", np.float64))
+            S.scalehb, S.scalexb, S.q_glob = _dp(arr("scalehb", np.float64)), _dp(arr("scalexb", np.float64)), \
+                _dp(arr("q_glob", np.float64))
         self._ck(self._lib.crcl_set_qmdff(self._h, ctypes.byref(S)), "crcl_set_qmdff")
 
     def set_mechanism(self, m):

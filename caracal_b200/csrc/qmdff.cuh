@@ -25,6 +25,19 @@ struct QmdffDev {
     double* vtors;
     int* nci;
     double* c6;  // [n][n] symmetric: c6xy(max,min) of the reference
+    // H/X-bond terms (ff_hb.f90)
+    int nhb, ndonor, use_hb;
+    int* hb;          // [nhb][3] A,B,H 0-based
+    double* vhb;      // [nhb][2]
+    int* isH;         // [nhb]: third atom is hydrogen -> eabhag, else eabxag
+    int* donor;       // [ndonor][3]: H, A, kind (1 halogen / 2 hydrogen), from the bond list
+    double* dthr;     // [ndonor]: dum1 of ff_hb.f90:157,239
+    double* dcoef;    // [ndonor]: halogen: scalexb*hbpara(-6.5,1,q_H); hydrogen: hbpara(10,5,q_A)*scalehb(A)
+    double* dscal;    // [ndonor]: hydrogen: scalehb(at(A))
+    double* acc_c1;   // [n]: hbpara(10,5,q_j)*scalehb(at(j))
+    double* acc_s;    // [n]: scalehb(at(j))
+    int* acc_no;      // [n]: at(j) is N or O (halogen-bond acceptor)
+    double radH;      // rad(1)
     // per element-type tables
     double rad[QM_MAXTYPE];
     double r0ab[QM_MAXTYPE][QM_MAXTYPE], zab[QM_MAXTYPE][QM_MAXTYPE], r094[QM_MAXTYPE][QM_MAXTYPE],

@@ -7,9 +7,11 @@
 //   ff_nonb.f90:88-193,339-417   nci pair list: D3-BJ-like dispersion, exponential repulsion,
 //                       Coulomb (Zahn / cut-off + exp_switch.f90 / plain)  -> qm_nci_kernel
 //   ff_nonb.f90:198-332,421-512  inter-molecular O(N^2) loops             -> qm_inter_kernel
+//   ff_hb.f90:35-280    hb list (eabhag.f90 analytic / eabxag.f90 + eabx.f90 numeric) and the
+//                       on-the-fly donor x acceptor search for nmols > 1   -> qm_hb_list_kernel,
+//                                                                             qm_hb_search_kernel
 // The SPME/Ewald branch of ff_nonb is dead code in the reference (ewald=.false., :337) and has
-// no counterpart.  ff_hb (H/X-bond terms) is not implemented yet: crcl_set_qmdff refuses tables
-// with nhb > 0.
+// no counterpart.
 //
 // Mapping: one thread per (image, term) for the lists, gradients accumulated with FP64
 // atomics (red.global.add.f64; a term touches 2-4 atoms, contention is negligible).  The
@@ -475,6 +477,172 @@ __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const d
     block_sum_to(e, &V[img]);
 }
 
+// ---- H/X-bond terms -------------------------------------------------------------------------------
+// eabhag.f90:30-210 (analytic); only drah is imaged, as in the reference (F9)
+__device__ __forceinline__ double eabhag_dev(const QmdffDev& D, const double* x, double* gi, int A, int B, int H,
+                                             double ca, double cb)
+{
+    double xa[3], xb[3], xh[3], drah[3], drbh[3], drab[3];
+    ld3(x, A, xa);
+    ld3(x, B, xb);
+    ld3(x, H, xh);
+    for (int c = 0; c < 3; c++) {
+        drah[c] = xa[c] - xh[c];
+        drbh[c] = xb[c] - xh[c];
+        drab[c] = xa[c] - xb[c];
+    }
+    if (D.periodic) box_image(D, drah);
+    const double rab2 = dot3(drab, drab), rab = sqrt(rab2), rah2 = dot3(drah, drah), rah = sqrt(rah2),
+                 rbh2 = dot3(drbh, drbh), rbh = sqrt(rbh2);
+    const double ratio = pow(rab / 8.0, 12.0);
+    const double rdampl = 1.0 / (1.0 + ratio) / rab2 / rab;
+    const bool far = rah2 > rbh2;
+    const double aprod = far ? 1.0 / rbh / rab : 1.0 / rah / rab;
+    const double cosabh = far ? -dot3(drbh, drab) * aprod : dot3(drah, drab) * aprod;
+    double aterm = 0.5 * (cosabh + 1.0);
+    const double a2 = aterm * aterm, a5 = a2 * a2 * aterm;   // aterm**(alp3-1), alp3 = 6
+    aterm = aterm * a5;
+    const double apref = 3.0 * a5;
+    const double rah4 = rah2 * rah2, rbh4 = rbh2 * rbh2, denom = 1.0 / (rah4 + rbh4);
+    const double da = (ca * rah4 + cb * rbh4) * denom;
+    const double eabh = -da * rdampl * aterm;
+    if (eabh > -1.e-8) return 0.0;
+    const double gia = -(4.0 * (ca - cb) * rah2 * rbh4 * denom * denom) * rdampl * aterm;
+    const double gib = -(4.0 * (cb - ca) * rbh2 * rah4 * denom * denom) * rdampl * aterm;
+    const double gid = rdampl * rdampl * rab * (3.0 + 15.0 * ratio) * da * aterm;
+    const double gip = -da * rdampl * apref;
+    double ga[3], gb[3], gh[3];
+    for (int c = 0; c < 3; c++) {
+        ga[c] = gia * drah[c];
+        gb[c] = gib * drbh[c];
+        gh[c] = -ga[c] - gb[c];
+        const double dg = gid * drab[c];
+        ga[c] += dg;
+        gb[c] -= dg;
+        if (far) {
+            const double d1 = gip * (-aprod * drbh[c] - cosabh * drab[c] / rab2);
+            const double d2 = gip * (aprod * drab[c] + cosabh * drbh[c] / rbh2);
+            ga[c] += d1;
+            gh[c] += d2;
+            gb[c] -= d1 + d2;
+        } else {
+            const double d1 = gip * (-aprod * drah[c] + cosabh * drab[c] / rab2);
+            const double d2 = gip * (-aprod * drab[c] + cosabh * drah[c] / rah2);
+            gb[c] += d1;
+            gh[c] += d2;
+            ga[c] -= d1 + d2;
+        }
+    }
+    add3(gi, A, ga);
+    add3(gi, B, gb);
+    add3(gi, H, gh);
+    return eabh;
+}
+// eabx.f90:30-110 on explicit positions
+__device__ __forceinline__ double eabx_dev(const QmdffDev& D, const double xa[3], const double xb[3],
+                                           const double xh[3], double ca)
+{
+    double r[3];
+    for (int c = 0; c < 3; c++) r[c] = xa[c] - xb[c];
+    if (D.periodic) box_image(D, r);
+    const double rab2 = dot3(r, r);
+    const double dampl = 1.0 / (1.0 + pow(rab2 / 120.0, 6.0));
+    for (int c = 0; c < 3; c++) r[c] = xa[c] - xh[c];
+    if (D.periodic) box_image(D, r);
+    const double d2ik = dot3(r, r);
+    for (int c = 0; c < 3; c++) r[c] = xh[c] - xb[c];
+    if (D.periodic) box_image(D, r);
+    const double d2jk = dot3(r, r);
+    const double term = (d2ik > d2jk) ? 0.5 * (rab2 + d2jk - d2ik) / sqrt(rab2 * d2jk)
+                                      : 0.5 * (rab2 + d2ik - d2jk) / sqrt(rab2 * d2ik);
+    return -ca * dampl * pow(0.5 * (term + 1.0), 6.0) / d2jk;
+}
+// eabxag.f90:30-150: central differences with step 1e-6; the reference assigns the scalar
+// (er-el)*dum to all three components on every pass, so the z-derivative is added to x, y and z (F9)
+__device__ __forceinline__ double eabxag_dev(const QmdffDev& D, const double* x, double* gi, int A, int B, int H,
+                                             double ca)
+{
+    const double step = 1.e-6, dum = 1.0 / (2.0 * step);
+    double p[3][3];
+    ld3(x, A, p[0]);
+    ld3(x, B, p[1]);
+    ld3(x, H, p[2]);
+    const double e0 = eabx_dev(D, p[0], p[1], p[2], ca);
+    const int who[3] = {A, B, H};
+    for (int w = 0; w < 3; w++) {
+        double gl = 0.0;
+        for (int j = 0; j < 3; j++) {
+            p[w][j] = p[w][j] + step;
+            const double er = eabx_dev(D, p[0], p[1], p[2], ca);
+            p[w][j] = p[w][j] - step * 2.0;
+            const double el = eabx_dev(D, p[0], p[1], p[2], ca);
+            p[w][j] = p[w][j] + step;
+            gl = (er - el) * dum;
+        }
+        const double v[3] = {gl, gl, gl};
+        add3(gi, who[w], v);
+    }
+    return e0;
+}
+__device__ __forceinline__ double dist_dev(const QmdffDev& D, const double* x, int a, int b, bool image)
+{
+    double r[3] = {x[3 * a] - x[3 * b], x[3 * a + 1] - x[3 * b + 1], x[3 * a + 2] - x[3 * b + 2]};
+    if (image && D.periodic) box_image(D, r);
+    return sqrt(dot3(r, r));
+}
+
+__global__ void __launch_bounds__(128) qm_hb_list_kernel(const QmdffDev D, const double* __restrict__ xyz,
+                                                         double* __restrict__ V, double* __restrict__ g)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+    const double* x = xyz + (size_t)img * 3 * D.n;
+    double* gi = g + (size_t)img * 3 * D.n;
+    double e = 0.0;
+    if (k < D.nhb) {
+        const int A = D.hb[3 * k], B = D.hb[3 * k + 1], H = D.hb[3 * k + 2];
+        if (!(dist_dev(D, x, A, B, true) > 15.0)) {
+            if (D.isH[k])
+                e = eabhag_dev(D, x, gi, A, B, H, D.vhb[2 * k], D.vhb[2 * k + 1]);
+            else
+                e = eabxag_dev(D, x, gi, A, B, H, D.vhb[2 * k]);
+        }
+    }
+    block_sum_to(e, &V[img]);
+}
+
+// ff_hb.f90:90-274: every (donor bond, atom j of another molecule) pair; grid (j tiles, donors, images)
+__global__ void __launch_bounds__(128) qm_hb_search_kernel(const QmdffDev D, const double* __restrict__ xyz,
+                                                           double* __restrict__ V, double* __restrict__ g)
+{
+    constexpr double c12 = (double)1.2f, c13 = (double)1.3f, b0 = (double)0.52917726f;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, img = blockIdx.z;
+    const double* x = xyz + (size_t)img * 3 * D.n;
+    double* gi = g + (size_t)img * 3 * D.n;
+    double e = 0.0;
+    if (j < D.n) {
+        const int H = D.donor[3 * d], A = D.donor[3 * d + 1], kind = D.donor[3 * d + 2];
+        if (D.molnum[H] != D.molnum[j]) {
+            if (kind == 1) {
+                if (D.acc_no[j]) {
+                    const double ri = dist_dev(D, x, A, H, true), rj = dist_dev(D, x, j, H, true);
+                    const double dum2 = c12 * (D.rad[D.type[j]] + D.rad[D.type[H]]) / b0;
+                    if (ri < D.dthr[d] || rj < dum2)
+                        if (!(dist_dev(D, x, A, j, false) > 15.0)) e = eabxag_dev(D, x, gi, A, j, H, D.dcoef[d]);
+                }
+            } else {
+                if (D.dscal[d] * D.acc_s[j] > 1e-6) {
+                    const double ri = dist_dev(D, x, A, H, true), rj = dist_dev(D, x, j, H, true);
+                    const double dum2 = c13 * (D.rad[D.type[j]] + D.radH) / b0;
+                    if (ri < D.dthr[d] || rj < dum2)
+                        if (!(dist_dev(D, x, A, j, true) > 15.0))
+                            e = eabhag_dev(D, x, gi, j, A, H, D.acc_c1[j], D.dcoef[d]);
+                }
+            }
+        }
+    }
+    block_sum_to(e, &V[img]);
+}
+
 __global__ void qm_init_kernel(double* V, int nimg, double e_zero)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,6 +678,24 @@ cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double
                 nl++;
             }
         }
+        if (D->use_hb && !(D->nhb < 1 && D->nmols == 0)) {   // ff_hb.f90:49 early return
+            if (D->nhb > 0) {
+                qm_hb_list_kernel<<<dim3((D->nhb + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                nl++;
+            }
+            if (D->nmols > 1 && D->ndonor > 0) {
+                for (int d0 = 0; d0 < D->ndonor; d0 += 65535) {
+                    QmdffDev Dd = *D;
+                    const int nd = std::min(65535, D->ndonor - d0);
+                    Dd.donor = D->donor + 3 * d0;
+                    Dd.dthr = D->dthr + d0;
+                    Dd.dcoef = D->dcoef + d0;
+                    Dd.dscal = D->dscal + d0;
+                    qm_hb_search_kernel<<<dim3((D->n + 127) / 128, nd, ni), 128, 0, s>>>(Dd, x, V, g);
+                    nl++;
+                }
+            }
+        }
     }
     if (launches) *launches += nl;
     return cudaGetLastError();
@@ -531,9 +717,9 @@ static T* up(const T* h, size_t n, bool& ok)
 int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err)
 {
     *out = nullptr;
-    if (T->nhb > 0) {
-        *err = "QMDFF H/X-bond terms (ff_hb) are not implemented on the device yet";
-        return CRCL_ENOSUP;
+    if (T->nhb > 0 && (!T->scalehb || !T->hb || !T->vhb)) {
+        *err = "nhb > 0 needs hb, vhb and the scalehb/scalexb/q_glob tables";
+        return CRCL_EINVAL;
     }
     const int n = T->n;
     QmdffDev* D = new QmdffDev();
@@ -632,7 +818,78 @@ int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err)
             const int lo = a < b ? a : b, hi = a < b ? b : a;
             c6[(size_t)a * n + b] = T->c6xy[(size_t)hi + (size_t)n * lo];
         }
+    // ff_hb tables: hb list, donor bonds (static topology) and per-atom acceptor data
+    D->use_hb = T->scalehb ? 1 : 0;
+    D->nhb = D->use_hb ? T->nhb : 0;
+    std::vector<int> hb(3 * (size_t)D->nhb), isH(D->nhb), donor, accno(n, 0);
+    std::vector<double> dthr, dcoef, dscal, accc1(n, 0.0), accs(n, 0.0);
+    if (D->use_hb) {
+        if (!T->scalexb || !T->q_glob) {
+            *err = "scalehb given without scalexb / q_glob";
+            delete D;
+            return CRCL_EINVAL;
+        }
+        auto hbpara = [](double a, double b, double q) { return std::exp(-a * q) / (std::exp(-a * q) + b); };
+        const double c12 = (double)1.2f, c13 = (double)1.3f, b0 = (double)0.52917726f;
+        for (int k = 0; k < D->nhb; k++) {
+            for (int c = 0; c < 3; c++) {
+                if (!idx_ok(T->hb[3 * k + c])) good = false;
+                hb[3 * k + c] = T->hb[3 * k + c] - 1;
+            }
+            if (good) isH[k] = T->at[hb[3 * k + 2]] == 1;
+        }
+        if (!good) {
+            *err = "hb list entry out of range";
+            delete D;
+            return CRCL_EINVAL;
+        }
+        D->radH = T->rad[0];
+        for (int a = 0; a < n; a++) {
+            const int z = T->at[a];
+            accs[a] = T->scalehb[z - 1];
+            accc1[a] = hbpara(10.0, 5.0, T->q_glob[a]) * T->scalehb[z - 1];
+            accno[a] = (z == 7 || z == 8);
+        }
+        auto isX = [](int z) { return z == 17 || z == 35 || z == 53 || z == 85; };
+        auto isAcc = [](int z) { return z == 7 || z == 8 || z == 9 || z == 16 || z == 17; };
+        for (int m = 0; m < T->nbond && T->nmols > 1; m++) {
+            const int i1 = T->bond[2 * m] - 1, i2 = T->bond[2 * m + 1] - 1;
+            const int z1 = T->at[i1], z2 = T->at[i2];
+            int xh = -1, xa = -1;
+            if (isX(z1)) {
+                if (z2 != 1) xh = i1, xa = i2;
+            } else if (isX(z2)) {
+                if (z1 != 1) xh = i2, xa = i1;
+            }
+            if (xh >= 0) {
+                donor.insert(donor.end(), {xh, xa, 1});
+                dthr.push_back(c12 * (T->rad[T->at[xa] - 1] + T->rad[T->at[xh] - 1]) / b0);
+                dcoef.push_back(T->scalexb[T->at[xh] - 1] * hbpara(-6.5, 1.0, T->q_glob[xh]));
+                dscal.push_back(0.0);
+            }
+            int hh = -1, ha = -1;
+            if (z1 == 1 && isAcc(z2)) hh = i1, ha = i2;
+            if (z2 == 1 && isAcc(z1)) hh = i2, ha = i1;
+            if (hh >= 0) {
+                donor.insert(donor.end(), {hh, ha, 2});
+                dthr.push_back(c13 * (T->rad[T->at[ha] - 1] + T->rad[0]) / b0);
+                dcoef.push_back(hbpara(10.0, 5.0, T->q_glob[ha]) * T->scalehb[T->at[ha] - 1]);
+                dscal.push_back(T->scalehb[T->at[ha] - 1]);
+            }
+        }
+        D->ndonor = (int)dthr.size();
+    }
     bool ok = true;
+    D->hb = up(hb.data(), hb.size(), ok);
+    D->vhb = up(D->nhb ? T->vhb : nullptr, 2 * (size_t)D->nhb, ok);
+    D->isH = up(isH.data(), isH.size(), ok);
+    D->donor = up(donor.data(), donor.size(), ok);
+    D->dthr = up(dthr.data(), dthr.size(), ok);
+    D->dcoef = up(dcoef.data(), dcoef.size(), ok);
+    D->dscal = up(dscal.data(), dscal.size(), ok);
+    D->acc_c1 = up(accc1.data(), accc1.size(), ok);
+    D->acc_s = up(accs.data(), accs.size(), ok);
+    D->acc_no = up(accno.data(), accno.size(), ok);
     D->type = up(type.data(), n, ok);
     D->molnum = up(mol.data(), n, ok);
     D->q = up(T->q, n, ok);
@@ -667,6 +924,16 @@ void qmdff_free(QmdffDev* D)
     cudaFree(D->vtors);
     cudaFree(D->nci);
     cudaFree(D->c6);
+    cudaFree(D->hb);
+    cudaFree(D->vhb);
+    cudaFree(D->isH);
+    cudaFree(D->donor);
+    cudaFree(D->dthr);
+    cudaFree(D->dcoef);
+    cudaFree(D->dscal);
+    cudaFree(D->acc_c1);
+    cudaFree(D->acc_s);
+    cudaFree(D->acc_no);
     delete D;
 }
 

@@ -34,7 +34,9 @@ class QmdffTables(ctypes.Structure):
                 ("rad", c_double_p), ("eps1", ctypes.c_double * 6), ("eps2", ctypes.c_double * 6),
                 ("periodic", ctypes.c_int), ("zahn", ctypes.c_int), ("box", ctypes.c_double * 3),
                 ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double), ("cut_low", ctypes.c_double),
-                ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double), ("e_zero", ctypes.c_double)]
+                ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double), ("e_zero", ctypes.c_double),
+                ("hb", c_int_p), ("vhb", c_double_p), ("scalehb", c_double_p), ("scalexb", c_double_p),
+                ("q_glob", c_double_p)]
 
 
 # every symbol include/caracal_gpu.h declares: (restype, argtypes)

@@ -126,6 +126,11 @@ typedef struct crcl_qmdff_tables {
     double box[3];        /* boxlen_x, boxlen_y, boxlen_z */
     double coul_cut, vdw_cut, cut_low, zahn_a, zahn_par;
     double e_zero;        /* E_zero1 (ESHIFT keyword) */
+    /* ff_hb.f90: hb(3,nhb) = A,B,H ; vhb(2,nhb); scalehb_glob(94), scalexb_glob(94), q_glob(n).
+     * scalehb == NULL switches the H/X-bond terms off entirely (then nhb must be 0). */
+    const int *hb;
+    const double *vhb;
+    const double *scalehb, *scalexb, *q_glob;
 } crcl_qmdff_tables;
 /* handle must have been created with pes_id = CRCL_PES_QMDFF and natoms = T->n */
 int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables *T);

@@ -233,7 +233,8 @@ class _QmdffStruct(ctypes.Structure):
                 ("periodic", ctypes.c_int), ("zahn", ctypes.c_int),
                 ("box", ctypes.c_double * 3), ("coul_cut", ctypes.c_double), ("vdw_cut", ctypes.c_double),
                 ("cut_low", ctypes.c_double), ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double),
-                ("e_zero", ctypes.c_double)]
+                ("e_zero", ctypes.c_double),
+                ("nhb", ctypes.c_int), ("hb", ip), ("vhb", dp), ("scalehb", dp), ("scalexb", dp), ("q_glob", dp)]
 
 
 class Qmdff:
@@ -266,6 +267,11 @@ class Qmdff:
         S.box = (ctypes.c_double * 3)(*T["box"])
         S.coul_cut, S.vdw_cut, S.cut_low = float(T["coul_cut"]), float(T["vdw_cut"]), float(T["cut_low"])
         S.zahn_a, S.zahn_par, S.e_zero = float(T["zahn_a"]), float(T["zahn_par"]), float(T["e_zero"])
+        S.nhb = int(T.get("nhb", 0))
+        if "scalehb" in T:
+            S.hb, S.vhb = _i(arr("hb", np.int32)), _d(arr("vhb", np.float64))
+            S.scalehb, S.scalexb, S.q_glob = _d(arr("scalehb", np.float64)), _d(arr("scalexb", np.float64)), \
+                _d(arr("q_glob", np.float64))
         self.S = S
         self.n = S.n
         self.L.orc_qmdff_egrad.argtypes = [ctypes.POINTER(_QmdffStruct), dp, ctypes.c_int, dp, dp]

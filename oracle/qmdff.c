@@ -13,7 +13,10 @@
  *                                        dispersion/repulsion and Coulomb (Zahn / cut-off /
  *                                        exp_switch.f90).  The Ewald/SPME branch is dead code
  *                                        (ewald=.false. at :337).
- *   gradient.f90:341-362   orc_qmdff_egrad  e = ff_eg + ff_nonb (+ ff_hb: NOT restated yet) + E_zero1
+ *   ff_hb.f90:35-280       orc_ff_hb     hb list + on-the-fly donor/acceptor search (nmols > 1);
+ *   eabhag.f90 (analytic H-bond, images only drah: F9), eabxag.f90 + eabx.f90 (X-bond, numeric
+ *   gradient whose last component is broadcast to all three: F9), hbpara.f90
+ *   gradient.f90:341-362   orc_qmdff_egrad  e = ff_eg + ff_nonb + ff_hb + E_zero1
  * Tables (c6xy, r0ab, zab, r094_mod, sr42, rad, eps1, eps2) are inputs, as they are for the
  * reference routines (built once by prepare.f90 / setnonb.f90); (94,94) and (n,n)
  * arrays are passed in Fortran order.  Atom indices are 1-based in the lists, as in the .qmdff file.
@@ -463,8 +466,236 @@ void orc_ff_nonb(const orc_qmdff *f, const double *xyz, double *e_io, double *g)
     *e_io = *e_io + e;
 }
 
-/* gradient.f90:341-362, nqmdff = 1 (ff_hb not restated: nhb must be 0 and, for nmols > 1, the
- * system must contain no H-bond donors/acceptors -- asserted by the caller) */
+/* eabhag.f90:30-210 */
+static void eabhag(const orc_qmdff *f, const double *xyz, int A, int B, int H, double ca, double cb, double *energy,
+                   double *g)
+{
+    const double longcut = 8.0, alp7 = 12.0, alp3 = 6.0;
+    double drah[3], drbh[3], drab[3], ga[3], gb[3], gh[3], dg[3], dg2[3];
+    double rab2, rab, rah2, rah, rbh2, rbh, ratio, rdampl, aprod, cosabh, aterm, apref, rah4, rbh4, denom, da, eabh, gi;
+    int c;
+    for (c = 0; c < 3; c++) {
+        drah[c] = X(A, c) - X(H, c);
+        drbh[c] = X(B, c) - X(H, c);
+        drab[c] = X(A, c) - X(B, c);
+    }
+    if (f->periodic) box_image(f, drah); /* only drah is imaged (eabhag.f90:60-62) */
+    rab2 = drab[0] * drab[0] + drab[1] * drab[1] + drab[2] * drab[2];
+    rab = sqrt(rab2);
+    rah2 = drah[0] * drah[0] + drah[1] * drah[1] + drah[2] * drah[2];
+    rah = sqrt(rah2);
+    rbh2 = drbh[0] * drbh[0] + drbh[1] * drbh[1] + drbh[2] * drbh[2];
+    rbh = sqrt(rbh2);
+    ratio = pow(rab / longcut, alp7);
+    rdampl = 1.0 / (1.0 + ratio);
+    rdampl = rdampl / rab2 / rab;
+    if (rah2 > rbh2) {
+        aprod = 1.0 / rbh / rab;
+        cosabh = -(drbh[0] * drab[0] + drbh[1] * drab[1] + drbh[2] * drab[2]) * aprod;
+    } else {
+        aprod = 1.0 / rah / rab;
+        cosabh = (drah[0] * drab[0] + drah[1] * drab[1] + drah[2] * drab[2]) * aprod;
+    }
+    aterm = 0.5 * (cosabh + 1.0);
+    apref = pow(aterm, alp3 - 1);
+    aterm = aterm * apref;
+    apref = alp3 * 0.5 * apref;
+    rah4 = rah2 * rah2;
+    rbh4 = rbh2 * rbh2;
+    denom = 1.0 / (rah4 + rbh4);
+    da = (ca * rah4 + cb * rbh4) * denom;
+    eabh = -da * rdampl * aterm;
+    if (eabh > -1.e-8) return;
+    *energy = *energy + eabh;
+    gi = 4.0 * (ca - cb) * rah2 * rbh4 * denom * denom;
+    gi = -gi * rdampl * aterm;
+    for (c = 0; c < 3; c++) ga[c] = gi * drah[c];
+    gi = 4.0 * (cb - ca) * rbh2 * rah4 * denom * denom;
+    gi = -gi * rdampl * aterm;
+    for (c = 0; c < 3; c++) {
+        gb[c] = gi * drbh[c];
+        gh[c] = -ga[c] - gb[c];
+    }
+    gi = rdampl * rdampl * rab * (3.0 + (3.0 + alp7) * ratio);
+    gi = gi * da * aterm;
+    for (c = 0; c < 3; c++) {
+        dg[c] = gi * drab[c];
+        ga[c] = ga[c] + dg[c];
+        gb[c] = gb[c] - dg[c];
+    }
+    gi = -da * rdampl * apref;
+    if (rah2 > rbh2) {
+        for (c = 0; c < 3; c++) {
+            dg[c] = gi * (-aprod * drbh[c] - cosabh * drab[c] / rab2);
+            dg2[c] = gi * (aprod * drab[c] + cosabh * drbh[c] / rbh2);
+            ga[c] = ga[c] + dg[c];
+            gh[c] = gh[c] + dg2[c];
+            gb[c] = gb[c] - dg[c] - dg2[c];
+        }
+    } else {
+        for (c = 0; c < 3; c++) {
+            dg[c] = gi * (-aprod * drah[c] + cosabh * drab[c] / rab2);
+            dg2[c] = gi * (-aprod * drab[c] + cosabh * drah[c] / rah2);
+            gb[c] = gb[c] + dg[c];
+            gh[c] = gh[c] + dg2[c];
+            ga[c] = ga[c] - dg[c] - dg2[c];
+        }
+    }
+    for (c = 0; c < 3; c++) {
+        G(A, c) += ga[c];
+        G(B, c) += gb[c];
+        G(H, c) += gh[c];
+    }
+}
+
+/* eabx.f90:30-110 */
+static double eabx(const orc_qmdff *f, const double *xyz, int A, int B, int H, double ca)
+{
+    const double longcut = 120., alp7 = 6, alp3 = 6;
+    double rb[3], rab2, dampl, d2ik, d2jk, xy, term, aterm;
+    int c;
+    for (c = 0; c < 3; c++) rb[c] = X(A, c) - X(B, c);
+    if (f->periodic) box_image(f, rb);
+    rab2 = rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2];
+    dampl = 1. / (1. + pow(rab2 / longcut, alp7));
+    for (c = 0; c < 3; c++) rb[c] = X(A, c) - X(H, c);
+    if (f->periodic) box_image(f, rb);
+    d2ik = rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2];
+    for (c = 0; c < 3; c++) rb[c] = X(H, c) - X(B, c);
+    if (f->periodic) box_image(f, rb);
+    d2jk = rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2];
+    if (d2ik > d2jk) {
+        xy = sqrt(rab2 * d2jk);
+        term = 0.5 * (rab2 + d2jk - d2ik) / xy;
+    } else {
+        xy = sqrt(rab2 * d2ik);
+        term = 0.5 * (rab2 + d2ik - d2jk) / xy;
+    }
+    aterm = pow(0.5 * (term + 1.0), alp3);
+    return -ca * dampl * aterm / d2jk;
+}
+
+/* eabxag.f90:30-150: numeric gradient, step 1e-6; g_local_* = (er-el)*dum assigns the scalar to all
+ * three components on every pass, so the z-derivative is what gets added to x, y and z (F9).  The
+ * coordinates are perturbed in place and restored by +step (eabxag.f90:108-113), as here. */
+static void eabxag(const orc_qmdff *f, double *xyz, int A, int B, int H, double ca, double *energy, double *g)
+{
+    const double step = 1.e-6, dum = 1. / (2.0 * step);
+    const int who[3] = {A, B, H};
+    double er, el, gl[3] = {0, 0, 0};
+    int w, j, c;
+    er = eabx(f, xyz, A, B, H, ca);
+    *energy = *energy + er;
+    for (w = 0; w < 3; w++) {
+        const int at = who[w];
+        for (j = 0; j < 3; j++) {
+            X(at, j) = X(at, j) + step;
+            er = eabx(f, xyz, A, B, H, ca);
+            X(at, j) = X(at, j) - step * 2.0;
+            el = eabx(f, xyz, A, B, H, ca);
+            X(at, j) = X(at, j) + step;
+            gl[w] = (er - el) * dum;
+        }
+        for (c = 0; c < 3; c++) G(at, c) += gl[w];
+    }
+}
+
+static double hbpara(double a, double b, double q) { return exp(-a * q) / (exp(-a * q) + b); }
+
+static double dist_img(const orc_qmdff *f, const double *xyz, int a, int b, int image)
+{
+    double r[3];
+    int c;
+    for (c = 0; c < 3; c++) r[c] = X(a, c) - X(b, c);
+    if (image && f->periodic) box_image(f, r);
+    return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+}
+
+/* ff_hb.f90:35-280: ADDS to e and g.  xyz is not const: eabxag perturbs and restores it. */
+void orc_ff_hb(const orc_qmdff *f, double *xyz, double *e_io, double *g)
+{
+    double eh = *e_io;
+    int k, i, j;
+    if (f->nhb < 1 && f->nmols == 0) return;
+    for (k = 0; k < f->nhb; k++) {
+        const int i1 = f->hb[3 * k], i2 = f->hb[3 * k + 1], ih = f->hb[3 * k + 2];
+        if (dist_img(f, xyz, i1, i2, 1) > 15.0) continue;
+        if (f->at[ih - 1] == 1)
+            eabhag(f, xyz, i1, i2, ih, f->vhb[2 * k], f->vhb[2 * k + 1], &eh, g);
+        else
+            eabxag(f, xyz, i1, i2, ih, f->vhb[2 * k], &eh, g);
+    }
+    if (f->nmols > 1) {
+        const double c12 = (double)1.2f, c13 = (double)1.3f, b0 = (double)0.52917726f;
+        for (i = 0; i < f->nbond; i++) {
+            const int i1 = f->bond[2 * i], i2 = f->bond[2 * i + 1];
+            const int z1 = f->at[i1 - 1], z2 = f->at[i2 - 1];
+            int at_H = 0, at_A = 0, halogen = 0, hydrogen = 0;
+            if (z1 == 17 || z1 == 35 || z1 == 53 || z1 == 85) {
+                if (z2 != 1) {
+                    at_H = i1;
+                    at_A = i2;
+                    halogen = 1;
+                }
+            } else if (z2 == 17 || z2 == 35 || z2 == 53 || z2 == 85) {
+                if (z1 != 1) {
+                    at_H = i2;
+                    at_A = i1;
+                    halogen = 1;
+                }
+            }
+            if (halogen)
+                for (j = 1; j <= f->n; j++) {
+                    const int zj = f->at[j - 1];
+                    double ri, rj, dum1, dum2, r;
+                    if (f->molnum[at_H - 1] == f->molnum[j - 1]) continue;
+                    if (!(zj == 7 || zj == 8)) continue;
+                    ri = dist_img(f, xyz, at_A, at_H, 1);
+                    rj = dist_img(f, xyz, j, at_H, 1);
+                    dum1 = c12 * (f->rad[f->at[at_A - 1] - 1] + f->rad[f->at[at_H - 1] - 1]) / b0;
+                    dum2 = c12 * (f->rad[zj - 1] + f->rad[f->at[at_H - 1] - 1]) / b0;
+                    if (ri < dum1 || rj < dum2) {
+                        r = dist_img(f, xyz, at_A, j, 0); /* not imaged (ff_hb.f90:159-161) */
+                        if (r > 15.0) continue;
+                        dum1 = hbpara(-6.5, 1.0, f->q_glob[at_H - 1]);
+                        eabxag(f, xyz, at_A, j, at_H, f->scalexb[f->at[at_H - 1] - 1] * dum1, &eh, g);
+                    }
+                }
+            if (z1 == 1 && (z2 == 7 || z2 == 8 || z2 == 9 || z2 == 16 || z2 == 17)) {
+                at_H = i1;
+                at_A = i2;
+                hydrogen = 1;
+            }
+            if (z2 == 1 && (z1 == 7 || z1 == 8 || z1 == 9 || z1 == 16 || z1 == 17)) {
+                at_H = i2;
+                at_A = i1;
+                hydrogen = 1;
+            }
+            if (hydrogen)
+                for (j = 1; j <= f->n; j++) {
+                    const int zj = f->at[j - 1];
+                    double cpar, ri, rj, dum1, dum2, r, c1, c2;
+                    if (f->molnum[at_H - 1] == f->molnum[j - 1]) continue;
+                    cpar = f->scalehb[f->at[at_A - 1] - 1] * f->scalehb[zj - 1];
+                    if (!(cpar > 1e-6)) continue;
+                    ri = dist_img(f, xyz, at_A, at_H, 1);
+                    rj = dist_img(f, xyz, j, at_H, 1);
+                    dum1 = c13 * (f->rad[f->at[at_A - 1] - 1] + f->rad[0]) / b0;
+                    dum2 = c13 * (f->rad[zj - 1] + f->rad[0]) / b0;
+                    if (ri < dum1 || rj < dum2) {
+                        r = dist_img(f, xyz, at_A, j, 1);
+                        if (r > 15.0) continue;
+                        c2 = hbpara(10.0, 5.0, f->q_glob[at_A - 1]) * f->scalehb[f->at[at_A - 1] - 1];
+                        c1 = hbpara(10.0, 5.0, f->q_glob[j - 1]) * f->scalehb[zj - 1];
+                        eabhag(f, xyz, j, at_A, at_H, c1, c2, &eh, g);
+                    }
+                }
+        }
+    }
+    *e_io = eh;
+}
+
+/* gradient.f90:341-362, nqmdff = 1 */
 void orc_qmdff_egrad(const orc_qmdff *f, const double *xyz, int nimg, double *V, double *g)
 {
     int s;
@@ -472,6 +703,13 @@ void orc_qmdff_egrad(const orc_qmdff *f, const double *xyz, int nimg, double *V,
         double e = 0.0;
         orc_ff_eg(f, xyz + (size_t)s * 3 * f->n, &e, g + (size_t)s * 3 * f->n);
         orc_ff_nonb(f, xyz + (size_t)s * 3 * f->n, &e, g + (size_t)s * 3 * f->n);
+        if (f->scalehb) {
+            /* eabxag perturbs xyz in place: work on a copy so the caller's array stays const */
+            double *tmp = (double *)malloc(sizeof(double) * 3 * f->n);
+            memcpy(tmp, xyz + (size_t)s * 3 * f->n, sizeof(double) * 3 * f->n);
+            orc_ff_hb(f, tmp, &e, g + (size_t)s * 3 * f->n);
+            free(tmp);
+        }
         V[s] = e + f->e_zero;
     }
 }

@@ -25,9 +25,16 @@ typedef struct orc_qmdff {
     int periodic, zahn;
     double box[3], coul_cut, vdw_cut, cut_low, zahn_a, zahn_par;
     double e_zero;
+    /* H/X-bond terms (ff_hb.f90) */
+    int nhb;
+    const int *hb;            /* (3,nhb): A, B, H */
+    const double *vhb;        /* (2,nhb) */
+    const double *scalehb, *scalexb; /* scalehb_glob(94), scalexb_glob(94) */
+    const double *q_glob;     /* (n) */
 } orc_qmdff;
 void orc_ff_eg(const orc_qmdff *f, const double *xyz, double *e, double *g);
 void orc_ff_nonb(const orc_qmdff *f, const double *xyz, double *e_io, double *g);
+void orc_ff_hb(const orc_qmdff *f, double *xyz, double *e_io, double *g);
 void orc_qmdff_egrad(const orc_qmdff *f, const double *xyz, int nimg, double *V, double *g);
 #ifdef __cplusplus
 }

@@ -23,6 +23,12 @@ FORMALDEHYDE = dict(
     bonds=[(1, 2), (1, 3), (1, 4)], inversions=[(2, 1, 3, 4)])   # (i, centre j, k, l)
 
 
+CHLOROMETHANE = dict(
+    Z=[6, 17, 1, 1, 1],
+    xyz=np.array([[0.0, 0.0, 0.0], [1.78, 0.0, 0.0], [-0.36, 1.03, 0.0], [-0.36, -0.51, 0.89], [-0.36, -0.51, -0.89]]),
+    bonds=[(1, 2), (1, 3), (1, 4), (1, 5)], inversions=[])
+
+
 def _topology(tpl):
     n = len(tpl["Z"])
     nb = {i: set() for i in range(1, n + 1)}
@@ -54,17 +60,21 @@ def _topology(tpl):
     return angles, tors, nci
 
 
-def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_formaldehyde=0.25):
+def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_formaldehyde=0.25, hb=False,
+                frac_halogen=0.0):
+    """hb=True adds the ff_hb tables (scalehb/scalexb, q_glob, an hb list); frac_halogen > 0 adds
+    chloromethane molecules so that the X-bond branch (eabxag) runs."""
     rng = np.random.default_rng(seed)
     side = int(np.ceil(nmol ** (1 / 3)))
     spacing = 5.2  # Angstrom
     box_A = box_A or side * spacing
     Z, xyz, q, molnum = [], [], [], []
-    bond, vbond, angl, vangl, tors, vtors, nci = [], [], [], [], [], [], []
+    bond, vbond, angl, vangl, tors, vtors, nci, hbl, vhb = [], [], [], [], [], [], [], [], []
     ldvt = 14
     off = 0
     for m in range(nmol):
-        tpl = FORMALDEHYDE if rng.random() < frac_formaldehyde else ETHANOL
+        u = rng.random()
+        tpl = CHLOROMETHANE if u < frac_halogen else (FORMALDEHYDE if u < frac_halogen + frac_formaldehyde else ETHANOL)
         n = len(tpl["Z"])
         A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
         cell = np.array([m % side, (m // side) % side, m // (side * side)]) * spacing + spacing / 2
@@ -104,12 +114,18 @@ def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_forma
             tors.append((i + off, j + off, k + off, l + off, 1, 2))
             vtors.append(row)
         nci += [(a + off, b + off, c) for a, b, c in ncil]
+        if hb and tpl is ETHANOL:          # intramolecular list entry (A, B, H): O, C1, H(O)
+            hbl.append((3 + off, 1 + off, 9 + off))
+            vhb.append((rng.uniform(0.1, 0.6), rng.uniform(0.1, 0.6)))
+        if hb and tpl is CHLOROMETHANE:    # list entry whose third atom is a halogen -> eabxag
+            hbl.append((1 + off, 3 + off, 2 + off))
+            vhb.append((rng.uniform(0.1, 0.6), 0.0))
         off += n
     n = off
     xyz = np.concatenate(xyz)
     T = lambda: np.zeros((94, 94))   # noqa: E731
     r0ab, zab, r094, sr42 = T(), T(), T(), T()
-    els = [1, 6, 8]
+    els = [1, 6, 8, 17]
     for a in els:
         for b in els:
             if a <= b:
@@ -117,7 +133,7 @@ def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_forma
                 for tab, val in zip((r0ab, zab, r094, sr42), v):
                     tab[a - 1, b - 1] = tab[b - 1, a - 1] = val
     rad = np.zeros(94)
-    rad[0], rad[5], rad[7] = 0.32, 0.75, 0.63
+    rad[0], rad[5], rad[7], rad[16] = 0.32, 0.75, 0.63, 0.99
     c6 = rng.uniform(5.0, 40.0, (n, n))
     c6 = 0.5 * (c6 + c6.T)
     eps1 = np.array([0, 0, 0.85, 1, 1, 1.0])      # setnonb.f90:164-169
@@ -140,4 +156,14 @@ def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_forma
         r094=np.asfortranarray(r094), sr42=np.asfortranarray(sr42), rad=rad, eps1=eps1, eps2=eps2,
         periodic=int(periodic), zahn=int(zahn and periodic), box=np.array([L, L, L]), coul_cut=coul_cut,
         vdw_cut=min(10.0 / BOHR, L / 2 - 0.1) if periodic else 10.0 / BOHR, cut_low=0.8 * coul_cut, zahn_a=zahn_a,
-        zahn_par=zahn_par, e_zero=-1.2345)
+        zahn_par=zahn_par, e_zero=-1.2345, **_hb_tables(hb, hbl, vhb, q))
+
+
+def _hb_tables(hb, hbl, vhb, q):
+    if not hb:
+        return dict(nhb=0)
+    scalehb, scalexb = np.zeros(94), np.zeros(94)
+    scalehb[6], scalehb[7], scalehb[8], scalehb[16] = 0.8, 0.3, 0.1, 2.0       # hbpara-scaled N, O, F, Cl
+    scalexb[16], scalexb[34], scalexb[52] = 0.3, 0.6, 0.8
+    return dict(nhb=len(hbl), hb=np.array(hbl, dtype=np.int32).reshape(-1, 3), vhb=np.array(vhb).reshape(-1, 2),
+                scalehb=scalehb, scalexb=scalexb, q_glob=np.array(q))

@@ -54,6 +54,34 @@ def test_egrad_matches_oracle(gpu, oracle, periodic, zahn, nmol, nimg):
     assert (err < tol).all(), (err / tol).max()
 
 
+@pytest.mark.parametrize("periodic,nmol,nimg,halogen", [(True, 12, 32, 0.0), (True, 12, 32, 0.3), (False, 12, 32, 0.3),
+                                                         (True, 125, 2, 0.1)])
+def test_hbond_terms_match_oracle(gpu, oracle, periodic, nmol, nimg, halogen):
+    """row a18: ff_hb list + donor/acceptor search, analytic H-bond (eabhag) and numeric X-bond
+    (eabxag, including the broadcast of the last numeric derivative)"""
+    T = make_system(nmol=nmol, seed=31 + nmol, periodic=periodic, zahn=periodic, hb=True, frac_halogen=halogen)
+    g, _ = handle(gpu, T)
+    Q = oracle.Qmdff(T)
+    T0 = {k: v for k, v in T.items() if k not in ("hb", "vhb", "scalehb", "scalexb", "q_glob")}
+    T0["nhb"] = 0
+    Q0 = oracle.Qmdff(T0)
+    rng = np.random.default_rng(1)
+    x = T["xyz"][None] + rng.normal(0, 0.06, (nimg,) + T["xyz"].shape)
+    Vo, go = Q.egrad(x)
+    V0, g0 = Q0.egrad(x)
+    assert np.abs(Vo - V0).max() > 1e-5                       # the H/X-bond terms are really active
+    Vd, gd, _ = g.egrad(x)
+    assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
+    tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T, x) ** 2)
+    err = C.rel_err_G(gd.reshape(go.shape), go)
+    assert (err < tol).all(), (err / tol).max()
+    # the hb part alone, free of the torsion conditioning: (full - without) on both sides
+    g2, _ = handle(gpu, T0)
+    Vd0, gd0, _ = g2.egrad(x)
+    dh_o, dh_d = go - g0, gd.reshape(go.shape) - gd0.reshape(go.shape)
+    assert np.abs(dh_d - dh_o).max() < 1e-10 * max(1e-3, np.abs(dh_o).max()) + 1e-13
+
+
 def test_rpmd_with_qmdff_on_split_path(gpu, oracle):
     T = make_system(nmol=4, seed=9, periodic=True, zahn=True)
     nb, nsteps = 4, 40
