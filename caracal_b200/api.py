@@ -18,7 +18,8 @@ from . import lib as _l
 # ---- unit helpers: the literal semantics of the reference's drivers ----------
 _F32 = np.float32
 EMASS = 5.485799095e-4  # general.f90:252
-AMU = {"H": 1.00782503207, "D": 2.0141017778, "C": 12.00000, "N": 14.0030740048, "O": 15.99491461956}
+AMU = {"H": 1.00782503207, "D": 2.0141017778, "C": 12.00000, "N": 14.0030740048, "O": 15.99491461956,
+       "F": 18.99840, "S": 32.06000, "CL": 34.96885268}   # atommass.f90:58-110
 
 
 def atomic_mass_au(symbol):

@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 def handle(gpu, T, nbeads=1, dt_fs=0.5):
-    mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O"}[int(z)]) for z in T["at"]])
+    mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O", 17: "CL"}[int(z)]) for z in T["at"]])
     g = gpu.RPMD(gpu.PES_QMDFF, nbeads, mass, C.beta_calc_rate(300.0), C.dt_au(dt_fs))
     g.set_qmdff(T)
     return g, mass
