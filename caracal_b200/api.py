@@ -133,8 +133,9 @@ class RPMD:
         self._ck(self._lib.crcl_set_host_gradient_cb(self._h, ctypes.cast(self._cb, ctypes.c_void_p), None),
                  "crcl_set_host_gradient_cb")
 
-    def set_qmdff(self, T):
-        """T: dict of QMDFF tables named as in the reference's module qmdff (see crcl_qmdff_tables)."""
+    def set_qmdff(self, T, second=False):
+        """T: dict of QMDFF tables named as in the reference's module qmdff (see crcl_qmdff_tables);
+        second=True loads the *_two table set of the second diabatic state."""
         keep = {}
 
         def arr(key, dtype):
@@ -162,7 +163,21 @@ class RPMD:
             S.hb, S.vhb = _ip(arr("hb", np.int32)), _dp(arr("vhb", np.float64))
             S.scalehb, S.scalexb, S.q_glob = _dp(arr("scalehb", np.float64)), _dp(arr("scalexb", np.float64)), \
                 _dp(arr("q_glob", np.float64))
-        self._ck(self._lib.crcl_set_qmdff(self._h, ctypes.byref(S)), "crcl_set_qmdff")
+        if second:
+            self._ck(self._lib.crcl_set_qmdff2(self._h, ctypes.byref(S)), "crcl_set_qmdff2")
+        else:
+            self._ck(self._lib.crcl_set_qmdff(self._h, ctypes.byref(S)), "crcl_set_qmdff")
+
+    def set_dgevb(self, E):
+        """E: dict(mode, coord_def[nat6,5], point_int[npoints,nat6], alph[npoints], b_vec[mat_size], g_thres)"""
+        cd = np.ascontiguousarray(E["coord_def"], dtype=np.int32)
+        pi = _f64(E["point_int"])
+        al, bv = _f64(E["alph"]), _f64(E["b_vec"])
+        P = _l.DgevbParams()
+        P.mode, P.npoints, P.nat6 = int(E["mode"]), len(al), len(cd)
+        P.coord_def, P.point_int, P.alph, P.b_vec = _ip(cd), _dp(pi), _dp(al), _dp(bv)
+        P.g_thres = float(E.get("g_thres", 1e-10))
+        self._ck(self._lib.crcl_set_dgevb(self._h, ctypes.byref(P)), "crcl_set_dgevb")
 
     def set_mechanism(self, m):
         bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)

@@ -15,6 +15,7 @@
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
 #include "qmdff.cuh"
+#include "dgevb.cuh"
 
 using namespace crcl;
 
@@ -39,6 +40,8 @@ struct crcl_handle_s {
     void* cb_user = nullptr;
     int path = CRCL_PATH_AUTO;
     QmdffDev* qmdff = nullptr;
+    QmdffDev* qmdff2 = nullptr;
+    DgevbDev* dgevb = nullptr;
     // split path: per-atom tables on the device, generic-size mechanism
     double *d_mass = nullptr, *d_wfrag = nullptr;
     int *d_atmove = nullptr, *d_frag = nullptr;
@@ -50,8 +53,8 @@ struct crcl_handle_s {
     long long launches = 0;
     std::string err;
     // grow-only device scratch
-    void* scratch[12] = {nullptr};
-    size_t scratch_sz[12] = {0};
+    void* scratch[16] = {nullptr};
+    size_t scratch_sz[16] = {0};
 };
 
 #define CK(call)                                                                     \
@@ -550,7 +553,8 @@ int crcl_create(crcl_handle* out, int device, int natoms, int nbeads, const doub
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CRCL_ENODEV;
     if (device < 0 || device >= ndev) return CRCL_EINVAL;
-    if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE && pes_id != CRCL_PES_QMDFF) {
+    if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE && pes_id != CRCL_PES_QMDFF &&
+        pes_id != CRCL_PES_DGEVB) {
         const int n = pes_natoms(pes_id);
         if (n < 0 || n != natoms) return CRCL_EINVAL;
     }
@@ -590,6 +594,8 @@ int crcl_destroy(crcl_handle h)
         if (s) cudaFree(s);
     if (h->d_fker) cudaFree(h->d_fker);
     qmdff_free(h->qmdff);
+    qmdff_free(h->qmdff2);
+    dgevb_free(h->dgevb);
     if (h->d_mass) cudaFree(h->d_mass);
     if (h->d_atmove) cudaFree(h->d_atmove);
     if (h->d_frag) cudaFree(h->d_frag);
@@ -714,6 +720,31 @@ int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables* T)
     return CRCL_OK;
 }
 
+int crcl_set_qmdff2(crcl_handle h, const crcl_qmdff_tables* T)
+{
+    if (!h || !T) return CRCL_EINVAL;
+    if (T->n != h->natoms) return fail(h, CRCL_EINVAL, "crcl_set_qmdff2: T->n differs from the handle's natoms");
+    CK(cudaSetDevice(h->device));
+    qmdff_free(h->qmdff2);
+    h->qmdff2 = nullptr;
+    const char* msg = "";
+    const int rc = qmdff_upload(T, &h->qmdff2, &msg, true);
+    if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
+int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params* P)
+{
+    if (!h || !P || !P->coord_def || !P->point_int || !P->alph || !P->b_vec) return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    dgevb_free(h->dgevb);
+    h->dgevb = nullptr;
+    const char* msg = "";
+    const int rc = dgevb_upload(P, h->natoms, &h->dgevb, &msg);
+    if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
 int crcl_set_path(crcl_handle h, int path)
 {
     if (!h || path < CRCL_PATH_AUTO || path > CRCL_PATH_SPLIT) return CRCL_EINVAL;
@@ -743,6 +774,34 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
                    double* d_dVdq, int* d_info)
 {
     if (!h || !d_q || !d_V || !d_dVdq || nimg < 0) return CRCL_EINVAL;
+    if (pes_id == CRCL_PES_DGEVB) {
+        if (!h->qmdff || !h->qmdff2 || !h->dgevb)
+            return fail(h, CRCL_ESTATE, "DG-EVB needs crcl_set_qmdff, crcl_set_qmdff2 and crcl_set_dgevb");
+        if (h->qmdff->n != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the QMDFF tables");
+        if (nimg == 0) return CRCL_OK;
+        CK(cudaSetDevice(h->device));
+        if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
+        const size_t n = (size_t)nimg * 3 * natoms;
+        double *g1, *g2, *v12;
+        int rc;
+        if ((rc = scratch(h, 12, n, &g1)) || (rc = scratch(h, 13, n, &g2)) || (rc = scratch(h, 14, (size_t)2 * nimg, &v12)))
+            return rc;
+        if (h->timed) {
+            next_event_pair(h);
+            cudaEventRecord(h->ev0, h->stream);
+        }
+        cudaError_t e = qmdff_egrad(h->qmdff, d_q, nimg, v12, g1, h->stream, &h->launches);
+        if (e == cudaSuccess) e = qmdff_egrad(h->qmdff2, d_q, nimg, v12 + nimg, g2, h->stream, &h->launches);
+        if (e == cudaSuccess)
+            e = dgevb_mix(h->dgevb, natoms, d_q, nimg, v12, g1, v12 + nimg, g2, d_V, d_dVdq, h->stream);
+        h->launches++;
+        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (e != cudaSuccess) {
+            h->err = std::string("dg-evb kernels: ") + cudaGetErrorString(e);
+            return CRCL_ECUDA;
+        }
+        return CRCL_OK;
+    }
     if (pes_id == CRCL_PES_QMDFF) {
         if (!h->qmdff) return fail(h, CRCL_ESTATE, "crcl_set_qmdff has not been called");
         if (h->qmdff->n != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the QMDFF tables");

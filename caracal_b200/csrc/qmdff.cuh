@@ -27,6 +27,7 @@ struct QmdffDev {
     double* c6;  // [n][n] symmetric: c6xy(max,min) of the reference
     // H/X-bond terms (ff_hb.f90)
     int nhb, ndonor, use_hb;
+    int is_two;       // evaluate with the *_two semantics (second diabatic state)
     int* hb;          // [nhb][3] A,B,H 0-based
     double* vhb;      // [nhb][2]
     int* isH;         // [nhb]: third atom is hydrogen -> eabhag, else eabxag
@@ -48,7 +49,7 @@ struct QmdffDev {
 };
 
 // host: build / free the device copy; evaluate nimg images (AoS [img][atom][xyz])
-int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err);
+int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, bool is_two = false);
 void qmdff_free(QmdffDev* D);
 cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g,
                         cudaStream_t s, long long* launches);

@@ -668,7 +668,8 @@ cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double
             qm_bonded_kernel<<<dim3((nterm + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
             nl++;
         }
-        if (!(D->nnci <= 1 && D->nmols == 0)) {   // ff_nonb.f90:74 early return
+        // early returns: ff_nonb.f90:74 (nnci <= 1 and nmols == 0), ff_nonb_two.f90:48 (nnci_two <= 1)
+        if (!(D->nnci <= 1 && (D->is_two || D->nmols == 0))) {
             if (D->nnci > 0) {
                 qm_nci_kernel<<<dim3((D->nnci + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
                 nl++;
@@ -714,7 +715,7 @@ static T* up(const T* h, size_t n, bool& ok)
     return d;
 }
 
-int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err)
+int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, bool is_two)
 {
     *out = nullptr;
     if (T->nhb > 0 && (!T->scalehb || !T->hb || !T->vhb)) {
@@ -778,6 +779,15 @@ int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err)
     D->zahn_a = T->zahn_a;
     D->zahn_par = T->zahn_par;
     D->e_zero = T->e_zero;
+    if (is_two) {
+        // ff_eg_two / ff_nonb_two / ff_hb_two: no PBC, no inter-molecular loops, Coulomb without cut-off
+        D->is_two = 1;
+        D->periodic = 0;
+        D->zahn = 0;
+        D->nmols = 1;
+        D->coul_cut = 1.0e300;
+        for (int a = 0; a < n; a++) mol[a] = 1;
+    }
     // lists -> 0-based
     auto idx_ok = [&](int v) { return v >= 1 && v <= n; };
     std::vector<int> bond(2 * (size_t)T->nbond), angl(3 * (size_t)T->nangl), tors(6 * (size_t)T->ntors),

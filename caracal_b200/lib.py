@@ -14,7 +14,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_u32_p = ctypes.POINTER(ctypes.c_uint32)
 
-PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_QMDFF, PES_HOSTCB = 0, 1, 2, 3, 10, 100
+PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_QMDFF, PES_DGEVB, PES_HOSTCB = 0, 1, 2, 3, 10, 11, 100
 PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H}
 PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6}
 TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
@@ -39,6 +39,12 @@ class QmdffTables(ctypes.Structure):
                 ("q_glob", c_double_p)]
 
 
+class DgevbParams(ctypes.Structure):
+    """crcl_dgevb_params of include/caracal_gpu.h"""
+    _fields_ = [("mode", ctypes.c_int), ("npoints", ctypes.c_int), ("nat6", ctypes.c_int), ("coord_def", c_int_p),
+                ("point_int", c_double_p), ("alph", c_double_p), ("b_vec", c_double_p), ("g_thres", ctypes.c_double)]
+
+
 # every symbol include/caracal_gpu.h declares: (restype, argtypes)
 _H = ctypes.c_void_p
 SIGNATURES = {
@@ -52,6 +58,8 @@ SIGNATURES = {
     "crcl_set_transform": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_host_gradient_cb": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "crcl_set_qmdff": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),
+    "crcl_set_qmdff2": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),
+    "crcl_set_dgevb": (ctypes.c_int, [_H, ctypes.POINTER(DgevbParams)]),
     "crcl_set_path": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                           ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),

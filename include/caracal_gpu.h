@@ -36,6 +36,8 @@ extern "C" {
 #define CRCL_PES_OH3 2   /* "oh3"  egrad_oh3.f  Schatz-Elgersma OH + H2, atoms O,H,H,H */
 #define CRCL_PES_CH4H 3  /* "ch4h" egrad_ch4h.f CBE CH4 + H, atoms H,C,H,H,H,H         */
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
+#define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
+                             crcl_set_qmdff2, crcl_set_dgevb */
 #define CRCL_PES_HOSTCB 100 /* custom_grad / external_grad stay on the host (callback)  */
 
 /* error codes */
@@ -132,8 +134,25 @@ typedef struct crcl_qmdff_tables {
     const double *vhb;
     const double *scalehb, *scalexb, *q_glob;
 } crcl_qmdff_tables;
-/* handle must have been created with pes_id = CRCL_PES_QMDFF and natoms = T->n */
+/* handle must have been created with pes_id = CRCL_PES_QMDFF (or CRCL_PES_DGEVB) and natoms = T->n */
 int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables *T);
+/* second diabatic state: the *_two table set (bond_two, vbond_two, ..., q_two, c6xy_two, E_zero2).
+ * Evaluated with the semantics of ff_eg_two.f90 / ff_nonb_two.f90 / ff_hb_two.f90: never periodic,
+ * list terms only, Coulomb q_i q_j eps1 / r without cut-off (periodic, nmols, zahn, cut-offs of T are
+ * ignored). */
+int crcl_set_qmdff2(crcl_handle h, const crcl_qmdff_tables *T);
+
+/* DG-EVB coupling (module evb_mod; read_pes.f90:2046-2225, evb_pars.dat): dg_mode 1..3,
+ * coord_def(nat6,5) flattened row-wise = type (1 dist, 2 angle, 3 dihedral, 4 out-of-plane) and up
+ * to four 1-based atoms; point_int(nat6,npoints) in Fortran order; alph_opt(npoints);
+ * b_vec(mat_size), mat_size = npoints * (1 | 1+nat6 | 1+nat6+nat6(nat6+1)/2); g_thres (1E-10). */
+typedef struct crcl_dgevb_params {
+    int mode, npoints, nat6;
+    const int *coord_def;
+    const double *point_int, *alph, *b_vec;
+    double g_thres;
+} crcl_dgevb_params;
+int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params *P);
 
 /* NVT{} section: thermostat 0 none, 1 Andersen, 2 Nose-Hoover chain (dynamic.f90:463-465);
  * andersen_step as evb_mod.f90:289; kelvin and nose_q for nhc.f90 / mdinit.f90:138-146 */

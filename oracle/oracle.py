@@ -290,3 +290,53 @@ class Qmdff:
         g = np.zeros_like(x)
         self.L.orc_ff_eg(ctypes.byref(self.S), _d(x), ctypes.byref(e), _d(g))
         return e.value, g
+
+
+class _DgevbStruct(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int), ("npoints", ctypes.c_int), ("nat6", ctypes.c_int), ("natoms", ctypes.c_int),
+                ("coord_def", ip), ("point_int", dp), ("alph", dp), ("b_vec", dp), ("g_thres", ctypes.c_double)]
+
+
+class Dgevb:
+    """Oracle of the DG-EVB branch of gradient.f90:365-537 on two QMDFF table sets."""
+
+    def __init__(self, T1, T2, E):
+        self.Q1, self.Q2 = Qmdff(T1), Qmdff(T2)
+        self.L = self.Q1.L
+        self.keep = dict(cd=np.ascontiguousarray(E["coord_def"], dtype=np.int32),
+                         pi=np.ascontiguousarray(E["point_int"], dtype=np.float64),
+                         al=np.ascontiguousarray(E["alph"], dtype=np.float64),
+                         bv=np.ascontiguousarray(E["b_vec"], dtype=np.float64))
+        S = _DgevbStruct()
+        S.mode, S.npoints, S.nat6, S.natoms = int(E["mode"]), len(E["alph"]), len(E["coord_def"]), self.Q1.n
+        S.coord_def, S.point_int, S.alph, S.b_vec = _i(self.keep["cd"]), _d(self.keep["pi"]), _d(self.keep["al"]), \
+            _d(self.keep["bv"])
+        S.g_thres = float(E.get("g_thres", 1e-10))
+        self.S = S
+        self.L.orc_dgevb_egrad.argtypes = [ctypes.POINTER(_QmdffStruct), ctypes.POINTER(_QmdffStruct),
+                                           ctypes.POINTER(_DgevbStruct), dp, ctypes.c_int, dp, dp]
+        self.L.orc_xyz_2int.argtypes = [ctypes.POINTER(_DgevbStruct), dp, dp]
+        self.L.orc_qmdff_two_one.argtypes = [ctypes.POINTER(_QmdffStruct), dp, ctypes.POINTER(ctypes.c_double), dp]
+
+    def second_state(self, xyz):
+        """E2 + E_zero2 and g2 of one structure (ff_eg_two + ff_nonb_two + ff_hb_two)"""
+        x = np.ascontiguousarray(xyz, dtype=np.float64)
+        e = ctypes.c_double(0.0)
+        g = np.zeros_like(x)
+        self.L.orc_qmdff_two_one(ctypes.byref(self.Q2.S), _d(x), ctypes.byref(e), _d(g))
+        return e.value + self.Q2.S.e_zero, g
+
+    def egrad(self, xyz):
+        n = self.Q1.n
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, n, 3)
+        V = np.zeros(x.shape[0])
+        g = np.zeros_like(x)
+        self.L.orc_dgevb_egrad(ctypes.byref(self.Q1.S), ctypes.byref(self.Q2.S), ctypes.byref(self.S), _d(x),
+                               x.shape[0], _d(V), _d(g))
+        return V, g
+
+    def internals(self, xyz):
+        x = np.ascontiguousarray(xyz, dtype=np.float64)
+        out = np.zeros(self.S.nat6)
+        self.L.orc_xyz_2int(ctypes.byref(self.S), _d(x), _d(out))
+        return out

@@ -167,3 +167,32 @@ def _hb_tables(hb, hbl, vhb, q):
     scalexb[16], scalexb[34], scalexb[52] = 0.3, 0.6, 0.8
     return dict(nhb=len(hbl), hb=np.array(hbl, dtype=np.int32).reshape(-1, 3), vhb=np.array(vhb).reshape(-1, 2),
                 scalehb=scalehb, scalexb=scalexb, q_glob=np.array(q))
+
+
+def make_dgevb(seed=0, mode=3, npoints=5):
+    """A gas-phase two-state system: one ethanol-like molecule described by two QMDFFs with different
+    parameters, a redundant-free internal coordinate set (bonds, angles, a dihedral, an out-of-plane)
+    and random distributed-Gaussian parameters of the given mode (evb_pars.dat layout,
+    read_pes.f90:2203-2225)."""
+    from oracle import oracle as O
+    T1 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True)
+    T2 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True)
+    rng = np.random.default_rng(seed + 100)
+    T2 = dict(T2)
+    T2["vbond"] = T1["vbond"] * rng.uniform(0.9, 1.1, T1["vbond"].shape)
+    T2["vangl"] = T1["vangl"] * rng.uniform(0.9, 1.1, T1["vangl"].shape)
+    T2["q"] = T1["q"] * 1.1
+    T2["q_glob"] = T2["q"]
+    T2["c6xy"] = np.asfortranarray(T1["c6xy"] * 0.9)
+    T2["e_zero"] = T1["e_zero"] + 0.01
+    T2["xyz"] = T1["xyz"]
+    coord_def = np.array([[1, 1, 2, 0, 0], [1, 2, 3, 0, 0], [1, 1, 4, 0, 0], [1, 3, 9, 0, 0], [1, 2, 7, 0, 0],
+                          [2, 1, 2, 3, 0], [2, 2, 3, 9, 0], [2, 4, 1, 2, 0], [3, 4, 1, 2, 3], [3, 1, 2, 3, 9],
+                          [4, 3, 7, 8, 2]], dtype=np.int32)
+    nat6 = len(coord_def)
+    E = dict(mode=mode, coord_def=coord_def, g_thres=1e-10)
+    tmp = O.Dgevb(T1, T2, dict(E, point_int=np.zeros((1, nat6)), alph=np.ones(1), b_vec=np.zeros(4000)))
+    pts = np.array([tmp.internals(T1["xyz"] + rng.normal(0, 0.08, T1["xyz"].shape)) for _ in range(npoints)])
+    mat = {1: npoints, 2: npoints * (1 + nat6), 3: npoints * (1 + nat6 + nat6 * (nat6 + 1) // 2)}[mode]
+    E.update(point_int=pts, alph=rng.uniform(0.5, 2.5, npoints), b_vec=rng.normal(0, 2e-4, mat))
+    return T1, T2, E
