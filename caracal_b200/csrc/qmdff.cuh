@@ -46,12 +46,16 @@ struct QmdffDev {
     double eps1[6], eps2[6];
     int periodic, zahn;
     double box[3], coul_cut, vdw_cut, cut_low, zahn_a, zahn_par, e_zero;
+    // grow-only scratch of qmdff_egrad: SoA copies of the positions, xs[img][c][n] (FP64), xf (FP32)
+    double* xs;
+    float4* xf;
+    size_t xs_cap;
 };
 
 // host: build / free the device copy; evaluate nimg images (AoS [img][atom][xyz])
 int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, bool is_two = false);
 void qmdff_free(QmdffDev* D);
-cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g,
+cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g,
                         cudaStream_t s, long long* launches);
 
 }  // namespace crcl

@@ -412,67 +412,192 @@ __global__ void __launch_bounds__(128) qm_nci_kernel(const QmdffDev D, const dou
     block_sum_to(e, &V[img]);
 }
 
-// inter-molecular all-pairs sweep; thread = atom i of image blockIdx.y, tiles of 128 atoms j
-__global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const double* __restrict__ xyz,
-                                                       double* __restrict__ V, double* __restrict__ g)
+// Per image: xs[img][c][n], an FP64 SoA copy of the positions (exact pair evaluation, coalesced
+// gathers), and xf[img][n] = {x, y, z, molnum} packed as float4 (one 16-byte load per atom in the
+// conservative FP32 pre-filters of qm_inter_kernel and qm_hb_search_kernel).
+__global__ void qm_soa_kernel(const double* __restrict__ xyz, const int* __restrict__ molnum, int n, size_t natot,
+                              double* __restrict__ xs, float4* __restrict__ xf)
 {
-    __shared__ double sx[128], sy[128], sz[128], sq[128];
-    __shared__ int st[128], sm[128];
-    const int img = blockIdx.y, n = D.n;
-    const double* x = xyz + (size_t)img * 3 * n;
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    const bool act = i < n;
-    double xi = 0, yi = 0, zi = 0, qi = 0, gx = 0, gy = 0, gz = 0, e = 0.0;
-    int ti = 0, mi = -1;
-    if (act) {
-        xi = x[3 * i];
-        yi = x[3 * i + 1];
-        zi = x[3 * i + 2];
-        qi = D.q[i];
-        ti = D.type[i];
-        mi = D.molnum[i];
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // (image, atom)
+    if (t >= natot) return;
+    const size_t img = t / (size_t)n;
+    const int a = (int)(t - img * n);
+    const double* p = xyz + 3 * t;
+    const double x = p[0], y = p[1], z = p[2];
+    double* o = xs + img * 3 * n + a;
+    o[0] = x;
+    o[n] = y;
+    o[2 * (size_t)n] = z;
+    xf[t] = make_float4((float)x, (float)y, (float)z, __int_as_float(molnum[a]));
+}
+
+// FP32 minimum image for the pre-filters (any distance; the exact box_image.f90 loop runs on the survivors)
+__device__ __forceinline__ float image_f(float v, float L, float iL) { return fmaf(-L, rintf(v * iL), v); }
+// relative slack of the FP32 pre-filters: covers the rounding of coordinates up to ~1e4 bohr
+#define QM_PREFILTER_SLACK 1.002f
+#define QM_HB_SEG 512   // atoms j per warp in qm_hb_search_kernel
+
+// Inter-molecular part of ff_nonb (ff_nonb.f90:198-332 dispersion/repulsion, :421-512 Coulomb), every
+// pair i < j of different molecules once.  One WARP per (image, atom i): the lanes sweep j = i+1..n-1
+// in chunks of 32 with a cheap test (other molecule, minimum image, r^2 inside the larger cut-off)
+// and compact the survivors into a per-warp queue in shared memory; whenever 32 pairs are queued
+// they are evaluated with all lanes busy, so that the expensive part (exp, erfc, reciprocals) never
+// runs on a mostly-idle warp -- with 10 A cut-offs in a 31 A box only ~14 % of the tests survive and
+// a lane-per-pair sweep without compaction executes the expensive path on almost every iteration.
+// g_i is reduced over the warp in registers, g_j goes out as red.global.add.f64.
+struct InterTables {
+    double r094[QM_MAXTYPE][QM_MAXTYPE], sr42[QM_MAXTYPE][QM_MAXTYPE], r0ab[QM_MAXTYPE][QM_MAXTYPE],
+        zab[QM_MAXTYPE][QM_MAXTYPE];
+};
+
+__global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const double* __restrict__ xs,
+                                                       const float4* __restrict__ xf, double* __restrict__ V,
+                                                       double* __restrict__ g)
+{
+    __shared__ InterTables tb;
+    __shared__ int queue[4][64];
+    const int img = blockIdx.y, n = D.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < QM_MAXTYPE * QM_MAXTYPE; t += 128) {
+        (&tb.r094[0][0])[t] = (&D.r094[0][0])[t];
+        (&tb.sr42[0][0])[t] = (&D.sr42[0][0])[t];
+        (&tb.r0ab[0][0])[t] = (&D.r0ab[0][0])[t];
+        (&tb.zab[0][0])[t] = (&D.zab[0][0])[t];
     }
-    for (int j0 = 0; j0 < n; j0 += 128) {
-        const int j = j0 + threadIdx.x;
-        __syncthreads();
-        if (j < n) {
-            sx[threadIdx.x] = x[3 * j];
-            sy[threadIdx.x] = x[3 * j + 1];
-            sz[threadIdx.x] = x[3 * j + 2];
-            sq[threadIdx.x] = D.q[j];
-            st[threadIdx.x] = D.type[j];
-            sm[threadIdx.x] = D.molnum[j];
-        }
-        __syncthreads();
-        if (!act) continue;
-        const int cnt = min(128, n - j0);
-        for (int jj = 0; jj < cnt; jj++) {
-            if (sm[jj] == mi) continue;
-            // orientation as the reference: vab = x(i1) - x(i2) with i1 < i2
-            const int jg = j0 + jj;
-            const double sgn = (i < jg) ? 1.0 : -1.0;
-            double vab[3] = {sgn * (xi - sx[jj]), sgn * (yi - sy[jj]), sgn * (zi - sz[jj])};
-            if (D.periodic) box_image(D, vab);
-            const double r2 = dot3(vab, vab), r = sqrt(r2);
-            double dr = 0.0, d1, d2, ep = 0.0;
-            if (!(D.periodic && r > D.vdw_cut)) {
-                const int lo = min(i, jg), hi = max(i, jg);
-                ep += vdw_pair(D, ti, st[jj], __ldg(&D.c6[(size_t)lo * n + hi]), r2, r, 1.0, d1);
-                dr += d1;
+    __syncthreads();
+    const double* X = xs + (size_t)img * 3 * n;
+    const double *Xx = X, *Xy = X + n, *Xz = X + 2 * (size_t)n;
+    const int i = blockIdx.x * 4 + warp;
+    double e = 0.0;
+    if (i < n - 1) {
+        const double xi = Xx[i], yi = Xy[i], zi = Xz[i], qi = D.q[i];
+        const int ti = D.type[i], mi = D.molnum[i];
+        const double* c6row = D.c6 + (size_t)i * n;
+        const bool per = D.periodic != 0;
+        const double Lx = D.box[0], Ly = D.box[1], Lz = D.box[2];
+        const double rc = fmax(D.vdw_cut, D.coul_cut);
+        double gx = 0.0, gy = 0.0, gz = 0.0;
+        int* qu = queue[warp];
+        int qn = 0;
+        auto image = [&](double& v, double L) {
+            const double L2 = 0.5 * L;
+            while (fabs(v) > L2) v -= (v >= 0.0) ? L : -L;   // box_image.f90
+        };
+        auto pair = [&](int j) {
+            double vab[3] = {xi - Xx[j], yi - Xy[j], zi - Xz[j]};   // x(i1) - x(i2), i1 < i2
+            if (per) {
+                image(vab[0], Lx);
+                image(vab[1], Ly);
+                image(vab[2], Lz);
             }
-            ep += coul_pair(D, qi * sq[jj], r2, r, 1.0, d2);
-            dr += d2;
-            e += 0.5 * ep;
-            gx += sgn * vab[0] * dr;
-            gy += sgn * vab[1] * dr;
-            gz += sgn * vab[2] * dr;
+            const double r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2], r = sqrt(r2);
+            const double oner = 1.0 / r, oner2 = oner * oner;
+            double dr = 0.0, ep = 0.0;
+            if (!(per && r > D.vdw_cut)) {
+                const int tj = D.type[j];
+                const double c6 = __ldg(&c6row[j]);
+                const double R0 = tb.r094[ti][tj];
+                const double r4 = r2 * r2, r6 = r4 * r2, R02 = R0 * R0, r06 = R02 * R02 * R02;
+                const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
+                const double it6 = 1.0 / t6, it8 = 1.0 / t8;
+                const double c6t6 = c6 * it6, t27 = tb.sr42[ti][tj] * (c6 * it8);
+                ep -= c6t6 + t27;
+                dr += c6t6 * 6.0 * r4 * it6 + 8.0 * t27 * r6 * it8;
+                if (r < 25.0) {
+                    const double alpha = tb.r0ab[ti][tj];
+                    const double tt = tb.zab[ti][tj] * exp(-alpha * r);
+                    ep += tt * oner;
+                    dr -= tt * (alpha * r + 1.0) * oner * oner2;
+                }
+            }
+            if (!(r > D.coul_cut)) {
+                const double qq = qi * D.q[j];
+                double e0;
+                if (D.zahn) {
+                    e0 = qq * (erfc(D.zahn_a * r) * oner - D.zahn_par * (r - D.coul_cut));
+                } else {
+                    double sw = 1.0;
+                    if (per && r > D.cut_low) {
+                        const double xv = (r - D.cut_low) / (D.coul_cut - D.cut_low);
+                        sw = exp(1.0) * exp(1.0 / (xv - 1.0));
+                    }
+                    e0 = qq * oner * sw;
+                }
+                ep += e0;
+                dr -= e0 * oner2;   // the reference uses e0/r^2 for every Coulomb form (ff_nonb.f90:470)
+            }
+            e += ep;
+            const double fx = vab[0] * dr, fy = vab[1] * dr, fz = vab[2] * dr;
+            gx += fx;
+            gy += fy;
+            gz += fz;
+            double* gj = g + (size_t)img * 3 * n + 3 * (size_t)j;
+            atomicAdd(gj, -fx);
+            atomicAdd(gj + 1, -fy);
+            atomicAdd(gj + 2, -fz);
+        };
+        // cheap test in FP32 with slack (the exact r > cut tests follow in pair()); the next chunk
+        // is loaded before the current one is tested / flushed
+        const float4* F = xf + (size_t)img * n;
+        const float4 fi = F[i];
+        const float Lxf = (float)Lx, Lyf = (float)Ly, Lzf = (float)Lz;
+        const float iLx = 1.0f / Lxf, iLy = 1.0f / Lyf, iLz = 1.0f / Lzf;
+        const float rc2f = (float)(rc * rc) * QM_PREFILTER_SLACK;
+        const float mif = __int_as_float(mi);
+        auto near = [&](const float4& c) {   // other molecule and inside the larger cut-off (with slack)
+            bool ok = __float_as_int(c.w) != mi;
+            if (per) {
+                const float dx = image_f(fi.x - c.x, Lxf, iLx), dy = image_f(fi.y - c.y, Lyf, iLy),
+                            dz = image_f(fi.z - c.z, Lzf, iLz);
+                ok = ok && (dx * dx + dy * dy + dz * dz <= rc2f);
+            }
+            return ok;
+        };
+        auto push = [&](bool ok, int j) {
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) qu[qn + __popc(m & ((1u << lane) - 1u))] = j;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                pair(qu[qn + lane]);
+                __syncwarp();
+            }
+        };
+        const float4 self = make_float4(0.f, 0.f, 0.f, mif);   // fails the molecule test
+        // first chunk (j > i) and last chunk (j < n) are guarded, the chunks in between are not
+        const int jstart = (i + 1) & ~31, jfull = n & ~31;
+        {
+            const int j = jstart + lane;
+            const float4 c = (j > i && j < n) ? F[j] : self;
+            push(near(c), j);
         }
-    }
-    if (act) {
-        double* gi = g + (size_t)img * 3 * n;
-        atomicAdd(&gi[3 * i], gx);
-        atomicAdd(&gi[3 * i + 1], gy);
-        atomicAdd(&gi[3 * i + 2], gz);
+        int j0 = jstart + 32;
+        if (j0 < jfull) {
+            float4 c = F[j0 + lane];
+            for (; j0 < jfull; j0 += 32) {
+                const int jn = j0 + 32 + lane;
+                const float4 nx = (jn < n) ? F[jn] : self;   // also prefetches the guarded last chunk
+                push(near(c), j0 + lane);
+                c = nx;
+            }
+            if (j0 < n) push(near(c), j0 + lane);            // c holds the (guarded) last partial chunk
+        } else if (j0 < n) {
+            const int j = j0 + lane;
+            const float4 c = (j < n) ? F[j] : self;
+            push(near(c), j);
+        }
+        if (lane < qn) pair(qu[lane]);
+        for (int o = 16; o > 0; o >>= 1) {
+            gx += __shfl_xor_sync(0xffffffffu, gx, o);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o);
+            gz += __shfl_xor_sync(0xffffffffu, gz, o);
+        }
+        if (lane == 0) {
+            double* gi = g + (size_t)img * 3 * n + 3 * (size_t)i;
+            atomicAdd(gi, gx);
+            atomicAdd(gi + 1, gy);
+            atomicAdd(gi + 2, gz);
+        }
     }
     block_sum_to(e, &V[img]);
 }
@@ -610,35 +735,75 @@ __global__ void __launch_bounds__(128) qm_hb_list_kernel(const QmdffDev D, const
     block_sum_to(e, &V[img]);
 }
 
-// ff_hb.f90:90-274: every (donor bond, atom j of another molecule) pair; grid (j tiles, donors, images)
+// ff_hb.f90:90-274: every (donor bond, atom j of another molecule) pair.  One WARP per (image,
+// donor): the lanes sweep all atoms j with a cheap test (other molecule, acceptor class, A..j
+// inside 15 bohr in FP32 with slack) and compact the survivors into a per-warp queue; queued
+// pairs go through the complete reference logic (exact distance tests included) 32 at a time.
 __global__ void __launch_bounds__(128) qm_hb_search_kernel(const QmdffDev D, const double* __restrict__ xyz,
-                                                           double* __restrict__ V, double* __restrict__ g)
+                                                           const float4* __restrict__ xf, double* __restrict__ V,
+                                                           double* __restrict__ g)
 {
     constexpr double c12 = (double)1.2f, c13 = (double)1.3f, b0 = (double)0.52917726f;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x, d = blockIdx.y, img = blockIdx.z;
-    const double* x = xyz + (size_t)img * 3 * D.n;
-    double* gi = g + (size_t)img * 3 * D.n;
+    __shared__ int queue[4][64];
+    const int img = blockIdx.y, n = D.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d = blockIdx.x * 4 + warp;
+    const double* x = xyz + (size_t)img * 3 * n;
+    double* gi = g + (size_t)img * 3 * n;
     double e = 0.0;
-    if (j < D.n) {
+    if (d < D.ndonor) {
         const int H = D.donor[3 * d], A = D.donor[3 * d + 1], kind = D.donor[3 * d + 2];
-        if (D.molnum[H] != D.molnum[j]) {
+        const int mH = D.molnum[H];
+        const double ri = dist_dev(D, x, A, H, true), dthr = D.dthr[d], dcoef = D.dcoef[d], dscal = D.dscal[d];
+        const double radHal = D.rad[D.type[H]];
+        auto pair = [&](int j) {
+            // the reference's tests, in its order (ff_hb.f90:150-274)
+            const double rj = dist_dev(D, x, j, H, true);
             if (kind == 1) {
-                if (D.acc_no[j]) {
-                    const double ri = dist_dev(D, x, A, H, true), rj = dist_dev(D, x, j, H, true);
-                    const double dum2 = c12 * (D.rad[D.type[j]] + D.rad[D.type[H]]) / b0;
-                    if (ri < D.dthr[d] || rj < dum2)
-                        if (!(dist_dev(D, x, A, j, false) > 15.0)) e = eabxag_dev(D, x, gi, A, j, H, D.dcoef[d]);
-                }
+                const double dum2 = c12 * (D.rad[D.type[j]] + radHal) / b0;
+                if (ri < dthr || rj < dum2)
+                    if (!(dist_dev(D, x, A, j, false) > 15.0)) e += eabxag_dev(D, x, gi, A, j, H, dcoef);
             } else {
-                if (D.dscal[d] * D.acc_s[j] > 1e-6) {
-                    const double ri = dist_dev(D, x, A, H, true), rj = dist_dev(D, x, j, H, true);
-                    const double dum2 = c13 * (D.rad[D.type[j]] + D.radH) / b0;
-                    if (ri < D.dthr[d] || rj < dum2)
-                        if (!(dist_dev(D, x, A, j, true) > 15.0))
-                            e = eabhag_dev(D, x, gi, j, A, H, D.acc_c1[j], D.dcoef[d]);
+                const double dum2 = c13 * (D.rad[D.type[j]] + D.radH) / b0;
+                if (ri < dthr || rj < dum2)
+                    if (!(dist_dev(D, x, A, j, true) > 15.0)) e += eabhag_dev(D, x, gi, j, A, H, D.acc_c1[j], dcoef);
+            }
+        };
+        const float4* F = xf + (size_t)img * n;
+        const float4 fa = F[A];
+        // kind 1 tests the A..j distance WITHOUT the minimum image (ff_hb.f90:176-180)
+        const bool img_aj = D.periodic && kind == 2;
+        const float Lxf = (float)D.box[0], Lyf = (float)D.box[1], Lzf = (float)D.box[2];
+        const float iLx = 1.0f / Lxf, iLy = 1.0f / Lyf, iLz = 1.0f / Lzf;
+        const float r2max = 225.0f * QM_PREFILTER_SLACK;
+        int* qu = queue[warp];
+        int qn = 0;
+        // blockIdx.z: segment of QM_HB_SEG atoms j (more warps in flight when there are few donors)
+        const int jbeg = blockIdx.z * QM_HB_SEG, jend = min(n, jbeg + QM_HB_SEG);
+        for (int j0 = jbeg; j0 < jend; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = j < jend;
+            if (ok) {
+                const float4 c = F[j];
+                float dx = fa.x - c.x, dy = fa.y - c.y, dz = fa.z - c.z;
+                if (img_aj) {
+                    dx = image_f(dx, Lxf, iLx);
+                    dy = image_f(dy, Lyf, iLy);
+                    dz = image_f(dz, Lzf, iLz);
                 }
+                ok = __float_as_int(c.w) != mH && dx * dx + dy * dy + dz * dz <= r2max;
+            }
+            if (ok) ok = (kind == 1) ? D.acc_no[j] != 0 : dscal * D.acc_s[j] > 1e-6;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) qu[qn + __popc(m & ((1u << lane) - 1u))] = j;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                pair(qu[qn + lane]);
+                __syncwarp();
             }
         }
+        if (lane < qn) pair(qu[lane]);
     }
     block_sum_to(e, &V[img]);
 }
@@ -649,12 +814,30 @@ __global__ void qm_init_kernel(double* V, int nimg, double e_zero)
     if (i < nimg) V[i] = e_zero;
 }
 
-cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g, cudaStream_t s,
+cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V, double* d_g, cudaStream_t s,
                         long long* launches)
 {
     if (nimg <= 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(d_g, 0, (size_t)nimg * 3 * D->n * sizeof(double), s);
     if (e != cudaSuccess) return e;
+    const bool inter = !(D->nnci <= 1 && (D->is_two || D->nmols == 0)) && D->nmols > 1;
+    const bool hbs = D->use_hb && D->nmols > 1 && D->ndonor > 0;
+    if (inter || hbs) {
+        const size_t natot = (size_t)nimg * D->n, total = 3 * natot;
+        if (total > D->xs_cap) {
+            // stream-ordered with the kernels that still read the old buffer
+            if (D->xs && (e = cudaFreeAsync(D->xs, s)) != cudaSuccess) return e;
+            if (D->xf && (e = cudaFreeAsync(D->xf, s)) != cudaSuccess) return e;
+            D->xs = nullptr;
+            D->xf = nullptr;
+            D->xs_cap = 0;
+            if ((e = cudaMallocAsync(&D->xs, total * sizeof(double), s)) != cudaSuccess) return e;
+            if ((e = cudaMallocAsync(&D->xf, natot * sizeof(float4), s)) != cudaSuccess) return e;
+            D->xs_cap = total;
+        }
+        qm_soa_kernel<<<(unsigned)((natot + 255) / 256), 256, 0, s>>>(d_xyz, D->molnum, D->n, natot, D->xs, D->xf);
+        if (launches) ++*launches;
+    }
     qm_init_kernel<<<(nimg + 127) / 128, 128, 0, s>>>(d_V, nimg, D->e_zero);
     int nl = 1;
     // blockIdx.y carries the image: at most 65535 images per launch
@@ -675,7 +858,8 @@ cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double
                 nl++;
             }
             if (D->nmols > 1) {
-                qm_inter_kernel<<<dim3((D->n + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                qm_inter_kernel<<<dim3((D->n + 3) / 4, ni), 128, 0, s>>>(*D, D->xs + (size_t)i0 * 3 * D->n,
+                                                                         D->xf + (size_t)i0 * D->n, V, g);
                 nl++;
             }
         }
@@ -685,16 +869,9 @@ cudaError_t qmdff_egrad(const QmdffDev* D, const double* d_xyz, int nimg, double
                 nl++;
             }
             if (D->nmols > 1 && D->ndonor > 0) {
-                for (int d0 = 0; d0 < D->ndonor; d0 += 65535) {
-                    QmdffDev Dd = *D;
-                    const int nd = std::min(65535, D->ndonor - d0);
-                    Dd.donor = D->donor + 3 * d0;
-                    Dd.dthr = D->dthr + d0;
-                    Dd.dcoef = D->dcoef + d0;
-                    Dd.dscal = D->dscal + d0;
-                    qm_hb_search_kernel<<<dim3((D->n + 127) / 128, nd, ni), 128, 0, s>>>(Dd, x, V, g);
-                    nl++;
-                }
+                qm_hb_search_kernel<<<dim3((D->ndonor + 3) / 4, ni, (D->n + QM_HB_SEG - 1) / QM_HB_SEG), 128, 0, s>>>(
+                    *D, x, D->xf + (size_t)i0 * D->n, V, g);
+                nl++;
             }
         }
     }
@@ -944,6 +1121,8 @@ void qmdff_free(QmdffDev* D)
     cudaFree(D->acc_c1);
     cudaFree(D->acc_s);
     cudaFree(D->acc_no);
+    cudaFree(D->xs);
+    cudaFree(D->xf);
     delete D;
 }
 

@@ -137,7 +137,11 @@ struct SmemLayout {
     // address different components of the same bead slot (keeps them in different banks)
     static constexpr int NBP = (LANES > 1 && NB > 1) ? NB + 1 : NB;
     static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC;  // {p,q}[c][b] interleaved, cen, dxi, add, ham
-    static constexpr int BLOCK = (3 * NB + 32 + 1) & ~1;    // fker, reduction scratch (even: double2 alignment)
+    // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
+    // load_fker), otherwise the three circulant kernels f[N]
+    static constexpr bool HTAB = (NB > 1 && NB <= 32);
+    static constexpr int FKER = HTAB ? 3 * NB * NB : 3 * NB;
+    static constexpr int BLOCK = (FKER + 32 + 1) & ~1;      // + reduction scratch (even: double2 alignment)
     static constexpr size_t bytes()
     {
         return sizeof(double) * (BLOCK + Group<NB, LANES>::GPB * PER_GROUP);
@@ -245,6 +249,30 @@ struct Traj {
             return;
         }
         G.sync();
+        if (SmemLayout<NAT, NB, L>::HTAB) {
+            // out_a = sum_b H[b][a] x_b with H = Circ(f) (I+J)/2 (or Circ(f)) tabulated by load_fker
+            double cp[NO], aq[NO], bp[NO], cq[NO];
+#pragma unroll
+            for (int k = 0; k < NO; k++) cp[k] = aq[k] = bp[k] = cq[k] = 0.0;
+            const double* hk = fk + G.bead;
+#pragma unroll 2
+            for (int b = 0; b < NB; b++) {
+                const double fc = hk[b * NB], fa = hk[NB * NB + b * NB], fb = hk[2 * NB * NB + b * NB];
+#pragma unroll
+                for (int k = 0; k < NO; k++) {
+                    const double2 u = pq[ob[k] + b];
+                    cp[k] = fma(fc, u.x, cp[k]);
+                    aq[k] = fma(fa, u.y, aq[k]);
+                    bp[k] = fma(fb, u.x, bp[k]);
+                    cq[k] = fma(fc, u.y, cq[k]);
+                }
+            }
+            G.sync();
+#pragma unroll
+            for (int k = 0; k < NO; k++)
+                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
+            return;
+        }
         if (A.symmetrize) {
             // (I+J)/2: x_a <- (x_a + x_{N-a})/2, what T.T does
             const int rb = (NB - G.bead) & (NB - 1);
@@ -296,14 +324,15 @@ struct Traj {
     // xi in umbrella form; mode 1: xi in recrossing form, nothing added.
     __device__ __forceinline__ void umbrella(int mode)
     {
+        if (mode == 2) {
+            // child trajectory: only the value of xi is ever used (recross.f90:597-602); read the
+            // shared centroid in place
+            xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
+            return;
+        }
         double x[NC], d[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) x[c] = cen[c];
-        if (mode == 2) {
-            // child trajectory: only the value of xi is ever used (recross.f90:597-602)
-            xi_real = xi_value<NAT>(A.mech, x, xi_ideal, 2);
-            return;
-        }
         if (mode == 1) {
             calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 2, xi_real, d, nullptr, A.beta);
             G.sync();
@@ -629,10 +658,22 @@ struct LaunchCfg {
     static constexpr int MINB = (PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : 1;
 };
 
-template <int NB>
+// Free ring-polymer kernels into shared memory.  NB <= 32: the dense tables
+//   H_x[b][a] = f_x((a-b) mod N)                          (CRCL_TRANSFORM_EXACT)
+//   H_x[b][a] = (f_x((a-b) mod N) + f_x((a+b) mod N)) / 2  (reference: Circ(f).(I+J)/2)
+// for x = c, a, b, so that the symmetrisation costs nothing per step; otherwise f_x[N] as they come.
+template <int NAT, int NB, int LANES>
 __device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
 {
-    for (int i = threadIdx.x; i < 3 * NB; i += blockDim.x) smem[i] = A.fker[i];
+    if (SmemLayout<NAT, NB, LANES>::HTAB) {
+        for (int i = threadIdx.x; i < 3 * NB * NB; i += blockDim.x) {
+            const int x = i / (NB * NB), r = i - x * NB * NB, b = r / NB, a = r - b * NB;
+            const double f1 = A.fker[x * NB + ((a - b) & (NB - 1))];
+            smem[i] = A.symmetrize ? 0.5 * (f1 + A.fker[x * NB + ((a + b) & (NB - 1))]) : f1;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 3 * NB; i += blockDim.x) smem[i] = A.fker[i];
+    }
     __syncthreads();
 }
 
@@ -644,8 +685,8 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<NB>(A, smem);
-    Grp G(smem + 3 * NB);
+    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
@@ -716,8 +757,8 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<NB>(A, smem);
-    Grp G(smem + 3 * NB);
+    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
@@ -769,8 +810,8 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<NB>(A, smem);
-    Grp G(smem + 3 * NB);
+    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);

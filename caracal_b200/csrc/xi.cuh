@@ -24,6 +24,7 @@ struct Mech {
     int frag[XI_MAXAT];  // fragment of each atom, -1 = none
     double mass_reac[XI_MAXREAC];
     double wfrag[XI_MAXAT];  // mass[a] / mass_reac[frag[a]] (0 if the atom is in no fragment)
+    double wk[XI_MAXREAC][XI_MAXAT];  // wfrag[a] if frag[a] == k else 0: COM_k = sum_a wk[k][a] x_a
     double R_inf;
     int valid;
 };
@@ -66,8 +67,10 @@ inline int build_mech(Mech& M, int natoms, const double* mass, int form_num, con
         }
         off += n_reac[k];
     }
-    for (int a = 0; a < XI_MAXAT; a++)
+    for (int a = 0; a < XI_MAXAT; a++) {
         M.wfrag[a] = (a < natoms && M.frag[a] >= 0) ? mass[a] / M.mass_reac[M.frag[a]] : 0.0;
+        for (int k = 0; k < XI_MAXREAC; k++) M.wk[k][a] = (M.frag[a] == k) ? M.wfrag[a] : 0.0;
+    }
     M.R_inf = R_inf;
     M.valid = 1;
     return 0;
@@ -85,38 +88,49 @@ CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w
 
 // xi only (no gradient): what a child trajectory needs every step (verlet.f90:1049-1050 calls
 // umbrella mode 1 only to learn the sign of xi_real, recross.f90:597-602).
+// Every array index below is a compile-time constant after unrolling, except the bond atoms, which
+// index the caller's x (shared memory in the trajectory kernels): nothing lives in local memory.
 template <int NAT>
 CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double xi_ideal, int mode)
 {
     double s1 = 0.0;
     const double fnum = (double)M.form_num, bnum = (double)M.break_num;
-    for (int i = 0; i < M.break_num; i++) {
-        const int a1 = M.bb[i][0], a2 = M.bb[i][1];
-        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-        s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) / bnum;
-    }
-    for (int i = 0; i < M.form_num; i++) {
-        const int a1 = M.bf[i][0], a2 = M.bf[i][1];
-        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-        s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) / fnum;
-    }
+#pragma unroll
+    for (int i = 0; i < XI_MAXBOND; i++)
+        if (i < M.break_num) {
+            const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+            const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+            s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) / bnum;
+        }
+#pragma unroll
+    for (int i = 0; i < XI_MAXBOND; i++)
+        if (i < M.form_num) {
+            const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+            const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+            s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) / fnum;
+        }
+    // calc_com.f90:36-58; atoms outside fragment k enter with weight 0 (same sums, same order)
     double com[XI_MAXREAC][3];
 #pragma unroll
-    for (int k = 0; k < XI_MAXREAC; k++) com[k][0] = com[k][1] = com[k][2] = 0.0;
+    for (int k = 0; k < XI_MAXREAC; k++) {
+        com[k][0] = com[k][1] = com[k][2] = 0.0;
+        if (k < M.sum_reacs) {
 #pragma unroll
-    for (int a = 0; a < NAT; a++) {
-        const int k = M.frag[a];
-        if (k >= 0) {
+            for (int a = 0; a < NAT; a++) {
 #pragma unroll
-            for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
+                for (int d = 0; d < 3; d++) com[k][d] += M.wk[k][a] * x[3 * a + d];
+            }
         }
     }
     double s0 = 0.0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++) {
-            const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
-            s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
-        }
+#pragma unroll
+    for (int i = 0; i < XI_MAXREAC; i++)
+#pragma unroll
+        for (int j = i + 1; j < XI_MAXREAC; j++)
+            if (j < M.sum_reacs) {
+                const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
+                s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
+            }
     s0 = s0 / (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
     return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
 }
