@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         rows = [r for r in self.rows if len(r) >= 6 and r[0].isdigit()]
@@ -153,7 +153,7 @@ def make_parents_cpu():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -284,8 +284,18 @@ def main():
     kernel_ms = float(np.mean(kms)) if len(kms) else elapsed_ms / args.steps
     peak = g.measure_fp64_tflops(16384)
     achieved = bead_steps_step * fl_bs / (kernel_ms * 1e-3) / 1e12
+    # DRAM bytes of one launch of this kernel at this shape from an `ncu --set full` capture
+    # (profiles/traffic_recross.json, written by profiles/ncu_traffic.py); null when not captured
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic_recross.json")) as f:
+            tr = json.load(f)
+        if tr.get("child_steps") == CHILD_EVOL and tr.get("child_pairs") == NPAIRS:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "fp64", "kernel": "recross_kernel<PesCH4H,16>", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
                 "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                 "algorithmic_flops_per_launch": bead_steps_step * fl_bs,
                 "note": "algorithmic flops = reference's own operation count (oracle census); the kernel executes "

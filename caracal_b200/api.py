@@ -59,7 +59,8 @@ def _f64(a):
 
 
 class Mechanism:
-    """MECHA{} section, BIMOLEC family: 1-based atom indices as in the key file."""
+    """MECHA{} section, BIMOLEC family: 1-based atom indices as in the key file; dist_inf is R_inf in
+    BOHR as module evb_mod holds it (the key file's DIST_INF is in Angstrom, calc_rate_read.f90:693)."""
 
     def __init__(self, bond_form, bond_break, reactants, dist_inf, ts_struc):
         self.bond_form = np.asarray(bond_form, dtype=np.int32).reshape(-1, 2)
@@ -179,6 +180,28 @@ class RPMD:
         P.g_thres = float(E.get("g_thres", 1e-10))
         self._ck(self._lib.crcl_set_dgevb(self._h, ctypes.byref(P)), "crcl_set_dgevb")
 
+    def set_ewald(self, P):
+        """P: dict(box[3], a_ewald, nfft, bsorder, bsmod[3, nfft]) as module pbc_mod holds them after
+        set_periodic.f90:114-231 (caracal_b200.ewald.ewald_setup builds one for a stand-alone run)."""
+        bs = _f64(P["bsmod"]).reshape(3, -1)
+        self._ew_keep = bs
+        S = _l.EwaldParams()
+        for d in range(3):
+            S.box[d] = float(P["box"][d])
+        S.a_ewald, S.nfft, S.bsorder = float(P["a_ewald"]), int(P["nfft"]), int(P.get("bsorder", 5))
+        S.bsmod1, S.bsmod2, S.bsmod3 = (bs[d].ctypes.data_as(_l.c_double_p) for d in range(3))
+        self._ck(self._lib.crcl_set_ewald(self._h, ctypes.byref(S)), "crcl_set_ewald")
+
+    def ewald_recip(self, xyz, q):
+        """ewald_recip(n,xyz,q,energy,grad) for a batch: xyz [nimg, n, 3] -> energy [nimg], grad [nimg, n, 3]"""
+        q = _f64(q)
+        x = _f64(xyz).reshape(-1, len(q), 3)
+        e = np.zeros(x.shape[0])
+        g = np.zeros_like(x)
+        self._ck(self._lib.crcl_ewald_recip(self._h, len(q), x.shape[0], _dp(x), _dp(q), _dp(e), _dp(g)),
+                 "crcl_ewald_recip")
+        return e, g
+
     def set_mechanism(self, m):
         bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
         bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)
@@ -285,6 +308,21 @@ class RPMD:
         self._ck(self._lib.crcl_umbrella_window(self._h, _dp(q0), float(xi0), float(k_force), int(ntraj),
                                                 int(equi_steps), int(sample_steps), int(traj_id0), _dp(avg),
                                                 _dp(var), _ip(st)), "crcl_umbrella_window")
+        return avg, var, st
+
+    def umbrella_windows(self, q0, xi0, k_force, ntraj, equi_steps, sample_steps, traj_id0=0, constrain=0):
+        """All windows of the umbrella phase in one batch: q0[nwin, nbeads, natoms, 3], xi0[nwin],
+        k_force[nwin] -> avg, var, status of shape [nwin, ntraj].  constrain 0 (calc_rate.f90) or 3 (no
+        removal of net translation / rotation)."""
+        q0 = _f64(q0)
+        xi0, kf = _f64(np.atleast_1d(xi0)), _f64(np.atleast_1d(k_force))
+        nwin = len(xi0)
+        avg = np.zeros((nwin, ntraj))
+        var = np.zeros((nwin, ntraj))
+        st = np.zeros((nwin, ntraj), dtype=np.int32)
+        self._ck(self._lib.crcl_umbrella_windows(self._h, nwin, _dp(q0), _dp(xi0), _dp(kf), int(ntraj),
+                                                 int(equi_steps), int(sample_steps), int(constrain), int(traj_id0),
+                                                 _dp(avg), _dp(var), _ip(st)), "crcl_umbrella_windows")
         return avg, var, st
 
     # -- hooks ------------------------------------------------------------------------------------

@@ -74,7 +74,10 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if rebuilt or not os.path.exists(LIB):
         nvcc = os.environ.get("NVCC", "nvcc")
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        # cuFFT (the FFTW of ewald_recip.f90) from the toolkit; rpath so that the library also loads in a
+        # process that has not imported torch's bundled copy first
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + \
+              ["-lcufft", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

@@ -16,6 +16,7 @@
 #include "split_kernels.cuh"
 #include "qmdff.cuh"
 #include "dgevb.cuh"
+#include "ewald.cuh"
 
 using namespace crcl;
 
@@ -42,6 +43,7 @@ struct crcl_handle_s {
     QmdffDev* qmdff = nullptr;
     QmdffDev* qmdff2 = nullptr;
     DgevbDev* dgevb = nullptr;
+    EwaldDev* ewald = nullptr;
     // split path: per-atom tables on the device, generic-size mechanism
     double *d_mass = nullptr, *d_wfrag = nullptr;
     int *d_atmove = nullptr, *d_frag = nullptr;
@@ -596,6 +598,7 @@ int crcl_destroy(crcl_handle h)
     qmdff_free(h->qmdff);
     qmdff_free(h->qmdff2);
     dgevb_free(h->dgevb);
+    ewald_free(h->ewald);
     if (h->d_mass) cudaFree(h->d_mass);
     if (h->d_atmove) cudaFree(h->d_atmove);
     if (h->d_frag) cudaFree(h->d_frag);
@@ -742,6 +745,46 @@ int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params* P)
     const char* msg = "";
     const int rc = dgevb_upload(P, h->natoms, &h->dgevb, &msg);
     if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
+int crcl_set_ewald(crcl_handle h, const crcl_ewald_params* P)
+{
+    if (!h || !P) return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    ewald_free(h->ewald);
+    h->ewald = nullptr;
+    const char* msg = "";
+    const int rc = ewald_upload(P, &h->ewald, &msg);
+    if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
+int crcl_ewald_recip(crcl_handle h, int n, int nimg, const double* xyz, const double* q, double* energy, double* grad)
+{
+    if (!h || !xyz || !q || !energy || !grad || n < 0 || nimg < 0) return CRCL_EINVAL;
+    if (!h->ewald) return fail(h, CRCL_ESTATE, "crcl_set_ewald has not been called");
+    if (n == 0 || nimg == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    const size_t nx = (size_t)nimg * 3 * n;
+    double *dx, *dg, *de, *dq;
+    int rc;
+    if ((rc = scratch(h, 0, nx, &dx)) || (rc = scratch(h, 1, nx, &dg)) || (rc = scratch(h, 2, (size_t)nimg, &de)) ||
+        (rc = scratch(h, 3, (size_t)n, &dq)))
+        return rc;
+    CK(cudaMemcpyAsync(dx, xyz, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->timed) {
+        next_event_pair(h);
+        cudaEventRecord(h->ev0, h->stream);
+    }
+    const char* msg = "";
+    rc = ewald_recip(h->ewald, n, nimg, dx, dq, de, dg, h->stream, &h->launches, &msg);
+    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    if (rc) return fail(h, rc, msg);
+    CK(cudaMemcpyAsync(energy, de, (size_t)nimg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(grad, dg, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     return CRCL_OK;
 }
 
@@ -1126,46 +1169,57 @@ int crcl_recross_children(crcl_handle h, const double* q_parents, int nparent, i
     return CRCL_OK;
 }
 
-int crcl_umbrella_window(crcl_handle h, const double* q0, double xi0, double k_force, int ntraj,
-                         int equi_steps, int sample_steps, uint32_t traj_id0, double* avg, double* var,
-                         int* status)
+int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const double* xi0, const double* k_force,
+                          int ntraj, int equi_steps, int sample_steps, int constrain, uint32_t traj_id0, double* avg,
+                          double* var, int* status)
 {
     int rc = check_traj_call(h, 0);
     if (rc) return rc;
-    if (!q0 || !avg || !var || ntraj < 0 || equi_steps < 0 || sample_steps <= 0) return CRCL_EINVAL;
-    if (ntraj == 0) return CRCL_OK;
+    if (!q0 || !xi0 || !k_force || !avg || !var || nwin < 0 || ntraj < 0 || equi_steps < 0 || sample_steps <= 0 ||
+        (constrain != 0 && constrain != 3))
+        return CRCL_EINVAL;
+    const int ntot = nwin * ntraj;
+    if (ntot == 0) return CRCL_OK;
     CK(cudaSetDevice(h->device));
     if ((rc = ensure_fker(h))) return rc;
-    const size_t per = (size_t)h->nbeads * h->natoms * 3, n = per * ntraj, nd = (size_t)ntraj * h->natoms * 3;
-    double *dq, *dp, *dg, *ddxi, *dep, *dnhc;
+    const size_t per = (size_t)h->nbeads * h->natoms * 3, n = per * ntot, nd = (size_t)ntot * h->natoms * 3;
+    double *dq, *dp, *dg, *ddxi, *dep, *dnhc, *dwin, *dv;
     int* dst;
     uint32_t* dev;
     if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
-        (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntraj * 4, &dep)) ||
-        (rc = scratch(h, 5, (size_t)ntraj, &dst)) || (rc = scratch(h, 6, (size_t)ntraj * 2, &dev)) ||
-        (rc = scratch(h, 7, (size_t)ntraj * 8, &dnhc)))
+        (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntot * 4, &dep)) ||
+        (rc = scratch(h, 5, (size_t)ntot, &dst)) || (rc = scratch(h, 6, (size_t)ntot * 2, &dev)) ||
+        (rc = scratch(h, 7, (size_t)ntot * 8, &dnhc)) || (rc = scratch(h, 8, (size_t)ntot * 2, &dwin)) ||
+        (rc = scratch(h, 9, (size_t)ntot * h->nbeads, &dv)))
         return rc;
     cudaStream_t s = h->stream;
-    // every trajectory starts from the window's equilibrated structure (calc_rate.f90:1523-1535)
-    std::vector<double> rep(n);
-    for (int t = 0; t < ntraj; t++) memcpy(rep.data() + t * per, q0, per * sizeof(double));
+    // every trajectory starts from its window's equilibrated structure (calc_rate.f90:1383-1387)
+    std::vector<double> rep(n), win(2 * (size_t)ntot);
+    for (int w = 0; w < nwin; w++)
+        for (int t = 0; t < ntraj; t++) {
+            const size_t i = (size_t)w * ntraj + t;
+            memcpy(rep.data() + i * per, q0 + (size_t)w * per, per * sizeof(double));
+            win[i] = xi0[w];
+            win[ntot + i] = k_force[w];
+        }
     CK(cudaMemcpyAsync(dq, rep.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(dwin, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(dp, 0, n * sizeof(double), s));
-    CK(cudaMemsetAsync(dev, 0, ntraj * 2 * sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(dst, 0, ntraj * sizeof(int), s));
-    CK(cudaMemsetAsync(dep, 0, ntraj * 4 * sizeof(double), s));
+    CK(cudaMemsetAsync(dev, 0, ntot * 2 * sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(dst, 0, ntot * sizeof(int), s));
+    CK(cudaMemsetAsync(dep, 0, ntot * 4 * sizeof(double), s));
     TrajArgs A;
     fill_args(h, A);
-    A.ntraj = ntraj;
-    A.constrain = 0;
-    A.xi_ideal_s = xi0;
-    A.k_force_s = k_force;
+    A.ntraj = ntot;
+    A.constrain = constrain;
+    A.xi_ideal = dwin;
+    A.k_force = dwin + ntot;
     A.q = dq;
     A.p = dp;
     A.g = dg;
     A.dxi = ddxi;
     A.epot = dep;
-    A.xi_real = dep + ntraj;
+    A.xi_real = dep + ntot;
     A.status = dst;
     A.nhc = dnhc;
     A.traj_id0 = traj_id0;
@@ -1174,26 +1228,35 @@ int crcl_umbrella_window(crcl_handle h, const double* q0, double xi0, double k_f
     A.nsteps = equi_steps;
     A.istep0 = 0;
     if (equi_steps > 0 && (rc = launch_traj(h, K_VERLET, A))) return rc;
-    // calc_rate.f90:1619-1623 recomputes the gradient before sampling: the forces in g are
-    // already those of the current positions, so nothing to do; the step counter restarts.
+    // calc_rate.f90:1619-1623 recomputes derivs with plain `gradient` calls before the sampling
+    // loop: the first half kick of the sampling phase sees the forces WITHOUT the umbrella bias
+    if ((rc = crcl_egrad_dev(h, h->pes, dq, h->natoms, ntot * h->nbeads, dv, dg, nullptr))) return rc;
     A.nsteps = sample_steps;
     A.istep0 = 0;
-    A.xi_sum = dep + 2 * ntraj;
-    A.xi_sum2 = dep + 3 * ntraj;
+    A.xi_sum = dep + 2 * ntot;
+    A.xi_sum2 = dep + 3 * ntot;
     if ((rc = launch_traj(h, K_VERLET, A))) return rc;
-    std::vector<double> sums(2 * (size_t)ntraj);
-    CK(cudaMemcpyAsync(sums.data(), dep + 2 * ntraj, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    std::vector<int> st(ntraj);
-    CK(cudaMemcpyAsync(st.data(), dst, ntraj * sizeof(int), cudaMemcpyDeviceToHost, s));
+    std::vector<double> sums(2 * (size_t)ntot);
+    CK(cudaMemcpyAsync(sums.data(), dep + 2 * ntot, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<int> st(ntot);
+    CK(cudaMemcpyAsync(st.data(), dst, ntot * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    for (int t = 0; t < ntraj; t++) {
+    for (int t = 0; t < ntot; t++) {
         // calc_rate.f90:1660-1664: av = sum/n, var = sum2/n - av^2
         const double a = sums[t] / sample_steps;
         avg[t] = a;
-        var[t] = sums[ntraj + t] / sample_steps - a * a;
+        var[t] = sums[ntot + t] / sample_steps - a * a;
         if (status) status[t] = st[t];
     }
     return CRCL_OK;
+}
+
+int crcl_umbrella_window(crcl_handle h, const double* q0, double xi0, double k_force, int ntraj,
+                         int equi_steps, int sample_steps, uint32_t traj_id0, double* avg, double* var,
+                         int* status)
+{
+    return crcl_umbrella_windows(h, 1, q0, &xi0, &k_force, ntraj, equi_steps, sample_steps, 0, traj_id0, avg, var,
+                                 status);
 }
 
 // ---- hooks ------------------------------------------------------------------------------------

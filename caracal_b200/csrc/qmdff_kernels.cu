@@ -779,28 +779,35 @@ __global__ void __launch_bounds__(128) qm_hb_search_kernel(const QmdffDev D, con
         int qn = 0;
         // blockIdx.z: segment of QM_HB_SEG atoms j (more warps in flight when there are few donors)
         const int jbeg = blockIdx.z * QM_HB_SEG, jend = min(n, jbeg + QM_HB_SEG);
-        for (int j0 = jbeg; j0 < jend; j0 += 32) {
-            const int j = j0 + lane;
-            bool ok = j < jend;
-            if (ok) {
-                const float4 c = F[j];
-                float dx = fa.x - c.x, dy = fa.y - c.y, dz = fa.z - c.z;
+        const float4 far4 = make_float4(0.f, 0.f, 0.f, __int_as_float(mH));   // fails the molecule test
+        for (int j0 = jbeg; j0 < jend; j0 += 128) {
+            // four chunks of 32 atoms: all loads first, then the tests (the sweep is latency-bound)
+            float4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + 32 * u + lane;
+                c[u] = (j < jend) ? F[j] : far4;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + 32 * u + lane;
+                float dx = fa.x - c[u].x, dy = fa.y - c[u].y, dz = fa.z - c[u].z;
                 if (img_aj) {
                     dx = image_f(dx, Lxf, iLx);
                     dy = image_f(dy, Lyf, iLy);
                     dz = image_f(dz, Lzf, iLz);
                 }
-                ok = __float_as_int(c.w) != mH && dx * dx + dy * dy + dz * dz <= r2max;
-            }
-            if (ok) ok = (kind == 1) ? D.acc_no[j] != 0 : dscal * D.acc_s[j] > 1e-6;
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) qu[qn + __popc(m & ((1u << lane) - 1u))] = j;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                qn -= 32;
-                pair(qu[qn + lane]);
+                bool ok = __float_as_int(c[u].w) != mH && dx * dx + dy * dy + dz * dz <= r2max;
+                if (ok) ok = (kind == 1) ? D.acc_no[j] != 0 : dscal * D.acc_s[j] > 1e-6;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) qu[qn + __popc(m & ((1u << lane) - 1u))] = j;
+                qn += __popc(m);
                 __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    pair(qu[qn + lane]);
+                    __syncwarp();
+                }
             }
         }
         if (lane < qn) pair(qu[lane]);

@@ -327,7 +327,9 @@ struct Traj {
         if (mode == 2) {
             // child trajectory: only the value of xi is ever used (recross.f90:597-602); read the
             // shared centroid in place
-            xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
+            // shared centroid in place.  Only thread 0 of the trajectory consumes xi_real (theta,
+            // xi sums), so for CTA-wide groups the other warps skip the evaluation.
+            if (Grp::WARP || threadIdx.x < 32) xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
             return;
         }
         double x[NC], d[NC];

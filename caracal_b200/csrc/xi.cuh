@@ -26,6 +26,7 @@ struct Mech {
     double wfrag[XI_MAXAT];  // mass[a] / mass_reac[frag[a]] (0 if the atom is in no fragment)
     double wk[XI_MAXREAC][XI_MAXAT];  // wfrag[a] if frag[a] == k else 0: COM_k = sum_a wk[k][a] x_a
     double R_inf;
+    double inv_form, inv_break, inv_pairs;  // 1/form_num, 1/break_num, 1/(number of reactant pairs)
     int valid;
 };
 
@@ -72,6 +73,9 @@ inline int build_mech(Mech& M, int natoms, const double* mass, int form_num, con
         for (int k = 0; k < XI_MAXREAC; k++) M.wk[k][a] = (M.frag[a] == k) ? M.wfrag[a] : 0.0;
     }
     M.R_inf = R_inf;
+    M.inv_form = form_num ? 1.0 / form_num : 0.0;
+    M.inv_break = break_num ? 1.0 / break_num : 0.0;
+    M.inv_pairs = 1.0 / (double)((sum_reacs * sum_reacs - sum_reacs) / 2);
     M.valid = 1;
     return 0;
 }
@@ -86,7 +90,8 @@ CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w
     for (int d = 0; d < 3; d++) o[d] = (rr * w[d] - r[d] * rw) * r3;
 }
 
-// xi only (no gradient): what a child trajectory needs every step (verlet.f90:1049-1050 calls
+// xi only (no gradient), with the averages as multiplications by host-computed reciprocals (exact
+// for 1, 2 and 4 bonds / pairs, one ulp otherwise): what a child trajectory needs every step (verlet.f90:1049-1050 calls
 // umbrella mode 1 only to learn the sign of xi_real, recross.f90:597-602).
 // Every array index below is a compile-time constant after unrolling, except the bond atoms, which
 // index the caller's x (shared memory in the trajectory kernels): nothing lives in local memory.
@@ -94,20 +99,19 @@ template <int NAT>
 CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double xi_ideal, int mode)
 {
     double s1 = 0.0;
-    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
 #pragma unroll
     for (int i = 0; i < XI_MAXBOND; i++)
         if (i < M.break_num) {
             const int a1 = M.bb[i][0], a2 = M.bb[i][1];
             const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-            s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) / bnum;
+            s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) * M.inv_break;
         }
 #pragma unroll
     for (int i = 0; i < XI_MAXBOND; i++)
         if (i < M.form_num) {
             const int a1 = M.bf[i][0], a2 = M.bf[i][1];
             const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-            s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) / fnum;
+            s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) * M.inv_form;
         }
     // calc_com.f90:36-58; atoms outside fragment k enter with weight 0 (same sums, same order)
     double com[XI_MAXREAC][3];
@@ -131,7 +135,7 @@ CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double x
                 const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
                 s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
             }
-    s0 = s0 / (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
+    s0 = s0 * M.inv_pairs;
     return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
 }
 

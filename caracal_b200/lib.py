@@ -45,6 +45,12 @@ class DgevbParams(ctypes.Structure):
                 ("point_int", c_double_p), ("alph", c_double_p), ("b_vec", c_double_p), ("g_thres", ctypes.c_double)]
 
 
+class EwaldParams(ctypes.Structure):
+    """crcl_ewald_params of include/caracal_gpu.h"""
+    _fields_ = [("box", ctypes.c_double * 3), ("a_ewald", ctypes.c_double), ("nfft", ctypes.c_int),
+                ("bsorder", ctypes.c_int), ("bsmod1", c_double_p), ("bsmod2", c_double_p), ("bsmod3", c_double_p)]
+
+
 # every symbol include/caracal_gpu.h declares: (restype, argtypes)
 _H = ctypes.c_void_p
 SIGNATURES = {
@@ -61,6 +67,9 @@ SIGNATURES = {
     "crcl_set_qmdff2": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),
     "crcl_set_dgevb": (ctypes.c_int, [_H, ctypes.POINTER(DgevbParams)]),
     "crcl_set_path": (ctypes.c_int, [_H, ctypes.c_int]),
+    "crcl_set_ewald": (ctypes.c_int, [_H, ctypes.POINTER(EwaldParams)]),
+    "crcl_ewald_recip": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p,
+                                        c_double_p]),
     "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                           ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),
     "crcl_set_thermostat": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
@@ -84,6 +93,9 @@ SIGNATURES = {
     "crcl_umbrella_window": (ctypes.c_int, [_H, c_double_p, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int, ctypes.c_uint32, c_double_p, c_double_p,
                                             c_int_p]),
+    "crcl_umbrella_windows": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, c_double_p,
+                                             c_double_p, c_int_p]),
     "crcl_rng_normals": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                                         ctypes.c_int, c_double_p]),
     "crcl_launch_count": (ctypes.c_longlong, [_H]),

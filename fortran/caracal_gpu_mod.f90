@@ -11,7 +11,31 @@ use, intrinsic :: iso_c_binding
 implicit none
 
 integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 3
+integer(c_int), parameter :: CRCL_PES_QMDFF = 10, CRCL_PES_DGEVB = 11, CRCL_PES_HOSTCB = 100
 type(c_ptr), save :: crcl_h = c_null_ptr        ! one handle per MPI rank / GPU
+
+!     struct crcl_qmdff_tables of include/caracal_gpu.h (field order and types must match)
+type, bind(C) :: crcl_qmdff_tables
+   integer(c_int) :: n
+   type(c_ptr) :: at, q, molnum
+   integer(c_int) :: nmols
+   integer(c_int) :: nbond, nangl, ntors, nhb, nnci, ldvt
+   type(c_ptr) :: bond, vbond, angl, vangl, tors, vtors, nci, c6xy
+   type(c_ptr) :: r0ab, zab, r094, sr42, rad
+   real(c_double) :: eps1(6), eps2(6)
+   integer(c_int) :: periodic, zahn
+   real(c_double) :: box(3)
+   real(c_double) :: coul_cut, vdw_cut, cut_low, zahn_a, zahn_par
+   real(c_double) :: e_zero
+   type(c_ptr) :: hb, vhb, scalehb, scalexb, q_glob
+end type crcl_qmdff_tables
+
+!     struct crcl_dgevb_params
+type, bind(C) :: crcl_dgevb_params
+   integer(c_int) :: mode, npoints, nat6
+   type(c_ptr) :: coord_def, point_int, alph, b_vec
+   real(c_double) :: g_thres
+end type crcl_dgevb_params
 
 interface
    function crcl_create(h, device, natoms, nbeads, mass, at_move, beta, dt, pes_id) bind(C, name="crcl_create")
@@ -126,6 +150,47 @@ interface
       integer(c_int), dimension(*), intent(out) :: status
       integer(c_int) :: crcl_umbrella_window
    end function crcl_umbrella_window
+
+   ! all windows of the umbrella phase in one batch (master/worker loop calc_rate.f90:1351-1376)
+   function crcl_umbrella_windows(h, nwin, q0, xi0, k_force, ntraj, equi_steps, sample_steps, constrain, traj_id0, &
+                                  avg, var, status) bind(C, name="crcl_umbrella_windows")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: nwin, ntraj, equi_steps, sample_steps, constrain, traj_id0
+      real(c_double), dimension(*), intent(in) :: q0, xi0, k_force
+      real(c_double), dimension(*), intent(out) :: avg, var
+      integer(c_int), dimension(*), intent(out) :: status
+      integer(c_int) :: crcl_umbrella_windows
+   end function crcl_umbrella_windows
+
+   ! QMDFF tables of module qmdff / pbc_mod (first and second diabatic state), DG-EVB parameters
+   function crcl_set_qmdff(h, T) bind(C, name="crcl_set_qmdff")
+      import :: c_ptr, c_int, crcl_qmdff_tables
+      type(c_ptr), value :: h
+      type(crcl_qmdff_tables), intent(in) :: T
+      integer(c_int) :: crcl_set_qmdff
+   end function crcl_set_qmdff
+   function crcl_set_qmdff2(h, T) bind(C, name="crcl_set_qmdff2")
+      import :: c_ptr, c_int, crcl_qmdff_tables
+      type(c_ptr), value :: h
+      type(crcl_qmdff_tables), intent(in) :: T
+      integer(c_int) :: crcl_set_qmdff2
+   end function crcl_set_qmdff2
+   function crcl_set_dgevb(h, P) bind(C, name="crcl_set_dgevb")
+      import :: c_ptr, c_int, crcl_dgevb_params
+      type(c_ptr), value :: h
+      type(crcl_dgevb_params), intent(in) :: P
+      integer(c_int) :: crcl_set_dgevb
+   end function crcl_set_dgevb
+
+   ! custom_grad / external_grad stay on the host: fn(xyz, e, g, natoms, user) is called per bead
+   function crcl_set_host_gradient_cb(h, fn, user) bind(C, name="crcl_set_host_gradient_cb")
+      import :: c_ptr, c_funptr, c_int
+      type(c_ptr), value :: h
+      type(c_funptr), value :: fn
+      type(c_ptr), value :: user
+      integer(c_int) :: crcl_set_host_gradient_cb
+   end function crcl_set_host_gradient_cb
 end interface
 
 contains
@@ -173,6 +238,40 @@ rc = crcl_set_mechanism(crcl_h, int(form_num, c_int), bf, int(break_num, c_int),
                         int(sum_reacs, c_int), int(n_reac(1:sum_reacs), c_int), atr, R_inf)
 rc = crcl_set_thermostat(crcl_h, int(thermostat, c_int), int(andersen_step, c_int), kelvin, nose_q)
 end subroutine gpu_init
+
+!
+!     gpu_set_qmdff: hand the tables of the first QMDFF (module qmdff, pbc_mod; built by prepare.f90,
+!     rdsolvff.f90, setnonb.f90, set_periodic.f90) to the library.  Call once after read_pes.
+!     The second state works the same way with the *_two arrays and crcl_set_qmdff2.
+!
+subroutine gpu_set_qmdff(n_one)
+use qmdff        ! at, q, molnum, nmols, bond, vbond, angl, vangl, tors, vtors, nci, c6xy, r0ab, zab,
+                 ! r094_mod, sr42, rad, eps1, eps2, hb, vhb, scalehb_glob, scalexb_glob, q_glob, nbond, ...
+use pbc_mod      ! periodic, zahn, boxlen_x/y/z, coul_cut, vdw_cut, cut_low, zahn_a, zahn_par
+use evb_mod      ! E_zero1
+integer, intent(in) :: n_one
+type(crcl_qmdff_tables) :: T
+integer(c_int) :: rc
+T%n = n_one
+T%at = c_loc(at);       T%q = c_loc(q);        T%molnum = c_loc(molnum);  T%nmols = nmols
+T%nbond = nbond; T%nangl = nangl; T%ntors = ntors; T%nhb = nhb; T%nnci = nnci; T%ldvt = size(vtors,1)
+T%bond = c_loc(bond);   T%vbond = c_loc(vbond); T%angl = c_loc(angl);     T%vangl = c_loc(vangl)
+T%tors = c_loc(tors);   T%vtors = c_loc(vtors); T%nci = c_loc(nci);       T%c6xy = c_loc(c6xy)
+T%r0ab = c_loc(r0ab);   T%zab = c_loc(zab);     T%r094 = c_loc(r094_mod); T%sr42 = c_loc(sr42)
+T%rad = c_loc(rad)
+T%eps1 = eps1; T%eps2 = eps2
+T%periodic = merge(1, 0, periodic); T%zahn = merge(1, 0, zahn)
+T%box = (/ boxlen_x, boxlen_y, boxlen_z /)
+T%coul_cut = coul_cut; T%vdw_cut = vdw_cut; T%cut_low = cut_low; T%zahn_a = zahn_a; T%zahn_par = zahn_par
+T%e_zero = E_zero1
+T%hb = c_loc(hb); T%vhb = c_loc(vhb)
+T%scalehb = c_loc(scalehb_glob); T%scalexb = c_loc(scalexb_glob); T%q_glob = c_loc(q_glob)
+rc = crcl_set_qmdff(crcl_h, T)
+if (rc .ne. 0) then
+   write(*,*) "caracal_gpu: crcl_set_qmdff failed with code", rc
+   call fatal
+end if
+end subroutine gpu_set_qmdff
 
 !
 !     verlet_gpu: same argument list as verlet (verlet.f90:65); operates on the module globals

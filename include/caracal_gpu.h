@@ -154,6 +154,23 @@ typedef struct crcl_dgevb_params {
 } crcl_dgevb_params;
 int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params *P);
 
+/* Smooth particle-mesh Ewald, reciprocal-space part (ewald_recip.f90:30-470).  The set-up quantities
+ * are those of module pbc_mod after set_periodic.f90:114-231: boxlen_x/y/z (bohr), a_ewald, nfft (one
+ * value for all three dimensions), bsorder (5) and the B-spline moduli bsmod1/2/3(nfft).
+ * NB the reference cannot reach ewald_recip (ff_nonb.f90:337 sets ewald=.false.): this entry point
+ * stands alone and is not part of CRCL_PES_QMDFF. */
+typedef struct crcl_ewald_params {
+    double box[3];
+    double a_ewald;
+    int nfft, bsorder;
+    const double *bsmod1, *bsmod2, *bsmod3;
+} crcl_ewald_params;
+int crcl_set_ewald(crcl_handle h, const crcl_ewald_params *P);
+/* ewald_recip(n,xyz,q,energy,grad) for nimg structures: xyz [nimg][n][3], q [n] -> energy [nimg],
+ * grad [nimg][n][3] (overwritten, the reference zeroes grad too, :421) */
+int crcl_ewald_recip(crcl_handle h, int n, int nimg, const double *xyz, const double *q,
+                     double *energy, double *grad);
+
 /* NVT{} section: thermostat 0 none, 1 Andersen, 2 Nose-Hoover chain (dynamic.f90:463-465);
  * andersen_step as evb_mod.f90:289; kelvin and nose_q for nhc.f90 / mdinit.f90:138-146 */
 int crcl_set_thermostat(crcl_handle h, int thermostat, int andersen_step, double kelvin,
@@ -214,6 +231,15 @@ int crcl_recross_children_dev(crcl_handle h, const double *d_q_parents, int npar
 int crcl_umbrella_window(crcl_handle h, const double *q0, double xi0, double k_force, int ntraj,
                          int equi_steps, int sample_steps, uint32_t traj_id0, double *avg,
                          double *var, int *status);
+/* The master/worker loop over windows (calc_rate.f90:1351-1376) as one batch: window w starts from
+ * q0[w] with (xi0[w], k_force[w]); trajectory t of window w is index w*ntraj+t in avg/var/status and
+ * uses RNG stream traj_id0 + w*ntraj + t.  Before the sampling phase the forces are recomputed
+ * without the bias, as calc_rate.f90:1619-1623 does.  constrain is the flag handed to verlet:
+ * 0 as calc_rate.f90 does, or 3 = the same biased dynamics without the removal of net
+ * translation / rotation (verlet.f90:1051,1300-1306; what pre_sample.f90:123 uses). */
+int crcl_umbrella_windows(crcl_handle h, int nwin, const double *q0, const double *xi0,
+                          const double *k_force, int ntraj, int equi_steps, int sample_steps,
+                          int constrain, uint32_t traj_id0, double *avg, double *var, int *status);
 
 /* ---- test / introspection hooks ---------------------------------------------------- */
 /* n standard normals of stream (seed, traj, event, bead), elements 0..n-1 (DESIGN.md "RNG") */

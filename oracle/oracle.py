@@ -55,6 +55,9 @@ def lib(exact=False):
         L.orc_calc_xi.argtypes = [ctypes.c_void_p, dp, ctypes.c_double, dp, dp, dp, ctypes.c_int]
         L.orc_umbrella.argtypes = [ctypes.c_void_p, dp, ctypes.c_double, dp, dp, dp, ctypes.c_int]
         L.orc_get_centroid.argtypes = [ctypes.c_void_p, dp]
+        L.orc_gradient.argtypes = [ctypes.c_void_p, dp, dp, dp]
+        L.oracle_sys_get_event.argtypes = [ctypes.c_void_p]
+        L.oracle_sys_get_event.restype = ctypes.c_uint32
         L.orc_andersen.argtypes = [ctypes.c_void_p]
         L.orc_transrot.argtypes = [ctypes.c_void_p]
         L.orc_transrot.restype = ctypes.c_int
@@ -173,6 +176,10 @@ class System:
     def set_rng(self, seed, traj, event=0):
         self.L.oracle_sys_set_rng(self.h, seed, traj, event)
 
+    def event(self):
+        """number of momentum-resampling events drawn so far on this stream"""
+        return int(self.L.oracle_sys_get_event(self.h))
+
     def inject_normals(self, z):
         z = np.ascontiguousarray(z, dtype=np.float64)
         self._keep.append(z)
@@ -185,6 +192,12 @@ class System:
 
     def mdinit(self, xi_ideal=0.0, bias_mode=0):
         self.L.orc_mdinit(self.h, _d(self.derivs), xi_ideal, _d(self.dxi), bias_mode)
+
+    def gradient_all(self):
+        """derivs <- plain PES gradient of every bead, no bias (calc_rate.f90:1619-1623)"""
+        e = ctypes.c_double(0.0)
+        for b in range(self.nbeads):
+            self.L.orc_gradient(self.h, _d(self.q[b]), ctypes.byref(e), _d(self.derivs[b]))
 
     def verlet(self, istep, xi_ideal=0.0, constrain=-1):
         epot = ctypes.c_double(0.0)
@@ -340,3 +353,49 @@ class Dgevb:
         out = np.zeros(self.S.nat6)
         self.L.orc_xyz_2int(ctypes.byref(self.S), _d(x), _d(out))
         return out
+
+
+class Ewald:
+    """Oracle of set_periodic.f90:114-231 (SPME set-up) and ewald_recip.f90 for an orthorhombic box."""
+
+    def __init__(self, box):
+        self.L = lib()
+        self.box = np.ascontiguousarray(box, dtype=np.float64)
+        self.L.orc_ewald_setup.restype = ctypes.c_void_p
+        self.L.orc_ewald_setup.argtypes = [dp]
+        self.L.orc_ewald_free.argtypes = [ctypes.c_void_p]
+        self.L.orc_ewald_nfft.argtypes = [ctypes.c_void_p]
+        self.L.orc_ewald_alpha.argtypes = [ctypes.c_void_p]
+        self.L.orc_ewald_alpha.restype = ctypes.c_double
+        self.L.orc_ewald_bsmod.argtypes = [ctypes.c_void_p, dp]
+        self.L.orc_ewald_recip.argtypes = [ctypes.c_void_p, ctypes.c_int, dp, dp, dp, dp]
+        self.L.orc_ewald_direct_recip.argtypes = [dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp]
+        self.h = ctypes.c_void_p(self.L.orc_ewald_setup(_d(self.box)))
+        self.nfft = int(self.L.orc_ewald_nfft(self.h))
+        self.a_ewald = float(self.L.orc_ewald_alpha(self.h))
+        self.bsorder = 5
+        bs = np.zeros(3 * self.nfft)
+        self.L.orc_ewald_bsmod(self.h, _d(bs))
+        self.bsmod = bs.reshape(3, self.nfft)
+
+    def __del__(self):
+        try:
+            self.L.orc_ewald_free(self.h)
+        except Exception:
+            pass
+
+    def recip(self, xyz, q):
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        qq = np.ascontiguousarray(q, dtype=np.float64)
+        e = ctypes.c_double(0.0)
+        g = np.zeros_like(x)
+        self.L.orc_ewald_recip(self.h, len(qq), _d(x), _d(qq), ctypes.byref(e), _d(g))
+        return e.value, g
+
+    def direct_recip(self, xyz, q, mmax):
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        qq = np.ascontiguousarray(q, dtype=np.float64)
+        e = ctypes.c_double(0.0)
+        g = np.zeros_like(x)
+        self.L.orc_ewald_direct_recip(_d(self.box), self.a_ewald, int(mmax), len(qq), _d(x), _d(qq), ctypes.byref(e), _d(g))
+        return e.value, g

@@ -191,6 +191,7 @@ void oracle_sys_inject_normals(orc_sys *s, const double *z, long n)
 void oracle_sys_set_custom_grad(orc_sys *s, orc_custom_grad_fn fn) { s->custom_grad = fn; }
 double *oracle_sys_q(orc_sys *s) { return s->q; }
 double *oracle_sys_p(orc_sys *s) { return s->p; }
+uint32_t oracle_sys_get_event(orc_sys *s) { return s->event; }
 void oracle_sys_get_nhc(orc_sys *s, double *v4q4)
 {
     int i;

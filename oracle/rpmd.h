@@ -68,6 +68,7 @@ void oracle_sys_set_custom_grad(orc_sys *s, orc_custom_grad_fn fn);
 double *oracle_sys_q(orc_sys *s);
 double *oracle_sys_p(orc_sys *s);
 void oracle_sys_get_nhc(orc_sys *s, double *v4q4);
+uint32_t oracle_sys_get_event(orc_sys *s);
 
 void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g);
 void orc_get_centroid(orc_sys *s, double *centroid);

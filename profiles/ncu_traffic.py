@@ -1,0 +1,27 @@
+"""Extract dram__bytes_read.sum / dram__bytes_write.sum of the one kernel in an .ncu-rep into
+profiles/traffic_recross.json (read by bench.py for roofline.traffic).
+Usage: python profiles/ncu_traffic.py gpurun_out/x.ncu-rep child_steps child_pairs"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+rep, steps, pairs = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units, vals = rows[0], rows[1], rows[2]
+M = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def b(key):
+    v, u = M[key]
+    return float(v) * scale[u]
+
+
+out = dict(kernel=M["Kernel Name"][0], child_steps=steps, child_pairs=pairs, dram_bytes_read=b("dram__bytes_read.sum"),
+           dram_bytes_write=b("dram__bytes_write.sum"), duration_us_under_ncu=float(M["gpu__time_duration.sum"][0]),
+           source=os.path.basename(rep))
+json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic_recross.json"), "w"), indent=1)
+print(out)

@@ -83,6 +83,7 @@ def test_umbrella_window_matches_oracle(gpu, oracle):
         o.mdinit(xi0, 2)
         for i in range(1, equi + 1):
             o.verlet(i, xi0, 0)
+        o.gradient_all()          # calc_rate.f90:1619-1623: forces without the bias before sampling
         xs = []
         for i in range(1, samp + 1):
             xs.append(o.verlet(i, xi0, 0)[1])
@@ -90,6 +91,21 @@ def test_umbrella_window_matches_oracle(gpu, oracle):
         assert abs(avg[t] - xs.mean()) < 1e-9
         assert abs(var[t] - (np.mean(xs ** 2) - xs.mean() ** 2)) < 1e-9
     assert (st == 0).all()
+
+
+def test_umbrella_windows_batch_equals_single_windows(gpu):
+    name, nb, ntraj, equi, samp = "h3", 8, 3, 20, 40
+    g, _ = C.make_pair(name, nb)
+    g.set_seed(C.SEED)
+    g.set_thermostat(1, 7, 300.0)
+    rng = np.random.default_rng(9)
+    q0 = np.array([C.ring_polymer(name, nb, rng, 0.02) for _ in range(4)])
+    xi0, kf = np.array([0.2, 0.5, 0.9, 1.02]), np.array([15.0, 15.0, 12.0, 15.0])
+    avg, var, st = g.umbrella_windows(q0, xi0, kf, ntraj, equi, samp, traj_id0=7)
+    assert (st == 0).all()
+    for w in range(4):
+        a1, v1, s1 = g.umbrella_window(q0[w], xi0[w], kf[w], ntraj, equi, samp, traj_id0=7 + w * ntraj)
+        assert np.array_equal(a1, avg[w]) and np.array_equal(v1, var[w])
 
 
 def test_rng_stream_matches_oracle_and_is_normal(gpu, oracle):
