@@ -14,6 +14,7 @@
 #include "pes_ch4h.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
+#include "split_xi.cuh"
 #include "qmdff.cuh"
 #include "dgevb.cuh"
 #include "ewald.cuh"
@@ -55,8 +56,8 @@ struct crcl_handle_s {
     long long launches = 0;
     std::string err;
     // grow-only device scratch
-    void* scratch[16] = {nullptr};
-    size_t scratch_sz[16] = {0};
+    void* scratch[32] = {nullptr};
+    size_t scratch_sz[32] = {0};
 };
 
 #define CK(call)                                                                     \
@@ -415,7 +416,8 @@ static void launch_kfr_reg(const SplitArgs& A, dim3 grid, cudaStream_t s)
 static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
 {
     const int nc = 3 * A.natoms;
-    dim3 grid((unsigned)((size_t)((nc + 127) / 128) * A.ntraj));
+    const size_t ncomp = (size_t)nc * A.ntraj;
+    dim3 grid((unsigned)((ncomp + 127) / 128));
     if (h->timed) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
@@ -435,7 +437,7 @@ static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
         const size_t smem = (size_t)(3 * A.nbeads + 2 * (size_t)A.nbeads * bd) * sizeof(double);
         if (smem > 200 * 1024) return fail(h, CRCL_ENOSUP, "split path: nbeads too large for the shared-memory transform");
         CK(cudaFuncSetAttribute(sp_kick_freerp_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 g2((unsigned)((size_t)((nc + bd - 1) / bd) * A.ntraj));
+        dim3 g2((unsigned)((ncomp + bd - 1) / bd));
         sp_kick_freerp_smem<<<g2, bd, smem, h->stream>>>(A);
     }
     }
@@ -445,24 +447,74 @@ static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
     return CRCL_OK;
 }
 
-// nsteps verlet steps on device-resident state (split path).  Supported this round: constrain -1
-// (plain MD incl. transrot) and 2 (child trajectory); thermostat 0 / 1.
-static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain, const double* d_xi_ideal,
-                        double xi_ideal_s, double* dq, double* dp, double* dg, double* dep, double* dxr, int* dst,
-                        const uint32_t* dtid, uint32_t* dev)
+// Device-resident state of a batch on the split path (all pointers device memory).
+struct SplitCall {
+    int ntraj = 0;
+    double *q = nullptr, *p = nullptr, *g = nullptr, *dxi = nullptr, *epot = nullptr, *xi_real = nullptr, *nhc = nullptr;
+    int* status = nullptr;
+    const uint32_t* tid = nullptr;
+    uint32_t* event = nullptr;
+    const double *xi_ideal = nullptr, *k_force = nullptr;   // per trajectory, or null -> scalars
+    double xi_ideal_s = 0.0, k_force_s = 0.0;
+    double *xi_sum = nullptr, *xi_sum2 = nullptr;           // umbrella sampling accumulators (may be null)
+    unsigned char* theta = nullptr;                         // [nsteps][ntraj] (recrossing; may be null)
+};
+
+static int nfree_of(crcl_handle h)
 {
-    if (constrain != -1 && constrain != 2)
-        return fail(h, CRCL_ENOSUP, "split path: constrain 0/1 (umbrella, SHAKE) not implemented yet");
-    if (h->thermostat == 2) return fail(h, CRCL_ENOSUP, "split path: Nose-Hoover chain not implemented yet");
-    if (constrain == 2 && !h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    int nf = 0;
+    for (int i = 0; i < h->natoms; i++)
+        if (h->at_move[i]) nf += 3;   // mdinit.f90:131-137: not multiplied by nbeads
+    return nf;
+}
+
+// scratch of the biased / constrained modes; fills S
+static int split_traj_scratch(crcl_handle h, const SplitCall& C, SpTraj& S)
+{
+    const int na = h->natoms, nc = 3 * na, nt = C.ntraj;
+    double *dh, *dw, *dco;
+    int* dbad;
+    int rc;
+    if ((rc = scratch(h, 16, (size_t)nt * nc, &dh)) || (rc = scratch(h, 17, (size_t)nt * SPX_NWORK * nc, &dw)) ||
+        (rc = scratch(h, 18, (size_t)nt * 2, &dco)) || (rc = scratch(h, 19, (size_t)nt, &dbad)))
+        return rc;
+    S.ntraj = nt;
+    S.natoms = na;
+    S.nbeads = h->nbeads;
+    S.dt = h->dt;
+    S.beta = h->beta;
+    S.mass = h->d_mass;
+    S.at_move = h->d_atmove;
+    S.xi_ideal = C.xi_ideal;
+    S.k_force = C.k_force;
+    S.xi_ideal_s = C.xi_ideal_s;
+    S.k_force_s = C.k_force_s;
+    S.xi_real = C.xi_real;
+    S.dxi = C.dxi;
+    S.hams = dh;
+    S.work = dw;
+    S.status = C.status;
+    S.bad = dbad;
+    S.coeff = dco;
+    return CRCL_OK;
+}
+
+// nsteps verlet steps on device-resident state (split path): every constrain mode of verlet.f90
+// (-1 plain MD, 0 / 3 umbrella, 1 SHAKE / RATTLE, 2 child trajectory), thermostats 0 / 1 / 2.
+static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep0, int constrain)
+{
+    if (constrain >= 0 && !h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
     int rc;
     if ((rc = ensure_split_tables(h)) || (rc = ensure_fker(h))) return rc;
-    const int na = h->natoms, nb = h->nbeads, nc = 3 * na;
+    const int na = h->natoms, nb = h->nbeads, nc = 3 * na, ntraj = C.ntraj;
     const size_t per = (size_t)nb * nc;
     double *dcen, *dV, *dsums;
     if ((rc = scratch(h, 8, (size_t)ntraj * nc, &dcen)) || (rc = scratch(h, 9, (size_t)ntraj * nb, &dV)) ||
         (rc = scratch(h, 10, (size_t)ntraj * 16, &dsums)))
         return rc;
+    SpTraj S{};
+    if (constrain >= 0 || h->thermostat == 2)
+        if ((rc = split_traj_scratch(h, C, S))) return rc;
     SplitArgs A;
     A.ntraj = ntraj;
     A.natoms = na;
@@ -473,32 +525,65 @@ static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int co
     A.mass = h->d_mass;
     A.at_move = h->d_atmove;
     A.fker = h->d_fker;
-    A.q = dq;
-    A.p = dp;
-    A.g = dg;
+    A.q = C.q;
+    A.p = C.p;
+    A.g = C.g;
     A.cen = dcen;
-    A.status = dst;
+    A.status = C.status;
     A.seed = h->seed;
-    A.traj_id = dtid;
+    A.traj_id = C.tid;
     A.traj_id0 = 0;
-    A.event = dev;
+    A.event = C.event;
     double mt = 0.0;
     for (int i = 0; i < na; i++) mt += h->mass[i];
     cudaStream_t s = h->stream;
     const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
     const int rblocks = (int)std::min<size_t>(64, ((size_t)na * nb + 255) / 256);
+    const int tb = (ntraj + 63) / 64, nfree = nfree_of(h);
+    const bool nhc_on = (constrain != 2 && h->thermostat == 2);
     for (int st = 1; st <= nsteps; st++) {
         const int istep = istep0 + st;
+        if (nhc_on) {                                                        // 1
+            sp_nhc<<<ntraj, 256, 0, s>>>(S, C.p, C.nhc, h->kelvin, nfree);
+            h->launches++;
+        }
         if ((rc = launch_kick_freerp(h, A))) return rc;                       // 2,3,4,6,7
-        if ((rc = split_forces(h, ntraj * nb, dq, dg, dV))) return rc;        // 10
-        sp_epot<<<(ntraj + 127) / 128, 128, 0, s>>>(dV, nb, ntraj, dep);
-        if (constrain == 2)                                                   // 12
-            sp_xi_value<<<(ntraj + 63) / 64, 64, 0, s>>>(h->mechd, na, ntraj, dcen, d_xi_ideal, xi_ideal_s, 2, dxr);
+        if (constrain == 1) {                                                 // 9
+            sp_shake_solve<<<tb, 64, 0, s>>>(h->mechd, S, dcen);
+            sp_shake_apply<<<gel, 256, 0, s>>>(S, C.q, C.p);
+            h->launches += 2;
+        }
+        if ((rc = split_forces(h, ntraj * nb, C.q, C.g, dV))) return rc;      // 10
+        sp_epot<<<(ntraj + 127) / 128, 128, 0, s>>>(dV, nb, ntraj, C.epot);
+        h->launches++;
+        if (constrain == 1) {
+            sp_shake_penalty<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, S.bad, C.epot);
+            h->launches++;
+        }
+        if (constrain == 0 || constrain == 3) {                               // 12
+            sp_calc_xi_kernel<<<tb, 64, 0, s>>>(h->mechd, S, dcen, 1, 1);
+            sp_add_bias<<<gel, 256, 0, s>>>(S, C.g);
+            h->launches += 2;
+        } else if (constrain == 1) {
+            sp_calc_xi_kernel<<<tb, 64, 0, s>>>(h->mechd, S, dcen, 2, 0);
+            h->launches++;
+        } else if (constrain == 2) {
+            sp_xi_value<<<tb, 64, 0, s>>>(h->mechd, na, ntraj, dcen, C.xi_ideal, C.xi_ideal_s, 2, C.xi_real);
+            h->launches++;
+        }
         sp_kick<<<gel, 256, 0, s>>>(A);                                       // 13, 18
-        h->launches += 2 + (constrain == 2);
+        h->launches++;
+        if (constrain == 1) {                                                 // 14
+            sp_rattle<<<ntraj, 256, 0, s>>>(S, C.p);
+            h->launches++;
+        }
+        if (nhc_on) {                                                         // 15
+            sp_nhc<<<ntraj, 256, 0, s>>>(S, C.p, C.nhc, h->kelvin, nfree);
+            h->launches++;
+        }
         if (constrain != 2 && h->thermostat == 1 && h->andersen_step > 0 && (istep % h->andersen_step) == 0) {
             sp_andersen<<<gel, 256, 0, s>>>(A);                               // 16
-            sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(dev, ntraj);
+            sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(C.event, ntraj);
             h->launches += 2;
         }
         if (constrain <= 0) {                                                 // 19
@@ -508,24 +593,120 @@ static int verlet_split(crcl_handle h, int ntraj, int nsteps, int istep0, int co
             sp_transrot_apply<<<rblocks * ntraj, 128, 0, s>>>(A, mt, dsums);
             h->launches += 3;
         }
+        if (C.xi_sum && constrain >= 0) {
+            sp_accum_xi<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.xi_real, C.xi_sum, C.xi_sum2);
+            h->launches++;
+        }
+        if (C.theta) {
+            sp_theta<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.xi_real, C.theta + (size_t)(st - 1) * ntraj);
+            h->launches++;
+        }
+        CK(cudaGetLastError());
+    }
+    // child steps only evaluate the value of xi; leave dxi as verlet.f90:1049-1050 would
+    if (constrain == 2 && nsteps > 0 && C.dxi) {
+        sp_calc_xi_kernel<<<tb, 64, 0, s>>>(h->mechd, S, dcen, 2, 0);
+        h->launches++;
         CK(cudaGetLastError());
     }
     return CRCL_OK;
 }
 
-// mdinit on the split path (bias_mode 0 only): forces of all beads + Andersen draw
-static int mdinit_split(crcl_handle h, int ntraj, int bias_mode, double* dq, double* dp, double* dg,
-                        const uint32_t* dtid, uint32_t* dev)
+// mdinit on the split path (mdinit.f90:40-172): forces of all beads, centroid, umbrella (bias_mode 1:
+// xi and dxi in the recrossing form; 2: bias applied), Andersen draw, NHC reset
+static int mdinit_split(crcl_handle h, const SplitCall& C, int bias_mode)
 {
-    if (bias_mode != 0) return fail(h, CRCL_ENOSUP, "split path: mdinit bias_mode 1/2 not implemented yet");
-    if (h->thermostat == 2) return fail(h, CRCL_ENOSUP, "split path: Nose-Hoover chain not implemented yet");
+    if (bias_mode && !h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
     int rc;
     if ((rc = ensure_split_tables(h))) return rc;
-    const int na = h->natoms, nb = h->nbeads;
-    const size_t per = (size_t)nb * 3 * na;
-    double* dV;
-    if ((rc = scratch(h, 9, (size_t)ntraj * nb, &dV))) return rc;
-    if ((rc = split_forces(h, ntraj * nb, dq, dg, dV))) return rc;
+    const int na = h->natoms, nb = h->nbeads, nc = 3 * na, ntraj = C.ntraj;
+    const size_t per = (size_t)nb * nc;
+    double *dV, *dcen;
+    if ((rc = scratch(h, 8, (size_t)ntraj * nc, &dcen)) || (rc = scratch(h, 9, (size_t)ntraj * nb, &dV))) return rc;
+    if ((rc = split_forces(h, ntraj * nb, C.q, C.g, dV))) return rc;
+    cudaStream_t s = h->stream;
+    const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
+    if (bias_mode) {
+        SpTraj S{};
+        if ((rc = split_traj_scratch(h, C, S))) return rc;
+        sp_centroid<<<(unsigned)(((size_t)ntraj * nc + 255) / 256), 256, 0, s>>>(ntraj, na, nb, C.q, dcen);
+        if (bias_mode == 1) {
+            sp_calc_xi_kernel<<<(ntraj + 63) / 64, 64, 0, s>>>(h->mechd, S, dcen, 2, 0);
+            h->launches += 2;
+        } else {
+            sp_calc_xi_kernel<<<(ntraj + 63) / 64, 64, 0, s>>>(h->mechd, S, dcen, 1, 1);
+            sp_add_bias<<<gel, 256, 0, s>>>(S, C.g);
+            h->launches += 3;
+        }
+    }
+    SplitArgs A{};
+    A.ntraj = ntraj;
+    A.natoms = na;
+    A.nbeads = nb;
+    A.beta = h->beta;
+    A.mass = h->d_mass;
+    A.at_move = h->d_atmove;
+    A.p = C.p;
+    A.seed = h->seed;
+    A.traj_id = C.tid;
+    A.event = C.event;
+    sp_andersen<<<gel, 256, 0, s>>>(A);
+    sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(C.event, ntraj);
+    h->launches += 2;
+    if (h->thermostat == 2 && C.nhc) {
+        sp_nhc_init<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.nhc, h->kelvin, h->nose_q, nfree_of(h));
+        h->launches++;
+    }
+    CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
+// recrossing children on the split path (recross.f90:515-628 / recross_serial.f90:172-229): the same
+// sequence as recross_kernel, composed from the split kernels
+static int recross_split(crcl_handle h, const double* d_q_parents, int nparent, int pair0, int npairs, int child_evol,
+                         double xi_ideal, double* d_kappa_num, double* d_kappa_denom, int* d_status)
+{
+    if (!h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    int rc;
+    if ((rc = ensure_split_tables(h)) || (rc = ensure_fker(h))) return rc;
+    const int ntraj = 2 * npairs, na = h->natoms, nb = h->nbeads, nc = 3 * na;
+    if (ntraj == 0) {
+        CK(cudaMemsetAsync(d_kappa_num, 0, (size_t)child_evol * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(d_kappa_denom, 0, sizeof(double), h->stream));
+        return CRCL_OK;
+    }
+    const size_t per = (size_t)nb * nc, n = per * ntraj;
+    double *dq, *dp, *dg, *ddxi, *dep, *dw, *dcen, *dV;
+    unsigned char* dth;
+    int* dst;
+    uint32_t* dtid;
+    if ((rc = scratch(h, 22, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
+        (rc = scratch(h, 3, (size_t)ntraj * nc, &ddxi)) || (rc = scratch(h, 23, (size_t)ntraj * 2, &dep)) ||
+        (rc = scratch(h, 6, (size_t)ntraj * 2, &dtid)) ||
+        (rc = scratch(h, 24, (size_t)ntraj * (child_evol > 0 ? child_evol : 1), &dth)) ||
+        (rc = scratch(h, 25, (size_t)ntraj * 2 + 2, &dw)) || (rc = scratch(h, 26, (size_t)ntraj + 1, &dst)) ||
+        (rc = scratch(h, 8, (size_t)ntraj * nc, &dcen)) || (rc = scratch(h, 9, (size_t)ntraj * nb, &dV)))
+        return rc;
+    cudaStream_t s = h->stream;
+    int* status = d_status ? d_status : dst;
+    CK(cudaMemsetAsync(status, 0, ntraj * sizeof(int), s));
+    SplitCall C;
+    C.ntraj = ntraj;
+    C.q = dq;
+    C.p = dp;
+    C.g = dg;
+    C.dxi = ddxi;
+    C.epot = dep;
+    C.xi_real = dep + ntraj;
+    C.status = status;
+    C.tid = dtid;
+    C.event = dtid + ntraj;
+    C.xi_ideal_s = xi_ideal;
+    C.theta = dth;
+    SpTraj S{};
+    if ((rc = split_traj_scratch(h, C, S))) return rc;
+    const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
+    sp_recross_init<<<gel, 256, 0, s>>>(ntraj, na, nb, nparent, pair0, d_q_parents, dq, dtid, dtid + ntraj);
     SplitArgs A{};
     A.ntraj = ntraj;
     A.natoms = na;
@@ -536,11 +717,27 @@ static int mdinit_split(crcl_handle h, int ntraj, int bias_mode, double* dq, dou
     A.p = dp;
     A.seed = h->seed;
     A.traj_id = dtid;
-    A.event = dev;
-    const dim3 gel((unsigned)(((per + 255) / 256) * ntraj));
-    sp_andersen<<<gel, 256, 0, h->stream>>>(A);
-    sp_bump_event<<<(ntraj + 127) / 128, 128, 0, h->stream>>>(dev, ntraj);
-    h->launches += 2;
+    A.event = dtid + ntraj;
+    sp_andersen<<<gel, 256, 0, s>>>(A);                       // the draw of recross_serial.f90:151
+    sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(dtid + ntraj, ntraj);
+    sp_flip_odd<<<gel, 256, 0, s>>>(ntraj, per, dp);           // child 2: p = -p_save (:160)
+    sp_centroid<<<(unsigned)(((size_t)ntraj * nc + 255) / 256), 256, 0, s>>>(ntraj, na, nb, dq, dcen);
+    sp_calc_xi_kernel<<<(ntraj + 63) / 64, 64, 0, s>>>(h->mechd, S, dcen, 2, 0);   // :163-164
+    h->launches += 6;
+    if ((rc = split_forces(h, ntraj * nb, dq, dg, dV))) return rc;                  // :165-169
+    sp_recross_weights<<<ntraj, 256, 0, s>>>(S, dp, dw, dw + ntraj);                // :170-190
+    h->launches++;
+    CK(cudaGetLastError());
+    const int th_save = h->thermostat, as_save = h->andersen_step;
+    h->thermostat = 0;                                          // no thermostat for the children (:131-135)
+    h->andersen_step = 0;
+    rc = verlet_split(h, C, child_evol, 0, 2);
+    h->thermostat = th_save;
+    h->andersen_step = as_save;
+    if (rc) return rc;
+    reduce_kappa_kernel<<<child_evol + 1, 256, 0, s>>>(dth, dw, dw + ntraj, ntraj, child_evol, d_kappa_num,
+                                                       d_kappa_denom);
+    h->launches++;
     CK(cudaGetLastError());
     return CRCL_OK;
 }
@@ -982,9 +1179,21 @@ int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
             CK(cudaMemcpyAsync(dtid, ids.data(), ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
         }
-        if ((rc = verlet_split(h, ntraj, nsteps, istep0, constrain, xi_ideal ? dxid : nullptr,
-                               xi_ideal ? 0.0 : 0.0, dq, dp, dg, dep, dxr, dst, dtid, dev)))
-            return rc;
+        SplitCall C;
+        C.ntraj = ntraj;
+        C.q = dq;
+        C.p = dp;
+        C.g = dg;
+        C.dxi = ddxi;
+        C.epot = dep;
+        C.xi_real = dxr;
+        C.nhc = dnhc;
+        C.status = dst;
+        C.tid = dtid;
+        C.event = dev;
+        C.xi_ideal = xi_ideal ? dxid : nullptr;
+        C.k_force = k_force ? dkf : nullptr;
+        if ((rc = verlet_split(h, C, nsteps, istep0, constrain))) return rc;
     } else if ((rc = launch_traj(h, K_VERLET, A)))
         return rc;
     CK(cudaMemcpyAsync(q, dq, n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1046,7 +1255,24 @@ int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double* xi_ideal,
             CK(cudaMemcpyAsync(dtid, ids.data(), ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
             CK(cudaStreamSynchronize(s));
         }
-        if ((rc = mdinit_split(h, ntraj, bias_mode, dq, dp, dg, dtid, dev))) return rc;
+        SplitCall C;
+        C.ntraj = ntraj;
+        C.q = dq;
+        C.p = dp;
+        C.g = dg;
+        C.dxi = ddxi;
+        C.epot = dep;
+        C.xi_real = dep + ntraj;
+        C.nhc = dnhc;
+        C.tid = dtid;
+        C.event = dev;
+        C.xi_ideal = xi_ideal ? dxid : nullptr;
+        C.k_force = k_force ? dkf : nullptr;
+        int* dst0;
+        if ((rc = scratch(h, 5, (size_t)ntraj, &dst0))) return rc;
+        CK(cudaMemsetAsync(dst0, 0, ntraj * sizeof(int), s));
+        C.status = dst0;
+        if ((rc = mdinit_split(h, C, bias_mode))) return rc;
     } else if ((rc = launch_traj(h, K_MDINIT, A, bias_mode)))
         return rc;
     CK(cudaMemcpyAsync(p, dp, n * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1061,7 +1287,7 @@ int crcl_calc_xi(crcl_handle h, int ncoord, const double* coords, const double* 
                  double* xi, double* dxi, double* hams)
 {
     if (!h || !coords || !xi || !dxi || ncoord < 0 || (mode != 1 && mode != 2)) return CRCL_EINVAL;
-    if (!h->mech.valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+    if (!h->mech.valid && !h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
     if (ncoord == 0) return CRCL_OK;
     CK(cudaSetDevice(h->device));
     const size_t n = (size_t)ncoord * h->natoms * 3;
@@ -1086,7 +1312,25 @@ int crcl_calc_xi(crcl_handle h, int ncoord, const double* coords, const double* 
     case 6: calc_xi_kernel<6><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
     case 7: calc_xi_kernel<7><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
     case 8: calc_xi_kernel<8><<<grid, tpb, 0, s>>>(A, ncoord, dc, dx + ncoord, mode, dx, dd, hp); break;
-    default: return fail(h, CRCL_ENOSUP, "calc_xi: natoms must be 3..8 on the in-register path");
+    default: {
+        // any number of atoms: the split path's Hessian-free evaluation (split_xi.cuh)
+        if (!h->mechd_valid) return fail(h, CRCL_ESTATE, "crcl_set_mechanism has not been called");
+        if ((rc = ensure_split_tables(h))) return rc;
+        SpTraj S{};
+        double* dw;
+        if ((rc = scratch(h, 17, (size_t)ncoord * SPX_NWORK * 3 * h->natoms, &dw))) return rc;
+        S.ntraj = ncoord;
+        S.natoms = h->natoms;
+        S.nbeads = 1;
+        S.beta = h->beta;
+        S.mass = h->d_mass;
+        S.xi_ideal = dx + ncoord;
+        S.xi_real = dx;
+        S.dxi = dd;
+        S.hams = dh;
+        S.work = dw;
+        sp_calc_xi_kernel<<<grid, tpb, 0, s>>>(h->mechd, S, dc, mode, (hams && mode == 1) ? 1 : 0);
+    }
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -1112,6 +1356,8 @@ int crcl_recross_children_dev(crcl_handle h, const double* d_q_parents, int npar
     unsigned char* dth;
     double* dw;
     int* dst;
+    if (use_split(h)) return recross_split(h, d_q_parents, nparent, pair0, npairs, child_evol, xi_ideal, d_kappa_num,
+                                           d_kappa_denom, d_status);
     if ((rc = scratch(h, 8, (size_t)ntraj * (child_evol > 0 ? child_evol : 1), &dth)) ||
         (rc = scratch(h, 9, (size_t)ntraj * 2 + 2, &dw)) || (rc = scratch(h, 10, (size_t)ntraj + 1, &dst)))
         return rc;
@@ -1189,8 +1435,8 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     if ((rc = scratch(h, 0, n, &dq)) || (rc = scratch(h, 1, n, &dg)) || (rc = scratch(h, 2, n, &dp)) ||
         (rc = scratch(h, 3, nd, &ddxi)) || (rc = scratch(h, 4, (size_t)ntot * 4, &dep)) ||
         (rc = scratch(h, 5, (size_t)ntot, &dst)) || (rc = scratch(h, 6, (size_t)ntot * 2, &dev)) ||
-        (rc = scratch(h, 7, (size_t)ntot * 8, &dnhc)) || (rc = scratch(h, 8, (size_t)ntot * 2, &dwin)) ||
-        (rc = scratch(h, 9, (size_t)ntot * h->nbeads, &dv)))
+        (rc = scratch(h, 7, (size_t)ntot * 8, &dnhc)) || (rc = scratch(h, 20, (size_t)ntot * 2, &dwin)) ||
+        (rc = scratch(h, 21, (size_t)ntot * h->nbeads, &dv)))
         return rc;
     cudaStream_t s = h->stream;
     // every trajectory starts from its window's equilibrated structure (calc_rate.f90:1383-1387)
@@ -1208,6 +1454,34 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     CK(cudaMemsetAsync(dev, 0, ntot * 2 * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(dst, 0, ntot * sizeof(int), s));
     CK(cudaMemsetAsync(dep, 0, ntot * 4 * sizeof(double), s));
+    if (use_split(h)) {
+        std::vector<uint32_t> ids(ntot);
+        for (int t = 0; t < ntot; t++) ids[t] = traj_id0 + (uint32_t)t;
+        uint32_t* dtid;
+        if ((rc = scratch(h, 27, (size_t)ntot, &dtid))) return rc;
+        CK(cudaMemcpyAsync(dtid, ids.data(), ntot * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        SplitCall C;
+        C.ntraj = ntot;
+        C.q = dq;
+        C.p = dp;
+        C.g = dg;
+        C.dxi = ddxi;
+        C.epot = dep;
+        C.xi_real = dep + ntot;
+        C.nhc = dnhc;
+        C.status = dst;
+        C.tid = dtid;
+        C.event = dev;
+        C.xi_ideal = dwin;
+        C.k_force = dwin + ntot;
+        if ((rc = mdinit_split(h, C, 2))) return rc;
+        if (equi_steps > 0 && (rc = verlet_split(h, C, equi_steps, 0, constrain))) return rc;
+        if ((rc = crcl_egrad_dev(h, h->pes, dq, h->natoms, ntot * h->nbeads, dv, dg, nullptr))) return rc;
+        C.xi_sum = dep + 2 * ntot;
+        C.xi_sum2 = dep + 3 * ntot;
+        if ((rc = verlet_split(h, C, sample_steps, 0, constrain))) return rc;
+    } else {
     TrajArgs A;
     fill_args(h, A);
     A.ntraj = ntot;
@@ -1236,6 +1510,7 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     A.xi_sum = dep + 2 * ntot;
     A.xi_sum2 = dep + 3 * ntot;
     if ((rc = launch_traj(h, K_VERLET, A))) return rc;
+    }
     std::vector<double> sums(2 * (size_t)ntot);
     CK(cudaMemcpyAsync(sums.data(), dep + 2 * ntot, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
     std::vector<int> st(ntot);

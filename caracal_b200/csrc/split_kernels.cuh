@@ -44,15 +44,17 @@ template <int NB>
 __global__ void __launch_bounds__(128) sp_kick_freerp_reg(const SplitArgs A)
 {
     const int nc = 3 * A.natoms;
-    const int tiles = gridDim.x / A.ntraj;   // 1-D grid: block = traj * tiles + tile
-    const int t = blockIdx.x / tiles;
-    const int c = (blockIdx.x - t * tiles) * blockDim.x + threadIdx.x;
-    if (c >= nc) return;
+    // flat index over (trajectory, component): CTAs stay full for small systems, and the threads of a
+    // warp still read contiguous runs (a whole trajectory's components are adjacent)
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)A.ntraj * nc) return;
+    const size_t t = gid / nc;
+    const int c = (int)(gid - t * nc);
     const int atom = c / 3;
     const double m = A.mass[atom];
     const bool mv = A.at_move[atom] != 0;
     const double h = 0.5 * A.dt;
-    const size_t base = (size_t)t * NB * nc + c;
+    const size_t base = t * NB * nc + c;
     double p[NB], q[NB];
 #pragma unroll
     for (int b = 0; b < NB; b++) {
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(128) sp_kick_freerp_reg(const SplitArgs A)
         A.q[i] = q[b];
         cs += q[b];
     }
-    A.cen[(size_t)t * nc + c] = cs / NB;
+    A.cen[t * nc + c] = cs / NB;
 }
 
 // ---- same, any bead count: the thread's column of beads lives in shared memory -------------------
@@ -121,15 +123,15 @@ __global__ void sp_kick_freerp_smem(const SplitArgs A)
     for (int i = threadIdx.x; i < 3 * NB; i += BD) fk[i] = A.fker[i];
     __syncthreads();
     const int nc = 3 * A.natoms;
-    const int tiles = gridDim.x / A.ntraj;
-    const int t = blockIdx.x / tiles;
-    const int c = (blockIdx.x - t * tiles) * BD + threadIdx.x;
-    if (c >= nc) return;
+    const size_t gid = (size_t)blockIdx.x * BD + threadIdx.x;   // flat (trajectory, component) index
+    if (gid >= (size_t)A.ntraj * nc) return;
+    const size_t t = gid / nc;
+    const int c = (int)(gid - t * nc);
     const int atom = c / 3, x = threadIdx.x;
     const double m = A.mass[atom], im = 1.0 / m;
     const bool mv = A.at_move[atom] != 0;
     const double h = 0.5 * A.dt;
-    const size_t base = (size_t)t * NB * nc + c;
+    const size_t base = t * NB * nc + c;
     for (int b = 0; b < NB; b++) {
         const size_t i = base + (size_t)b * nc;
         const double pv = A.p[i] - h * A.g[i];
@@ -169,7 +171,7 @@ __global__ void sp_kick_freerp_smem(const SplitArgs A)
             cs += qn;
         }
     }
-    A.cen[(size_t)t * nc + c] = cs / NB;
+    A.cen[t * nc + c] = cs / NB;
 }
 
 // ---- second half kick + mask + NaN/Inf scan (verlet.f90:1060-1073, 1256-1275) --------------------

@@ -155,3 +155,107 @@ def test_free_ring_polymer_at_box_shape(gpu):
         assert np.abs(q[0, a] - q[0, nb - a]).max() < 1e-11
     ms, best, gbs = g.bench_propagate(64, reps=3)
     assert ms > 0 and gbs > 100.0
+
+
+# ---- umbrella bias, SHAKE / RATTLE, Nose-Hoover chain, work units on the split path ------------------
+def run_split_biased(gpu, oracle, name, nb, constrain, thermo, astep, bias_mode, ntraj=2, nsteps=100, xi0=0.97,
+                     kf=0.05 * 300.0, nose_q=100.0):
+    rng = np.random.default_rng(nb * 100 + constrain + 3 * thermo)
+    g, _ = C.make_pair(name, nb)
+    g.set_path(gpu.PATH_SPLIT)
+    g.set_seed(C.SEED)
+    g.set_thermostat(thermo, astep, 300.0, nose_q)
+    q0 = np.array([C.ring_polymer(name, nb, rng, 0.02) for _ in range(ntraj)])
+    tid = np.arange(40, 40 + ntraj, dtype=np.uint32)
+    xi = np.full(ntraj, xi0) + 0.01 * np.arange(ntraj)
+    k = np.full(ntraj, kf)
+    q = q0.copy()
+    p, d, dxi, ev = g.mdinit(q, bias_mode, xi_ideal=xi, k_force=k, traj_id=tid)
+    ep, xr, st = g.verlet(q, p, d, nsteps=nsteps, constrain=constrain, xi_ideal=xi, k_force=k, dxi=dxi, traj_id=tid,
+                          event=ev)
+    for t in range(ntraj):
+        _, o = C.make_pair(name, nb)
+        o.q[:] = q0[t]
+        o.set_rng(C.SEED, int(tid[t]))
+        o.set_thermostat(thermo, astep, 300.0, nose_q)
+        o.set_kforce(kf)
+        o.mdinit(float(xi[t]), bias_mode)
+        for i in range(1, nsteps + 1):
+            epo, xro, sto = o.verlet(i, float(xi[t]), constrain)
+            assert sto == 0
+        assert st[t] == 0
+        assert np.abs(q[t] - o.q).max() < C.TOL_QP
+        assert (np.abs(p[t] - o.p) / np.abs(o.p).max()).max() < C.TOL_QP
+        assert abs(ep[t] - epo) < 1e-9 * max(1.0, abs(epo))
+        assert abs(xr[t] - xro) < 1e-9
+        assert np.abs(dxi[t] - o.dxi).max() < 1e-9
+        if constrain == 1:
+            # xi_real is evaluated on the centroid of step 6, before SHAKE moved the beads (verlet.f90:649,
+            # 1047); on the constrained structure itself xi vanishes
+            assert abs(g.calc_xi(q[t].mean(axis=0), float(xi[t]), 2)[0][0]) < 1e-7
+
+
+@pytest.mark.parametrize("name,nb,constrain,thermo,astep,bias_mode", [
+    ("h3", 8, 0, 1, 9, 2),        # umbrella window dynamics (bias + hams force + transrot)
+    ("ch4h", 16, 0, 1, 11, 2),
+    ("h3", 8, 3, 1, 9, 2),        # same without the rotation removal
+    ("h3", 8, 1, 1, 9, 2),        # constrained parent: SHAKE / RATTLE
+    ("ch4h", 4, 1, 1, 7, 2),
+    ("oh3", 6, 1, 0, 0, 1),       # non-power-of-two beads, mdinit bias_mode 1
+    ("h3", 8, -1, 2, 0, 0),       # Nose-Hoover chain
+    ("h3", 12, 0, 2, 0, 2),       # NHC + umbrella
+])
+def test_split_biased_modes_match_oracle(gpu, oracle, name, nb, constrain, thermo, astep, bias_mode):
+    run_split_biased(gpu, oracle, name, nb, constrain, thermo, astep, bias_mode)
+
+
+def test_split_work_units_equal_fused(gpu):
+    """crcl_recross_children and crcl_umbrella_windows through the split kernels give what the fused
+    trajectory kernels give (same RNG streams, same operation sequence)."""
+    name, nb = "ch4h", 8
+    rng = np.random.default_rng(4)
+    qp = np.array([C.ring_polymer(name, nb, rng, 0.01) for _ in range(3)])
+    q0 = np.array([C.ring_polymer(name, nb, rng, 0.02) for _ in range(3)])
+    xi0, kf = np.array([0.9, 0.97, 1.01]), np.full(3, 15.0)
+    res = []
+    for path in (gpu.PATH_FUSED, gpu.PATH_SPLIT):
+        g, _ = C.make_pair(name, nb)
+        g.set_path(path)
+        g.set_seed(C.SEED)
+        num, den, st = g.recross_children(qp, 6, 60, 0.985, pair0=5)
+        g.set_thermostat(1, 7, 300.0)
+        avg, var, st2 = g.umbrella_windows(q0, xi0, kf, 2, 30, 50, traj_id0=9)
+        assert (st == 0).all() and (st2 == 0).all()
+        res.append((num, den, avg, var))
+    (n1, d1, a1, v1), (n2, d2, a2, v2) = res
+    assert abs(d1 - d2) < 1e-10 * abs(d1) and np.abs(n1 - n2).max() < 1e-10 * abs(d1)
+    assert np.abs(a1 - a2).max() < 1e-9 and np.abs(v1 - v2).max() < 1e-10
+
+
+def test_rate_pipeline_on_a_qmdff_surface_runs_on_the_split_path(gpu):
+    """configuration 4 shape in miniature: a DG-EVB surface (two QMDFFs + coupling, 9 atoms) through
+    mdinit / umbrella windows / constrained parent / recrossing children on the split path."""
+    from tests.qmdff_synth import make_dgevb
+    T1, T2, E = make_dgevb(seed=5, mode=3, npoints=4)
+    nb = 4
+    mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O"}[int(z)]) for z in T1["at"]])
+    g = gpu.RPMD(gpu.PES_DGEVB, nb, mass, C.beta_calc_rate(300.0), C.dt_au(0.2))
+    g.set_qmdff(T1)
+    g.set_qmdff(T2, second=True)
+    g.set_dgevb(E)
+    g.set_seed(C.SEED)
+    ts = T1["xyz"]
+    # "reaction": O-H bond (3-9) breaks, H moves to C1 (1-9); fragments: the rest / the hydrogen
+    g.set_mechanism(C.Mechanism([[1, 9]], [[3, 9]], [[1, 2, 3, 4, 5, 6, 7, 8], [9]], 12.0, ts))
+    g.set_thermostat(1, 5, 300.0)
+    q0 = np.repeat(ts[None, None], nb, axis=1) + np.random.default_rng(1).normal(0, 0.01, (1, nb) + ts.shape)
+    # the reference structure is the "TS" of this mechanism: s1 = 0 there, xi = 1 in the umbrella form
+    avg, var, st = g.umbrella_windows(np.repeat(q0, 2, axis=0), np.array([1.0, 0.99]), np.array([15.0, 15.0]), 2, 20, 40)
+    assert (st == 0).all() and np.isfinite(avg).all() and (var >= 0).all() and np.abs(avg - 1.0).max() < 0.1
+    q = q0.copy()
+    p, d, dxi, ev = g.mdinit(q, 2, xi_ideal=1.0, k_force=15.0)
+    ep, xr, st = g.verlet(q, p, d, nsteps=30, constrain=1, xi_ideal=1.0, k_force=15.0, dxi=dxi, event=ev)
+    assert st[0] == 0 and abs(g.calc_xi(q[0].mean(axis=0), 1.0, 2)[0][0]) < 1e-7   # generic-size calc_xi
+    g.set_thermostat(0, 0, 300.0)
+    num, den, stc = g.recross_children(q, 4, 25, 1.0)
+    assert (stc == 0).all() and den > 0 and np.isfinite(num).all() and abs(num[0] / den - 1.0) < 0.5
