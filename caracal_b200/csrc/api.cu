@@ -1142,6 +1142,7 @@ int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
     dkf = dep + 3 * ntraj;
     dev = dtid + ntraj;
     cudaStream_t s = h->stream;
+    CK(cudaMemsetAsync(dep, 0, (size_t)ntraj * 2 * sizeof(double), s));   // epot, xi_real: 0 unless the mode sets them
     CK(cudaMemcpyAsync(dq, q, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(dp, p, n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(dg, derivs, n * sizeof(double), cudaMemcpyHostToDevice, s));

@@ -136,7 +136,10 @@ struct SmemLayout {
     // bead stride of the {p,q}[c][b] staging in double2 units: +1 when several lanes of a bead
     // address different components of the same bead slot (keeps them in different banks)
     static constexpr int NBP = (LANES > 1 && NB > 1) ? NB + 1 : NB;
-    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC;  // {p,q}[c][b] interleaved, cen, dxi, add, ham
+    // staging of the bead-symmetrised {p,q} sums s_b = x_b + x_{N-b}, b = 0..N/2 (reference transform, NB <= 32)
+    static constexpr int NH = NB / 2 + 1;
+    static constexpr int SYM_STAGE = (NB > 1 && NB <= 32) ? 2 * NC * NH : 0;
+    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE;  // {p,q}[c][b], cen, dxi, add, ham, sym
     // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
     // load_fker), otherwise the three circulant kernels f[N]
     static constexpr bool HTAB = (NB > 1 && NB <= 32);
@@ -172,6 +175,8 @@ struct Traj {
     double* dxi;    // shared dxi [NC]
     double* add;    // shared k (xi - xi0) dxi, the umbrella force added to every bead [NC]
     double* ham;    // shared hams force (umbrella.f90:144-174) [NC]
+    double2* sq;    // shared bead-symmetrised sums {p,q}[c][b], b = 0..N/2 (free_rp, reference transform)
+    bool want_epot; // false: forces() skips the all-reduce of the bead energies (recrossing children)
     const double* fk;
     double xi_ideal, k_force, xi_real, epot;
     double vnh[4], qnh[4];
@@ -188,6 +193,8 @@ struct Traj {
         dxi = cen + NC;
         add = dxi + NC;
         ham = add + NC;
+        sq = reinterpret_cast<double2*>(ham + NC);
+        want_epot = true;
         status = 0;
         xi_real = 0.0;
         epot = 0.0;
@@ -255,19 +262,49 @@ struct Traj {
 #pragma unroll
             for (int k = 0; k < NO; k++) cp[k] = aq[k] = bp[k] = cq[k] = 0.0;
             const double* hk = fk + G.bead;
-#pragma unroll 2
-            for (int b = 0; b < NB; b++) {
-                const double fc = hk[b * NB], fa = hk[NB * NB + b * NB], fb = hk[2 * NB * NB + b * NB];
-#pragma unroll
-                for (int k = 0; k < NO; k++) {
-                    const double2 u = pq[ob[k] + b];
-                    cp[k] = fma(fc, u.x, cp[k]);
-                    aq[k] = fma(fa, u.y, aq[k]);
-                    bp[k] = fma(fb, u.x, bp[k]);
-                    cq[k] = fma(fc, u.y, cq[k]);
+            if (A.symmetrize) {
+                // H[b][a] = H[N-b][a]: out_a = sum_{b=0}^{N/2} H[b][a] s_b with s_b = x_b + x_{N-b}
+                // (s_0 = x_0, s_{N/2} = x_{N/2}) staged once per trajectory -- N/2+1 terms instead of N
+                constexpr int NH = SmemLayout<NAT, NB, L>::NH;
+                for (int i = G.tig; i < NC * NH; i += Grp::T) {
+                    const int c = i / NH, b = i - c * NH;
+                    double2 u = pq[c * NBP + b];
+                    if (b > 0 && 2 * b < NB) {
+                        const double2 w = pq[c * NBP + NB - b];
+                        u.x += w.x;
+                        u.y += w.y;
+                    }
+                    sq[i] = u;
                 }
+                G.sync();
+#pragma unroll 3
+                for (int b = 0; b < NH; b++) {
+                    const double fc = hk[b * NB], fa = hk[NB * NB + b * NB], fb = hk[2 * NB * NB + b * NB];
+#pragma unroll
+                    for (int k = 0; k < NO; k++) {
+                        const double2 u = sq[(ob[k] / NBP) * NH + b];
+                        cp[k] = fma(fc, u.x, cp[k]);
+                        aq[k] = fma(fa, u.y, aq[k]);
+                        bp[k] = fma(fb, u.x, bp[k]);
+                        cq[k] = fma(fc, u.y, cq[k]);
+                    }
+                }
+                // every read of pq happened before the barrier above: no second barrier before the write
+            } else {
+#pragma unroll 2
+                for (int b = 0; b < NB; b++) {
+                    const double fc = hk[b * NB], fa = hk[NB * NB + b * NB], fb = hk[2 * NB * NB + b * NB];
+#pragma unroll
+                    for (int k = 0; k < NO; k++) {
+                        const double2 u = pq[ob[k] + b];
+                        cp[k] = fma(fc, u.x, cp[k]);
+                        aq[k] = fma(fa, u.y, aq[k]);
+                        bp[k] = fma(fb, u.x, bp[k]);
+                        cq[k] = fma(fc, u.y, cq[k]);
+                    }
+                }
+                G.sync();
             }
-            G.sync();
 #pragma unroll
             for (int k = 0; k < NO; k++)
                 if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
@@ -318,7 +355,7 @@ struct Traj {
         const double2* base = pq + G.bead;
         const int w = PES::eval_coop([&](int c) { return base[c * NBP].y; }, G.lane, G.mask, e, g);
         if (w) status |= CRCL_TRAJ_PESWARN;
-        return G.sum(e);
+        return want_epot ? G.sum(e) : 0.0;
     }
     // umbrella.f90:66-175 on the shared centroid.  mode 0: bias + hams force added to the forces,
     // xi in umbrella form; mode 1: xi in recrossing form, nothing added.
@@ -817,6 +854,7 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
     Traj<PES, NB> T(A, G, smem);
+    T.want_epot = false;   // the child body never reads epot (recross_serial.f90:192-199)
     const int pair = A.pair0 + (traj >> 1);
     const double sign = (traj & 1) ? -1.0 : 1.0;
     const size_t poff = ((size_t)(pair % A.nparent) * NB + G.bead) * NC;
