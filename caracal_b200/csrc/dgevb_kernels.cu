@@ -12,8 +12,7 @@
 // table sets (the second with the *_two semantics: never periodic, list terms only, Coulomb
 // without cut-off; ff_eg_two.f90, ff_nonb_two.f90, ff_hb_two.f90).
 //
-// One CTA (64 threads) per image: thread l owns internal coordinate l for sum_dv12 (the
-// O(points * nat6^3) part of mode 3), B entries are spread over all threads.
+// One warp per image (see dgevb_mix_kernel).
 #include <cmath>
 #include <vector>
 #include "dgevb.cuh"
@@ -91,112 +90,84 @@ __device__ __forceinline__ void ic_load(const DgevbDev& P, const double* x, int 
     }
 }
 
-__global__ void __launch_bounds__(64) dgevb_mix_kernel(const DgevbDev P, int natoms, const double* __restrict__ xyz,
-                                                      const double* __restrict__ V1, const double* __restrict__ G1,
-                                                      const double* __restrict__ V2, const double* __restrict__ G2,
-                                                      double* __restrict__ V, double* __restrict__ G)
+// packed index (1-based, as sum_dv12.f90 counts `inc`) of coefficient (k,m), k <= m, of the upper triangle
+__device__ __forceinline__ int tri(int k, int m, int n) { return (k - 1) * (2 * n - k + 2) / 2 + (m - k + 1); }
+
+// One WARP per image.  Per Gaussian the mode-3 gradient of sum_dv12.f90:124-176 is evaluated in its
+// closed form -- with Q = 1/2 q^T B q (B the symmetric matrix of the second-order coefficients),
+//   g_l = -expo [ 1/2 a^2 b0 d q_l + a q_l (b1.q) - b1_l + a q_l Q - (B q)_l ],
+// O(nat6^2) per point instead of the reference's O(nat6^3) loop nest over (l,k,m); the two differ by
+// rounding only.  Lane l owns g_V12(l) and row l of B q; the numeric Wilson B entries are spread over
+// all lanes.
+__global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int natoms, int nimg,
+                                                       const double* __restrict__ xyz, const double* __restrict__ V1,
+                                                       const double* __restrict__ G1, const double* __restrict__ V2,
+                                                       const double* __restrict__ G2, double* __restrict__ V,
+                                                       double* __restrict__ G)
 {
     extern __shared__ double sm[];
-    const int nat6 = P.nat6, n3 = 3 * natoms, img = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-    double* internal = sm;           // [nat6]
-    double* gq = internal + nat6;    // [nat6]
-    double* qq = gq + nat6;          // [nat6]
-    double* gv = qq + nat6;          // [3n]
-    double* red = gv + n3;           // [2]: d_p, V12
+    const int nat6 = P.nat6, n3 = 3 * natoms, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int img = blockIdx.x * (blockDim.x >> 5) + wib;
+    if (img >= nimg) return;                                  // whole warps leave together
+    const int per = 4 * nat6 + n3;
+    double* internal = sm + (size_t)wib * per;   // [nat6]
+    double* gq = internal + nat6;                // [nat6]
+    double* qq = gq + nat6;                      // [nat6]
+    double* Bq = qq + nat6;                      // [nat6]
+    double* gv = Bq + nat6;                      // [3n]
     const double* x = xyz + (size_t)img * n3;
-    for (int i = tid; i < nat6; i += nth) {
+    for (int i = lane; i < nat6; i += 32) {
         int ty, nact, at[4];
         double p[4][3];
         ic_load(P, x, i, ty, nact, at, p);
         internal[i] = ic_eval(ty, p);
         gq[i] = 0.0;
     }
-    for (int c = tid; c < n3; c += nth) gv[c] = 0.0;
-    if (tid == 0) red[1] = 0.0;
-    __syncthreads();
+    for (int c = lane; c < n3; c += 32) gv[c] = 0.0;
+    __syncwarp();
     const int mode = P.mode;
     const int block = 1 + nat6 + nat6 * (nat6 + 1) / 2, first = 1 + nat6;
     const double* b = P.b_vec - 1;   // 1-based as in the reference
+    double V12 = 0.0;
     for (int j = 1; j <= P.npoints; j++) {
         const double* pt = P.point_int + (size_t)(j - 1) * nat6;
         const double al = P.alph[j - 1];
-        for (int k = tid; k < nat6; k += nth) qq[k] = internal[k] - pt[k];
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int k = 0; k < nat6; k++) s += qq[k] * qq[k];
-            red[0] = s;
-        }
-        __syncthreads();
-        const double d_p = red[0];
+        for (int k = lane; k < nat6; k += 32) qq[k] = internal[k] - pt[k];
+        __syncwarp();
+        double d_p = 0.0;
+        for (int k = 0; k < nat6; k++) d_p += qq[k] * qq[k];   // every lane: same order as dot_product
         const double expo = exp(-0.5 * al * d_p);
         if (!(expo < P.g_thres)) {
-            // ---- sum_v12: thread 0 (O(nat6^2) at most) ----
-            if (tid == 0) {
-                double v = 0.0;
-                if (mode == 1) {
-                    v = b[j] * (1 + 0.5 * al * d_p) * expo;
-                } else if (mode == 2) {
-                    v = b[(j - 1) * nat6 + j] * (1 + 0.5 * al * d_p) * expo;
-                    for (int k = 1; k <= nat6; k++) v += b[j + (j - 1) * nat6 + k] * qq[k - 1] * expo;
-                } else {
-                    v = b[(j - 1) * (block - 1) + j] * (1 + 0.5 * al * d_p) * expo;
-                    for (int k = 1; k <= nat6; k++) v += b[k + (j - 1) * block + 1] * qq[k - 1] * expo;
-                    int inc = 0;
-                    for (int k = 1; k <= nat6; k++)
-                        for (int l = k; l <= nat6; l++) {
-                            inc++;
-                            const double bb = b[inc + (j - 1) * block + first];
-                            v += (k == l) ? bb * 0.5 * qq[k - 1] * qq[l - 1] * expo : bb * qq[k - 1] * qq[l - 1] * expo;
-                        }
+            // offsets of the coefficient blocks of point j (sum_v12.f90 / sum_dv12.f90 index arithmetic)
+            const double b0 = (mode == 1) ? b[j] : (mode == 2 ? b[(j - 1) * nat6 + j] : b[(j - 1) * (block - 1) + j]);
+            const double* b1 = (mode == 2) ? b + j + (j - 1) * nat6 : b + (j - 1) * block + 1;   // b1[k], k = 1..nat6
+            const double* b2 = b + (j - 1) * block + first;                                      // b2[inc]
+            double b1q = 0.0, Q = 0.0;
+            if (mode >= 2)
+                for (int k = 1; k <= nat6; k++) b1q += b1[k] * qq[k - 1];
+            if (mode == 3) {
+                for (int l = lane + 1; l <= nat6; l += 32) {
+                    double acc = 0.0;
+                    for (int m = 1; m <= nat6; m++) acc += b2[(l <= m) ? tri(l, m, nat6) : tri(m, l, nat6)] * qq[m - 1];
+                    Bq[l - 1] = acc;
                 }
-                red[1] += v;
+                __syncwarp();
+                for (int k = 0; k < nat6; k++) Q += qq[k] * Bq[k];
+                Q *= 0.5;
             }
-            // ---- sum_dv12: thread l owns g_V12(l) ----
-            for (int l = tid + 1; l <= nat6; l += nth) {
-                double a = 0.0;
+            V12 += (b0 * (1 + 0.5 * al * d_p) + b1q + Q) * expo;
+            for (int l = lane + 1; l <= nat6; l += 32) {
                 const double ql = qq[l - 1];
-                if (mode == 1) {
-                    a -= 0.5 * al * al * b[j] * d_p * ql * expo;
-                } else if (mode == 2) {
-                    a -= 0.5 * al * al * b[(j - 1) * nat6 + j] * d_p * ql * expo;
-                    for (int k = 1; k <= nat6; k++) {
-                        const double bb = b[j + (j - 1) * nat6 + k];
-                        a -= (k == l) ? bb * (al * qq[k - 1] * ql - 1.0) * expo : bb * al * ql * qq[k - 1] * expo;
-                    }
-                } else {
-                    a -= 0.5 * al * al * b[(j - 1) * (block - 1) + j] * d_p * ql * expo;
-                    for (int k = 1; k <= nat6; k++) {
-                        const double bb = b[k + (j - 1) * block + 1];
-                        a -= (k == l) ? bb * (al * qq[k - 1] * ql - 1.0) * expo : bb * al * ql * qq[k - 1] * expo;
-                    }
-                    int inc = 0;
-                    for (int k = 1; k <= nat6; k++) {
-                        const double qk = qq[k - 1];
-                        for (int m = k; m <= nat6; m++) {
-                            inc++;
-                            const double bb = b[inc + (j - 1) * block + first], qm = qq[m - 1];
-                            if (m == k) {
-                                a -= (l == k) ? 0.5 * bb * qk * (al * qk * qk - 2.0) * expo
-                                              : 0.5 * bb * al * qk * qk * ql * expo;
-                            } else {
-                                if (l == k)
-                                    a -= bb * qm * (al * qk * qk - 1.0) * expo;
-                                else if (l == m)
-                                    a -= bb * qk * (al * qm * qm - 1.0) * expo;
-                                else
-                                    a -= bb * al * qm * qk * ql * expo;
-                            }
-                        }
-                    }
-                }
-                gq[l - 1] += a;
+                double a = 0.5 * al * al * b0 * d_p * ql;
+                if (mode >= 2) a += al * ql * b1q - b1[l];
+                if (mode == 3) a += al * ql * Q - Bq[l - 1];
+                gq[l - 1] -= a * expo;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     // ---- numeric Wilson B (calc_wilson.f90:114-178) contracted with gq: gv = B^T gq ----
-    for (int w = tid; w < nat6 * 12; w += nth) {
+    for (int w = lane; w < nat6 * 12; w += 32) {
         const int i = w / 12, slot = w - 12 * i;
         int ty, nact, at[4];
         double p[4][3];
@@ -213,20 +184,20 @@ __global__ void __launch_bounds__(64) dgevb_mix_kernel(const DgevbDev P, int nat
             atomicAdd(&gv[3 * at[a] + m], (hi - lo) / (2 * shift) * gq[i]);
         }
     }
-    __syncthreads();
+    __syncwarp();
     const double e1 = V1[img], e2 = V2[img];
-    const double ediff = e1 - e2, V12 = red[1], off4 = 4.0 * V12;
+    const double ediff = e1 - e2, off4 = 4.0 * V12;
     const bool unset = (ediff * ediff + off4 < 0.0);
     const double root2 = unset ? 1.0 : sqrt(ediff * ediff + off4);
     const double* g1 = G1 + (size_t)img * n3;
     const double* g2 = G2 + (size_t)img * n3;
     double* g = G + (size_t)img * n3;
-    for (int c = tid; c < n3; c += nth) {
+    for (int c = lane; c < n3; c += 32) {
         const double deldiscr = ediff * (g1[c] - g2[c]) + 2.0 * gv[c];
         const double delsqrt = unset ? 0.0 : deldiscr / root2;
         g[c] = 0.5 * (g1[c] + g2[c] - delsqrt);
     }
-    if (tid == 0) {
+    if (lane == 0) {
         const double root = (0.5 * ediff) * (0.5 * ediff) + V12;
         V[img] = (root <= 0) ? 0.5 * (e1 + e2) : 0.5 * (e1 + e2) - sqrt(root);
     }
@@ -236,12 +207,15 @@ cudaError_t dgevb_mix(const DgevbDev* P, int natoms, const double* xyz, int nimg
                       const double* V2, const double* G2, double* V, double* G, cudaStream_t s)
 {
     if (nimg <= 0) return cudaSuccess;
-    const size_t smem = sizeof(double) * (3 * (size_t)P->nat6 + 3 * (size_t)natoms + 2);
+    const size_t per = sizeof(double) * (4 * (size_t)P->nat6 + 3 * (size_t)natoms);
+    int wpb = 4;                                  // warps (images) per CTA
+    while (wpb > 1 && per * wpb > 96 * 1024) wpb >>= 1;
+    const size_t smem = per * wpb;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(dgevb_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dgevb_mix_kernel<<<nimg, 64, smem, s>>>(*P, natoms, xyz, V1, G1, V2, G2, V, G);
+    dgevb_mix_kernel<<<(nimg + wpb - 1) / wpb, 32 * wpb, smem, s>>>(*P, natoms, nimg, xyz, V1, G1, V2, G2, V, G);
     return cudaGetLastError();
 }
 

@@ -81,15 +81,41 @@ __device__ __forceinline__ double block_sum_to(double v, double* dst)
     return v;
 }
 
+// (image, term) of this thread for the list kernels.  Two launch shapes: grid (term tiles, images) with
+// a block reduction of the energy per image (large lists), or -- when a list is shorter than a CTA
+// (gas-phase molecules x thousands of ring-polymer beads) -- one flat index over (image, term) so
+// that CTAs stay full; the energy then goes out with one atomic per term.
+__device__ __forceinline__ void term_index(int nterm, int nimg, int flat, int& t, int& img)
+{
+    if (flat) {
+        const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const size_t im = gidx / (size_t)nterm;
+        t = (im < (size_t)nimg) ? (int)(gidx - im * nterm) : nterm;
+        img = (im < (size_t)nimg) ? (int)im : 0;
+    } else {
+        t = blockIdx.x * blockDim.x + threadIdx.x;
+        img = blockIdx.y;
+    }
+}
+__device__ __forceinline__ void term_energy(double e, double* dst, int flat)
+{
+    if (flat) {
+        if (e != 0.0) atomicAdd(dst, e);
+    } else {
+        block_sum_to(e, dst);
+    }
+}
+
 // ---- bonded terms: term index t in [0, nbond+nangl+ntors) -------------------------------------------
 __global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const double* __restrict__ xyz,
-                                                        double* __restrict__ V, double* __restrict__ g)
+                                                        double* __restrict__ V, double* __restrict__ g, int nimg,
+                                                        int flat)
 {
     constexpr double PI = 3.1415926535897932384626433832795029, PI2 = 6.28318530717958623199592693708837,
                      SPI = 1.77245385090551599275151910313925;
     const int nterm = D.nbond + D.nangl + D.ntors;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int img = blockIdx.y;
+    int t, img;
+    term_index(nterm, nimg, flat, t, img);
     const double* x = xyz + (size_t)img * 3 * D.n;
     double* gi = g + (size_t)img * 3 * D.n;
     double e = 0.0;
@@ -334,7 +360,7 @@ __global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const 
         add3(gi, k, gC);
         add3(gi, l, gD);
     }
-    block_sum_to(e, &V[img]);
+    term_energy(e, &V[img], flat);
 }
 
 // dispersion + repulsion of one pair (ff_nonb.f90:120-160): returns the energy, dr = gradient factor
@@ -379,10 +405,10 @@ __device__ __forceinline__ double coul_pair(const QmdffDev& D, double qq, double
 }
 
 __global__ void __launch_bounds__(128) qm_nci_kernel(const QmdffDev D, const double* __restrict__ xyz,
-                                                     double* __restrict__ V, double* __restrict__ g)
+                                                     double* __restrict__ V, double* __restrict__ g, int nimg, int flat)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int img = blockIdx.y;
+    int k, img;
+    term_index(D.nnci, nimg, flat, k, img);
     const double* x = xyz + (size_t)img * 3 * D.n;
     double* gi = g + (size_t)img * 3 * D.n;
     double e = 0.0;
@@ -409,7 +435,7 @@ __global__ void __launch_bounds__(128) qm_nci_kernel(const QmdffDev D, const dou
         v[2] = -v[2];
         add3(gi, i2, v);
     }
-    block_sum_to(e, &V[img]);
+    term_energy(e, &V[img], flat);
 }
 
 // Per image: xs[img][c][n], an FP64 SoA copy of the positions (exact pair evaluation, coalesced
@@ -717,9 +743,11 @@ __device__ __forceinline__ double dist_dev(const QmdffDev& D, const double* x, i
 }
 
 __global__ void __launch_bounds__(128) qm_hb_list_kernel(const QmdffDev D, const double* __restrict__ xyz,
-                                                         double* __restrict__ V, double* __restrict__ g)
+                                                         double* __restrict__ V, double* __restrict__ g, int nimg,
+                                                         int flat)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.y;
+    int k, img;
+    term_index(D.nhb, nimg, flat, k, img);
     const double* x = xyz + (size_t)img * 3 * D.n;
     double* gi = g + (size_t)img * 3 * D.n;
     double e = 0.0;
@@ -732,7 +760,7 @@ __global__ void __launch_bounds__(128) qm_hb_list_kernel(const QmdffDev D, const
                 e = eabxag_dev(D, x, gi, A, B, H, D.vhb[2 * k]);
         }
     }
-    block_sum_to(e, &V[img]);
+    term_energy(e, &V[img], flat);
 }
 
 // ff_hb.f90:90-274: every (donor bond, atom j of another molecule) pair.  One WARP per (image,
@@ -855,13 +883,19 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         double* V = d_V + i0;
         const int nterm = D->nbond + D->nangl + D->ntors;
         if (nterm > 0) {
-            qm_bonded_kernel<<<dim3((nterm + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+            if (nterm < 96)   // short lists: flat (image, term) index
+                qm_bonded_kernel<<<(unsigned)(((size_t)nterm * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 1);
+            else
+                qm_bonded_kernel<<<dim3((nterm + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g, ni, 0);
             nl++;
         }
         // early returns: ff_nonb.f90:74 (nnci <= 1 and nmols == 0), ff_nonb_two.f90:48 (nnci_two <= 1)
         if (!(D->nnci <= 1 && (D->is_two || D->nmols == 0))) {
             if (D->nnci > 0) {
-                qm_nci_kernel<<<dim3((D->nnci + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                if (D->nnci < 96)
+                    qm_nci_kernel<<<(unsigned)(((size_t)D->nnci * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 1);
+                else
+                    qm_nci_kernel<<<dim3((D->nnci + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g, ni, 0);
                 nl++;
             }
             if (D->nmols > 1) {
@@ -872,7 +906,10 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         }
         if (D->use_hb && !(D->nhb < 1 && D->nmols == 0)) {   // ff_hb.f90:49 early return
             if (D->nhb > 0) {
-                qm_hb_list_kernel<<<dim3((D->nhb + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g);
+                if (D->nhb < 96)
+                    qm_hb_list_kernel<<<(unsigned)(((size_t)D->nhb * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 1);
+                else
+                    qm_hb_list_kernel<<<dim3((D->nhb + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g, ni, 0);
                 nl++;
             }
             if (D->nmols > 1 && D->ndonor > 0) {
