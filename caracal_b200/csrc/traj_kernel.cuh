@@ -217,6 +217,9 @@ struct Traj {
     __device__ __forceinline__ double& Q(int c) { return pq[c * NBP + G.bead].y; }
     __device__ __forceinline__ double& Pk(int k) { return pq[ob[k] + G.bead].x; }
     __device__ __forceinline__ double& Qk(int k) { return pq[ob[k] + G.bead].y; }
+    // threads that hold a valid xi_real after a child step (umbrella mode 2), and the one that reports it
+    __device__ __forceinline__ bool xi_thread() const { return Grp::WARP || (int)threadIdx.x >= Grp::T - 32; }
+    __device__ __forceinline__ bool xi_writer() const { return Grp::WARP ? G.tig == 0 : (int)threadIdx.x == Grp::T - 32; }
     __device__ __forceinline__ bool own(int k) const { return oc[k] >= 0; }
     __device__ __forceinline__ bool mov(int k) const { return (mv >> k) & 1u; }
 
@@ -364,9 +367,10 @@ struct Traj {
         if (mode == 2) {
             // child trajectory: only the value of xi is ever used (recross.f90:597-602); read the
             // shared centroid in place
-            // shared centroid in place.  Only thread 0 of the trajectory consumes xi_real (theta,
-            // xi sums), so for CTA-wide groups the other warps skip the evaluation.
-            if (Grp::WARP || threadIdx.x < 32) xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
+            // shared centroid in place.  One thread of the trajectory consumes xi_real (theta), so for
+            // CTA-wide groups only the LAST warp evaluates it -- the first one has just done the
+            // centroid sums, which keeps the warps of a CTA in step at the next barrier.
+            if (xi_thread()) xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
             return;
         }
         double x[NC], d[NC];
@@ -637,7 +641,10 @@ struct Traj {
     }
 
     // one verlet step (SURVEY.md 3.5 numbering)
-    __device__ __forceinline__ void step(int istep)
+    // check_nan: run the NaN / Inf scan of verlet.f90:1256-1275 in this step.  A NaN coordinate never
+    // recovers, so the callers scan every 16th and the last step of a launch: same status, one
+    // CTA-wide vote less per step.
+    __device__ __forceinline__ void step(int istep, bool check_nan = true)
     {
         const int c = A.constrain, th = A.thermostat;
         if (c != 2 && th == 2) nhc();                          // 1
@@ -663,14 +670,16 @@ struct Traj {
         if (c != 2 && th == 2) nhc();                          // 15
         if (c != 2 && th == 1 && A.andersen_step > 0 && (istep % A.andersen_step) == 0)
             andersen();                                        // 16
-        int nan = 0;                                           // 18
+        if (check_nan) {                                       // 18
+            int nan = 0;
 #pragma unroll
-        for (int k = 0; k < NO; k++)
-            if (oc[k] >= 0) {
-                const double v = Q(oc[k]);
-                nan |= (v != v) || (v > 1.79769313486231570815e308);
-            }
-        if (G.any(nan)) status |= CRCL_TRAJ_NAN;
+            for (int k = 0; k < NO; k++)
+                if (oc[k] >= 0) {
+                    const double v = Q(oc[k]);
+                    nan |= (v != v) || (v > 1.79769313486231570815e308);
+                }
+            if (G.any(nan)) status |= CRCL_TRAJ_NAN;
+        }
         if (c <= 0)                                            // 19
             if (transrot()) status |= CRCL_TRAJ_SINGULAR;
     }
@@ -753,7 +762,7 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
     for (int s = 1; s <= A.nsteps; s++) {
         // a failed trajectory is frozen (the reference aborts or restarts it)
         if (T.status & (CRCL_TRAJ_SHAKE_FAIL | CRCL_TRAJ_NAN | CRCL_TRAJ_SINGULAR)) break;
-        T.step(A.istep0 + s);
+        T.step(A.istep0 + s, (s & 15) == 0 || s == A.nsteps);
         sx += T.xi_real;
         sx2 += T.xi_real * T.xi_real;
     }
@@ -884,8 +893,8 @@ recross_kernel(const __grid_constant__ TrajArgs A)
         A.denom_part[traj] = (vs > 0) ? w : 0.0;
     }
     for (int l = 1; l <= A.nsteps; l++) {
-        if (!(T.status & CRCL_TRAJ_NAN)) T.step(l);
-        if (G.tig == 0) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
+        if (!(T.status & CRCL_TRAJ_NAN)) T.step(l, (l & 15) == 0 || l == A.nsteps);
+        if (T.xi_writer()) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
     }
     if (G.tig == 0 && A.status) A.status[traj] = T.status;
 }

@@ -158,6 +158,10 @@ def test_unsupported_bead_count_is_an_error(gpu):
     g.set_path(gpu.PATH_AUTO)
     p, d, dxi, ev = g.mdinit(q)
     assert np.isfinite(p).all() and np.abs(p).max() > 0
-    # stages the split path does not cover yet are refused, not silently skipped
-    with pytest.raises(gpu.CaracalGpuError, match="ENOSUP"):
+    # the split path covers the constrained modes too, but needs the MECHA tables like the fused one
+    with pytest.raises(gpu.CaracalGpuError, match="ESTATE"):
         g.verlet(q, p, d, nsteps=1, constrain=1, xi_ideal=0.9, k_force=1.0)
+    g.set_mechanism(C.mechanism("h3"))
+    p, d, dxi, ev = g.mdinit(q, 2, xi_ideal=0.98, k_force=15.0)
+    ep, xr, st = g.verlet(q, p, d, nsteps=3, constrain=1, xi_ideal=0.98, k_force=15.0, dxi=dxi, event=ev)
+    assert st[0] == 0 and np.isfinite(q).all()
