@@ -476,6 +476,7 @@ struct InterTables {
         zab[QM_MAXTYPE][QM_MAXTYPE];
 };
 
+template <bool PER>
 __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const double* __restrict__ xs,
                                                        const float4* __restrict__ xf, double* __restrict__ V,
                                                        double* __restrict__ g)
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const d
         const double xi = Xx[i], yi = Xy[i], zi = Xz[i], qi = D.q[i];
         const int ti = D.type[i], mi = D.molnum[i];
         const double* c6row = D.c6 + (size_t)i * n;
-        const bool per = D.periodic != 0;
+        constexpr bool per = PER;
         const double Lx = D.box[0], Ly = D.box[1], Lz = D.box[2];
         const double rc = fmax(D.vdw_cut, D.coul_cut);
         double gx = 0.0, gy = 0.0, gz = 0.0;
@@ -569,18 +570,20 @@ __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const d
         const float iLx = 1.0f / Lxf, iLy = 1.0f / Lyf, iLz = 1.0f / Lzf;
         const float rc2f = (float)(rc * rc) * QM_PREFILTER_SLACK;
         const float mif = __int_as_float(mi);
-        auto near = [&](const float4& c) {   // other molecule and inside the larger cut-off (with slack)
+        // other molecule and inside the larger cut-off (with slack); branch-free
+        auto near = [&](const float4& c) {
             bool ok = __float_as_int(c.w) != mi;
             if (per) {
                 const float dx = image_f(fi.x - c.x, Lxf, iLx), dy = image_f(fi.y - c.y, Lyf, iLy),
                             dz = image_f(fi.z - c.z, Lzf, iLz);
-                ok = ok && (dx * dx + dy * dy + dz * dz <= rc2f);
+                ok = ok & (dx * dx + dy * dy + dz * dz <= rc2f);
             }
             return ok;
         };
+        const unsigned lt = (1u << lane) - 1u;
         auto push = [&](bool ok, int j) {
             const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) qu[qn + __popc(m & ((1u << lane) - 1u))] = j;
+            if (ok) qu[qn + __popc(m & lt)] = j;
             qn += __popc(m);
             __syncwarp();
             if (qn >= 32) {
@@ -590,27 +593,40 @@ __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const d
             }
         };
         const float4 self = make_float4(0.f, 0.f, 0.f, mif);   // fails the molecule test
-        // first chunk (j > i) and last chunk (j < n) are guarded, the chunks in between are not
+        // first chunk (j > i) and last chunk (j < n) are guarded, the chunks in between are not;
+        // the main loop walks a pointer, two chunks per trip (the loads of the next two are in flight
+        // while the current two are tested / flushed)
         const int jstart = (i + 1) & ~31, jfull = n & ~31;
         {
             const int j = jstart + lane;
             const float4 c = (j > i && j < n) ? F[j] : self;
             push(near(c), j);
         }
-        int j0 = jstart + 32;
-        if (j0 < jfull) {
-            float4 c = F[j0 + lane];
-            for (; j0 < jfull; j0 += 32) {
-                const int jn = j0 + 32 + lane;
-                const float4 nx = (jn < n) ? F[jn] : self;   // also prefetches the guarded last chunk
-                push(near(c), j0 + lane);
-                c = nx;
+        int j = jstart + 32 + lane;                      // this lane's atom in the current chunk
+        const float4* pf = F + j;
+        const int jend2 = jfull - 64;                     // last j0 for which two full chunks remain
+        if (jstart + 32 <= jend2) {
+            float4 c0 = pf[0], c1 = pf[32];
+            for (;;) {
+                const bool more = (j - lane) + 64 <= jend2;
+                float4 n0 = self, n1 = self;
+                if (more) {
+                    n0 = pf[64];
+                    n1 = pf[96];
+                }
+                push(near(c0), j);
+                push(near(c1), j + 32);
+                j += 64;
+                pf += 64;
+                if (!more) break;
+                c0 = n0;
+                c1 = n1;
             }
-            if (j0 < n) push(near(c), j0 + lane);            // c holds the (guarded) last partial chunk
-        } else if (j0 < n) {
-            const int j = j0 + lane;
-            const float4 c = (j < n) ? F[j] : self;
-            push(near(c), j);
+        }
+        for (int j0 = j - lane; j0 < n; j0 += 32) {      // at most one full chunk and the partial one
+            const int jj = j0 + lane;
+            const float4 c = (jj < n) ? F[jj] : self;
+            push(near(c), jj);
         }
         if (lane < qn) pair(qu[lane]);
         for (int o = 16; o > 0; o >>= 1) {
@@ -899,8 +915,12 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
                 nl++;
             }
             if (D->nmols > 1) {
-                qm_inter_kernel<<<dim3((D->n + 3) / 4, ni), 128, 0, s>>>(*D, D->xs + (size_t)i0 * 3 * D->n,
-                                                                         D->xf + (size_t)i0 * D->n, V, g);
+                if (D->periodic)
+                    qm_inter_kernel<true><<<dim3((D->n + 3) / 4, ni), 128, 0, s>>>(*D, D->xs + (size_t)i0 * 3 * D->n,
+                                                                                   D->xf + (size_t)i0 * D->n, V, g);
+                else
+                    qm_inter_kernel<false><<<dim3((D->n + 3) / 4, ni), 128, 0, s>>>(*D, D->xs + (size_t)i0 * 3 * D->n,
+                                                                                    D->xf + (size_t)i0 * D->n, V, g);
                 nl++;
             }
         }
