@@ -138,7 +138,7 @@ struct SmemLayout {
     static constexpr int NBP = (LANES > 1 && NB > 1) ? NB + 1 : NB;
     // staging of the bead-symmetrised {p,q} sums s_b = x_b + x_{N-b}, b = 0..N/2 (reference transform, NB <= 32)
     static constexpr int NH = NB / 2 + 1;
-    static constexpr int SYM_STAGE = (NB > 1 && NB <= 32) ? 2 * NC * NH : 0;
+    static constexpr int SYM_STAGE = (NB > 1) ? 2 * NC * NH : 0;
     static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE;  // {p,q}[c][b], cen, dxi, add, ham, sym
     // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
     // load_fker), otherwise the three circulant kernels f[N]
@@ -313,25 +313,43 @@ struct Traj {
                 if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
             return;
         }
-        if (A.symmetrize) {
-            // (I+J)/2: x_a <- (x_a + x_{N-a})/2, what T.T does
-            const int rb = (NB - G.bead) & (NB - 1);
-            double2 t[NO];
-#pragma unroll
-            for (int k = 0; k < NO; k++) {
-                const double2 u = pq[ob[k] + G.bead], w = pq[ob[k] + rb];
-                t[k].x = 0.5 * (u.x + w.x);
-                t[k].y = 0.5 * (u.y + w.y);
-            }
-            G.sync();
-#pragma unroll
-            for (int k = 0; k < NO; k++)
-                if (own(k)) pq[ob[k] + G.bead] = t[k];
-            G.sync();
-        }
         double cp[NO], aq[NO], bp[NO], cq[NO];
 #pragma unroll
         for (int k = 0; k < NO; k++) cp[k] = aq[k] = bp[k] = cq[k] = 0.0;
+        if (A.symmetrize) {
+            // NB > 32: no room for the dense tables; same half-sum form with the coefficients
+            // (f(a-b) + f(a+b))/2 built on the fly from the circulant kernels
+            constexpr int NH = SmemLayout<NAT, NB, L>::NH;
+            for (int i = G.tig; i < NC * NH; i += Grp::T) {
+                const int c = i / NH, b = i - c * NH;
+                double2 u = pq[c * NBP + b];
+                if (b > 0 && 2 * b < NB) {
+                    const double2 w = pq[c * NBP + NB - b];
+                    u.x += w.x;
+                    u.y += w.y;
+                }
+                sq[i] = u;
+            }
+            G.sync();
+#pragma unroll 2
+            for (int b = 0; b < NH; b++) {
+                const int i1 = (G.bead - b) & (NB - 1), i2 = (G.bead + b) & (NB - 1);
+                const double fc = 0.5 * (fk[i1] + fk[i2]), fa = 0.5 * (fk[NB + i1] + fk[NB + i2]),
+                             fb = 0.5 * (fk[2 * NB + i1] + fk[2 * NB + i2]);
+#pragma unroll
+                for (int k = 0; k < NO; k++) {
+                    const double2 u = sq[(ob[k] / NBP) * NH + b];
+                    cp[k] = fma(fc, u.x, cp[k]);
+                    aq[k] = fma(fa, u.y, aq[k]);
+                    bp[k] = fma(fb, u.x, bp[k]);
+                    cq[k] = fma(fc, u.y, cq[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NO; k++)
+                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
+            return;
+        }
 #pragma unroll 2
         for (int b = 0; b < NB; b++) {
             const int idx = (G.bead - b) & (NB - 1);
@@ -700,10 +718,17 @@ struct Traj {
 #ifndef CRCL_MINB_L4
 #define CRCL_MINB_L4 7
 #endif
+// one-lane surfaces in single-warp CTAs (H3 / OH3 with <= 32 beads): 12 CTAs per SM (168 registers) instead
+// of the 236 the compiler takes unbounded: +19 % on a 65536-replica H + H2 batch, -3 % at 1024 replicas
+// (profiles/r1k_*; the kernel is bound by instruction-cache misses at 2 warps per scheduler)
+#ifndef CRCL_MINB_L1
+#define CRCL_MINB_L1 12
+#endif
 template <class PES, int NB>
 struct LaunchCfg {
     static constexpr int TPB = Group<NB, PES::LANES>::TPB;
-    static constexpr int MINB = (PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : 1;
+    // one-lane surfaces (H3, OH3): CRCL_MINB_L1 resident CTAs requested when a CTA is a single warp
+    static constexpr int MINB = (PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : ((TPB == 32) ? CRCL_MINB_L1 : 1);
 };
 
 // Free ring-polymer kernels into shared memory.  NB <= 32: the dense tables
