@@ -356,6 +356,10 @@ class RPMD:
     def measure_fp64_tflops(self, iters=8192):
         return float(self._lib.crcl_measure_fp64_tflops(self._h, int(iters)))
 
+    def measure_dmma_tflops(self, iters=8192):
+        """FP64 tensor-core (mma.sync.m8n8k4.f64) throughput of this device"""
+        return float(self._lib.crcl_measure_dmma_tflops(self._h, int(iters)))
+
 
 # ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
 _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"]}

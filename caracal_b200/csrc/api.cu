@@ -214,6 +214,25 @@ __global__ void fp64_peak_kernel(double* out, int iters, double a, double b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// DMMA throughput probe: mma.sync.m8n8k4.f64 (the only FP64 tensor-core shape; tcgen05 has no FP64 kind),
+// 4 independent accumulator pairs per warp.  2*8*8*4 = 512 flops per instruction per warp.
+__global__ void dmma_peak_kernel(double* out, int iters, double a, double b)
+{
+    double c0[2] = {0.0, 0.0}, c1[2] = {1.0, 0.0}, c2[2] = {0.0, 1.0}, c3[2] = {1.0, 1.0};
+    const double av = a + threadIdx.x * 1e-9, bv = b;
+    for (int i = 0; i < iters; i++) {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[0]), "+d"(c0[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c1[0]), "+d"(c1[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c2[0]), "+d"(c2[1]) : "d"(av), "d"(bv));
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c3[0]), "+d"(c3[1]) : "d"(av), "d"(bv));
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+}
+
 namespace crcl {
 // kappa_num[l] = sum_t weight[t]*theta[l][t], kappa_denom = sum_t denom_part[t]; fixed
 // summation order -> bit-reproducible for a given (pair0, npairs) regardless of launch shape.
@@ -1649,6 +1668,32 @@ double crcl_measure_fp64_tflops(crcl_handle h, int iters)
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev0, h->ev1);
         const double flops = 2.0 * 8.0 * (double)iters * grid * tpb;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    return best;
+}
+
+double crcl_measure_dmma_tflops(crcl_handle h, int iters)
+{
+    if (!h) return -1.0;
+    if (iters <= 0) iters = 4096;
+    cudaSetDevice(h->device);
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, h->device) != cudaSuccess) return -1.0;
+    const int tpb = 256, grid = pr.multiProcessorCount * 8;
+    double* d;
+    if (scratch(h, 11, (size_t)grid * tpb, &d)) return -1.0;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(h->ev0, h->stream);
+        dmma_peak_kernel<<<grid, tpb, 0, h->stream>>>(d, iters, 1.0000001, 1e-9);
+        cudaEventRecord(h->ev1, h->stream);
+        h->launches++;
+        if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+        const double flops = 4.0 * 512.0 * (double)iters * grid * (tpb / 32);
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;
     }

@@ -103,6 +103,7 @@ SIGNATURES = {
     "crcl_kernel_timings": (ctypes.c_int, [_H, c_double_p, ctypes.c_int]),
     "crcl_bench_propagate": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p]),
     "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
+    "crcl_measure_dmma_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
 }
 
 

@@ -78,9 +78,25 @@ def generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_
 
 
 def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, umbr_steps, traj_id0=1 << 20,
-                      max_retry=5, constrain=0):
+                      max_retry=5, constrain=0, shard=None, device="cpu"):
     """Phase 2: all windows x umbr_traj trajectories in one batch (crcl_umbrella_windows); returns the
-    window averages and variances of xi as statistics/bias_* hold them (calc_rate.f90:1690-1700)."""
+    window averages and variances of xi as statistics/bias_* hold them (calc_rate.f90:1690-1700).
+    shard = (rank, world): the windows are partitioned over the ranks (one GPU each) and the statistics
+    gathered with one all-reduce; RNG streams are keyed by the global window index, so the result does not
+    depend on the number of ranks."""
+    if shard is not None:
+        from .shard import umbrella_sharded
+        kf_all = np.broadcast_to(np.asarray(k_force, dtype=np.float64), (len(xi_wins),))
+        nerr_box = [0]
+
+        def compute(w0, cnt):
+            a, v, ne = umbrella_sampling(g, xi_wins[w0:w0 + cnt], struc_equi[w0:w0 + cnt], kf_all[w0:w0 + cnt],
+                                         umbr_traj, equi_steps, umbr_steps, traj_id0=traj_id0 + w0 * umbr_traj,
+                                         max_retry=max_retry, constrain=constrain)
+            nerr_box[0] = ne
+            return a, v
+        avg, var = umbrella_sharded(compute, len(xi_wins), shard[0], shard[1], device=device)
+        return avg, var, nerr_box[0]
     nwin = len(xi_wins)
     k_force = np.broadcast_to(np.asarray(k_force, dtype=np.float64), (nwin,)).copy()
     q0 = np.repeat(struc_equi[:, None], g.nbeads, axis=1)

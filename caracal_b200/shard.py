@@ -4,8 +4,9 @@ The reference parallelises only whole work units with an MPI master/worker schem
 (recross.f90:334-417: child +/- pairs; calc_rate.f90:1351-1376: umbrella windows) and ships
 results through files or point-to-point messages.  Here every rank takes a contiguous block of
 the global unit range -- units are independent, so the data path has no collective -- and the
-only exchange is the sum of the kappa(t) numerators and the denominator (child_evol+1 doubles),
-all-reduced with torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
+only exchanges are the sum of the kappa(t) numerators and the denominator (child_evol+1 doubles) and
+the gather of the window statistics of the umbrella phase (2 doubles per window), both all-reduced
+with torch.distributed (NCCL over NVLink on GPUs, gloo in the CPU tests).
 RNG streams are keyed by the GLOBAL pair index, so the reduced sums do not depend on the
 number of ranks beyond floating-point summation order.
 """
@@ -45,3 +46,23 @@ def recross_sharded(compute, total_pairs, child_evol, rank=None, world=None, dev
     t[child_evol] = float(den)
     reduce_sums(t, group)
     return t[:child_evol], float(t[child_evol])
+
+
+def umbrella_sharded(compute, nwin, rank=None, world=None, device="cpu", group=None):
+    """Umbrella windows partitioned over the ranks (the reference hands whole windows to MPI workers and
+    collects their statistics through files, calc_rate.f90:1351-1376,1690-1734).  compute(w0, count) ->
+    (average[count], variance[count]) for this rank's contiguous block of windows; every rank gets the
+    (average[nwin], variance[nwin]) of all windows back: each rank fills its slice of a zero vector and
+    the vectors are summed (2*nwin doubles, the only exchange of the umbrella phase)."""
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    start, count = shard_range(nwin, rank, world)
+    t = torch.zeros(2 * nwin, dtype=torch.float64, device=device)
+    if count > 0:
+        avg, var = compute(start, count)
+        t[start:start + count] = torch.as_tensor(avg, dtype=torch.float64)
+        t[nwin + start:nwin + start + count] = torch.as_tensor(var, dtype=torch.float64)
+    reduce_sums(t, group)
+    return t[:nwin].cpu().numpy(), t[nwin:].cpu().numpy()

@@ -261,6 +261,9 @@ int crcl_bench_propagate(crcl_handle h, int ntraj, int reps, double *ms_out);
 /* sustained FP64 FMA throughput of the device in TFLOP/s (DFMA microbenchmark, used as the
  * roofline denominator because MEASURED_PEAKS.json has no FP64 entry) */
 double crcl_measure_fp64_tflops(crcl_handle h, int iters);
+/* same for the FP64 tensor-core path (mma.sync.m8n8k4.f64): the evidence behind keeping the bead
+ * transform on the DFMA pipe */
+double crcl_measure_dmma_tflops(crcl_handle h, int iters);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-from caracal_b200.shard import recross_sharded, shard_range  # noqa: E402
+from caracal_b200.shard import recross_sharded, shard_range, umbrella_sharded  # noqa: E402
 
 
 def test_shard_range_covers_everything():
@@ -71,3 +71,42 @@ def test_two_rank_reduction_equals_single_process(tmp_path):
     num1, den1 = recross_sharded(_compute_factory(), NPAIRS, EVOL, 0, 1)
     assert abs(den1 - den2) < 1e-12 * abs(den1)
     assert (num1 - num2).abs().max().item() < 1e-12 * max(1.0, num1.abs().max().item())
+
+
+# ---- umbrella windows partitioned over two ranks (rate.umbrella_sampling(shard=...)) ------------------
+def _umbrella(shard):
+    from caracal_b200 import rate as R
+    from tests import common as C
+    from tests.oracle_handle import OracleRPMD
+    name, nb = "h3", 2
+    g = OracleRPMD(name, nb, C.masses(name), C.beta_calc_rate(300.0), C.dt_au(0.1))
+    g.set_mechanism(C.mechanism(name))
+    g.set_seed(C.SEED)
+    g.set_thermostat(1, 5, 300.0)
+    xi = np.array([0.95, 0.97, 0.99, 1.0, 1.01])
+    struc = np.array([C.ring_polymer(name, 1, np.random.default_rng(k), 0.0)[0] for k in range(5)])
+    return R.umbrella_sampling(g, xi, struc, 15.0, 2, 6, 12, shard=shard)
+
+
+def _worker_umb(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    avg, var, _ = _umbrella((rank, world))
+    if rank == 1:                                   # every rank holds the gathered statistics
+        torch.save((avg, var), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_umbrella_windows_sharded_over_two_ranks(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "umb.pt")
+    mp.spawn(_worker_umb, args=(2, port, out), nprocs=2, join=True)
+    avg2, var2 = torch.load(out, weights_only=False)
+    avg1, var1, _ = _umbrella(None)
+    assert np.abs(avg1 - avg2).max() < 1e-13 and np.abs(var1 - var2).max() < 1e-13
+    assert umbrella_sharded(lambda w0, c: (np.arange(w0, w0 + c), np.ones(c)), 4, 0, 1)[0].tolist() == [0, 1, 2, 3]
