@@ -7,7 +7,7 @@ mdinit / verlet / recross / umbrella work units on batches of ring polymers.
 """
 from .lib import (CaracalGpuError, LIB_PATH, PES_CH4H, PES_H3, PES_IDS, PES_OH3, TRANSFORM_EXACT,  # noqa: F401
                   TRANSFORM_REFERENCE, PATH_AUTO, PATH_FUSED, PATH_SPLIT, PES_HOSTCB, PES_QMDFF, PES_DGEVB, PES_NONE, load)
-from .api import (RPMD, Mechanism, atomic_mass_au, beta_calc_rate, beta_dynamic, dt_au, egrad, egrad_ch4h,  # noqa: F401
+from .api import (RPMD, Mechanism, UnimolMechanism, AtomShiftMechanism, atomic_mass_au, beta_calc_rate, beta_dynamic, dt_au, egrad, egrad_ch4h,  # noqa: F401
                   egrad_h3, egrad_oh3)
 
 

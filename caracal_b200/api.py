@@ -73,6 +73,29 @@ class Mechanism:
         self.break_ref = np.array([np.linalg.norm(ts[a - 1] - ts[b - 1]) for a, b in self.bond_break])
 
 
+class UnimolMechanism:
+    """MECHA{} of the unimolecular types CYCLOREVER / REARRANGE / DECOM_1BOND / ELIMINATION: bond lists plus
+    the TS and the reactant structures the reference lengths come from (bonds_ref.f90:39-109)."""
+    kind = "unimol"
+
+    def __init__(self, bond_form, bond_break, ts_struc, reac_struc):
+        self.bond_form = np.asarray(bond_form, dtype=np.int32).reshape(-1, 2)
+        self.bond_break = np.asarray(bond_break, dtype=np.int32).reshape(-1, 2)
+        ts, rs = _f64(ts_struc), _f64(reac_struc)
+        ln = lambda x, b: np.array([np.linalg.norm(x[a - 1] - x[c - 1]) for a, c in b])
+        self.form_ref, self.break_ref = ln(ts, self.bond_form), ln(ts, self.bond_break)
+        self.form_reac, self.break_reac = ln(rs, self.bond_form), ln(rs, self.bond_break)
+
+
+class AtomShiftMechanism:
+    """MECHA{ type atom_shift }: shift_atom (1-based), shift_coord 1..6, limits in bohr (calc_rate_read.f90:805-849)"""
+    kind = "atom_shift"
+
+    def __init__(self, shift_atom, shift_coord, shift_lo, shift_hi, shift2_lo=0.0, shift2_hi=0.0):
+        self.shift_atom, self.shift_coord = int(shift_atom), int(shift_coord)
+        self.shift_lo, self.shift_hi, self.shift2_lo, self.shift2_hi = map(float, (shift_lo, shift_hi, shift2_lo, shift2_hi))
+
+
 class RPMD:
     """One handle per process/GPU: the explicit form of the reference's module globals."""
 
@@ -203,6 +226,18 @@ class RPMD:
         return e, g
 
     def set_mechanism(self, m):
+        kind = getattr(m, "kind", "bimolec")
+        if kind == "unimol":
+            bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
+            bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)
+            self._ck(self._lib.crcl_set_mechanism_unimol(self._h, len(bf), _ip(bf), len(bb), _ip(bb), _dp(_f64(m.form_ref)),
+                                                         _dp(_f64(m.break_ref)), _dp(_f64(m.form_reac)),
+                                                         _dp(_f64(m.break_reac))), "crcl_set_mechanism_unimol")
+            return
+        if kind == "atom_shift":
+            self._ck(self._lib.crcl_set_mechanism_atom_shift(self._h, m.shift_atom, m.shift_coord, m.shift_lo, m.shift_hi,
+                                                             m.shift2_lo, m.shift2_hi), "crcl_set_mechanism_atom_shift")
+            return
         bf = np.ascontiguousarray(m.bond_form, dtype=np.int32)
         bb = np.ascontiguousarray(m.bond_break, dtype=np.int32)
         nr = np.array([len(r) for r in m.reactants], dtype=np.int32)

@@ -926,6 +926,102 @@ int crcl_set_mechanism(crcl_handle h, int form_num, const int* bond_form, int br
     return CRCL_OK;
 }
 
+// shared by the two entry points below: bond lists of the unimolecular mechanisms, no fragments
+static int set_bond_lists(crcl_handle h, int form_num, const int* bond_form, int break_num, const int* bond_break,
+                          const double* form_ref, const double* break_ref)
+{
+    if (form_num < 0 || break_num < 0 || form_num > 8 || break_num > 8)
+        return fail(h, CRCL_ENOSUP, "mechanism limits: <= 8 forming / breaking bonds");
+    if ((form_num > 0 && (!bond_form || !form_ref)) || (break_num > 0 && (!bond_break || !break_ref))) return CRCL_EINVAL;
+    MechDev& D = h->mechd;
+    D = MechDev();
+    D.form_num = form_num;
+    D.break_num = break_num;
+    for (int i = 0; i < form_num; i++) {
+        D.bf[i][0] = bond_form[2 * i] - 1;
+        D.bf[i][1] = bond_form[2 * i + 1] - 1;
+        D.fref[i] = form_ref[i];
+        if (D.bf[i][0] < 0 || D.bf[i][0] >= h->natoms || D.bf[i][1] < 0 || D.bf[i][1] >= h->natoms)
+            return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    }
+    for (int i = 0; i < break_num; i++) {
+        D.bb[i][0] = bond_break[2 * i] - 1;
+        D.bb[i][1] = bond_break[2 * i + 1] - 1;
+        D.bref[i] = break_ref[i];
+        if (D.bb[i][0] < 0 || D.bb[i][0] >= h->natoms || D.bb[i][1] < 0 || D.bb[i][1] >= h->natoms)
+            return fail(h, CRCL_EINVAL, "mechanism atom index out of range");
+    }
+    h->frag_h.assign(h->natoms, -1);
+    h->wfrag_h.assign(h->natoms, 0.0);
+    h->mech = Mech();
+    h->mech.form_num = form_num;
+    h->mech.break_num = break_num;
+    if (h->natoms <= XI_MAXAT && form_num <= XI_MAXBOND && break_num <= XI_MAXBOND) {
+        for (int i = 0; i < form_num; i++) {
+            h->mech.bf[i][0] = D.bf[i][0];
+            h->mech.bf[i][1] = D.bf[i][1];
+            h->mech.fref[i] = D.fref[i];
+        }
+        for (int i = 0; i < break_num; i++) {
+            h->mech.bb[i][0] = D.bb[i][0];
+            h->mech.bb[i][1] = D.bb[i][1];
+            h->mech.bref[i] = D.bref[i];
+        }
+        for (int a = 0; a < XI_MAXAT; a++) h->mech.frag[a] = -1;
+        h->mech.inv_form = form_num ? 1.0 / form_num : 0.0;
+        h->mech.inv_break = break_num ? 1.0 / break_num : 0.0;
+    }
+    return CRCL_OK;
+}
+
+int crcl_set_mechanism_unimol(crcl_handle h, int form_num, const int* bond_form, int break_num, const int* bond_break,
+                              const double* form_ref, const double* break_ref, const double* form_reac,
+                              const double* break_reac)
+{
+    if (!h) return CRCL_EINVAL;
+    if ((form_num > 0 && !form_reac) || (break_num > 0 && !break_reac) || form_num + break_num <= 0) return CRCL_EINVAL;
+    int rc = set_bond_lists(h, form_num, bond_form, break_num, bond_break, form_ref, break_ref);
+    if (rc) return rc;
+    MechDev& D = h->mechd;
+    D.type = 1;
+    for (int i = 0; i < form_num; i++) D.freac[i] = form_reac[i];
+    for (int i = 0; i < break_num; i++) D.breac[i] = break_reac[i];
+    h->mechd_valid = true;
+    CK(cudaSetDevice(h->device));
+    if ((rc = upload_mechd(h))) return rc;
+    if (h->natoms <= XI_MAXAT && form_num <= XI_MAXBOND && break_num <= XI_MAXBOND) {
+        mech_set_unimol(h->mech, form_reac, break_reac);
+        h->mech.valid = 1;
+    }
+    return CRCL_OK;
+}
+
+int crcl_set_mechanism_atom_shift(crcl_handle h, int shift_atom, int shift_coord, double shift_lo, double shift_hi,
+                                  double shift2_lo, double shift2_hi)
+{
+    if (!h) return CRCL_EINVAL;
+    int rc = set_bond_lists(h, 0, nullptr, 0, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    Mech tmp = Mech();
+    if (mech_set_atom_shift(tmp, h->natoms, shift_atom, shift_coord, shift_lo, shift_hi, shift2_lo, shift2_hi))
+        return fail(h, CRCL_EINVAL, "ATOM_SHIFT: atom must be 1..natoms and the coordinate code 1..6");
+    MechDev& D = h->mechd;
+    D.type = 2;
+    D.shift_atom = tmp.shift_atom;
+    D.shift_c1 = tmp.shift_c1;
+    D.shift_c2 = tmp.shift_c2;
+    D.shift_lo = shift_lo;
+    D.shift_hi = shift_hi;
+    D.shift2_lo = shift2_lo;
+    D.shift2_hi = shift2_hi;
+    h->mechd_valid = true;
+    CK(cudaSetDevice(h->device));
+    if ((rc = upload_mechd(h))) return rc;
+    if (h->natoms <= XI_MAXAT)
+        mech_set_atom_shift(h->mech, h->natoms, shift_atom, shift_coord, shift_lo, shift_hi, shift2_lo, shift2_hi);
+    return CRCL_OK;
+}
+
 int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables* T)
 {
     if (!h || !T) return CRCL_EINVAL;

@@ -231,37 +231,66 @@ struct MechDev {
     const int* frag;       // [natoms] device: fragment of each atom or -1
     const double* wfrag;   // [natoms] device: mass[a]/mass_reac[frag[a]]
     double R_inf;
+    // umbr_type family as in xi.cuh: 0 BIMOLEC family, 1 unimolecular, 2 ATOM_SHIFT
+    int type;
+    double freac[8], breac[8];
+    int shift_atom, shift_c1, shift_c2;
+    double shift_lo, shift_hi, shift2_lo, shift2_hi;
 };
+__device__ __forceinline__ void sp_shift_s(const MechDev& M, const double* x, double& s0, double& s1)
+{
+    const double a = x[3 * M.shift_atom + M.shift_c1];
+    if (M.shift_c2 < 0) {
+        s1 = a - M.shift_hi;
+        s0 = a - M.shift_lo;
+    } else {
+        const double b = x[3 * M.shift_atom + M.shift_c2];
+        s1 = ((a - M.shift_hi) + (b - M.shift2_hi)) / 2.0;
+        s0 = ((a - M.shift_lo) + (b - M.shift2_lo)) / 2.0;
+    }
+}
 __global__ void sp_xi_value(MechDev M, int natoms, int ntraj, const double* cen, const double* xi_ideal,
                             double xi_ideal_s, int mode, double* xi_out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntraj) return;
     const double* x = cen + (size_t)t * 3 * natoms;
-    double s1 = 0.0;
-    for (int i = 0; i < M.break_num; i++) {
-        const int a1 = M.bb[i][0], a2 = M.bb[i][1];
-        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-        s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) / (double)M.break_num;
-    }
-    for (int i = 0; i < M.form_num; i++) {
-        const int a1 = M.bf[i][0], a2 = M.bf[i][1];
-        const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-        s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) / (double)M.form_num;
-    }
-    double com[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int a = 0; a < natoms; a++) {
-        const int k = M.frag[a];
-        if (k >= 0)
-            for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
-    }
-    double s0 = 0.0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++) {
-            const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
-            s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
+    double s1 = 0.0, s0 = 0.0;
+    if (M.type == 2) {
+        sp_shift_s(M, x, s0, s1);
+    } else {
+        double s0u = 0.0;
+        for (int i = 0; i < M.break_num; i++) {
+            const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+            const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz);
+            s1 += (r - M.bref[i]) / (double)M.break_num;
+            s0u += (r - M.breac[i]) / (double)M.break_num;
         }
-    s0 = s0 / (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
+        for (int i = 0; i < M.form_num; i++) {
+            const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+            const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+            const double r = sqrt(dx * dx + dy * dy + dz * dz);
+            s1 -= (r - M.fref[i]) / (double)M.form_num;
+            s0u -= (r - M.freac[i]) / (double)M.form_num;
+        }
+        if (M.type == 1) {
+            s0 = s0u;
+        } else {
+            double com[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int a = 0; a < natoms; a++) {
+                const int k = M.frag[a];
+                if (k >= 0)
+                    for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
+            }
+            for (int i = 0; i < M.sum_reacs; i++)
+                for (int j = i + 1; j < M.sum_reacs; j++) {
+                    const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
+                    s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
+                }
+            s0 = s0 / (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
+        }
+    }
     const double xid = xi_ideal ? xi_ideal[t] : xi_ideal_s;
     xi_out[t] = (mode == 1) ? s0 / (s0 - s1) : xid * s1 + (1 - xid) * s0;
 }

@@ -32,26 +32,31 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
         ds1[t] = 0.0;
     }
     double Rf[8][3], Rb[8][3], fi[8], bi[8];
-    double s1 = 0.0;
+    double s1 = 0.0, s0u = 0.0;
     const double fnum = (double)M.form_num, bnum = (double)M.break_num;
-    for (int i = 0; i < M.break_num; i++) {
+    // ATOM_SHIFT has no bond terms, the unimolecular mechanisms no fragment terms (xi.cuh)
+    const int nform = (M.type == 2) ? 0 : M.form_num, nbreak = (M.type == 2) ? 0 : M.break_num;
+    const int nreac = (M.type == 0) ? M.sum_reacs : 0;
+    for (int i = 0; i < nbreak; i++) {
         const int a1 = M.bb[i][0], a2 = M.bb[i][1];
         for (int d = 0; d < 3; d++) Rb[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
         const double r = sqrt(Rb[i][0] * Rb[i][0] + Rb[i][1] * Rb[i][1] + Rb[i][2] * Rb[i][2]);
         bi[i] = 1.0 / r;
         s1 += (r - M.bref[i]) / bnum;
+        s0u += (r - M.breac[i]) / bnum;
         for (int d = 0; d < 3; d++) {
             const double u = Rb[i][d] * bi[i] / bnum;
             ds1[3 * a1 + d] += u;
             ds1[3 * a2 + d] -= u;
         }
     }
-    for (int i = 0; i < M.form_num; i++) {
+    for (int i = 0; i < nform; i++) {
         const int a1 = M.bf[i][0], a2 = M.bf[i][1];
         for (int d = 0; d < 3; d++) Rf[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
         const double r = sqrt(Rf[i][0] * Rf[i][0] + Rf[i][1] * Rf[i][1] + Rf[i][2] * Rf[i][2]);
         fi[i] = 1.0 / r;
         s1 -= (r - M.fref[i]) / fnum;
+        s0u -= (r - M.freac[i]) / fnum;
         for (int d = 0; d < 3; d++) {
             const double u = Rf[i][d] * fi[i] / fnum;
             ds1[3 * a1 + d] -= u;
@@ -59,7 +64,7 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
         }
     }
     double com[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int a = 0; a < natoms; a++) {
+    for (int a = 0; a < natoms && nreac > 0; a++) {
         const int k = M.frag[a];
         if (k >= 0)
             for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
@@ -67,8 +72,8 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
     const double fterms = (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
     double s0 = 0.0, Red[6][3], ri[6];
     int np = 0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+    for (int i = 0; i < nreac; i++)
+        for (int j = i + 1; j < nreac; j++, np++) {
             for (int d = 0; d < 3; d++) Red[np][d] = com[j][d] - com[i][d];
             const double r = sqrt(Red[np][0] * Red[np][0] + Red[np][1] * Red[np][1] + Red[np][2] * Red[np][2]);
             ri[np] = 1.0 / r;
@@ -83,6 +88,15 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
             }
         }
     s0 = s0 / fterms;
+    if (M.type == 1) {          // calc_xi.f90:722-728, :765
+        s0 = s0u;
+        for (int t = 0; t < nc; t++) ds0[t] = ds1[t];
+    } else if (M.type == 2) {   // calc_xi.f90:523-620
+        sp_shift_s(M, x, s0, s1);
+        const double u = (M.shift_c2 < 0) ? 1.0 : 0.5;
+        ds0[3 * M.shift_atom + M.shift_c1] = ds1[3 * M.shift_atom + M.shift_c1] = u;
+        if (M.shift_c2 >= 0) ds0[3 * M.shift_atom + M.shift_c2] = ds1[3 * M.shift_atom + M.shift_c2] = u;
+    }
     if (mode == 1) {
         const double D = s0 - s1;
         xi = s0 / D;
@@ -105,7 +119,7 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
             H1v[t] = 0.0;
             H0v[t] = 0.0;
         }
-    for (int i = 0; i < M.form_num; i++) {
+    for (int i = 0; i < nform; i++) {
         const int a1 = M.bf[i][0], a2 = M.bf[i][1];
         double u[3], o[3];
         for (int d = 0; d < 3; d++) u[d] = v[3 * a1 + d] - v[3 * a2 + d];
@@ -115,7 +129,7 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
             H1v[3 * a2 + d] += o[d] / fnum;
         }
     }
-    for (int i = 0; i < M.break_num; i++) {
+    for (int i = 0; i < nbreak; i++) {
         const int a1 = M.bb[i][0], a2 = M.bb[i][1];
         double u[3], o[3];
         for (int d = 0; d < 3; d++) u[d] = v[3 * a1 + d] - v[3 * a2 + d];
@@ -126,8 +140,8 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
         }
     }
     np = 0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+    for (int i = 0; i < nreac; i++)
+        for (int j = i + 1; j < nreac; j++, np++) {
             double W[3] = {0, 0, 0}, o[3];
             for (int a = 0; a < natoms; a++) {
                 const int k = M.frag[a];
@@ -145,6 +159,8 @@ __device__ inline void sp_xi_grad(const MechDev& M, int natoms, const double* __
                 }
             }
         }
+    if (M.type == 1)
+        for (int t = 0; t < nc; t++) H0v[t] = H1v[t];   // d2s0 = d2s1 (calc_xi.f90:913)
     const double coeff1 = 2.0 * PI_UMBR * beta;
     fs2 = fs2 / coeff1;
     const double pref = (-1.0 / beta) / (coeff1 * fs2);

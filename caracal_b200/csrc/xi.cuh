@@ -27,8 +27,28 @@ struct Mech {
     double wk[XI_MAXREAC][XI_MAXAT];  // wfrag[a] if frag[a] == k else 0: COM_k = sum_a wk[k][a] x_a
     double R_inf;
     double inv_form, inv_break, inv_pairs;  // 1/form_num, 1/break_num, 1/(number of reactant pairs)
+    // umbr_type family: 0 BIMOLEC family (calc_xi.f90:108-502), 1 unimolecular CYCLOREVER / REARRANGE /
+    // DECOM_1BOND / ELIMINATION (:673-938: s0 from the reactant bond lengths), 2 ATOM_SHIFT (:523-672)
+    int type;
+    double freac[XI_MAXBOND], breac[XI_MAXBOND];  // form_reac, break_reac (bonds_ref.f90:81-109)
+    int shift_atom, shift_c1, shift_c2;           // ATOM_SHIFT: atom, first coordinate, second (-1: none)
+    double shift_lo, shift_hi, shift2_lo, shift2_hi;
     int valid;
 };
+
+// s0, s1 of ATOM_SHIFT on structure x (calc_xi.f90:523-560)
+CRCL_HD __forceinline__ void xi_shift_s(const Mech& M, const double* x, double& s0, double& s1)
+{
+    const double a = x[3 * M.shift_atom + M.shift_c1];
+    if (M.shift_c2 < 0) {
+        s1 = a - M.shift_hi;
+        s0 = a - M.shift_lo;
+    } else {
+        const double b = x[3 * M.shift_atom + M.shift_c2];
+        s1 = ((a - M.shift_hi) + (b - M.shift2_hi)) / 2.0;
+        s0 = ((a - M.shift_lo) + (b - M.shift2_lo)) / 2.0;
+    }
+}
 
 // Host-side construction from the MECHA{} tables (1-based atom indices as in the key file,
 // calc_rate_read.f90:430-870).  Returns 0, or a negative code: -1 limits exceeded, -2 bad index.
@@ -80,6 +100,30 @@ inline int build_mech(Mech& M, int natoms, const double* mass, int form_num, con
     return 0;
 }
 
+// unimolecular mechanisms: bond lists as build_mech sets them (without fragments) + reactant references
+inline void mech_set_unimol(Mech& M, const double* form_reac, const double* break_reac)
+{
+    M.type = 1;
+    for (int i = 0; i < M.form_num; i++) M.freac[i] = form_reac[i];
+    for (int i = 0; i < M.break_num; i++) M.breac[i] = break_reac[i];
+}
+// ATOM_SHIFT: shift_coord 1..3 = x,y,z; 4 = (x+y)/2, 5 = (x+z)/2, 6 = (y+z)/2 (calc_rate_read.f90:805-817)
+inline int mech_set_atom_shift(Mech& M, int natoms, int shift_atom, int shift_coord, double lo, double hi, double lo2,
+                               double hi2)
+{
+    if (shift_atom < 1 || shift_atom > natoms || shift_coord < 1 || shift_coord > 6) return -2;
+    M.type = 2;
+    M.shift_atom = shift_atom - 1;
+    M.shift_c1 = (shift_coord < 4) ? shift_coord - 1 : ((shift_coord == 6) ? 1 : 0);
+    M.shift_c2 = (shift_coord < 4) ? -1 : ((shift_coord == 4) ? 1 : 2);
+    M.shift_lo = lo;
+    M.shift_hi = hi;
+    M.shift2_lo = lo2;
+    M.shift2_hi = hi2;
+    M.valid = 1;
+    return 0;
+}
+
 // M w with M = (r^2 I - r r^T)/r^3
 CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w[3], double o[3])
 {
@@ -98,6 +142,34 @@ CRCL_HD __forceinline__ void proj(const double r[3], double rinv, const double w
 template <int NAT>
 CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double xi_ideal, int mode)
 {
+    if (M.type == 2) {
+        double s0, s1;
+        xi_shift_s(M, x, s0, s1);
+        return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    }
+    if (M.type == 1) {   // unimolecular: both dividing surfaces from the same bonds (value only; divisions as written)
+        double s1 = 0.0, s0 = 0.0;
+        const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+#pragma unroll
+        for (int i = 0; i < XI_MAXBOND; i++)
+            if (i < M.break_num) {
+                const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+                const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+                const double r = sqrt(dx * dx + dy * dy + dz * dz);
+                s1 += (r - M.bref[i]) / bnum;
+                s0 += (r - M.breac[i]) / bnum;
+            }
+#pragma unroll
+        for (int i = 0; i < XI_MAXBOND; i++)
+            if (i < M.form_num) {
+                const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+                const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
+                const double r = sqrt(dx * dx + dy * dy + dz * dz);
+                s1 -= (r - M.fref[i]) / fnum;
+                s0 -= (r - M.freac[i]) / fnum;
+            }
+        return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    }
     double s1 = 0.0;
 #pragma unroll
     for (int i = 0; i < XI_MAXBOND; i++)
@@ -154,15 +226,19 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         ds1[t] = 0.0;
     }
     double Rf[XI_MAXBOND][3], Rb[XI_MAXBOND][3], fi[XI_MAXBOND], bi[XI_MAXBOND];
-    double s1 = 0.0;
+    double s1 = 0.0, s0u = 0.0;   // s0u: s0 of the unimolecular mechanisms (reactant bond references)
     const double fnum = (double)M.form_num, bnum = (double)M.break_num;
-    for (int i = 0; i < M.break_num; i++) {
+    // ATOM_SHIFT has no bond terms, the unimolecular mechanisms no fragment terms
+    const int nform = (M.type == 2) ? 0 : M.form_num, nbreak = (M.type == 2) ? 0 : M.break_num;
+    const int nreac = (M.type == 0) ? M.sum_reacs : 0;
+    for (int i = 0; i < nbreak; i++) {
         const int a1 = M.bb[i][0], a2 = M.bb[i][1];
 #pragma unroll
         for (int d = 0; d < 3; d++) Rb[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
         const double r = sqrt(Rb[i][0] * Rb[i][0] + Rb[i][1] * Rb[i][1] + Rb[i][2] * Rb[i][2]);
         bi[i] = 1.0 / r;
         s1 += (r - M.bref[i]) / bnum;
+        s0u += (r - M.breac[i]) / bnum;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const double v = Rb[i][d] * bi[i] / bnum;
@@ -170,13 +246,14 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
             ds1[3 * a2 + d] -= v;
         }
     }
-    for (int i = 0; i < M.form_num; i++) {
+    for (int i = 0; i < nform; i++) {
         const int a1 = M.bf[i][0], a2 = M.bf[i][1];
 #pragma unroll
         for (int d = 0; d < 3; d++) Rf[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
         const double r = sqrt(Rf[i][0] * Rf[i][0] + Rf[i][1] * Rf[i][1] + Rf[i][2] * Rf[i][2]);
         fi[i] = 1.0 / r;
         s1 -= (r - M.fref[i]) / fnum;
+        s0u -= (r - M.freac[i]) / fnum;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const double v = Rf[i][d] * fi[i] / fnum;
@@ -201,8 +278,8 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
     double s0 = 0.0;
     double Red[XI_MAXREAC * (XI_MAXREAC - 1) / 2][3], ri[XI_MAXREAC * (XI_MAXREAC - 1) / 2];
     int np = 0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+    for (int i = 0; i < nreac; i++)
+        for (int j = i + 1; j < nreac; j++, np++) {
 #pragma unroll
             for (int d = 0; d < 3; d++) Red[np][d] = com[j][d] - com[i][d];
             const double r =
@@ -221,6 +298,19 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
             }
         }
     s0 = s0 / fterms;
+    if (M.type == 1) {          // calc_xi.f90:722-728, :765 (ds0 = ds1)
+        s0 = s0u;
+#pragma unroll
+        for (int t = 0; t < 3 * NAT; t++) ds0[t] = ds1[t];
+    } else if (M.type == 2) {   // calc_xi.f90:523-620
+        xi_shift_s(M, x, s0, s1);
+        const double w = (M.shift_c2 < 0) ? 1.0 : 0.5;
+#pragma unroll
+        for (int t = 0; t < 3 * NAT; t++) {
+            const bool on = (t == 3 * M.shift_atom + M.shift_c1) || (M.shift_c2 >= 0 && t == 3 * M.shift_atom + M.shift_c2);
+            ds0[t] = ds1[t] = on ? w : 0.0;
+        }
+    }
 
     if (mode == 1) {
         const double D = s0 - s1;
@@ -250,7 +340,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
             H1v[t] = 0.0;
             H0v[t] = 0.0;
         }
-    for (int i = 0; i < M.form_num; i++) {  // forming bonds: block = -(r^2 I - r r^T)/r^3
+    for (int i = 0; i < nform; i++) {  // forming bonds: block = -(r^2 I - r r^T)/r^3
         const int a1 = M.bf[i][0], a2 = M.bf[i][1];
         double w[3], o[3];
 #pragma unroll
@@ -262,7 +352,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
             H1v[3 * a2 + d] += o[d] / fnum;
         }
     }
-    for (int i = 0; i < M.break_num; i++) {  // breaking bonds: block = +(r^2 I - r r^T)/r^3
+    for (int i = 0; i < nbreak; i++) {  // breaking bonds: block = +(r^2 I - r r^T)/r^3
         const int a1 = M.bb[i][0], a2 = M.bb[i][1];
         double w[3], o[3];
 #pragma unroll
@@ -275,8 +365,8 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         }
     }
     np = 0;
-    for (int i = 0; i < M.sum_reacs; i++)
-        for (int j = i + 1; j < M.sum_reacs; j++, np++) {
+    for (int i = 0; i < nreac; i++)
+        for (int j = i + 1; j < nreac; j++, np++) {
             double W[3] = {0, 0, 0}, o[3];
 #pragma unroll
             for (int a = 0; a < NAT; a++) {
@@ -300,6 +390,10 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
                 }
             }
         }
+    if (M.type == 1) {          // d2s0 = d2s1 (calc_xi.f90:913)
+#pragma unroll
+        for (int t = 0; t < 3 * NAT; t++) H0v[t] = H1v[t];
+    }
     const double coeff1 = 2.0 * PI_UMBR * beta;
     fs2 = fs2 / coeff1;
     const double pref = (-1.0 / beta) / (coeff1 * fs2);

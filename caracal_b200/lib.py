@@ -72,6 +72,10 @@ SIGNATURES = {
                                         c_double_p]),
     "crcl_set_mechanism": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                           ctypes.c_int, c_int_p, c_int_p, ctypes.c_double]),
+    "crcl_set_mechanism_unimol": (ctypes.c_int, [_H, ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
+                                                 c_double_p, c_double_p]),
+    "crcl_set_mechanism_atom_shift": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
+                                                     ctypes.c_double, ctypes.c_double]),
     "crcl_set_thermostat": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
     "crcl_set_seed": (ctypes.c_int, [_H, ctypes.c_uint64]),
     "crcl_egrad": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,

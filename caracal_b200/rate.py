@@ -228,6 +228,16 @@ def calc_k_t(kappa, pmf_max, pmf_min, beta, mass_reac, R_inf, npaths):
     return k_t, k_t / avogadro
 
 
+def calc_k_t_unimol(kappa, pmf_max, pmf_min, kelvin, npaths):
+    """calc_k_t.f90:199-262, CYCLOREVER / REARRANGE / DECOM_1BOND / ELIMINATION: the simple TST formula
+    k(T) = kappa n_paths k_B T / h exp(-(W(xi_TS) - W(xi_min)) / (k_B T)) in s^-1.  pmf_* in hartree; the
+    constants are the reference's REAL*4 literals (F3)."""
+    f32 = lambda x: float(np.float32(x))
+    w_max, w_min = pmf_max * 2625.50, pmf_min * 2625.50          # kJ/mol (:235-236)
+    return kappa * npaths * f32(1.3806485E-23) * kelvin / f32(6.62607E-34) * \
+        math.exp(-(w_max - w_min) / (f32(0.00831447) * kelvin))
+
+
 def calc_rate(g, g1, ts_xyz, mass, mech, kelvin, beta, umbr_lo=-0.05, umbr_hi=1.05, umbr_dist=0.01, k_force_all=0.05,
               gen_steps=10000, equi_steps=10000, umbr_steps=20000, umbr_traj=10, xi_min=-0.05, xi_max=1.05,
               nbins=5000, recr_equi=50000, child_tot=10000, child_interv=1000, child_point=100, child_evol=500,

@@ -163,6 +163,25 @@ interface
       integer(c_int) :: crcl_umbrella_windows
    end function crcl_umbrella_windows
 
+   ! the other umbr_type families of calc_xi.f90: unimolecular (:673-938) and ATOM_SHIFT (:523-672)
+   function crcl_set_mechanism_unimol(h, form_num, bond_form, break_num, bond_break, form_ref, break_ref, &
+                                      form_reac, break_reac) bind(C, name="crcl_set_mechanism_unimol")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: form_num, break_num
+      integer(c_int), dimension(*), intent(in) :: bond_form, bond_break
+      real(c_double), dimension(*), intent(in) :: form_ref, break_ref, form_reac, break_reac
+      integer(c_int) :: crcl_set_mechanism_unimol
+   end function crcl_set_mechanism_unimol
+   function crcl_set_mechanism_atom_shift(h, shift_atom, shift_coord, shift_lo, shift_hi, shift2_lo, shift2_hi) &
+                                          bind(C, name="crcl_set_mechanism_atom_shift")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: shift_atom, shift_coord
+      real(c_double), value :: shift_lo, shift_hi, shift2_lo, shift2_hi
+      integer(c_int) :: crcl_set_mechanism_atom_shift
+   end function crcl_set_mechanism_atom_shift
+
    ! QMDFF tables of module qmdff / pbc_mod (first and second diabatic state), DG-EVB parameters
    function crcl_set_qmdff(h, T) bind(C, name="crcl_set_qmdff")
       import :: c_ptr, c_int, crcl_qmdff_tables

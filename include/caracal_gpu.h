@@ -101,6 +101,18 @@ int crcl_set_mechanism(crcl_handle h, int form_num, const int *bond_form, int br
                        const int *bond_break, const double *form_ref, const double *break_ref,
                        int sum_reacs, const int *n_reac, const int *at_reac, double R_inf);
 
+/* The other umbr_type families of calc_xi.f90 (both dividing surfaces without fragment centres of mass):
+ * unimolecular CYCLOREVER / REARRANGE / DECOM_1BOND / ELIMINATION (calc_xi.f90:673-938): s1 from the TS
+ * reference bond lengths as above, s0 from the reactant references form_reac / break_reac
+ * (bonds_ref.f90:81-109, REACTANTS_STRUC);
+ * ATOM_SHIFT (calc_xi.f90:523-672): one Cartesian coordinate of one atom, shift_coord 1..3 = x,y,z,
+ * 4..6 = mean of (x,y), (x,z), (y,z) with the second pair of limits (calc_rate_read.f90:805-849; bohr). */
+int crcl_set_mechanism_unimol(crcl_handle h, int form_num, const int *bond_form, int break_num,
+                              const int *bond_break, const double *form_ref, const double *break_ref,
+                              const double *form_reac, const double *break_reac);
+int crcl_set_mechanism_atom_shift(crcl_handle h, int shift_atom, int shift_coord, double shift_lo,
+                                  double shift_hi, double shift2_lo, double shift2_hi);
+
 /* Tables of one QMDFF exactly as the reference holds them after prepare.f90 / rdsolvff.f90 /
  * setnonb.f90 / set_periodic.f90 (module qmdff, qmdff.f90:49-110; pbc_mod): the library receives
  * them, it does not rebuild them.  Index lists are 1-based as in the .qmdff file;

@@ -78,6 +78,10 @@ def lib(exact=False):
     return _libs[name]
 
 
+def _f64c(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
 def _d(a):
     return a.ctypes.data_as(dp)
 
@@ -144,6 +148,21 @@ class System:
 
     def set_mechanism(self, m):
         """m: caracal_b200.api.Mechanism-like (1-based indices) -> 0-based for the oracle."""
+        kind = getattr(m, "kind", "bimolec")
+        if kind == "atom_shift":
+            self.L.oracle_sys_set_atom_shift.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [ctypes.c_double] * 4
+            self.L.oracle_sys_set_atom_shift(self.h, m.shift_atom - 1, m.shift_coord, m.shift_lo, m.shift_hi, m.shift2_lo,
+                                             m.shift2_hi)
+            return
+        if kind == "unimol":
+            bf = np.ascontiguousarray(m.bond_form - 1, dtype=np.int32)
+            bb = np.ascontiguousarray(m.bond_break - 1, dtype=np.int32)
+            fr, br = _f64c(m.form_ref), _f64c(m.break_ref)
+            nr, ar = np.zeros(1, dtype=np.int32), np.zeros(1, dtype=np.int32)
+            self.L.oracle_sys_set_mecha(self.h, len(bf), _i(bf), len(bb), _i(bb), _d(fr), _d(br), 0, _i(nr), _i(ar), 0.0)
+            self.L.oracle_sys_set_unimol.argtypes = [ctypes.c_void_p, dp, dp]
+            self.L.oracle_sys_set_unimol(self.h, _d(_f64c(m.form_reac)), _d(_f64c(m.break_reac)))
+            return
         bf = np.ascontiguousarray(m.bond_form - 1, dtype=np.int32)
         bb = np.ascontiguousarray(m.bond_break - 1, dtype=np.int32)
         nr = np.array([len(r) for r in m.reactants], dtype=np.int32)

@@ -167,6 +167,26 @@ void oracle_sys_set_mecha(orc_sys *s, int form_num, const int *bond_form, int br
     s->R_inf = R_inf;
 }
 
+/* unimolecular mechanisms: bond lists as set by oracle_sys_set_mecha plus the reactant references */
+void oracle_sys_set_unimol(orc_sys *s, const double *form_reac, const double *break_reac)
+{
+    int i;
+    s->umbr_type = 1;
+    for (i = 0; i < s->form_num; i++) s->form_reac[i] = form_reac[i];
+    for (i = 0; i < s->break_num; i++) s->break_reac[i] = break_reac[i];
+}
+void oracle_sys_set_atom_shift(orc_sys *s, int shift_atom, int shift_coord, double shift_lo, double shift_hi,
+                               double shift2_lo, double shift2_hi)
+{
+    s->umbr_type = 2;
+    s->shift_atom = shift_atom;
+    s->shift_coord = shift_coord;
+    s->shift_lo = shift_lo;
+    s->shift_hi = shift_hi;
+    s->shift2_lo = shift2_lo;
+    s->shift2_hi = shift2_hi;
+}
+
 void oracle_sys_set_thermostat(orc_sys *s, int thermostat, int andersen_step, double kelvin,
                                double nose_q)
 {
@@ -284,12 +304,65 @@ static void add_hess_block(double *h, int n, int a1, int a2, double sgn, const d
             H4(h, n, i1, a1, i2, a2) = H4(h, n, i1, a1, i2, a2) + sgn * (d[map[i1][i2]] / scale);
 }
 
-/* calc_xi.f90:63-502, BIMOLEC family.  mode 1: umbrella form, mode 2: recrossing form.
+/* calc_xi.f90:523-672, ATOM_SHIFT: one Cartesian coordinate (or the mean of two) of one atom */
+static void orc_calc_xi_shift(const orc_sys *s, const double *coords, double xi_ideal, double *xi_act,
+                              double *dxi_act, double *d2xi_act, int mode)
+{
+    const int n = s->natoms, a = s->shift_atom, sc = s->shift_coord;
+    double s0, s1;
+    double *ds0 = (double *)calloc((size_t)3 * n, sizeof(double));
+    double *ds1 = (double *)calloc((size_t)3 * n, sizeof(double));
+    int c1 = 0, c2 = -1, i;
+    if (sc < 4) {
+        c1 = sc - 1;
+        s1 = D2(coords, c1, a) - s->shift_hi;
+        s0 = D2(coords, c1, a) - s->shift_lo;
+        D2(ds1, c1, a) = 1.0;
+        D2(ds0, c1, a) = 1.0;
+    } else {
+        c1 = (sc == 6) ? 1 : 0;
+        c2 = (sc == 4) ? 1 : 2;
+        s1 = ((D2(coords, c1, a) - s->shift_hi) + (D2(coords, c2, a) - s->shift2_hi)) / 2.0;
+        s0 = ((D2(coords, c1, a) - s->shift_lo) + (D2(coords, c2, a) - s->shift2_lo)) / 2.0;
+        D2(ds1, c1, a) = 0.5;
+        D2(ds1, c2, a) = 0.5;
+        D2(ds0, c1, a) = 0.5;
+        D2(ds0, c2, a) = 0.5;
+    }
+    if (mode == 1) {
+        *xi_act = s0 / (s0 - s1);
+        for (i = 0; i < 3 * n; i++) dxi_act[i] = (s0 * ds1[i] - s1 * ds0[i]) / ((s0 - s1) * (s0 - s1));
+    } else {
+        *xi_act = xi_ideal * s1 + (1 - xi_ideal) * s0;
+        for (i = 0; i < 3 * n; i++) dxi_act[i] = xi_ideal * ds1[i] + (1 - xi_ideal) * ds0[i];
+    }
+    if (d2xi_act) { /* d2s0 = d2s1 = 0 (:633-634) */
+        int i1, j1, i2, j2;
+        memset(d2xi_act, 0, sizeof(double) * 9 * n * n);
+        if (mode == 1)
+            for (i1 = 0; i1 < 3; i1++)
+                for (j1 = 0; j1 < n; j1++)
+                    for (i2 = 0; i2 < 3; i2++)
+                        for (j2 = 0; j2 < n; j2++)
+                            H4(d2xi_act, n, i1, j1, i2, j2) =
+                                ((s0 * 0.0 + D2(ds0, i2, j2) * D2(ds1, i1, j1) - D2(ds1, i2, j2) * D2(ds0, i1, j1) -
+                                  s1 * 0.0) * (s0 - s1) -
+                                 2.0 * (s0 * D2(ds1, i1, j1) - s1 * D2(ds0, i1, j1)) *
+                                     (D2(ds0, i2, j2) - D2(ds1, i2, j2))) /
+                                ((s0 - s1) * (s0 - s1) * (s0 - s1));
+    }
+    free(ds0);
+    free(ds1);
+}
+
+/* calc_xi.f90:63-502, BIMOLEC family, and :673-938, the unimolecular mechanisms (s0 from the reactant
+ * reference bond lengths, ds0 = ds1, d2s0 = d2s1).  mode 1: umbrella form, mode 2: recrossing form.
  * d2xi may be NULL (the value is not needed by the caller; the reference always builds it). */
 void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double *xi_act,
                  double *dxi_act, double *d2xi_act, int mode)
 {
     const int n = s->natoms;
+    const int unimol = (s->umbr_type == 1);
     double R_f[ORC_MAXBOND][3], R_b[ORC_MAXBOND][3], form_act[ORC_MAXBOND], break_act[ORC_MAXBOND];
     double Red[ORC_MAXREAC][ORC_MAXREAC][3], r_eds[ORC_MAXREAC][ORC_MAXREAC];
     double com[ORC_MAXREAC][3];
@@ -300,6 +373,12 @@ void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double
     const float fnum = (float)s->form_num, bnum = (float)s->break_num; /* real(form_num) */
     float fterms;
 
+    if (s->umbr_type == 2) {
+        free(ds0);
+        free(ds1);
+        orc_calc_xi_shift(s, coords, xi_ideal, xi_act, dxi_act, d2xi_act, mode);
+        return;
+    }
     for (i = 0; i < s->form_num; i++) {
         int a1 = s->bond_form[i][0], a2 = s->bond_form[i][1];
         R_f[i][0] = D2(coords, 0, a1) - D2(coords, 0, a2);
@@ -318,9 +397,13 @@ void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double
     for (i = 0; i < s->break_num; i++) s1 = s1 + (break_act[i] - s->break_ref[i]) / bnum;
     for (i = 0; i < s->form_num; i++) s1 = s1 - (form_act[i] - s->form_ref[i]) / fnum;
 
-    orc_calc_com(s, coords, com);
     s0 = 0.0;
-    for (i = 0; i < s->sum_reacs; i++)
+    if (unimol) { /* calc_xi.f90:722-728 */
+        for (i = 0; i < s->break_num; i++) s0 = s0 + (break_act[i] - s->break_reac[i]) / bnum;
+        for (i = 0; i < s->form_num; i++) s0 = s0 - (form_act[i] - s->form_reac[i]) / fnum;
+    } else
+        orc_calc_com(s, coords, com);
+    for (i = 0; i < (unimol ? 0 : s->sum_reacs); i++)
         for (j = i + 1; j < s->sum_reacs; j++) {
             Red[i][j][0] = com[j][0] - com[i][0];
             Red[i][j][1] = com[j][1] - com[i][1];
@@ -331,7 +414,7 @@ void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double
         }
     s0_terms = (s->sum_reacs * s->sum_reacs - s->sum_reacs) / 2;
     fterms = (float)s0_terms;
-    s0 = s0 / fterms;
+    if (!unimol) s0 = s0 / fterms;
 
     if (mode == 1)
         *xi_act = s0 / (s0 - s1);
@@ -356,7 +439,8 @@ void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double
         }
     }
     /* gradient of s0 */
-    for (i = 0; i < s->sum_reacs; i++)
+    if (unimol) memcpy(ds0, ds1, sizeof(double) * 3 * n); /* ds0 = ds1 (:765) */
+    for (i = 0; i < (unimol ? 0 : s->sum_reacs); i++)
         for (j = i + 1; j < s->sum_reacs; j++) {
             Rinv = 1.0 / r_eds[i][j];
             for (k = 0; k < s->n_reac[i]; k++) {
@@ -416,7 +500,8 @@ void orc_calc_xi(const orc_sys *s, const double *coords, double xi_ideal, double
             add_hess_block(d2s1, n, a2, a1, -1.0, d, bnum);
             add_hess_block(d2s1, n, a2, a2, +1.0, d, bnum);
         }
-        for (i = 0; i < s->sum_reacs; i++)
+        if (unimol) memcpy(d2s0, d2s1, sizeof(double) * hs); /* d2s0 = d2s1 (:913) */
+        for (i = 0; i < (unimol ? 0 : s->sum_reacs); i++)
             for (j = i + 1; j < s->sum_reacs; j++) {
                 const double *r = Red[i][j];
                 double dm[6], mf;

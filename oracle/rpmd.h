@@ -39,6 +39,12 @@ typedef struct orc_sys {
     double form_ref[ORC_MAXBOND], break_ref[ORC_MAXBOND];
     int sum_reacs, n_reac[ORC_MAXREAC], at_reac[ORC_MAXREAC][ORC_MAXREACAT];
     double mass_reac[ORC_MAXREAC], R_inf;
+    /* umbr_type family: 0 BIMOLEC family (calc_xi.f90:108-502), 1 unimolecular CYCLOREVER / REARRANGE /
+     * DECOM_1BOND / ELIMINATION (:673-938), 2 ATOM_SHIFT (:523-672) */
+    int umbr_type;
+    double form_reac[ORC_MAXBOND], break_reac[ORC_MAXBOND]; /* bonds_ref.f90:81-109 */
+    int shift_atom, shift_coord;                           /* 0-based atom, coord 1..6 as in the reference */
+    double shift_lo, shift_hi, shift2_lo, shift2_hi;
     double k_force; /* k_force(um_window_act) */
     double *q, *p;  /* [bead][atom][xyz] */
     /* normal-deviate source */
@@ -69,6 +75,9 @@ double *oracle_sys_q(orc_sys *s);
 double *oracle_sys_p(orc_sys *s);
 void oracle_sys_get_nhc(orc_sys *s, double *v4q4);
 uint32_t oracle_sys_get_event(orc_sys *s);
+void oracle_sys_set_unimol(orc_sys *s, const double *form_reac, const double *break_reac);
+void oracle_sys_set_atom_shift(orc_sys *s, int shift_atom, int shift_coord, double shift_lo, double shift_hi,
+                               double shift2_lo, double shift2_hi);
 
 void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g);
 void orc_get_centroid(orc_sys *s, double *centroid);

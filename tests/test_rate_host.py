@@ -47,6 +47,12 @@ def test_calc_k_t_formula():
     assert 1e-17 < k_mol < 1e-14                          # H + H2 at 300 K: ~1e-16 cm^3/(molecule s)
 
 
+def test_calc_k_t_unimolecular_formula():
+    # Eyring: k_B T / h = 6.25e12 1/s at 300 K; a 50 kJ/mol barrier gives exp(-20.05)
+    k = R.calc_k_t_unimol(1.0, 1, 50.0 / 2625.50, 0.0, 300.0, 1)
+    assert abs(k / (6.2509e12 * math.exp(-50.0 / (0.00831447 * 300.0))) - 1.0) < 1e-4
+
+
 def test_whole_pipeline_on_the_oracle(oracle):
     from tests.oracle_handle import OracleRPMD
     name, nb, kelvin = "h3", 4, 300.0
