@@ -49,7 +49,7 @@ def test_calc_k_t_formula():
 
 def test_calc_k_t_unimolecular_formula():
     # Eyring: k_B T / h = 6.25e12 1/s at 300 K; a 50 kJ/mol barrier gives exp(-20.05)
-    k = R.calc_k_t_unimol(1.0, 1, 50.0 / 2625.50, 0.0, 300.0, 1)
+    k = R.calc_k_t_unimol(1.0, 50.0 / 2625.50, 0.0, 300.0, 1)
     assert abs(k / (6.2509e12 * math.exp(-50.0 / (0.00831447 * 300.0))) - 1.0) < 1e-4
 
 
