@@ -19,7 +19,7 @@ from . import lib as _l
 _F32 = np.float32
 EMASS = 5.485799095e-4  # general.f90:252
 AMU = {"H": 1.00782503207, "D": 2.0141017778, "C": 12.00000, "N": 14.0030740048, "O": 15.99491461956,
-       "F": 18.99840, "S": 32.06000, "CL": 34.96885268}   # atommass.f90:58-110
+       "F": 18.99840, "S": 32.06000, "CL": 34.96885268, "BR": 78.9183371}   # atommass.f90:58-129
 
 
 def atomic_mass_au(symbol):
@@ -142,6 +142,10 @@ class RPMD:
 
     def set_path(self, path):
         self._ck(self._lib.crcl_set_path(self._h, int(path)), "crcl_set_path")
+
+    def set_graph(self, on):
+        """Split path: replay steps from a CUDA graph (default on)."""
+        self._ck(self._lib.crcl_set_graph(self._h, int(bool(on))), "crcl_set_graph")
 
     def set_host_gradient(self, fn):
         """fn(xyz[natoms,3]) -> (e, g[natoms,3]): the custom_grad / external_grad plug-in seam."""
@@ -397,7 +401,8 @@ class RPMD:
 
 
 # ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
-_PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"]}
+_PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"],
+             _l.PES_BRH2: ["H", "BR", "H"]}
 _egrad_handles = {}
 
 
@@ -420,6 +425,10 @@ def egrad_h3(q, Natoms=3, Nbeads=None):
 
 def egrad_oh3(q, Natoms=4, Nbeads=None):
     return egrad(_l.PES_OH3, q, Natoms, Nbeads)
+
+
+def egrad_brh2(q, Natoms=3, Nbeads=None):
+    return egrad(_l.PES_BRH2, q, Natoms, Nbeads)
 
 
 def egrad_ch4h(q, Natoms=6, Nbeads=None):

@@ -12,6 +12,7 @@
 #include "pes_h3.cuh"
 #include "pes_oh3.cuh"
 #include "pes_ch4h.cuh"
+#include "pes_brh2.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
 #include "split_xi.cuh"
@@ -41,6 +42,7 @@ struct crcl_handle_s {
     crcl_host_grad_fn cb = nullptr;
     void* cb_user = nullptr;
     int path = CRCL_PATH_AUTO;
+    bool use_graph = true;   // split path: replay steps from a CUDA graph (crcl_set_graph)
     QmdffDev* qmdff = nullptr;
     QmdffDev* qmdff2 = nullptr;
     DgevbDev* dgevb = nullptr;
@@ -268,15 +270,17 @@ __global__ void reduce_kappa_kernel(const unsigned char* theta, const double* we
 // ---- dispatch --------------------------------------------------------------------------------
 static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode = 0)
 {
-    static const traj_launch_fn table[3][3] = {
+    static const traj_launch_fn table[4][3] = {
         {launch_h3_verlet, launch_h3_mdinit, launch_h3_recross},
         {launch_oh3_verlet, launch_oh3_mdinit, launch_oh3_recross},
-        {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross}};
+        {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross},
+        {launch_brh2_verlet, launch_brh2_mdinit, launch_brh2_recross}};
     int row;
     switch (h->pes) {
     case CRCL_PES_H3: row = 0; break;
     case CRCL_PES_OH3: row = 1; break;
     case CRCL_PES_CH4H: row = 2; break;
+    case CRCL_PES_BRH2: row = 3; break;
     default: return fail(h, CRCL_ENOSUP, "no device trajectory kernel for this PES id");
     }
     if (A.ntraj <= 0) return CRCL_OK;
@@ -321,6 +325,7 @@ static int pes_natoms(int pes)
     case CRCL_PES_H3: return 3;
     case CRCL_PES_OH3: return 4;
     case CRCL_PES_CH4H: return 6;
+    case CRCL_PES_BRH2: return 3;
     }
     return -1;
 }
@@ -560,8 +565,17 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
     const int rblocks = (int)std::min<size_t>(64, ((size_t)na * nb + 255) / 256);
     const int tb = (ntraj + 63) / 64, nfree = nfree_of(h);
     const bool nhc_on = (constrain != 2 && h->thermostat == 2);
-    for (int st = 1; st <= nsteps; st++) {
-        const int istep = istep0 + st;
+    // One step as a sequence of 6-14 small launches.  Small systems are launch-bound, so steps 2..nsteps are
+    // replayed from a CUDA graph captured once per call (two variants: with / without the Andersen draw);
+    // step 1 runs eagerly so that every grow-only scratch buffer has its final size before the capture.
+    const bool can_graph = h->use_graph && !h->timed && nsteps >= 4 && h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE;
+    uint32_t* dctr = nullptr;   // device step counter: where sp_theta writes when the step is a graph replay
+    if (can_graph && C.theta) {
+        if ((rc = scratch(h, 27, (size_t)2, &dctr))) return rc;
+        CK(cudaMemsetAsync(dctr, 0, 2 * sizeof(uint32_t), s));
+    }
+    auto one_step = [&](int st, bool andersen_now) -> int {
+        int rc;
         if (nhc_on) {                                                        // 1
             sp_nhc<<<ntraj, 256, 0, s>>>(S, C.p, C.nhc, h->kelvin, nfree);
             h->launches++;
@@ -600,7 +614,7 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
             sp_nhc<<<ntraj, 256, 0, s>>>(S, C.p, C.nhc, h->kelvin, nfree);
             h->launches++;
         }
-        if (constrain != 2 && h->thermostat == 1 && h->andersen_step > 0 && (istep % h->andersen_step) == 0) {
+        if (andersen_now) {
             sp_andersen<<<gel, 256, 0, s>>>(A);                               // 16
             sp_bump_event<<<(ntraj + 127) / 128, 128, 0, s>>>(C.event, ntraj);
             h->launches += 2;
@@ -617,10 +631,69 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
             h->launches++;
         }
         if (C.theta) {
-            sp_theta<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.xi_real, C.theta + (size_t)(st - 1) * ntraj);
+            sp_theta<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.xi_real, C.theta + (dctr ? 0 : (size_t)(st - 1) * ntraj), dctr);
             h->launches++;
+            if (dctr) {
+                sp_bump_event<<<1, 32, 0, s>>>(dctr, 1);
+                h->launches++;
+            }
         }
         CK(cudaGetLastError());
+        return CRCL_OK;
+    };
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    long long glaunches[2] = {0, 0};
+    auto drop_graphs = [&]() {
+        for (auto& g : gexec)
+            if (g) {
+                cudaGraphExecDestroy(g);
+                g = nullptr;
+            }
+    };
+    for (int st = 1; st <= nsteps; st++) {
+        const int istep = istep0 + st;
+        const bool an = (constrain != 2 && h->thermostat == 1 && h->andersen_step > 0 && (istep % h->andersen_step) == 0);
+        if (!can_graph || st == 1) {
+            if ((rc = one_step(st, an))) {
+                drop_graphs();
+                return rc;
+            }
+            continue;
+        }
+        const int v = an ? 1 : 0;
+        if (!gexec[v]) {
+            const long long l0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+            if (e != cudaSuccess) {
+                drop_graphs();
+                h->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e);
+                return CRCL_ECUDA;
+            }
+            rc = one_step(st, an);
+            e = cudaStreamEndCapture(s, &graph);
+            glaunches[v] = h->launches - l0;
+            h->launches = l0;
+            if (rc == CRCL_OK && e == cudaSuccess) e = cudaGraphInstantiate(&gexec[v], graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc || e != cudaSuccess) {
+                drop_graphs();
+                if (!rc) h->err = std::string("CUDA graph capture of a split-path step: ") + cudaGetErrorString(e);
+                return rc ? rc : CRCL_ECUDA;
+            }
+        }
+        cudaError_t e = cudaGraphLaunch(gexec[v], s);
+        if (e != cudaSuccess) {
+            drop_graphs();
+            h->err = std::string("cudaGraphLaunch: ") + cudaGetErrorString(e);
+            return CRCL_ECUDA;
+        }
+        h->launches += glaunches[v];
+    }
+    if (gexec[0] || gexec[1]) {
+        // the executable graphs must outlive their last replay
+        CK(cudaStreamSynchronize(s));
+        drop_graphs();
     }
     // child steps only evaluate the value of xi; leave dxi as verlet.f90:1049-1050 would
     if (constrain == 2 && nsteps > 0 && C.dxi) {
@@ -1107,6 +1180,13 @@ int crcl_set_path(crcl_handle h, int path)
     return CRCL_OK;
 }
 
+int crcl_set_graph(crcl_handle h, int on)
+{
+    if (!h) return CRCL_EINVAL;
+    h->use_graph = on != 0;
+    return CRCL_OK;
+}
+
 int crcl_set_thermostat(crcl_handle h, int thermostat, int andersen_step, double kelvin, double nose_q)
 {
     if (!h || thermostat < 0 || thermostat > 2) return CRCL_EINVAL;
@@ -1188,6 +1268,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_H3: egrad_kernel<PesH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_OH3: egrad_kernel<PesOH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_CH4H: egrad_kernel<PesCH4H><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_BRH2: egrad_kernel<PesBrH2><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     default: return fail(h, CRCL_ENOSUP, "unknown PES id");
     }
     if (h->timed) cudaEventRecord(h->ev1, h->stream);

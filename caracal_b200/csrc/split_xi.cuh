@@ -451,9 +451,12 @@ __global__ void __launch_bounds__(256) sp_recross_weights(SpTraj S, const double
         denom_part[t] = (vs > 0) ? w : 0.0;
     }
 }
-__global__ void sp_theta(int ntraj, const double* __restrict__ xr, unsigned char* __restrict__ theta)
+// step_ctr (may be null): device-resident step index, so that a CUDA-graph replay of a step writes its own row
+__global__ void sp_theta(int ntraj, const double* __restrict__ xr, unsigned char* __restrict__ theta,
+                         const uint32_t* __restrict__ step_ctr)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (step_ctr) theta += (size_t)step_ctr[0] * ntraj;
     if (t < ntraj) theta[t] = (xr[t] > 0) ? 1 : 0;
 }
 

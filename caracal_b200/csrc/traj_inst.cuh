@@ -71,5 +71,8 @@ CRCL_DECLARE_TRAJ(launch_oh3_recross);
 CRCL_DECLARE_TRAJ(launch_ch4h_verlet);
 CRCL_DECLARE_TRAJ(launch_ch4h_mdinit);
 CRCL_DECLARE_TRAJ(launch_ch4h_recross);
+CRCL_DECLARE_TRAJ(launch_brh2_verlet);
+CRCL_DECLARE_TRAJ(launch_brh2_mdinit);
+CRCL_DECLARE_TRAJ(launch_brh2_recross);
 
 }  // namespace crcl

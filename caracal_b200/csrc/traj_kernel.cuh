@@ -139,7 +139,8 @@ struct SmemLayout {
     // staging of the bead-symmetrised {p,q} sums s_b = x_b + x_{N-b}, b = 0..N/2 (reference transform, NB <= 32)
     static constexpr int NH = NB / 2 + 1;
     static constexpr int SYM_STAGE = (NB > 1) ? 2 * NC * NH : 0;
-    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE;  // {p,q}[c][b], cen, dxi, add, ham, sym
+    static constexpr int XI_SCR = (3 * NC + 1) & ~1;        // calc_xi_coop scratch (ds0, ds1, v), even for double2 alignment
+    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE + XI_SCR;  // {p,q}[c][b], cen, dxi, add, ham, sym, xi scratch
     // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
     // load_fker), otherwise the three circulant kernels f[N]
     static constexpr bool HTAB = (NB > 1 && NB <= 32);
@@ -176,6 +177,7 @@ struct Traj {
     double* add;    // shared k (xi - xi0) dxi, the umbrella force added to every bead [NC]
     double* ham;    // shared hams force (umbrella.f90:144-174) [NC]
     double2* sq;    // shared bead-symmetrised sums {p,q}[c][b], b = 0..N/2 (free_rp, reference transform)
+    double* xis;    // shared scratch of calc_xi_coop [3 NC]
     bool want_epot; // false: forces() skips the all-reduce of the bead energies (recrossing children)
     const double* fk;
     double xi_ideal, k_force, xi_real, epot;
@@ -194,6 +196,7 @@ struct Traj {
         add = dxi + NC;
         ham = add + NC;
         sq = reinterpret_cast<double2*>(ham + NC);
+        xis = ham + NC + Lay::SYM_STAGE;
         want_epot = true;
         status = 0;
         xi_real = 0.0;
@@ -391,36 +394,18 @@ struct Traj {
             if (xi_thread()) xi_real = xi_value<NAT>(A.mech, cen, xi_ideal, 2);
             return;
         }
-        double x[NC], d[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) x[c] = cen[c];
+        // xi, dxi (and the hams force) cooperatively: thread t < NC gathers component t (xi.cuh, calc_xi_coop);
+        // results go straight to the shared dxi / ham
+        auto gsync = [&]() { G.sync(); };
         if (mode == 1) {
-            calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 2, xi_real, d, nullptr, A.beta);
-            G.sync();
-            if (G.tig == 0) {
-#pragma unroll
-                for (int c = 0; c < NC; c++) dxi[c] = d[c];
-            }
+            xi_real = calc_xi_coop<NAT, Grp::T>(A.mech, A.mass, cen, xi_ideal, 2, false, A.beta, G.tig, gsync, xis, dxi, ham);
         } else {
-            double h[NC];
-            calc_xi<NAT>(A.mech, A.mass, x, xi_ideal, 1, xi_real, d, h, A.beta);
+            xi_real = calc_xi_coop<NAT, Grp::T>(A.mech, A.mass, cen, xi_ideal, 1, true, A.beta, G.tig, gsync, xis, dxi, ham);
             const double kd = k_force * (xi_real - xi_ideal);
-            G.sync();
-            if (G.tig == 0) {
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    dxi[c] = d[c];
-                    add[c] = kd * d[c];
-                }
-            }
-            if (G.tig == 0) {
-#pragma unroll
-                for (int c = 0; c < NC; c++) ham[c] = h[c];
-            }
             G.sync();
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (own(k)) g[k] = (g[k] + add[oc[k]]) + ham[oc[k]];
+                if (own(k)) g[k] = (g[k] + kd * dxi[oc[k]]) + ham[oc[k]];
         }
         G.sync();
     }

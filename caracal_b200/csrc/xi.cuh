@@ -409,4 +409,193 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
     }
 }
 
+// ---- cooperative form for the T threads of one trajectory (fused trajectory kernels) ---------------------------
+// calc_xi above keeps ds0/ds1/v/H0v/H1v in per-thread arrays that the bond lists index at run time, i.e. in local
+// memory, and the trajectory kernels used to run it redundantly on every thread of a trajectory (ncu, umbrella
+// phase of CH4+H x 16 beads: 6 GB of local-memory write-back per 150 steps, 35 % of the stall samples).  Here
+// thread t < 3 NAT owns component t = 3 atom + xyz and GATHERS its entries: it walks the bond and fragment-pair
+// lists and adds the terms that touch its atom, in the order the scatter loops of calc_xi add them, so every
+// number is bit-identical to calc_xi's.  The structure x, the velocities v = dxi/m and ds0/ds1 are exchanged
+// through shared memory; no array is indexed at run time.
+//   x       shared structure [3 NAT] (the centroid), complete before the call
+//   scr     shared scratch [3 * 3 NAT]
+//   dxi_sh  shared out [3 NAT];  hams_sh shared out [3 NAT] (written if want_hams; mode 1 only)
+// `sync` synchronises the T threads.  The outputs are complete after the caller's next sync.  Every thread
+// returns xi.
+template <int NAT, int T, class SyncF>
+__device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass, const double* x, double xi_ideal, int mode,
+                                               bool want_hams, double beta, int tig, SyncF sync, double* scr,
+                                               double* dxi_sh, double* hams_sh)
+{
+    constexpr int NC = 3 * NAT, NPASS = (NC + T - 1) / T;
+    double* s_ds0 = scr;
+    double* s_ds1 = scr + NC;
+    double* s_v = scr + 2 * NC;
+    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+    const int nform = (M.type == 2) ? 0 : M.form_num, nbreak = (M.type == 2) ? 0 : M.break_num;
+    const int nreac = (M.type == 0) ? M.sum_reacs : 0;
+    const double fterms = (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
+    auto sel = [](const double (&r)[3], int d) { return d == 0 ? r[0] : (d == 1 ? r[1] : r[2]); };
+    // fragment centres of mass and pair vectors: the same for every component, kept in registers
+    double com[XI_MAXREAC][3];
+#pragma unroll
+    for (int k = 0; k < XI_MAXREAC; k++) {
+        com[k][0] = com[k][1] = com[k][2] = 0.0;
+        if (k < nreac) {
+#pragma unroll
+            for (int a = 0; a < NAT; a++)
+#pragma unroll
+                for (int d = 0; d < 3; d++) com[k][d] += M.wk[k][a] * x[3 * a + d];
+        }
+    }
+    double s0 = 0.0, s1 = 0.0, s0u = 0.0;
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+        const int t = tig + p * T;
+        const bool active = t < NC;
+        const int tt = active ? t : 0, a = tt / 3, d = tt - 3 * a;
+        double ds1 = 0.0, ds0 = 0.0;
+        s1 = 0.0;
+        s0u = 0.0;
+        for (int i = 0; i < nbreak; i++) {
+            const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+            const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
+            const double r = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]), ri = 1.0 / r;
+            s1 += (r - M.bref[i]) / bnum;
+            s0u += (r - M.breac[i]) / bnum;
+            const double v = sel(R, d) * ri / bnum;
+            if (a == a1) ds1 += v;
+            if (a == a2) ds1 -= v;
+        }
+        for (int i = 0; i < nform; i++) {
+            const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+            const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
+            const double r = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]), ri = 1.0 / r;
+            s1 -= (r - M.fref[i]) / fnum;
+            s0u -= (r - M.freac[i]) / fnum;
+            const double v = sel(R, d) * ri / fnum;
+            if (a == a1) ds1 -= v;
+            if (a == a2) ds1 += v;
+        }
+        s0 = 0.0;
+        const int ka = M.frag[a];
+        const double wa = M.wfrag[a];
+#pragma unroll
+        for (int i = 0; i < XI_MAXREAC; i++)
+#pragma unroll
+            for (int j = i + 1; j < XI_MAXREAC; j++)
+                if (j < nreac) {
+                    const double Red[3] = {com[j][0] - com[i][0], com[j][1] - com[i][1], com[j][2] - com[i][2]};
+                    const double r = sqrt(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2]), ri = 1.0 / r;
+                    s0 += M.R_inf - r;
+                    if (ka == i || ka == j) {
+                        const double sg = (ka == i) ? 1.0 : -1.0;
+                        ds0 += sel(Red, d) * (sg * ri * wa / fterms);
+                    }
+                }
+        s0 = s0 / fterms;
+        if (M.type == 1) {
+            s0 = s0u;
+            ds0 = ds1;
+        } else if (M.type == 2) {
+            xi_shift_s(M, x, s0, s1);
+            const double w = (M.shift_c2 < 0) ? 1.0 : 0.5;
+            const bool on = (tt == 3 * M.shift_atom + M.shift_c1) || (M.shift_c2 >= 0 && tt == 3 * M.shift_atom + M.shift_c2);
+            ds0 = ds1 = on ? w : 0.0;
+        }
+        double dx;
+        if (mode == 1) {
+            const double D = s0 - s1;
+            dx = (s0 * ds1 - s1 * ds0) * (1.0 / (D * D));
+        } else {
+            dx = xi_ideal * ds1 + (1 - xi_ideal) * ds0;
+        }
+        if (active) {
+            dxi_sh[t] = dx;
+            s_ds0[t] = ds0;
+            s_ds1[t] = ds1;
+            s_v[t] = dx / mass[a];
+        }
+    }
+    const double xi = (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    if (!want_hams) return xi;
+    sync();
+    double fs2 = 0.0, d1v = 0.0, d0v = 0.0;
+#pragma unroll
+    for (int t = 0; t < NC; t++) {
+        const double v = s_v[t];
+        fs2 += dxi_sh[t] * v;
+        d1v += s_ds1[t] * v;
+        d0v += s_ds0[t] * v;
+    }
+    const double coeff1 = 2.0 * PI_UMBR * beta;
+    fs2 = fs2 / coeff1;
+    const double pref = (-1.0 / beta) / (coeff1 * fs2);
+    const double D = s0 - s1;
+    const double iD3 = 1.0 / (D * D * D);
+    const double cross2 = 2.0 * (s0 * d1v - s1 * d0v);
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) {
+        const int t = tig + p * T;
+        const bool active = t < NC;
+        const int tt = active ? t : 0, a = tt / 3, d = tt - 3 * a;
+        double H1 = 0.0, H0 = 0.0;
+        for (int i = 0; i < nform; i++) {
+            const int a1 = M.bf[i][0], a2 = M.bf[i][1];
+            if (a == a1 || a == a2) {
+                const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
+                const double ri = 1.0 / sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+                const double w[3] = {s_v[3 * a1] - s_v[3 * a2], s_v[3 * a1 + 1] - s_v[3 * a2 + 1], s_v[3 * a1 + 2] - s_v[3 * a2 + 2]};
+                double o[3];
+                proj(R, ri, w, o);
+                const double od = sel(o, d) / fnum;
+                if (a == a1) H1 -= od;
+                if (a == a2) H1 += od;
+            }
+        }
+        for (int i = 0; i < nbreak; i++) {
+            const int a1 = M.bb[i][0], a2 = M.bb[i][1];
+            if (a == a1 || a == a2) {
+                const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
+                const double ri = 1.0 / sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+                const double w[3] = {s_v[3 * a1] - s_v[3 * a2], s_v[3 * a1 + 1] - s_v[3 * a2 + 1], s_v[3 * a1 + 2] - s_v[3 * a2 + 2]};
+                double o[3];
+                proj(R, ri, w, o);
+                const double od = sel(o, d) / bnum;
+                if (a == a1) H1 += od;
+                if (a == a2) H1 -= od;
+            }
+        }
+        const int ka = M.frag[a];
+        const double wa = M.wfrag[a];
+#pragma unroll
+        for (int i = 0; i < XI_MAXREAC; i++)
+#pragma unroll
+            for (int j = i + 1; j < XI_MAXREAC; j++)
+                if (j < nreac && (ka == i || ka == j)) {
+                    const double Red[3] = {com[j][0] - com[i][0], com[j][1] - com[i][1], com[j][2] - com[i][2]};
+                    const double ri = 1.0 / sqrt(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2]);
+                    double W[3] = {0, 0, 0}, o[3];
+#pragma unroll
+                    for (int b = 0; b < NAT; b++) {
+                        const int kb = M.frag[b];
+                        if (kb == i || kb == j) {
+                            const double w = ((kb == i) ? 1.0 : -1.0) * M.wfrag[b];
+#pragma unroll
+                            for (int e = 0; e < 3; e++) W[e] += w * s_v[3 * b + e];
+                        }
+                    }
+                    proj(Red, ri, W, o);
+                    const double sg = (ka == i) ? 1.0 : -1.0;
+                    H0 += (-sg * wa / fterms) * sel(o, d);
+                }
+        if (M.type == 1) H0 = H1;
+        const double ds0 = s_ds0[tt], ds1 = s_ds1[tt];
+        const double h = ((s0 * H1 + ds0 * d1v - ds1 * d0v - s1 * H0) * D - cross2 * (ds0 - ds1)) * iD3;
+        if (active) hams_sh[t] = h * pref;
+    }
+    return xi;
+}
+
+
 }  // namespace crcl

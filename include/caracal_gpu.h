@@ -35,6 +35,7 @@ extern "C" {
 #define CRCL_PES_H3 1    /* "h3"   egrad_h3.f   BKMP2 H + H2, 3 atoms                 */
 #define CRCL_PES_OH3 2   /* "oh3"  egrad_oh3.f  Schatz-Elgersma OH + H2, atoms O,H,H,H */
 #define CRCL_PES_CH4H 3  /* "ch4h" egrad_ch4h.f CBE CH4 + H, atoms H,C,H,H,H,H         */
+#define CRCL_PES_BRH2 4  /* "brh2" egrad_brh2.f DIM-3C Br + H2, atoms H,Br,H   */
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
                              crcl_set_qmdff2, crcl_set_dgevb */
@@ -92,6 +93,10 @@ int crcl_set_beta_dt(crcl_handle h, double beta, double dt);
 int crcl_set_transform(crcl_handle h, int mode);
 int crcl_set_host_gradient_cb(crcl_handle h, crcl_host_grad_fn fn, void *user);
 int crcl_set_path(crcl_handle h, int path);
+/* Split path only: steps 2..nsteps of one crcl_verlet / work-unit call are replayed from a CUDA graph of the
+ * step's 6-14 launches (default on; off = one launch per kernel as the first step always does).  Has no
+ * counterpart in the reference: verlet.f90 is called once per step by its drivers. */
+int crcl_set_graph(crcl_handle h, int on);
 
 /* MECHA{} section, BIMOLEC family (calc_rate_read.f90:430-870, bonds_ref.f90): 1-based
  * atom pairs bond_form(form_num,2), bond_break(break_num,2) flattened row-wise; reference

@@ -1,4 +1,4 @@
-// count_flops.cpp -- dynamic operation census of the three reference surfaces:
+// count_flops.cpp -- dynamic operation census of the reference surfaces:
 // compiles the oracle's PES sources with `real` = counting type and evaluates them at
 // TS-neighbourhood geometries.  Output: one JSON object on stdout.  TEST INFRASTRUCTURE.
 #include <cstdio>
@@ -9,6 +9,7 @@ cnt_counters g_cnt = {0, 0, 0, 0, 0, 0};
 #include "pes_h3.c"
 #include "pes_oh3.c"
 #include "pes_ch4h.c"
+#include "pes_brh2.c"
 
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
@@ -44,7 +45,9 @@ int main()
     printf("{\n");
     census("h3", oracle_egrad_h3_real, 3, h3, 2000, false);
     census("oh3", oracle_egrad_oh3_real, 4, oh3, 2000, false);
-    census("ch4h", oracle_egrad_ch4h_real, 6, ch5, 2000, true);
+    const double brh2[9] = {0, 0, 0, 0, 0, -2.72158888, 0, 0, 2.64056088};
+    census("ch4h", oracle_egrad_ch4h_real, 6, ch5, 2000, false);
+    census("brh2", oracle_egrad_brh2_real, 3, brh2, 2000, true);
     printf("}\n");
     return 0;
 }

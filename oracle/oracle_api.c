@@ -23,6 +23,11 @@ void oracle_egrad_ch4h(const double *q, int natoms, int nbeads, double *V, doubl
 {
     oracle_egrad_ch4h_real(q, natoms, nbeads, V, dVdq, info);
 }
+void oracle_egrad_brh2(const double *q, int natoms, int nbeads, double *V, double *dVdq, int *info)
+{
+    oracle_egrad_brh2_real(q, natoms, nbeads, V, dVdq, info);
+}
+void oracle_brh2_pot(const double R[3], double *V, double dVdR[3], int *ierr) { oracle_brh2_pot_real(R, V, dVdR, ierr); }
 void oracle_h3_pote(const double R[3], double *pe, double dpe[3]) { oracle_h3_pote_real(R, pe, dpe); }
 void oracle_oh3_pot(const double R[6], double *V, double dVdR[6]) { oracle_oh3_pot_real(R, V, dVdR); }
 void oracle_ch4h_parts(const double *q18, double parts[3], double *V)
@@ -37,6 +42,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_H3: oracle_egrad_h3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_OH3: oracle_egrad_oh3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_CH4H: oracle_egrad_ch4h_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_BRH2: oracle_egrad_brh2_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

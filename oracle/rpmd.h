@@ -17,6 +17,7 @@
 #define ORC_PES_H3 1
 #define ORC_PES_OH3 2
 #define ORC_PES_CH4H 3
+#define ORC_PES_BRH2 4
 
 #ifdef __cplusplus
 extern "C" {

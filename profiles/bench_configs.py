@@ -60,6 +60,33 @@ for ntraj in (1, 1024, 65536):
            gpu_bead_steps_per_s=ntraj * nb * nsteps / sec, cpu_bead_steps_per_s_one_core=cpu)
 g.close()
 
+# ---- C2 umbrella phase: CH4+H 16 beads, 111 windows x 10 trajectories x (10k + 20k) steps ----
+name, nb = "ch4h", 16
+g, o = C.make_pair(name, nb)
+g.set_seed(C.SEED)
+g.set_thermostat(1, 70, 300.0)
+xi0 = np.linspace(-0.05, 1.05, 111)
+kf = np.full(111, 0.05 * 300.0)
+q0 = np.array([C.ring_polymer(name, nb, rng, 0.01) for _ in range(111)])
+equi, samp, ntw = 10000, 20000, 10
+t0 = time.perf_counter()
+avg, var, st = g.umbrella_windows(q0, xi0, kf, ntw, equi, samp)
+sec = time.perf_counter() - t0
+o.set_thermostat(1, 70, 300.0)
+t0 = time.perf_counter()
+o.q[:] = q0[55]
+o.set_rng(C.SEED, 0)
+o.set_kforce(float(kf[55]))
+o.mdinit(float(xi0[55]), 2)
+for i in range(1, 301):
+    o.verlet(i, float(xi0[55]), 0)
+cpu = 300 * nb / (time.perf_counter() - t0)
+report(config="C2 calc_rate CH4+H (egrad_ch4h) 16 beads umbrella phase: 111 windows x 10 trajectories x (10k+20k) steps",
+       ntraj=111 * ntw, steps=equi + samp, gpu_bead_steps_per_s=111 * ntw * nb * (equi + samp) / sec, gpu_seconds=sec,
+       frac_status0=float((st == 0).mean()),
+       cpu_bead_steps_per_s_one_core=cpu)
+g.close()
+
 # ---- C3: calc_rate OH + H2 (egrad_oh3), 64 beads, recrossing children, temperature sweep ------------
 name, nb, npairs, evol = "oh3", 64, 512, 500
 for kelvin in (200.0, 300.0, 1000.0):
@@ -78,7 +105,7 @@ for kelvin in (200.0, 300.0, 1000.0):
 # ---- C4: DG-EVB-QMDFF RPMD, 32 beads, child trajectories on the split path ---------------------------
 # (the only DG-EVB fixture the reference ships needs evbopt.x output; synthetic 9-atom two-state system)
 T1, T2, E = make_dgevb(seed=5, mode=3, npoints=7)
-nb, ntraj, nsteps = 32, 256, 20
+nb, ntraj, nsteps = 32, 256, 100
 mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O"}[int(z)]) for z in T1["at"]])
 beta, dt = C.beta_calc_rate(300.0), C.dt_au(0.2)
 g = caracal_b200.RPMD(caracal_b200.PES_DGEVB, nb, mass, beta, dt)
@@ -89,7 +116,10 @@ g.set_seed(C.SEED)
 g.set_thermostat(1, 10, 300.0)
 q = np.ascontiguousarray(T1["xyz"][None, None] + rng.normal(0, 0.01, (ntraj, nb) + T1["xyz"].shape))
 p, d, dxi, ev = g.mdinit(q, 0)
-sec = timed(lambda: g.verlet(q, p, d, nsteps=nsteps, constrain=-1, event=ev), reps=2)
+secs = {}
+for graph in (0, 1):
+    g.set_graph(graph)
+    secs[graph] = timed(lambda: g.verlet(q, p, d, nsteps=nsteps, constrain=-1, event=ev), reps=2)
 D = O.Dgevb(T1, T2, E)
 os_ = O.System(0, nb, mass, beta, dt)
 os_.set_custom_grad(lambda x: tuple(a[0] for a in D.egrad(x)))
@@ -101,8 +131,11 @@ t0 = time.perf_counter()
 for i in range(1, 6):
     os_.verlet(i, 0.0, -1)
 cpu = 5 * nb / (time.perf_counter() - t0)
-report(config="C4 DG-EVB-QMDFF RPMD (2 x QMDFF + mode-3 coupling, 9 atoms synthetic) 32 beads, split path",
-       ntraj=ntraj, steps=nsteps, gpu_bead_steps_per_s=ntraj * nb * nsteps / sec, cpu_bead_steps_per_s_one_core=cpu)
+for graph in (0, 1):
+    report(config="C4 DG-EVB-QMDFF RPMD (2 x QMDFF + mode-3 coupling, 9 atoms synthetic) 32 beads, split path, "
+                  + ("CUDA-graph replay" if graph else "one launch per kernel"),
+           ntraj=ntraj, steps=nsteps, gpu_bead_steps_per_s=ntraj * nb * nsteps / secs[graph],
+           gpu_us_per_step=1e6 * secs[graph] / nsteps, cpu_bead_steps_per_s_one_core=cpu)
 g.close()
 
 # ---- C5: periodic QMDFF box NVT (~3000 atoms, Zahn, H bonds), classical and 8 beads ------------------

@@ -31,12 +31,21 @@ def ch5_ts():
     return q / BOHR
 
 
+def brh2_ts():
+    """Collinear saddle of the DIM-3C surface located with the oracle (profiles: r(H-Br) = 1.4402 A,
+    r(H-H) = 1.3973 A, 21.0 kcal/mol above Br + H2); atom order H, Br, H (egrad_brh2.f:47-62)."""
+    return np.array([[0, 0, 0], [0, 0, -2.72158888], [0, 0, 2.64056088]])
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
                mecha=dict(bond_form=[[2, 3]], bond_break=[[1, 2]], reactants=[[1, 2], [3]], dist_inf=16.0)),
     "oh3": dict(pes="oh3", symbols=["O", "H", "H", "H"], ts=oh3_ts,
                 mecha=dict(bond_form=[[1, 3]], bond_break=[[3, 4]], reactants=[[1, 2], [3, 4]], dist_inf=16.0)),
+    "brh2": dict(pes="brh2", symbols=["H", "BR", "H"], ts=brh2_ts,
+                 # Br + H2 -> HBr + H: reactant1 2, reactant2 1 3, bond_form 2-1, bond_break 1-3
+                 mecha=dict(bond_form=[[2, 1]], bond_break=[[1, 3]], reactants=[[2], [1, 3]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # SURVEY 8(d) C2: reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

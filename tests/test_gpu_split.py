@@ -259,3 +259,36 @@ def test_rate_pipeline_on_a_qmdff_surface_runs_on_the_split_path(gpu):
     g.set_thermostat(0, 0, 300.0)
     num, den, stc = g.recross_children(q, 4, 25, 1.0)
     assert (stc == 0).all() and den > 0 and np.isfinite(num).all() and abs(num[0] / den - 1.0) < 0.5
+
+
+def test_graph_replay_is_bit_identical_to_eager_launches(gpu):
+    """Steps 2..n of a split-path call are replayed from a CUDA graph (crcl_set_graph); the replay launches the
+    same kernels with the same arguments, so every mode must give bit-identical state with it on and off:
+    Andersen on some steps only (two graph variants), SHAKE / RATTLE, NHC, the umbrella accumulators and the
+    per-step theta rows of the recrossing work unit."""
+    name, nb, ntraj = "ch4h", 8, 3
+    rng = np.random.default_rng(12)
+    q0 = np.array([C.ring_polymer(name, nb, rng, 0.02) for _ in range(ntraj)])
+    qp = np.array([C.ring_polymer(name, nb, rng, 0.01) for _ in range(2)])
+    xi, k = np.full(ntraj, 0.97), np.full(ntraj, 15.0)
+    out = []
+    for on in (1, 0):
+        g, _ = C.make_pair(name, nb)
+        g.set_path(gpu.PATH_SPLIT)
+        g.set_graph(on)
+        g.set_seed(C.SEED)
+        res = []
+        for constrain, thermo, astep, bias in ((-1, 1, 7, 0), (0, 1, 5, 2), (1, 1, 9, 2), (2, 0, 0, 0), (0, 2, 0, 2)):
+            g.set_thermostat(thermo, astep, 300.0, 100.0)
+            q = q0.copy()
+            p, d, dxi, ev = g.mdinit(q, bias, xi_ideal=xi, k_force=k)
+            l0 = g.launch_count()
+            ep, xr, st = g.verlet(q, p, d, nsteps=40, constrain=constrain, xi_ideal=xi, k_force=k, dxi=dxi, event=ev)
+            res += [q, p, d, ep, xr, np.array([g.launch_count() - l0])]
+        g.set_thermostat(0, 0, 300.0)
+        num, den, st = g.recross_children(qp, 3, 30, 0.985, pair0=2)
+        g.set_thermostat(1, 7, 300.0)
+        avg, var, st2 = g.umbrella_windows(q0, np.array([0.9, 0.97, 1.01]), k, 2, 20, 30, traj_id0=4)
+        out.append(res + [num, np.array([den]), avg, var])
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
