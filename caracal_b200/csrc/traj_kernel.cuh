@@ -139,7 +139,7 @@ struct SmemLayout {
     // staging of the bead-symmetrised {p,q} sums s_b = x_b + x_{N-b}, b = 0..N/2 (reference transform, NB <= 32)
     static constexpr int NH = NB / 2 + 1;
     static constexpr int SYM_STAGE = (NB > 1) ? 2 * NC * NH : 0;
-    static constexpr int XI_SCR = (3 * NC + 1) & ~1;        // calc_xi_coop scratch (ds0, ds1, v), even for double2 alignment
+    static constexpr int XI_SCR = (3 * NC + 2) & ~1;        // calc_xi_coop scratch (ds0, ds1, v, xi), even for double2 alignment
     static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE + XI_SCR;  // {p,q}[c][b], cen, dxi, add, ham, sym, xi scratch
     // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
     // load_fker), otherwise the three circulant kernels f[N]
@@ -409,32 +409,29 @@ struct Traj {
         }
         G.sync();
     }
-    // constrain_q.f90:30-112 (SHAKE on the centroid with the previous step's dxi)
+    // constrain_q.f90:30-112 (SHAKE on the centroid with the previous step's dxi).  The trial structure lives in
+    // the shared `add` slot, the gradient of xi on it in `ham` (both free in the constrained mode); calc_xi_coop
+    // evaluates it across the threads of the trajectory; every thread forms the same dsigma in the reference's order.
     __device__ __forceinline__ int constrain_q()
     {
-        double x[NC], d[NC], dn[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            x[c] = cen[c];
-            d[c] = dxi[c];
-        }
+        auto gsync = [&]() { G.sync(); };
         const double dt = A.dt;
         double mult = 0.0, coeff = 0.0;
         int ok = 0;
         for (int iter = 1; iter <= 200; iter++) {
             coeff = mult * dt * dt / NB;
-            double xt[NC], xin;
-#pragma unroll
-            for (int j = 0; j < NAT; j++)
-#pragma unroll
-                for (int k = 0; k < 3; k++) xt[3 * j + k] = x[3 * j + k] + coeff * d[3 * j + k] / A.mass[j];
-            calc_xi<NAT>(A.mech, A.mass, xt, xi_ideal, 2, xin, dn, nullptr, A.beta);
+            G.sync();
+            for (int c = G.tig; c < NC; c += Grp::T) add[c] = cen[c] + coeff * dxi[c] / A.mass[c / 3];
+            G.sync();
+            const double xin =
+                calc_xi_coop<NAT, Grp::T>(A.mech, A.mass, add, xi_ideal, 2, false, A.beta, G.tig, gsync, xis, ham, ham);
+            G.sync();
             double dsigma = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; k++)
 #pragma unroll
                 for (int j = 0; j < NAT; j++)
-                    dsigma += dn[3 * j + k] * dt * dt * d[3 * j + k] / (A.mass[j] * NB);
+                    dsigma += ham[3 * j + k] * dt * dt * dxi[3 * j + k] / (A.mass[j] * NB);
             const double dx = xin / dsigma;
             mult -= dx;
             // 1.0E-8 / 1.0E-10 are REAL*4 literals in constrain_q.f90:93

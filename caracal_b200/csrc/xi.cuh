@@ -428,6 +428,24 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
                                                double* dxi_sh, double* hams_sh)
 {
     constexpr int NC = 3 * NAT, NPASS = (NC + T - 1) / T;
+    if constexpr (NPASS > 1) {
+        // fewer threads than components (few beads): a thread would repeat the list walks for each of its
+        // components (measured: the one-bead start-structure chain of calc_rate ran 5x slower), so every thread
+        // evaluates the serial form and thread 0 publishes it -- the same numbers by construction
+        double xl[NC], dl[NC], hl[NC], xi;
+#pragma unroll
+        for (int c = 0; c < NC; c++) xl[c] = x[c];
+        calc_xi<NAT>(M, mass, xl, xi_ideal, mode, xi, dl, want_hams ? hl : nullptr, beta);
+        sync();
+        if (tig == 0) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                dxi_sh[c] = dl[c];
+                if (want_hams) hams_sh[c] = hl[c];
+            }
+        }
+        return xi;
+    }
     double* s_ds0 = scr;
     double* s_ds1 = scr + NC;
     double* s_v = scr + 2 * NC;
@@ -436,12 +454,14 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
     const int nreac = (M.type == 0) ? M.sum_reacs : 0;
     const double fterms = (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
     auto sel = [](const double (&r)[3], int d) { return d == 0 ? r[0] : (d == 1 ? r[1] : r[2]); };
+    // warps of a CTA-wide trajectory that own no component skip the work and pick xi up from shared memory
+    const bool work = (T <= 32) || ((tig & ~31) < NC);
     // fragment centres of mass and pair vectors: the same for every component, kept in registers
     double com[XI_MAXREAC][3];
 #pragma unroll
     for (int k = 0; k < XI_MAXREAC; k++) {
         com[k][0] = com[k][1] = com[k][2] = 0.0;
-        if (k < nreac) {
+        if (work && k < nreac) {
 #pragma unroll
             for (int a = 0; a < NAT; a++)
 #pragma unroll
@@ -451,6 +471,7 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
     double s0 = 0.0, s1 = 0.0, s0u = 0.0;
 #pragma unroll
     for (int p = 0; p < NPASS; p++) {
+        if (!work) break;
         const int t = tig + p * T;
         const bool active = t < NC;
         const int tt = active ? t : 0, a = tt / 3, d = tt - 3 * a;
@@ -517,9 +538,11 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             s_v[t] = dx / mass[a];
         }
     }
-    const double xi = (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
-    if (!want_hams) return xi;
-    sync();
+    double xi = (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    if (T > 32 && tig == 0) scr[3 * NC] = xi;
+    if (T > 32 || want_hams) sync();
+    if (!work) xi = scr[3 * NC];
+    if (!want_hams || !work) return xi;
     double fs2 = 0.0, d1v = 0.0, d0v = 0.0;
 #pragma unroll
     for (int t = 0; t < NC; t++) {

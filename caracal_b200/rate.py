@@ -247,21 +247,32 @@ def calc_rate(g, g1, ts_xyz, mass, mech, kelvin, beta, umbr_lo=-0.05, umbr_hi=1.
     set_mechanism and set_seed.  umbr_constrain: the constrain flag of the biased phases 1 and 2, 0 as
     calc_rate.f90 passes it, 3 for the same dynamics without verlet.f90:1300-1306's removal of net
     rotation ("published figures").  Returns a dict with every intermediate."""
-    say = log or (lambda *a: None)
+    import time
+    t_prev = [time.perf_counter()]
+    timings = {}
+
+    def say(msg, phase=None):
+        now = time.perf_counter()
+        if phase:
+            timings[phase] = now - t_prev[0]
+            msg += "  [%.2f s]" % timings[phase]
+        t_prev[0] = now
+        if log:
+            log(msg)
     n_over, n_samplings, n_all, xi_wins = window_grid(umbr_lo, umbr_hi, umbr_dist)
     k_force = np.full(n_all - 1, k_force_all * kelvin)          # calc_rate.f90:699
     g1.set_thermostat(1, andersen_step, kelvin)
     struc, start_xis = generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_force, gen_steps,
                                                  constrain=umbr_constrain)
-    say("start structures: xi reached in [%.3f, %.3f]" % (start_xis.min(), start_xis.max()))
+    say("start structures: xi reached in [%.3f, %.3f]" % (start_xis.min(), start_xis.max()), "start_structures")
     g.set_thermostat(1, andersen_step, kelvin)
     average, variance, nerr = umbrella_sampling(g, xi_wins, struc, k_force, umbr_traj, equi_steps, umbr_steps,
                                                 constrain=umbr_constrain)
-    say("umbrella sampling: %d windows, %d re-run trajectories" % (len(xi_wins), nerr))
+    say("umbrella sampling: %d windows, %d re-run trajectories" % (len(xi_wins), nerr), "umbrella_sampling")
     bin_coord, pmf = umbrella_integration(xi_wins, average, variance, k_force, beta, xi_min, xi_max, nbins, umbr_traj,
                                           umbr_steps)
     maxloc, minloc, xi_barrier = locate_extrema(bin_coord, pmf, xi_min, xi_max, pmf_minloc)
-    say("PMF: barrier %.3f kJ/mol at xi = %.4f" % ((pmf[maxloc] - pmf[minloc]) * HARTREE_KJ, xi_barrier))
+    say("PMF: barrier %.3f kJ/mol at xi = %.4f" % ((pmf[maxloc] - pmf[minloc]) * HARTREE_KJ, xi_barrier), "umbrella_integration")
     ts_locate = int(np.argmin(np.abs(xi_wins - xi_barrier)))     # calc_rate.f90:2183-2187
     q_start = np.repeat(struc[ts_locate][None], g.nbeads, axis=0)
     num, den, parents, status = recrossing(g, q_start, xi_barrier, k_force[ts_locate], kelvin, recr_equi, child_tot,
@@ -272,8 +283,8 @@ def calc_rate(g, g1, ts_xyz, mass, mech, kelvin, beta, umbr_lo=-0.05, umbr_hi=1.
         kappa = 1.0
     mass_reac = [sum(mass[a - 1] for a in r) for r in mech.reactants]
     k_t, k_t_molec = calc_k_t(kappa, pmf[maxloc], pmf[minloc], beta, mass_reac, mech.R_inf, npaths)
-    say("kappa = %.4f, k(T) = %.4e cm^3/(molecule s)" % (kappa, k_t_molec))
+    say("kappa = %.4f, k(T) = %.4e cm^3/(molecule s)" % (kappa, k_t_molec), "recrossing")
     return dict(xi_wins=xi_wins, struc_equi=struc, start_xis=start_xis, average=average, variance=variance,
                 bin_coord=bin_coord, pmf=pmf, maxlocate=maxloc, minlocate=minloc, xi_barrier=xi_barrier,
                 delta_w_kj=(pmf[maxloc] - pmf[minloc]) * HARTREE_KJ, kappa_t=kappa_t, kappa=kappa, k_t=k_t,
-                k_t_molec=k_t_molec, child_status=status, n_rerun=nerr)
+                k_t_molec=k_t_molec, child_status=status, n_rerun=nerr, timings=timings)

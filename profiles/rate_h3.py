@@ -33,7 +33,7 @@ out = R.calc_rate(g, g1, C.h3_ts(), m, mech, kelvin, beta, npaths=2, umbr_constr
 wall = time.perf_counter() - t0
 res = dict(example="examples/calc_rate/h+h2/rate.key (full size)", nbeads=nb,
            transform="exact" if exact else "reference (rfft/irfft as written)",
-           rotation_removed_in_umbrella_phase=not norot, wall_s=wall,
+           rotation_removed_in_umbrella_phase=not norot, wall_s=wall, phase_s=out["timings"],
            pmf_at={"%.1f" % x: float((out["pmf"][int(np.argmin(np.abs(out["bin_coord"][:-1] - x)))]
                                        - out["pmf"][out["minlocate"]]) * R.HARTREE_KJ) for x in (0.2, 0.4, 0.6, 0.8, 0.9)}, xi_barrier=float(out["xi_barrier"]),
            delta_w_kj=float(out["delta_w_kj"]), kappa=float(out["kappa"]), kappa_t_every_50=out["kappa_t"][49::50].tolist(),
