@@ -6,7 +6,7 @@ operator interface for the path (api.py): egrad_<pes>(q,Natoms,Nbeads) -> V,dVdq
 mdinit / verlet / recross / umbrella work units on batches of ring polymers.
 """
 from .lib import (CaracalGpuError, LIB_PATH, PES_BRH2, PES_CH4H, PES_H3, PES_IDS, PES_OH3, TRANSFORM_EXACT,  # noqa: F401
-                  TRANSFORM_REFERENCE, PATH_AUTO, PATH_FUSED, PATH_SPLIT, PES_HOSTCB, PES_QMDFF, PES_DGEVB, PES_NONE, load)
+                  TRANSFORM_REFERENCE, PATH_AUTO, PATH_FUSED, PATH_SPLIT, PES_HOSTCB, PES_QMDFF, PES_DGEVB, PES_WATER, PES_NONE, load)
 from .api import (RPMD, Mechanism, UnimolMechanism, AtomShiftMechanism, atomic_mass_au, beta_calc_rate, beta_dynamic, dt_au, egrad, egrad_ch4h,  # noqa: F401
                   egrad_brh2, egrad_h3, egrad_oh3)
 

@@ -196,6 +196,21 @@ class RPMD:
         else:
             self._ck(self._lib.crcl_set_qmdff(self._h, ctypes.byref(S)), "crcl_set_qmdff")
 
+    def set_water(self, W):
+        """W: dict(n, periodic, zahn, box[3], coul_cut, zahn_a, zahn_par, pars[11], q[n], is_O[n]): the module state
+        after water_init.f90 / set_periodic.f90 (pes WATER_SPC)."""
+        q = _f64(W["q"])
+        o = np.ascontiguousarray(W["is_O"], dtype=np.int32)
+        P = _l.WaterParams()
+        P.n, P.periodic, P.zahn = int(W["n"]), int(W["periodic"]), int(W["zahn"])
+        for d in range(3):
+            P.box[d] = float(W["box"][d])
+        P.coul_cut, P.zahn_a, P.zahn_par = float(W["coul_cut"]), float(W["zahn_a"]), float(W["zahn_par"])
+        for k in range(11):
+            P.pars[k] = float(W["pars"][k])
+        P.q, P.is_O = _dp(q), _ip(o)
+        self._ck(self._lib.crcl_set_water(self._h, ctypes.byref(P)), "crcl_set_water")
+
     def set_dgevb(self, E):
         """E: dict(mode, coord_def[nat6,5], point_int[npoints,nat6], alph[npoints], b_vec[mat_size], g_thres)"""
         cd = np.ascontiguousarray(E["coord_def"], dtype=np.int32)

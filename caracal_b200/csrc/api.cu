@@ -19,6 +19,7 @@
 #include "qmdff.cuh"
 #include "dgevb.cuh"
 #include "ewald.cuh"
+#include "water.cuh"
 
 using namespace crcl;
 
@@ -47,6 +48,7 @@ struct crcl_handle_s {
     QmdffDev* qmdff2 = nullptr;
     DgevbDev* dgevb = nullptr;
     EwaldDev* ewald = nullptr;
+    WaterDev* water = nullptr;
     // split path: per-atom tables on the device, generic-size mechanism
     double *d_mass = nullptr, *d_wfrag = nullptr;
     int *d_atmove = nullptr, *d_frag = nullptr;
@@ -845,7 +847,7 @@ int crcl_create(crcl_handle* out, int device, int natoms, int nbeads, const doub
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return CRCL_ENODEV;
     if (device < 0 || device >= ndev) return CRCL_EINVAL;
     if (pes_id != CRCL_PES_HOSTCB && pes_id != CRCL_PES_NONE && pes_id != CRCL_PES_QMDFF &&
-        pes_id != CRCL_PES_DGEVB) {
+        pes_id != CRCL_PES_DGEVB && pes_id != CRCL_PES_WATER) {
         const int n = pes_natoms(pes_id);
         if (n < 0 || n != natoms) return CRCL_EINVAL;
     }
@@ -888,6 +890,7 @@ int crcl_destroy(crcl_handle h)
     qmdff_free(h->qmdff2);
     dgevb_free(h->dgevb);
     ewald_free(h->ewald);
+    water_free(h->water);
     if (h->d_mass) cudaFree(h->d_mass);
     if (h->d_atmove) cudaFree(h->d_atmove);
     if (h->d_frag) cudaFree(h->d_frag);
@@ -1121,6 +1124,19 @@ int crcl_set_qmdff2(crcl_handle h, const crcl_qmdff_tables* T)
     return CRCL_OK;
 }
 
+int crcl_set_water(crcl_handle h, const crcl_water_params* P)
+{
+    if (!h || !P) return CRCL_EINVAL;
+    if (P->n != h->natoms) return fail(h, CRCL_EINVAL, "crcl_set_water: P->n differs from the handle's natoms");
+    CK(cudaSetDevice(h->device));
+    water_free(h->water);
+    h->water = nullptr;
+    const char* msg = "";
+    const int rc = water_upload(P, &h->water, &msg);
+    if (rc) return fail(h, rc, msg);
+    return CRCL_OK;
+}
+
 int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params* P)
 {
     if (!h || !P || !P->coord_def || !P->point_int || !P->alph || !P->b_vec) return CRCL_EINVAL;
@@ -1233,6 +1249,24 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
         if (h->timed) cudaEventRecord(h->ev1, h->stream);
         if (e != cudaSuccess) {
             h->err = std::string("dg-evb kernels: ") + cudaGetErrorString(e);
+            return CRCL_ECUDA;
+        }
+        return CRCL_OK;
+    }
+    if (pes_id == CRCL_PES_WATER) {
+        if (!h->water) return fail(h, CRCL_ESTATE, "crcl_set_water has not been called");
+        if (h->water->n != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the water box");
+        if (nimg == 0) return CRCL_OK;
+        CK(cudaSetDevice(h->device));
+        if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
+        if (h->timed) {
+            next_event_pair(h);
+            cudaEventRecord(h->ev0, h->stream);
+        }
+        cudaError_t e = water_egrad(h->water, d_q, nimg, d_V, d_dVdq, h->stream, &h->launches);
+        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (e != cudaSuccess) {
+            h->err = std::string("water kernels: ") + cudaGetErrorString(e);
             return CRCL_ECUDA;
         }
         return CRCL_OK;

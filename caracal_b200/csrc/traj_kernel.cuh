@@ -70,12 +70,24 @@ struct TrajArgs {
 // The T = NB*LANES threads of one trajectory: a sub-warp segment when T <= 32 (32/T trajectories
 // per warp, masked shuffles / __syncwarp so trajectories sharing a warp never wait on each
 // other), otherwise one whole CTA.
+// Sub-warp trajectories are packed CRCL_WTPB threads to a CTA and the CTA's warps are re-aligned with one barrier per
+// step: the step body of the unrolled surfaces is ~90 KB of SASS, and single-warp CTAs drifting through it
+// independently were bound by instruction-cache misses (ncu, H + H2 x 16 beads: no_instruction 7.4 of 13 stall
+// cycles per issued instruction, profiles/r1m_verlet_h3_nb16_minb12.txt); warps in step share the fetched lines.
+#ifndef CRCL_WTPB
+#define CRCL_WTPB 128
+#endif
 template <int NB, int LANES>
 struct Group {
     static constexpr int T = NB * LANES;
     static constexpr bool WARP = (T <= 32);
-    static constexpr int TPB = WARP ? 32 : T;      // threads per block
-    static constexpr int GPB = WARP ? 32 / T : 1;  // trajectories per block
+    static constexpr int TPB = WARP ? CRCL_WTPB : T;      // threads per block
+    static constexpr int GPB = WARP ? CRCL_WTPB / T : 1;  // trajectories per block
+    // re-align the warps of a CTA of sub-warp trajectories (no-op for CTA-wide trajectories, which synchronise anyway)
+    static __device__ __forceinline__ void align_warps()
+    {
+        if (WARP && CRCL_WTPB > 32) __syncthreads();
+    }
     int tig, bead, lane, gib;                      // thread in group, bead, lane of the bead, group in block
     unsigned mask;
     double* red;  // CTA-wide scratch (T > 32): [T/32]
@@ -710,7 +722,9 @@ template <class PES, int NB>
 struct LaunchCfg {
     static constexpr int TPB = Group<NB, PES::LANES>::TPB;
     // one-lane surfaces (H3, OH3): CRCL_MINB_L1 resident CTAs requested when a CTA is a single warp
-    static constexpr int MINB = (PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : ((TPB == 32) ? CRCL_MINB_L1 : 1);
+    static constexpr bool WARP = Group<NB, PES::LANES>::WARP;
+    static constexpr int MINB = WARP ? ((PES::LANES > 1) ? 2 : (CRCL_MINB_L1 * 32 / CRCL_WTPB > 0 ? CRCL_MINB_L1 * 32 / CRCL_WTPB : 1))
+                                     : ((PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : 1);
 };
 
 // Free ring-polymer kernels into shared memory.  NB <= 32: the dense tables
@@ -767,11 +781,13 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
     G.sync();
     double sx = 0.0, sx2 = 0.0;
     for (int s = 1; s <= A.nsteps; s++) {
+        Grp::align_warps();
         // a failed trajectory is frozen (the reference aborts or restarts it)
-        if (T.status & (CRCL_TRAJ_SHAKE_FAIL | CRCL_TRAJ_NAN | CRCL_TRAJ_SINGULAR)) break;
-        T.step(A.istep0 + s, (s & 15) == 0 || s == A.nsteps);
-        sx += T.xi_real;
-        sx2 += T.xi_real * T.xi_real;
+        if (!(T.status & (CRCL_TRAJ_SHAKE_FAIL | CRCL_TRAJ_NAN | CRCL_TRAJ_SINGULAR))) {
+            T.step(A.istep0 + s, (s & 15) == 0 || s == A.nsteps);
+            sx += T.xi_real;
+            sx2 += T.xi_real * T.xi_real;
+        }
     }
     // child steps only evaluate the value of xi; leave dxi as verlet.f90:1049-1050 would
     if (A.constrain == 2 && A.nsteps > 0) T.umbrella(1);
@@ -900,6 +916,7 @@ recross_kernel(const __grid_constant__ TrajArgs A)
         A.denom_part[traj] = (vs > 0) ? w : 0.0;
     }
     for (int l = 1; l <= A.nsteps; l++) {
+        Grp::align_warps();
         if (!(T.status & CRCL_TRAJ_NAN)) T.step(l, (l & 15) == 0 || l == A.nsteps);
         if (T.xi_writer()) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
     }

@@ -14,7 +14,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
 c_u32_p = ctypes.POINTER(ctypes.c_uint32)
 
-PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_BRH2, PES_QMDFF, PES_DGEVB, PES_HOSTCB = 0, 1, 2, 3, 4, 10, 11, 100
+PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_BRH2, PES_QMDFF, PES_DGEVB, PES_WATER, PES_HOSTCB = 0, 1, 2, 3, 4, 10, 11, 12, 100
 PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H, "brh2": PES_BRH2}
 PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6, PES_BRH2: 3}
 TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
@@ -22,6 +22,13 @@ PATH_AUTO, PATH_FUSED, PATH_SPLIT = 0, 1, 2
 ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM", -4: "CRCL_ECUDA",
           -5: "CRCL_ENOSUP", -6: "CRCL_ESTATE"}
 TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_PESWARN = 0, 1, 2, 5, 16
+
+class WaterParams(ctypes.Structure):
+    """crcl_water_params of include/caracal_gpu.h"""
+    _fields_ = [("n", ctypes.c_int), ("periodic", ctypes.c_int), ("zahn", ctypes.c_int), ("box", ctypes.c_double * 3),
+                ("coul_cut", ctypes.c_double), ("zahn_a", ctypes.c_double), ("zahn_par", ctypes.c_double),
+                ("pars", ctypes.c_double * 11), ("q", c_double_p), ("is_O", c_int_p)]
+
 
 class QmdffTables(ctypes.Structure):
     """crcl_qmdff_tables of include/caracal_gpu.h"""
@@ -68,6 +75,7 @@ SIGNATURES = {
     "crcl_set_dgevb": (ctypes.c_int, [_H, ctypes.POINTER(DgevbParams)]),
     "crcl_set_path": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_graph": (ctypes.c_int, [_H, ctypes.c_int]),
+    "crcl_set_water": (ctypes.c_int, [_H, ctypes.POINTER(WaterParams)]),
     "crcl_set_ewald": (ctypes.c_int, [_H, ctypes.POINTER(EwaldParams)]),
     "crcl_ewald_recip": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p,
                                         c_double_p]),

@@ -10,7 +10,7 @@ module caracal_gpu
 use, intrinsic :: iso_c_binding
 implicit none
 
-integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 3, CRCL_PES_BRH2 = 4
+integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 3, CRCL_PES_BRH2 = 4, CRCL_PES_WATER = 12
 integer(c_int), parameter :: CRCL_PES_QMDFF = 10, CRCL_PES_DGEVB = 11, CRCL_PES_HOSTCB = 100
 type(c_ptr), save :: crcl_h = c_null_ptr        ! one handle per MPI rank / GPU
 
@@ -36,6 +36,13 @@ type, bind(C) :: crcl_dgevb_params
    type(c_ptr) :: coord_def, point_int, alph, b_vec
    real(c_double) :: g_thres
 end type crcl_dgevb_params
+
+!     struct crcl_water_params (pes WATER_SPC: water_init.f90:53-107, set_periodic.f90:66-104)
+type, bind(C) :: crcl_water_params
+   integer(c_int) :: n, periodic, zahn
+   real(c_double) :: box(3), coul_cut, zahn_a, zahn_par, pars(11)
+   type(c_ptr) :: q, is_O
+end type crcl_water_params
 
 interface
    function crcl_create(h, device, natoms, nbeads, mass, at_move, beta, dt, pes_id) bind(C, name="crcl_create")
@@ -201,6 +208,21 @@ interface
       type(crcl_dgevb_params), intent(in) :: P
       integer(c_int) :: crcl_set_dgevb
    end function crcl_set_dgevb
+
+   ! egrad_water(xyz_act,g_act,e_act) (egrad_water.f90:36): tables once, then crcl_egrad(..., CRCL_PES_WATER, ...)
+   function crcl_set_water(h, P) bind(C, name="crcl_set_water")
+      import :: c_ptr, c_int, crcl_water_params
+      type(c_ptr), value :: h
+      type(crcl_water_params), intent(in) :: P
+      integer(c_int) :: crcl_set_water
+   end function crcl_set_water
+   ! HBM-resident path: CUDA-graph replay of steps 2..n of one multi-step call (default on)
+   function crcl_set_graph(h, on) bind(C, name="crcl_set_graph")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int), value :: on
+      integer(c_int) :: crcl_set_graph
+   end function crcl_set_graph
 
    ! custom_grad / external_grad stay on the host: fn(xyz, e, g, natoms, user) is called per bead
    function crcl_set_host_gradient_cb(h, fn, user) bind(C, name="crcl_set_host_gradient_cb")

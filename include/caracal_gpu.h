@@ -39,6 +39,7 @@ extern "C" {
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
                              crcl_set_qmdff2, crcl_set_dgevb */
+#define CRCL_PES_WATER 12 /* flexible SPC water box, pes WATER_SPC (gradient.f90:212-213 -> egrad_water.f90): crcl_set_water */
 #define CRCL_PES_HOSTCB 100 /* custom_grad / external_grad stay on the host (callback)  */
 
 /* error codes */
@@ -170,6 +171,22 @@ typedef struct crcl_dgevb_params {
     double g_thres;
 } crcl_dgevb_params;
 int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params *P);
+
+/* Flexible SPC water box (pes WATER_SPC): what water_init.f90:53-107 and set_periodic.f90:66-104 leave in the modules.
+ * n = 3 nwater atoms ordered O,H,H per molecule; pars = water_pars(1:11) in atomic units (r_0, r_0HH, D_e, a, k_theta,
+ * k_rtheta, k_rr, e_H, e_O, sigma_OO, eps_OO); q(n) the charges laid out by water_init.f90:103-107; is_O(n) = name(i)=="O".
+ * Then crcl_egrad(..., CRCL_PES_WATER, ...) replaces egrad_water(xyz_act,g_act,e_act) (egrad_water.f90:36), and the
+ * integrator runs on the HBM-resident path with it.  Host pointers, copied. */
+typedef struct crcl_water_params {
+    int n;
+    int periodic, zahn;
+    double box[3];
+    double coul_cut, zahn_a, zahn_par;
+    double pars[11];
+    const double *q;
+    const int *is_O;
+} crcl_water_params;
+int crcl_set_water(crcl_handle h, const crcl_water_params *P);
 
 /* Smooth particle-mesh Ewald, reciprocal-space part (ewald_recip.f90:30-470).  The set-up quantities
  * are those of module pbc_mod after set_periodic.f90:114-231: boxlen_x/y/z (bohr), a_ewald, nfft (one

@@ -419,3 +419,42 @@ class Ewald:
         g = np.zeros_like(x)
         self.L.orc_ewald_direct_recip(_d(self.box), self.a_ewald, int(mmax), len(qq), _d(x), _d(qq), ctypes.byref(e), _d(g))
         return e.value, g
+
+
+class _WaterStruct(ctypes.Structure):
+    _fields_ = [("natoms", ctypes.c_int), ("periodic", ctypes.c_int), ("zahn", ctypes.c_int),
+                ("box", ctypes.c_double * 3), ("coul_cut", ctypes.c_double), ("zahn_a", ctypes.c_double),
+                ("zahn_par", ctypes.c_double), ("pars", ctypes.c_double * 11), ("q", dp), ("is_O", ip)]
+
+
+def water_default_pars():
+    """water_init.f90:75-101: the eleven parameters in atomic units"""
+    p = (ctypes.c_double * 11)()
+    lib().orc_water_default_pars(p)
+    return np.array(list(p))
+
+
+class Water:
+    """Oracle of egrad_water.f90 (pes WATER_SPC).  W: dict(n, periodic, zahn, box, coul_cut, zahn_a, zahn_par, pars,
+    q, is_O) -- what water_init.f90 and set_periodic.f90 leave in the modules."""
+
+    def __init__(self, W):
+        self.L = lib()
+        self.n = int(W["n"])
+        self.keep = dict(q=np.ascontiguousarray(W["q"], dtype=np.float64),
+                         o=np.ascontiguousarray(W["is_O"], dtype=np.int32))
+        S = _WaterStruct()
+        S.natoms, S.periodic, S.zahn = self.n, int(W["periodic"]), int(W["zahn"])
+        S.box = (ctypes.c_double * 3)(*[float(v) for v in W["box"]])
+        S.coul_cut, S.zahn_a, S.zahn_par = float(W["coul_cut"]), float(W["zahn_a"]), float(W["zahn_par"])
+        S.pars = (ctypes.c_double * 11)(*[float(v) for v in W["pars"]])
+        S.q, S.is_O = _d(self.keep["q"]), _i(self.keep["o"])
+        self.S = S
+        self.L.orc_water_egrad.argtypes = [ctypes.POINTER(_WaterStruct), dp, ctypes.c_int, dp, dp]
+
+    def egrad(self, xyz):
+        x = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, self.n, 3)
+        V = np.zeros(x.shape[0])
+        g = np.zeros_like(x)
+        self.L.orc_water_egrad(ctypes.byref(self.S), _d(x), x.shape[0], _d(V), _d(g))
+        return V, g

@@ -158,5 +158,27 @@ for nb, nsteps in ((1, 50), (8, 50)):
            cpu_bead_steps_per_s_one_core=1.0 / cpu_img)
     g.close()
 
+# ---- C5 (native water model): flexible SPC box, pes WATER_SPC, 1000 molecules, 31.07 A, Zahn ---------------
+from caracal_b200 import water as WT  # noqa: E402
+Wt = WT.water_box(1000, periodic_angstrom=[31.07] * 3)
+xw = WT.water_lattice(1000, 31.07, rng)
+mass = np.tile([C.atomic_mass_au("O"), C.atomic_mass_au("H"), C.atomic_mass_au("H")], 1000)
+Qw = O.Water(Wt)
+t0 = time.perf_counter()
+Qw.egrad(xw[None])
+cpu_img = time.perf_counter() - t0
+for nb, nsteps in ((1, 200), (8, 200)):
+    g = caracal_b200.RPMD(caracal_b200.PES_WATER, nb, mass, C.beta_calc_rate(300.0), C.dt_au(0.5))
+    g.set_water(Wt)
+    g.set_seed(C.SEED)
+    g.set_thermostat(1, 70, 300.0)
+    q = np.ascontiguousarray(xw[None, None] + rng.normal(0, 0.01, (1, nb) + xw.shape))
+    p, d, dxi, ev = g.mdinit(q, 0)
+    sec = timed(lambda: g.verlet(q, p, d, nsteps=nsteps, constrain=-1, event=ev), reps=2)
+    report(config="C5 flexible SPC water box (pes WATER_SPC) NVT, 3000 atoms, Zahn, %d bead(s), split path" % nb, ntraj=1,
+           steps=nsteps, gpu_bead_steps_per_s=nb * nsteps / sec, gpu_ms_per_step=1e3 * sec / nsteps,
+           cpu_bead_steps_per_s_one_core=1.0 / cpu_img)
+    g.close()
+
 if len(sys.argv) > 1:
     json.dump(rows, open(sys.argv[1], "w"), indent=1)
