@@ -77,16 +77,23 @@ struct TrajArgs {
 #ifndef CRCL_WTPB
 #define CRCL_WTPB 128
 #endif
+// Multi-warp trajectories (T > 32) are packed up to CRCL_CTPB threads to a CTA for the same reason; each trajectory
+// then synchronises on its own named barrier (bar.sync 1 + gib, T), because SHAKE's iteration count and the failure
+// paths are per trajectory, and barrier 0 re-aligns the whole CTA once per step.
+#ifndef CRCL_CTPB
+#define CRCL_CTPB 128
+#endif
 template <int NB, int LANES>
 struct Group {
     static constexpr int T = NB * LANES;
     static constexpr bool WARP = (T <= 32);
-    static constexpr int TPB = WARP ? CRCL_WTPB : T;      // threads per block
-    static constexpr int GPB = WARP ? CRCL_WTPB / T : 1;  // trajectories per block
-    // re-align the warps of a CTA of sub-warp trajectories (no-op for CTA-wide trajectories, which synchronise anyway)
+    static constexpr int CPB = (CRCL_CTPB / T > 1) ? (CRCL_CTPB / T < 15 ? CRCL_CTPB / T : 15) : 1;   // 15 named barriers
+    static constexpr int TPB = WARP ? CRCL_WTPB : T * CPB;  // threads per block
+    static constexpr int GPB = WARP ? CRCL_WTPB / T : CPB;  // trajectories per block
+    // re-align the warps of a CTA that holds several trajectories (one barrier per step)
     static __device__ __forceinline__ void align_warps()
     {
-        if (WARP && CRCL_WTPB > 32) __syncthreads();
+        if (WARP ? (CRCL_WTPB > 32) : (GPB > 1)) __syncthreads();
     }
     int tig, bead, lane, gib;                      // thread in group, bead, lane of the bead, group in block
     unsigned mask;
@@ -110,8 +117,10 @@ struct Group {
     {
         if (WARP)
             __syncwarp(mask);
-        else
+        else if (GPB == 1)
             __syncthreads();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(gib + 1), "r"(T) : "memory");
     }
     // all-reduce sum over the threads of the trajectory; every thread gets the same bits
     __device__ __forceinline__ double sum(double v) const
@@ -123,12 +132,12 @@ struct Group {
         } else {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            __syncthreads();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-            __syncthreads();
+            sync();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;   // red is indexed by the warp's number in the CTA
+            sync();
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < T / 32; w++) t += red[w];
+            for (int w = 0; w < T / 32; w++) t += red[gib * (T / 32) + w];
             return t;
         }
     }
@@ -136,8 +145,18 @@ struct Group {
     {
         if (WARP)
             return __any_sync(mask, pred);
-        else
+        else if (GPB == 1)
             return __syncthreads_or(pred);
+        else {
+            const int w = __any_sync(0xffffffffu, pred);
+            sync();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w ? 1.0 : 0.0;
+            sync();
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < T / 32; k++) t += red[gib * (T / 32) + k];
+            return t != 0.0;
+        }
     }
 };
 
@@ -233,8 +252,8 @@ struct Traj {
     __device__ __forceinline__ double& Pk(int k) { return pq[ob[k] + G.bead].x; }
     __device__ __forceinline__ double& Qk(int k) { return pq[ob[k] + G.bead].y; }
     // threads that hold a valid xi_real after a child step (umbrella mode 2), and the one that reports it
-    __device__ __forceinline__ bool xi_thread() const { return Grp::WARP || (int)threadIdx.x >= Grp::T - 32; }
-    __device__ __forceinline__ bool xi_writer() const { return Grp::WARP ? G.tig == 0 : (int)threadIdx.x == Grp::T - 32; }
+    __device__ __forceinline__ bool xi_thread() const { return Grp::WARP || G.tig >= Grp::T - 32; }
+    __device__ __forceinline__ bool xi_writer() const { return Grp::WARP ? G.tig == 0 : G.tig == Grp::T - 32; }
     __device__ __forceinline__ bool own(int k) const { return oc[k] >= 0; }
     __device__ __forceinline__ bool mov(int k) const { return (mv >> k) & 1u; }
 
@@ -723,8 +742,10 @@ struct LaunchCfg {
     static constexpr int TPB = Group<NB, PES::LANES>::TPB;
     // one-lane surfaces (H3, OH3): CRCL_MINB_L1 resident CTAs requested when a CTA is a single warp
     static constexpr bool WARP = Group<NB, PES::LANES>::WARP;
+    // lane-split surfaces on multi-warp trajectories: the CRCL_MINB_L4 x 64 threads of the single-wave tuning, whatever
+    // the packing (7 CTAs of 64 threads or 4 of 128: a 128-register cap either way)
     static constexpr int MINB = WARP ? ((PES::LANES > 1) ? 2 : (CRCL_MINB_L1 * 32 / CRCL_WTPB > 0 ? CRCL_MINB_L1 * 32 / CRCL_WTPB : 1))
-                                     : ((PES::LANES > 1 && TPB <= 128) ? CRCL_MINB_L4 : 1);
+                                     : ((PES::LANES > 1 && TPB <= 128) ? (CRCL_MINB_L4 * 64 / TPB > 0 ? (CRCL_MINB_L4 * 64 + TPB - 1) / TPB : 1) : 1);
 };
 
 // Free ring-polymer kernels into shared memory.  NB <= 32: the dense tables

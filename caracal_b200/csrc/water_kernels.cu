@@ -69,9 +69,50 @@ __global__ void __launch_bounds__(128) wat_intra_kernel(const WaterDev W, const 
     if ((threadIdx.x & 31) == 0) atomicAdd(&V[img], e);
 }
 
+// One pair (i, j) inside the cut-off: Coulomb (+ Lennard-Jones when atom i is an oxygen); adds to the warp lane's
+// partial force on i and energy, sends the reaction to j.
+__device__ __forceinline__ void wat_pair(const WaterDev& W, const double* __restrict__ x, double* __restrict__ gi, int j,
+                                         double xi0, double xi1, double xi2, double qi, bool oi, double& f0, double& f1,
+                                         double& f2, double& e)
+{
+    double d0 = xi0 - x[3 * j], d1 = xi1 - x[3 * j + 1], d2 = xi2 - x[3 * j + 2];
+    if (W.periodic) {
+        d0 = wat_image(d0, W.box[0], 0.5 * W.box[0]);
+        d1 = wat_image(d1, W.box[1], 0.5 * W.box[1]);
+        d2 = wat_image(d2, W.box[2], 0.5 * W.box[2]);
+    }
+    const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    const double oner = 1.0 / r;
+    double e0;
+    if (W.zahn)
+        e0 = qi * W.q[j] * ((erfc(W.zahn_a * r) * oner) - W.zahn_par * (r - W.coul_cut));
+    else
+        e0 = qi * W.q[j] * oner;
+    double s = e0 * oner * oner;
+    e += e0;
+    if (oi) {
+        const double sig = W.pars[9], eps = W.pars[10];
+        const double s2 = (sig * oner) * (sig * oner), s6 = s2 * s2 * s2;
+        e += 4.0 * eps * (s6 * s6 - s6);
+        s += 24.0 * eps * oner * oner * s6 * (2.0 * s6 - 1.0);
+    }
+    const double g0 = s * d0, g1 = s * d1, g2 = s * d2;
+    f0 -= g0;
+    f1 -= g1;
+    f2 -= g2;
+    atomicAdd(&gi[3 * j], g0);
+    atomicAdd(&gi[3 * j + 1], g1);
+    atomicAdd(&gi[3 * j + 2], g2);
+}
+
+// The sweep over j > i is split in a cheap test (minimum image, r < cut: ~14 % of the pairs of a 31 A box survive) and
+// the expensive evaluation (erfc, divisions).  Survivors are compacted into a per-warp queue (ballot + popc) and
+// evaluated 32 at a time with all lanes busy; without the queue nearly every warp iteration paid for the expensive
+// path because some lane is always inside the cut-off (same scheme as qm_inter_kernel).
 __global__ void __launch_bounds__(128) wat_inter_kernel(const WaterDev W, const double* __restrict__ xyz, int nimg,
                                                         double* __restrict__ V, double* __restrict__ g)
 {
+    __shared__ int queue[4][64];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int i = blockIdx.x * (blockDim.x >> 5) + wib, img = blockIdx.y;
     if (i >= W.n - 1) return;                       // whole warps leave together; the last atom has no j > i
@@ -80,41 +121,34 @@ __global__ void __launch_bounds__(128) wat_inter_kernel(const WaterDev W, const 
     const double xi0 = x[3 * i], xi1 = x[3 * i + 1], xi2 = x[3 * i + 2], qi = W.q[i];
     const bool oi = W.is_O[i] != 0;
     const int mi = i / 3;
-    const double sig = W.pars[9], eps = W.pars[10];
-    const double L0 = W.box[0], L1 = W.box[1], L2 = W.box[2];
+    int* q = queue[wib];
+    int cnt = 0;                                    // warp-uniform
     double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
-    for (int j = i + 1 + lane; j < W.n; j += 32) {
-        if (j / 3 == mi) continue;
-        double d0 = xi0 - x[3 * j], d1 = xi1 - x[3 * j + 1], d2 = xi2 - x[3 * j + 2];
-        if (W.periodic) {
-            d0 = wat_image(d0, L0, 0.5 * L0);
-            d1 = wat_image(d1, L1, 0.5 * L1);
-            d2 = wat_image(d2, L2, 0.5 * L2);
-        }
-        const double r = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-        if (r < W.coul_cut || !W.periodic) {
-            const double oner = 1.0 / r;
-            double e0;
-            if (W.zahn)
-                e0 = qi * W.q[j] * ((erfc(W.zahn_a * r) * oner) - W.zahn_par * (r - W.coul_cut));
-            else
-                e0 = qi * W.q[j] * oner;
-            double s = e0 * oner * oner;
-            e += e0;
-            if (oi) {
-                const double s2 = (sig * oner) * (sig * oner), s6 = s2 * s2 * s2;
-                e += 4.0 * eps * (s6 * s6 - s6);
-                s += 24.0 * eps * oner * oner * s6 * (2.0 * s6 - 1.0);
+    for (int j0 = i + 1; j0 < W.n; j0 += 32) {
+        const int j = j0 + lane;
+        bool in = false;
+        if (j < W.n && j / 3 != mi) {
+            double d0 = xi0 - x[3 * j], d1 = xi1 - x[3 * j + 1], d2 = xi2 - x[3 * j + 2];
+            if (W.periodic) {
+                d0 = wat_image(d0, W.box[0], 0.5 * W.box[0]);
+                d1 = wat_image(d1, W.box[1], 0.5 * W.box[1]);
+                d2 = wat_image(d2, W.box[2], 0.5 * W.box[2]);
             }
-            const double g0 = s * d0, g1 = s * d1, g2 = s * d2;
-            f0 -= g0;
-            f1 -= g1;
-            f2 -= g2;
-            atomicAdd(&gi[3 * j], g0);
-            atomicAdd(&gi[3 * j + 1], g1);
-            atomicAdd(&gi[3 * j + 2], g2);
+            in = (sqrt(d0 * d0 + d1 * d1 + d2 * d2) < W.coul_cut) || !W.periodic;   // egrad_water.f90:268, exact
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        if (in) q[cnt + __popc(m & ((1u << lane) - 1u))] = j;
+        cnt += __popc(m);
+        __syncwarp();
+        if (cnt >= 32) {
+            wat_pair(W, x, gi, q[lane], xi0, xi1, xi2, qi, oi, f0, f1, f2, e);
+            __syncwarp();
+            cnt -= 32;
+            if (lane < cnt) q[lane] = q[32 + lane];
+            __syncwarp();
         }
     }
+    if (lane < cnt) wat_pair(W, x, gi, q[lane], xi0, xi1, xi2, qi, oi, f0, f1, f2, e);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         f0 += __shfl_xor_sync(0xffffffffu, f0, o);

@@ -102,41 +102,44 @@ for kelvin in (200.0, 300.0, 1000.0):
            cpu_bead_steps_per_s_one_core=cpu)
     g.close()
 
-# ---- C4: DG-EVB-QMDFF RPMD, 32 beads, child trajectories on the split path ---------------------------
-# (the only DG-EVB fixture the reference ships needs evbopt.x output; synthetic 9-atom two-state system)
-T1, T2, E = make_dgevb(seed=5, mode=3, npoints=7)
-nb, ntraj, nsteps = 32, 256, 100
-mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O"}[int(z)]) for z in T1["at"]])
-beta, dt = C.beta_calc_rate(300.0), C.dt_au(0.2)
-g = caracal_b200.RPMD(caracal_b200.PES_DGEVB, nb, mass, beta, dt)
-g.set_qmdff(T1)
-g.set_qmdff(T2, second=True)
-g.set_dgevb(E)
-g.set_seed(C.SEED)
-g.set_thermostat(1, 10, 300.0)
-q = np.ascontiguousarray(T1["xyz"][None, None] + rng.normal(0, 0.01, (ntraj, nb) + T1["xyz"].shape))
-p, d, dxi, ev = g.mdinit(q, 0)
-secs = {}
-for graph in (0, 1):
-    g.set_graph(graph)
-    secs[graph] = timed(lambda: g.verlet(q, p, d, nsteps=nsteps, constrain=-1, event=ev), reps=2)
-D = O.Dgevb(T1, T2, E)
-os_ = O.System(0, nb, mass, beta, dt)
-os_.set_custom_grad(lambda x: tuple(a[0] for a in D.egrad(x)))
-os_.q[:] = q[0]
-os_.set_rng(C.SEED, 0)
-os_.set_thermostat(1, 10, 300.0)
-os_.mdinit(0.0, 0)
-t0 = time.perf_counter()
-for i in range(1, 6):
-    os_.verlet(i, 0.0, -1)
-cpu = 5 * nb / (time.perf_counter() - t0)
-for graph in (0, 1):
-    report(config="C4 DG-EVB-QMDFF RPMD (2 x QMDFF + mode-3 coupling, 9 atoms synthetic) 32 beads, split path, "
-                  + ("CUDA-graph replay" if graph else "one launch per kernel"),
-           ntraj=ntraj, steps=nsteps, gpu_bead_steps_per_s=ntraj * nb * nsteps / secs[graph],
-           gpu_us_per_step=1e6 * secs[graph] / nsteps, cpu_bead_steps_per_s_one_core=cpu)
-g.close()
+# ---- C4: DG-EVB-QMDFF RPMD, 32 beads, on the split path -------------------------------------------------
+# (the only DG-EVB fixture the reference ships is the 6-atom examples/evbopt/DG-EVB, whose evb_pars.dat needs
+# evbopt.x; synthetic two-state systems: 9 atoms (ethanol-like) and SURVEY 8(d)'s 20 atoms / nat6 = 12 / 7 points)
+from tests.qmdff_synth import HEXANE  # noqa: E402
+for label, tpl in (("9 atoms", None), ("20 atoms, nat6 12", HEXANE)):
+    T1, T2, E = make_dgevb(seed=5, mode=3, npoints=7, template=tpl)
+    nb, ntraj, nsteps = 32, 256, 100
+    mass = np.array([C.atomic_mass_au({1: "H", 6: "C", 8: "O"}[int(z)]) for z in T1["at"]])
+    beta, dt = C.beta_calc_rate(300.0), C.dt_au(0.2)
+    g = caracal_b200.RPMD(caracal_b200.PES_DGEVB, nb, mass, beta, dt)
+    g.set_qmdff(T1)
+    g.set_qmdff(T2, second=True)
+    g.set_dgevb(E)
+    g.set_seed(C.SEED)
+    g.set_thermostat(1, 10, 300.0)
+    q = np.ascontiguousarray(T1["xyz"][None, None] + rng.normal(0, 0.01, (ntraj, nb) + T1["xyz"].shape))
+    p, d, dxi, ev = g.mdinit(q, 0)
+    secs = {}
+    for graph in (0, 1):
+        g.set_graph(graph)
+        secs[graph] = timed(lambda: g.verlet(q, p, d, nsteps=nsteps, constrain=-1, event=ev), reps=2)
+    D = O.Dgevb(T1, T2, E)
+    os_ = O.System(0, nb, mass, beta, dt)
+    os_.set_custom_grad(lambda x: tuple(a[0] for a in D.egrad(x)))
+    os_.q[:] = q[0]
+    os_.set_rng(C.SEED, 0)
+    os_.set_thermostat(1, 10, 300.0)
+    os_.mdinit(0.0, 0)
+    t0 = time.perf_counter()
+    for i in range(1, 6):
+        os_.verlet(i, 0.0, -1)
+    cpu = 5 * nb / (time.perf_counter() - t0)
+    for graph in (0, 1):
+        report(config="C4 DG-EVB-QMDFF RPMD (2 x QMDFF + mode-3 coupling, %s synthetic) 32 beads, split path, " % label
+                      + ("CUDA-graph replay" if graph else "one launch per kernel"),
+               ntraj=ntraj, steps=nsteps, gpu_bead_steps_per_s=ntraj * nb * nsteps / secs[graph],
+               gpu_us_per_step=1e6 * secs[graph] / nsteps, cpu_bead_steps_per_s_one_core=cpu)
+    g.close()
 
 # ---- C5: periodic QMDFF box NVT (~3000 atoms, Zahn, H bonds), classical and 8 beads ------------------
 T = make_system(nmol=385, seed=12, periodic=True, zahn=True, hb=True)

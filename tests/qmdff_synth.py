@@ -29,6 +29,39 @@ CHLOROMETHANE = dict(
     bonds=[(1, 2), (1, 3), (1, 4), (1, 5)], inversions=[])
 
 
+def _hexane():
+    """n-hexane, 20 atoms: zig-zag carbon chain (C1..C6 first), tetrahedral hydrogens; SURVEY.md 8(d) C4 asks for a
+    ~20-atom two-state system with nat6 = 12"""
+    cc, ch, th = 1.53, 1.09, np.deg2rad(111.5) / 2
+    C = np.array([[i * cc * np.sin(th), (i % 2) * cc * np.cos(th), 0.0] for i in range(6)])
+    xyz, bonds = list(C), [(i + 1, i + 2) for i in range(5)]
+    for i in range(6):
+        up = np.array([0.0, -1.0 if i % 2 == 0 else 1.0, 0.0])
+        hs = [up * 0.55 + np.array([0, 0, 0.83]), up * 0.55 - np.array([0, 0, 0.83])]
+        if i in (0, 5):
+            hs.append(np.array([-0.9 if i == 0 else 0.9, 0.5 * (1.0 if i % 2 == 0 else -1.0), 0.0]))
+        for h in hs:
+            xyz.append(C[i] + ch * h / np.linalg.norm(h))
+            bonds.append((i + 1, len(xyz)))
+    xyz = np.array(xyz)
+    # twist the all-trans chain about its three inner C-C bonds: dihedrals at exactly pi would put every torsion and
+    # dihedral internal coordinate on the ill-conditioned point of the reference's acos formulas
+    owner = list(range(6)) + [b[0] - 1 for b in bonds[5:]]          # carbon each atom hangs on
+    for k, deg in ((1, 55.0), (2, -70.0), (3, 40.0)):               # bond C(k+1)-C(k+2), 0-based k
+        a, b = xyz[k], xyz[k + 1]
+        u = (b - a) / np.linalg.norm(b - a)
+        t = np.deg2rad(deg)
+        K = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
+        Rm = np.eye(3) + np.sin(t) * K + (1 - np.cos(t)) * (K @ K)
+        for i in range(20):
+            if owner[i] > k:
+                xyz[i] = b + Rm @ (xyz[i] - b)
+    return dict(Z=[6] * 6 + [1] * 14, xyz=xyz, bonds=bonds, inversions=[])
+
+
+HEXANE = _hexane()
+
+
 def _topology(tpl):
     n = len(tpl["Z"])
     nb = {i: set() for i in range(1, n + 1)}
@@ -61,7 +94,7 @@ def _topology(tpl):
 
 
 def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_formaldehyde=0.25, hb=False,
-                frac_halogen=0.0):
+                frac_halogen=0.0, template=None):
     """hb=True adds the ff_hb tables (scalehb/scalexb, q_glob, an hb list); frac_halogen > 0 adds
     chloromethane molecules so that the X-bond branch (eabxag) runs."""
     rng = np.random.default_rng(seed)
@@ -75,6 +108,8 @@ def make_system(nmol=8, seed=0, periodic=True, zahn=True, box_A=None, frac_forma
     for m in range(nmol):
         u = rng.random()
         tpl = CHLOROMETHANE if u < frac_halogen else (FORMALDEHYDE if u < frac_halogen + frac_formaldehyde else ETHANOL)
+        if template is not None:
+            tpl = template
         n = len(tpl["Z"])
         A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
         cell = np.array([m % side, (m // side) % side, m // (side * side)]) * spacing + spacing / 2
@@ -169,14 +204,14 @@ def _hb_tables(hb, hbl, vhb, q):
                 scalehb=scalehb, scalexb=scalexb, q_glob=np.array(q))
 
 
-def make_dgevb(seed=0, mode=3, npoints=5):
+def make_dgevb(seed=0, mode=3, npoints=5, template=None):
     """A gas-phase two-state system: one ethanol-like molecule described by two QMDFFs with different
     parameters, a redundant-free internal coordinate set (bonds, angles, a dihedral, an out-of-plane)
     and random distributed-Gaussian parameters of the given mode (evb_pars.dat layout,
     read_pes.f90:2203-2225)."""
     from oracle import oracle as O
-    T1 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True)
-    T2 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True)
+    T1 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True, template=template)
+    T2 = make_system(nmol=1, seed=seed, periodic=False, frac_formaldehyde=0.0, hb=True, template=template)
     rng = np.random.default_rng(seed + 100)
     T2 = dict(T2)
     T2["vbond"] = T1["vbond"] * rng.uniform(0.9, 1.1, T1["vbond"].shape)
@@ -189,6 +224,10 @@ def make_dgevb(seed=0, mode=3, npoints=5):
     coord_def = np.array([[1, 1, 2, 0, 0], [1, 2, 3, 0, 0], [1, 1, 4, 0, 0], [1, 3, 9, 0, 0], [1, 2, 7, 0, 0],
                           [2, 1, 2, 3, 0], [2, 2, 3, 9, 0], [2, 4, 1, 2, 0], [3, 4, 1, 2, 3], [3, 1, 2, 3, 9],
                           [4, 3, 7, 8, 2]], dtype=np.int32)
+    if template is HEXANE:   # 5 C-C bonds, a C-H bond, 3 C-C-C angles, 3 C-C-C-C dihedrals: nat6 = 12
+        coord_def = np.array([[1, 1, 2, 0, 0], [1, 2, 3, 0, 0], [1, 3, 4, 0, 0], [1, 4, 5, 0, 0], [1, 5, 6, 0, 0],
+                              [1, 3, 11, 0, 0], [2, 1, 2, 3, 0], [2, 2, 3, 4, 0], [2, 3, 4, 5, 0], [3, 1, 2, 3, 4],
+                              [3, 2, 3, 4, 5], [3, 3, 4, 5, 6]], dtype=np.int32)
     nat6 = len(coord_def)
     E = dict(mode=mode, coord_def=coord_def, g_thres=1e-10)
     tmp = O.Dgevb(T1, T2, dict(E, point_int=np.zeros((1, nat6)), alph=np.ones(1), b_vec=np.zeros(4000)))

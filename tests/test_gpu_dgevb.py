@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from tests import common as C
-from tests.qmdff_synth import make_dgevb
+from tests.qmdff_synth import HEXANE, make_dgevb
 from tests.test_gpu_qmdff import torsion_conditioning
 
 pytestmark = pytest.mark.gpu
@@ -107,3 +107,22 @@ def test_rpmd_with_dgevb_on_split_path(gpu, oracle):
     assert np.abs(q[0] - o.q).max() < C.TOL_QP
     assert (np.abs(p[0] - o.p) / np.abs(o.p).max()).max() < C.TOL_QP
     assert abs(ep[0] - epo) < 1e-9 * max(1.0, abs(epo))
+
+
+def test_twenty_atom_two_state_system_matches_oracle(gpu, oracle):
+    """BASELINE config 4's shape: ~20 atoms (n-hexane-like: 19 bonds, 36 angles, 45 torsions, 135
+    nci pairs), 7 distributed Gaussians, mode 3, nat6 = 12 with three dihedral internal coordinates."""
+    T1, T2, E = make_dgevb(seed=5, mode=3, npoints=7, template=HEXANE)
+    assert T1["n"] == 20 and len(E["coord_def"]) == 12
+    g, _ = handle(gpu, T1, T2, E)
+    D = oracle.Dgevb(T1, T2, E)
+    rng = np.random.default_rng(2)
+    x = T1["xyz"][None] + rng.normal(0, 0.04, (48,) + T1["xyz"].shape)
+    Vo, go = D.egrad(x)
+    Vd, gd, _ = g.egrad(x)
+    assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
+    tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T1, x) ** 2)
+    tol = np.maximum(tol, 4e-12 / wilson_conditioning(E, x))
+    err = C.rel_err_G(gd.reshape(go.shape), go)
+    assert (err < tol).all(), (err / tol).max()
+    assert (tol < 1e-9).mean() > 0.8
