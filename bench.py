@@ -158,6 +158,15 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # the contract is ONE JSON line on stdout: libraries that write to the C-level stdout (NCCL prints its version
+    # banner there) are sent to stderr for the duration of the run, the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -176,7 +185,7 @@ def main():
         O.build()
         qp = make_parents_cpu()
         val, sec, sample = run_cpu_reference(qp, args.steps, max(args.warmup, 1), cores)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -184,7 +193,7 @@ def main():
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "C restatement (oracle/) of the reference's Fortran path; gfortran/MPI/FFTW are absent, the "
-                    "reference itself cannot be built (SURVEY.md F1)"}))
+                    "reference itself cannot be built (SURVEY.md F1)"})
         return 0
 
     import torch
@@ -313,7 +322,8 @@ def main():
                    "d2h_bytes_per_step": int(8 * (CHILD_EVOL + 1) + 4 * NPAIRS * 2)},
            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
            "kernel_ms": {"mean": kernel_ms, "n": int(len(kms)), "share_of_step": kernel_ms / (elapsed_ms / args.steps)}}
-    print(json.dumps(out))
+    if rank == 0:
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
     return 0

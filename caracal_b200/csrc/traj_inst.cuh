@@ -74,5 +74,8 @@ CRCL_DECLARE_TRAJ(launch_ch4h_recross);
 CRCL_DECLARE_TRAJ(launch_brh2_verlet);
 CRCL_DECLARE_TRAJ(launch_brh2_mdinit);
 CRCL_DECLARE_TRAJ(launch_brh2_recross);
+CRCL_DECLARE_TRAJ(launch_o3_verlet);
+CRCL_DECLARE_TRAJ(launch_o3_mdinit);
+CRCL_DECLARE_TRAJ(launch_o3_recross);
 
 }  // namespace crcl

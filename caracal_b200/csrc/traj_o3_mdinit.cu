@@ -1,0 +1,6 @@
+// traj_o3_mdinit.cu -- instantiates the mdinit trajectory kernels for the "o3" surface.
+#include "pes_o3.cuh"
+#include "traj_inst.cuh"
+namespace crcl {
+CRCL_DECLARE_TRAJ(launch_o3_mdinit) { return launch_traj_pes<PesO3, K_MDINIT>(nbeads, A, bias_mode, nose_q, s, nosup); }
+}  // namespace crcl

@@ -10,6 +10,7 @@ cnt_counters g_cnt = {0, 0, 0, 0, 0, 0};
 #include "pes_oh3.c"
 #include "pes_ch4h.c"
 #include "pes_brh2.c"
+#include "pes_o3.c"
 
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
@@ -47,7 +48,9 @@ int main()
     census("oh3", oracle_egrad_oh3_real, 4, oh3, 2000, false);
     const double brh2[9] = {0, 0, 0, 0, 0, -2.72158888, 0, 0, 2.64056088};
     census("ch4h", oracle_egrad_ch4h_real, 6, ch5, 2000, false);
-    census("brh2", oracle_egrad_brh2_real, 3, brh2, 2000, true);
+    const double o3[9] = {0, 0, 0, 1.60 / b, 0, 0, -0.4017 / b, 1.2364 / b, 0};
+    census("brh2", oracle_egrad_brh2_real, 3, brh2, 2000, false);
+    census("o3", oracle_egrad_o3_real, 3, o3, 2000, true);
     printf("}\n");
     return 0;
 }

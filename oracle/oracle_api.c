@@ -43,6 +43,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_OH3: oracle_egrad_oh3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_CH4H: oracle_egrad_ch4h_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_BRH2: oracle_egrad_brh2_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_O3: oracle_egrad_o3_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

@@ -18,6 +18,7 @@
 #define ORC_PES_OH3 2
 #define ORC_PES_CH4H 3
 #define ORC_PES_BRH2 4
+#define ORC_PES_O3 5
 
 #ifdef __cplusplus
 extern "C" {

@@ -37,6 +37,13 @@ def brh2_ts():
     return np.array([[0, 0, 0], [0, 0, -2.72158888], [0, 0, 2.64056088]])
 
 
+def o3_ts():
+    """the shallow C2v minimum of the 1 1A" surface (oracle: r = 1.35709 A, 105.25 deg, +10.17 kcal/mol above
+    O + O2), stretched along one bond towards O + O2; central atom first"""
+    r1, r2, th = 1.60 / BOHR, 1.30 / BOHR, np.deg2rad(108.0)
+    return np.array([[0, 0, 0], [r1, 0, 0], [r2 * np.cos(th), r2 * np.sin(th), 0]])
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -46,6 +53,9 @@ SYSTEMS = {
     "brh2": dict(pes="brh2", symbols=["H", "BR", "H"], ts=brh2_ts,
                  # Br + H2 -> HBr + H: reactant1 2, reactant2 1 3, bond_form 2-1, bond_break 1-3
                  mecha=dict(bond_form=[[2, 1]], bond_break=[[1, 3]], reactants=[[2], [1, 3]], dist_inf=16.0)),
+    "o3": dict(pes="o3", symbols=["O", "O", "O"], ts=o3_ts,
+               # O + O2 exchange: the bond 1-2 breaks (atom 2 leaves), fragments O2 (1,3) and O (2); bond_form 2-3
+               mecha=dict(bond_form=[[2, 3]], bond_break=[[1, 2]], reactants=[[1, 3], [2]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

@@ -32,6 +32,8 @@ CASES = [
     ("brh2", 16, 0, 1, 40, 2, 0.9, 15.0, 3),      # DIM-3C Br + H2, umbrella window
     ("brh2", 8, 1, 1, 31, 2, 0.98, 15.0, 2),      # constrained parent
     ("brh2", 32, 2, 0, 0, 2, 0.98, 0.0, 3),       # child trajectories
+    ("o3", 16, 0, 1, 40, 2, 0.9, 15.0, 3),        # O3 1 1A" PIP surface, umbrella window
+    ("o3", 8, 2, 0, 0, 2, 0.98, 0.0, 4),          # child trajectories
 ]
 
 
