@@ -649,10 +649,27 @@ struct Traj {
             t[1][1] += 0.000001;
             t[2][2] += 0.000001;
         }
-        if (invert3(t)) return 1;
+        // invert.f90's full-pivot Gauss-Jordan keeps its pivot bookkeeping in (local-memory) arrays: on trajectories of
+        // a warp or more one thread inverts and publishes the angular velocity (same arithmetic, 1/T of the traffic)
         double vang[3];
+        if (Grp::T >= 32) {
+            if (G.tig == 0) {
+                const int sing = invert3(t);
 #pragma unroll
-        for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
+                for (int i = 0; i < 3; i++) xis[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
+                xis[3] = sing ? 1.0 : 0.0;
+            }
+            G.sync();
+            const bool sing = xis[3] != 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) vang[i] = xis[i];
+            G.sync();
+            if (sing) return 1;
+        } else {
+            if (invert3(t)) return 1;
+#pragma unroll
+            for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
+        }
 #pragma unroll
         for (int k = 0; k < NO; k++)
             if (oc[k] >= 0) {
