@@ -754,6 +754,13 @@ struct Traj {
 #ifndef CRCL_MINB_L1
 #define CRCL_MINB_L1 12
 #endif
+// one-lane surfaces on multi-warp trajectories (OH + H2 x 64 beads: 12 components per thread, four accumulators
+// each in the free ring-polymer step): resident 128-thread CTAs requested.  4 (128 registers instead of the 220 the
+// compiler takes unbounded, 184 bytes of spills) puts the 512 CTAs of 1024 child trajectories in one wave instead of
+// 1.7: 12.9 -> 11.7 ms per 500 steps (3: 13.0 ms)
+#ifndef CRCL_MINB_C1
+#define CRCL_MINB_C1 4
+#endif
 template <class PES, int NB>
 struct LaunchCfg {
     static constexpr int TPB = Group<NB, PES::LANES>::TPB;
@@ -762,7 +769,8 @@ struct LaunchCfg {
     // lane-split surfaces on multi-warp trajectories: the CRCL_MINB_L4 x 64 threads of the single-wave tuning, whatever
     // the packing (7 CTAs of 64 threads or 4 of 128: a 128-register cap either way)
     static constexpr int MINB = WARP ? ((PES::LANES > 1) ? 2 : (CRCL_MINB_L1 * 32 / CRCL_WTPB > 0 ? CRCL_MINB_L1 * 32 / CRCL_WTPB : 1))
-                                     : ((PES::LANES > 1 && TPB <= 128) ? (CRCL_MINB_L4 * 64 / TPB > 0 ? (CRCL_MINB_L4 * 64 + TPB - 1) / TPB : 1) : 1);
+                                     : ((PES::LANES > 1 && TPB <= 128) ? (CRCL_MINB_L4 * 64 / TPB > 0 ? (CRCL_MINB_L4 * 64 + TPB - 1) / TPB : 1)
+                                                                       : ((PES::LANES == 1 && TPB <= 128) ? CRCL_MINB_C1 : 1));
 };
 
 // Free ring-polymer kernels into shared memory.  NB <= 32: the dense tables
