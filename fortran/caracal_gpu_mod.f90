@@ -44,6 +44,13 @@ type, bind(C) :: crcl_water_params
    type(c_ptr) :: q, is_O
 end type crcl_water_params
 
+!     struct crcl_ewald_params (pbc_mod after set_periodic.f90:114-231)
+type, bind(C) :: crcl_ewald_params
+   real(c_double) :: box(3), a_ewald
+   integer(c_int) :: nfft, bsorder
+   type(c_ptr) :: bsmod1, bsmod2, bsmod3
+end type crcl_ewald_params
+
 interface
    function crcl_create(h, device, natoms, nbeads, mass, at_move, beta, dt, pes_id) bind(C, name="crcl_create")
       import :: c_ptr, c_int, c_double
@@ -223,6 +230,57 @@ interface
       integer(c_int), value :: on
       integer(c_int) :: crcl_set_graph
    end function crcl_set_graph
+
+   ! calc_xi(coords,xi_ideal,xi_act,dxi_act,d2xi_act,mode) (calc_xi.f90:63) for ncoord structures; d2xi may be c_null_ptr
+   function crcl_calc_xi(h, ncoord, coords, xi_ideal, mode, xi, dxi, d2xi) bind(C, name="crcl_calc_xi")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: ncoord, mode
+      real(c_double), dimension(*), intent(in) :: coords, xi_ideal
+      real(c_double), dimension(*), intent(out) :: xi, dxi
+      type(c_ptr), value :: d2xi
+      integer(c_int) :: crcl_calc_xi
+   end function crcl_calc_xi
+   ! ewald_recip(n,xyz,q,energy,grad) (ewald_recip.f90:30) for nimg structures
+   function crcl_set_ewald(h, P) bind(C, name="crcl_set_ewald")
+      import :: c_ptr, c_int, crcl_ewald_params
+      type(c_ptr), value :: h
+      type(crcl_ewald_params), intent(in) :: P
+      integer(c_int) :: crcl_set_ewald
+   end function crcl_set_ewald
+   function crcl_ewald_recip(h, n, nimg, xyz, q, energy, grad) bind(C, name="crcl_ewald_recip")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: n, nimg
+      real(c_double), dimension(*), intent(in) :: xyz, q
+      real(c_double), dimension(*), intent(out) :: energy, grad
+      integer(c_int) :: crcl_ewald_recip
+   end function crcl_ewald_recip
+   ! 0: the rfft / irfft pair as written (SURVEY.md F2), 1: true normal-mode transform
+   function crcl_set_transform(h, mode) bind(C, name="crcl_set_transform")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int), value :: mode
+      integer(c_int) :: crcl_set_transform
+   end function crcl_set_transform
+   ! 0 automatic, 1 fused in-register kernels, 2 HBM-resident path
+   function crcl_set_path(h, path) bind(C, name="crcl_set_path")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int), value :: path
+      integer(c_int) :: crcl_set_path
+   end function crcl_set_path
+   function crcl_synchronize(h) bind(C, name="crcl_synchronize")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int) :: crcl_synchronize
+   end function crcl_synchronize
+   ! text of the last error of this handle (NUL-terminated C string)
+   function crcl_last_error(h) bind(C, name="crcl_last_error")
+      import :: c_ptr
+      type(c_ptr), value :: h
+      type(c_ptr) :: crcl_last_error
+   end function crcl_last_error
 
    ! custom_grad / external_grad stay on the host: fn(xyz, e, g, natoms, user) is called per bead
    function crcl_set_host_gradient_cb(h, fn, user) bind(C, name="crcl_set_host_gradient_cb")
