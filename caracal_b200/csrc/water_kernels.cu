@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(128) wat_inter_kernel(const WaterDev W, const 
     int* q = queue[wib];
     int cnt = 0;                                    // warp-uniform
     double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0;
+    const double c2 = W.coul_cut * W.coul_cut, c2lo = c2 * (1.0 - 1e-12), c2hi = c2 * (1.0 + 1e-12);
     for (int j0 = i + 1; j0 < W.n; j0 += 32) {
         const int j = j0 + lane;
         bool in = false;
@@ -134,7 +135,10 @@ __global__ void __launch_bounds__(128) wat_inter_kernel(const WaterDev W, const 
                 d1 = wat_image(d1, W.box[1], 0.5 * W.box[1]);
                 d2 = wat_image(d2, W.box[2], 0.5 * W.box[2]);
             }
-            in = (sqrt(d0 * d0 + d1 * d1 + d2 * d2) < W.coul_cut) || !W.periodic;   // egrad_water.f90:268, exact
+            // egrad_water.f90:268 `r < cut`, exact: sqrt is monotone and correctly rounded, so only squared
+            // distances within 1e-12 of cut^2 need the FP64 square root of the reference's own test
+            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+            in = !W.periodic || r2 < c2lo || (r2 < c2hi && sqrt(r2) < W.coul_cut);
         }
         const unsigned m = __ballot_sync(0xffffffffu, in);
         if (in) q[cnt + __popc(m & ((1u << lane) - 1u))] = j;
