@@ -14,6 +14,7 @@
 #include "pes_ch4h.cuh"
 #include "pes_brh2.cuh"
 #include "pes_o3.cuh"
+#include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
 #include "split_xi.cuh"
@@ -273,12 +274,13 @@ __global__ void reduce_kappa_kernel(const unsigned char* theta, const double* we
 // ---- dispatch --------------------------------------------------------------------------------
 static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode = 0)
 {
-    static const traj_launch_fn table[5][3] = {
+    static const traj_launch_fn table[6][3] = {
         {launch_h3_verlet, launch_h3_mdinit, launch_h3_recross},
         {launch_oh3_verlet, launch_oh3_mdinit, launch_oh3_recross},
         {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross},
         {launch_brh2_verlet, launch_brh2_mdinit, launch_brh2_recross},
-        {launch_o3_verlet, launch_o3_mdinit, launch_o3_recross}};
+        {launch_o3_verlet, launch_o3_mdinit, launch_o3_recross},
+        {launch_ch4oh_verlet, launch_ch4oh_mdinit, launch_ch4oh_recross}};
     int row;
     switch (h->pes) {
     case CRCL_PES_H3: row = 0; break;
@@ -286,6 +288,7 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
     case CRCL_PES_CH4H: row = 2; break;
     case CRCL_PES_BRH2: row = 3; break;
     case CRCL_PES_O3: row = 4; break;
+    case CRCL_PES_CH4OH: row = 5; break;
     default: return fail(h, CRCL_ENOSUP, "no device trajectory kernel for this PES id");
     }
     if (A.ntraj <= 0) return CRCL_OK;
@@ -332,6 +335,7 @@ static int pes_natoms(int pes)
     case CRCL_PES_CH4H: return 6;
     case CRCL_PES_BRH2: return 3;
     case CRCL_PES_O3: return 3;
+    case CRCL_PES_CH4OH: return 7;
     }
     return -1;
 }
@@ -1308,6 +1312,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_CH4H: egrad_kernel<PesCH4H><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_BRH2: egrad_kernel<PesBrH2><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_O3: egrad_kernel<PesO3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_CH4OH: egrad_kernel<PesCH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     default: return fail(h, CRCL_ENOSUP, "unknown PES id");
     }
     if (h->timed) cudaEventRecord(h->ev1, h->stream);

@@ -70,9 +70,69 @@ CRCL_HD __forceinline__ double dot(const double a[3], const double b[3])
 
 }  // namespace ch4h
 
-struct PesCH4H {
-    static constexpr int NATOMS = 6;
-    static constexpr int ID = CRCL_PES_CH4H;
+namespace ch4h {
+// the namespace constants above as the constants struct of the one-lane template
+struct K6 {
+    static constexpr int NATOMS = 6, ID = CRCL_PES_CH4H;
+    static constexpr bool HAS_OH = false;
+    static constexpr double R0CH = ch4h::R0CH;
+    static constexpr double A1CH = ch4h::A1CH;
+    static constexpr double B1CH = ch4h::B1CH;
+    static constexpr double C1CH = ch4h::C1CH;
+    static constexpr double R0HH = ch4h::R0HH;
+    static constexpr double AHH = ch4h::AHH;
+    static constexpr double R0CB = ch4h::R0CB;
+    static constexpr double ACB = ch4h::ACB;
+    static constexpr double D1CH = ch4h::D1CH;
+    static constexpr double D3CH = ch4h::D3CH;
+    static constexpr double D1HH = ch4h::D1HH;
+    static constexpr double D3HH = ch4h::D3HH;
+    static constexpr double D1CB = ch4h::D1CB;
+    static constexpr double D3CB = ch4h::D3CB;
+    static constexpr double A3S = ch4h::A3S;
+    static constexpr double B3S = ch4h::B3S;
+    static constexpr double APHI = ch4h::APHI;
+    static constexpr double BPHI = ch4h::BPHI;
+    static constexpr double CPHI = ch4h::CPHI;
+    static constexpr double ATHETA = ch4h::ATHETA;
+    static constexpr double BTHETA = ch4h::BTHETA;
+    static constexpr double CTHETA = ch4h::CTHETA;
+    static constexpr double FCH3 = ch4h::FCH3;
+    static constexpr double HCH3 = ch4h::HCH3;
+    static constexpr double FKINF = ch4h::FKINF;
+    static constexpr double AK = ch4h::AK;
+    static constexpr double AA1 = ch4h::AA1;
+    static constexpr double AA2 = ch4h::AA2;
+    static constexpr double AA3 = ch4h::AA3;
+    static constexpr double AA4 = ch4h::AA4;
+    static constexpr double A1S = ch4h::A1S;
+    static constexpr double B1S = ch4h::B1S;
+    static constexpr double A2S = ch4h::A2S;
+    static constexpr double B2S = ch4h::B2S;
+    static constexpr double FKH2OEQ = 0.0, ALPH2O = 0.0, ANH2OEQ = 0.0;   // unused without HAS_OH
+};
+}  // namespace ch4h
+
+// K: the constants of one member of the CBE family (ch4h::K6 below, ch4oh::K7 in pes_ch4oh.cuh).  With K::HAS_OH the
+// abstracting atom is the oxygen of an OH radical (7 atoms) and the three terms egrad_ch4oh.f adds to the template
+// are evaluated too: O-H Morse bond (:616-659, :769-774), four H-O-H bends (:1059-1171); the switched C-O triplet
+// depth (:590-592) is the constant D3CB because the shipped BLOCK DATA has a3cb = 0 (:2104).
+template <class K>
+struct PesCBE1 {
+    static constexpr int NATOMS = K::NATOMS;
+    static constexpr int ID = K::ID;
+    // one-lane trajectory interface (traj_kernel.cuh): the thread of a bead owns all 3 NATOMS components
+    static constexpr int LANES = 1;
+    static constexpr int NOWN = 3 * NATOMS;
+    CRCL_HD static __forceinline__ int owned(int, int k) { return k; }
+    template <class QF>
+    CRCL_HD static __forceinline__ int eval_coop(QF qf, int, unsigned, double& V, double* gown)
+    {
+        double x[NOWN];
+#pragma unroll
+        for (int c = 0; c < NOWN; c++) x[c] = qf(c);
+        return eval(x, V, gown);
+    }
 
     // q, g: [atom][xyz] in bohr / hartree bohr^-1, atom order H, C, H, H, H, H_b
     // (nnc=2, nnb=6, nnh=3,4,5,1; egrad_ch4h.f:1852-1854)
@@ -111,6 +171,13 @@ struct PesCH4H {
                 }
             }
         }
+        double tno[3] = {0, 0, 0}, rno = 1.0;   // H(O) - O in Angstrom (coorden_ch4oh :351,:361)
+        if constexpr (K::HAS_OH) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) tno[d] = q[3 * 6 + d] * 0.52918 - q[3 * BA + d] * 0.52918;
+            rno = sqrt(dot(tno, tno));
+        }
+        double gO[3] = {0, 0, 0}, gBx[3] = {0, 0, 0};   // explicit vector parts on H(O) and on the abstracting atom
         // accumulators: dV/d(distance) and explicit vector parts
         double Dch[4] = {0, 0, 0, 0}, Dbh[4] = {0, 0, 0, 0}, Dcb = 0.0;
         double gH[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, gC[3] = {0, 0, 0};
@@ -120,53 +187,53 @@ struct PesCH4H {
         double s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
 #pragma unroll
         for (int x = 0; x < 4; x++) {
-            const double r = rch[x], dr = r - R0CH;
+            const double r = rch[x], dr = r - K::R0CH;
             double omt, ms2;
             {
-                const double u = r - B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
-                const double arg = A1S * dr * u8;
+                const double u = r - K::B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
+                const double arg = K::A1S * dr * u8;
                 if (arg < 19.0) {
                     one_minus_tanh(arg, omt, ms2);
                     s1[x] = omt;
-                    ds1[x] = A1S * (u8 + 8.0 * dr * u7) * ms2;
+                    ds1[x] = K::A1S * (u8 + 8.0 * dr * u7) * ms2;
                 } else {
                     s1[x] = 0.0;
                     ds1[x] = 0.0;
                 }
             }
             {
-                const double u = r - B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
-                const double arg = A2S * dr * u6;
+                const double u = r - K::B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
+                const double arg = K::A2S * dr * u6;
                 if (arg < 19.0) {
                     one_minus_tanh(arg, omt, ms2);
                     s2[x] = omt;
-                    ds2[x] = A2S * (u6 + 6.0 * dr * u5) * ms2;
+                    ds2[x] = K::A2S * (u6 + 6.0 * dr * u5) * ms2;
                 } else {
                     s2[x] = 0.0;
                     ds2[x] = 0.0;
                 }
             }
             {
-                const double u = r - B3S;
-                const double arg = A3S * dr * u * u;
+                const double u = r - K::B3S;
+                const double arg = K::A3S * dr * u * u;
                 if (arg < 19.0) {
                     one_minus_tanh(arg, omt, ms2);
                     s3[x] = omt;
-                    ds3[x] = A3S * (3.0 * r * r - 2.0 * r * (R0CH + 2.0 * B3S) + B3S * (B3S + 2.0 * R0CH)) * ms2;
+                    ds3[x] = K::A3S * (3.0 * r * r - 2.0 * r * (K::R0CH + 2.0 * K::B3S) + K::B3S * (K::B3S + 2.0 * K::R0CH)) * ms2;
                 } else {
                     s3[x] = 0.0;
                     ds3[x] = 0.0;
                 }
             }
             if (r < 3.8) {
-                const double u = r - CPHI, ex = exp(BPHI * u * u * u);
-                one_minus_tanh(APHI * dr * ex, omt, ms2);
+                const double u = r - K::CPHI, ex = exp(K::BPHI * u * u * u);
+                one_minus_tanh(K::APHI * dr * ex, omt, ms2);
                 sphi[x] = omt;
-                dsphi[x] = APHI * (1.0 + 3.0 * BPHI * dr * u * u) * ex * ms2;
-                const double v = r - CTHETA, ev = exp(BTHETA * v * v * v);
-                one_minus_tanh(ATHETA * dr * ev, omt, ms2);
+                dsphi[x] = K::APHI * (1.0 + 3.0 * K::BPHI * dr * u * u) * ex * ms2;
+                const double v = r - K::CTHETA, ev = exp(K::BTHETA * v * v * v);
+                one_minus_tanh(K::ATHETA * dr * ev, omt, ms2);
                 sth[x] = omt;
-                dsth[x] = ATHETA * (1.0 + 3.0 * BTHETA * dr * v * v) * ev * ms2;
+                dsth[x] = K::ATHETA * (1.0 + 3.0 * K::BTHETA * dr * v * v) * ev * ms2;
             } else {
                 sphi[x] = 0.0;
                 dsphi[x] = 0.0;
@@ -185,24 +252,24 @@ struct PesCH4H {
         // ---- stretching (stretch_ch4h): LEPS for each (C-H_i, C-H_b, H_b-H_i) triple ----
         {
             const double rav = (rch[0] + rch[1] + rch[2] + rch[3]) / 4.0;
-            const double arga = C1CH * (rav - R0CH);
+            const double arga = K::C1CH * (rav - K::R0CH);
             double ach, dach;  // dach = d ach / d rch_x (same for every x)
             if (arga < 19.0) {
                 double omt, ms2;
                 one_minus_tanh(arga, omt, ms2);
-                ach = A1CH + B1CH * (2.0 - omt) * 0.5;
-                dach = -B1CH * C1CH * 0.5 * ms2 * 0.25;
+                ach = K::A1CH + K::B1CH * (2.0 - omt) * 0.5;
+                dach = -K::B1CH * K::C1CH * 0.5 * ms2 * 0.25;
             } else {
-                ach = A1CH + B1CH;
+                ach = K::A1CH + K::B1CH;
                 dach = 0.0;
             }
-            const Leps cb = leps(D1CB, D3CB, ACB, rcb - R0CB);
+            const Leps cb = leps(K::D1CB, K::D3CB, K::ACB, rcb - K::R0CB);
             double Dach = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const double dr = rch[i] - R0CH;
-                const Leps ch = leps(D1CH, D3CH, ach, dr);
-                const Leps bh = leps(D1HH, D3HH, AHH, rbh[i] - R0HH);
+                const double dr = rch[i] - K::R0CH;
+                const Leps ch = leps(K::D1CH, K::D3CH, ach, dr);
+                const Leps bh = leps(K::D1HH, K::D3HH, K::AHH, rbh[i] - K::R0HH);
                 const double a = ch.vj, b = cb.vj, cc = bh.vj;
                 const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
                 en += ch.vq + cb.vq + bh.vq + vj;
@@ -230,7 +297,7 @@ struct PesCH4H {
                 const int j = (i + 1) & 3, k = (i + 2) & 3, l = (i + 3) & 3;
                 const double pj = s3[j], pk = s3[k], pl = s3[l];
                 const double sw = (1.0 - s3[i]) * pj * pk * pl;
-                const double fd = sw * FCH3, hd = sw * HCH3;
+                const double fd = sw * K::FCH3, hd = sw * K::HCH3;
                 // a = H_k - H_j, b = H_l - H_j (Angstrom), from unit vectors and lengths
                 double a[3], b[3], n[3];
 #pragma unroll
@@ -296,7 +363,7 @@ struct PesCH4H {
                 }
                 en += fd * sum2 + hd * sum4;
                 // force-constant derivatives (opforce_ch4h)
-                const double fs = FCH3 * sum2 + HCH3 * sum4;
+                const double fs = K::FCH3 * sum2 + K::HCH3 * sum4;
                 Dch[i] -= fs * ds3[i] * pj * pk * pl;
                 Dch[j] += fs * (1.0 - s3[i]) * ds3[j] * pk * pl;
                 Dch[k] += fs * (1.0 - s3[i]) * pj * ds3[k] * pl;
@@ -306,19 +373,19 @@ struct PesCH4H {
 
         // ---- in-plane bending (ipbend_ch4h, ipforce_ch4h) ----
         {
-            constexpr double f0 = FKINF + AK, f2 = FKINF;
+            constexpr double f0 = K::FKINF + K::AK, f2 = K::FKINF;
             double f1[4], df1c[4], df1h[4];
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                const double dr = rch[x] - R0CH, dh = rbh[x] - R0HH;
-                const double e1 = exp(-AA1 * rbh[x] * rbh[x]);
-                const double e2 = exp(-AA4 * dh * dh);
+                const double dr = rch[x] - K::R0CH, dh = rbh[x] - K::R0HH;
+                const double e1 = exp(-K::AA1 * rbh[x] * rbh[x]);
+                const double e2 = exp(-K::AA4 * dh * dh);
                 const double a1 = 1.0 - e1;
-                const double a2 = AA2 + AA3 * e2;
+                const double a2 = K::AA2 + K::AA3 * e2;
                 const double E = exp(-a2 * dr * dr);
                 f1[x] = a1 * E;
                 df1c[x] = -2.0 * dr * a1 * a2 * E;
-                df1h[x] = 2.0 * AA1 * rbh[x] * e1 * E + 2.0 * AA3 * AA4 * dh * e2 * dr * dr * a1 * E;
+                df1h[x] = 2.0 * K::AA1 * rbh[x] * e1 * E + 2.0 * K::AA3 * K::AA4 * dh * e2 * dr * dr * a1 * E;
             }
             constexpr int PI_[6] = {0, 0, 0, 1, 1, 2}, PJ_[6] = {1, 2, 3, 2, 3, 3};
             constexpr int PK_[6] = {2, 1, 1, 0, 0, 0}, PL_[6] = {3, 3, 2, 3, 2, 1};
@@ -327,11 +394,11 @@ struct PesCH4H {
                 const int i = PI_[p], j = PJ_[p], k = PK_[p], l = PL_[p];
                 const double fk0 = f0 + f0 * (s1[i] * s1[j] - 1.0) + (f0 - f2) * (s2[k] * s2[l] - 1.0);
                 const double ff = f1[i] * f1[j];
-                const double K = fk0 * ff;
+                const double Kf = fk0 * ff;
                 const double cs = dot(c[i], c[j]);
                 const double del = acos(cs) - theta0(i, j, k, l);
-                en += 0.5 * K * del * del;
-                const double w = K * del;                  // dV/d(delta)
+                en += 0.5 * Kf * del * del;
+                const double w = Kf * del;                 // dV/d(delta)
                 const double wc = -w / sqrt(1.0 - cs * cs);  // dV/d(cos)
                 const double fi = wc / rch[i], fj = wc / rch[j];
 #pragma unroll
@@ -353,6 +420,49 @@ struct PesCH4H {
             }
         }
 
+        if constexpr (K::HAS_OH) {
+            // ---- O-H Morse bond (stretch_ch4oh :616-621, :652-659, :769-774) ----
+            const double ex = exp(-K::AHH * (rno - K::R0HH)), om = 1.0 - ex;
+            en += K::D1HH * (om * om);
+            const double de = 2.0 * K::AHH * K::D1HH * om * ex / rno;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                gBx[d] -= de * tno[d];
+                gO[d] += de * tno[d];
+            }
+            // ---- H_i-O-H(O) bends, force constant switched off with r(O-H_i) (ipbend_ch4oh :1059-1171) ----
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double tb[3];   // the reference's tbh(i,:) = O - H_i
+#pragma unroll
+                for (int d = 0; d < 3; d++) tb[d] = -ubh[i][d] * rbh[i];
+                double cs = -dot(tno, tb) / (rno * rbh[i]);
+                cs = fmin(1.0, fmax(-1.0, cs));
+                const double dang = acos(cs) - K::ANH2OEQ;
+                const double arga = K::ALPH2O * (rbh[i] - K::R0HH);
+                double omt, ms2;
+                one_minus_tanh(arga, omt, ms2);
+                const double fk = (arga < 19.0) ? K::FKH2OEQ * omt : 0.0;
+                en += 0.5 * fk * dang * dang;
+                Dbh[i] += K::FKH2OEQ * K::ALPH2O * ms2 * (0.5 * dang * dang);   // dkdr is not guarded (:1104-1107)
+                const double dstda = fk * dang;
+                double pv[3], v1[3], v2[3];
+                cross(tno, tb, pv);
+                double rp = sqrt(dot(pv, pv));
+                if (rp < 1.0e-6) rp = 1.0e-6;
+                const double terma = dstda / (rbh[i] * rbh[i] * rp), termc = dstda / (rno * rno * rp);
+                cross(tb, pv, v1);
+                cross(tno, pv, v2);
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const double hi = -terma * v1[d], ho = -termc * v2[d];
+                    gH[i][d] += hi;
+                    gO[d] += ho;
+                    gBx[d] += -hi - ho;
+                }
+            }
+        }
+
         // ---- chain rule to Cartesians, unit conversion ----
         V = en * 0.03812;
         constexpr double GF = 0.0201723;
@@ -360,7 +470,7 @@ struct PesCH4H {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             double cC = gC[d] - Dcb * ucb[d];
-            double cB = Dcb * ucb[d];
+            double cB = Dcb * ucb[d] + gBx[d];
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 const double vc = Dch[x] * c[x][d], vb = Dbh[x] * ubh[x][d];
@@ -371,10 +481,13 @@ struct PesCH4H {
             g[3 * CA + d] = cC * GF;
             gB[d] = cB * GF;
             g[3 * BA + d] = gB[d];
+            if constexpr (K::HAS_OH) g[3 * 6 + d] = gO[d] * GF;
         }
         return 0;
     }
 };
+
+using PesCH4H = PesCBE1<ch4h::K6>;
 
 }  // namespace crcl
 

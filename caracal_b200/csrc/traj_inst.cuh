@@ -77,5 +77,8 @@ CRCL_DECLARE_TRAJ(launch_brh2_recross);
 CRCL_DECLARE_TRAJ(launch_o3_verlet);
 CRCL_DECLARE_TRAJ(launch_o3_mdinit);
 CRCL_DECLARE_TRAJ(launch_o3_recross);
+CRCL_DECLARE_TRAJ(launch_ch4oh_verlet);
+CRCL_DECLARE_TRAJ(launch_ch4oh_mdinit);
+CRCL_DECLARE_TRAJ(launch_ch4oh_recross);
 
 }  // namespace crcl

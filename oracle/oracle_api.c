@@ -34,6 +34,10 @@ void oracle_ch4h_parts(const double *q18, double parts[3], double *V)
 {
     oracle_ch4h_parts_real(q18, parts, V);
 }
+void oracle_ch4oh_parts(const double *q21, double parts[3], double *V)
+{
+    oracle_ch4oh_parts_real(q21, parts, V);
+}
 
 int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, double *dVdq)
 {
@@ -44,6 +48,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_CH4H: oracle_egrad_ch4h_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_BRH2: oracle_egrad_brh2_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_O3: oracle_egrad_o3_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_CH4OH: oracle_egrad_ch4oh_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

@@ -24,6 +24,13 @@
  *   PREPOT_ch4h      :1687-1796  ch4h_prepot (one-shot unit scaling applied at init here)
  *   BLOCK DATA       :1798-1888  constants (all d0 -> clean doubles)
  * The reference does not clamp acos / 1/sqrt(1-x^2) arguments; neither does the oracle.
+ *
+ * With -DCBE_CH4OH (set by pes_ch4oh.c, which includes this file) the same routines restate
+ * /root/reference/src/egrad_ch4oh.f (Espinosa-Garcia, Corchado, J. Chem. Phys. 112, 5731 (2000);
+ * CH4 + OH -> CH3 + H2O, 7 atoms): that file is this template with the "b" atom an oxygen, its own
+ * BLOCK DATA (:2066-2106), and three additions marked CBE_CH4OH below -- the C-O triplet depth
+ * switched on the mean C-H distance (:590-592, :681-699), the O-H Morse bond (:616-621, :644-659, :769-774)
+ * and the four H-O-H bends with a tanh-switched force constant (:1059-1171).
  */
 #include "oracle_real.h"
 #include "oracle.h"
@@ -36,6 +43,10 @@ typedef struct {
         b3s, aphi, bphi, cphi, atheta, btheta, ctheta, fch3, hch3, fkinf, ak, bk, aa1, aa2, aa3,
         aa4;
     int nc[4], nhb[4], nh[5][4]; /* /ndx/ */
+#ifdef CBE_CH4OH
+    double d3cbi, a3cb, b3cb, rcbsp, fkh2oeq, alph2o, anh2oeq; /* egrad_ch4oh.f:2080,2101-2106 */
+    int no[4];
+#endif
 } ch4h_par;
 
 typedef struct {
@@ -48,7 +59,12 @@ typedef struct {
     real a1s, b1s, a2s, b2s;                              /* /fsw1/    */
     real s1[5], ds1[5], s2[5], ds2[5];                    /* /ip1/     */
     real s3[5], ds3[5];                                   /* /op1/     */
+#ifdef CBE_CH4OH
+    real q[22], pdot[22];                                 /* /qpdot_pl/ */
+    real rno, tno[4];                                     /* /bonds/, /coords/ */
+#else
     real q[19], pdot[19];                                 /* /qpdot_pl/ */
+#endif
     real sphi[5], dsphi[5], stheta[5], dstheta[5];        /* /switch1/ */
 } ch4h_state;
 
@@ -59,6 +75,55 @@ static void ch4h_prepot(ch4h_par *p)
     const int nnh[5] = {0, 3, 4, 5, 1};
     const double fact1 = 0.041840, fact2 = 6.022045;
     int ind, i, icount;
+#ifdef CBE_CH4OH
+    const int nno = 7;
+    const double fact3 = 2.0 * CH4H_PI / 360.0;
+#endif
+#ifdef CBE_CH4OH
+    /* BLOCK DATA PTPACM_ch4oh (egrad_ch4oh.f:2066-2106), PREPOT_ch4oh (:1972-2002) */
+    p->r0ch = 1.09397;
+    p->d1ch = 112.17000;
+    p->d3ch = 32.65328;
+    p->a1ch = 1.78000;
+    p->b1ch = 0.15000;
+    p->c1ch = 15.00000;
+    p->r0hh = 0.97060;
+    p->d1hh = 125.44000;
+    p->d3hh = 20.41017;
+    p->ahh = 2.15000;
+    p->r0cb = 1.49092;
+    p->d1cb = 91.47526;
+    p->d3cbi = 112.69509;
+    p->acb = 2.98688;
+    p->a3s = 0.1419100;
+    p->b3s = -0.3068400;
+    p->aphi = 0.5287900;
+    p->bphi = 0.4006600;
+    p->cphi = 1.9209900;
+    p->atheta = 0.9078700;
+    p->btheta = 0.3548900;
+    p->ctheta = 1.8915500;
+    p->fch3 = 0.0740000;
+    p->hch3 = 0.1915000;
+    p->fkinf = 0.4400000;
+    p->ak = 0.1260000;
+    p->bk = 10.7132;
+    p->aa1 = 0.303746;
+    p->aa2 = 1.599960;
+    p->aa3 = 3.216595;
+    p->aa4 = 11.569980;
+    p->fkh2oeq = 0.7300000;
+    p->alph2o = 1.1080000;
+    p->anh2oeq = 104.7132000;
+    p->a3cb = 0.000000;
+    p->b3cb = 0.900000;
+    p->rcbsp = 2.606485;
+    p->d3cb = 0.0; /* a function of the geometry here, see ch4h_stretch */
+    for (ind = 1; ind <= 3; ind++) p->no[ind] = 3 * nno + ind - 3;
+    p->d3cbi = p->d3cbi * fact1;
+    p->a3cb = p->a3cb * fact1;
+    p->anh2oeq = p->anh2oeq * fact3;
+#else
     p->r0ch = 1.08898;
     p->d1ch = 111.266;
     p->d3ch = 48.96226;
@@ -90,6 +155,7 @@ static void ch4h_prepot(ch4h_par *p)
     p->aa2 = 0.000710;
     p->aa3 = 0.985920;
     p->aa4 = 2.785060;
+#endif
     for (ind = 1; ind <= 3; ind++) {
         icount = ind - 3;
         p->nc[ind] = 3 * nnc + icount;
@@ -120,6 +186,10 @@ static void ch4h_coorden(const ch4h_par *p, ch4h_state *s)
         }
     }
     s->rcb = sqrt(s->tcb[1] * s->tcb[1] + s->tcb[2] * s->tcb[2] + s->tcb[3] * s->tcb[3]);
+#ifdef CBE_CH4OH
+    for (ind = 1; ind <= 3; ind++) s->tno[ind] = s->q[p->no[ind]] - s->q[p->nhb[ind]]; /* :351 */
+    s->rno = sqrt(s->tno[1] * s->tno[1] + s->tno[2] * s->tno[2] + s->tno[3] * s->tno[3]); /* :361 */
+#endif
     for (i = 1; i <= 4; i++) {
         s->rch[i] = sqrt(s->tch[i][1] * s->tch[i][1] + s->tch[i][2] * s->tch[i][2] +
                          s->tch[i][3] * s->tch[i][3]);
@@ -145,10 +215,17 @@ static void ch4h_switchf(const ch4h_par *p, ch4h_state *s)
 {
     const real argmax = 19.0;
     int i;
+#ifdef CBE_CH4OH
+    s->a1s = 1.5313681e-7; /* egrad_ch4oh.f:1808-1811 */
+    s->b1s = -4.6696246;
+    s->a2s = 1.0147402e-7;
+    s->b2s = -12.363798;
+#else
     s->a1s = 1.5132681e-7;
     s->b1s = -4.3792246;
     s->a2s = 1.9202402e-7;
     s->b2s = -12.323018;
+#endif
     for (i = 1; i <= 4; i++) {
         real rch = s->rch[i];
         real args1, args2, args3;
@@ -270,13 +347,23 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
     real vqch[5], vjch[5], vqbh[5], vjbh[5], vq[5], vj[5], achdc[4], achdh[5][4];
     real rav, vstr, arga, ach, dumach, e1, e3, vqcb, vjcb, dumqcb;
     const double r0ch = p->r0ch, r0cb = p->r0cb, r0hh = p->r0hh, acb = p->acb, ahh = p->ahh,
-                 d1cb = p->d1cb, d3cb = p->d3cb, d1ch = p->d1ch, d3ch = p->d3ch, d1hh = p->d1hh,
-                 d3hh = p->d3hh;
+                 d1cb = p->d1cb, d1ch = p->d1ch, d3ch = p->d3ch, d1hh = p->d1hh, d3hh = p->d3hh;
+#ifdef CBE_CH4OH
+    real d3cb, dd3cb, texp, dt, expterm, vno, deddt, de, ded[4], addd3;
+#else
+    const double d3cb = p->d3cb;
+#endif
     real *rch = s->rch, *rbh = s->rbh, rcb = s->rcb, *pdot = s->pdot;
     const int *nc = p->nc, *nhb = p->nhb;
     int i, ind, j, k;
     rav = (rch[1] + rch[2] + rch[3] + rch[4]) / 4.0;
     vstr = 0.0;
+#ifdef CBE_CH4OH
+    /* d3cb and dd3cb (:590-592); x**4.d0 and x**3.d0 are real powers of a possibly negative base */
+    texp = exp(-pow(4.0 * (rav - p->rcbsp) / p->b3cb, 4.0));
+    d3cb = (p->d3cbi - p->a3cb) + p->a3cb * texp;
+    dd3cb = -4.0 * p->a3cb * texp * pow(rav - p->rcbsp, 3.0) * pow(4.0 / p->b3cb, 4.0);
+#endif
     arga = p->c1ch * (rav - r0ch);
     if (arga < 19.0) {
         ach = p->a1ch + p->b1ch * (tanh(arga) + 1.0) * 0.5;
@@ -289,6 +376,12 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
     e3 = d3cb * (exp(-2.0 * acb * (rcb - r0cb)) + 2.0 * exp(-acb * (rcb - r0cb)));
     vqcb = (e1 + e3) * 0.5;
     vjcb = (e1 - e3) * 0.5;
+#ifdef CBE_CH4OH
+    /* O-H Morse term (:616-621) */
+    dt = (s->rno - r0hh);
+    expterm = exp(-ahh * dt);
+    vno = d1hh * ((1.0 - expterm) * (1.0 - expterm));
+#endif
     for (i = 1; i <= 4; i++) {
         e1 = d1ch * (exp(-2.0 * ach * (rch[i] - r0ch)) - 2.0 * exp(-ach * (rch[i] - r0ch)));
         e3 = d3ch * (exp(-2.0 * ach * (rch[i] - r0ch)) + 2.0 * exp(-ach * (rch[i] - r0ch)));
@@ -304,6 +397,12 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
                       0.5);
         vstr = vstr + vq[i] + vj[i];
     }
+#ifdef CBE_CH4OH
+    vstr = vstr + vno;                                      /* :646 */
+    deddt = 2.0 * ahh * d1hh * (1.0 - expterm) * expterm;   /* :652-659 */
+    de = deddt / s->rno;
+    for (i = 1; i <= 3; i++) ded[i] = de * s->tno[i];
+#endif
     for (ind = 1; ind <= 3; ind++) {
         achdc[ind] = dumach *
                      (s->tch[1][ind] / rch[1] + s->tch[2][ind] / rch[2] + s->tch[3][ind] / rch[3] +
@@ -321,6 +420,12 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
                  ((d1hh + d3hh) * exp(-2.0 * ahh * (rbh[i] - r0hh)) -
                   (d1hh - d3hh) * exp(-ahh * (rbh[i] - r0hh))) /
                  rbh[i];
+#ifdef CBE_CH4OH
+        /* "adding the derv of D3cb wrt r" as written (:681-686) */
+        addd3 = dd3cb * (exp(-2.0 * acb * (rcb - r0cb)) + 2.0 * exp(-acb * (rcb - r0cb)));
+        addd3 = addd3 / 4.0 * 0.5 / rcb;
+        dumqbh = dumqbh + addd3;
+#endif
         factj = 0.5 / vj[i];
         dumjcb = -acb *
                  ((d1cb - d3cb) * exp(-2.0 * acb * (rcb - r0cb)) -
@@ -330,6 +435,11 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
                  ((d1hh - d3hh) * exp(-2.0 * ahh * (rbh[i] - r0hh)) -
                   (d1hh + d3hh) * exp(-ahh * (rbh[i] - r0hh))) *
                  factj / rbh[i];
+#ifdef CBE_CH4OH
+        addd3 = dd3cb * (exp(-2.0 * acb * (rcb - r0cb)) + 2.0 * exp(-acb * (rcb - r0cb))); /* :694-699 */
+        addd3 = addd3 / 4.0 * 0.5 * factj / rcb;
+        dumjbh = dumjbh - addd3;
+#endif
         for (ind = 1; ind <= 3; ind++) {
             real dumqch, dumqhi, dumjch, dumjhi;
             real tcb = s->tcb[ind], tbh = s->tbh[i][ind], tch = s->tch[i][ind];
@@ -380,6 +490,12 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
             }
         }
     }
+#ifdef CBE_CH4OH
+    for (ind = 1; ind <= 3; ind++) {                         /* :769-774 */
+        pdot[nhb[ind]] = pdot[nhb[ind]] - ded[ind];
+        pdot[p->no[ind]] = pdot[p->no[ind]] + ded[ind];
+    }
+#endif
     *vstr_out = vstr;
 }
 
@@ -747,17 +863,92 @@ static void ch4h_ipbend(const ch4h_par *p, ch4h_state *s, real *vip_out)
                 }
             }
         }
+#ifdef CBE_CH4OH
+    {   /* H(i)-O-H(O) bends, egrad_ch4oh.f:1059-1171 */
+        real angh2o[5], fkh2o[5], dkdr[5], dkdx[5][4], dedo[4], dedhi[4], dedho[4];
+        real dot, cosine, arga, dang, deno, term1, dstda, xp, yp, zp, rp, terma, termc;
+        const real *tno = s->tno, rno = s->rno;
+        for (i = 1; i <= 4; i++) {
+            dot = 0.0;
+            for (j = 1; j <= 3; j++) dot = dot - tno[j] * s->tbh[i][j];
+            cosine = dot / (rno * rbh[i]);
+            cosine = (cosine > -1.0) ? cosine : (real)(-1.0);   /* min(1, max(-1, cosine)) */
+            cosine = (cosine < 1.0) ? cosine : (real)1.0;
+            angh2o[i] = acos(cosine);
+        }
+        for (i = 1; i <= 4; i++) {
+            arga = p->alph2o * (rbh[i] - p->r0hh);
+            if (arga < 19.0)
+                fkh2o[i] = p->fkh2oeq * (1 - tanh(arga));
+            else
+                fkh2o[i] = 0.0;
+        }
+        for (i = 1; i <= 4; i++) {
+            dang = (angh2o[i] - p->anh2oeq);
+            vip = vip + 0.5 * fkh2o[i] * dang * dang;
+        }
+        for (i = 1; i <= 4; i++) {
+            deno = cosh(p->alph2o * (rbh[i] - p->r0hh));
+            dkdr[i] = -(p->fkh2oeq * p->alph2o) / (deno * deno);
+        }
+        for (i = 1; i <= 4; i++) {
+            dkdr[i] = dkdr[i] / rbh[i];
+            for (j = 1; j <= 3; j++) dkdx[i][j] = dkdr[i] * s->tbh[i][j];
+        }
+        for (i = 1; i <= 4; i++)
+            for (j = 1; j <= 3; j++) {
+                term1 = 0.5 * ((angh2o[i] - p->anh2oeq) * (angh2o[i] - p->anh2oeq));
+                pdot[p->nhb[j]] = pdot[p->nhb[j]] + dkdx[i][j] * term1;
+                pdot[p->nh[i][j]] = pdot[p->nh[i][j]] - dkdx[i][j] * term1;
+            }
+        for (i = 1; i <= 4; i++) {
+            dstda = fkh2o[i] * (angh2o[i] - p->anh2oeq);
+            xp = tno[2] * s->tbh[i][3] - tno[3] * s->tbh[i][2];
+            yp = tno[3] * s->tbh[i][1] - tno[1] * s->tbh[i][3];
+            zp = tno[1] * s->tbh[i][2] - tno[2] * s->tbh[i][1];
+            rp = sqrt(xp * xp + yp * yp + zp * zp);
+            if (rp < 1.0e-6) rp = 1.0e-6;
+            terma = dstda / (rbh[i] * rbh[i] * rp);
+            termc = dstda / (rno * rno * rp);
+            dedhi[1] = -terma * (s->tbh[i][2] * zp - s->tbh[i][3] * yp);
+            dedhi[2] = -terma * (s->tbh[i][3] * xp - s->tbh[i][1] * zp);
+            dedhi[3] = -terma * (s->tbh[i][1] * yp - s->tbh[i][2] * xp);
+            dedho[1] = -termc * (tno[2] * zp - tno[3] * yp);
+            dedho[2] = -termc * (tno[3] * xp - tno[1] * zp);
+            dedho[3] = -termc * (tno[1] * yp - tno[2] * xp);
+            dedo[1] = -dedhi[1] - dedho[1];
+            dedo[2] = -dedhi[2] - dedho[2];
+            dedo[3] = -dedhi[3] - dedho[3];
+            for (j = 1; j <= 3; j++) {
+                pdot[p->nhb[j]] = pdot[p->nhb[j]] + dedo[j];
+                pdot[p->nh[i][j]] = pdot[p->nh[i][j]] + dedhi[j];
+                pdot[p->no[j]] = pdot[p->no[j]] + dedho[j];
+            }
+        }
+    }
+#endif
     *vip_out = vip;
 }
 
 /* ---- POT_ch4h (:161-285): R(1..18) cartesians in bohr -> energy (hartree), DEGSDR ---- */
-static void ch4h_pot(const ch4h_par *p, const real R[19], real *en_out, real DEGSDR[19],
+#ifdef CBE_CH4OH
+#define CBE_NC 21   /* POT_ch4oh :157-286 */
+#define CBE_NAT 7
+#define CBE_EGRAD oracle_egrad_ch4oh_real
+#define CBE_PARTS oracle_ch4oh_parts_real
+#else
+#define CBE_NC 18
+#define CBE_NAT 6
+#define CBE_EGRAD oracle_egrad_ch4h_real
+#define CBE_PARTS oracle_ch4h_parts_real
+#endif
+static void ch4h_pot(const ch4h_par *p, const real R[CBE_NC + 1], real *en_out, real DEGSDR[CBE_NC + 1],
                      real parts[3])
 {
     ch4h_state s;
     real vstr, vop, vip, en;
     int i;
-    for (i = 1; i <= 18; i++) {
+    for (i = 1; i <= CBE_NC; i++) {
         s.q[i] = R[i] * 0.52918;
         s.pdot[i] = 0.0;
     }
@@ -770,7 +961,7 @@ static void ch4h_pot(const ch4h_par *p, const real R[19], real *en_out, real DEG
     en = vstr + vop + vip;
     en = en * 0.03812;
     *en_out = en;
-    for (i = 1; i <= 18; i++) DEGSDR[i] = s.pdot[i] * 0.0201723;
+    for (i = 1; i <= CBE_NC; i++) DEGSDR[i] = s.pdot[i] * 0.0201723;
     if (parts) {
         parts[0] = vstr;
         parts[1] = vop;
@@ -779,7 +970,7 @@ static void ch4h_pot(const ch4h_par *p, const real R[19], real *en_out, real DEG
 }
 
 /* ---- egrad_ch4h (:74-132); atom order H,C,H,H,H,H(b) (nnc=2, nnb=6, nnh=3,4,5,1) ---- */
-void oracle_egrad_ch4h_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info)
+void CBE_EGRAD(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info)
 {
     ch4h_par par;
     int k, i, j;
@@ -788,22 +979,22 @@ void oracle_egrad_ch4h_real(const real *q, int natoms, int nbeads, real *V, real
     for (k = 0; k < nbeads; k++) {
         const real *qk = q + (long)k * 3 * natoms;
         real *gk = dVdq + (long)k * 3 * natoms;
-        real R[19], D[19];
-        for (j = 0; j < 6; j++)
+        real R[CBE_NC + 1], D[CBE_NC + 1];
+        for (j = 0; j < CBE_NAT; j++)
             for (i = 0; i < 3; i++) R[3 * j + i + 1] = qk[3 * j + i];
         ch4h_pot(&par, R, &V[k], D, (real *)0);
         for (j = 0; j < natoms; j++)
-            for (i = 0; i < 3; i++) gk[3 * j + i] = (j < 6) ? D[3 * j + i + 1] : (real)0.0;
+            for (i = 0; i < 3; i++) gk[3 * j + i] = (j < CBE_NAT) ? D[3 * j + i + 1] : (real)0.0;
     }
 }
 
 /* energy split (vstr, vop, vip in 1e5 J/mol) for the per-term tests */
-void oracle_ch4h_parts_real(const real *q18, real parts[3], real *V)
+void CBE_PARTS(const real *q18, real parts[3], real *V)
 {
     ch4h_par par;
-    real R[19], D[19];
+    real R[CBE_NC + 1], D[CBE_NC + 1];
     int i;
     ch4h_prepot(&par);
-    for (i = 0; i < 18; i++) R[i + 1] = q18[i];
+    for (i = 0; i < CBE_NC; i++) R[i + 1] = q18[i];
     ch4h_pot(&par, R, V, D, parts);
 }

@@ -19,6 +19,7 @@
 #define ORC_PES_CH4H 3
 #define ORC_PES_BRH2 4
 #define ORC_PES_O3 5
+#define ORC_PES_CH4OH 6
 
 #ifdef __cplusplus
 extern "C" {

@@ -44,6 +44,15 @@ def o3_ts():
     return np.array([[0, 0, 0], [r1, 0, 0], [r2 * np.cos(th), r2 * np.sin(th), 0]])
 
 
+def ch4oh_ts():
+    """examples/explore/ts_irc_ch4oh/ts_start.xyz of the reference (Angstrom): the start structure of its own saddle
+    search on this surface; atom 4 is the hydrogen in flight.  Atom order H, C, H, H, H, O, H(O)."""
+    return np.array([[-4.62878267, 1.25606861, 0.95459788], [-4.85261637, 2.15380812, 0.37457524],
+                     [-4.27740626, 2.99438311, 0.76831501], [-4.53003946, 1.95346377, -0.88649386],
+                     [-5.91912714, 2.37708958, 0.44643735], [-4.21407574, 1.75722671, -2.12170961],
+                     [-3.93964920, 2.62885961, -2.44704966]]) / BOHR
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -56,6 +65,9 @@ SYSTEMS = {
     "o3": dict(pes="o3", symbols=["O", "O", "O"], ts=o3_ts,
                # O + O2 exchange: the bond 1-2 breaks (atom 2 leaves), fragments O2 (1,3) and O (2); bond_form 2-3
                mecha=dict(bond_form=[[2, 3]], bond_break=[[1, 2]], reactants=[[1, 3], [2]], dist_inf=16.0)),
+    "ch4oh": dict(pes="ch4oh", symbols=["H", "C", "H", "H", "H", "O", "H"], ts=ch4oh_ts,
+                  # CH4 + OH -> CH3 + H2O, atom 4 transferred: reactant1 1-5, reactant2 6 7, bond_form 4-6, bond_break 2-4
+                  mecha=dict(bond_form=[[4, 6]], bond_break=[[2, 4]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("name,sigma,n", [("h3", 0.15, 100000), ("h3", 0.5, 30000), ("oh3", 0.15, 100000),
                                           ("oh3", 0.5, 30000), ("ch4h", 0.15, 100000), ("ch4h", 0.4, 30000),
-                                          ("brh2", 0.15, 100000), ("brh2", 0.5, 30000), ("o3", 0.15, 100000), ("o3", 0.4, 30000)])
+                                          ("brh2", 0.15, 100000), ("brh2", 0.5, 30000), ("o3", 0.15, 100000), ("o3", 0.4, 30000),
+                                          ("ch4oh", 0.15, 100000), ("ch4oh", 0.4, 30000)])
 def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, n, sigma, rng)
@@ -46,6 +47,9 @@ def test_reference_signature_wrappers(gpu, oracle):
     assert V.shape == (5,)
     V, dVdq, info = gpu.egrad_oh3(C.ts_cloud("oh3", 3, 0.1, np.random.default_rng(3)), 4, 3)
     assert V.shape == (3,)
+    q = C.ts_cloud("ch4oh", 4, 0.1, np.random.default_rng(4))
+    V, dVdq, info = gpu.egrad_ch4oh(q, 7, 4)
+    assert V.shape == (4,) and dVdq.shape == q.shape and info == 0
 
 
 def test_edge_sizes(gpu, oracle):
@@ -75,7 +79,7 @@ def test_h3_compact_branch_and_warning_bits(gpu, oracle):
     assert info == oinfo == 2
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh"])
 def test_invariances_at_scale(gpu, name):
     """size-independent properties on 1e6 images: rigid motions and permutations of equivalent
     hydrogens leave E unchanged and rotate/permute the gradient."""
@@ -96,7 +100,8 @@ def test_invariances_at_scale(gpu, name):
     assert C.rel_err_G(g2, g @ A.T, 1e-2).max() < 1e-8
     # net force and torque vanish
     assert np.abs(g.sum(axis=1)).max() < 1e-10
-    perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5], "brh2": [2, 1, 0], "o3": [1, 2, 0]}[name]
+    perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5], "brh2": [2, 1, 0], "o3": [1, 2, 0],
+            "ch4oh": [3, 1, 2, 0, 4, 5, 6]}[name]
     V3, g3, _ = gpu.egrad(name, q[:, perm])
     ok = np.ones(len(q), dtype=bool)
     if name == "brh2":

@@ -1,0 +1,103 @@
+"""CPU tests of the CH4 + OH oracle (oracle/pes_ch4oh.c, egrad_ch4oh.f).  The reference ships no
+outputs for this surface; what it does ship is the start structure of its own saddle search
+(examples/explore/ts_irc_ch4oh/ts_start.xyz), used here as the geometry the clouds are drawn around."""
+import numpy as np
+import pytest
+
+from tests import common as C
+
+KCAL = 627.509474
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as O
+    O.build()
+    return O
+
+
+def fd_gradient(O, q, h=1e-4):
+    g = np.zeros_like(q)
+    for a in range(q.shape[0]):
+        for d in range(3):
+            qp, qm = q.copy(), q.copy()
+            qp[a, d] += h
+            qm[a, d] -= h
+            g[a, d] = (O.egrad("ch4oh", qp[None])[0][0] - O.egrad("ch4oh", qm[None])[0][0]) / (2 * h)
+    return g
+
+
+def test_gradient_is_the_derivative_of_the_energy(oracle):
+    """central differences; the floor is the reference's own 2e-6 mismatch between its energy and gradient unit
+    factors (0.03812 * 0.52918 against 0.0201723, egrad_ch4oh.f:267,:276), as on the CH4 + H surface"""
+    q = C.ts_cloud("ch4oh", 6, 0.1, np.random.default_rng(3))
+    V, g, info = oracle.egrad("ch4oh", q)
+    assert info == 0 and np.isfinite(V).all()
+    for im in range(len(q)):
+        gn = fd_gradient(oracle, q[im])
+        assert np.abs(gn - g[im].reshape(7, 3)).max() < 1e-5 * np.abs(g[im]).max()
+
+
+def test_each_added_term_has_a_consistent_gradient(oracle):
+    """the three energy parts (stretch incl. the O-H Morse bond, out-of-plane, in-plane incl. the H-O-H bends) move
+    when the atoms they depend on move: H(O) enters only through the added terms, so its finite-difference force
+    checks them in isolation"""
+    q = C.ts_cloud("ch4oh", 4, 0.1, np.random.default_rng(5))
+    _, g, _ = oracle.egrad("ch4oh", q)
+    for im in range(len(q)):
+        gn = fd_gradient(oracle, q[im])
+        assert np.abs(g[im].reshape(7, 3)[6]).max() > 1e-4            # the added terms act on H(O)
+        assert np.abs(gn[6] - g[im].reshape(7, 3)[6]).max() < 1e-5 * np.abs(g[im]).max()
+
+
+def test_invariances(oracle):
+    rng = np.random.default_rng(7)
+    q = C.ts_cloud("ch4oh", 50, 0.15, rng)
+    V, g, _ = oracle.egrad("ch4oh", q)
+    g = g.reshape(q.shape)
+    assert np.abs(g.sum(axis=1)).max() < 1e-12                         # no net force
+    assert np.abs(np.cross(q, g).sum(axis=1)).max() < 1e-10            # no net torque
+    A = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    V2, g2, _ = oracle.egrad("ch4oh", q @ A.T + 1.5)
+    assert np.abs(V2 - V).max() < 1e-11
+    assert np.abs(g2.reshape(q.shape) - g @ A.T).max() < 1e-10
+    # the four methane hydrogens are equivalent (atoms 1, 3, 4, 5)
+    for perm in ([3, 1, 2, 0, 4, 5, 6], [0, 1, 4, 2, 3, 5, 6], [2, 1, 0, 4, 3, 5, 6]):
+        V3, g3, _ = oracle.egrad("ch4oh", q[:, perm])
+        assert np.abs(V3 - V).max() < 1e-10
+        assert np.abs(g3.reshape(q.shape) - g[:, perm]).max() < 1e-9
+
+
+def test_shipped_saddle_search_start_is_close_to_stationary(oracle):
+    """ts_start.xyz is where the reference starts `job opt_ts` on this surface: forces there are a small fraction of
+    those a 0.1 bohr displacement produces"""
+    V0, g0, _ = oracle.egrad("ch4oh", C.ch4oh_ts()[None])
+    _, g, _ = oracle.egrad("ch4oh", C.ts_cloud("ch4oh", 20, 0.1, np.random.default_rng(1)))
+    assert np.abs(g0).max() < 0.01
+    assert np.abs(g0).max() < 0.2 * np.median(np.abs(g).max(axis=(1,) if g.ndim == 2 else (1, 2)))
+
+
+def test_fragments_sit_at_the_constants_of_the_block_data(oracle):
+    """products far apart (CH3 ... H2O, 12 A): the water O-H bonds relax to r0hh = 0.9706 A and the bend to
+    anh2oeq = 104.7132 deg (egrad_ch4oh.f:2078,:2103) -- the added Morse bond and bends carry exactly these minima"""
+    from scipy.optimize import minimize
+    r, th = 0.9706 / C.BOHR, np.deg2rad(104.7132)
+    t = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]]) / np.sqrt(3)
+    q = np.zeros((7, 3))
+    q[2], q[3], q[4] = t[1] * 2.05, t[2] * 2.05, t[3] * 2.05          # CH3
+    q[5] = t[0] * 12.0 / C.BOHR                                        # O
+    q[0] = q[5] - t[0] * r * 1.05                                      # H taken from methane, now on the oxygen
+    e2 = t[1] - (t[1] @ t[0]) * t[0]
+    e2 /= np.linalg.norm(e2)
+    q[6] = q[5] + 1.05 * r * (np.cos(th + 0.1) * (-t[0]) + np.sin(th + 0.1) * e2)
+
+    def f(x):
+        V, g, _ = oracle.egrad("ch4oh", x.reshape(1, 7, 3))
+        return V[0], g.reshape(-1)
+    res = minimize(f, q.reshape(-1), jac=True, method="BFGS", options=dict(gtol=1e-7, maxiter=2000))
+    x = res.x.reshape(7, 3)
+    a, b = x[0] - x[5], x[6] - x[5]
+    assert abs(np.linalg.norm(a) * C.BOHR - 0.9706) < 2e-3
+    assert abs(np.linalg.norm(b) * C.BOHR - 0.9706) < 2e-3
+    ang = np.degrees(np.arccos(a @ b / np.linalg.norm(a) / np.linalg.norm(b)))
+    assert abs(ang - 104.7132) < 0.3
