@@ -19,7 +19,7 @@ from . import lib as _l
 _F32 = np.float32
 EMASS = 5.485799095e-4  # general.f90:252
 AMU = {"H": 1.00782503207, "D": 2.0141017778, "C": 12.00000, "N": 14.0030740048, "O": 15.99491461956,
-       "F": 18.99840, "S": 32.06000, "CL": 34.96885268, "BR": 78.9183371}   # atommass.f90:58-129
+       "F": 18.99840, "S": 32.06000, "CL": 34.96885268, "BR": 78.9183371, "GE": 72.61}   # atommass.f90:58-129
 
 
 def atomic_mass_au(symbol):
@@ -418,7 +418,7 @@ class RPMD:
 # ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
 _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"],
              _l.PES_BRH2: ["H", "BR", "H"], _l.PES_O3: ["O", "O", "O"],
-             _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"]}
+             _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"], _l.PES_GEH4OH: ["H", "GE", "H", "H", "H", "O", "H"]}
 _egrad_handles = {}
 
 
@@ -453,6 +453,10 @@ def egrad_o3(q, Natoms=3, Nbeads=None):
 
 def egrad_ch4oh(q, Natoms=7, Nbeads=None):
     return egrad(_l.PES_CH4OH, q, Natoms, Nbeads)
+
+
+def egrad_geh4oh(q, Natoms=7, Nbeads=None):
+    return egrad(_l.PES_GEH4OH, q, Natoms, Nbeads)
 
 
 def egrad_ch4h(q, Natoms=6, Nbeads=None):

@@ -110,6 +110,8 @@ struct K6 {
     static constexpr double A2S = ch4h::A2S;
     static constexpr double B2S = ch4h::B2S;
     static constexpr double FKH2OEQ = 0.0, ALPH2O = 0.0, ANH2OEQ = 0.0;   // unused without HAS_OH
+    static constexpr bool SPHI_ANY_R = false;
+    static constexpr double TAU_PLANAR = 0.5;
 };
 }  // namespace ch4h
 
@@ -225,18 +227,21 @@ struct PesCBE1 {
                     ds3[x] = 0.0;
                 }
             }
-            if (r < 3.8) {
+            if (K::SPHI_ANY_R || r < 3.8) {   // egrad_geh4oh.f:1793-1804 drops the cut for sphi only
                 const double u = r - K::CPHI, ex = exp(K::BPHI * u * u * u);
                 one_minus_tanh(K::APHI * dr * ex, omt, ms2);
                 sphi[x] = omt;
                 dsphi[x] = K::APHI * (1.0 + 3.0 * K::BPHI * dr * u * u) * ex * ms2;
+            } else {
+                sphi[x] = 0.0;
+                dsphi[x] = 0.0;
+            }
+            if (r < 3.8) {
                 const double v = r - K::CTHETA, ev = exp(K::BTHETA * v * v * v);
                 one_minus_tanh(K::ATHETA * dr * ev, omt, ms2);
                 sth[x] = omt;
                 dsth[x] = K::ATHETA * (1.0 + 3.0 * K::BTHETA * dr * v * v) * ev * ms2;
             } else {
-                sphi[x] = 0.0;
-                dsphi[x] = 0.0;
                 sth[x] = 0.0;
                 dsth[x] = 0.0;
             }
@@ -244,7 +249,7 @@ struct PesCBE1 {
         // reference angles theta0(i,j) = tau + ta (sphi_i sphi_j - 1) + tb (sth_k sth_l - 1)
         // with {k,l} the complement of {i,j} (refangles_ch4h)
         const double tau = acos(-1.0 / 3.0);
-        const double ta = tau - 0.5 * PI, tb = tau - 2.0 * PI / 3.0;
+        const double ta = tau - K::TAU_PLANAR * PI, tb = tau - 2.0 * PI / 3.0;   // halfpi, or taugeh (egrad_geh4oh.f:368)
         auto theta0 = [&](int i, int j, int k, int l) {
             return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
         };

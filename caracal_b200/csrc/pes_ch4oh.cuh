@@ -1,4 +1,4 @@
-// pes_ch4oh.cuh -- CH4 + OH -> CH3 + H2O surface of Espinosa-Garcia and Corchado (J. Chem. Phys. 112, 5731
+// pes_ch4oh.cuh -- CH4 + OH -> CH3 + H2O and GeH4 + OH -> GeH3 + H2O; first: the CH4 + OH surface of Espinosa-Garcia and Corchado (J. Chem. Phys. 112, 5731
 // (2000); POTLIB form), one thread per image, FP64.  SURVEY.md 8(f) row N4.
 //
 // Replaces /root/reference/src/egrad_ch4oh.f: egrad_ch4oh :69-124, POT_ch4oh :157-286 and the routines below it.
@@ -34,14 +34,40 @@ struct K7 {
     static constexpr double FKINF = 0.4400000 * 6.022045, AK = 0.1260000 * 6.022045;
     static constexpr double AA1 = 0.303746, AA2 = 1.599960, AA3 = 3.216595, AA4 = 11.569980;
     static constexpr double A1S = 1.5313681e-7, B1S = -4.6696246, A2S = 1.0147402e-7, B2S = -12.363798;
-    // H-O-H bends: fkh2oeq is NOT scaled by PREPOT (only anh2oeq is, by fact3)
-    static constexpr double FKH2OEQ = 0.7300000, ALPH2O = 1.1080000;
+    // H-O-H bends: fkh2oeq scaled by fact2, anh2oeq by fact3 (:2001-2002)
+    static constexpr double FKH2OEQ = 0.7300000 * 6.022045, ALPH2O = 1.1080000;
     static constexpr double ANH2OEQ = 104.7132000 * (2.0 * 3.141592653589793 / 360.0);
+    static constexpr bool SPHI_ANY_R = false;
+    static constexpr double TAU_PLANAR = 0.5;
 };
 static_assert(K7::A3CB == 0.0, "a switched C-O triplet depth needs the dd3cb terms of stretch_ch4oh :681-699");
 
 }  // namespace ch4oh
 
 using PesCH4OH = PesCBE1<ch4oh::K7>;
+
+// GeH4 + OH -> GeH3 + H2O, /root/reference/src/egrad_geh4oh.f: the CH4 + OH file with the central atom a germanium --
+// BLOCK DATA :2002-2042, in-plane reference angle on taugeh = 0.678 pi (:368, :382-440: pyramidal GeH3), sphi
+// evaluated at every distance (:1793-1804).  Atom order H, Ge, H, H, H, O, H(O).
+namespace geh4oh {
+struct K7 : ch4oh::K7 {
+    static constexpr int ID = CRCL_PES_GEH4OH;
+    static constexpr double R0CH = 1.52500, A1CH = 1.43925, B1CH = 0.12330, C1CH = 2.00400;
+    static constexpr double AHH = 2.18200, R0CB = 1.90035, ACB = 0.67621;
+    static constexpr double D1CH = 86.50000 * 0.041840, D3CH = 41.50000 * 0.041840;
+    static constexpr double D1HH = 120.94800 * 0.041840, D3HH = 31.86417 * 0.041840;
+    static constexpr double D1CB = 41.50283 * 0.041840;
+    static constexpr double D3CB = (10.50589 * 0.041840 - A3CB) + A3CB;
+    static constexpr double A3S = 0.2019100, B3S = -0.6068400;
+    static constexpr double CPHI = 11.8809900;
+    static constexpr double FCH3 = 0.0150000 * 6.022045;
+    static constexpr double FKINF = 0.3060000 * 6.022045;
+    static constexpr double AA1 = 0.173746, AA3 = 2.166595;
+    static constexpr bool SPHI_ANY_R = true;
+    static constexpr double TAU_PLANAR = 0.678;
+};
+}  // namespace geh4oh
+
+using PesGeH4OH = PesCBE1<geh4oh::K7>;
 
 }  // namespace crcl

@@ -1,0 +1,6 @@
+// traj_geh4oh_verlet.cu -- instantiates the verlet trajectory kernels for the "geh4oh" surface.
+#include "pes_ch4oh.cuh"
+#include "traj_inst.cuh"
+namespace crcl {
+CRCL_DECLARE_TRAJ(launch_geh4oh_verlet) { return launch_traj_pes<PesGeH4OH, K_VERLET>(nbeads, A, bias_mode, nose_q, s, nosup); }
+}  // namespace crcl

@@ -80,5 +80,8 @@ CRCL_DECLARE_TRAJ(launch_o3_recross);
 CRCL_DECLARE_TRAJ(launch_ch4oh_verlet);
 CRCL_DECLARE_TRAJ(launch_ch4oh_mdinit);
 CRCL_DECLARE_TRAJ(launch_ch4oh_recross);
+CRCL_DECLARE_TRAJ(launch_geh4oh_verlet);
+CRCL_DECLARE_TRAJ(launch_geh4oh_mdinit);
+CRCL_DECLARE_TRAJ(launch_geh4oh_recross);
 
 }  // namespace crcl

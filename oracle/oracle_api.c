@@ -49,6 +49,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_BRH2: oracle_egrad_brh2_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_O3: oracle_egrad_o3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_CH4OH: oracle_egrad_ch4oh_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_GEH4OH: oracle_egrad_geh4oh_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

@@ -31,6 +31,9 @@
  * BLOCK DATA (:2066-2106), and three additions marked CBE_CH4OH below -- the C-O triplet depth
  * switched on the mean C-H distance (:590-592, :681-699), the O-H Morse bond (:616-621, :644-659, :769-774)
  * and the four H-O-H bends with a tanh-switched force constant (:1059-1171).
+ * With -DCBE_GEH4OH in addition (pes_geh4oh.c) they restate /root/reference/src/egrad_geh4oh.f (GeH4 + OH ->
+ * GeH3 + H2O): the CH4 + OH file again with its own BLOCK DATA (:2002-2042), the in-plane reference angle built
+ * on taugeh = 0.678 pi instead of pi/2 (:368, :382-440) and sphi evaluated at every distance (:1793-1804).
  */
 #include "oracle_real.h"
 #include "oracle.h"
@@ -120,8 +123,33 @@ static void ch4h_prepot(ch4h_par *p)
     p->rcbsp = 2.606485;
     p->d3cb = 0.0; /* a function of the geometry here, see ch4h_stretch */
     for (ind = 1; ind <= 3; ind++) p->no[ind] = 3 * nno + ind - 3;
+#ifdef CBE_GEH4OH
+    /* BLOCK DATA PTPACM_geh4oh (egrad_geh4oh.f:2002-2042): the entries that differ from CH4 + OH */
+    p->r0ch = 1.52500;
+    p->d1ch = 86.50000;
+    p->d3ch = 41.50000;
+    p->a1ch = 1.43925;
+    p->b1ch = 0.12330;
+    p->c1ch = 2.00400;
+    p->d1hh = 120.94800;
+    p->d3hh = 31.86417;
+    p->ahh = 2.18200;
+    p->r0cb = 1.90035;
+    p->d1cb = 41.50283;
+    p->d3cbi = 10.50589;
+    p->acb = 0.67621;
+    p->a3s = 0.2019100;
+    p->b3s = -0.6068400;
+    p->cphi = 11.8809900;
+    p->fch3 = 0.0150000;
+    p->fkinf = 0.3060000;
+    p->bk = 50.7132;
+    p->aa1 = 0.173746;
+    p->aa3 = 2.166595;
+#endif
     p->d3cbi = p->d3cbi * fact1;
     p->a3cb = p->a3cb * fact1;
+    p->fkh2oeq = p->fkh2oeq * fact2;  /* egrad_ch4oh.f:2001, egrad_geh4oh.f:1937 */
     p->anh2oeq = p->anh2oeq * fact3;
 #else
     p->r0ch = 1.08898;
@@ -259,7 +287,11 @@ static void ch4h_switchf(const ch4h_par *p, ch4h_state *s)
             s->s3[i] = 0.0;
             s->ds3[i] = 0.0;
         }
+#ifdef CBE_GEH4OH
+        if (1) {   /* the rch < 3.8 test is commented out for sphi (egrad_geh4oh.f:1793-1804), kept for stheta */
+#else
         if (rch < 3.8) {
+#endif
             real argsphi = p->aphi * (rch - p->r0ch) * exp(p->bphi * ipow(rch - p->cphi, 3));
             s->sphi[i] = 1.0 - tanh(argsphi);
             s->dsphi[i] =
@@ -292,7 +324,11 @@ static void ch4h_refangles(ch4h_state *s)
     real tau = acos((real)(-1.0 / 3.0));
     real halfpi = 0.5 * pi;
     real twopi = 2.0 * pi;
+#ifdef CBE_GEH4OH
+    real ta = tau - 0.678 * pi;    /* (tau-taugeh), taugeh=0.678d0*pi: pyramidal GeH3 (egrad_geh4oh.f:368,:382-440) */
+#else
     real ta = tau - halfpi;        /* (tau-halfpi)        */
+#endif
     real tb = tau - twopi / 3.0;   /* (tau-twopi/3.0d0)   */
     real *sphi = s->sphi, *dsphi = s->dsphi, *stheta = s->stheta, *dstheta = s->dstheta;
     int i, j, k;
@@ -931,7 +967,12 @@ static void ch4h_ipbend(const ch4h_par *p, ch4h_state *s, real *vip_out)
 }
 
 /* ---- POT_ch4h (:161-285): R(1..18) cartesians in bohr -> energy (hartree), DEGSDR ---- */
-#ifdef CBE_CH4OH
+#if defined(CBE_GEH4OH)
+#define CBE_NC 21   /* pot_geh4oh :84-217 */
+#define CBE_NAT 7
+#define CBE_EGRAD oracle_egrad_geh4oh_real
+#define CBE_PARTS oracle_geh4oh_parts_real
+#elif defined(CBE_CH4OH)
 #define CBE_NC 21   /* POT_ch4oh :157-286 */
 #define CBE_NAT 7
 #define CBE_EGRAD oracle_egrad_ch4oh_real

@@ -20,6 +20,7 @@
 #define ORC_PES_BRH2 4
 #define ORC_PES_O3 5
 #define ORC_PES_CH4OH 6
+#define ORC_PES_GEH4OH 7
 
 #ifdef __cplusplus
 extern "C" {

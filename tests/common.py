@@ -53,6 +53,22 @@ def ch4oh_ts():
                      [-3.93964920, 2.62885961, -2.44704966]]) / BOHR
 
 
+def geh4oh_ts():
+    """GeH4 + OH near the abstraction saddle region: tetrahedral GeH4 (r0ch = 1.525 A, egrad_geh4oh.f:2006) with the
+    hydrogen in flight (atom 1) at 1.62 A, O 1.35 A beyond it, H(O) at 0.97 A and 100 deg.  Atom order
+    H, Ge, H, H, H, O, H(O)."""
+    t = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]]) / np.sqrt(3)
+    q = np.zeros((7, 3))
+    q[0] = t[0] * 1.62
+    q[2], q[3], q[4] = t[1] * 1.525, t[2] * 1.525, t[3] * 1.525
+    q[5] = t[0] * (1.62 + 1.35)
+    e2 = t[1] - (t[1] @ t[0]) * t[0]
+    e2 /= np.linalg.norm(e2)
+    th = np.deg2rad(100.0)
+    q[6] = q[5] + 0.97 * (np.cos(th) * (-t[0]) + np.sin(th) * e2)
+    return q / BOHR
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -68,6 +84,8 @@ SYSTEMS = {
     "ch4oh": dict(pes="ch4oh", symbols=["H", "C", "H", "H", "H", "O", "H"], ts=ch4oh_ts,
                   # CH4 + OH -> CH3 + H2O, atom 4 transferred: reactant1 1-5, reactant2 6 7, bond_form 4-6, bond_break 2-4
                   mecha=dict(bond_form=[[4, 6]], bond_break=[[2, 4]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
+    "geh4oh": dict(pes="geh4oh", symbols=["H", "GE", "H", "H", "H", "O", "H"], ts=geh4oh_ts,
+                   mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

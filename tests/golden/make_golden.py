@@ -27,7 +27,7 @@ def main():
         V, g, _ = O.egrad(name, q)
         pes[name] = dict(q=q.tolist(), V=V.tolist(), g=g.tolist())
     # surfaces added later draw from their own stream so that the records above stay as first generated
-    for k, name in enumerate(("ch4oh",)):
+    for k, name in enumerate(("ch4oh", "geh4oh")):
         r2 = np.random.default_rng(C.SEED + 100 + k)
         q = np.concatenate([C.SYSTEMS[name]["ts"]()[None], C.ts_cloud(name, 15, 0.15, r2)])
         V, g, _ = O.egrad(name, q)

@@ -16,7 +16,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name,sigma,n", [("h3", 0.15, 100000), ("h3", 0.5, 30000), ("oh3", 0.15, 100000),
                                           ("oh3", 0.5, 30000), ("ch4h", 0.15, 100000), ("ch4h", 0.4, 30000),
                                           ("brh2", 0.15, 100000), ("brh2", 0.5, 30000), ("o3", 0.15, 100000), ("o3", 0.4, 30000),
-                                          ("ch4oh", 0.15, 100000), ("ch4oh", 0.4, 30000)])
+                                          ("ch4oh", 0.15, 100000), ("ch4oh", 0.4, 30000),
+                                          ("geh4oh", 0.15, 100000), ("geh4oh", 0.4, 30000)])
 def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, n, sigma, rng)
@@ -79,7 +80,7 @@ def test_h3_compact_branch_and_warning_bits(gpu, oracle):
     assert info == oinfo == 2
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh"])
 def test_invariances_at_scale(gpu, name):
     """size-independent properties on 1e6 images: rigid motions and permutations of equivalent
     hydrogens leave E unchanged and rotate/permute the gradient."""
@@ -101,7 +102,7 @@ def test_invariances_at_scale(gpu, name):
     # net force and torque vanish
     assert np.abs(g.sum(axis=1)).max() < 1e-10
     perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5], "brh2": [2, 1, 0], "o3": [1, 2, 0],
-            "ch4oh": [3, 1, 2, 0, 4, 5, 6]}[name]
+            "ch4oh": [3, 1, 2, 0, 4, 5, 6], "geh4oh": [0, 1, 3, 2, 4, 5, 6]}[name]
     V3, g3, _ = gpu.egrad(name, q[:, perm])
     ok = np.ones(len(q), dtype=bool)
     if name == "brh2":
