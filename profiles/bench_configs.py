@@ -183,5 +183,20 @@ for nb, nsteps in ((1, 200), (8, 200)):
            cpu_bead_steps_per_s_one_core=1.0 / cpu_img)
     g.close()
 
+# ---- N4: the 7-atom CBE-family surfaces (one-lane PesCBE1<K>), recrossing children at config 2's shape ----------
+for name in ("ch4oh", "geh4oh"):
+    nb, npairs, evol = 16, 512, 500
+    g, o = C.make_pair(name, nb)
+    g.set_seed(C.SEED)
+    qp = np.array([C.ring_polymer(name, nb, rng, 0.01) for _ in range(8)])
+    sec = timed(lambda: g.recross_children(qp, npairs, evol, 0.98), reps=2)
+    t0 = time.perf_counter()
+    o.recross_children(qp, 0, 2, 50, 0.98, C.SEED, nthreads=1)
+    cpu = 2 * 2 * nb * 50 / (time.perf_counter() - t0)
+    report(config="N4 calc_rate %s (egrad_%s) 16 beads, %d children x %d steps" % (name, name, 2 * npairs, evol),
+           ntraj=2 * npairs, steps=evol, gpu_bead_steps_per_s=2 * npairs * nb * evol / sec,
+           cpu_bead_steps_per_s_one_core=cpu)
+    g.close()
+
 if len(sys.argv) > 1:
     json.dump(rows, open(sys.argv[1], "w"), indent=1)
