@@ -11,6 +11,19 @@ cnt_counters g_cnt = {0, 0, 0, 0, 0, 0};
 #include "pes_ch4h.c"
 #include "pes_brh2.c"
 #include "pes_o3.c"
+// the 7-atom members of the CBE family are the CH4 + H source compiled again (pes_ch4oh.c, pes_geh4oh.c)
+// (ipow takes the counting type, which lives in the global namespace: renamed so that argument-dependent lookup
+// does not see the copy of the first inclusion)
+namespace cbe_ch4oh {
+#define ipow ipow_ch4oh
+#include "pes_ch4oh.c"
+#undef ipow
+}
+namespace cbe_geh4oh {
+#define ipow ipow_geh4oh
+#include "pes_geh4oh.c"
+#undef ipow
+}
 
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
@@ -21,7 +34,7 @@ static void census(const char* name, egrad_fn fn, int nat, const double* ts, int
     cnt_counters z = {0, 0, 0, 0, 0, 0};
     g_cnt = z;
     for (int s = 0; s < n; s++) {
-        real q[18], V[1], g[18];
+        real q[21], V[1], g[21];
         int info;
         for (int i = 0; i < 3 * nat; i++) q[i] = cnt_real(ts[i] + nd(gen));
         fn(q, nat, 1, V, g, &info);
@@ -50,7 +63,17 @@ int main()
     census("ch4h", oracle_egrad_ch4h_real, 6, ch5, 2000, false);
     const double o3[9] = {0, 0, 0, 1.60 / b, 0, 0, -0.4017 / b, 1.2364 / b, 0};
     census("brh2", oracle_egrad_brh2_real, 3, brh2, 2000, false);
-    census("o3", oracle_egrad_o3_real, 3, o3, 2000, true);
+    census("o3", oracle_egrad_o3_real, 3, o3, 2000, false);
+    // examples/explore/ts_irc_ch4oh/ts_start.xyz; tests/common.py geh4oh_ts
+    const double ch4oh[21] = {-4.62878267 / b, 1.25606861 / b, 0.95459788 / b, -4.85261637 / b, 2.15380812 / b, 0.37457524 / b,
+                              -4.27740626 / b, 2.99438311 / b, 0.76831501 / b, -4.53003946 / b, 1.95346377 / b, -0.88649386 / b,
+                              -5.91912714 / b, 2.37708958 / b, 0.44643735 / b, -4.21407574 / b, 1.75722671 / b, -2.12170961 / b,
+                              -3.93964920 / b, 2.62885961 / b, -2.44704966 / b};
+    census("ch4oh", cbe_ch4oh::oracle_egrad_ch4oh_real, 7, ch4oh, 2000, false);
+    const double t0 = 1.62 * s3 / b, t1 = 1.525 * s3 / b, to = 2.97 * s3 / b;
+    const double geh4oh[21] = {t0, t0, t0, 0, 0, 0, t1, -t1, -t1, -t1, t1, -t1, -t1, -t1, t1, to, to, to,
+                               to + 0.97 * 0.6650 / b, to - 0.97 * 0.6820 / b, to - 0.97 * 0.3040 / b};
+    census("geh4oh", cbe_geh4oh::oracle_egrad_geh4oh_real, 7, geh4oh, 2000, true);
     printf("}\n");
     return 0;
 }

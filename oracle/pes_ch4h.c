@@ -967,6 +967,10 @@ static void ch4h_ipbend(const ch4h_par *p, ch4h_state *s, real *vip_out)
 }
 
 /* ---- POT_ch4h (:161-285): R(1..18) cartesians in bohr -> energy (hartree), DEGSDR ---- */
+#undef CBE_NC
+#undef CBE_NAT
+#undef CBE_EGRAD
+#undef CBE_PARTS
 #if defined(CBE_GEH4OH)
 #define CBE_NC 21   /* pot_geh4oh :84-217 */
 #define CBE_NAT 7

@@ -28,10 +28,9 @@ for name in ("h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh"):
     for _ in range(4):
         g.egrad(q)
     ms = float(np.min(g.kernel_timings()[1:]))
-    # no census entry (ch4oh): the operation count of the CH4 + H template it extends is a lower bound
-    fl = census[name]["flops"] if name in census else census["ch4h"]["flops"]
+    fl = census[name]["flops"]
     natoms = q.shape[1]
-    row = dict(pes=name, flops_source="census" if name in census else "ch4h census (lower bound)", images=nimg, kernel_ms=ms, evaluations_per_s=nimg / (ms * 1e-3), flops_per_evaluation=fl,
+    row = dict(pes=name, images=nimg, kernel_ms=ms, evaluations_per_s=nimg / (ms * 1e-3), flops_per_evaluation=fl,
                achieved_tflops=nimg * fl / (ms * 1e-3) / 1e12, dfma_peak_tflops=peak, frac=nimg * fl / (ms * 1e-3) / 1e12 / peak,
                algorithmic_bytes_per_evaluation=48 * natoms + 8, hbm_gbs=nimg * (48 * natoms + 8) / (ms * 1e-3) / 1e9)
     rows.append(row)
