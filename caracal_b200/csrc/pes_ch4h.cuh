@@ -511,19 +511,23 @@ using PesCH4H = PesCBE1<ch4h::K6>;
 #ifdef __CUDACC__
 namespace crcl {
 
-struct PesCH4H4 {
-    static constexpr int NATOMS = 6;
-    static constexpr int ID = CRCL_PES_CH4H;
+// K as for PesCBE1: ch4h::K6 (6 atoms), or a 7-atom member with K::HAS_OH, whose added terms split the same way --
+// lane x evaluates the H_x-O-H(O) bend of its own hydrogen, lane 0 the O-H(O) Morse bond.
+template <class K>
+struct PesCBE4 {
+    static constexpr int NATOMS = K::NATOMS;
+    static constexpr int ID = K::ID;
     static constexpr int LANES = 4;
-    static constexpr int NOWN = 5;  // components owned per lane (5,5,4,4 of 18)
+    static constexpr int NOWN = K::HAS_OH ? 6 : 5;  // components owned per lane (5,5,4,4 of 18; 6,5,5,5 of 21)
 
     // component (atom*3+xyz) number k owned by lane x, or -1: the lane's hydrogen, then C and H_b
-    // spread as lane0: Cx,Cy  lane1: Cz,Bx  lane2: By  lane3: Bz
+    // spread as lane0: Cx,Cy  lane1: Cz,Bx  lane2: By  lane3: Bz; with H(O): lane2: x  lane3: y  lane0: z
     __device__ static __forceinline__ int owned(int x, int k)
     {
         if (k < 3) return 3 * ((x == 3) ? 0 : x + 2) + k;
         if (k == 3) return (x == 0) ? 3 : (x == 1) ? 5 : (x == 2) ? 16 : 17;
-        return (x == 0) ? 4 : (x == 1) ? 15 : -1;
+        if (k == 4) return (x == 0) ? 4 : (x == 1) ? 15 : (K::HAS_OH ? (x == 2 ? 18 : 19) : -1);
+        return (x == 0) ? 20 : -1;
     }
 
     // q(c): position component c of this image (any callable); x: lane 0..3; mask: shuffle mask.
@@ -559,55 +563,55 @@ struct PesCH4H4 {
         // own switching functions
         double sw[10];  // s1,ds1,s2,ds2,s3,ds3,sphi,dsphi,sth,dsth
         {
-            const double r = rcho, dr = r - R0CH;
+            const double r = rcho, dr = r - K::R0CH;
             double omt, ms2;
             {
-                const double u = r - B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
-                const double arg = A1S * dr * u8;
+                const double u = r - K::B1S, u2 = u * u, u4 = u2 * u2, u7 = u4 * u2 * u, u8 = u4 * u4;
+                const double arg = K::A1S * dr * u8;
                 one_minus_tanh(arg, omt, ms2);
                 const bool on = arg < 19.0;
                 sw[0] = on ? omt : 0.0;
-                sw[1] = on ? A1S * (u8 + 8.0 * dr * u7) * ms2 : 0.0;
+                sw[1] = on ? K::A1S * (u8 + 8.0 * dr * u7) * ms2 : 0.0;
             }
             {
-                const double u = r - B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
-                const double arg = A2S * dr * u6;
+                const double u = r - K::B2S, u2 = u * u, u4 = u2 * u2, u5 = u4 * u, u6 = u4 * u2;
+                const double arg = K::A2S * dr * u6;
                 one_minus_tanh(arg, omt, ms2);
                 const bool on = arg < 19.0;
                 sw[2] = on ? omt : 0.0;
-                sw[3] = on ? A2S * (u6 + 6.0 * dr * u5) * ms2 : 0.0;
+                sw[3] = on ? K::A2S * (u6 + 6.0 * dr * u5) * ms2 : 0.0;
             }
             {
-                const double u = r - B3S;
-                const double arg = A3S * dr * u * u;
+                const double u = r - K::B3S;
+                const double arg = K::A3S * dr * u * u;
                 one_minus_tanh(arg, omt, ms2);
                 const bool on = arg < 19.0;
                 sw[4] = on ? omt : 0.0;
-                sw[5] = on ? A3S * (3.0 * r * r - 2.0 * r * (R0CH + 2.0 * B3S) + B3S * (B3S + 2.0 * R0CH)) * ms2 : 0.0;
+                sw[5] = on ? K::A3S * (3.0 * r * r - 2.0 * r * (K::R0CH + 2.0 * K::B3S) + K::B3S * (K::B3S + 2.0 * K::R0CH)) * ms2 : 0.0;
             }
             {
-                const bool on = r < 3.8;
-                const double u = r - CPHI, ex = exp(BPHI * u * u * u);
-                one_minus_tanh(APHI * dr * ex, omt, ms2);
-                sw[6] = on ? omt : 0.0;
-                sw[7] = on ? APHI * (1.0 + 3.0 * BPHI * dr * u * u) * ex * ms2 : 0.0;
-                const double v = r - CTHETA, ev = exp(BTHETA * v * v * v);
-                one_minus_tanh(ATHETA * dr * ev, omt, ms2);
+                const bool on = r < 3.8, onphi = K::SPHI_ANY_R || on;
+                const double u = r - K::CPHI, ex = exp(K::BPHI * u * u * u);
+                one_minus_tanh(K::APHI * dr * ex, omt, ms2);
+                sw[6] = onphi ? omt : 0.0;
+                sw[7] = onphi ? K::APHI * (1.0 + 3.0 * K::BPHI * dr * u * u) * ex * ms2 : 0.0;
+                const double v = r - K::CTHETA, ev = exp(K::BTHETA * v * v * v);
+                one_minus_tanh(K::ATHETA * dr * ev, omt, ms2);
                 sw[8] = on ? omt : 0.0;
-                sw[9] = on ? ATHETA * (1.0 + 3.0 * BTHETA * dr * v * v) * ev * ms2 : 0.0;
+                sw[9] = on ? K::ATHETA * (1.0 + 3.0 * K::BTHETA * dr * v * v) * ev * ms2 : 0.0;
             }
         }
         // own f1 and derivatives (ipforce_ch4h)
         double f1o, df1co, df1ho;
         {
-            const double dr = rcho - R0CH, dh = rbho - R0HH;
-            const double e1 = exp(-AA1 * rbho * rbho);
-            const double e2 = exp(-AA4 * dh * dh);
-            const double a1 = 1.0 - e1, a2 = AA2 + AA3 * e2;
+            const double dr = rcho - K::R0CH, dh = rbho - K::R0HH;
+            const double e1 = exp(-K::AA1 * rbho * rbho);
+            const double e2 = exp(-K::AA4 * dh * dh);
+            const double a1 = 1.0 - e1, a2 = K::AA2 + K::AA3 * e2;
             const double E = exp(-a2 * dr * dr);
             f1o = a1 * E;
             df1co = -2.0 * dr * a1 * a2 * E;
-            df1ho = 2.0 * AA1 * rbho * e1 * E + 2.0 * AA3 * AA4 * dh * e2 * dr * dr * a1 * E;
+            df1ho = 2.0 * K::AA1 * rbho * e1 * E + 2.0 * K::AA3 * K::AA4 * dh * e2 * dr * dr * a1 * E;
         }
         // rotated gathers: local t <-> hydrogen (x+t)&3
         double c[4][3], rch[4], irch[4], s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
@@ -636,7 +640,7 @@ struct PesCH4H4 {
             }
         }
         const double tau = acos(-1.0 / 3.0);
-        const double ta = tau - 0.5 * PI, tb = tau - 2.0 * PI / 3.0;
+        const double ta = tau - K::TAU_PLANAR * PI, tb = tau - 2.0 * PI / 3.0;
         auto theta0 = [&](int i, int j, int k, int l) {
             return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
         };
@@ -648,16 +652,16 @@ struct PesCH4H4 {
         // ---- stretching, own triple (C-H_x, C-H_b, H_b-H_x) ----
         {
             const double rav = (rch[0] + rch[1] + rch[2] + rch[3]) / 4.0;
-            const double arga = C1CH * (rav - R0CH);
+            const double arga = K::C1CH * (rav - K::R0CH);
             double omt, ms2;
             one_minus_tanh(arga, omt, ms2);
             const bool on = arga < 19.0;
-            const double ach = on ? A1CH + B1CH * (2.0 - omt) * 0.5 : A1CH + B1CH;
-            const double dach = on ? -B1CH * C1CH * 0.5 * ms2 * 0.25 : 0.0;
-            const Leps cb = leps(D1CB, D3CB, ACB, rcb - R0CB);
-            const double dr = rcho - R0CH;
-            const Leps ch = leps(D1CH, D3CH, ach, dr);
-            const Leps bh = leps(D1HH, D3HH, AHH, rbho - R0HH);
+            const double ach = on ? K::A1CH + K::B1CH * (2.0 - omt) * 0.5 : K::A1CH + K::B1CH;
+            const double dach = on ? -K::B1CH * K::C1CH * 0.5 * ms2 * 0.25 : 0.0;
+            const Leps cb = leps(K::D1CB, K::D3CB, K::ACB, rcb - K::R0CB);
+            const double dr = rcho - K::R0CH;
+            const Leps ch = leps(K::D1CH, K::D3CH, ach, dr);
+            const Leps bh = leps(K::D1HH, K::D3HH, K::AHH, rbho - K::R0HH);
             const double a = ch.vj, b = cb.vj, cc = bh.vj;
             const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
             en += ch.vq + cb.vq + bh.vq + vj;
@@ -676,7 +680,7 @@ struct PesCH4H4 {
         {
             const double pj = s3[1], pk = s3[2], pl = s3[3];
             const double swi = (1.0 - s3[0]) * pj * pk * pl;
-            const double fd = swi * FCH3, hd = swi * HCH3;
+            const double fd = swi * K::FCH3, hd = swi * K::HCH3;
             double a[3], b[3], n[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
@@ -729,7 +733,7 @@ struct PesCH4H4 {
                 }
             }
             en += fd * sum2 + hd * sum4;
-            const double fs = FCH3 * sum2 + HCH3 * sum4;
+            const double fs = K::FCH3 * sum2 + K::HCH3 * sum4;
             Dch[0] -= fs * ds3[0] * pj * pk * pl;
             Dch[1] += fs * (1.0 - s3[0]) * ds3[1] * pk * pl;
             Dch[2] += fs * (1.0 - s3[0]) * pj * ds3[2] * pl;
@@ -737,18 +741,18 @@ struct PesCH4H4 {
         }
         // ---- in-plane bending: pair local (0,1) on every lane, local (0,2) on lanes 0 and 1 ----
         {
-            constexpr double f0 = FKINF + AK, f2 = FKINF;
+            constexpr double f0 = K::FKINF + K::AK, f2 = K::FKINF;
 #pragma unroll
             for (int pp = 0; pp < 2; pp++) {
                 const int j = pp + 1, k = pp ? 1 : 2, l = 3;
                 if (pp == 1 && x >= 2) break;
                 const double fk0 = f0 + f0 * (s1[0] * s1[j] - 1.0) + (f0 - f2) * (s2[k] * s2[l] - 1.0);
                 const double ff = f1[0] * f1[j];
-                const double K = fk0 * ff;
+                const double Kf = fk0 * ff;
                 const double cs = dot(c[0], c[j]);
                 const double del = acos(cs) - theta0(0, j, k, l);
-                en += 0.5 * K * del * del;
-                const double w = K * del;
+                en += 0.5 * Kf * del * del;
+                const double w = Kf * del;
                 const double wc = -w * rsqrt(1.0 - cs * cs);
                 const double fi = wc * irch[0], fj = wc * irch[j];
 #pragma unroll
@@ -768,6 +772,51 @@ struct PesCH4H4 {
                 Dbh[j] += hd2 * fk0 * f1[0] * df1h[j];
             }
         }
+        double gO[3] = {0, 0, 0}, gBx[3] = {0, 0, 0};   // explicit vector parts on H(O) and on the abstracting atom
+        if constexpr (K::HAS_OH) {
+            double tno[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) tno[d] = q(18 + d) * 0.52918 - q(15 + d) * 0.52918;
+            const double rno = sqrt(dot(tno, tno));
+            // O-H(O) Morse bond (stretch_ch4oh :616-621, :652-659, :769-774): lane 0 only
+            const double m0 = (x == 0) ? 1.0 : 0.0;
+            const double ex = exp(-K::AHH * (rno - K::R0HH)), om = 1.0 - ex;
+            en += m0 * K::D1HH * (om * om);
+            const double de = m0 * 2.0 * K::AHH * K::D1HH * om * ex / rno;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                gBx[d] -= de * tno[d];
+                gO[d] += de * tno[d];
+            }
+            // H_x-O-H(O) bend of the own hydrogen (ipbend_ch4oh :1059-1171)
+            double tbv[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) tbv[d] = -ubo[d] * rbho;
+            double cs = -dot(tno, tbv) / (rno * rbho);
+            cs = fmin(1.0, fmax(-1.0, cs));
+            const double dang = acos(cs) - K::ANH2OEQ;
+            const double arga = K::ALPH2O * (rbho - K::R0HH);
+            double omt, ms2;
+            one_minus_tanh(arga, omt, ms2);
+            const double fk = (arga < 19.0) ? K::FKH2OEQ * omt : 0.0;
+            en += 0.5 * fk * dang * dang;
+            Dbh[0] += K::FKH2OEQ * K::ALPH2O * ms2 * (0.5 * dang * dang);
+            const double dstda = fk * dang;
+            double pv[3], v1[3], v2[3];
+            cross(tno, tbv, pv);
+            double rp = sqrt(dot(pv, pv));
+            if (rp < 1.0e-6) rp = 1.0e-6;
+            const double terma = dstda / (rbho * rbho * rp), termc = dstda / (rno * rno * rp);
+            cross(tbv, pv, v1);
+            cross(tno, pv, v2);
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const double hi = -terma * v1[d], ho = -termc * v2[d];
+                gH[0][d] += hi;
+                gO[d] += ho;
+                gBx[d] += -hi - ho;
+            }
+        }
         // ---- reduce-scatter to the owner lane: hydrogen y collects local t from lane y-t ----
         double DchT = Dch[0], DbhT = Dbh[0], gHT[3] = {gH[0][0], gH[0][1], gH[0][2]};
 #pragma unroll
@@ -784,7 +833,7 @@ struct PesCH4H4 {
             const double vc = DchT * co[d], vb = DbhT * ubo[d], vcb = Dcb * ucb[d];
             gHT[d] += vc + vb;
             gC[d] -= vc + vcb;
-            gB[d] = vcb - vb;
+            gB[d] = vcb - vb + gBx[d];
         }
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
@@ -792,6 +841,7 @@ struct PesCH4H4 {
             for (int d = 0; d < 3; d++) {
                 gC[d] += __shfl_xor_sync(mask, gC[d], o, 4);
                 gB[d] += __shfl_xor_sync(mask, gB[d], o, 4);
+                if constexpr (K::HAS_OH) gO[d] += __shfl_xor_sync(mask, gO[d], o, 4);
             }
             en += __shfl_xor_sync(mask, en, o, 4);
         }
@@ -801,10 +851,13 @@ struct PesCH4H4 {
         gown[1] = gHT[1] * GF;
         gown[2] = gHT[2] * GF;
         gown[3] = ((x == 0) ? gC[0] : (x == 1) ? gC[2] : (x == 2) ? gB[1] : gB[2]) * GF;
-        gown[4] = ((x == 0) ? gC[1] : (x == 1) ? gB[0] : 0.0) * GF;
+        gown[4] = ((x == 0) ? gC[1] : (x == 1) ? gB[0] : K::HAS_OH ? ((x == 2) ? gO[0] : gO[1]) : 0.0) * GF;
+        if constexpr (K::HAS_OH) gown[5] = (x == 0) ? gO[2] * GF : 0.0;
         return 0;
     }
 };
+
+using PesCH4H4 = PesCBE4<ch4h::K6>;
 
 }  // namespace crcl
 #endif

@@ -69,5 +69,10 @@ struct K7 : ch4oh::K7 {
 }  // namespace geh4oh
 
 using PesGeH4OH = PesCBE1<geh4oh::K7>;
+#ifdef __CUDACC__
+// four lanes per bead in the trajectory kernels (pes_ch4h.cuh, PesCBE4): lane x owns methane / germane hydrogen x
+using PesCH4OH4 = PesCBE4<ch4oh::K7>;
+using PesGeH4OH4 = PesCBE4<geh4oh::K7>;
+#endif
 
 }  // namespace crcl

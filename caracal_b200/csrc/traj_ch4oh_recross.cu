@@ -2,5 +2,5 @@
 #include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
 namespace crcl {
-CRCL_DECLARE_TRAJ(launch_ch4oh_recross) { return launch_traj_pes<PesCH4OH, K_RECROSS>(nbeads, A, bias_mode, nose_q, s, nosup); }
+CRCL_DECLARE_TRAJ(launch_ch4oh_recross) { return launch_traj_pes<PesCH4OH4, K_RECROSS>(nbeads, A, bias_mode, nose_q, s, nosup); }
 }  // namespace crcl

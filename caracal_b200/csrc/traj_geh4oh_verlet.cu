@@ -2,5 +2,5 @@
 #include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
 namespace crcl {
-CRCL_DECLARE_TRAJ(launch_geh4oh_verlet) { return launch_traj_pes<PesGeH4OH, K_VERLET>(nbeads, A, bias_mode, nose_q, s, nosup); }
+CRCL_DECLARE_TRAJ(launch_geh4oh_verlet) { return launch_traj_pes<PesGeH4OH4, K_VERLET>(nbeads, A, bias_mode, nose_q, s, nosup); }
 }  // namespace crcl
