@@ -4,8 +4,8 @@
 // Replaces /root/reference/src/egrad_ch4oh.f: egrad_ch4oh :69-124, POT_ch4oh :157-286 and the routines below it.
 // That file is the CH4 + H template of egrad_ch4h.f with the abstracting atom an oxygen, its own BLOCK DATA
 // (:2066-2106, scaled once as PREPOT_ch4oh :1989-2002 does), its own switching constants (:1808-1811) and three
-// added terms; the evaluation is PesCBE1 of pes_ch4h.cuh with the constants below (K::HAS_OH selects the added
-// terms).  Atom order H, C, H, H, H, O, H(O) (nnc=2, nnb=6, nnh=3,4,5,1, nno=7); the four methane hydrogens are
+// added terms; the evaluation is PesCBE1 (one thread per image, crcl_egrad) and PesCBE4 (four lanes per
+// bead, trajectory kernels) of pes_ch4h.cuh with the constants below (K::HAS_OH selects the added terms).  Atom order H, C, H, H, H, O, H(O) (nnc=2, nnb=6, nnh=3,4,5,1, nno=7); the four methane hydrogens are
 // equivalent, any of them can be the one abstracted (the shipped examples/explore/ts_irc_ch4oh/ts_start.xyz
 // transfers atom 4).
 #pragma once
