@@ -475,7 +475,8 @@ struct PesCBE1 {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             double cC = gC[d] - Dcb * ucb[d];
-            double cB = Dcb * ucb[d] + gBx[d];
+            double cB = Dcb * ucb[d];
+            if constexpr (K::HAS_OH) cB += gBx[d];
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 const double vc = Dch[x] * c[x][d], vb = Dbh[x] * ubh[x][d];
@@ -833,7 +834,8 @@ struct PesCBE4 {
             const double vc = DchT * co[d], vb = DbhT * ubo[d], vcb = Dcb * ucb[d];
             gHT[d] += vc + vb;
             gC[d] -= vc + vcb;
-            gB[d] = vcb - vb + gBx[d];
+            gB[d] = vcb - vb;
+            if constexpr (K::HAS_OH) gB[d] += gBx[d];   // (x + 0.0 is not a no-op in IEEE arithmetic: keep it out of the 6-atom code)
         }
 #pragma unroll
         for (int o = 1; o < 4; o <<= 1) {
