@@ -269,6 +269,16 @@ class RPMD:
         self._ck(self._lib.crcl_set_thermostat(self._h, int(thermostat), int(andersen_step), float(kelvin),
                                                float(nose_q)), "crcl_set_thermostat")
 
+    def set_box(self, periodic, box=None):
+        """pbc_mod: periodic, boxlen_x/y/z (bohr) -> periodic wrap of verlet.f90:591-641 (set_qmdff / set_water set it too)"""
+        b = _f64([0.0, 0.0, 0.0] if box is None else box)
+        self._ck(self._lib.crcl_set_box(self._h, int(bool(periodic)), _dp(b)), "crcl_set_box")
+
+    def set_rpmd_check(self, on, energy_ts=0.0, energy_tol=0.0, xi_tol=0.0):
+        """rpmd_check.f90:88-116 after every step of the biased / constrained modes: status bits TRAJ_ENERGY / TRAJ_XI_RANGE"""
+        self._ck(self._lib.crcl_set_rpmd_check(self._h, int(bool(on)), float(energy_ts), float(energy_tol), float(xi_tol)),
+                 "crcl_set_rpmd_check")
+
     def set_seed(self, seed):
         self._ck(self._lib.crcl_set_seed(self._h, int(seed)), "crcl_set_seed")
 
@@ -378,6 +388,28 @@ class RPMD:
                                                  int(equi_steps), int(sample_steps), int(constrain), int(traj_id0),
                                                  _dp(avg), _dp(var), _ip(st)), "crcl_umbrella_windows")
         return avg, var, st
+
+    # -- multi-GPU: NCCL communicator behind the C-ABI ----------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the 128 bytes every rank hands to comm_init (ship them with MPI / torch.distributed / a file)"""
+        buf = ctypes.create_string_buffer(128)
+        _l.check(_l.load().crcl_comm_unique_id(buf), None, "crcl_comm_unique_id")
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        """collective; afterwards recross_children(_dev) and umbrella_windows take the GLOBAL unit range on every
+        rank and return the result of the whole job (all-reduce inside the library)"""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self._lib.crcl_comm_init(self._h, int(nranks), int(rank), buf), "crcl_comm_init")
+
+    def comm_destroy(self):
+        self._ck(self._lib.crcl_comm_destroy(self._h), "crcl_comm_destroy")
+
+    def comm_info(self):
+        n, r, v = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        self._ck(self._lib.crcl_comm_info(self._h, ctypes.byref(n), ctypes.byref(r), ctypes.byref(v)), "crcl_comm_info")
+        return n.value, r.value, v.value
 
     # -- hooks ------------------------------------------------------------------------------------
     def rng_normals(self, seed, traj, event, bead, n):

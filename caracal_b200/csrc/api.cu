@@ -22,6 +22,7 @@
 #include "dgevb.cuh"
 #include "ewald.cuh"
 #include "water.cuh"
+#include "comm.cuh"
 
 using namespace crcl;
 
@@ -45,6 +46,11 @@ struct crcl_handle_s {
     crcl_host_grad_fn cb = nullptr;
     void* cb_user = nullptr;
     int path = CRCL_PATH_AUTO;
+    // pbc_mod (wrap of verlet.f90:591-641) and the rpmd_check settings
+    int periodic = 0;
+    double box[3] = {0.0, 0.0, 0.0};
+    int chk_on = 0;
+    double chk_energy_ts = 0.0, chk_energy_tol = 0.0, chk_xi_tol = 0.0;
     bool use_graph = true;   // split path: replay steps from a CUDA graph (crcl_set_graph)
     QmdffDev* qmdff = nullptr;
     QmdffDev* qmdff2 = nullptr;
@@ -60,6 +66,7 @@ struct crcl_handle_s {
     std::vector<double> wfrag_h;
     std::vector<double> hostbuf_q, hostbuf_g, hostbuf_v;
     long long launches = 0;
+    Comm* comm = nullptr;   // NCCL communicator of the job (crcl_comm_init); null = single process
     std::string err;
     // grow-only device scratch
     void* scratch[32] = {nullptr};
@@ -327,6 +334,9 @@ static void fill_args(crcl_handle h, TrajArgs& A)
     A.mech = h->mech;
     A.seed = h->seed;
     A.fker = h->d_fker;
+    A.chk_on = h->chk_on;
+    A.chk_emax = (h->chk_energy_ts + h->chk_energy_tol) * h->nbeads;   // rpmd_check.f90:100
+    A.chk_xi_tol = h->chk_xi_tol;
 }
 
 static int pes_natoms(int pes)
@@ -393,7 +403,7 @@ static bool fused_ok(crcl_handle h)
 }
 static bool use_split(crcl_handle h)
 {
-    if (h->path == CRCL_PATH_SPLIT) return true;
+    if (h->path == CRCL_PATH_SPLIT || h->periodic) return true;
     if (h->path == CRCL_PATH_FUSED) return false;
     return !fused_ok(h);
 }
@@ -571,6 +581,8 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
     A.traj_id = C.tid;
     A.traj_id0 = 0;
     A.event = C.event;
+    A.periodic = h->periodic;
+    for (int d = 0; d < 3; d++) A.box[d] = h->box[d];
     double mt = 0.0;
     for (int i = 0; i < na; i++) mt += h->mass[i];
     cudaStream_t s = h->stream;
@@ -615,6 +627,12 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
             h->launches++;
         } else if (constrain == 2) {
             sp_xi_value<<<tb, 64, 0, s>>>(h->mechd, na, ntraj, dcen, C.xi_ideal, C.xi_ideal_s, 2, C.xi_real);
+            h->launches++;
+        }
+        if (h->chk_on && constrain >= 0 && constrain != 2) {                  // rpmd_check.f90:88-116
+            sp_rpmd_check<<<(ntraj + 127) / 128, 128, 0, s>>>(ntraj, C.epot, C.xi_real, C.xi_ideal, C.xi_ideal_s,
+                                                              (h->chk_energy_ts + h->chk_energy_tol) * nb,
+                                                              h->chk_xi_tol, constrain != 1, C.status);
             h->launches++;
         }
         sp_kick<<<gel, 256, 0, s>>>(A);                                       // 13, 18
@@ -894,6 +912,7 @@ int crcl_destroy(crcl_handle h)
     if (!h) return CRCL_EINVAL;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    crcl_comm_destroy(h);
     for (auto& s : h->scratch)
         if (s) cudaFree(s);
     if (h->d_fker) cudaFree(h->d_fker);
@@ -1119,7 +1138,8 @@ int crcl_set_qmdff(crcl_handle h, const crcl_qmdff_tables* T)
     const char* msg = "";
     const int rc = qmdff_upload(T, &h->qmdff, &msg);
     if (rc) return fail(h, rc, msg);
-    return CRCL_OK;
+    // `periodic` and boxlen_* are one global state in the reference (pbc_mod): the integrator wraps when the PES is periodic
+    return crcl_set_box(h, T->periodic, T->box);
 }
 
 int crcl_set_qmdff2(crcl_handle h, const crcl_qmdff_tables* T)
@@ -1145,7 +1165,7 @@ int crcl_set_water(crcl_handle h, const crcl_water_params* P)
     const char* msg = "";
     const int rc = water_upload(P, &h->water, &msg);
     if (rc) return fail(h, rc, msg);
-    return CRCL_OK;
+    return crcl_set_box(h, P->periodic, P->box);
 }
 
 int crcl_set_dgevb(crcl_handle h, const crcl_dgevb_params* P)
@@ -1197,6 +1217,86 @@ int crcl_ewald_recip(crcl_handle h, int n, int nimg, const double* xyz, const do
     CK(cudaMemcpyAsync(energy, de, (size_t)nimg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(grad, dg, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return CRCL_OK;
+}
+
+int crcl_comm_unique_id(void* id_out)
+{
+    if (!id_out) return CRCL_EINVAL;
+    static_assert(sizeof(ncclUniqueId) == CRCL_UNIQUE_ID_BYTES, "CRCL_UNIQUE_ID_BYTES must be sizeof(ncclUniqueId)");
+    NcclApi* N = nccl_api(nullptr);
+    if (!N) return CRCL_ESTATE;
+    ncclUniqueId id;
+    if (N->GetUniqueId(&id) != ncclSuccess) return CRCL_ECUDA;
+    memcpy(id_out, &id, sizeof(id));
+    return CRCL_OK;
+}
+
+int crcl_comm_init(crcl_handle h, int nranks, int rank, const void* unique_id)
+{
+    if (!h || !unique_id || nranks < 1 || rank < 0 || rank >= nranks) return CRCL_EINVAL;
+    if (h->comm) return fail(h, CRCL_ESTATE, "crcl_comm_init: the handle already has a communicator");
+    std::string err;
+    NcclApi* N = nccl_api(&err);
+    if (!N) return fail(h, CRCL_ESTATE, err.c_str());
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof(id));
+    Comm* c = new Comm();
+    c->nranks = nranks;
+    c->rank = rank;
+    const ncclResult_t r = N->CommInitRank(&c->comm, nranks, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        h->err = std::string("ncclCommInitRank: ") + N->GetErrorString(r);
+        return CRCL_ECUDA;
+    }
+    h->comm = c;
+    return CRCL_OK;
+}
+
+int crcl_comm_destroy(crcl_handle h)
+{
+    if (!h) return CRCL_EINVAL;
+    if (h->comm) {
+        NcclApi* N = nccl_api(nullptr);
+        cudaStreamSynchronize(h->stream);
+        if (N && h->comm->comm) N->CommDestroy(h->comm->comm);
+        delete h->comm;
+        h->comm = nullptr;
+    }
+    return CRCL_OK;
+}
+
+int crcl_comm_info(crcl_handle h, int* nranks, int* rank, int* nccl_version)
+{
+    if (!h) return CRCL_EINVAL;
+    if (nranks) *nranks = h->comm ? h->comm->nranks : 1;
+    if (rank) *rank = h->comm ? h->comm->rank : 0;
+    if (nccl_version) {
+        *nccl_version = 0;
+        NcclApi* N = nccl_api(nullptr);
+        if (N) N->GetVersion(nccl_version);
+    }
+    return CRCL_OK;
+}
+
+int crcl_set_box(crcl_handle h, int periodic, const double* boxlen)
+{
+    if (!h || (periodic && !boxlen)) return CRCL_EINVAL;
+    if (periodic && !(boxlen[0] > 0 && boxlen[1] > 0 && boxlen[2] > 0)) return fail(h, CRCL_EINVAL, "box lengths must be positive");
+    h->periodic = periodic ? 1 : 0;
+    for (int d = 0; d < 3; d++) h->box[d] = periodic ? boxlen[d] : 0.0;
+    return CRCL_OK;
+}
+
+int crcl_set_rpmd_check(crcl_handle h, int on, double energy_ts, double energy_tol, double xi_tol)
+{
+    if (!h) return CRCL_EINVAL;
+    h->chk_on = on ? 1 : 0;
+    h->chk_energy_ts = energy_ts;
+    h->chk_energy_tol = energy_tol;
+    h->chk_xi_tol = xi_tol;
     return CRCL_OK;
 }
 
@@ -1587,16 +1687,30 @@ int crcl_calc_xi(crcl_handle h, int ncoord, const double* coords, const double* 
 }
 
 // ---- work-unit seam ---------------------------------------------------------------------------
-int crcl_recross_children_dev(crcl_handle h, const double* d_q_parents, int nparent, int pair0, int npairs,
-                              int child_evol, double xi_ideal, double* d_kappa_num, double* d_kappa_denom,
-                              int* d_status)
+// all-reduce (sum) over the ranks of the handle's communicator, in place, on the handle's stream
+static int comm_allreduce(crcl_handle h, void* a, size_t na, void* b, size_t nb, bool b_is_int)
 {
-    int rc = check_traj_call(h, 2);
-    if (rc) return rc;
-    if (!d_q_parents || !d_kappa_num || !d_kappa_denom || nparent <= 0 || npairs < 0 || child_evol < 0)
-        return CRCL_EINVAL;
-    CK(cudaSetDevice(h->device));
-    if ((rc = ensure_fker(h))) return rc;
+    std::string err;
+    NcclApi* N = nccl_api(&err);
+    if (!N) return fail(h, CRCL_ESTATE, err.c_str());
+    ncclResult_t r = N->GroupStart();
+    if (r == ncclSuccess && na) r = N->AllReduce(a, a, na, ncclDouble, ncclSum, h->comm->comm, h->stream);
+    if (r == ncclSuccess && nb) r = N->AllReduce(b, b, nb, b_is_int ? ncclInt : ncclDouble, ncclSum, h->comm->comm, h->stream);
+    const ncclResult_t r2 = N->GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) {
+        h->err = std::string("ncclAllReduce: ") + N->GetErrorString(r);
+        return CRCL_ECUDA;
+    }
+    return CRCL_OK;
+}
+
+// the rank-local part of the recrossing work unit: pairs [pair0, pair0+npairs)
+static int recross_local(crcl_handle h, const double* d_q_parents, int nparent, int pair0, int npairs,
+                         int child_evol, double xi_ideal, double* d_kappa_num, double* d_kappa_denom,
+                         int* d_status)
+{
+    int rc;
     const int ntraj = 2 * npairs;
     unsigned char* dth;
     double* dw;
@@ -1627,6 +1741,31 @@ int crcl_recross_children_dev(crcl_handle h, const double* d_q_parents, int npar
                                                             d_kappa_num, d_kappa_denom);
     h->launches++;
     CK(cudaGetLastError());
+    return CRCL_OK;
+}
+
+int crcl_recross_children_dev(crcl_handle h, const double* d_q_parents, int nparent, int pair0, int npairs,
+                              int child_evol, double xi_ideal, double* d_kappa_num, double* d_kappa_denom,
+                              int* d_status)
+{
+    int rc = check_traj_call(h, 2);
+    if (rc) return rc;
+    if (!d_q_parents || !d_kappa_num || !d_kappa_denom || nparent <= 0 || npairs < 0 || child_evol < 0)
+        return CRCL_EINVAL;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    if (!h->comm) return recross_local(h, d_q_parents, nparent, pair0, npairs, child_evol, xi_ideal, d_kappa_num,
+                                       d_kappa_denom, d_status);
+    // collective form (recross.f90:334-417 master/worker + :390,411 result messages): every rank passes the GLOBAL
+    // pair range, runs its contiguous block and receives the sums of the whole job
+    long long lo, cnt;
+    shard_range(npairs, h->comm->rank, h->comm->nranks, &lo, &cnt);
+    if (d_status) CK(cudaMemsetAsync(d_status, 0, (size_t)2 * npairs * sizeof(int), h->stream));
+    if ((rc = recross_local(h, d_q_parents, nparent, pair0 + (int)lo, (int)cnt, child_evol, xi_ideal, d_kappa_num,
+                            d_kappa_denom, d_status ? d_status + 2 * lo : nullptr)))
+        return rc;
+    if ((rc = comm_allreduce(h, d_kappa_num, (size_t)child_evol, d_kappa_denom, 1, false))) return rc;
+    if (d_status && npairs && (rc = comm_allreduce(h, nullptr, 0, d_status, (size_t)2 * npairs, true))) return rc;
     return CRCL_OK;
 }
 
@@ -1669,10 +1808,15 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     if (!q0 || !xi0 || !k_force || !avg || !var || nwin < 0 || ntraj < 0 || equi_steps < 0 || sample_steps <= 0 ||
         (constrain != 0 && constrain != 3))
         return CRCL_EINVAL;
-    const int ntot = nwin * ntraj;
-    if (ntot == 0) return CRCL_OK;
+    const int nglob = nwin * ntraj;
+    if (nglob == 0) return CRCL_OK;
     CK(cudaSetDevice(h->device));
     if ((rc = ensure_fker(h))) return rc;
+    // With a communicator the (window, trajectory) units of the whole job are partitioned over the ranks
+    // (calc_rate.f90:1351-1376 hands whole windows to MPI workers); this rank runs units [lo, lo+ntot)
+    long long lo = 0, cnt = nglob;
+    if (h->comm) shard_range(nglob, h->comm->rank, h->comm->nranks, &lo, &cnt);
+    const int ntot = (int)cnt;
     const size_t per = (size_t)h->nbeads * h->natoms * 3, n = per * ntot, nd = (size_t)ntot * h->natoms * 3;
     double *dq, *dp, *dg, *ddxi, *dep, *dnhc, *dwin, *dv;
     int* dst;
@@ -1684,24 +1828,27 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
         (rc = scratch(h, 21, (size_t)ntot * h->nbeads, &dv)))
         return rc;
     cudaStream_t s = h->stream;
+    std::vector<double> sums(2 * (size_t)ntot);
+    std::vector<int> st(ntot);
+    if (ntot > 0) {
     // every trajectory starts from its window's equilibrated structure (calc_rate.f90:1383-1387)
     std::vector<double> rep(n), win(2 * (size_t)ntot);
-    for (int w = 0; w < nwin; w++)
-        for (int t = 0; t < ntraj; t++) {
-            const size_t i = (size_t)w * ntraj + t;
-            memcpy(rep.data() + i * per, q0 + (size_t)w * per, per * sizeof(double));
-            win[i] = xi0[w];
-            win[ntot + i] = k_force[w];
-        }
+    for (int i = 0; i < ntot; i++) {
+        const int w = (int)((lo + i) / ntraj);
+        memcpy(rep.data() + (size_t)i * per, q0 + (size_t)w * per, per * sizeof(double));
+        win[i] = xi0[w];
+        win[ntot + i] = k_force[w];
+    }
     CK(cudaMemcpyAsync(dq, rep.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(dwin, win.data(), win.size() * sizeof(double), cudaMemcpyHostToDevice, s));
     CK(cudaMemsetAsync(dp, 0, n * sizeof(double), s));
     CK(cudaMemsetAsync(dev, 0, ntot * 2 * sizeof(uint32_t), s));
     CK(cudaMemsetAsync(dst, 0, ntot * sizeof(int), s));
     CK(cudaMemsetAsync(dep, 0, ntot * 4 * sizeof(double), s));
+    const uint32_t tid0 = traj_id0 + (uint32_t)lo;   // RNG streams are keyed by the GLOBAL unit index
     if (use_split(h)) {
         std::vector<uint32_t> ids(ntot);
-        for (int t = 0; t < ntot; t++) ids[t] = traj_id0 + (uint32_t)t;
+        for (int t = 0; t < ntot; t++) ids[t] = tid0 + (uint32_t)t;
         uint32_t* dtid;
         if ((rc = scratch(h, 27, (size_t)ntot, &dtid))) return rc;
         CK(cudaMemcpyAsync(dtid, ids.data(), ntot * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
@@ -1722,7 +1869,8 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
         C.k_force = dwin + ntot;
         if ((rc = mdinit_split(h, C, 2))) return rc;
         if (equi_steps > 0 && (rc = verlet_split(h, C, equi_steps, 0, constrain))) return rc;
-        if ((rc = crcl_egrad_dev(h, h->pes, dq, h->natoms, ntot * h->nbeads, dv, dg, nullptr))) return rc;
+        // plain forces before sampling (calc_rate.f90:1619-1623); split_forces also serves the host-callback PES
+        if ((rc = split_forces(h, ntot * h->nbeads, dq, dg, dv))) return rc;
         C.xi_sum = dep + 2 * ntot;
         C.xi_sum2 = dep + 3 * ntot;
         if ((rc = verlet_split(h, C, sample_steps, 0, constrain))) return rc;
@@ -1741,7 +1889,7 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     A.xi_real = dep + ntot;
     A.status = dst;
     A.nhc = dnhc;
-    A.traj_id0 = traj_id0;
+    A.traj_id0 = tid0;
     A.event = dev;
     if ((rc = launch_traj(h, K_MDINIT, A, 2))) return rc;
     A.nsteps = equi_steps;
@@ -1756,17 +1904,43 @@ int crcl_umbrella_windows(crcl_handle h, int nwin, const double* q0, const doubl
     A.xi_sum2 = dep + 3 * ntot;
     if ((rc = launch_traj(h, K_VERLET, A))) return rc;
     }
-    std::vector<double> sums(2 * (size_t)ntot);
     CK(cudaMemcpyAsync(sums.data(), dep + 2 * ntot, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    std::vector<int> st(ntot);
     CK(cudaMemcpyAsync(st.data(), dst, ntot * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    }
+    if (h->comm) {
+        for (int t = 0; t < nglob; t++) {
+            avg[t] = var[t] = 0.0;
+            if (status) status[t] = 0;
+        }
+    }
     for (int t = 0; t < ntot; t++) {
         // calc_rate.f90:1660-1664: av = sum/n, var = sum2/n - av^2
         const double a = sums[t] / sample_steps;
-        avg[t] = a;
-        var[t] = sums[ntot + t] / sample_steps - a * a;
-        if (status) status[t] = st[t];
+        avg[lo + t] = a;
+        var[lo + t] = sums[ntot + t] / sample_steps - a * a;
+        if (status) status[lo + t] = st[t];
+    }
+    if (h->comm) {
+        // the statistics files of calc_rate.f90:1690-1734 become one all-reduce: every rank fills its own slice of
+        // zero vectors (average, variance, status as doubles) and the vectors are summed
+        double* dred;
+        if ((rc = scratch(h, 28, (size_t)3 * nglob, &dred))) return rc;
+        std::vector<double> pack(3 * (size_t)nglob);
+        for (int t = 0; t < nglob; t++) {
+            pack[t] = avg[t];
+            pack[nglob + t] = var[t];
+            pack[2 * (size_t)nglob + t] = status ? (double)status[t] : 0.0;
+        }
+        CK(cudaMemcpyAsync(dred, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        if ((rc = comm_allreduce(h, dred, pack.size(), nullptr, 0, false))) return rc;
+        CK(cudaMemcpyAsync(pack.data(), dred, pack.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int t = 0; t < nglob; t++) {
+            avg[t] = pack[t];
+            var[t] = pack[nglob + t];
+            if (status) status[t] = (int)pack[2 * (size_t)nglob + t];
+        }
     }
     return CRCL_OK;
 }

@@ -37,7 +37,32 @@ struct SplitArgs {
     const uint32_t* traj_id;
     uint32_t traj_id0;
     uint32_t* event;
+    int periodic;           // pbc_mod: wrap of verlet.f90:591-641 after the position update
+    double box[3];          // boxlen_x, boxlen_y, boxlen_z
 };
+
+// Periodic wrap of one (atom, xyz) column of beads, plain-box branch of verlet.f90:591-641: the beads are visited in
+// order; while the visited bead lies below 0 (above L) ALL beads of the column are shifted by +L (-L); `tries` counts
+// both directions together and more than 100 is `fatal` in the reference (returns true; the caller sets
+// CRCL_TRAJ_PBC_FAIL).  get(b) / set(b, v) address bead b of the column.
+template <class Get, class Set>
+__device__ __forceinline__ bool sp_wrap_column(int nb, double boxlen, Get get, Set set)
+{
+    bool fail = false;
+    for (int i = 0; i < nb; i++) {
+        int tries = 0;
+        while (get(i) < 0 && tries <= 100) {
+            for (int b = 0; b < nb; b++) set(b, get(b) + boxlen);
+            tries++;
+        }
+        while (get(i) > boxlen && tries <= 100) {
+            for (int b = 0; b < nb; b++) set(b, get(b) - boxlen);
+            tries++;
+        }
+        fail |= tries > 100;
+    }
+    return fail;
+}
 
 // ---- kick + free ring polymer + centroid, beads in registers (NB <= 16 compile-time) ----------
 template <int NB>
@@ -99,6 +124,21 @@ __global__ void __launch_bounds__(128) sp_kick_freerp_reg(const SplitArgs A)
         for (int b = 0; b < NB; b++) {
             p[b] = pn[b];
             q[b] = qn[b];
+        }
+    }
+    if (A.periodic) {                                                     // 5
+        const double boxlen = A.box[c - 3 * atom];
+        bool out = false;
+#pragma unroll
+        for (int b = 0; b < NB; b++) out |= (q[b] < 0) || (q[b] > boxlen);
+        if (out) {   // rare: the column goes through local memory only on the step an atom crosses a face
+            double qw[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++) qw[b] = q[b];
+            if (sp_wrap_column(NB, boxlen, [&](int b) { return qw[b]; }, [&](int b, double v) { qw[b] = v; }))
+                atomicOr(&A.status[t], CRCL_TRAJ_PBC_FAIL);
+#pragma unroll
+            for (int b = 0; b < NB; b++) q[b] = qw[b];
         }
     }
     double cs = 0.0;
@@ -169,6 +209,21 @@ __global__ void sp_kick_freerp_smem(const SplitArgs A)
             A.p[i] = mv ? pn : 0.0;
             A.q[i] = qn;
             cs += qn;
+        }
+    }
+    if (A.periodic) {                                                     // 5: on the thread's own column in HBM
+        const double boxlen = A.box[c - 3 * atom];
+        bool out = false;
+        for (int b = 0; b < NB; b++) {
+            const double qv = A.q[base + (size_t)b * nc];
+            out |= (qv < 0) || (qv > boxlen);
+        }
+        if (out) {
+            if (sp_wrap_column(NB, boxlen, [&](int b) { return A.q[base + (size_t)b * nc]; },
+                               [&](int b, double v) { A.q[base + (size_t)b * nc] = v; }))
+                atomicOr(&A.status[t], CRCL_TRAJ_PBC_FAIL);
+            cs = 0.0;
+            for (int b = 0; b < NB; b++) cs += A.q[base + (size_t)b * nc];
         }
     }
     A.cen[t * nc + c] = cs / NB;

@@ -398,6 +398,21 @@ __global__ void sp_accum_xi(int ntraj, const double* __restrict__ xr, double* __
     s2[t] += xr[t] * xr[t];
 }
 // epot penalty of a failed SHAKE (verlet.f90:749-755)
+// rpmd_check.f90:88-116 after a step of the biased / constrained modes (see Traj::step in traj_kernel.cuh)
+__global__ void sp_rpmd_check(int ntraj, const double* __restrict__ epot, const double* __restrict__ xi_real,
+                              const double* __restrict__ xi_ideal, double xi_ideal_s, double emax, double xi_tol,
+                              int test_xi, int* __restrict__ status)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntraj) return;
+    const double e = epot[t];
+    int st = 0;
+    if (e != e || e > 1.79769313486231570815e308) st |= CRCL_TRAJ_NAN;
+    if (e > emax) st |= CRCL_TRAJ_ENERGY;
+    if (test_xi && fabs(xi_real[t] - (xi_ideal ? xi_ideal[t] : xi_ideal_s)) > xi_tol) st |= CRCL_TRAJ_XI_RANGE;
+    if (st) atomicOr(&status[t], st);
+}
+
 __global__ void sp_shake_penalty(int ntraj, const int* __restrict__ bad, double* __restrict__ epot)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -65,6 +65,10 @@ struct TrajArgs {
     unsigned char* theta;  // [nsteps][ntraj]: xi_real > 0 after step l
     double* weight;        // [ntraj]: v_s/f_s of the child
     double* denom_part;    // [ntraj]: v_s/f_s if v_s > 0 else 0
+    // rpmd_check.f90:100-116 after every step with constrain 0 / 1 / 3 (crcl_set_rpmd_check)
+    int chk_on;
+    double chk_emax;       // (ts_energy + energy_tol) * nbeads
+    double chk_xi_tol;
 };
 
 // The T = NB*LANES threads of one trajectory: a sub-warp segment when T <= 32 (32/T trajectories
@@ -730,6 +734,13 @@ struct Traj {
         }
         if (c <= 0)                                            // 19
             if (transrot()) status |= CRCL_TRAJ_SINGULAR;
+        // the drivers' rpmd_check right after verlet (rpmd_check.f90:88-116; calc_rate.f90:945,1575,1633,
+        // recross.f90:275 -- the latter passes xi_ideal twice, so the xi test only exists in the umbrella modes)
+        if (A.chk_on && c >= 0 && c != 2) {
+            if (epot != epot || epot > 1.79769313486231570815e308) status |= CRCL_TRAJ_NAN;
+            if (epot > A.chk_emax) status |= CRCL_TRAJ_ENERGY;
+            if (c != 1 && fabs(xi_real - xi_ideal) > A.chk_xi_tol) status |= CRCL_TRAJ_XI_RANGE;
+        }
     }
 
     // state <-> HBM in the reference layout [traj][bead][atom][xyz]
@@ -829,7 +840,7 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
     for (int s = 1; s <= A.nsteps; s++) {
         Grp::align_warps();
         // a failed trajectory is frozen (the reference aborts or restarts it)
-        if (!(T.status & (CRCL_TRAJ_SHAKE_FAIL | CRCL_TRAJ_NAN | CRCL_TRAJ_SINGULAR))) {
+        if (!(T.status & CRCL_TRAJ_FATAL)) {
             T.step(A.istep0 + s, (s & 15) == 0 || s == A.nsteps);
             sx += T.xi_real;
             sx2 += T.xi_real * T.xi_real;

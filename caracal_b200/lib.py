@@ -22,7 +22,8 @@ TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
 PATH_AUTO, PATH_FUSED, PATH_SPLIT = 0, 1, 2
 ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM", -4: "CRCL_ECUDA",
           -5: "CRCL_ENOSUP", -6: "CRCL_ESTATE"}
-TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_PESWARN = 0, 1, 2, 5, 16
+TRAJ_OK, TRAJ_SHAKE_FAIL, TRAJ_NAN, TRAJ_SINGULAR, TRAJ_ENERGY, TRAJ_PESWARN, TRAJ_XI_RANGE, TRAJ_PBC_FAIL = 0, 1, 2, 4, 8, 16, 32, 64
+TRAJ_FATAL = 1 | 2 | 4 | 8 | 32 | 64
 
 class WaterParams(ctypes.Structure):
     """crcl_water_params of include/caracal_gpu.h"""
@@ -88,6 +89,12 @@ SIGNATURES = {
                                                      ctypes.c_double, ctypes.c_double]),
     "crcl_set_thermostat": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double]),
     "crcl_set_seed": (ctypes.c_int, [_H, ctypes.c_uint64]),
+    "crcl_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "crcl_comm_init": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "crcl_comm_destroy": (ctypes.c_int, [_H]),
+    "crcl_comm_info": (ctypes.c_int, [_H, c_int_p, c_int_p, c_int_p]),
+    "crcl_set_box": (ctypes.c_int, [_H, ctypes.c_int, c_double_p]),
+    "crcl_set_rpmd_check": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]),
     "crcl_egrad": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
                                   c_int_p]),
     "crcl_egrad_dev": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

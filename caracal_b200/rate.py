@@ -78,30 +78,35 @@ def generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_
 
 
 def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, umbr_steps, traj_id0=1 << 20,
-                      max_retry=5, constrain=0, shard=None, device="cpu"):
+                      max_retry=5, constrain=0, shard=None, device="cpu", win0=0, nwin_global=None):
     """Phase 2: all windows x umbr_traj trajectories in one batch (crcl_umbrella_windows); returns the
     window averages and variances of xi as statistics/bias_* hold them (calc_rate.f90:1690-1700).
     shard = (rank, world): the windows are partitioned over the ranks (one GPU each) and the statistics
-    gathered with one all-reduce; RNG streams are keyed by the global window index, so the result does not
-    depend on the number of ranks."""
+    gathered with one all-reduce.  RNG streams are keyed by the GLOBAL window index -- trajectory t of global window
+    w uses stream traj_id0 + w*umbr_traj + t, and its r-th re-run traj_id0 + r*nwin_global*umbr_traj + w*umbr_traj + t
+    -- so neither the first pass nor a retry depends on the number of ranks (win0: global index of xi_wins[0])."""
     if shard is not None:
-        from .shard import umbrella_sharded
+        from .shard import umbrella_sharded, reduce_sums
+        import torch
         kf_all = np.broadcast_to(np.asarray(k_force, dtype=np.float64), (len(xi_wins),))
         nerr_box = [0]
 
         def compute(w0, cnt):
             a, v, ne = umbrella_sampling(g, xi_wins[w0:w0 + cnt], struc_equi[w0:w0 + cnt], kf_all[w0:w0 + cnt],
-                                         umbr_traj, equi_steps, umbr_steps, traj_id0=traj_id0 + w0 * umbr_traj,
-                                         max_retry=max_retry, constrain=constrain)
+                                         umbr_traj, equi_steps, umbr_steps, traj_id0=traj_id0,
+                                         max_retry=max_retry, constrain=constrain, win0=w0, nwin_global=len(xi_wins))
             nerr_box[0] = ne
             return a, v
         avg, var = umbrella_sharded(compute, len(xi_wins), shard[0], shard[1], device=device)
-        return avg, var, nerr_box[0]
+        ne = torch.tensor([float(nerr_box[0])], dtype=torch.float64, device=device)
+        reduce_sums(ne)                       # the count of re-run trajectories of the whole job
+        return avg, var, int(ne.item())
     nwin = len(xi_wins)
+    nglob = nwin if nwin_global is None else int(nwin_global)
     k_force = np.broadcast_to(np.asarray(k_force, dtype=np.float64), (nwin,)).copy()
     q0 = np.repeat(struc_equi[:, None], g.nbeads, axis=1)
-    avg, var, st = g.umbrella_windows(q0, xi_wins, k_force, umbr_traj, equi_steps, umbr_steps, traj_id0=traj_id0,
-                                      constrain=constrain)
+    avg, var, st = g.umbrella_windows(q0, xi_wins, k_force, umbr_traj, equi_steps, umbr_steps,
+                                      traj_id0=traj_id0 + win0 * umbr_traj, constrain=constrain)
     nerr = 0
     for r in range(max_retry):
         bad = (st != 0) | ~(var <= 1e-2)      # calc_rate.f90:1679 (1E-2 is a REAL*4 literal; var is far away)
@@ -109,11 +114,12 @@ def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, um
         if len(wbad) == 0:
             break
         nerr += int(bad.sum())
-        a2, v2, s2 = g.umbrella_windows(q0[wbad], xi_wins[wbad], k_force[wbad], umbr_traj, equi_steps, umbr_steps,
-                                        traj_id0=traj_id0 + (r + 1) * nwin * umbr_traj, constrain=constrain)
-        for i, w in enumerate(wbad):
+        for w in wbad:                        # rare: one call per window keeps the stream ids global
+            a2, v2, s2 = g.umbrella_windows(q0[w:w + 1], xi_wins[w:w + 1], k_force[w:w + 1], umbr_traj, equi_steps,
+                                            umbr_steps, constrain=constrain,
+                                            traj_id0=traj_id0 + ((r + 1) * nglob + win0 + int(w)) * umbr_traj)
             sel = bad[w]
-            avg[w, sel], var[w, sel], st[w, sel] = a2[i, sel], v2[i, sel], s2[i, sel]
+            avg[w, sel], var[w, sel], st[w, sel] = a2[0, sel], v2[0, sel], s2[0, sel]
     else:
         if ((st != 0) | ~(var <= 1e-2)).any():
             raise RuntimeError("umbrella trajectories keep failing (rpmd_check.f90 would call fatal)")
@@ -205,12 +211,12 @@ def recrossing(g, q_start, xi_barrier, k_force, kelvin, recr_equi, child_tot, ch
             raise RuntimeError("recrossing parent failed in segment %d (status %d)" % (i, st[0]))
     # children: pair g belongs to parent g mod child_times; no thermostat, no bias (:131-135)
     npairs = child_times * npp
-    lo, hi = 0, npairs
+    lo, cnt = 0, npairs
     if shard is not None:
         from .shard import shard_range
-        lo, hi = shard_range(npairs, shard[0], shard[1])
+        lo, cnt = shard_range(npairs, shard[0], shard[1])      # (start, count)
     g.set_thermostat(0, 0, kelvin)
-    num, den, status = g.recross_children(parents, hi - lo, child_evol, xi_barrier, pair0=lo)
+    num, den, status = g.recross_children(parents, cnt, child_evol, xi_barrier, pair0=lo)
     return num, den, parents, status
 
 

@@ -14,6 +14,19 @@ import torch
 import torch.distributed as dist
 
 
+def comm_init_from_torch(g, device=None, group=None):
+    """Gives the handle `g` (caracal_b200.RPMD) the job's NCCL communicator behind the C-ABI (crcl_comm_init): rank 0
+    makes the unique id, torch.distributed ships its 128 bytes -- the role mpi_bcast plays in the Fortran drivers.
+    From then on g.recross_children(_dev) / g.umbrella_windows are collective over the global unit range."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(g.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0, group=group)
+    g.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    return world, rank
+
+
 def shard_range(n, rank, world):
     """Contiguous block [start, start+count) of n units for this rank; blocks differ by at most 1."""
     base, rem = divmod(int(n), int(world))

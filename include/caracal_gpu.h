@@ -54,12 +54,17 @@ extern "C" {
 #define CRCL_ENOSUP (-5)   /* combination not implemented on the device path       */
 #define CRCL_ESTATE (-6)   /* call order (e.g. no mechanism set, no resident state) */
 
-/* per-trajectory status written by the integrator (verlet.f90 / rpmd_check.f90 outcomes) */
+/* per-trajectory status written by the integrator (verlet.f90 / rpmd_check.f90 outcomes): bit flags, OR-ed
+ * over the steps of a call; a trajectory with any of the fatal bits (all but PESWARN) is frozen from then on */
 #define CRCL_TRAJ_OK 0
-#define CRCL_TRAJ_SHAKE_FAIL 1 /* constrain_q.f90:95-98 const_good=1 (epot += 1e5)       */
-#define CRCL_TRAJ_NAN 2        /* verlet.f90:1256-1275 NaN/Inf coordinate (reference: fatal) */
-#define CRCL_TRAJ_SINGULAR 5   /* invert.f90 singular inertia tensor (reference: fatal)  */
-#define CRCL_TRAJ_PESWARN 16   /* PES printed a geometry warning (egrad_h3.f:1465,1471)  */
+#define CRCL_TRAJ_SHAKE_FAIL 1 /* constrain_q.f90:95-98 const_good=1 (epot += 1e5)                      */
+#define CRCL_TRAJ_NAN 2        /* verlet.f90:1256-1275 / rpmd_check.f90:76-95 NaN/Inf coordinate or energy */
+#define CRCL_TRAJ_SINGULAR 4   /* invert.f90 singular inertia tensor (reference: fatal)                  */
+#define CRCL_TRAJ_ENERGY 8     /* rpmd_check.f90:100-106 act_energy > (ts_energy+energy_tol)*nbeads      */
+#define CRCL_TRAJ_PESWARN 16   /* PES printed a geometry warning (egrad_h3.f:1465,1471); not fatal       */
+#define CRCL_TRAJ_XI_RANGE 32  /* rpmd_check.f90:112-116 abs(xi_real-xi_ideal) > xi_tol                   */
+#define CRCL_TRAJ_PBC_FAIL 64  /* verlet.f90:601-640 more than 100 box shifts of one coordinate (fatal)  */
+#define CRCL_TRAJ_FATAL (1 | 2 | 4 | 8 | 32 | 64)
 
 /* bead-transform flavour */
 #define CRCL_TRANSFORM_REFERENCE 0 /* rfft.f90/irfft.f90 as written: Re(DFT)/sqrt(N) both ways */
@@ -208,12 +213,45 @@ int crcl_set_ewald(crcl_handle h, const crcl_ewald_params *P);
 int crcl_ewald_recip(crcl_handle h, int n, int nimg, const double *xyz, const double *q,
                      double *energy, double *grad);
 
+/* pbc_mod: periodic, boxlen_x/y/z (bohr).  Switches on the wrap of verlet.f90:591-641 (plain-box branch: all beads
+ * of an atom are shifted together until every bead lies in [0, L]).  crcl_set_qmdff / crcl_set_water set it from
+ * their tables; this entry point serves the host-callback PES (and switches it off again).  A periodic handle always
+ * runs on the HBM-resident path (the analytic gas-phase surfaces of the fused kernels have no box). */
+int crcl_set_box(crcl_handle h, int periodic, const double *boxlen /* [3] */);
+
+/* rpmd_check (rpmd_check.f90:69-116), the guard the drivers call after every verlet step of the start-structure,
+ * umbrella and recrossing-parent phases (calc_rate.f90:945,1072,1575,1633; recross.f90:275,476): when switched on,
+ * every step with constrain 0, 1 or 3 tests epot > (energy_ts + energy_tol) * nbeads -> CRCL_TRAJ_ENERGY (a failed
+ * SHAKE trips it through its 1e5 penalty, as in the reference), NaN energy -> CRCL_TRAJ_NAN, and for constrain 0 / 3
+ * abs(xi_real - xi_ideal) > xi_tol -> CRCL_TRAJ_XI_RANGE (recross passes xi_ideal twice, so constrain 1 never trips
+ * it).  The restart bookkeeping (err_count, new start structures) stays with the caller.  Units: hartree, xi. */
+int crcl_set_rpmd_check(crcl_handle h, int on, double energy_ts, double energy_tol, double xi_tol);
+
 /* NVT{} section: thermostat 0 none, 1 Andersen, 2 Nose-Hoover chain (dynamic.f90:463-465);
  * andersen_step as evb_mod.f90:289; kelvin and nose_q for nhc.f90 / mdinit.f90:138-146 */
 int crcl_set_thermostat(crcl_handle h, int thermostat, int andersen_step, double kelvin,
                         double nose_q);
 /* counter-based RNG (replaces random_init_local, andersen.f90:131) */
 int crcl_set_seed(crcl_handle h, uint64_t seed);
+
+/* ---- multi-GPU: the one exchange step of the path --------------------------------------------
+ * One process per GPU, one handle per process.  Replaces the result traffic of the reference's MPI master/worker
+ * schemes: recross.f90:390,411 (`message(child_evol+2)` from every worker to rank 0) and the statistics files of
+ * calc_rate.f90:1690-1734.  Rank 0 calls crcl_comm_unique_id, the caller ships the CRCL_UNIQUE_ID_BYTES bytes to the
+ * other ranks (mpi_bcast in the Fortran drivers; torch.distributed or a file in Python), every rank calls
+ * crcl_comm_init (collective).  From then on crcl_recross_children(_dev) and crcl_umbrella_windows are COLLECTIVE
+ * calls: every rank passes the same GLOBAL unit range, runs its contiguous block of it (blocks differ by at most one
+ * unit; RNG streams are keyed by the global unit index, so results do not depend on the number of ranks beyond the
+ * summation order) and receives the result of the whole job: ncclAllReduce(sum, double, child_evol + 1) of the
+ * kappa(t) numerators and the denominator, and of the per-trajectory (average, variance, status) vectors.
+ * NCCL is bound at run time (libnccl.so.2, or $CRCL_NCCL_LIB); without it these three calls return CRCL_ESTATE and
+ * everything else works. */
+#define CRCL_UNIQUE_ID_BYTES 128
+int crcl_comm_unique_id(void *id_out /* CRCL_UNIQUE_ID_BYTES bytes */);
+int crcl_comm_init(crcl_handle h, int nranks, int rank, const void *unique_id);
+int crcl_comm_destroy(crcl_handle h);
+/* any pointer may be NULL; nccl_version as ncclGetVersion reports it (0: NCCL not loadable) */
+int crcl_comm_info(crcl_handle h, int *nranks, int *rank, int *nccl_version);
 
 /* ---- PES seam: egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info) --------------------------------
  * Same argument order and layout as egrad_h3.f:29 / egrad_ch4h.f:74 / egrad_oh3.f:33;
@@ -253,11 +291,13 @@ int crcl_calc_xi(crcl_handle h, int ncoord, const double *coords, const double *
  * pairs pair0..pair0+npairs-1; pair g starts from parent snapshot (g mod nparent), draws
  * momenta with RNG stream (seed, traj=g), runs the +p and -p child for child_evol free
  * steps.  kappa_num[child_evol] and *kappa_denom receive this call's sums (reduce across
- * ranks/GPUs by plain addition).  status[npairs] may be NULL. */
+ * ranks/GPUs by plain addition; with a communicator, crcl_comm_init, the call is collective over the GLOBAL range
+ * pair0..pair0+npairs-1 and returns the sums of the whole job on every rank).  status[npairs] may be NULL. */
 int crcl_recross_children(crcl_handle h, const double *q_parents, int nparent, int pair0,
                           int npairs, int child_evol, double xi_ideal, double *kappa_num,
                           double *kappa_denom, int *status);
-/* same with q_parents / outputs resident in device memory (async on the stream) */
+/* same with q_parents / outputs resident in device memory (async on the stream); d_status holds 2*npairs ints,
+ * one per child trajectory */
 int crcl_recross_children_dev(crcl_handle h, const double *d_q_parents, int nparent, int pair0,
                               int npairs, int child_evol, double xi_ideal, double *d_kappa_num,
                               double *d_kappa_denom, int *d_status);

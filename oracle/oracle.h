@@ -24,6 +24,9 @@ void oracle_egrad_oh3_real(const real *q, int natoms, int nbeads, real *V, real 
 void oracle_oh3_pot_real(const real R[6], real *V, real dVdR[6]);
 void oracle_egrad_ch4h_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_ch4h_parts_real(const real *q18, real parts[3], real *V);
+void oracle_ch4h_parts_grad_real(const real *q18, real parts[3], real *gparts);
+void oracle_ch4oh_parts_grad_real(const real *q21, real parts[3], real *gparts);
+void oracle_geh4oh_parts_grad_real(const real *q21, real parts[3], real *gparts);
 void oracle_egrad_brh2_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_egrad_o3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_egrad_ch4oh_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);

@@ -190,6 +190,16 @@ class System:
         self.L.oracle_sys_set_custom_grad.argtypes = [ctypes.c_void_p, CB]
         self.L.oracle_sys_set_custom_grad(self.h, self._cb)
 
+    def set_box(self, periodic, box):
+        """pbc_mod: periodic, boxlen_x/y/z (bohr) -> the wrap of verlet.f90:591-641"""
+        self.L.oracle_sys_set_box.argtypes = [ctypes.c_void_p, ctypes.c_int, dp]
+        self.L.oracle_sys_set_box(self.h, int(periodic), _d(_f64c(box)))
+
+    def set_rpmd_check(self, on, energy_ts=0.0, energy_tol=0.0, xi_tol=0.0):
+        """rpmd_check.f90:100-116 after every biased / constrained step"""
+        self.L.oracle_sys_set_rpmd_check.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_double] * 3
+        self.L.oracle_sys_set_rpmd_check(self.h, int(on), energy_ts, energy_tol, xi_tol)
+
     def set_kforce(self, k):
         self.L.oracle_sys_set_kforce(self.h, k)
 

@@ -34,6 +34,9 @@ void oracle_ch4h_parts(const double *q18, double parts[3], double *V)
 {
     oracle_ch4h_parts_real(q18, parts, V);
 }
+void oracle_ch4h_parts_grad(const double *q18, double parts[3], double *gparts) { oracle_ch4h_parts_grad_real(q18, parts, gparts); }
+void oracle_ch4oh_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_ch4oh_parts_grad_real(q21, parts, gparts); }
+void oracle_geh4oh_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_geh4oh_parts_grad_real(q21, parts, gparts); }
 void oracle_ch4oh_parts(const double *q21, double parts[3], double *V)
 {
     oracle_ch4oh_parts_real(q21, parts, V);
@@ -91,7 +94,7 @@ static void *rc_worker(void *arg)
         s->thermostat = 0; s->andersen_step = 0; s->k_force = 0.0; /* recross_serial.f90:157-160 */
         oracle_sys_set_rng(s, jb->seed, (uint32_t)pair, 0);
         st = orc_recross_pair(s, jb->xi_ideal, jb->child_evol, jb->num, &jb->denom);
-        if (st) jb->status = st;
+        jb->status |= st;
     }
     oracle_sys_free(s);
     return 0;
@@ -123,7 +126,7 @@ int oracle_recross_children(orc_sys *proto, const double *q_parents, int nparent
         pthread_join(th[t], 0);
         for (l = 0; l < child_evol; l++) kappa_num[l] += jobs[t].num[l];
         *kappa_denom += jobs[t].denom;
-        if (jobs[t].status) status = jobs[t].status;
+        status |= jobs[t].status;
         free(jobs[t].num);
     }
     free(th);

@@ -971,24 +971,37 @@ static void ch4h_ipbend(const ch4h_par *p, ch4h_state *s, real *vip_out)
 #undef CBE_NAT
 #undef CBE_EGRAD
 #undef CBE_PARTS
+#undef CBE_PARTS_GRAD
 #if defined(CBE_GEH4OH)
 #define CBE_NC 21   /* pot_geh4oh :84-217 */
 #define CBE_NAT 7
 #define CBE_EGRAD oracle_egrad_geh4oh_real
 #define CBE_PARTS oracle_geh4oh_parts_real
+#define CBE_PARTS_GRAD oracle_geh4oh_parts_grad_real
 #elif defined(CBE_CH4OH)
 #define CBE_NC 21   /* POT_ch4oh :157-286 */
 #define CBE_NAT 7
 #define CBE_EGRAD oracle_egrad_ch4oh_real
 #define CBE_PARTS oracle_ch4oh_parts_real
+#define CBE_PARTS_GRAD oracle_ch4oh_parts_grad_real
 #else
 #define CBE_NC 18
 #define CBE_NAT 6
 #define CBE_EGRAD oracle_egrad_ch4h_real
 #define CBE_PARTS oracle_ch4h_parts_real
+#define CBE_PARTS_GRAD oracle_ch4h_parts_grad_real
 #endif
+static void ch4h_pot_g(const ch4h_par *p, const real R[CBE_NC + 1], real *en_out, real DEGSDR[CBE_NC + 1],
+                       real parts[3], real *gparts);
 static void ch4h_pot(const ch4h_par *p, const real R[CBE_NC + 1], real *en_out, real DEGSDR[CBE_NC + 1],
                      real parts[3])
+{
+    ch4h_pot_g(p, R, en_out, DEGSDR, parts, (real *)0);
+}
+/* gparts (may be null): [3][CBE_NC] = pdot after stretch, the increment of opbend, the increment of ipbend
+ * (all three accumulate into the same pdot(150), egrad_ch4h.f:250-262), in the routine's own units per Angstrom */
+static void ch4h_pot_g(const ch4h_par *p, const real R[CBE_NC + 1], real *en_out, real DEGSDR[CBE_NC + 1],
+                       real parts[3], real *gparts)
 {
     ch4h_state s;
     real vstr, vop, vip, en;
@@ -1001,8 +1014,14 @@ static void ch4h_pot(const ch4h_par *p, const real R[CBE_NC + 1], real *en_out, 
     ch4h_switchf(p, &s);
     ch4h_refangles(&s);
     ch4h_stretch(p, &s, &vstr);
+    if (gparts)
+        for (i = 1; i <= CBE_NC; i++) gparts[i - 1] = s.pdot[i];
     ch4h_opbend(p, &s, &vop);
+    if (gparts)
+        for (i = 1; i <= CBE_NC; i++) gparts[CBE_NC + i - 1] = s.pdot[i] - gparts[i - 1];
     ch4h_ipbend(p, &s, &vip);
+    if (gparts)
+        for (i = 1; i <= CBE_NC; i++) gparts[2 * CBE_NC + i - 1] = s.pdot[i] - gparts[i - 1] - gparts[CBE_NC + i - 1];
     en = vstr + vop + vip;
     en = en * 0.03812;
     *en_out = en;
@@ -1042,4 +1061,15 @@ void CBE_PARTS(const real *q18, real parts[3], real *V)
     ch4h_prepot(&par);
     for (i = 0; i < CBE_NC; i++) R[i + 1] = q18[i];
     ch4h_pot(&par, R, V, D, parts);
+}
+
+/* the same with the gradient of every part, d(part)/d(q in Angstrom), [3][CBE_NC] */
+void CBE_PARTS_GRAD(const real *q18, real parts[3], real *gparts)
+{
+    ch4h_par par;
+    real R[CBE_NC + 1], D[CBE_NC + 1], V;
+    int i;
+    ch4h_prepot(&par);
+    for (i = 0; i < CBE_NC; i++) R[i + 1] = q18[i];
+    ch4h_pot_g(&par, R, &V, D, parts, gparts);
 }

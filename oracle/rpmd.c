@@ -4,8 +4,8 @@
  *
  * TEST INFRASTRUCTURE ONLY (see oracle.h).  Parity UNPINNED by the reference.
  *
- * Literal restatement (graded paths only: no NPT / AFM / mirrors / box walls / bias lists /
- * periodic wrap) of
+ * Literal restatement (graded paths only: no NPT / AFM / mirrors / box walls / bias lists;
+ * the periodic wrap of verlet.f90:591-641 in its plain-box form, not the VASP fractional branch) of
  *   verlet.f90:65-1308          orc_verlet          (operation order: SURVEY.md 3.5)
  *   rfft.f90:35-60, irfft.f90:35-62  orc_rfft       (both are forward DFT, real part, 1/sqrt(N))
  *   get_centroid.f90:67-82      orc_get_centroid
@@ -20,6 +20,7 @@
  *   constrain_p.f90:30-75       orc_constrain_p
  *   recross_serial.f90:172-229  orc_recross_pair    (one +/- child pair)
  *   gradient.f90:140-207        orc_gradient        (analytic PES dispatch, one bead/call)
+ *   rpmd_check.f90:69-112       orc_rpmd_check      (the drivers' per-step guards, as status bits)
  *
  * The reference's RNG (gfortran random_number + Marsaglia polar, andersen.f90:84-126) is
  * not reproducible outside one gfortran build.  Normal deviates come either from an
@@ -985,8 +986,9 @@ void orc_mdinit(orc_sys *s, double *derivs, double xi_ideal, double *dxi_act, in
     free(centroid);
 }
 
-/* verlet.f90:65-1308, graded paths.  Returns status: 0 ok, 1 SHAKE failed (epot carries the
- * 1e5 penalty), 2 NaN/Inf coordinate (reference: fatal), 5 singular inertia tensor (fatal). */
+/* verlet.f90:65-1308, graded paths.  Returns status bits: 1 SHAKE failed (epot carries the
+ * 1e5 penalty), 2 NaN/Inf coordinate (reference: fatal), 4 singular inertia tensor (fatal),
+ * 64 periodic wrap gave up (fatal); 8 / 32 from orc_rpmd_check when it is switched on. */
 int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_ideal,
                double *xi_real, double *dxi_act, int constrain)
 {
@@ -1055,6 +1057,26 @@ int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_id
                 orc_rfft(&Q(s, i, j, 0), 3 * n, nb, costab);
             }
     }
+    /* 5: periodic wrap, plain-box branch (verlet.f90:591-641): beads outer, atoms, xyz inner; every
+     * shift moves ALL beads of that (atom, xyz); `tries` counts lower and upper shifts together and
+     * more than 100 is `fatal` in the reference (here: status bit 64, the trajectory carries on) */
+    if (s->periodic) {
+        for (i = 0; i < nb; i++)
+            for (j = 0; j < n; j++)
+                for (k = 0; k < 3; k++) {
+                    const double boxlen = s->box[k];
+                    int tries = 0, b;
+                    while (Q(s, k, j, i) < 0 && tries <= 100) {
+                        for (b = 0; b < nb; b++) Q(s, k, j, b) = Q(s, k, j, b) + boxlen;
+                        tries = tries + 1;
+                    }
+                    while (Q(s, k, j, i) > boxlen && tries <= 100) {
+                        for (b = 0; b < nb; b++) Q(s, k, j, b) = Q(s, k, j, b) - boxlen;
+                        tries = tries + 1;
+                    }
+                    if (tries > 100) status |= 64;
+                }
+    }
     /* 6: centroid ; 7: mask */
     orc_get_centroid(s, centroid);
     orc_mask(s);
@@ -1064,7 +1086,7 @@ int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_id
         *epot = 0.0;
     else {
         *epot = 100000.0;
-        status = 1;
+        status |= 1;
     }
     /* 10: per-bead gradient */
     for (i = 0; i < nb; i++) {
@@ -1090,12 +1112,48 @@ int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_id
         orc_andersen(s);
     /* 18: NaN / Inf check */
     for (t = 0; t < tot; t++)
-        if (s->q[t] != s->q[t] || s->q[t] > 1.79769313486231570815e308) status = 2;
+        if (s->q[t] != s->q[t] || s->q[t] > 1.79769313486231570815e308) status |= 2;
     /* 19: transrot */
     if (constrain <= 0)
-        if (orc_transrot(s)) status = 5;
+        if (orc_transrot(s)) status |= 4;
+    /* the drivers call rpmd_check right after verlet in the biased / constrained phases
+     * (calc_rate.f90:945,1072,1575,1633 with the window's xi; recross.f90:275,476 with xi_ideal twice) */
+    if (s->chk_on && constrain >= 0 && constrain != 2)
+        status |= orc_rpmd_check(s, *epot, xi_ideal, (constrain == 1) ? xi_ideal : *xi_real);
     free(centroid);
     return status;
+}
+
+/* rpmd_check.f90:69-112 without its restart bookkeeping: bit 2 NaN / Inf structure or energy (:76-95),
+ * bit 8 act_energy > (ts_energy+energy_tol)*nbeads (:100-106), bit 32 abs(xi_real-xi_ideal) > xi_tol (:112-116) */
+int orc_rpmd_check(const orc_sys *s, double act_energy, double xi_ideal, double xi_real)
+{
+    const double infinity = 1.79769313486231570815e308;
+    size_t t, tot = (size_t)3 * s->natoms * s->nbeads;
+    int err = 0;
+    for (t = 0; t < tot; t++)
+        if (s->q[t] != s->q[t] || s->q[t] > infinity) err |= 2;
+    if (act_energy != act_energy || act_energy > infinity) err |= 2;
+    if (act_energy > (s->chk_energy_ts + s->chk_energy_tol) * s->nbeads) err |= 8;
+    if (fabs(xi_real - xi_ideal) > s->chk_xi_tol) err |= 32;
+    return err;
+}
+
+void oracle_sys_set_rpmd_check(orc_sys *s, int on, double energy_ts, double energy_tol, double xi_tol)
+{
+    s->chk_on = on;
+    s->chk_energy_ts = energy_ts;
+    s->chk_energy_tol = energy_tol;
+    s->chk_xi_tol = xi_tol;
+}
+
+/* pbc_mod: periodic, boxlen_x/y/z (bohr) */
+void oracle_sys_set_box(orc_sys *s, int periodic, const double *box)
+{
+    s->periodic = periodic;
+    s->box[0] = box[0];
+    s->box[1] = box[1];
+    s->box[2] = box[2];
 }
 
 /* recross_serial.f90:172-229: one +/- child pair started from q_save (=current s->q).
@@ -1133,7 +1191,7 @@ int orc_recross_pair(orc_sys *s, double xi_ideal, int child_evol, double *num, d
         if (vs > 0) *denom = *denom + vs / fs;
         for (l = 1; l <= child_evol; l++) {
             st = orc_verlet(s, l, derivs, &epot, xi_ideal, &xi_real, dxi, 2);
-            if (st) status = st;
+            status |= st;
             if (xi_real > 0) num[l - 1] = num[l - 1] + vs / fs;
         }
     }

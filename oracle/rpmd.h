@@ -57,6 +57,12 @@ typedef struct orc_sys {
     const double *inject;
     long inject_len, inject_pos;
     orc_custom_grad_fn custom_grad;
+    /* pbc_mod: periodic, boxlen_x/y/z -- the plain-box wrap of verlet.f90:591-641 */
+    int periodic;
+    double box[3];
+    /* rpmd_check.f90 settings: ts_energy, energy_tol (RPMD_EN_TOL), xi_tol */
+    int chk_on;
+    double chk_energy_ts, chk_energy_tol, chk_xi_tol;
 } orc_sys;
 
 void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
@@ -98,6 +104,9 @@ int orc_transrot(orc_sys *s);
 void orc_mdinit(orc_sys *s, double *derivs, double xi_ideal, double *dxi_act, int bias_mode);
 int orc_verlet(orc_sys *s, int istep, double *derivs, double *epot, double xi_ideal,
                double *xi_real, double *dxi_act, int constrain);
+int orc_rpmd_check(const orc_sys *s, double act_energy, double xi_ideal, double xi_real);
+void oracle_sys_set_rpmd_check(orc_sys *s, int on, double energy_ts, double energy_tol, double xi_tol);
+void oracle_sys_set_box(orc_sys *s, int periodic, const double *box);
 int orc_recross_pair(orc_sys *s, double xi_ideal, int child_evol, double *num, double *denom);
 
 #ifdef __cplusplus

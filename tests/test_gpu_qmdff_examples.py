@@ -56,6 +56,7 @@ def test_ethanol_box_rpmd_steps_match_oracle(gpu, oracle):
     Q = oracle.Qmdff(T)
     o = oracle.System(0, nb, m, beta, dt)
     o.set_custom_grad(lambda xyz: tuple(a[0] for a in Q.egrad(xyz)))
+    o.set_box(True, T["box"])                             # periodic tables: the wrap of verlet.f90:591-641 is on
     o.q[:] = q0[0]
     o.set_rng(C.SEED, 0)
     o.set_thermostat(1, 3, 200.0)
