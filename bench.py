@@ -4,9 +4,16 @@
 Workload (BASELINE.json configs[1]): calc_rate CH4+H on the CBE surface
 (egrad_ch4h), 16 beads, T = 300 K, dt = 0.1 fs, 512 +/- child pairs = 1024 child trajectories
 x child_evol = 1000 free steps per GPU, started from 8 constrained parent snapshots.  One bench
-"step" = one pass of the work unit over that batch = 1024*16*1000 bead-steps.  Weak scaling:
-every rank owns its own block of 512 pairs (global pair index keys the RNG streams); the only
-exchange is the all-reduce of the kappa(t) sums (child_evol+1 doubles).
+"step" = one pass of the work unit over that batch = 1024*16*1000 bead-steps.
+
+Multi-GPU (one rank per GPU under torchrun): the job's NCCL communicator sits behind the C-ABI
+(crcl_comm_init); crcl_recross_children(_dev) is then a collective call over the GLOBAL pair range, every
+rank runs its contiguous block and the kappa(t) sums (child_evol+1 doubles) are all-reduced inside the
+library.  Two legs are timed in every run:
+  weak   (the line's `value`, "scaling": "weak"): 512 pairs PER GPU, the shape that keeps a B200 busy;
+  strong (`strong_scaling` in the same line): BASELINE.json configs[1] as written, 1024 children IN TOTAL
+         sharded over the N GPUs (128 children per GPU at N = 8).
+--scaling strong makes the strong leg the line's `value` instead.
 
   python bench.py --gpus N --steps K --warmup W           product (one rank per GPU under torchrun)
   python bench.py --impl reference ...                    the CPU restatement of the reference path
@@ -38,8 +45,9 @@ WORKLOAD = ("calc_rate CH4+H (egrad_ch4h, CBE) 16 beads: %d recrossing child tra
 
 
 def system():
-    from tests import common as C
-    return C.masses("ch4h"), C.beta_calc_rate(KELVIN), C.dt_au(DT_FS), C.mechanism("ch4h"), C.ch5_ts()
+    from caracal_b200 import systems as S
+    from caracal_b200.api import beta_calc_rate, dt_au
+    return S.masses("ch4h"), beta_calc_rate(KELVIN), dt_au(DT_FS), S.mechanism("ch4h"), S.ch5_ts()
 
 
 def flops_per_bead_step():
@@ -156,6 +164,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="which leg is the line's `value`: 512 pairs per GPU (weak) or 512 pairs in total (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that write to the C-level stdout (NCCL prints its version
@@ -187,7 +197,7 @@ def main():
         val, sec, sample = run_cpu_reference(qp, args.steps, max(args.warmup, 1), cores)
         emit({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,7 +209,7 @@ def main():
     import torch
     import torch.distributed as dist
     import caracal_b200
-    from caracal_b200.shard import reduce_sums
+    from caracal_b200.shard import comm_init_from_torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU leg)")
     torch.cuda.set_device(local_rank)
@@ -214,99 +224,110 @@ def main():
     qp = make_parents_gpu(g)               # identical on every rank (same seed and stream)
     stream = torch.cuda.current_stream()
     g.set_stream(stream.cuda_stream)
+    if world > 1:
+        # the job's communicator goes behind the C-ABI: from here on the work unit is a collective call over the global
+        # pair range with the all-reduce of the kappa(t) sums inside the library (torch only ships the 128-byte id)
+        comm_init_from_torch(g, device=dev)
+    nccl_version = g.comm_info()[2]
 
-    # ---- device-resident leg: inputs in HBM before the timed region --------------------------------
     d_qp = torch.as_tensor(qp, device=dev).contiguous()
     d_sums = torch.zeros(CHILD_EVOL + 1, dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    pair_base = rank * NPAIRS * 1000       # disjoint pair ranges per rank and per step
-
-    def step_dev(it):
-        flush.zero_()
-        g.recross_children_dev(d_qp.data_ptr(), NPARENT, NPAIRS, CHILD_EVOL, XI_DAG, d_sums.data_ptr(),
-                               d_sums.data_ptr() + 8 * CHILD_EVOL, pair0=pair_base + it * NPAIRS)
-        reduce_sums(d_sums)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for it in range(args.warmup):
-        step_dev(it)
-    barrier()
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def device_leg(npairs_global, steps, warmup, base):
+        """inputs resident in HBM; K timed steps bracketed by barrier + synchronize, CUDA events, max over ranks"""
+        def step(it):
+            flush.zero_()
+            g.recross_children_dev(d_qp.data_ptr(), NPARENT, npairs_global, CHILD_EVOL, XI_DAG, d_sums.data_ptr(),
+                                   d_sums.data_ptr() + 8 * CHILD_EVOL, pair0=base + it * npairs_global)
+        for it in range(warmup):
+            step(it)
+        barrier()
+        l0 = g.launch_count()
+        g.kernel_timings()                 # drop the warm-up launches from the event ring
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(steps):
+            step(warmup + it)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        kms = g.kernel_timings()
+        return dict(ms_per_step=ms / steps, value=2 * npairs_global * NBEADS * CHILD_EVOL * steps / (ms * 1e-3),
+                    launches=g.launch_count() - l0, kernel_ms=kms, kappa_end=float(d_sums[CHILD_EVOL - 1] / d_sums[CHILD_EVOL]))
+
+    def e2e_leg(npairs_global, steps, base):
+        """the same work unit through the host-pointer C-ABI call: pinned host buffers, H2D / D2H and the all-reduce
+        inside the timed region"""
+        h_qp = torch.as_tensor(qp).pin_memory()
+        qp_np = h_qp.numpy()
+        barrier()
+        for it in range(2):
+            g.recross_children(qp_np, npairs_global, CHILD_EVOL, XI_DAG, pair0=base + it * npairs_global)
+        barrier()
+        t0 = time.perf_counter()
+        for it in range(steps):
+            num, den, st = g.recross_children(qp_np, npairs_global, CHILD_EVOL, XI_DAG, pair0=base + (2 + it) * npairs_global)
+        barrier()
+        ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        return 2 * npairs_global * NBEADS * CHILD_EVOL * steps / (ms * 1e-3)
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = g.launch_count()
-    g.kernel_timings()                     # drop the warm-up launches from the event ring
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for it in range(args.steps):
-        step_dev(args.warmup + it)
-    e1.record()
-    barrier()
-    elapsed_ms = e0.elapsed_time(e1)
-    launches = g.launch_count() - l0
-    # per-launch duration of the dominant kernel (recross_kernel<PesCH4H,16>) inside the timed region:
-    # CUDA events recorded by the library on the launching stream around each launch
-    kms = g.kernel_timings()
+    legs = {}
+    main_leg = args.scaling
+    np_glob = {"weak": world * NPAIRS, "strong": NPAIRS}
+    legs[main_leg] = device_leg(np_glob[main_leg], args.steps, args.warmup, 0)
     sampler.stop_flag.set()
     sampler.join()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    other = "strong" if main_leg == "weak" else "weak"
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    bead_steps_step = 2 * NPAIRS * NBEADS * CHILD_EVOL
-    value = world * bead_steps_step * args.steps / (elapsed_ms * 1e-3)
-
-    # ---- end-to-end leg: host buffers through the C-ABI, H2D/D2H inside the timed region ---------
-    h_qp = torch.as_tensor(qp).pin_memory()
-    qp_np = h_qp.numpy()
-    barrier()
-    for it in range(2):
-        g.recross_children(qp_np, NPAIRS, CHILD_EVOL, XI_DAG, pair0=pair_base + (500 + it) * NPAIRS)
-    barrier()
-    t0 = time.perf_counter()
+        legs[other] = device_leg(np_glob[other], max(5, args.steps // 2), 3, 1 << 24)
+    else:
+        legs[other] = legs[main_leg]       # one GPU: the two shapes coincide
     e2e_steps = max(3, args.steps // 2)
-    for it in range(e2e_steps):
-        num, den, st = g.recross_children(qp_np, NPAIRS, CHILD_EVOL, XI_DAG, pair0=pair_base + (600 + it) * NPAIRS)
-        hs = torch.zeros(CHILD_EVOL + 1, dtype=torch.float64)
-        hs[:CHILD_EVOL] = torch.from_numpy(num)
-        hs[CHILD_EVOL] = den
-        if world > 1:
-            ds = hs.to(dev)
-            reduce_sums(ds)
-            hs = ds.cpu()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * bead_steps_step * e2e_steps / (float(t.item()) * 1e-3)
+    e2e_val = e2e_leg(np_glob[main_leg], e2e_steps, 1 << 26)
+    e2e_other = e2e_leg(np_glob[other], e2e_steps, 1 << 27) if world > 1 else e2e_val
 
     if rank != 0:
         if world > 1:
+            g.comm_destroy()
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------
-    kernel_ms = float(np.mean(kms)) if len(kms) else elapsed_ms / args.steps
+    L = legs[main_leg]
+    kms = L["kernel_ms"]
+    local_pairs = np_glob[main_leg] // world     # rank 0's block (blocks differ by at most one pair)
+    bead_steps_launch = 2 * local_pairs * NBEADS * CHILD_EVOL
+    kernel_ms = float(np.mean(kms)) if len(kms) else L["ms_per_step"]
     peak = g.measure_fp64_tflops(16384)
-    achieved = bead_steps_step * fl_bs / (kernel_ms * 1e-3) / 1e12
+    achieved = bead_steps_launch * fl_bs / (kernel_ms * 1e-3) / 1e12
     # DRAM bytes of one launch of this kernel at this shape from an `ncu --set full` capture
     # (profiles/traffic_recross.json, written by profiles/ncu_traffic.py); null when not captured
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic_recross.json")) as f:
             tr = json.load(f)
-        if tr.get("child_steps") == CHILD_EVOL and tr.get("child_pairs") == NPAIRS:
+        if tr.get("child_steps") == CHILD_EVOL and tr.get("child_pairs") == local_pairs:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "fp64", "kernel": "recross_kernel<PesCH4H,16>", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
-                "peak_source": "DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                "algorithmic_flops_per_launch": bead_steps_step * fl_bs,
+                "peak_source": "builder-measured: DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flops_per_launch": bead_steps_launch * fl_bs,
                 "note": "algorithmic flops = reference's own operation count (oracle census); the kernel executes "
                         "fewer (re-derived PES), see DESIGN.md"}
     cpu_baseline = None
@@ -315,16 +336,25 @@ def main():
         O.build()
         v, sec, sample = run_cpu_reference(qp, 1, 0, cores, long=True)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+
+    def leg_summary(name, e2e):
+        X = legs[name]
+        return {"value": X["value"], "ms_per_step": X["ms_per_step"], "e2e": e2e, "child_pairs_total": np_glob[name],
+                "children_per_gpu": 2 * np_glob[name] // world, "kappa_end": X["kappa_end"]}
+    out = {"metric": METRIC, "value": L["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": L["ms_per_step"], "higher_is_better": True, "scaling": main_leg, "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": config, "clocks": sampler.summary(),
            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(qp.nbytes),
-                   "d2h_bytes_per_step": int(8 * (CHILD_EVOL + 1) + 4 * NPAIRS * 2)},
-           "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-           "kernel_ms": {"mean": kernel_ms, "n": int(len(kms)), "share_of_step": kernel_ms / (elapsed_ms / args.steps)}}
-    if rank == 0:
-        emit(out)
+                   "d2h_bytes_per_step": int(8 * (CHILD_EVOL + 1) + 4 * np_glob[main_leg])},
+           "gpu_launches": int(L["launches"]), "roofline": roofline, "cpu_baseline": cpu_baseline,
+           "kernel_ms": {"mean": kernel_ms, "n": int(len(kms)), "share_of_step": kernel_ms / L["ms_per_step"]},
+           "weak_scaling": leg_summary("weak", e2e_val if main_leg == "weak" else e2e_other),
+           "strong_scaling": leg_summary("strong", e2e_val if main_leg == "strong" else e2e_other),
+           "collective": {"where": "inside libcaracal_gpu.so (crcl_comm_init: ncclAllReduce of child_evol+1 doubles per step)",
+                          "nccl_version": nccl_version, "ranks": world}}
+    emit(out)
     if world > 1:
+        g.comm_destroy()
         dist.destroy_process_group()
     return 0
 

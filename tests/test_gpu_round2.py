@@ -210,3 +210,20 @@ def test_single_rank_communicator(gpu):
     g.comm_destroy()
     a0, v0, s0 = g.umbrella_windows(q0, [0.9], [15.0], 3, 5, 10, traj_id0=3)
     assert (a1 == a0).all() and (v1 == v0).all() and (s1 == s0).all()
+
+
+def test_multi_rank_communicator(gpu):
+    """the collective form over all GPUs of the box (torchrun, one rank per GPU); skipped on a one-GPU box"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU: the multi-rank form is covered by tests/multi_gpu_comm.py under gpurun --gpus N")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_comm.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count(" ok: kappa") == n
