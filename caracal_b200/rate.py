@@ -78,13 +78,17 @@ def generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_
 
 
 def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, umbr_steps, traj_id0=1 << 20,
-                      max_retry=5, constrain=0, shard=None, device="cpu", win0=0, nwin_global=None):
+                      max_retry=5, constrain=0, shard=None, device="cpu", win0=0, nwin_global=None, per_trajectory=False,
+                      window_ids=None):
     """Phase 2: all windows x umbr_traj trajectories in one batch (crcl_umbrella_windows); returns the
     window averages and variances of xi as statistics/bias_* hold them (calc_rate.f90:1690-1700).
     shard = (rank, world): the windows are partitioned over the ranks (one GPU each) and the statistics
     gathered with one all-reduce.  RNG streams are keyed by the GLOBAL window index -- trajectory t of global window
     w uses stream traj_id0 + w*umbr_traj + t, and its r-th re-run traj_id0 + r*nwin_global*umbr_traj + w*umbr_traj + t
-    -- so neither the first pass nor a retry depends on the number of ranks (win0: global index of xi_wins[0])."""
+    -- so neither the first pass nor a retry depends on the number of ranks (win0: global index of xi_wins[0]).
+    window_ids: the global indices of the given windows when they are a non-contiguous subset (restart of a run with
+    some statistics files already complete): every window is then its own launch with its global stream ids.
+    per_trajectory: return the [nwin, umbr_traj] arrays (one line each of statistics/bias_<xi>) instead of the means."""
     if shard is not None:
         from .shard import umbrella_sharded, reduce_sums
         import torch
@@ -105,8 +109,17 @@ def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, um
     nglob = nwin if nwin_global is None else int(nwin_global)
     k_force = np.broadcast_to(np.asarray(k_force, dtype=np.float64), (nwin,)).copy()
     q0 = np.repeat(struc_equi[:, None], g.nbeads, axis=1)
-    avg, var, st = g.umbrella_windows(q0, xi_wins, k_force, umbr_traj, equi_steps, umbr_steps,
-                                      traj_id0=traj_id0 + win0 * umbr_traj, constrain=constrain)
+    gid = (win0 + np.arange(nwin)) if window_ids is None else np.asarray(window_ids, dtype=np.int64)
+    if window_ids is None or (np.diff(gid) == 1).all():
+        avg, var, st = g.umbrella_windows(q0, xi_wins, k_force, umbr_traj, equi_steps, umbr_steps,
+                                          traj_id0=traj_id0 + int(gid[0]) * umbr_traj, constrain=constrain)
+    else:
+        avg, var = np.zeros((nwin, umbr_traj)), np.zeros((nwin, umbr_traj))
+        st = np.zeros((nwin, umbr_traj), dtype=np.int32)
+        for w in range(nwin):
+            avg[w:w + 1], var[w:w + 1], st[w:w + 1] = g.umbrella_windows(
+                q0[w:w + 1], xi_wins[w:w + 1], k_force[w:w + 1], umbr_traj, equi_steps, umbr_steps, constrain=constrain,
+                traj_id0=traj_id0 + int(gid[w]) * umbr_traj)
     nerr = 0
     for r in range(max_retry):
         bad = (st != 0) | ~(var <= 1e-2)      # calc_rate.f90:1679 (1E-2 is a REAL*4 literal; var is far away)
@@ -117,12 +130,14 @@ def umbrella_sampling(g, xi_wins, struc_equi, k_force, umbr_traj, equi_steps, um
         for w in wbad:                        # rare: one call per window keeps the stream ids global
             a2, v2, s2 = g.umbrella_windows(q0[w:w + 1], xi_wins[w:w + 1], k_force[w:w + 1], umbr_traj, equi_steps,
                                             umbr_steps, constrain=constrain,
-                                            traj_id0=traj_id0 + ((r + 1) * nglob + win0 + int(w)) * umbr_traj)
+                                            traj_id0=traj_id0 + ((r + 1) * nglob + int(gid[w])) * umbr_traj)
             sel = bad[w]
             avg[w, sel], var[w, sel], st[w, sel] = a2[0, sel], v2[0, sel], s2[0, sel]
     else:
         if ((st != 0) | ~(var <= 1e-2)).any():
             raise RuntimeError("umbrella trajectories keep failing (rpmd_check.f90 would call fatal)")
+    if per_trajectory:
+        return avg, var, nerr
     return avg.mean(axis=1), var.mean(axis=1), nerr
 
 
@@ -176,12 +191,13 @@ def locate_extrema(bin_coord, pmf, xi_min, xi_max, pmf_minloc="ZERO", xi_pos_man
 
 
 def recrossing(g, q_start, xi_barrier, k_force, kelvin, recr_equi, child_tot, child_interv, child_point, child_evol,
-               traj_id0=1 << 24, shard=None):
+               traj_id0=1 << 24, shard=None, folder=None, rounds_per_launch=None):
     """Phase 4 (recross_serial.f90:83-307): constrained parent equilibrated for recr_equi steps, then
     child_times = child_tot/child_point spawn points child_interv constrained steps apart, child_point/2
     +/- pairs each, child_evol free steps per child.  Returns kappa(t)[child_evol], num, denom.
     shard = (rank, world): this rank evaluates its contiguous block of the pair range (the reference
-    hands out pairs to MPI workers, recross.f90:334-417); sums must then be added across ranks."""
+    hands out pairs to MPI workers, recross.f90:334-417); sums must then be added across ranks.
+    folder (rate_io.RunFolder): keep the reference's restart files and resume from them."""
     child_times = child_tot // child_point
     npp = child_point // 2
     q = np.array(q_start, dtype=np.float64).reshape(1, g.nbeads, g.natoms, 3).copy()
@@ -211,11 +227,33 @@ def recrossing(g, q_start, xi_barrier, k_force, kelvin, recr_equi, child_tot, ch
             raise RuntimeError("recrossing parent failed in segment %d (status %d)" % (i, st[0]))
     # children: pair g belongs to parent g mod child_times; no thermostat, no bias (:131-135)
     npairs = child_times * npp
+    g.set_thermostat(0, 0, kelvin)
+    if folder is not None and shard is None:
+        # restartable form (recross.f90:134-226,420-440): the pair range is processed in launches of whole ROUNDS
+        # (round r = the r-th pair of every parent = pairs [r*child_times, (r+1)*child_times)), so any chunking gives
+        # the sums of the single launch; after every launch the accumulated sums and the bunch count go to the files
+        # the reference keeps (a round is child_times/npp of its "bunches")
+        done_b, num, den, _ = folder.recross_resume(child_evol, g.nbeads, g.natoms)
+        r0 = (done_b * npp) // child_times if (done_b * npp) % child_times == 0 else 0
+        if r0 == 0:
+            num, den = np.zeros(child_evol), 0.0
+        rounds = npp
+        step = rounds if not rounds_per_launch else int(rounds_per_launch)
+        status = np.zeros(npairs, dtype=np.int32)
+        while r0 < rounds:
+            r1 = min(rounds, r0 + step)
+            n_, d_, st_ = g.recross_children(parents, (r1 - r0) * child_times, child_evol, xi_barrier, pair0=r0 * child_times)
+            num, den = num + n_, den + d_
+            status[r0 * child_times:r1 * child_times] = st_
+            r0 = r1
+            folder.recross_checkpoint((r0 * child_times) // npp, num, den, q[0])
+        folder.write_recrossing_time(num, den, g.dt)
+        folder.recross_finished(num[-1] / den)
+        return num, den, parents, status
     lo, cnt = 0, npairs
     if shard is not None:
         from .shard import shard_range
         lo, cnt = shard_range(npairs, shard[0], shard[1])      # (start, count)
-    g.set_thermostat(0, 0, kelvin)
     num, den, status = g.recross_children(parents, cnt, child_evol, xi_barrier, pair0=lo)
     return num, den, parents, status
 
@@ -247,12 +285,15 @@ def calc_k_t_unimol(kappa, pmf_max, pmf_min, kelvin, npaths):
 def calc_rate(g, g1, ts_xyz, mass, mech, kelvin, beta, umbr_lo=-0.05, umbr_hi=1.05, umbr_dist=0.01, k_force_all=0.05,
               gen_steps=10000, equi_steps=10000, umbr_steps=20000, umbr_traj=10, xi_min=-0.05, xi_max=1.05,
               nbins=5000, recr_equi=50000, child_tot=10000, child_interv=1000, child_point=100, child_evol=500,
-              andersen_step=80, npaths=1, pmf_minloc="ZERO", umbr_constrain=0, log=None):
+              andersen_step=80, npaths=1, pmf_minloc="ZERO", umbr_constrain=0, log=None, workdir=None, names=None,
+              rounds_per_launch=None):
     """The whole calc_rate.x run (defaults = examples/calc_rate/h+h2/rate.key).  g: handle with the
     ring-polymer bead count, g1: one-bead handle of the same system (phase 1); both need
     set_mechanism and set_seed.  umbr_constrain: the constrain flag of the biased phases 1 and 2, 0 as
     calc_rate.f90 passes it, 3 for the same dynamics without verlet.f90:1300-1306's removal of net
-    rotation ("published figures").  Returns a dict with every intermediate."""
+    rotation ("published figures").  workdir: keep the reference's files and restart markers under
+    workdir/<T>K_<n>bead/ (rate_io.RunFolder) and resume from them -- finished phases are read back instead of run
+    again, as calc_rate.f90 does.  Returns a dict with every intermediate."""
     import time
     t_prev = [time.perf_counter()]
     timings = {}
@@ -267,22 +308,55 @@ def calc_rate(g, g1, ts_xyz, mass, mech, kelvin, beta, umbr_lo=-0.05, umbr_hi=1.
             log(msg)
     n_over, n_samplings, n_all, xi_wins = window_grid(umbr_lo, umbr_hi, umbr_dist)
     k_force = np.full(n_all - 1, k_force_all * kelvin)          # calc_rate.f90:699
-    g1.set_thermostat(1, andersen_step, kelvin)
-    struc, start_xis = generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_force, gen_steps,
-                                                 constrain=umbr_constrain)
-    say("start structures: xi reached in [%.3f, %.3f]" % (start_xis.min(), start_xis.max()), "start_structures")
+    folder = None
+    if workdir is not None:
+        from .rate_io import RunFolder
+        folder = RunFolder(workdir, kelvin, g.nbeads)
+    # ---- phase 1 (skipped when the marker of a previous run is there, calc_rate.f90:751,1153-1163)
+    if folder is not None and folder.has("start_finished"):
+        xi_file, struc = folder.read_start_structures()
+        start_xis = xi_file.copy()
+        say("start structures: read from %s" % folder.f("equilibrated_struc.xyz"), "start_structures")
+    else:
+        g1.set_thermostat(1, andersen_step, kelvin)
+        struc, start_xis = generate_start_structures(g1, ts_xyz, mass, xi_wins, n_over, n_samplings, k_force, gen_steps,
+                                                     constrain=umbr_constrain)
+        if folder is not None:
+            folder.write_start_structures(names or ["X"] * len(mass), xi_wins, start_xis, struc)
+            _, struc = folder.read_start_structures()          # the reference always continues from the file (:1302-1313)
+        say("start structures: xi reached in [%.3f, %.3f]" % (start_xis.min(), start_xis.max()), "start_structures")
+    # ---- phase 2 (statistics/bias_<xi> per window; windows already on file are not run again, :1420-1478)
     g.set_thermostat(1, andersen_step, kelvin)
-    average, variance, nerr = umbrella_sampling(g, xi_wins, struc, k_force, umbr_traj, equi_steps, umbr_steps,
-                                                constrain=umbr_constrain)
+    if folder is None:
+        average, variance, nerr = umbrella_sampling(g, xi_wins, struc, k_force, umbr_traj, equi_steps, umbr_steps,
+                                                    constrain=umbr_constrain)
+    else:
+        nerr = 0
+        if not folder.has("sampling_finished"):
+            todo = [w for w in range(len(xi_wins)) if folder.stats_resume(xi_wins[w], umbr_traj)[0] <= umbr_traj]
+            if todo:
+                # a window that was interrupted half way is run again as a whole (its trajectories are one launch here)
+                a_t, v_t, nerr = umbrella_sampling(g, xi_wins[todo], struc[todo], k_force[todo], umbr_traj, equi_steps,
+                                                   umbr_steps, constrain=umbr_constrain, per_trajectory=True,
+                                                   window_ids=todo, nwin_global=len(xi_wins))
+                for i, w in enumerate(todo):
+                    folder.stats_write(xi_wins[w], 1, a_t[i], v_t[i], umbr_traj)
+            from .rate_io import touch
+            touch(folder.f("sampling_finished"))
+        average, variance = folder.stats_read(xi_wins, umbr_traj)
+        folder.write_umbr_int(xi_wins, average, variance)
     say("umbrella sampling: %d windows, %d re-run trajectories" % (len(xi_wins), nerr), "umbrella_sampling")
     bin_coord, pmf = umbrella_integration(xi_wins, average, variance, k_force, beta, xi_min, xi_max, nbins, umbr_traj,
                                           umbr_steps)
+    if folder is not None:
+        folder.write_pmf(bin_coord, pmf)
     maxloc, minloc, xi_barrier = locate_extrema(bin_coord, pmf, xi_min, xi_max, pmf_minloc)
     say("PMF: barrier %.3f kJ/mol at xi = %.4f" % ((pmf[maxloc] - pmf[minloc]) * HARTREE_KJ, xi_barrier), "umbrella_integration")
     ts_locate = int(np.argmin(np.abs(xi_wins - xi_barrier)))     # calc_rate.f90:2183-2187
     q_start = np.repeat(struc[ts_locate][None], g.nbeads, axis=0)
     num, den, parents, status = recrossing(g, q_start, xi_barrier, k_force[ts_locate], kelvin, recr_equi, child_tot,
-                                           child_interv, child_point, child_evol)
+                                           child_interv, child_point, child_evol, folder=folder,
+                                           rounds_per_launch=rounds_per_launch)
     kappa_t = num / den
     kappa = kappa_t[-1]
     if kappa < 0.002:                                            # calc_rate.f90:2236-2252
