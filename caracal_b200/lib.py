@@ -136,6 +136,25 @@ class CaracalGpuError(RuntimeError):
     pass
 
 
+def _prefer_bundled_nccl():
+    """The library binds NCCL at run time (dlopen of libnccl.so.2, csrc/comm.cuh).  In a Python process that also
+    imports PyTorch the two must agree on ONE libnccl.so.2: whichever is loaded first wins for the whole process (the
+    loader deduplicates by soname), and PyTorch does not import against an older system NCCL.  So point the library
+    at the pip-installed copy PyTorch itself uses, unless the user chose one (CRCL_NCCL_LIB).  No torch import here."""
+    if os.environ.get("CRCL_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CRCL_NCCL_LIB"] = cand
+                return
+    except (ImportError, ValueError, AttributeError):
+        pass
+
+
 def load():
     """Load libcaracal_gpu.so and bind every declared symbol; raises if anything is missing."""
     global _lib
@@ -144,6 +163,7 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise CaracalGpuError(
             "%s not found: build it with `python -m caracal_b200.build` (no CPU fallback exists)" % LIB_PATH)
+    _prefer_bundled_nccl()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

@@ -48,7 +48,9 @@ def test_ethanol_box_100_steps_with_atoms_crossing_faces(gpu, oracle):
     assert st[0] == 0
     moved = np.abs(o.q - q0[0]).max(axis=0) > 0.5 * T["box"][0]
     assert moved.sum() >= 3, "no atom wrapped"            # several coordinates went through a face
-    assert (o.q >= -1e-12).all() and (o.q <= np.asarray(T["box"]) + 1e-12).all()
+    # a ring polymer that straddles a face is shifted back and forth bead by bead (verlet.f90:593-640 visits the beads in
+    # order and every shift moves all of them), so beads end within the polymer's width of the box, not strictly inside
+    assert (o.q >= -0.5).all() and (o.q <= np.asarray(T["box"]) + 0.5).all()
     assert np.abs(q[0] - o.q).max() < C.TOL_QP
     assert (np.abs(p[0] - o.p) / np.abs(o.p).max()).max() < C.TOL_QP
     assert abs(ep[0] - epo) < 1e-9 * max(1.0, abs(epo))
