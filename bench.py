@@ -158,6 +158,301 @@ def make_parents_cpu():
     return np.array(snaps)
 
 
+# ---- BASELINE.json configs[0], [2], [3], [4]: the same JSON line for the other configurations ---------------------------
+def census(name):
+    with open(os.path.join(ROOT, "oracle", "flop_census.json")) as f:
+        return json.load(f)[name]["flops"]
+
+
+def census_qmdff(key):
+    with open(os.path.join(ROOT, "oracle", "flop_census_qmdff.json")) as f:
+        return json.load(f)[key]
+
+
+def other_config(args, emit, rank, world, local_rank, cores):
+    """c1 H + H2 NVT (replicas), c3 OH + H2 64-bead recrossing children over the temperature sweep, c4 DG-EVB 20 atoms x
+    32 beads, c5 periodic QMDFF box ~3000 atoms x 8 beads.  One bench step = one call of the work unit named in
+    `workload`; value from device-resident state (crcl_verlet_dev / crcl_recross_children_dev), e2e through the
+    host-pointer call.  Multi-GPU: independent replicas of the same work per rank (weak), no exchange (c1, c4, c5 do not
+    shard: SURVEY.md 8e "replicas only"; c3 shards like c2, measured here per GPU)."""
+    import numpy as np
+    from caracal_b200 import systems as S
+    from caracal_b200.api import atomic_mass_au, beta_calc_rate, beta_dynamic, dt_au
+    cfg = args.config
+    ref = args.impl == "reference"
+    if ref and rank != 0:
+        return 0
+    O = None
+    if ref or not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+    if not ref:
+        import torch
+        import torch.distributed as dist
+        import caracal_b200
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU leg)")
+        torch.cuda.set_device(local_rank)
+        dev = torch.device("cuda", local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        caracal_b200.build_if_needed()
+    rng = np.random.default_rng(SEED + rank)
+    spec = {}
+    # ------------------------------------------------------------------------------------------ set-up per configuration
+    if cfg == "c1":
+        name, nb, kelvin, ntraj, nsteps = "h3", 16, 300.0, 65536, 200
+        mass, beta, dt = S.masses(name), beta_dynamic(kelvin), dt_au(0.1)
+        fl = census("h3") + 24 * nb * 3 + 2 * 2 * 3 * 3
+        spec = dict(kind="verlet", pes=name, nbeads=nb, natoms=3, ntraj=ntraj, nsteps=nsteps, constrain=-1, thermostat=(1, 70, kelvin),
+                    flops_per_bead_step=fl, kernel="verlet_kernel<PesH3,16>",
+                    workload="RPMD NVT trajectory on analytic H+H2 PES (egrad_h3), 16 beads, T=300 K, Andersen every 70 steps, dt 0.1 fs: "
+                             "%d independent replicas x %d steps per bench step (a single trajectory does not shard; 10k steps = %d "
+                             "bench steps)" % (ntraj, nsteps, 10000 // nsteps))
+        q0 = np.array([S.ring_polymer(name, nb, rng, 0.02) for _ in range(64)])
+        q0 = np.ascontiguousarray(np.resize(q0, (ntraj,) + q0.shape[1:]))
+        cpu_steps = 200000
+    elif cfg == "c3":
+        name, nb, npairs, evol = "oh3", 64, 512, 500
+        temps = [200.0, 300.0, 400.0, 600.0, 800.0, 1000.0]
+        mass, dt = S.masses(name), dt_au(0.1)
+        fl = census("oh3") + 24 * nb * 4 + 2 * 2 * 3 * 4
+        spec = dict(kind="recross", pes=name, nbeads=nb, natoms=4, npairs=npairs, evol=evol, temps=temps, flops_per_bead_step=fl,
+                    kernel="recross_kernel<PesOH3,64>",
+                    workload="calc_rate OH+H2 (egrad_oh3) 64 beads, temperature sweep 200-1000 K: per bench step %d recrossing child "
+                             "trajectories x %d steps at each of the %d temperatures" % (2 * npairs, evol, len(temps)))
+    elif cfg == "c4":
+        from caracal_b200.qmdff_synth import HEXANE, make_dgevb
+        T1, T2, E = make_dgevb(seed=1, mode=3, npoints=7, template=HEXANE)
+        nb, kelvin, ntraj, nsteps = 32, 300.0, 256, 50
+        sym = {1: "H", 6: "C", 8: "O"}
+        mass = np.array([atomic_mass_au(sym[int(z)]) for z in T1["at"]])
+        beta, dt = beta_calc_rate(kelvin), dt_au(0.5)
+        cz = census_qmdff("dgevb_hexane_mode3_7points")
+        fl = cz["flops_per_image"] + 24 * nb * T1["n"] + 2 * 2 * 3 * T1["n"]
+        spec = dict(kind="verlet", pes="dgevb", nbeads=nb, natoms=int(T1["n"]), ntraj=ntraj, nsteps=nsteps, constrain=-1,
+                    thermostat=(1, 70, kelvin), flops_per_bead_step=fl, kernel="qm_bonded_kernel + dgevb_mix_kernel (split path)",
+                    tables=(T1, T2, E),
+                    workload="dG-EVB-QMDFF RPMD on a synthetic 20-atom two-state system (n-hexane-like QMDFF pair, 7 Gaussians, mode 3, "
+                             "nat6 = 12), 32 beads, NVT Andersen: %d trajectories x %d steps per bench step" % (ntraj, nsteps))
+        q0 = T1["xyz"][None, None] + rng.normal(0, 0.02, (ntraj, nb) + T1["xyz"].shape)
+        cpu_steps = 1500
+    else:
+        from caracal_b200.qmdff_synth import make_system
+        T = make_system(nmol=385, seed=12, periodic=True, zahn=True, hb=True)
+        nb, kelvin, ntraj, nsteps = 8, 300.0, 1, 100
+        sym = {1: "H", 6: "C", 8: "O", 17: "CL"}
+        mass = np.array([atomic_mass_au(sym[int(z)]) for z in T["at"]])
+        beta, dt = beta_dynamic(kelvin), dt_au(0.5)
+        cz = census_qmdff("box_385_molecules_hb1")
+        fl = cz["flops_per_image"] + 24 * nb * T["n"] + 2 * 2 * 3 * T["n"]
+        spec = dict(kind="verlet", pes="qmdff", nbeads=nb, natoms=int(T["n"]), ntraj=ntraj, nsteps=nsteps, constrain=-1,
+                    thermostat=(1, 70, kelvin), flops_per_bead_step=fl, kernel="qm_inter_cell_kernel (split path)", tables=(T,),
+                    workload="periodic QMDFF box NVT (synthetic: 385 molecules = %d atoms, Zahn Coulomb, 10 A cut-offs, H bonds), 8 beads "
+                             "RPMD: %d trajectory x %d steps per bench step" % (T["n"], ntraj, nsteps))
+        q0 = T["xyz"][None, None] + rng.normal(0, 0.01, (ntraj, nb) + T["xyz"].shape)
+        cpu_steps = 5
+    nb, natoms = spec["nbeads"], spec["natoms"]
+    config = {"workload": spec["workload"], "pes": spec["pes"], "natoms": natoms, "nbeads": nb, "dt_fs": 0.1 if cfg in ("c1", "c3") else 0.5,
+              "transform": "reference (rfft/irfft as written)", "parallelism": "independent replicas per GPU, %d GPU(s)" % world,
+              "l2": "256 MiB device memset between timed steps (inside the timed region)",
+              "flops_per_bead_step": spec["flops_per_bead_step"]}
+
+    # ------------------------------------------------------------------------------------------ CPU restatement of the unit
+    def cpu_leg():
+        """-> (bead-steps/s, seconds, sample text, cores used)"""
+        if spec["kind"] == "recross":
+            o = O.System(spec["pes"], nb, mass, beta_calc_rate(300.0), dt)
+            o.set_mechanism(S.mechanism(spec["pes"]))
+            qp = np.array([S.ring_polymer(spec["pes"], nb, np.random.default_rng(k), 0.01) for k in range(8)])
+            npr, ev = 8 * cores, 500
+            t0 = time.perf_counter()
+            o.recross_children(qp, 0, npr, ev, XI_DAG, SEED, nthreads=cores)
+            sec = time.perf_counter() - t0
+            return 2 * npr * nb * ev / sec, sec, "%d +/- pairs x %d steps x %d beads on %d threads (300 K)" % (npr, ev, nb, cores), cores
+        o = O.System(spec["pes"] if cfg == "c1" else 0, nb, mass, beta, dt)
+        if cfg == "c4":
+            D = O.Dgevb(*spec["tables"])
+            o.set_custom_grad(lambda xyz: tuple(a[0] for a in D.egrad(xyz)))
+        elif cfg == "c5":
+            Q = O.Qmdff(spec["tables"][0])
+            o.set_custom_grad(lambda xyz: tuple(a[0] for a in Q.egrad(xyz)))
+            o.set_box(True, spec["tables"][0]["box"])
+        o.set_thermostat(*spec["thermostat"])
+        o.set_rng(SEED, 0)
+        o.q[:] = q0[0]
+        o.mdinit(0.0, 0)
+        t0 = time.perf_counter()
+        for i in range(1, cpu_steps + 1):
+            o.verlet(i, 0.0, -1)
+        sec = time.perf_counter() - t0
+        # one trajectory on one core: the reference's MPI gives dynamic.x no speed-up (SURVEY.md F8)
+        return nb * cpu_steps / sec, sec, "1 trajectory x %d steps x %d beads on 1 core" % (cpu_steps, nb), 1
+    if ref:
+        times = []
+        for it in range(max(args.warmup, 1) + args.steps):
+            v, sec, sample, used = cpu_leg()
+            if it >= max(args.warmup, 1):
+                times.append((v, sec))
+            if sum(t[1] for t in times) > 120.0:
+                break
+        v = float(np.mean([t[0] for t in times]))
+        emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+              "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean([t[1] for t in times])), "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+              "cpu_baseline": {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+              "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+              "note": "C restatement (oracle/) of the reference's Fortran path (SURVEY.md F1)"})
+        return 0
+
+    # ------------------------------------------------------------------------------------------ product
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    T = lambda a, dt_=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt_, device=dev)
+    if spec["kind"] == "recross":
+        hs = []
+        for kel in spec["temps"]:
+            g = caracal_b200.RPMD(spec["pes"], nb, mass, beta_calc_rate(kel), dt, device=local_rank)
+            g.set_mechanism(S.mechanism(spec["pes"]))
+            g.set_seed(SEED)
+            g.set_stream(stream.cuda_stream)
+            hs.append(g)
+        qp = np.array([S.ring_polymer(spec["pes"], nb, np.random.default_rng(k), 0.01) for k in range(8)])
+        d_qp = T(qp)
+        d_sums = torch.zeros(len(hs), spec["evol"] + 1, dtype=torch.float64, device=dev)
+        bead_steps = len(hs) * 2 * spec["npairs"] * nb * spec["evol"]
+        h2d, d2h = qp.nbytes * len(hs), len(hs) * (8 * (spec["evol"] + 1) + 4 * spec["npairs"])
+
+        def step_dev(it):
+            flush.zero_()
+            for k, g in enumerate(hs):
+                g.recross_children_dev(d_qp.data_ptr(), 8, spec["npairs"], spec["evol"], XI_DAG, d_sums[k].data_ptr(),
+                                       d_sums[k].data_ptr() + 8 * spec["evol"], pair0=(rank * 1000 + it) * spec["npairs"])
+
+        def step_host(it):
+            for g in hs:
+                g.recross_children(qp, spec["npairs"], spec["evol"], XI_DAG, pair0=(rank * 1000 + 500 + it) * spec["npairs"])
+        g0 = hs[0]
+    else:
+        pid = {"h3": "h3", "dgevb": caracal_b200.PES_DGEVB, "qmdff": caracal_b200.PES_QMDFF}[spec["pes"]]
+        g0 = caracal_b200.RPMD(pid, nb, mass, beta, dt, device=local_rank)
+        if cfg == "c4":
+            g0.set_qmdff(spec["tables"][0])
+            g0.set_qmdff(spec["tables"][1], second=True)
+            g0.set_dgevb(spec["tables"][2])
+        elif cfg == "c5":
+            g0.set_qmdff(spec["tables"][0])
+        g0.set_seed(SEED)
+        g0.set_thermostat(*spec["thermostat"])
+        ntraj, nsteps = spec["ntraj"], spec["nsteps"]
+        q = q0.copy()
+        p, d, dxi, ev = g0.mdinit(q, 0)
+        g0.set_stream(stream.cuda_stream)
+        dq, dp, dd = T(q), T(p), T(d)
+        dep, dxr = torch.zeros(ntraj, dtype=torch.float64, device=dev), torch.zeros(ntraj, dtype=torch.float64, device=dev)
+        ddxi = torch.zeros(ntraj * natoms * 3, dtype=torch.float64, device=dev)
+        dst = torch.zeros(ntraj, dtype=torch.int32, device=dev)
+        dtid = torch.arange(ntraj, dtype=torch.int32, device=dev)
+        dev_ = torch.as_tensor(ev.astype(np.int32), device=dev)
+        bead_steps = ntraj * nb * nsteps
+        h2d, d2h = 3 * q.nbytes, 3 * q.nbytes + 16 * ntraj
+        hq, hp, hd = (torch.as_tensor(a).pin_memory().numpy() for a in (q, p, d))
+        hev = ev.copy()
+        done = [0]
+
+        def step_dev(it):
+            flush.zero_()
+            g0.verlet_dev(ntraj, nsteps, dq.data_ptr(), dp.data_ptr(), dd.data_ptr(), dep.data_ptr(), dxr.data_ptr(), ddxi.data_ptr(),
+                          dst.data_ptr(), dev_.data_ptr(), istep0=done[0], constrain=-1, d_traj_id=dtid.data_ptr())
+            done[0] += nsteps
+
+        def step_host(it):
+            g0.verlet(hq, hp, hd, nsteps=nsteps, istep0=done[0], constrain=-1, event=hev)
+            done[0] += nsteps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    handles = hs if spec["kind"] == "recross" else [g0]
+    for it in range(args.warmup):
+        step_dev(it)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = sum(g.launch_count() for g in handles)
+    for g in handles:
+        g.kernel_timings()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(args.steps):
+        step_dev(args.warmup + it)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = sum(g.launch_count() for g in handles) - l0
+    kms = np.concatenate([g.kernel_timings() for g in handles]) if spec["kind"] == "recross" else g0.kernel_timings()
+    sampler.stop_flag.set()
+    sampler.join()
+    value = world * bead_steps * args.steps / (ms * 1e-3)
+    if spec["kind"] != "recross":
+        st_host = dst.cpu().numpy()
+        if (st_host & caracal_b200.lib.TRAJ_FATAL).any():
+            raise SystemExit("bench.py: %d trajectories failed (status %s)" % (int((st_host != 0).sum()), np.unique(st_host)))
+    # end to end: host buffers through the C-ABI
+    barrier()
+    for it in range(1):
+        step_host(it)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, args.steps // 4)
+    for it in range(e2e_steps):
+        step_host(1 + it)
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e_val = world * bead_steps * e2e_steps / (e2e_ms * 1e-3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+    peak = g0.measure_fp64_tflops(16384)
+    step_ms = ms / args.steps
+    if spec["kind"] == "recross" or not len(kms):
+        kernel_ms = float(np.mean(kms)) if len(kms) else step_ms
+        per_launch = bead_steps / max(len(handles), 1) if spec["kind"] == "recross" else bead_steps
+    else:
+        # fused path: one trajectory-kernel launch per step; split path: the step is many launches, use the whole step
+        fused = cfg == "c1"
+        kernel_ms = float(np.mean(kms)) if fused else step_ms
+        per_launch = bead_steps
+    achieved = per_launch * spec["flops_per_bead_step"] / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "kernel": spec["kernel"], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "peak_source": "builder-measured: DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+                "algorithmic_flops_per_launch": per_launch * spec["flops_per_bead_step"],
+                "note": "algorithmic flops = the reference's own operation count from the counting build of the restatement "
+                        "(oracle/flop_census*.json; pairs outside the cut-offs not counted) + 24 N natoms for the transform"}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        v, sec, sample, used = cpu_leg()
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": used, "kind": "port", "sample": sample}
+    emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": config, "clocks": sampler.summary(),
+          "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+          "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+          "kernel_ms": {"mean": kernel_ms, "n": int(len(kms)), "share_of_step": kernel_ms / step_ms}})
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +462,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="which leg is the line's `value`: 512 pairs per GPU (weak) or 512 pairs in total (strong)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs[0..4]; c2 (default) is the configuration the metric is quoted on")
     args = ap.parse_args()
     # the contract is ONE JSON line on stdout: libraries that write to the C-level stdout (NCCL prints its version
     # banner there) are sent to stderr for the duration of the run, the line itself goes to the saved descriptor
@@ -181,6 +478,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
+    if args.config != "c2":
+        return other_config(args, emit, rank, world, local_rank, cores)
     fl_bs, fl_pes = flops_per_bead_step()
     config = {"workload": WORKLOAD, "pes": "ch4h", "natoms": 6, "nbeads": NBEADS, "child_pairs_per_gpu": NPAIRS,
               "child_steps": CHILD_EVOL, "parents": NPARENT, "kelvin": KELVIN, "dt_fs": DT_FS, "xi_ideal": XI_DAG,

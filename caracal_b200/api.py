@@ -355,6 +355,14 @@ class RPMD:
                                                  _ip(st)), "crcl_recross_children")
         return num, den.value, st[:npairs]
 
+    def verlet_dev(self, ntraj, nsteps, d_q, d_p, d_derivs, d_epot, d_xi_real, d_dxi, d_status, d_event, istep0=0, constrain=-1,
+                   d_xi_ideal=None, d_k_force=None, d_traj_id=None):
+        """crcl_verlet_dev: device pointers as ints (torch.Tensor.data_ptr()); asynchronous on the handle's stream"""
+        vp = lambda x: ctypes.c_void_p(x) if x else None
+        self._ck(self._lib.crcl_verlet_dev(self._h, int(ntraj), int(nsteps), int(istep0), int(constrain), vp(d_xi_ideal),
+                                           vp(d_k_force), vp(d_q), vp(d_p), vp(d_derivs), vp(d_epot), vp(d_xi_real), vp(d_dxi),
+                                           vp(d_status), vp(d_traj_id), vp(d_event)), "crcl_verlet_dev")
+
     def recross_children_dev(self, d_q_parents, nparent, npairs, child_evol, xi_ideal, d_num, d_denom, pair0=0,
                              d_status=None):
         """Device-pointer variant (ints from torch.Tensor.data_ptr()); asynchronous on the handle's stream."""

@@ -1553,6 +1553,66 @@ int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
     return CRCL_OK;
 }
 
+// crcl_verlet on state resident in device memory (asynchronous on the handle's stream, nothing crosses PCIe)
+int crcl_verlet_dev(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain, const double* d_xi_ideal,
+                    const double* d_k_force, double* d_q, double* d_p, double* d_derivs, double* d_epot,
+                    double* d_xi_real, double* d_dxi, int* d_status, const uint32_t* d_traj_id, uint32_t* d_event)
+{
+    int rc = check_traj_call(h, constrain);
+    if (rc) return rc;
+    if (!d_q || !d_p || !d_derivs || !d_epot || !d_xi_real || !d_dxi || !d_status || !d_event || ntraj < 0 || nsteps < 0)
+        return CRCL_EINVAL;
+    if (ntraj == 0) return CRCL_OK;
+    CK(cudaSetDevice(h->device));
+    if ((rc = ensure_fker(h))) return rc;
+    double* dnhc;
+    if ((rc = scratch(h, 7, (size_t)ntraj * 8, &dnhc))) return rc;
+    if (use_split(h)) {
+        uint32_t* dtid = nullptr;
+        if (!d_traj_id) {
+            if ((rc = scratch(h, 29, (size_t)ntraj, &dtid))) return rc;
+            std::vector<uint32_t> ids(ntraj);
+            for (int t = 0; t < ntraj; t++) ids[t] = (uint32_t)t;
+            CK(cudaMemcpyAsync(dtid, ids.data(), ntraj * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        SplitCall C;
+        C.ntraj = ntraj;
+        C.q = d_q;
+        C.p = d_p;
+        C.g = d_derivs;
+        C.dxi = d_dxi;
+        C.epot = d_epot;
+        C.xi_real = d_xi_real;
+        C.nhc = dnhc;
+        C.status = d_status;
+        C.tid = d_traj_id ? d_traj_id : dtid;
+        C.event = d_event;
+        C.xi_ideal = d_xi_ideal;
+        C.k_force = d_k_force;
+        return verlet_split(h, C, nsteps, istep0, constrain);
+    }
+    TrajArgs A;
+    fill_args(h, A);
+    A.ntraj = ntraj;
+    A.nsteps = nsteps;
+    A.istep0 = istep0;
+    A.constrain = constrain;
+    A.xi_ideal = d_xi_ideal;
+    A.k_force = d_k_force;
+    A.q = d_q;
+    A.p = d_p;
+    A.g = d_derivs;
+    A.dxi = d_dxi;
+    A.epot = d_epot;
+    A.xi_real = d_xi_real;
+    A.status = d_status;
+    A.nhc = dnhc;
+    A.traj_id = d_traj_id;
+    A.event = d_event;
+    return launch_traj(h, K_VERLET, A);
+}
+
 int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double* xi_ideal, const double* k_force,
                 const double* q, double* p, double* derivs, double* dxi, const uint32_t* traj_id,
                 uint32_t* event0)

@@ -50,6 +50,12 @@ struct QmdffDev {
     double* xs;
     float4* xf;
     size_t xs_cap;
+    // cell sweep of the inter-molecular part (qm_cellsort_kernel / qm_inter_cell_kernel): atoms sorted by cell
+    float4* sf;       // [img][pos] {wrapped x, y, z, atom number}
+    int* smol;        // [img][pos] molnum
+    int* cstart;      // [img][ncell+1]
+    size_t cell_cap_a, cell_cap_c;
+    int cells_enabled;
 };
 
 // host: build / free the device copy; evaluate nimg images (AoS [img][atom][xyz])

@@ -22,6 +22,7 @@
 // periodic case ~20 % of the pairs of a 27 A box survive the distance test.
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include "qmdff.cuh"
 
@@ -476,6 +477,316 @@ struct InterTables {
         zab[QM_MAXTYPE][QM_MAXTYPE];
 };
 
+// One inter-molecular pair i < j evaluated exactly as ff_nonb.f90:198-332 (dispersion / repulsion) and :421-512
+// (Coulomb) do: vab = x(i) - x(j), the box_image.f90 loop, the exact r > cut tests.  ep = energy of the pair,
+// (fx,fy,fz) = its gradient contribution on atom i (atom j gets the negative).  Shared by the O(N^2) sweep
+// (qm_inter_kernel) and the cell sweep (qm_inter_cell_kernel) so that a pair gives the same bits in both.
+template <bool PER>
+__device__ __forceinline__ void qm_pair_exact(const QmdffDev& D, const InterTables& tb, const double* __restrict__ Xx,
+                                              const double* __restrict__ Xy, const double* __restrict__ Xz, int i, int j,
+                                              double& ep, double& fx, double& fy, double& fz)
+{
+    constexpr bool per = PER;
+    auto image = [&](double& v, double L) {
+        const double L2 = 0.5 * L;
+        while (fabs(v) > L2) v -= (v >= 0.0) ? L : -L;   // box_image.f90
+    };
+    double vab[3] = {Xx[i] - Xx[j], Xy[i] - Xy[j], Xz[i] - Xz[j]};   // x(i1) - x(i2), i1 < i2
+    if (per) {
+        image(vab[0], D.box[0]);
+        image(vab[1], D.box[1]);
+        image(vab[2], D.box[2]);
+    }
+    const double r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2], r = sqrt(r2);
+    const double oner = 1.0 / r, oner2 = oner * oner;
+    double dr = 0.0;
+    ep = 0.0;
+    if (!(per && r > D.vdw_cut)) {
+        const int ti = D.type[i], tj = D.type[j];
+        const double c6 = __ldg(&D.c6[(size_t)i * D.n + j]);
+        const double R0 = tb.r094[ti][tj];
+        const double r4 = r2 * r2, r6 = r4 * r2, R02 = R0 * R0, r06 = R02 * R02 * R02;
+        const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
+        const double it6 = 1.0 / t6, it8 = 1.0 / t8;
+        const double c6t6 = c6 * it6, t27 = tb.sr42[ti][tj] * (c6 * it8);
+        ep -= c6t6 + t27;
+        dr += c6t6 * 6.0 * r4 * it6 + 8.0 * t27 * r6 * it8;
+        if (r < 25.0) {
+            const double alpha = tb.r0ab[ti][tj];
+            const double tt = tb.zab[ti][tj] * exp(-alpha * r);
+            ep += tt * oner;
+            dr -= tt * (alpha * r + 1.0) * oner * oner2;
+        }
+    }
+    if (!(r > D.coul_cut)) {
+        const double qq = D.q[i] * D.q[j];
+        double e0;
+        if (D.zahn) {
+            e0 = qq * (erfc(D.zahn_a * r) * oner - D.zahn_par * (r - D.coul_cut));
+        } else {
+            double sw = 1.0;
+            if (per && r > D.cut_low) {
+                const double xv = (r - D.cut_low) / (D.coul_cut - D.cut_low);
+                sw = exp(1.0) * exp(1.0 / (xv - 1.0));
+            }
+            e0 = qq * oner * sw;
+        }
+        ep += e0;
+        dr -= e0 * oner2;   // the reference uses e0/r^2 for every Coulomb form (ff_nonb.f90:470)
+    }
+    fx = vab[0] * dr;
+    fy = vab[1] * dr;
+    fz = vab[2] * dr;
+}
+
+// ---- cell sweep of the inter-molecular part (periodic boxes of at least 2M+1 cells per dimension) -----------------
+// The reference tests all n(n-1)/2 pairs per image (ff_nonb.f90:198,421: double loops over the atoms); with 10 A
+// cut-offs in a 31 A box 86 % of those tests fail.  Here the atoms of an image are binned into cells of edge
+// >= rc (1 + slack) / M (M = 2 or 3) and sorted by cell; a CTA owns one home cell and tests its atoms against the
+// half shell of (2M+1)^3 neighbour cells (every unordered cell pair once; own cell: sorted position j > i) in FP32 on
+// the wrapped coordinates, with the periodic shift a constant of the neighbour run instead of a rounding per pair.
+// Survivors go to a CTA-wide queue in shared memory and are evaluated 128 at a time by qm_pair_exact on the
+// original FP64 coordinates, ordered (min, max) by atom number as the reference's loops are: every pair inside the
+// cut-offs gives the same bits as in the O(N^2) sweep, only the order of the FP64 accumulation differs (which the
+// red.global.add of the O(N^2) sweep leaves open as well).
+struct CellGrid {
+    int nc[3], ncell, m;      // cells per dimension, total, neighbour range
+    float rc2f;               // (larger cut-off)^2 with slack
+};
+#define QM_CELL_MAXCELL 8192   // shared-memory counters of qm_cellsort_kernel
+#define QM_CELL_IB 32          // home-cell atoms per batch
+#define QM_CELL_MAXRUN 80      // 1 + 3 x (M(2M+1) + M+1) segment slots, M <= 3
+
+// one CTA per image: count, scan, scatter.  sf[pos] = {wrapped x, y, z, atom number}, smol[pos] = molnum,
+// cstart[img][ncell+1]
+__global__ void __launch_bounds__(1024) qm_cellsort_kernel(const QmdffDev D, const CellGrid G, const double* __restrict__ xs,
+                                                           float4* __restrict__ sf, int* __restrict__ smol,
+                                                           int* __restrict__ cstart)
+{
+    __shared__ int cnt[QM_CELL_MAXCELL + 1];
+    __shared__ int part[1024];
+    const int img = blockIdx.x, n = D.n, tid = threadIdx.x;
+    const double* X = xs + (size_t)img * 3 * n;
+    for (int c = tid; c <= G.ncell; c += 1024) cnt[c] = 0;
+    __syncthreads();
+    auto wrapped = [&](int a, float w[3], int& cell) {
+        int ci[3];
+        for (int d = 0; d < 3; d++) {
+            const double L = D.box[d], v = X[(size_t)d * n + a];
+            double u = v - L * floor(v / L);              // [0, L] (== L only by rounding)
+            int k = (int)(u * ((double)G.nc[d] / L));
+            k = k < 0 ? 0 : (k >= G.nc[d] ? G.nc[d] - 1 : k);
+            ci[d] = k;
+            w[d] = (float)u;
+        }
+        cell = (ci[2] * G.nc[1] + ci[1]) * G.nc[0] + ci[0];
+    };
+    for (int a = tid; a < n; a += 1024) {
+        float w[3];
+        int cell;
+        wrapped(a, w, cell);
+        atomicAdd(&cnt[cell], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the cells: thread t owns a contiguous chunk
+    const int chunk = (G.ncell + 1023) / 1024, c0 = tid * chunk, c1 = min(G.ncell, c0 + chunk);
+    int s = 0;
+    for (int c = c0; c < c1; c++) s += cnt[c];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < 1024; t++) {
+            const int v = part[t];
+            part[t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    int run = part[tid];
+    int* cs = cstart + (size_t)img * (G.ncell + 1);
+    for (int c = c0; c < c1; c++) {
+        const int v = cnt[c];
+        cs[c] = run;
+        cnt[c] = run;      // becomes the cell's cursor
+        run += v;
+    }
+    if (tid == 0) cs[G.ncell] = n;
+    __syncthreads();
+    for (int a = tid; a < n; a += 1024) {
+        float w[3];
+        int cell;
+        wrapped(a, w, cell);
+        const int pos = atomicAdd(&cnt[cell], 1);
+        sf[(size_t)img * n + pos] = make_float4(w[0], w[1], w[2], __int_as_float(a));
+        smol[(size_t)img * n + pos] = D.molnum[a];
+    }
+}
+
+__global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, const CellGrid G, const double* __restrict__ xs,
+                                                            const float4* __restrict__ sf, const int* __restrict__ smol,
+                                                            const int* __restrict__ cstart, double* __restrict__ V,
+                                                            double* __restrict__ g)
+{
+    __shared__ InterTables tb;
+    __shared__ int run_beg[QM_CELL_MAXRUN], run_pre[QM_CELL_MAXRUN + 1];
+    __shared__ float run_sh[QM_CELL_MAXRUN][3];
+    __shared__ float4 si[QM_CELL_IB];
+    __shared__ int simol[QM_CELL_IB];
+    __shared__ int2 queue[128 + 128 * QM_CELL_IB];
+    __shared__ int qcount, nrun_s;
+    const int img = blockIdx.y, n = D.n, tid = threadIdx.x, lane = tid & 31;
+    for (int t = tid; t < QM_MAXTYPE * QM_MAXTYPE; t += 128) {
+        (&tb.r094[0][0])[t] = (&D.r094[0][0])[t];
+        (&tb.sr42[0][0])[t] = (&D.sr42[0][0])[t];
+        (&tb.r0ab[0][0])[t] = (&D.r0ab[0][0])[t];
+        (&tb.zab[0][0])[t] = (&D.zab[0][0])[t];
+    }
+    const int* cs = cstart + (size_t)img * (G.ncell + 1);
+    const int home = blockIdx.x, hb = cs[home], he = cs[home + 1];
+    if (hb == he) return;                                  // empty home cell (uniform for the CTA)
+    const int M = G.m, ncx = G.nc[0], ncy = G.nc[1], ncz = G.nc[2];
+    const int cx = home % ncx, cy = (home / ncx) % ncy, cz = home / (ncx * ncy);
+    // runs of the half shell: rows (oz, oy) with oz > 0, or oz == 0 and oy >= 0; the row (0, 0) only holds the
+    // cells ox = 1..M (the home cell itself is run 0).  A row's cells are contiguous in the sorted order except
+    // where the periodic wrap splits it: up to three segments, each with its own shift.
+    // thread t < nrows fills the three segment slots of row t (empty segments keep length 0), thread 0 the prefix
+    __shared__ int run_len[QM_CELL_MAXRUN];
+    const int nrows = M * (2 * M + 1) + (M + 1);
+    if (tid < nrows) {
+        // rows in the order (oz = 0: oy = 0..M), (oz = 1..M: oy = -M..M)
+        int oz, oy;
+        if (tid <= M) {
+            oz = 0;
+            oy = tid;
+        } else {
+            const int t = tid - (M + 1);
+            oz = 1 + t / (2 * M + 1);
+            oy = t % (2 * M + 1) - M;
+        }
+        const float Lx = (float)D.box[0], Ly = (float)D.box[1], Lz = (float)D.box[2];
+        int z2 = cz + oz, y2 = cy + oy;
+        float shz = 0.f, shy = 0.f;
+        if (z2 >= ncz) { z2 -= ncz; shz = Lz; }
+        if (y2 < 0) { y2 += ncy; shy = -Ly; } else if (y2 >= ncy) { y2 -= ncy; shy = Ly; }
+        const int row = (z2 * ncy + y2) * ncx;
+        const int xa = cx + ((oz == 0 && oy == 0) ? 1 : -M), xb = cx + M;   // inclusive cell range, may leave [0, ncx)
+        // segments: [xa, -1] -> +ncx, shift -Lx ; [max(xa,0), min(xb,ncx-1)] ; [ncx, xb] -> -ncx, shift +Lx
+        const int lo[3] = {xa, xa > 0 ? xa : 0, ncx}, hi[3] = {-1 < xb ? -1 : xb, xb < ncx - 1 ? xb : ncx - 1, xb};
+        const int off[3] = {ncx, 0, -ncx};
+        const float shx[3] = {-Lx, 0.f, Lx};
+        for (int sgm = 0; sgm < 3; sgm++) {
+            const int k = 1 + 3 * tid + sgm;
+            int b = 0, len = 0;
+            if (lo[sgm] <= hi[sgm]) {
+                b = cs[row + lo[sgm] + off[sgm]];
+                len = cs[row + hi[sgm] + off[sgm] + 1] - b;
+            }
+            run_beg[k] = b;
+            run_len[k] = len;
+            run_sh[k][0] = shx[sgm];
+            run_sh[k][1] = shy;
+            run_sh[k][2] = shz;
+        }
+    }
+    if (tid == 0) {
+        run_beg[0] = hb;                                  // run 0: the home cell itself (pairs with jpos > ipos)
+        run_len[0] = he - hb;
+        run_sh[0][0] = run_sh[0][1] = run_sh[0][2] = 0.f;
+        qcount = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nr = 1 + 3 * nrows;
+        int acc = 0;
+        for (int k = 0; k < nr; k++) {
+            run_pre[k] = acc;
+            acc += run_len[k];
+        }
+        run_pre[nr] = acc;
+        nrun_s = nr;
+    }
+    __syncthreads();
+    const int nrun = nrun_s, total = run_pre[nrun];
+    const double* X = xs + (size_t)img * 3 * n;
+    const double *Xx = X, *Xy = X + n, *Xz = X + 2 * (size_t)n;
+    const float4* F = sf + (size_t)img * n;
+    const int* Mo = smol + (size_t)img * n;
+    double e = 0.0;
+    auto flush_one = [&](int2 pr) {
+        const int i = pr.x < pr.y ? pr.x : pr.y, j = pr.x < pr.y ? pr.y : pr.x;
+        double ep, fx, fy, fz;
+        qm_pair_exact<true>(D, tb, Xx, Xy, Xz, i, j, ep, fx, fy, fz);
+        e += ep;
+        double* gi = g + (size_t)img * 3 * n + 3 * (size_t)i;
+        double* gj = g + (size_t)img * 3 * n + 3 * (size_t)j;
+        atomicAdd(gi, fx);
+        atomicAdd(gi + 1, fy);
+        atomicAdd(gi + 2, fz);
+        atomicAdd(gj, -fx);
+        atomicAdd(gj + 1, -fy);
+        atomicAdd(gj + 2, -fz);
+    };
+    for (int ib = hb; ib < he; ib += QM_CELL_IB) {
+        const int nb = min(QM_CELL_IB, he - ib);
+        __syncthreads();
+        if (tid < nb) {
+            si[tid] = F[ib + tid];
+            simol[tid] = Mo[ib + tid];
+        }
+        __syncthreads();
+        int r = 0;
+        for (int f0 = 0; f0 < total; f0 += 128) {
+            const int f = f0 + tid;
+            const bool valid = f < total;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            int molj = -1, jpos = 0;
+            bool own = false;
+            if (valid) {
+                while (f >= run_pre[r + 1]) r++;
+                jpos = run_beg[r] + (f - run_pre[r]);
+                c = F[jpos];
+                molj = Mo[jpos];
+                c.x += run_sh[r][0];
+                c.y += run_sh[r][1];
+                c.z += run_sh[r][2];
+                own = (r == 0);
+            }
+            const int ja = __float_as_int(c.w);
+            for (int ii = 0; ii < nb; ii++) {
+                const float4 a = si[ii];
+                const float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z;
+                bool ok = valid && (dx * dx + dy * dy + dz * dz <= G.rc2f) && (simol[ii] != molj);
+                if (own) ok = ok && (jpos > ib + ii);
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&qcount, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (ok) queue[base + __popc(m & ((1u << lane) - 1u))] = make_int2(__float_as_int(a.w), ja);
+                }
+            }
+            // flush whole groups of 128 queued pairs.  Two barriers per chunk: every push is in before the count is
+            // read, and every thread has read it before the next chunk pushes again
+            __syncthreads();
+            int qn = qcount;
+            __syncthreads();
+            if (qn >= 128) {                                // uniform
+                while (qn >= 128) {
+                    const int2 pr = queue[qn - 128 + tid];
+                    qn -= 128;
+                    flush_one(pr);
+                }
+                if (tid == 0) qcount = qn;
+                __syncthreads();                            // popped entries are free again, the new count is visible
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < qcount) flush_one(queue[tid]);
+    block_sum_to(e, &V[img]);
+}
+
 template <bool PER>
 __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const double* __restrict__ xs,
                                                        const float4* __restrict__ xf, double* __restrict__ V,
@@ -496,64 +807,17 @@ __global__ void __launch_bounds__(128) qm_inter_kernel(const QmdffDev D, const d
     const int i = blockIdx.x * 4 + warp;
     double e = 0.0;
     if (i < n - 1) {
-        const double xi = Xx[i], yi = Xy[i], zi = Xz[i], qi = D.q[i];
-        const int ti = D.type[i], mi = D.molnum[i];
-        const double* c6row = D.c6 + (size_t)i * n;
+        const int mi = D.molnum[i];
         constexpr bool per = PER;
         const double Lx = D.box[0], Ly = D.box[1], Lz = D.box[2];
         const double rc = fmax(D.vdw_cut, D.coul_cut);
         double gx = 0.0, gy = 0.0, gz = 0.0;
         int* qu = queue[warp];
         int qn = 0;
-        auto image = [&](double& v, double L) {
-            const double L2 = 0.5 * L;
-            while (fabs(v) > L2) v -= (v >= 0.0) ? L : -L;   // box_image.f90
-        };
         auto pair = [&](int j) {
-            double vab[3] = {xi - Xx[j], yi - Xy[j], zi - Xz[j]};   // x(i1) - x(i2), i1 < i2
-            if (per) {
-                image(vab[0], Lx);
-                image(vab[1], Ly);
-                image(vab[2], Lz);
-            }
-            const double r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2], r = sqrt(r2);
-            const double oner = 1.0 / r, oner2 = oner * oner;
-            double dr = 0.0, ep = 0.0;
-            if (!(per && r > D.vdw_cut)) {
-                const int tj = D.type[j];
-                const double c6 = __ldg(&c6row[j]);
-                const double R0 = tb.r094[ti][tj];
-                const double r4 = r2 * r2, r6 = r4 * r2, R02 = R0 * R0, r06 = R02 * R02 * R02;
-                const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
-                const double it6 = 1.0 / t6, it8 = 1.0 / t8;
-                const double c6t6 = c6 * it6, t27 = tb.sr42[ti][tj] * (c6 * it8);
-                ep -= c6t6 + t27;
-                dr += c6t6 * 6.0 * r4 * it6 + 8.0 * t27 * r6 * it8;
-                if (r < 25.0) {
-                    const double alpha = tb.r0ab[ti][tj];
-                    const double tt = tb.zab[ti][tj] * exp(-alpha * r);
-                    ep += tt * oner;
-                    dr -= tt * (alpha * r + 1.0) * oner * oner2;
-                }
-            }
-            if (!(r > D.coul_cut)) {
-                const double qq = qi * D.q[j];
-                double e0;
-                if (D.zahn) {
-                    e0 = qq * (erfc(D.zahn_a * r) * oner - D.zahn_par * (r - D.coul_cut));
-                } else {
-                    double sw = 1.0;
-                    if (per && r > D.cut_low) {
-                        const double xv = (r - D.cut_low) / (D.coul_cut - D.cut_low);
-                        sw = exp(1.0) * exp(1.0 / (xv - 1.0));
-                    }
-                    e0 = qq * oner * sw;
-                }
-                ep += e0;
-                dr -= e0 * oner2;   // the reference uses e0/r^2 for every Coulomb form (ff_nonb.f90:470)
-            }
+            double ep, fx, fy, fz;
+            qm_pair_exact<PER>(D, tb, Xx, Xy, Xz, i, j, ep, fx, fy, fz);
             e += ep;
-            const double fx = vab[0] * dr, fy = vab[1] * dr, fz = vab[2] * dr;
             gx += fx;
             gy += fy;
             gz += fz;
@@ -889,6 +1153,49 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         qm_soa_kernel<<<(unsigned)((natot + 255) / 256), 256, 0, s>>>(d_xyz, D->molnum, D->n, natot, D->xs, D->xf);
         if (launches) ++*launches;
     }
+    // cell sweep of the inter-molecular part: periodic boxes that hold at least 2M+1 cells of edge rc(1+slack)/M per
+    // dimension (M = 3 when the box allows it, else 2); everything else keeps the O(N^2) sweep.  CRCL_QM_CELLS=0
+    // switches it off (A/B measurements, tests of the fallback)
+    CellGrid G{};
+    bool use_cells = false;
+    if (inter && D->periodic && D->cells_enabled) {
+        const double rc = std::max(D->vdw_cut, D->coul_cut), rcs = rc * std::sqrt((double)QM_PREFILTER_SLACK) * 1.0005;
+        const char* em = getenv("CRCL_QM_CELL_M");
+        const int m_hi = (em && em[0] == '2') ? 2 : 3;
+        for (int m = m_hi; m >= 2 && !use_cells; m--) {
+            bool ok = true;
+            long long nct = 1;
+            for (int d = 0; d < 3; d++) {
+                G.nc[d] = (int)std::floor(D->box[d] * m / rcs);
+                ok = ok && G.nc[d] >= 2 * m + 1;
+                nct *= G.nc[d];
+            }
+            if (ok && nct <= QM_CELL_MAXCELL) {
+                G.m = m;
+                G.ncell = (int)nct;
+                G.rc2f = (float)(rc * rc) * QM_PREFILTER_SLACK;
+                use_cells = true;
+            }
+        }
+    }
+    if (use_cells) {
+        const int ni_max = std::min(65535, nimg);
+        const size_t need_a = (size_t)ni_max * D->n, need_c = (size_t)ni_max * (G.ncell + 1);
+        if (need_a > D->cell_cap_a || need_c > D->cell_cap_c) {
+            if (D->sf && (e = cudaFreeAsync(D->sf, s)) != cudaSuccess) return e;
+            if (D->smol && (e = cudaFreeAsync(D->smol, s)) != cudaSuccess) return e;
+            if (D->cstart && (e = cudaFreeAsync(D->cstart, s)) != cudaSuccess) return e;
+            D->sf = nullptr;
+            D->smol = nullptr;
+            D->cstart = nullptr;
+            D->cell_cap_a = D->cell_cap_c = 0;
+            if ((e = cudaMallocAsync(&D->sf, need_a * sizeof(float4), s)) != cudaSuccess) return e;
+            if ((e = cudaMallocAsync(&D->smol, need_a * sizeof(int), s)) != cudaSuccess) return e;
+            if ((e = cudaMallocAsync(&D->cstart, need_c * sizeof(int), s)) != cudaSuccess) return e;
+            D->cell_cap_a = need_a;
+            D->cell_cap_c = need_c;
+        }
+    }
     qm_init_kernel<<<(nimg + 127) / 128, 128, 0, s>>>(d_V, nimg, D->e_zero);
     int nl = 1;
     // blockIdx.y carries the image: at most 65535 images per launch
@@ -915,7 +1222,12 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
                 nl++;
             }
             if (D->nmols > 1) {
-                if (D->periodic)
+                if (use_cells) {
+                    qm_cellsort_kernel<<<ni, 1024, 0, s>>>(*D, G, D->xs + (size_t)i0 * 3 * D->n, D->sf, D->smol, D->cstart);
+                    qm_inter_cell_kernel<<<dim3(G.ncell, ni), 128, 0, s>>>(*D, G, D->xs + (size_t)i0 * 3 * D->n, D->sf,
+                                                                           D->smol, D->cstart, V, g);
+                    nl++;
+                } else if (D->periodic)
                     qm_inter_kernel<true><<<dim3((D->n + 3) / 4, ni), 128, 0, s>>>(*D, D->xs + (size_t)i0 * 3 * D->n,
                                                                                    D->xf + (size_t)i0 * D->n, V, g);
                 else
@@ -966,6 +1278,10 @@ int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, b
     const int n = T->n;
     QmdffDev* D = new QmdffDev();
     memset(D, 0, sizeof(*D));
+    {
+        const char* ev = getenv("CRCL_QM_CELLS");
+        D->cells_enabled = !(ev && ev[0] == '0');
+    }
     D->n = n;
     D->nbond = T->nbond;
     D->nangl = T->nangl;
@@ -1187,6 +1503,9 @@ void qmdff_free(QmdffDev* D)
     cudaFree(D->acc_no);
     cudaFree(D->xs);
     cudaFree(D->xf);
+    cudaFree(D->sf);
+    cudaFree(D->smol);
+    cudaFree(D->cstart);
     delete D;
 }
 

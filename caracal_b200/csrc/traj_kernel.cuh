@@ -931,8 +931,15 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
 // trajectory t = 2*g + k is child k (0: +p, 1: -p) of pair pair0+g.  Both children of a pair
 // draw the same momenta (RNG stream keyed by the pair index).  Writes weight = v_s/f_s,
 // denom_part and, per step, theta = [xi_real > 0]; kappa sums are formed by reduce_kappa.
+// CRCL_RECROSS_MAXNREG (tuning builds): an explicit register cap for the lane-split child kernel instead of the
+// minimum-blocks form, whose cap ptxas rounds down to a power-of-two-ish 128 (64-thread CTAs x 7 per SM would allow 144)
+#ifdef CRCL_RECROSS_MAXNREG
+#define CRCL_RECROSS_BOUNDS(PES, NB) __maxnreg__(CRCL_RECROSS_MAXNREG)
+#else
+#define CRCL_RECROSS_BOUNDS(PES, NB) __launch_bounds__(LaunchCfg<PES, NB>::TPB, LaunchCfg<PES, NB>::MINB)
+#endif
 template <class PES, int NB>
-__global__ void __launch_bounds__(LaunchCfg<PES, NB>::TPB, LaunchCfg<PES, NB>::MINB)
+__global__ void CRCL_RECROSS_BOUNDS(PES, NB)
 recross_kernel(const __grid_constant__ TrajArgs A)
 {
     extern __shared__ __align__(16) double smem[];

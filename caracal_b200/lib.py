@@ -102,6 +102,7 @@ SIGNATURES = {
     "crcl_verlet": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p,
                                    c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_int_p,
                                    c_u32_p, c_u32_p]),
+    "crcl_verlet_dev": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 11),
     "crcl_mdinit": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, c_double_p,
                                    c_double_p, c_double_p, c_u32_p, c_u32_p]),
     "crcl_calc_xi": (ctypes.c_int, [_H, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, c_double_p, c_double_p,

@@ -14,6 +14,15 @@ integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 
                              CRCL_PES_CH4OH = 6, CRCL_PES_GEH4OH = 7, CRCL_PES_WATER = 12
 integer(c_int), parameter :: CRCL_PES_QMDFF = 10, CRCL_PES_DGEVB = 11, CRCL_PES_HOSTCB = 100
 type(c_ptr), save :: crcl_h = c_null_ptr        ! one handle per MPI rank / GPU
+!     per-trajectory status bits (include/caracal_gpu.h): SHAKE_FAIL 1, NAN 2, SINGULAR 4, ENERGY 8, PESWARN 16,
+!     XI_RANGE 32, PBC_FAIL 64; CRCL_TRAJ_FATAL = all but PESWARN
+integer(c_int), parameter :: CRCL_TRAJ_SHAKE_FAIL = 1, CRCL_TRAJ_NAN = 2, CRCL_TRAJ_SINGULAR = 4, CRCL_TRAJ_ENERGY = 8, &
+                             CRCL_TRAJ_PESWARN = 16, CRCL_TRAJ_XI_RANGE = 32, CRCL_TRAJ_PBC_FAIL = 64, CRCL_TRAJ_FATAL = 111
+integer(c_int), parameter :: CRCL_UNIQUE_ID_BYTES = 128
+!     RNG stream of the trajectory this rank is propagating through verlet_gpu / mdinit_gpu: the library draws
+!     Philox(seed, traj, event, bead, component pair); the event counter must survive from call to call, otherwise
+!     every Andersen resample repeats the first draw (the drivers call verlet one step at a time)
+integer(c_int32_t), target, save :: crcl_traj(1) = 0_c_int32_t, crcl_event(1) = 0_c_int32_t
 
 !     struct crcl_qmdff_tables of include/caracal_gpu.h (field order and types must match)
 type, bind(C) :: crcl_qmdff_tables
@@ -283,6 +292,42 @@ interface
       type(c_ptr) :: crcl_last_error
    end function crcl_last_error
 
+   ! pbc_mod -> periodic wrap of verlet.f90:591-641 (crcl_set_qmdff / crcl_set_water set it from their tables)
+   function crcl_set_box(h, periodic, boxlen) bind(C, name="crcl_set_box")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: periodic
+      real(c_double), dimension(3), intent(in) :: boxlen
+      integer(c_int) :: crcl_set_box
+   end function crcl_set_box
+   ! rpmd_check.f90:88-116 inside the step: status bits CRCL_TRAJ_ENERGY / CRCL_TRAJ_XI_RANGE
+   function crcl_set_rpmd_check(h, on, energy_ts, energy_tol, xi_tol) bind(C, name="crcl_set_rpmd_check")
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      integer(c_int), value :: on
+      real(c_double), value :: energy_ts, energy_tol, xi_tol
+      integer(c_int) :: crcl_set_rpmd_check
+   end function crcl_set_rpmd_check
+   ! multi-GPU: NCCL communicator behind the C-ABI (one handle per rank); afterwards crcl_recross_children and
+   ! crcl_umbrella_windows are collective over the GLOBAL unit range with the reduction inside the library
+   function crcl_comm_unique_id(id_out) bind(C, name="crcl_comm_unique_id")
+      import :: c_int, c_char
+      character(kind=c_char), dimension(128), intent(out) :: id_out
+      integer(c_int) :: crcl_comm_unique_id
+   end function crcl_comm_unique_id
+   function crcl_comm_init(h, nranks, rank, unique_id) bind(C, name="crcl_comm_init")
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: h
+      integer(c_int), value :: nranks, rank
+      character(kind=c_char), dimension(128), intent(in) :: unique_id
+      integer(c_int) :: crcl_comm_init
+   end function crcl_comm_init
+   function crcl_comm_destroy(h) bind(C, name="crcl_comm_destroy")
+      import :: c_ptr, c_int
+      type(c_ptr), value :: h
+      integer(c_int) :: crcl_comm_destroy
+   end function crcl_comm_destroy
+
    ! custom_grad / external_grad stay on the host: fn(xyz, e, g, natoms, user) is called per bead
    function crcl_set_host_gradient_cb(h, fn, user) bind(C, name="crcl_set_host_gradient_cb")
       import :: c_ptr, c_funptr, c_int
@@ -298,10 +343,17 @@ contains
 !
 !     gpu_init: call once after read_pes / calc_rate_read (all globals below are set by then)
 !
-subroutine gpu_init(rank, pes_id)
+subroutine gpu_init(rank, pes_id, seed, psize)
 use general      ! natoms, mass(:), at_move(:), kelvin, thermostat, nose_q
 use evb_mod      ! nbeads, beta, andersen_step, bond_form, bond_break, form_ref, break_ref, ...
+implicit none
+include 'mpif.h' ! as the reference's drivers do (calc_rate.f90, recross.f90)
 integer, intent(in) :: rank, pes_id
+integer(kind=8), intent(in) :: seed      ! RANDOM_SEED of the key file (or a clock value broadcast from rank 0): the SAME
+                                         ! on every rank -- streams are told apart by the trajectory number, not the seed
+integer, intent(in), optional :: psize   ! number of MPI ranks: > 1 sets up the NCCL communicator behind the C-ABI
+character(kind=c_char), dimension(128) :: uid
+integer :: ierr
 integer(c_int) :: rc, i, k, n
 integer(c_int), allocatable :: amove(:), bf(:), bb(:), atr(:)
 real(kind=8) :: dt_dummy
@@ -337,7 +389,59 @@ end do
 rc = crcl_set_mechanism(crcl_h, int(form_num, c_int), bf, int(break_num, c_int), bb, form_ref, break_ref, &
                         int(sum_reacs, c_int), int(n_reac(1:sum_reacs), c_int), atr, R_inf)
 rc = crcl_set_thermostat(crcl_h, int(thermostat, c_int), int(andersen_step, c_int), kelvin, nose_q)
+!     counter-based RNG: one seed for the whole job (replaces random_init_local, andersen.f90:131); the trajectory
+!     this rank propagates starts as its rank number, gpu_new_trajectory sets it per window / trajectory / round
+rc = crcl_set_seed(crcl_h, int(seed, c_int64_t))
+crcl_traj(1) = int(rank, c_int32_t)
+crcl_event(1) = 0_c_int32_t
+!     the one exchange of the path: rank 0 makes the NCCL id, MPI ships its 128 bytes, every rank joins
+if (present(psize)) then
+   if (psize .gt. 1) then
+      if (rank .eq. 0) rc = crcl_comm_unique_id(uid)
+      call mpi_bcast(uid, 128, MPI_CHARACTER, 0, MPI_COMM_WORLD, ierr)
+      rc = crcl_comm_init(crcl_h, int(psize, c_int), int(rank, c_int), uid)
+      if (rc .ne. 0) then
+         write(*,*) "caracal_gpu: crcl_comm_init failed with code", rc
+         call fatal
+      end if
+   end if
+end if
 end subroutine gpu_init
+
+!
+!     gpu_new_trajectory: call where the drivers start a NEW trajectory (a new umbrella window / trajectory,
+!     calc_rate.f90:1387; a new recrossing parent, recross.f90:249): gives it its own RNG stream.  traj_id must be
+!     unique in the job, e.g. window*umbr_traj + j, and must not depend on the number of ranks.
+!
+subroutine gpu_new_trajectory(traj_id)
+integer, intent(in) :: traj_id
+crcl_traj(1) = int(traj_id, c_int32_t)
+crcl_event(1) = 0_c_int32_t
+end subroutine gpu_new_trajectory
+
+!
+!     mdinit_gpu: same argument list as mdinit (mdinit.f90:40); draws the momenta from the current stream and
+!     advances its event counter
+!
+subroutine mdinit_gpu(derivs, xi_ideal, dxi_act, bias_mode, rank)
+use general
+use evb_mod
+integer :: bias_mode, rank
+real(kind=8) :: xi_ideal
+real(kind=8) :: derivs(3,natoms,nbeads), dxi_act(3,natoms)
+integer(c_int) :: rc
+real(c_double) :: xi1(1), kf1(1)
+rc = crcl_set_thermostat(crcl_h, int(thermostat, c_int), int(andersen_step, c_int), kelvin, nose_q)
+xi1(1) = xi_ideal
+kf1(1) = 0.d0
+if (bias_mode .ne. 0) kf1(1) = k_force(um_window_act)
+rc = crcl_mdinit(crcl_h, 1_c_int, int(bias_mode, c_int), xi1, kf1, q_i, p_i, derivs, dxi_act, &
+                 c_loc(crcl_traj), c_loc(crcl_event))
+if (rc .ne. 0) then
+   write(*,*) "caracal_gpu: crcl_mdinit failed with code", rc
+   call fatal
+end if
+end subroutine mdinit_gpu
 
 !
 !     gpu_set_qmdff: hand the tables of the first QMDFF (module qmdff, pbc_mod; built by prepare.f90,
@@ -393,12 +497,16 @@ xi1(1) = xi_ideal
 kf1(1) = 0.d0
 if (constrain .ge. 0) kf1(1) = k_force(um_window_act)
 st(1) = 0
+!     the stream (trajectory number, event counter) lives in the module and is handed in and out on every call:
+!     with null pointers every Andersen resample would redraw event 0 of trajectory 0 (ADVICE r1)
 rc = crcl_verlet(crcl_h, 1_c_int, 1_c_int, int(istep-1, c_int), int(constrain, c_int), xi1, kf1, &
-                 q_i, p_i, derivs, ep1, xr1, dxi_act, st, c_null_ptr, c_null_ptr)
+                 q_i, p_i, derivs, ep1, xr1, dxi_act, st, c_loc(crcl_traj), c_loc(crcl_event))
 epot = ep1(1)
 xi_real = xr1(1)
-if (rc .ne. 0 .or. iand(st(1), 2+4) .ne. 0) then
-   ! verlet.f90:1256-1275: NaN/Inf coordinate is fatal in the reference
+!     verlet.f90:1256-1275, invert.f90, verlet.f90:601-640: NaN/Inf coordinate, singular inertia tensor and a
+!     runaway periodic wrap are `fatal` in the reference; a failed SHAKE only raises epot (rpmd_check then restarts),
+!     CRCL_TRAJ_ENERGY / CRCL_TRAJ_XI_RANGE go back to the caller's rpmd_check logic through epot / xi_real
+if (rc .ne. 0 .or. iand(st(1), CRCL_TRAJ_NAN + CRCL_TRAJ_SINGULAR + CRCL_TRAJ_PBC_FAIL) .ne. 0) then
    write(*,*) "Something went wrong during the dynamics (GPU status", st(1), ")"
    call fatal
 end if

@@ -275,6 +275,13 @@ int crcl_verlet(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain,
                 double *derivs, double *epot, double *xi_real, double *dxi, int *status,
                 const uint32_t *traj_id, uint32_t *event0);
 
+/* the same on state resident in device memory: every pointer is a device pointer, the call is asynchronous on the
+ * handle's stream and nothing crosses PCIe.  d_q, d_p, d_derivs, d_epot, d_xi_real, d_dxi, d_status, d_event must be
+ * given; d_xi_ideal, d_k_force, d_traj_id may be NULL as above. */
+int crcl_verlet_dev(crcl_handle h, int ntraj, int nsteps, int istep0, int constrain, const double *d_xi_ideal,
+                    const double *d_k_force, double *d_q, double *d_p, double *d_derivs, double *d_epot,
+                    double *d_xi_real, double *d_dxi, int *d_status, const uint32_t *d_traj_id, uint32_t *d_event);
+
 /* mdinit(derivs,xi_ideal,dxi_act,bias_mode,rank) (mdinit.f90:40): gradient of all beads,
  * umbrella (bias_mode 1 -> xi only, 2 -> bias applied, 0 -> none), fresh momenta, NHC reset. */
 int crcl_mdinit(crcl_handle h, int ntraj, int bias_mode, const double *xi_ideal,

@@ -30,6 +30,13 @@
 #define PI2_Q 6.28318530717958623199592693708837
 #define SPI_Q 1.77245385090551599275151910313925
 
+/* census hooks: the counting build (count_qmdff.cpp) drops the operations of a pair / donor-acceptor test that fails
+ * its cut-off, so that the census holds algorithmic work only ("only pairs inside the cutoff") */
+#ifndef ORC_MARK
+#define ORC_MARK()
+#define ORC_REJECT()
+#endif
+
 static void box_image(const orc_qmdff *f, double v[3])
 {
     int d;
@@ -382,11 +389,15 @@ static void nonb_vdw_pair(const orc_qmdff *f, const double *xyz, int i1, int i2,
     double vab[3], r2, r, oner, R0, c6, r4, r6, r06, t6, t8, c6t6, c6t8, t27, e0, drij, ga[3];
     const int iz1 = f->at[i1 - 1], iz2 = f->at[i2 - 1];
     int c;
+    ORC_MARK();
     for (c = 0; c < 3; c++) vab[c] = X(i1, c) - X(i2, c);
     if (f->periodic) box_image(f, vab);
     r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2];
     r = sqrt(r2);
-    if (f->periodic && r > f->vdw_cut) return;
+    if (f->periodic && r > f->vdw_cut) {
+        ORC_REJECT();
+        return;
+    }
     oner = 1.0 / r;
     R0 = T94(f->r094, iz1, iz2);
     c6 = f->c6xy[(i2 - 1) + (size_t)f->n * (i1 - 1)];
@@ -420,18 +431,25 @@ static void nonb_coul_pair(const orc_qmdff *f, const double *xyz, int i1, int i2
 {
     double vab[3], r2, r, sw = 1.0, oner, e0, drij;
     int c;
+    ORC_MARK();
     for (c = 0; c < 3; c++) vab[c] = X(i1, c) - X(i2, c);
     if (f->periodic) box_image(f, vab);
     r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2];
     r = sqrt(r2);
     if (f->periodic) {
-        if (r > f->coul_cut) return;
+        if (r > f->coul_cut) {
+            ORC_REJECT();
+            return;
+        }
         if (!f->zahn && r > f->cut_low) {
             const double xv = (r - f->cut_low) / (f->coul_cut - f->cut_low);
             sw = exp(1.0) * exp(1.0 / (xv - 1.0));
         }
     }
-    if (r > f->coul_cut) return;
+    if (r > f->coul_cut) {
+        ORC_REJECT();
+        return;
+    }
     oner = 1.0 / r;
     if (f->zahn)
         e0 = f->q[i1 - 1] * f->q[i2 - 1] * ((erfc(f->zahn_a * r) * oner) - f->zahn_par * (r - f->coul_cut));
@@ -650,15 +668,21 @@ void orc_ff_hb(const orc_qmdff *f, double *xyz, double *e_io, double *g)
                     double ri, rj, dum1, dum2, r;
                     if (f->molnum[at_H - 1] == f->molnum[j - 1]) continue;
                     if (!(zj == 7 || zj == 8)) continue;
+                    ORC_MARK();
                     ri = dist_img(f, xyz, at_A, at_H, 1);
                     rj = dist_img(f, xyz, j, at_H, 1);
                     dum1 = c12 * (f->rad[f->at[at_A - 1] - 1] + f->rad[f->at[at_H - 1] - 1]) / b0;
                     dum2 = c12 * (f->rad[zj - 1] + f->rad[f->at[at_H - 1] - 1]) / b0;
                     if (ri < dum1 || rj < dum2) {
                         r = dist_img(f, xyz, at_A, j, 0); /* not imaged (ff_hb.f90:159-161) */
-                        if (r > 15.0) continue;
+                        if (r > 15.0) {
+                            ORC_REJECT();
+                            continue;
+                        }
                         dum1 = hbpara(-6.5, 1.0, f->q_glob[at_H - 1]);
                         eabxag(f, xyz, at_A, j, at_H, f->scalexb[f->at[at_H - 1] - 1] * dum1, &eh, g);
+                    } else {
+                        ORC_REJECT();
                     }
                 }
             if (z1 == 1 && (z2 == 7 || z2 == 8 || z2 == 9 || z2 == 16 || z2 == 17)) {
@@ -678,16 +702,22 @@ void orc_ff_hb(const orc_qmdff *f, double *xyz, double *e_io, double *g)
                     if (f->molnum[at_H - 1] == f->molnum[j - 1]) continue;
                     cpar = f->scalehb[f->at[at_A - 1] - 1] * f->scalehb[zj - 1];
                     if (!(cpar > 1e-6)) continue;
+                    ORC_MARK();
                     ri = dist_img(f, xyz, at_A, at_H, 1);
                     rj = dist_img(f, xyz, j, at_H, 1);
                     dum1 = c13 * (f->rad[f->at[at_A - 1] - 1] + f->rad[0]) / b0;
                     dum2 = c13 * (f->rad[zj - 1] + f->rad[0]) / b0;
                     if (ri < dum1 || rj < dum2) {
                         r = dist_img(f, xyz, at_A, j, 1);
-                        if (r > 15.0) continue;
+                        if (r > 15.0) {
+                            ORC_REJECT();
+                            continue;
+                        }
                         c2 = hbpara(10.0, 5.0, f->q_glob[at_A - 1]) * f->scalehb[f->at[at_A - 1] - 1];
                         c1 = hbpara(10.0, 5.0, f->q_glob[j - 1]) * f->scalehb[zj - 1];
                         eabhag(f, xyz, j, at_A, at_H, c1, c2, &eh, g);
+                    } else {
+                        ORC_REJECT();
                     }
                 }
         }

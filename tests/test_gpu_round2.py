@@ -229,3 +229,45 @@ def test_multi_rank_communicator(gpu):
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count(" ok: kappa") == n
+
+
+@pytest.mark.parametrize("nmol,nimg", [(125, 3), (385, 2)])
+def test_cell_sweep_equals_n2_sweep_and_oracle(gpu, oracle, nmol, nimg):
+    """the cell-binned sweep of the inter-molecular part (qm_inter_cell_kernel, M = 3 and 2) against
+    the O(N^2) sweep it replaces (CRCL_QM_CELLS=0) and, for the smaller box, the oracle: same pairs, same bits per pair,
+    only the accumulation order differs -> 1e-12 relative between the sweeps, 1e-10 against the oracle.  Atoms are pushed
+    out of the box and onto faces so that the wrapped coordinates and the shifts of the wrap segments are exercised."""
+    import os
+    from tests.qmdff_synth import make_system
+    from tests.test_gpu_qmdff import handle, torsion_conditioning
+    T = make_system(nmol=nmol, seed=21, periodic=True, zahn=True, hb=False)
+    rng = np.random.default_rng(4)
+    x = T["xyz"][None] + rng.normal(0, 0.06, (nimg,) + T["xyz"].shape)
+    box = np.asarray(T["box"])
+    x[0] += 0.37 * box                                          # whole image displaced: most atoms leave the box
+    x[-1] -= np.floor(x[-1].min(axis=0) / box) * box + x[-1].min(axis=0) % box   # the lowest atom exactly on the faces
+    res = {}
+    for key, env in (("m3", {"CRCL_QM_CELLS": "1", "CRCL_QM_CELL_M": "3"}), ("m2", {"CRCL_QM_CELLS": "1", "CRCL_QM_CELL_M": "2"}),
+                     ("n2", {"CRCL_QM_CELLS": "0"})):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            g, _ = handle(gpu, T)
+            res[key] = g.egrad(x)[:2]
+            g.close()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    V0, g0 = res["n2"]
+    for key in ("m3", "m2"):
+        V, gr = res[key]
+        assert np.abs(V - V0).max() < 1e-12 * np.abs(V0).max(), key
+        assert C.rel_err_G(gr.reshape(nimg, -1, 3), g0.reshape(nimg, -1, 3)).max() < 1e-12, key
+    if nmol <= 125:
+        Vo, go = oracle.Qmdff(T).egrad(x)
+        assert C.rel_err_E(res["m3"][0], Vo).max() < C.TOL_EG
+        tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T, x) ** 2)
+        assert (C.rel_err_G(res["m3"][1].reshape(go.shape), go) < tol).all()
