@@ -33,10 +33,13 @@ CRCL_HD __forceinline__ void morse(double D, double B, double T, double r, doubl
     dV += 2.0 * B * D * u * x;
 }
 
-// H2O-like three-body term on (r_OHa, r_OHb, r_HaHb) (VH2O_oh3); adds to V and the
-// three derivatives in that argument order (the reference's DEDR(2)<->DEDR(3) swap folded in).
+// H2O-like three-body term on (r_OHa, r_OHb, r_HaHb) (VH2O_oh3); adds to V and the three derivatives in that
+// argument order (the reference's DEDR(2)<->DEDR(3) swap folded in).  D[3] mirrors COMMON /POT2CM_oh3/ DEDR(1:3) in the
+// caller's argument order: where Q(I) = 0 (0.5 gamma (R - Re) >= 43, R_OH > 37 a0) the reference skips the assignment
+// and the value of the PREVIOUS routine (V3POT_oh3, or the first VH2O_oh3 call) stays in DEDR(I), is swapped with the
+// others and added to the gradient (egrad_oh3.f:570-583) -- reproduced, so parity holds there too.
 CRCL_HD __forceinline__ void vh2o(double roha, double rohb, double rhh, double& V, double& da,
-                                     double& db, double& dhh)
+                                     double& db, double& dhh, double D[3])
 {
     const double S1 = roha - REOH, S3 = rohb - REOH, S2 = rhh - REHH;
     const double S[3] = {S1, S2, S3};
@@ -50,7 +53,7 @@ CRCL_HD __forceinline__ void vh2o(double roha, double rohb, double rhh, double& 
             one_minus_tanh(X, omt, ms2);
             Q[i] = omt;
             L[i] = 0.5 * GAM[i] * ms2 / omt;
-        } else {  // reference sets Q=0 and leaves DEDR stale; E is then exactly 0
+        } else {  // reference sets Q=0 and leaves DEDR(I) stale; E is then exactly 0
             Q[i] = 0.0;
             L[i] = 0.0;
         }
@@ -62,9 +65,16 @@ CRCL_HD __forceinline__ void vh2o(double roha, double rohb, double rhh, double& 
     const double DP2 = CON2 + CON4 * S2 + CON5 * (S1 + S3);
     const double DP3 = CON1 + CON3 * S3 + CON5 * S2 + CON6 * S1;
     V += E;
-    da += E * (L[0] + DP1 / P);
-    dhh += E * (L[1] + DP2 / P);
-    db += E * (L[2] + DP3 / P);
+    // DEDR(1:3) before the swap is indexed like S: (r_OHa, r_HH, r_OHb)
+    const double p0 = (Q[0] == 0.0) ? D[0] : E * (L[0] + DP1 / P);
+    const double p1 = (Q[1] == 0.0) ? D[1] : E * (L[1] + DP2 / P);
+    const double p2 = (Q[2] == 0.0) ? D[2] : E * (L[2] + DP3 / P);
+    D[0] = p0;
+    D[1] = p2;   // DEDR(2) <-> DEDR(3)
+    D[2] = p1;
+    da += D[0];
+    db += D[1];
+    dhh += D[2];
 }
 
 CRCL_HD __forceinline__ void pot(const double R[6], double& V, double dV[6])
@@ -75,6 +85,7 @@ CRCL_HD __forceinline__ void pot(const double R[6], double& V, double dV[6])
     morse(DE0, BETA0, RE0, R[0], V, dV[0]);
     morse(DE1, BETA1, RE1, R[3], V, dV[3]);
     morse(DE1, BETA1, RE1, R[4], V, dV[4]);
+    double DEDR[3];   // COMMON /POT2CM_oh3/ DEDR(1:3) as the routines below leave it (see vh2o)
     // three-body LEPS on (OH2, OH3, H2H3)  (V3POT_oh3)
     {
         constexpr double Z = SATO, ZPO = 1.0 + Z, OP3Z = 1.0 + 3.0 * Z, TOP3Z = 2.0 * OP3Z,
@@ -99,12 +110,12 @@ CRCL_HD __forceinline__ void pot(const double R[6], double& V, double dV[6])
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double B = be[i] * (de[i] / 4.0 / ZPO) * 2.0;
-            dV[idx[i]] += B * X[i] *
-                          ((3.0 * EX[i] - S) * RS2 * (OP3Z * X[i] - ZP3) / RAD - ZP3 * X[i] + OP3Z);
+            DEDR[i] = B * X[i] * ((3.0 * EX[i] - S) * RS2 * (OP3Z * X[i] - ZP3) / RAD - ZP3 * X[i] + OP3Z);
+            dV[idx[i]] += DEDR[i];
         }
     }
-    vh2o(R[0], R[1], R[3], V, dV[0], dV[1], dV[3]);
-    vh2o(R[0], R[2], R[4], V, dV[0], dV[2], dV[4]);
+    vh2o(R[0], R[1], R[3], V, dV[0], dV[1], dV[3], DEDR);
+    vh2o(R[0], R[2], R[4], V, dV[0], dV[2], dV[4], DEDR);
     // four-body term on (OH2, OH3, H1H2, H1H3)  (V4POT_oh3; A=ALP, C=CLAM, COF=ACON)
     {
         const double r[4] = {R[1], R[2], R[3], R[4]};

@@ -52,6 +52,10 @@ def test_egrad_matches_oracle(gpu, oracle, periodic, zahn, nmol, nimg):
     tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T, x) ** 2)
     err = C.rel_err_G(gd.reshape(go.shape), go)
     assert (err < tol).all(), (err / tol).max()
+    # how far the stated 1e-10 is widened: over the five parameter sets 15 of 163 images hold a torsion
+    # within |sin phi| < 4.5e-4 of 0 or pi and are compared at a looser bound, the loosest 2.2e-8; every other image at 1e-10
+    widened = int((tol > C.TOL_EG).sum())
+    assert widened <= max(2, nimg // 6) and tol.max() < 5e-8, (widened, tol.max())
 
 
 @pytest.mark.parametrize("periodic,nmol,nimg,halogen", [(True, 12, 32, 0.0), (True, 12, 32, 0.3), (False, 12, 32, 0.3),

@@ -48,6 +48,30 @@ def test_h3_compact_geometries(oracle, host_harness):
     assert C.rel_err_G(gd, go).max() < C.TOL_EG
 
 
+def test_oh3_stale_dedr_region(oracle, host_harness):
+    """VH2O_oh3 (egrad_oh3.f:549-583): for 0.5 gamma (R - Re) >= 43 (an O-H or H-H distance beyond ~37 a0) the routine
+    sets Q(I) = 0, skips DEDR(I) and the value the previous routine left in COMMON /POT2CM_oh3/ is swapped and added to
+    the gradient.  The device functor reproduces that (no longer an unsampled divergence): separated
+    fragments OH + H2, OH2 ... H, O ... H3 at 40-80 a0, energies and gradients against the literal restatement."""
+    rng = np.random.default_rng(9)
+    base = C.oh3_ts()
+    qs = []
+    for far in ([3], [2, 3], [1], [1, 2, 3], [2]):
+        for dist in (40.0, 55.0, 80.0):
+            q = base + rng.normal(0, 0.05, base.shape)
+            for a in far:
+                q[a] += rng.normal(0, 1.0, 3) / np.sqrt(3) * 0.0 + np.array([dist, 0.3 * a, -0.2 * a])
+            qs.append(q)
+    q = np.array(qs)
+    Vo, go, _ = oracle.egrad("oh3", q)
+    Vd, gd = hh_egrad(host_harness, "oh3", q)
+    assert np.isfinite(Vo).all() and np.isfinite(go).all()
+    assert C.rel_err_E(Vd, Vo).max() < C.TOL_EG
+    assert (np.abs(gd - go).max(axis=(1, 2)) < 1e-10 * np.maximum(np.abs(go).max(axis=(1, 2)), 1e-6)).all()
+    # the region is really the stale one: a functor that returned 0 there would miss a finite contribution
+    assert np.abs(go).max() > 1e-4
+
+
 def _hh_xi(H, name, x, xi_ideal, mode, beta, hams):
     m = C.masses(name)
     mech = C.mechanism(name)
