@@ -41,6 +41,7 @@ struct crcl_handle_s {
     cudaEvent_t evs[2 * NEV] = {nullptr};
     int ev_head = 0, ev_count = 0;
     bool timed = false;
+    bool capturing = false;   // inside a stream capture: no event records (they would become graph nodes)
     double* d_fker = nullptr;
     bool fker_dirty = true;
     crcl_host_grad_fn cb = nullptr;
@@ -302,13 +303,13 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
     }
     if (A.ntraj <= 0) return CRCL_OK;
     int nosup = 0;
-    if (h->timed) {
+    if (h->timed && !h->capturing) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
     }
     cudaError_t e = table[row][kind](h->nbeads, A, bias_mode, h->nose_q, h->stream, &nosup);
     if (nosup) return fail(h, CRCL_ENOSUP, "fused trajectory kernel: nbeads must be a power of two <= 128");
-    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
     h->launches++;
     if (e != cudaSuccess) {
         h->err = std::string("trajectory kernel launch: ") + cudaGetErrorString(e);
@@ -465,7 +466,7 @@ static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
     const int nc = 3 * A.natoms;
     const size_t ncomp = (size_t)nc * A.ntraj;
     dim3 grid((unsigned)((ncomp + 127) / 128));
-    if (h->timed) {
+    if (h->timed && !h->capturing) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
     }
@@ -488,7 +489,7 @@ static int launch_kick_freerp(crcl_handle h, const SplitArgs& A)
         sp_kick_freerp_smem<<<g2, bd, smem, h->stream>>>(A);
     }
     }
-    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
     h->launches++;
     CK(cudaGetLastError());
     return CRCL_OK;
@@ -593,7 +594,7 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
     // One step as a sequence of 6-14 small launches.  Small systems are launch-bound, so steps 2..nsteps are
     // replayed from a CUDA graph captured once per call (two variants: with / without the Andersen draw);
     // step 1 runs eagerly so that every grow-only scratch buffer has its final size before the capture.
-    const bool can_graph = h->use_graph && !h->timed && nsteps >= 4 && h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE;
+    const bool can_graph = h->use_graph && nsteps >= 4 && h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE;
     uint32_t* dctr = nullptr;   // device step counter: where sp_theta writes when the step is a graph replay
     if (can_graph && C.theta) {
         if ((rc = scratch(h, 27, (size_t)2, &dctr))) return rc;
@@ -701,7 +702,9 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
                 h->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e);
                 return CRCL_ECUDA;
             }
+            h->capturing = true;
             rc = one_step(st, an);
+            h->capturing = false;
             e = cudaStreamEndCapture(s, &graph);
             glaunches[v] = h->launches - l0;
             h->launches = l0;
@@ -1206,13 +1209,13 @@ int crcl_ewald_recip(crcl_handle h, int n, int nimg, const double* xyz, const do
         return rc;
     CK(cudaMemcpyAsync(dx, xyz, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(dq, q, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (h->timed) {
+    if (h->timed && !h->capturing) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
     }
     const char* msg = "";
     rc = ewald_recip(h->ewald, n, nimg, dx, dq, de, dg, h->stream, &h->launches, &msg);
-    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
     if (rc) return fail(h, rc, msg);
     CK(cudaMemcpyAsync(energy, de, (size_t)nimg * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(grad, dg, nx * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1348,7 +1351,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
         int rc;
         if ((rc = scratch(h, 12, n, &g1)) || (rc = scratch(h, 13, n, &g2)) || (rc = scratch(h, 14, (size_t)2 * nimg, &v12)))
             return rc;
-        if (h->timed) {
+        if (h->timed && !h->capturing) {
             next_event_pair(h);
             cudaEventRecord(h->ev0, h->stream);
         }
@@ -1357,7 +1360,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
         if (e == cudaSuccess)
             e = dgevb_mix(h->dgevb, natoms, d_q, nimg, v12, g1, v12 + nimg, g2, d_V, d_dVdq, h->stream);
         h->launches++;
-        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
         if (e != cudaSuccess) {
             h->err = std::string("dg-evb kernels: ") + cudaGetErrorString(e);
             return CRCL_ECUDA;
@@ -1370,12 +1373,12 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
         if (nimg == 0) return CRCL_OK;
         CK(cudaSetDevice(h->device));
         if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
-        if (h->timed) {
+        if (h->timed && !h->capturing) {
             next_event_pair(h);
             cudaEventRecord(h->ev0, h->stream);
         }
         cudaError_t e = water_egrad(h->water, d_q, nimg, d_V, d_dVdq, h->stream, &h->launches);
-        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
         if (e != cudaSuccess) {
             h->err = std::string("water kernels: ") + cudaGetErrorString(e);
             return CRCL_ECUDA;
@@ -1388,12 +1391,12 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
         if (nimg == 0) return CRCL_OK;
         CK(cudaSetDevice(h->device));
         if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
-        if (h->timed) {
+        if (h->timed && !h->capturing) {
             next_event_pair(h);
             cudaEventRecord(h->ev0, h->stream);
         }
         cudaError_t e = qmdff_egrad(h->qmdff, d_q, nimg, d_V, d_dVdq, h->stream, &h->launches);
-        if (h->timed) cudaEventRecord(h->ev1, h->stream);
+        if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
         if (e != cudaSuccess) {
             h->err = std::string("qmdff kernels: ") + cudaGetErrorString(e);
             return CRCL_ECUDA;
@@ -1405,7 +1408,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     CK(cudaSetDevice(h->device));
     const int tpb = 128, grid = (nimg + tpb - 1) / tpb;
     if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
-    if (h->timed) {
+    if (h->timed && !h->capturing) {
         next_event_pair(h);
         cudaEventRecord(h->ev0, h->stream);
     }
@@ -1419,7 +1422,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_GEH4OH: egrad_kernel<PesGeH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     default: return fail(h, CRCL_ENOSUP, "unknown PES id");
     }
-    if (h->timed) cudaEventRecord(h->ev1, h->stream);
+    if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);
     h->launches++;
     CK(cudaGetLastError());
     return CRCL_OK;

@@ -8,6 +8,7 @@
 namespace crcl {
 
 constexpr int QM_MAXTYPE = 12;  // distinct elements in one force field
+constexpr int QM_MAXCLS = 256;  // distinct rows of the c6 table that are still kept as classes
 
 struct QmdffDev {
     int n, nbond, nangl, ntors, nnci, ldvt, nmols, ntype;
@@ -25,6 +26,9 @@ struct QmdffDev {
     double* vtors;
     int* nci;
     double* c6;  // [n][n] symmetric: c6xy(max,min) of the reference
+    int ncls;    // > 0: c6(i,j) == c6c[cls[i]][cls[j]] for every pair (verified at upload)
+    int* cls;    // [n]
+    double* c6c; // [ncls][ncls]
     // H/X-bond terms (ff_hb.f90)
     int nhb, ndonor, use_hb;
     int is_two;       // evaluate with the *_two semantics (second diabatic state)

@@ -503,7 +503,7 @@ __device__ __forceinline__ void qm_pair_exact(const QmdffDev& D, const InterTabl
     ep = 0.0;
     if (!(per && r > D.vdw_cut)) {
         const int ti = D.type[i], tj = D.type[j];
-        const double c6 = __ldg(&D.c6[(size_t)i * D.n + j]);
+        const double c6 = D.ncls ? __ldg(&D.c6c[D.cls[i] * D.ncls + D.cls[j]]) : __ldg(&D.c6[(size_t)i * D.n + j]);
         const double R0 = tb.r094[ti][tj];
         const double r4 = r2 * r2, r6 = r4 * r2, R02 = R0 * R0, r06 = R02 * R02 * R02;
         const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
@@ -629,13 +629,12 @@ __global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, co
                                                             double* __restrict__ g)
 {
     __shared__ InterTables tb;
-    __shared__ int run_beg[QM_CELL_MAXRUN], run_pre[QM_CELL_MAXRUN + 1];
+    __shared__ int run_beg[QM_CELL_MAXRUN], run_pre[QM_CELL_MAXRUN + 1], run_len[QM_CELL_MAXRUN];
     __shared__ float run_sh[QM_CELL_MAXRUN][3];
     __shared__ float4 si[QM_CELL_IB];
     __shared__ int simol[QM_CELL_IB];
-    __shared__ int2 queue[128 + 128 * QM_CELL_IB];
-    __shared__ int qcount, nrun_s;
-    const int img = blockIdx.y, n = D.n, tid = threadIdx.x, lane = tid & 31;
+    __shared__ int2 queue[4][64];                          // per warp: < 32 left over + up to 32 new per test round
+    const int img = blockIdx.y, n = D.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < QM_MAXTYPE * QM_MAXTYPE; t += 128) {
         (&tb.r094[0][0])[t] = (&D.r094[0][0])[t];
         (&tb.sr42[0][0])[t] = (&D.sr42[0][0])[t];
@@ -649,13 +648,11 @@ __global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, co
     const int cx = home % ncx, cy = (home / ncx) % ncy, cz = home / (ncx * ncy);
     // runs of the half shell: rows (oz, oy) with oz > 0, or oz == 0 and oy >= 0; the row (0, 0) only holds the
     // cells ox = 1..M (the home cell itself is run 0).  A row's cells are contiguous in the sorted order except
-    // where the periodic wrap splits it: up to three segments, each with its own shift.
-    // thread t < nrows fills the three segment slots of row t (empty segments keep length 0), thread 0 the prefix
-    __shared__ int run_len[QM_CELL_MAXRUN];
+    // where the periodic wrap splits it: up to three segments, each with its own shift.  Thread t < nrows fills
+    // the three segment slots of row t (empty segments keep length 0), thread 0 the prefix.
     const int nrows = M * (2 * M + 1) + (M + 1);
     if (tid < nrows) {
-        // rows in the order (oz = 0: oy = 0..M), (oz = 1..M: oy = -M..M)
-        int oz, oy;
+        int oz, oy;                                        // rows in the order (0; 0..M), (1..M; -M..M)
         if (tid <= M) {
             oz = 0;
             oy = tid;
@@ -693,26 +690,27 @@ __global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, co
         run_beg[0] = hb;                                  // run 0: the home cell itself (pairs with jpos > ipos)
         run_len[0] = he - hb;
         run_sh[0][0] = run_sh[0][1] = run_sh[0][2] = 0.f;
-        qcount = 0;
     }
     __syncthreads();
+    const int nrun = 1 + 3 * nrows;
     if (tid == 0) {
-        const int nr = 1 + 3 * nrows;
         int acc = 0;
-        for (int k = 0; k < nr; k++) {
+        for (int k = 0; k < nrun; k++) {
             run_pre[k] = acc;
             acc += run_len[k];
         }
-        run_pre[nr] = acc;
-        nrun_s = nr;
+        run_pre[nrun] = acc;
     }
     __syncthreads();
-    const int nrun = nrun_s, total = run_pre[nrun];
+    const int total = run_pre[nrun];
     const double* X = xs + (size_t)img * 3 * n;
     const double *Xx = X, *Xy = X + n, *Xz = X + 2 * (size_t)n;
     const float4* F = sf + (size_t)img * n;
     const int* Mo = smol + (size_t)img * n;
     double e = 0.0;
+    int2* qu = queue[warp];
+    int qn = 0;
+    const unsigned lt = (1u << lane) - 1u;
     auto flush_one = [&](int2 pr) {
         const int i = pr.x < pr.y ? pr.x : pr.y, j = pr.x < pr.y ? pr.y : pr.x;
         double ep, fx, fy, fz;
@@ -729,15 +727,17 @@ __global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, co
     };
     for (int ib = hb; ib < he; ib += QM_CELL_IB) {
         const int nb = min(QM_CELL_IB, he - ib);
-        __syncthreads();
+        __syncthreads();                                   // the previous batch is no longer read
         if (tid < nb) {
             si[tid] = F[ib + tid];
             simol[tid] = Mo[ib + tid];
         }
         __syncthreads();
+        // every warp sweeps its own 32 candidates of each 128-chunk against the batch and keeps its own queue: no
+        // CTA-wide barrier inside the sweep, warps drift apart and hide each other's latencies
         int r = 0;
-        for (int f0 = 0; f0 < total; f0 += 128) {
-            const int f = f0 + tid;
+        for (int f0 = warp * 32; f0 < total; f0 += 128) {  // uniform per warp
+            const int f = f0 + lane;
             const bool valid = f < total;
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
             int molj = -1, jpos = 0;
@@ -759,31 +759,22 @@ __global__ void __launch_bounds__(128) qm_inter_cell_kernel(const QmdffDev D, co
                 bool ok = valid && (dx * dx + dy * dy + dz * dz <= G.rc2f) && (simol[ii] != molj);
                 if (own) ok = ok && (jpos > ib + ii);
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (m) {
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&qcount, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (ok) queue[base + __popc(m & ((1u << lane) - 1u))] = make_int2(__float_as_int(a.w), ja);
+                if (m) {                                   // uniform
+                    if (ok) qu[qn + __popc(m & lt)] = make_int2(__float_as_int(a.w), ja);
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        const int2 pr = qu[qn + lane];
+                        __syncwarp();
+                        flush_one(pr);
+                    }
                 }
-            }
-            // flush whole groups of 128 queued pairs.  Two barriers per chunk: every push is in before the count is
-            // read, and every thread has read it before the next chunk pushes again
-            __syncthreads();
-            int qn = qcount;
-            __syncthreads();
-            if (qn >= 128) {                                // uniform
-                while (qn >= 128) {
-                    const int2 pr = queue[qn - 128 + tid];
-                    qn -= 128;
-                    flush_one(pr);
-                }
-                if (tid == 0) qcount = qn;
-                __syncthreads();                            // popped entries are free again, the new count is visible
             }
         }
     }
-    __syncthreads();
-    if (tid < qcount) flush_one(queue[tid]);
+    __syncwarp();
+    if (lane < qn) flush_one(qu[lane]);
     block_sum_to(e, &V[img]);
 }
 
@@ -1154,14 +1145,16 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         if (launches) ++*launches;
     }
     // cell sweep of the inter-molecular part: periodic boxes that hold at least 2M+1 cells of edge rc(1+slack)/M per
-    // dimension (M = 3 when the box allows it, else 2); everything else keeps the O(N^2) sweep.  CRCL_QM_CELLS=0
+    // dimension (M = 2; 3 on request); everything else keeps the O(N^2) sweep.  CRCL_QM_CELLS=0
     // switches it off (A/B measurements, tests of the fallback)
     CellGrid G{};
     bool use_cells = false;
     if (inter && D->periodic && D->cells_enabled) {
         const double rc = std::max(D->vdw_cut, D->coul_cut), rcs = rc * std::sqrt((double)QM_PREFILTER_SLACK) * 1.0005;
+        // M = 2 by default: measured on B200 (profiles/r2d_bench_qmdff_cells.json) the finer M = 3 grid loses more to its
+        // short inner loops (4 atoms per home cell) than its tighter shell saves; CRCL_QM_CELL_M=3 selects it
         const char* em = getenv("CRCL_QM_CELL_M");
-        const int m_hi = (em && em[0] == '2') ? 2 : 3;
+        const int m_hi = (em && em[0] == '3') ? 3 : 2;
         for (int m = m_hi; m >= 2 && !use_cells; m--) {
             bool ok = true;
             long long nct = 1;
@@ -1385,6 +1378,59 @@ int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, b
             const int lo = a < b ? a : b, hi = a < b ? b : a;
             c6[(size_t)a * n + b] = T->c6xy[(size_t)hi + (size_t)n * lo];
         }
+    // c6 classes: atoms whose rows of the symmetric table coincide share a class (a box of identical solvent molecules
+    // has one class per atom of the molecule).  c6(i,j) = c6c[cls(i)][cls(j)] is verified for EVERY pair before it is
+    // used, so the pair kernels read the same doubles from a table that lives in L1 / L2 instead of gathering from the
+    // n x n array (73 MB at 3030 atoms); more than QM_MAXCLS classes or any mismatch keeps the full table.
+    std::vector<int> cls(n, 0);
+    std::vector<double> c6c;
+    int ncls = 0;
+    {
+        std::vector<int> rep;
+        std::vector<unsigned long long> rep_hash;
+        for (int a = 0; a < n && ncls >= 0; a++) {
+            unsigned long long hsh = 1469598103934665603ull;   // FNV-1a over the row's bytes: rows are only compared on a hit
+            const unsigned char* rb = reinterpret_cast<const unsigned char*>(&c6[(size_t)a * n]);
+            for (size_t t = 0; t < sizeof(double) * (size_t)n; t++) hsh = (hsh ^ rb[t]) * 1099511628211ull;
+            int found = -1;
+            for (int k = 0; k < (int)rep.size(); k++)
+                if (rep_hash[k] == hsh && memcmp(&c6[(size_t)a * n], &c6[(size_t)rep[k] * n], sizeof(double) * n) == 0) {
+                    found = k;
+                    break;
+                }
+            if (found < 0) {
+                if ((int)rep.size() == QM_MAXCLS) {
+                    ncls = -1;
+                    break;
+                }
+                found = (int)rep.size();
+                rep.push_back(a);
+                rep_hash.push_back(hsh);
+            }
+            cls[a] = found;
+        }
+        if (ncls >= 0) {
+            ncls = (int)rep.size();
+            c6c.assign((size_t)ncls * ncls, 0.0);
+            for (int k = 0; k < ncls; k++)
+                for (int l = 0; l < ncls; l++) {
+                    // a representative pair of (k, l): first atom of class l other than rep[k] if possible
+                    int b = rep[l];
+                    c6c[(size_t)k * ncls + l] = c6[(size_t)rep[k] * n + b];
+                }
+            // rows equal does not yet make c6(a,b) a function of the classes of BOTH atoms: check every entry
+            bool same = true;
+            for (int a = 0; a < n && same; a++)
+                for (int b = 0; b < n; b++)
+                    if (memcmp(&c6[(size_t)a * n + b], &c6c[(size_t)cls[a] * ncls + cls[b]], sizeof(double)) != 0) {
+                        same = false;
+                        break;
+                    }
+            if (!same) ncls = -1;
+        }
+        if (ncls < 0) ncls = 0;
+    }
+    D->ncls = ncls;
     // ff_hb tables: hb list, donor bonds (static topology) and per-atom acceptor data
     D->use_hb = T->scalehb ? 1 : 0;
     D->nhb = D->use_hb ? T->nhb : 0;
@@ -1468,6 +1514,8 @@ int qmdff_upload(const crcl_qmdff_tables* T, QmdffDev** out, const char** err, b
     D->vtors = up(T->vtors, (size_t)T->ldvt * T->ntors, ok);
     D->nci = up(nci.data(), nci.size(), ok);
     D->c6 = up(c6.data(), c6.size(), ok);
+    D->cls = up(cls.data(), cls.size(), ok);
+    D->c6c = up(c6c.data(), c6c.size(), ok);
     if (!ok) {
         qmdff_free(D);
         *err = "device allocation / upload of the QMDFF tables failed";
@@ -1491,6 +1539,8 @@ void qmdff_free(QmdffDev* D)
     cudaFree(D->vtors);
     cudaFree(D->nci);
     cudaFree(D->c6);
+    cudaFree(D->cls);
+    cudaFree(D->c6c);
     cudaFree(D->hb);
     cudaFree(D->vhb);
     cudaFree(D->isH);
