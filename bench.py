@@ -307,7 +307,10 @@ def other_config(args, emit, rank, world, local_rank, cores):
         return 0
 
     # ------------------------------------------------------------------------------------------ product
-    stream = torch.cuda.current_stream()
+    # everything (torch's flush, the library's launches, the timing events) on one non-default stream: the HBM-resident
+    # path replays its steps from a CUDA graph, and a capture cannot start on the legacy default stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     T = lambda a, dt_=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt_, device=dev)
     if spec["kind"] == "recross":

@@ -594,7 +594,9 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
     // One step as a sequence of 6-14 small launches.  Small systems are launch-bound, so steps 2..nsteps are
     // replayed from a CUDA graph captured once per call (two variants: with / without the Andersen draw);
     // step 1 runs eagerly so that every grow-only scratch buffer has its final size before the capture.
-    const bool can_graph = h->use_graph && nsteps >= 4 && h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE;
+    // (a capture cannot start on the legacy default stream: a handle that was given stream 0 launches eagerly)
+    bool can_graph = h->use_graph && nsteps >= 4 && h->pes != CRCL_PES_HOSTCB && h->pes != CRCL_PES_NONE && s != nullptr &&
+                     s != cudaStreamLegacy;
     uint32_t* dctr = nullptr;   // device step counter: where sp_theta writes when the step is a graph replay
     if (can_graph && C.theta) {
         if ((rc = scratch(h, 27, (size_t)2, &dctr))) return rc;
@@ -698,9 +700,14 @@ static int verlet_split(crcl_handle h, const SplitCall& C, int nsteps, int istep
             cudaGraph_t graph = nullptr;
             cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
             if (e != cudaSuccess) {
-                drop_graphs();
-                h->err = std::string("cudaStreamBeginCapture: ") + cudaGetErrorString(e);
-                return CRCL_ECUDA;
+                // this stream cannot be captured (e.g. it is itself part of somebody else's capture): eager launches
+                cudaGetLastError();
+                can_graph = false;
+                if ((rc = one_step(st, an))) {
+                    drop_graphs();
+                    return rc;
+                }
+                continue;
             }
             h->capturing = true;
             rc = one_step(st, an);
