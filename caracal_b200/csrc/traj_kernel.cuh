@@ -93,6 +93,7 @@ struct Group {
     static constexpr bool WARP = (T <= 32);
     static constexpr int CPB = (CRCL_CTPB / T > 1) ? (CRCL_CTPB / T < 15 ? CRCL_CTPB / T : 15) : 1;   // 15 named barriers
     static constexpr int TPB = WARP ? CRCL_WTPB : T * CPB;  // threads per block
+    static constexpr int RED_N = 9;                          // values per warp in the reduction scratch (sum_n)
     static constexpr int GPB = WARP ? CRCL_WTPB / T : CPB;  // trajectories per block
     // re-align the warps of a CTA that holds several trajectories (one barrier per step)
     static __device__ __forceinline__ void align_warps()
@@ -137,12 +138,43 @@ struct Group {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             sync();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;   // red is indexed by the warp's number in the CTA
+            if ((threadIdx.x & 31) == 0) red[(threadIdx.x >> 5) * RED_N] = v;   // red is indexed by the warp's number in the CTA
             sync();
             double t = 0.0;
 #pragma unroll
-            for (int w = 0; w < T / 32; w++) t += red[gib * (T / 32) + w];
+            for (int w = 0; w < T / 32; w++) t += red[(gib * (T / 32) + w) * RED_N];
             return t;
+        }
+    }
+    // the same all-reduce for N values at once: every value goes through the same shuffle tree and the same order over the
+    // warps as in sum() (identical bits), but a multi-warp trajectory pays ONE pair of barriers instead of N
+    template <int N>
+    __device__ __forceinline__ void sum_n(double (&v)[N]) const
+    {
+        static_assert(N <= RED_N, "enlarge the reduction scratch");
+        if (WARP) {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int o = T / 2; o > 0; o >>= 1) v[i] += __shfl_xor_sync(mask, v[i], o);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; i++)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+            sync();
+            if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+                for (int i = 0; i < N; i++) red[(threadIdx.x >> 5) * RED_N + i] = v[i];
+            }
+            sync();
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                double t = 0.0;
+#pragma unroll
+                for (int w = 0; w < T / 32; w++) t += red[(gib * (T / 32) + w) * RED_N + i];
+                v[i] = t;
+            }
         }
     }
     __device__ __forceinline__ int any(int pred) const
@@ -154,11 +186,11 @@ struct Group {
         else {
             const int w = __any_sync(0xffffffffu, pred);
             sync();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w ? 1.0 : 0.0;
+            if ((threadIdx.x & 31) == 0) red[(threadIdx.x >> 5) * RED_N] = w ? 1.0 : 0.0;
             sync();
             double t = 0.0;
 #pragma unroll
-            for (int k = 0; k < T / 32; k++) t += red[gib * (T / 32) + k];
+            for (int k = 0; k < T / 32; k++) t += red[(gib * (T / 32) + k) * RED_N];
             return t != 0.0;
         }
     }
@@ -180,7 +212,7 @@ struct SmemLayout {
     // load_fker), otherwise the three circulant kernels f[N]
     static constexpr bool HTAB = (NB > 1 && NB <= 32);
     static constexpr int FKER = HTAB ? 3 * NB * NB : 3 * NB;
-    static constexpr int BLOCK = (FKER + 32 + 1) & ~1;      // + reduction scratch (even: double2 alignment)
+    static constexpr int BLOCK = (FKER + 32 * Group<NB, LANES>::RED_N + 1) & ~1;   // + reduction scratch: RED_N values for each of up to 32 warps (even: double2 alignment)
     static constexpr size_t bytes()
     {
         return sizeof(double) * (BLOCK + Group<NB, LANES>::GPB * PER_GROUP);
@@ -615,8 +647,14 @@ struct Traj {
                     s[7] -= qx * v * w;
                 }
             }
+        {
+            double s9[9];
 #pragma unroll
-        for (int i = 0; i < 9; i++) s[i] = G.sum(s[i]);
+            for (int i = 0; i < 9; i++) s9[i] = s[i];
+            G.sum_n(s9);
+#pragma unroll
+            for (int i = 0; i < 9; i++) s[i] = s9[i];
+        }
         const double totmass = (mt * NB) * NB;
         double vtot[3], ctr[3], mang[3];
 #pragma unroll
@@ -641,12 +679,16 @@ struct Traj {
                 yz += yd * zd * w;
                 zz += zd * zd * w;
             }
-        xx = G.sum(xx);
-        xy = G.sum(xy);
-        xz = G.sum(xz);
-        yy = G.sum(yy);
-        yz = G.sum(yz);
-        zz = G.sum(zz);
+        {
+            double s6[6] = {xx, xy, xz, yy, yz, zz};
+            G.sum_n(s6);
+            xx = s6[0];
+            xy = s6[1];
+            xz = s6[2];
+            yy = s6[3];
+            yz = s6[4];
+            zz = s6[5];
+        }
         double t[3][3] = {{yy + zz, -xy, -xz}, {-xy, xx + zz, -yz}, {-xz, -yz, xx + yy}};
         if (NAT <= 2) {
             t[0][0] += 0.000001;
@@ -841,6 +883,9 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
         Grp::align_warps();
         // a failed trajectory is frozen (the reference aborts or restarts it)
         if (!(T.status & CRCL_TRAJ_FATAL)) {
+            // epot leaves the kernel from the last step only (and feeds rpmd_check when that is on): the other steps skip
+            // the trajectory-wide sum of the bead energies.  A failed SHAKE still raises the status on its own step.
+            T.want_epot = (s == A.nsteps) || A.chk_on;
             T.step(A.istep0 + s, (s & 15) == 0 || s == A.nsteps);
             sx += T.xi_real;
             sx2 += T.xi_real * T.xi_real;
