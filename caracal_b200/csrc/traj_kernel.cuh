@@ -624,12 +624,15 @@ struct Traj {
         double mt = 0.0;
 #pragma unroll
         for (int j = 0; j < NAT; j++) mt += A.mass[j];
+        double vk[NO];   // velocity of the owned components, p / m as the reference divides it (kept for the last loop)
 #pragma unroll
-        for (int k = 0; k < NO; k++)
+        for (int k = 0; k < NO; k++) {
+            vk[k] = 0.0;
             if (oc[k] >= 0) {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
                 const double w = A.mass[j];
                 const double v = P(c) / w;
+                vk[k] = v;
                 const double qx = Q(3 * j), qy = Q(3 * j + 1), qz = Q(3 * j + 2);
                 s[d] += v * w;
                 // (q x e_d) v w
@@ -647,6 +650,7 @@ struct Traj {
                     s[7] -= qx * v * w;
                 }
             }
+        }
         {
             double s9[9];
 #pragma unroll
@@ -695,34 +699,19 @@ struct Traj {
             t[1][1] += 0.000001;
             t[2][2] += 0.000001;
         }
-        // invert.f90's full-pivot Gauss-Jordan keeps its pivot bookkeeping in (local-memory) arrays: on trajectories of
-        // a warp or more one thread inverts and publishes the angular velocity (same arithmetic, 1/T of the traffic)
+        // every thread inverts its own copy of the tensor: the sums above are bit-identical on all threads of the
+        // trajectory and invert3 lives in registers, so this costs no barrier and nobody waits for a publishing thread
+        if (invert3(t)) return 1;
         double vang[3];
-        if (Grp::T >= 32) {
-            if (G.tig == 0) {
-                const int sing = invert3(t);
 #pragma unroll
-                for (int i = 0; i < 3; i++) xis[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
-                xis[3] = sing ? 1.0 : 0.0;
-            }
-            G.sync();
-            const bool sing = xis[3] != 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) vang[i] = xis[i];
-            G.sync();
-            if (sing) return 1;
-        } else {
-            if (invert3(t)) return 1;
-#pragma unroll
-            for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
-        }
+        for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
 #pragma unroll
         for (int k = 0; k < NO; k++)
             if (oc[k] >= 0) {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
                 const double w = A.mass[j];
                 const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
-                double v = P(c) / w - vtot[d];
+                double v = vk[k] - vtot[d];
                 if (d == 0)
                     v = v - vang[1] * zd + vang[2] * yd;
                 else if (d == 1)
