@@ -458,7 +458,8 @@ class RPMD:
 # ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
 _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"],
              _l.PES_BRH2: ["H", "BR", "H"], _l.PES_O3: ["O", "O", "O"],
-             _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"], _l.PES_GEH4OH: ["H", "GE", "H", "H", "H", "O", "H"]}
+             _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"], _l.PES_GEH4OH: ["H", "GE", "H", "H", "H", "O", "H"],
+             _l.PES_CH4CN: ["H", "C", "H", "H", "H", "C", "N"]}
 _egrad_handles = {}
 
 
@@ -497,6 +498,10 @@ def egrad_ch4oh(q, Natoms=7, Nbeads=None):
 
 def egrad_geh4oh(q, Natoms=7, Nbeads=None):
     return egrad(_l.PES_GEH4OH, q, Natoms, Nbeads)
+
+
+def egrad_ch4cn(q, Natoms=7, Nbeads=None):
+    return egrad(_l.PES_CH4CN, q, Natoms, Nbeads)
 
 
 def egrad_ch4h(q, Natoms=6, Nbeads=None):

@@ -37,7 +37,7 @@ constexpr double GS = G0 / RHX;
 CRCL_HD __forceinline__ void hx(double R, double& vs, double& va, double& dvs, double& dva)
 {
     const double d = R - RHX, d2 = d * d;
-    const double e1 = exp(-AHX * d), e2 = exp(-BHX * d2 * d);
+    const double e1 = CRCL_EXP(-AHX * d), e2 = CRCL_EXP(-BHX * d2 * d);
     const double t = DHX * e1 * e2, t1 = 2.0 * AHX * t, t2 = 3.0 * BHX * d2;
     vs = t * (e1 - 2.0);
     va = t * (e1 + 2.0);
@@ -81,7 +81,7 @@ CRCL_HD __forceinline__ double lowest_root(double (&a)[10], double (&u)[4], int&
                 h += d[k] * d[k];
             }
             double f = d[l - 1];
-            double g = -sgn(sqrt(h), f);
+            double g = -sgn(CRCL_SQRT(h), f);   // h in [1/l, 1] after the scaling
             e[i] = scale * g;
             h = h - f * g;
             d[l - 1] = f - g;
@@ -108,7 +108,7 @@ CRCL_HD __forceinline__ double lowest_root(double (&a)[10], double (&u)[4], int&
             }
         }
         d[i] = a[pk(i, i)];
-        a[pk(i, i)] = scale * sqrt(h);
+        a[pk(i, i)] = scale * CRCL_SQRT0(h);
     }
     // TQL2 (:808-978) on the tridiagonal (d, e); z accumulates the rotations
     double z[4][4];
@@ -141,7 +141,7 @@ CRCL_HD __forceinline__ double lowest_root(double (&a)[10], double (&u)[4], int&
                 iter++;
                 const double g0 = d[l];
                 double p = (d[l + 1] - g0) / (2.0 * e[l]);
-                double r = sqrt(p * p + 1.0);
+                double r = CRCL_SQRT(p * p + 1.0);
                 d[l] = e[l] / (p + sgn(r, p));
                 const double h = g0 - d[l];
 #pragma unroll
@@ -155,13 +155,13 @@ CRCL_HD __forceinline__ double lowest_root(double (&a)[10], double (&u)[4], int&
                         const double g = c * e[i], hh = c * p;
                         if (!(fabs(p) < fabs(e[i]))) {
                             c = e[i] / p;
-                            r = sqrt(c * c + 1.0);
+                            r = CRCL_SQRT(c * c + 1.0);
                             e[i + 1] = s * p * r;
                             s = c / r;
                             c = 1.0 / r;
                         } else {
                             c = p / e[i];
-                            r = sqrt(c * c + 1.0);
+                            r = CRCL_SQRT(c * c + 1.0);
                             e[i + 1] = s * e[i] * r;
                             s = 1.0 / r;
                             c = c * s;
@@ -216,19 +216,19 @@ CRCL_HD __forceinline__ void pot(double R1, double R2, double R3, double& V, dou
     if (R2 > R1 + R3) R2 = R1 + R3;
     if (R3 > R1 + R2) R3 = R1 + R2;
     const double R1S = R1 * R1, R2S = R2 * R2, R3S = R3 * R3;
-    const double i12 = 1.0 / (R1 * R2), i13 = 1.0 / (R1 * R3), i23 = 1.0 / (R2 * R3);
+    const double i12 = CRCL_RCP(R1 * R2), i13 = CRCL_RCP(R1 * R3), i23 = CRCL_RCP(R2 * R3);
     const double T3 = 0.5 * (R1S + R2S - R3S), T2 = 0.5 * (R1S + R3S - R2S), T1 = 0.5 * (R2S + R3S - R1S);
     // angle A at H1 (between R1 and R3), angle B at H3 (between R2 and R3); G is the angle at Br
     double csa = T2 * i13;
     if (fabs(csa) > 1.0) csa = copysign(1.0, csa);
     const double ca2 = csa * csa, sa2 = 1.0 - ca2;
     const bool lcol = sa2 < EPS;
-    const double sna = sqrt(sa2), s2a = 2.0 * csa * sna;
+    const double sna = CRCL_SQRT0(sa2), s2a = 2.0 * csa * sna;
     const double ka = lcol ? 0.0 : 2.0 * (sa2 - ca2) / sna;       // d sin2A / d cosA
     double csb = T1 * i23;
     if (fabs(csb) > 1.0) csb = copysign(1.0, csb);
     const double cb2 = csb * csb, sb2 = 1.0 - cb2;
-    const double snb = sqrt(sb2), s2b = 2.0 * csb * snb;
+    const double snb = CRCL_SQRT0(sb2), s2b = 2.0 * csb * snb;
     const double kb = lcol ? 0.0 : 2.0 * (sb2 - cb2) / snb;
     // d cosA / dR_i and d cosB / dR_i
     const double a1 = T3 * i13 / R1, a2 = -R2 * i13, a3 = T1 * i13 / R3;
@@ -240,7 +240,7 @@ CRCL_HD __forceinline__ void pot(double R1, double R2, double R3, double& V, dou
     double v1hh, v3hh, dv1hh, dv3hh;
     {
         const double d = R3 - RHH, dd = d * d;
-        const double e1 = exp(-AHH * d), e2 = exp(-BHH * d * dd);
+        const double e1 = CRCL_EXP(-AHH * d), e2 = CRCL_EXP(-BHH * d * dd);
         const double t = DHH * e1 * e2, t1 = 2.0 * AHH * t, t2 = 3.0 * BHH * dd;
         v1hh = t * (e1 - 2.0);
         v3hh = ETAHH * t * (e1 + 2.0);
@@ -302,24 +302,24 @@ CRCL_HD __forceinline__ void pot(double R1, double R2, double R3, double& V, dou
     // three-centre term (:406-427)
     double shh, dshh, shx1, dshx1, shx2, dshx2;
     {
-        const double t = XIH * R3, ex = exp(-t);
+        const double t = XIH * R3, ex = CRCL_EXP(-t);
         shh = (1.0 + t * (1.0 + C3 * t)) * ex;
         dshh = -XIH * t * (1.0 + t) * C3 * ex;
     }
     constexpr double TX = XIB * RHX;
-    const double iden = 1.0 / (2.0 * RHX * (1.0 + TX * (1.0 + C3 * TX)) * exp(-TX));
+    const double iden = 1.0 / (2.0 * RHX * (1.0 + TX * (1.0 + C3 * TX)) * CRCL_EXP(-TX));
     {
-        const double t = XIB * R1, ex = exp(-t) * iden;
+        const double t = XIB * R1, ex = CRCL_EXP(-t) * iden;
         shx1 = R1 * (1.0 + t * (1.0 + C3 * t)) * ex;
         dshx1 = (1.0 + t * (1.0 - C3 * t * t)) * ex;
     }
     {
-        const double t = XIB * R2, ex = exp(-t) * iden;
+        const double t = XIB * R2, ex = CRCL_EXP(-t) * iden;
         shx2 = R2 * (1.0 + t * (1.0 + C3 * t)) * ex;
         dshx2 = (1.0 + t * (1.0 - C3 * t * t)) * ex;
     }
     const double rd = R1 - R2;
-    const double tg = GS * exp(-ALFW * rd * rd);
+    const double tg = GS * CRCL_EXP(-ALFW * rd * rd);
     const double ov = shh * (shx1 + shx2) + shx1 * shx2;
     const double tw = 2.0 * ALFW * rd * csg2;
     V = e0 + ov * tg * csg2 + DHH;
@@ -354,13 +354,14 @@ struct PesBrH2 {
             v2[d] = q[6 + d] - q[3 + d];
             v3[d] = q[6 + d] - q[d];
         }
-        const double R1 = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
-        const double R2 = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
-        const double R3 = sqrt(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]);
+        double R1, R2, R3, iR1, iR2, iR3;
+        sqrt_rsqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], R1, iR1);
+        sqrt_rsqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2], R2, iR2);
+        sqrt_rsqrt(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2], R3, iR3);
         double d1, d2, d3;
         int fail;
         brh2::pot(R1, R2, R3, V, d1, d2, d3, fail);
-        const double f1 = d1 / R1, f2 = d2 / R2, f3 = d3 / R3;
+        const double f1 = d1 * iR1, f2 = d2 * iR2, f3 = d3 * iR3;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             g[d] = -f1 * v1[d] - f3 * v3[d];

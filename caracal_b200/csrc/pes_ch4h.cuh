@@ -41,6 +41,7 @@ constexpr double AA1 = 1.265960, AA2 = 0.000710, AA3 = 0.985920, AA4 = 2.785060;
 // switchf_ch4h :1598-1601
 constexpr double A1S = 1.5132681e-7, B1S = -4.3792246, A2S = 1.9202402e-7, B2S = -12.323018;
 constexpr double PI = 3.141592653589793;
+constexpr double TAU_TET = 1.9106332362490186;   // acos(-1/3), the tetrahedral angle (refangles_ch4h)
 
 // Morse-like singlet/triplet pair for one bond: vq, vj and their r- and a-derivatives
 struct Leps {
@@ -48,7 +49,7 @@ struct Leps {
 };
 CRCL_HD __forceinline__ Leps leps(double d1, double d3, double a, double dr)
 {
-    const double X1 = exp(-a * dr), X2 = X1 * X1;
+    const double X1 = CRCL_EXP(-a * dr), X2 = X1 * X1;
     Leps o;
     o.vq = 0.5 * ((d1 + d3) * X2 - 2.0 * (d1 - d3) * X1);
     o.vj = 0.5 * ((d1 - d3) * X2 - 2.0 * (d1 + d3) * X1);
@@ -110,6 +111,7 @@ struct K6 {
     static constexpr double A2S = ch4h::A2S;
     static constexpr double B2S = ch4h::B2S;
     static constexpr double FKH2OEQ = 0.0, ALPH2O = 0.0, ANH2OEQ = 0.0;   // unused without HAS_OH
+    static constexpr double MORSE_R0 = 0.0, MORSE_A = 0.0, MORSE_D = 0.0;
     static constexpr bool SPHI_ANY_R = false;
     static constexpr double TAU_PLANAR = 0.5;
 };
@@ -145,14 +147,15 @@ struct PesCBE1 {
         constexpr int HA[4] = {2, 3, 4, 0};  // 0-based atom index of methane hydrogen x
         constexpr int CA = 1, BA = 5;
         double c[4][3], ubh[4][3], ucb[3];  // unit vectors H-C, H-Hb, Hb-C
-        double rch[4], rbh[4], rcb;
+        double rch[4], irch[4], rbh[4], rcb;
         {
             double t[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) t[d] = q[3 * BA + d] * 0.52918 - q[3 * CA + d] * 0.52918;
-            rcb = sqrt(dot(t, t));
+            double ircb;
+            sqrt_rsqrt(dot(t, t), rcb, ircb);
 #pragma unroll
-            for (int d = 0; d < 3; d++) ucb[d] = t[d] / rcb;
+            for (int d = 0; d < 3; d++) ucb[d] = t[d] * ircb;
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 double tc[3], tb[3];
@@ -164,20 +167,21 @@ struct PesCBE1 {
                     tc[d] = h - q[3 * CA + d] * 0.52918;
                     tb[d] = h - q[3 * BA + d] * 0.52918;
                 }
-                rch[x] = sqrt(dot(tc, tc));
-                rbh[x] = sqrt(dot(tb, tb));
+                double irbh;
+                sqrt_rsqrt(dot(tc, tc), rch[x], irch[x]);
+                sqrt_rsqrt(dot(tb, tb), rbh[x], irbh);
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    c[x][d] = tc[d] / rch[x];
-                    ubh[x][d] = tb[d] / rbh[x];
+                    c[x][d] = tc[d] * irch[x];
+                    ubh[x][d] = tb[d] * irbh;
                 }
             }
         }
-        double tno[3] = {0, 0, 0}, rno = 1.0;   // H(O) - O in Angstrom (coorden_ch4oh :351,:361)
+        double tno[3] = {0, 0, 0}, rno = 1.0, irno = 1.0;   // H(O) - O in Angstrom (coorden_ch4oh :351,:361)
         if constexpr (K::HAS_OH) {
 #pragma unroll
             for (int d = 0; d < 3; d++) tno[d] = q[3 * 6 + d] * 0.52918 - q[3 * BA + d] * 0.52918;
-            rno = sqrt(dot(tno, tno));
+            sqrt_rsqrt(dot(tno, tno), rno, irno);
         }
         double gO[3] = {0, 0, 0}, gBx[3] = {0, 0, 0};   // explicit vector parts on H(O) and on the abstracting atom
         // accumulators: dV/d(distance) and explicit vector parts
@@ -228,7 +232,7 @@ struct PesCBE1 {
                 }
             }
             if (K::SPHI_ANY_R || r < 3.8) {   // egrad_geh4oh.f:1793-1804 drops the cut for sphi only
-                const double u = r - K::CPHI, ex = exp(K::BPHI * u * u * u);
+                const double u = r - K::CPHI, ex = CRCL_EXP(K::BPHI * u * u * u);
                 one_minus_tanh(K::APHI * dr * ex, omt, ms2);
                 sphi[x] = omt;
                 dsphi[x] = K::APHI * (1.0 + 3.0 * K::BPHI * dr * u * u) * ex * ms2;
@@ -237,7 +241,7 @@ struct PesCBE1 {
                 dsphi[x] = 0.0;
             }
             if (r < 3.8) {
-                const double v = r - K::CTHETA, ev = exp(K::BTHETA * v * v * v);
+                const double v = r - K::CTHETA, ev = CRCL_EXP(K::BTHETA * v * v * v);
                 one_minus_tanh(K::ATHETA * dr * ev, omt, ms2);
                 sth[x] = omt;
                 dsth[x] = K::ATHETA * (1.0 + 3.0 * K::BTHETA * dr * v * v) * ev * ms2;
@@ -248,7 +252,7 @@ struct PesCBE1 {
         }
         // reference angles theta0(i,j) = tau + ta (sphi_i sphi_j - 1) + tb (sth_k sth_l - 1)
         // with {k,l} the complement of {i,j} (refangles_ch4h)
-        const double tau = acos(-1.0 / 3.0);
+        const double tau = TAU_TET;
         const double ta = tau - K::TAU_PLANAR * PI, tb = tau - 2.0 * PI / 3.0;   // halfpi, or taugeh (egrad_geh4oh.f:368)
         auto theta0 = [&](int i, int j, int k, int l) {
             return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
@@ -276,17 +280,19 @@ struct PesCBE1 {
                 const Leps ch = leps(K::D1CH, K::D3CH, ach, dr);
                 const Leps bh = leps(K::D1HH, K::D3HH, K::AHH, rbh[i] - K::R0HH);
                 const double a = ch.vj, b = cb.vj, cc = bh.vj;
-                const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
+                double vjs, ivjs;
+                sqrt_rsqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5, vjs, ivjs);
+                const double vj = -vjs;
                 en += ch.vq + cb.vq + bh.vq + vj;
-                const double h = 0.5 / vj;
+                const double h = -0.5 * ivjs;
                 const double wa = (2.0 * a - b - cc) * h, wb = (2.0 * b - a - cc) * h,
                              wc = (2.0 * cc - a - b) * h;
                 const double dch = ch.dvq + wa * ch.dvj;
                 Dch[i] += dch;
                 Dbh[i] += bh.dvq + wc * bh.dvj;
                 Dcb += cb.dvq + wb * cb.dvj;
-                // d/d(ach): exp(-a dr) depends on a exactly as on r with dr/a swapped
-                Dach += dch * (dr / ach);
+                // d/d(ach): CRCL_EXP(-a dr) depends on a exactly as on r with dr/a swapped
+                Dach += dch * CRCL_DIV(dr, ach);
             }
             const double t = Dach * dach;
 #pragma unroll
@@ -312,8 +318,7 @@ struct PesCBE1 {
                     b[d] = c[l][d] * rch[l] - hj;
                 }
                 cross(a, b, n);
-                const double nn = sqrt(dot(n, n));
-                const double inn = 1.0 / nn;
+                const double inn = CRCL_RSQRT(dot(n, n));
                 double u[3];
                 u[0] = dot(n, c[j]) * inn;
                 u[1] = dot(n, c[k]) * inn;
@@ -332,14 +337,14 @@ struct PesCBE1 {
                 for (int t = 0; t < 3; t++) {
                     const int m = m3[t];
                     const double um = sg * u[t];
-                    const double del = acos(um) - theta0(i, m, ca[t], cb2[t]);
+                    const double del = CRCL_ACOS(um) - theta0(i, m, ca[t], cb2[t]);
                     const double d2 = del * del;
                     sum2 += d2;
                     sum4 += d2 * d2;
                     const double w = 2.0 * fd * del + 4.0 * hd * d2 * del;
-                    const double wu = -w / sqrt(1.0 - um * um);  // dV/du_m
+                    const double wu = -w * CRCL_RSQRT(1.0 - um * um);  // dV/du_m
                     // u_m = nhat . chat_m : direct part through chat_m
-                    const double f = wu / rch[m];
+                    const double f = wu * irch[m];
 #pragma unroll
                     for (int d = 0; d < 3; d++) {
                         const double v = f * (nh[d] - um * c[m][d]);
@@ -383,11 +388,11 @@ struct PesCBE1 {
 #pragma unroll
             for (int x = 0; x < 4; x++) {
                 const double dr = rch[x] - K::R0CH, dh = rbh[x] - K::R0HH;
-                const double e1 = exp(-K::AA1 * rbh[x] * rbh[x]);
-                const double e2 = exp(-K::AA4 * dh * dh);
+                const double e1 = CRCL_EXP(-K::AA1 * rbh[x] * rbh[x]);
+                const double e2 = CRCL_EXP(-K::AA4 * dh * dh);
                 const double a1 = 1.0 - e1;
                 const double a2 = K::AA2 + K::AA3 * e2;
-                const double E = exp(-a2 * dr * dr);
+                const double E = CRCL_EXP(-a2 * dr * dr);
                 f1[x] = a1 * E;
                 df1c[x] = -2.0 * dr * a1 * a2 * E;
                 df1h[x] = 2.0 * K::AA1 * rbh[x] * e1 * E + 2.0 * K::AA3 * K::AA4 * dh * e2 * dr * dr * a1 * E;
@@ -401,11 +406,11 @@ struct PesCBE1 {
                 const double ff = f1[i] * f1[j];
                 const double Kf = fk0 * ff;
                 const double cs = dot(c[i], c[j]);
-                const double del = acos(cs) - theta0(i, j, k, l);
+                const double del = CRCL_ACOS(cs) - theta0(i, j, k, l);
                 en += 0.5 * Kf * del * del;
                 const double w = Kf * del;                 // dV/d(delta)
-                const double wc = -w / sqrt(1.0 - cs * cs);  // dV/d(cos)
-                const double fi = wc / rch[i], fj = wc / rch[j];
+                const double wc = -w * CRCL_RSQRT(1.0 - cs * cs);  // dV/d(cos)
+                const double fi = wc * irch[i], fj = wc * irch[j];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
                     const double vi = fi * (c[j][d] - cs * c[i][d]);
@@ -427,9 +432,9 @@ struct PesCBE1 {
 
         if constexpr (K::HAS_OH) {
             // ---- O-H Morse bond (stretch_ch4oh :616-621, :652-659, :769-774) ----
-            const double ex = exp(-K::AHH * (rno - K::R0HH)), om = 1.0 - ex;
-            en += K::D1HH * (om * om);
-            const double de = 2.0 * K::AHH * K::D1HH * om * ex / rno;
+            const double ex = CRCL_EXP(-K::MORSE_A * (rno - K::MORSE_R0)), om = 1.0 - ex;
+            en += K::MORSE_D * (om * om);
+            const double de = 2.0 * K::MORSE_A * K::MORSE_D * om * ex * irno;
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 gBx[d] -= de * tno[d];
@@ -441,9 +446,9 @@ struct PesCBE1 {
                 double tb[3];   // the reference's tbh(i,:) = O - H_i
 #pragma unroll
                 for (int d = 0; d < 3; d++) tb[d] = -ubh[i][d] * rbh[i];
-                double cs = -dot(tno, tb) / (rno * rbh[i]);
+                double cs = -dot(tno, tb) * CRCL_RCP(rno * rbh[i]);
                 cs = fmin(1.0, fmax(-1.0, cs));
-                const double dang = acos(cs) - K::ANH2OEQ;
+                const double dang = CRCL_ACOS(cs) - K::ANH2OEQ;
                 const double arga = K::ALPH2O * (rbh[i] - K::R0HH);
                 double omt, ms2;
                 one_minus_tanh(arga, omt, ms2);
@@ -453,9 +458,9 @@ struct PesCBE1 {
                 const double dstda = fk * dang;
                 double pv[3], v1[3], v2[3];
                 cross(tno, tb, pv);
-                double rp = sqrt(dot(pv, pv));
+                double rp = CRCL_SQRT(fmax(dot(pv, pv), 1.0e-300));
                 if (rp < 1.0e-6) rp = 1.0e-6;
-                const double terma = dstda / (rbh[i] * rbh[i] * rp), termc = dstda / (rno * rno * rp);
+                const double terma = dstda * CRCL_RCP(rbh[i] * rbh[i] * rp), termc = dstda * CRCL_RCP(rno * rno * rp);
                 cross(tb, pv, v1);
                 cross(tno, pv, v2);
 #pragma unroll
@@ -520,6 +525,12 @@ struct PesCBE4 {
     static constexpr int ID = K::ID;
     static constexpr int LANES = 4;
     static constexpr int NOWN = K::HAS_OH ? 6 : 5;  // components owned per lane (5,5,4,4 of 18; 6,5,5,5 of 21)
+#ifndef CRCL_CBE_SHFL_GATHER
+    // per-hydrogen quantities travel between the four lanes of a bead through shared memory: 18 doubles per lane,
+    // written as nine 16-byte stores and read back as nine 16-byte loads per neighbour (36 memory instructions instead
+    // of the 102 SHFL of the 51 doubles a lane gathers).  -DCRCL_CBE_SHFL_GATHER restores the shuffles (A/B builds).
+    static constexpr int COOP_SCRATCH = 18;
+#endif
 
     // component (atom*3+xyz) number k owned by lane x, or -1: the lane's hydrogen, then C and H_b
     // spread as lane0: Cx,Cy  lane1: Cz,Bx  lane2: By  lane3: Bz; with H(O): lane2: x  lane3: y  lane0: z
@@ -534,7 +545,8 @@ struct PesCBE4 {
     // q(c): position component c of this image (any callable); x: lane 0..3; mask: shuffle mask.
     // Returns the energy on lane 0 (0 on the others) and the gradient of the owned components.
     template <class QF>
-    __device__ static __forceinline__ int eval_coop(QF q, int x, unsigned mask, double& V, double gown[NOWN])
+    __device__ static __forceinline__ int eval_coop(QF q, int x, unsigned mask, double& V, double gown[NOWN],
+                                                   double* scr = nullptr)
     {
         using namespace ch4h;
         auto shf = [&](double v, int src) { return __shfl_sync(mask, v, src & 3, 4); };
@@ -549,11 +561,10 @@ struct PesCBE4 {
                 tc[d] = h - C;
                 tb[d] = h - B;
             }
-            rcb = sqrt(dot(t, t));
-            rcho = sqrt(dot(tc, tc));
-            rbho = sqrt(dot(tb, tb));
-            ircho = 1.0 / rcho;
-            const double ircb = 1.0 / rcb, irbho = 1.0 / rbho;
+            double ircb, irbho;
+            sqrt_rsqrt(dot(t, t), rcb, ircb);
+            sqrt_rsqrt(dot(tc, tc), rcho, ircho);
+            sqrt_rsqrt(dot(tb, tb), rbho, irbho);
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 ucb[d] = t[d] * ircb;
@@ -592,11 +603,11 @@ struct PesCBE4 {
             }
             {
                 const bool on = r < 3.8, onphi = K::SPHI_ANY_R || on;
-                const double u = r - K::CPHI, ex = exp(K::BPHI * u * u * u);
+                const double u = r - K::CPHI, ex = CRCL_EXP(K::BPHI * u * u * u);
                 one_minus_tanh(K::APHI * dr * ex, omt, ms2);
                 sw[6] = onphi ? omt : 0.0;
                 sw[7] = onphi ? K::APHI * (1.0 + 3.0 * K::BPHI * dr * u * u) * ex * ms2 : 0.0;
-                const double v = r - K::CTHETA, ev = exp(K::BTHETA * v * v * v);
+                const double v = r - K::CTHETA, ev = CRCL_EXP(K::BTHETA * v * v * v);
                 one_minus_tanh(K::ATHETA * dr * ev, omt, ms2);
                 sw[8] = on ? omt : 0.0;
                 sw[9] = on ? K::ATHETA * (1.0 + 3.0 * K::BTHETA * dr * v * v) * ev * ms2 : 0.0;
@@ -606,10 +617,10 @@ struct PesCBE4 {
         double f1o, df1co, df1ho;
         {
             const double dr = rcho - K::R0CH, dh = rbho - K::R0HH;
-            const double e1 = exp(-K::AA1 * rbho * rbho);
-            const double e2 = exp(-K::AA4 * dh * dh);
+            const double e1 = CRCL_EXP(-K::AA1 * rbho * rbho);
+            const double e2 = CRCL_EXP(-K::AA4 * dh * dh);
             const double a1 = 1.0 - e1, a2 = K::AA2 + K::AA3 * e2;
-            const double E = exp(-a2 * dr * dr);
+            const double E = CRCL_EXP(-a2 * dr * dr);
             f1o = a1 * E;
             df1co = -2.0 * dr * a1 * a2 * E;
             df1ho = 2.0 * K::AA1 * rbho * e1 * E + 2.0 * K::AA3 * K::AA4 * dh * e2 * dr * dr * a1 * E;
@@ -617,6 +628,59 @@ struct PesCBE4 {
         // rotated gathers: local t <-> hydrogen (x+t)&3
         double c[4][3], rch[4], irch[4], s1[4], ds1[4], s2[4], ds2[4], s3[4], ds3[4], sphi[4], dsphi[4], sth[4], dsth[4];
         double f1[3], df1c[3], df1h[3];
+#ifndef CRCL_CBE_SHFL_GATHER
+        // scr: this bead's [lane][18] block; own values out, a warp-level fence, the neighbours' in -- in TWO phases: what the
+        // stretch and the out-of-plane term read now, the in-plane term's share (s1, s2, f1 and derivatives: 21 doubles)
+        // only after the out-of-plane term, behind a second fence, so that they are not live through it
+        const double2* nb[3];
+        {
+            double2* mine = reinterpret_cast<double2*>(scr + x * 18);
+            __syncwarp();   // the previous evaluation's reads of this block are complete
+            mine[0] = make_double2(co[0], co[1]);
+            mine[1] = make_double2(co[2], rcho);
+            mine[2] = make_double2(ircho, sw[4]);
+            mine[3] = make_double2(sw[5], sw[6]);
+            mine[4] = make_double2(sw[7], sw[8]);
+            mine[5] = make_double2(sw[9], sw[0]);
+            mine[6] = make_double2(sw[1], sw[2]);
+            mine[7] = make_double2(sw[3], f1o);
+            mine[8] = make_double2(df1co, df1ho);
+            __syncwarp();
+            c[0][0] = co[0], c[0][1] = co[1], c[0][2] = co[2];
+            rch[0] = rcho, irch[0] = ircho;
+            s3[0] = sw[4], ds3[0] = sw[5];
+            sphi[0] = sw[6], dsphi[0] = sw[7], sth[0] = sw[8], dsth[0] = sw[9];
+#pragma unroll
+            for (int t = 1; t < 4; t++) {
+                const double2* o = reinterpret_cast<const double2*>(scr + ((x + t) & 3) * 18);
+                nb[t - 1] = o;
+                const double2 v0 = o[0], v1 = o[1], v2 = o[2], v3 = o[3], v4 = o[4];
+                c[t][0] = v0.x, c[t][1] = v0.y, c[t][2] = v1.x;
+                rch[t] = v1.y, irch[t] = v2.x;
+                s3[t] = v2.y, ds3[t] = v3.x;
+                sphi[t] = v3.y, dsphi[t] = v4.x, sth[t] = v4.y;
+                dsth[t] = reinterpret_cast<const double*>(o)[10];
+            }
+        }
+        auto gather_inplane = [&]() {
+            __syncwarp();   // keeps the loads below from being scheduled above the out-of-plane term
+            s1[0] = sw[0], ds1[0] = sw[1], s2[0] = sw[2], ds2[0] = sw[3];
+            f1[0] = f1o, df1c[0] = df1co, df1h[0] = df1ho;
+#pragma unroll
+            for (int t = 1; t < 4; t++) {
+                const double2* o = nb[t - 1];
+                const double v5y = reinterpret_cast<const double*>(o)[11];
+                const double2 v6 = o[6];
+                const double v7x = reinterpret_cast<const double*>(o)[14];
+                s1[t] = v5y, ds1[t] = v6.x, s2[t] = v6.y, ds2[t] = v7x;
+                if (t < 3) {
+                    const double v7y = reinterpret_cast<const double*>(o)[15];
+                    const double2 v8 = o[8];
+                    f1[t] = v7y, df1c[t] = v8.x, df1h[t] = v8.y;
+                }
+            }
+        };
+#else
 #pragma unroll
         for (int t = 0; t < 4; t++) {
             const int src = x + t;
@@ -640,7 +704,9 @@ struct PesCBE4 {
                 df1h[t] = t ? shf(df1ho, src) : df1ho;
             }
         }
-        const double tau = acos(-1.0 / 3.0);
+        auto gather_inplane = [&]() {};
+#endif
+        const double tau = TAU_TET;
         const double ta = tau - K::TAU_PLANAR * PI, tb = tau - 2.0 * PI / 3.0;
         auto theta0 = [&](int i, int j, int k, int l) {
             return tau + ta * (sphi[i] * sphi[j] - 1.0) + tb * (sth[k] * sth[l] - 1.0);
@@ -664,14 +730,16 @@ struct PesCBE4 {
             const Leps ch = leps(K::D1CH, K::D3CH, ach, dr);
             const Leps bh = leps(K::D1HH, K::D3HH, K::AHH, rbho - K::R0HH);
             const double a = ch.vj, b = cb.vj, cc = bh.vj;
-            const double vj = -sqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5);
+            double vjs, ivjs;
+            sqrt_rsqrt((sqr(a - b) + sqr(b - cc) + sqr(cc - a)) * 0.5, vjs, ivjs);
+            const double vj = -vjs;
             en += ch.vq + cb.vq + bh.vq + vj;
-            const double h = 0.5 / vj;
+            const double h = -0.5 * ivjs;
             const double wa = (2.0 * a - b - cc) * h, wb = (2.0 * b - a - cc) * h, wc = (2.0 * cc - a - b) * h;
             const double dch = ch.dvq + wa * ch.dvj;
             Dbh[0] += bh.dvq + wc * bh.dvj;
             Dcb += cb.dvq + wb * cb.dvj;
-            const double tt = dch * (dr / ach) * dach;
+            const double tt = dch * CRCL_DIV(dr, ach) * dach;
             Dch[0] += dch + tt;
             Dch[1] += tt;
             Dch[2] += tt;
@@ -690,8 +758,7 @@ struct PesCBE4 {
                 b[d] = c[3][d] * rch[3] - hj;
             }
             cross(a, b, n);
-            const double nn = sqrt(dot(n, n));
-            const double inn = 1.0 / nn;
+            const double inn = CRCL_RSQRT(dot(n, n));
             double u[3] = {dot(n, c[1]) * inn, dot(n, c[2]) * inn, dot(n, c[3]) * inn};
             const int npos = (u[0] > 0.0) + (u[1] > 0.0) + (u[2] > 0.0);
             const double sg = (npos & 1) ? -1.0 : 1.0;
@@ -702,12 +769,12 @@ struct PesCBE4 {
                 const int m = t + 1;
                 const int ca = (t == 0) ? 2 : 1, cb2 = (t == 2) ? 2 : 3;
                 const double um = sg * u[t];
-                const double del = acos(um) - theta0(0, m, ca, cb2);
+                const double del = CRCL_ACOS(um) - theta0(0, m, ca, cb2);
                 const double d2 = del * del;
                 sum2 += d2;
                 sum4 += d2 * d2;
                 const double w = 2.0 * fd * del + 4.0 * hd * d2 * del;
-                const double wu = -w * rsqrt(1.0 - um * um);
+                const double wu = -w * CRCL_RSQRT(1.0 - um * um);
                 const double f = wu * irch[m];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
@@ -741,6 +808,7 @@ struct PesCBE4 {
             Dch[3] += fs * (1.0 - s3[0]) * pj * pk * ds3[3];
         }
         // ---- in-plane bending: pair local (0,1) on every lane, local (0,2) on lanes 0 and 1 ----
+        gather_inplane();
         {
             constexpr double f0 = K::FKINF + K::AK, f2 = K::FKINF;
 #pragma unroll
@@ -751,10 +819,10 @@ struct PesCBE4 {
                 const double ff = f1[0] * f1[j];
                 const double Kf = fk0 * ff;
                 const double cs = dot(c[0], c[j]);
-                const double del = acos(cs) - theta0(0, j, k, l);
+                const double del = CRCL_ACOS(cs) - theta0(0, j, k, l);
                 en += 0.5 * Kf * del * del;
                 const double w = Kf * del;
-                const double wc = -w * rsqrt(1.0 - cs * cs);
+                const double wc = -w * CRCL_RSQRT(1.0 - cs * cs);
                 const double fi = wc * irch[0], fj = wc * irch[j];
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
@@ -778,12 +846,13 @@ struct PesCBE4 {
             double tno[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) tno[d] = q(18 + d) * 0.52918 - q(15 + d) * 0.52918;
-            const double rno = sqrt(dot(tno, tno));
+            double rno, irno;
+            sqrt_rsqrt(dot(tno, tno), rno, irno);
             // O-H(O) Morse bond (stretch_ch4oh :616-621, :652-659, :769-774): lane 0 only
             const double m0 = (x == 0) ? 1.0 : 0.0;
-            const double ex = exp(-K::AHH * (rno - K::R0HH)), om = 1.0 - ex;
-            en += m0 * K::D1HH * (om * om);
-            const double de = m0 * 2.0 * K::AHH * K::D1HH * om * ex / rno;
+            const double ex = CRCL_EXP(-K::MORSE_A * (rno - K::MORSE_R0)), om = 1.0 - ex;
+            en += m0 * K::MORSE_D * (om * om);
+            const double de = m0 * 2.0 * K::MORSE_A * K::MORSE_D * om * ex * irno;
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 gBx[d] -= de * tno[d];
@@ -793,9 +862,9 @@ struct PesCBE4 {
             double tbv[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) tbv[d] = -ubo[d] * rbho;
-            double cs = -dot(tno, tbv) / (rno * rbho);
+            double cs = -dot(tno, tbv) * CRCL_RCP(rno * rbho);
             cs = fmin(1.0, fmax(-1.0, cs));
-            const double dang = acos(cs) - K::ANH2OEQ;
+            const double dang = CRCL_ACOS(cs) - K::ANH2OEQ;
             const double arga = K::ALPH2O * (rbho - K::R0HH);
             double omt, ms2;
             one_minus_tanh(arga, omt, ms2);
@@ -805,9 +874,9 @@ struct PesCBE4 {
             const double dstda = fk * dang;
             double pv[3], v1[3], v2[3];
             cross(tno, tbv, pv);
-            double rp = sqrt(dot(pv, pv));
+            double rp = CRCL_SQRT(fmax(dot(pv, pv), 1.0e-300));
             if (rp < 1.0e-6) rp = 1.0e-6;
-            const double terma = dstda / (rbho * rbho * rp), termc = dstda / (rno * rno * rp);
+            const double terma = dstda * CRCL_RCP(rbho * rbho * rp), termc = dstda * CRCL_RCP(rno * rno * rp);
             cross(tbv, pv, v1);
             cross(tno, pv, v2);
 #pragma unroll

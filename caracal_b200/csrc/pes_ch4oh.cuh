@@ -37,6 +37,8 @@ struct K7 {
     // H-O-H bends: fkh2oeq scaled by fact2, anh2oeq by fact3 (:2001-2002)
     static constexpr double FKH2OEQ = 0.7300000 * 6.022045, ALPH2O = 1.1080000;
     static constexpr double ANH2OEQ = 104.7132000 * (2.0 * 3.141592653589793 / 360.0);
+    // Morse bond of the seventh atom: O-H(O) on the H-H... constants r0hh, ahh, d1hh (stretch_ch4oh :616-621)
+    static constexpr double MORSE_R0 = R0HH, MORSE_A = AHH, MORSE_D = D1HH;
     static constexpr bool SPHI_ANY_R = false;
     static constexpr double TAU_PLANAR = 0.5;
 };
@@ -56,6 +58,7 @@ struct K7 : ch4oh::K7 {
     static constexpr double AHH = 2.18200, R0CB = 1.90035, ACB = 0.67621;
     static constexpr double D1CH = 86.50000 * 0.041840, D3CH = 41.50000 * 0.041840;
     static constexpr double D1HH = 120.94800 * 0.041840, D3HH = 31.86417 * 0.041840;
+    static constexpr double MORSE_R0 = R0HH, MORSE_A = AHH, MORSE_D = D1HH;
     static constexpr double D1CB = 41.50283 * 0.041840;
     static constexpr double D3CB = (10.50589 * 0.041840 - A3CB) + A3CB;
     static constexpr double A3S = 0.2019100, B3S = -0.6068400;
@@ -69,6 +72,30 @@ struct K7 : ch4oh::K7 {
 }  // namespace geh4oh
 
 using PesGeH4OH = PesCBE1<geh4oh::K7>;
+
+// CH4 + CN -> CH3 + HCN (Espinosa-Garcia, Rangel, Suleimanov, PCCP 19, 19341 (2017)), /root/reference/src/egrad_ch4cn.f:
+// egrad_ch4oh.f line for line with the abstracting atom the carbon of CN and the seventh atom its nitrogen -- its own
+// BLOCK DATA (:2074-2114), the H-C-N "bend" on 180 degrees, and the C-N Morse bond on literal constants (:625-627,
+// :659-660: r0 = 1.172 A, a = 0.80 / A, D = 80.0 in the routine's 1e5 J/mol, NOT scaled by PREPOT's fact1).
+// Atom order H, C, H, H, H, C(N), N.
+namespace ch4cn {
+struct K7 : ch4oh::K7 {
+    static constexpr int ID = CRCL_PES_CH4CN;
+    static constexpr double A1CH = 1.75000, B1CH = 0.12000, C1CH = 5.00000;
+    static constexpr double R0HH = 1.06497, AHH = 1.70000, R0CB = 1.72592, ACB = 3.08688;
+    static constexpr double D3CH = 14.65328 * 0.041840;
+    static constexpr double D1HH = 132.17000 * 0.041840, D3HH = 44.63017 * 0.041840;
+    static constexpr double D3CB = (88.69509 * 0.041840 - A3CB) + A3CB;
+    static constexpr double AA1 = 0.273746;
+    static constexpr double FKH2OEQ = 0.2600000 * 6.022045, ALPH2O = 3.1080000;
+    static constexpr double ANH2OEQ = 180.0000000 * (2.0 * 3.141592653589793 / 360.0);
+    static constexpr double MORSE_R0 = 1.172, MORSE_A = 0.80, MORSE_D = 80.0;
+};
+}  // namespace ch4cn
+using PesCH4CN = PesCBE1<ch4cn::K7>;
+#ifdef __CUDACC__
+using PesCH4CN4 = PesCBE4<ch4cn::K7>;
+#endif
 #ifdef __CUDACC__
 // four lanes per bead in the trajectory kernels (pes_ch4h.cuh, PesCBE4): lane x owns methane / germane hydrogen x
 using PesCH4OH4 = PesCBE4<ch4oh::K7>;

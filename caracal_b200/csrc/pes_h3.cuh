@@ -68,7 +68,7 @@ CRCL_HD constexpr CbSet CBD_()
 }
 
 // Schwenke H2 singlet curve (VH2OPT95, egrad_h3.f:322-397): E and dE/dR.
-CRCL_HD __forceinline__ void singlet(double R, double& E, double& dE)
+CRCL_HD __forceinline__ void singlet(double R, double rinv, double& E, double& dE)
 {
     constexpr double A0 = FL(0.03537359271649620), A1 = FL(2.013977588700072),
                      A2 = FL(-2.827452449964767), A3 = FL(2.713257715593500),
@@ -82,7 +82,6 @@ CRCL_HD __forceinline__ void singlet(double R, double& E, double& dE)
     constexpr double R0 = 3.5284882, DD = 0.160979391, C6 = 6.499027, C8 = 124.3991,
                      C10 = 3285.828;
     constexpr double R02 = R0 * R0, R04 = R02 * R02, R06 = R04 * R02;
-    const double rinv = 1.0 / R;
     // alpha(R) = A0/R + sum_{n=0}^{15} A_{n+1} R^n  and its derivative, Horner
     double al = A16, dal = 15.0 * A16;
     al = fma(al, R, A15);  dal = fma(dal, R, 14.0 * A15);
@@ -102,10 +101,10 @@ CRCL_HD __forceinline__ void singlet(double R, double& E, double& dE)
     al = fma(al, R, A1);
     al = fma(A0, rinv, al);
     dal = fma(-A0 * rinv, rinv, dal);
-    const double ex = exp(al);
+    const double ex = CRCL_EXP(al);
     const double em1 = ex - 1.0;
     const double R2 = R * R, R4 = R2 * R2, R6 = R4 * R2;
-    const double i2 = 1.0 / (R2 + R02), i4 = 1.0 / (R4 + R04), i6 = 1.0 / (R6 + R06);
+    const double i2 = CRCL_RCP(R2 + R02), i4 = CRCL_RCP(R4 + R04), i6 = CRCL_RCP(R6 + R06);
     const double i25 = i2 * i2 * i2 * i2 * i2;
     E = DD * em1 * em1 - DD - C6 * i6 - C8 * i4 * i4 - C10 * i25;
     dE = 2.0 * DD * em1 * ex * dal +
@@ -113,31 +112,27 @@ CRCL_HD __forceinline__ void singlet(double R, double& E, double& dE)
 }
 
 // H2 triplet curve (TRIPLET95, egrad_h3.f:251-320) given the singlet values.
-CRCL_HD __forceinline__ void triplet(double R, double E1, double dE1, double& E3, double& dE3)
+CRCL_HD __forceinline__ void triplet(double R, double rinv, double E1, double dE1, double& E3, double& dE3)
 {
     constexpr double RL = 0.95, RR = 1.15;
     constexpr double A1 = FL(-0.0298546962), A2 = FL(-23.9604445036), A3 = FL(-42.5185569474),
                      A4 = FL(2.0382390988), A5 = FL(-11.5214861455), A6 = FL(1.5309487826),
                      C1 = FL(-0.4106358351531854), C2 = FL(-0.0770355790707090),
                      C3 = FL(0.4303193846943223);
-    if (R >= RR) {
-        const double ex = exp(-A4 * R);
-        const double ra6 = pow(R, -A6);
-        const double RSQ = R * R;
-        E3 = A1 * (A2 + R + A3 * RSQ + A5 * ra6) * ex;
-        dE3 = A1 * ex *
-              (1.0 - A2 * A4 + (2.0 * A3 - A4) * R - A3 * A4 * RSQ - A5 * A6 * (ra6 / R) -
-               A4 * A5 * ra6);
-    } else {
-        const double DR = R - RL;
-        if (R <= RL) {
-            E3 = E1 + C2 * DR + C3;
-            dE3 = dE1 + C2;
-        } else {
-            E3 = E1 + C1 * DR * DR * DR + C2 * DR + C3;
-            dE3 = dE1 + 3.0 * C1 * DR * DR + C2;
-        }
-    }
+    // the three branches of the reference as selects: the outer form costs one exp and one log + exp now, and a
+    // warp whose images straddle R = 1.15 a0 no longer executes both sides one after the other
+    const double ex = CRCL_EXP(-A4 * R);
+    const double ra6 = CRCL_POW(R, -A6);
+    const double RSQ = R * R;
+    const double Eo = A1 * (A2 + R + A3 * RSQ + A5 * ra6) * ex;
+    const double dEo = A1 * ex *
+                       (1.0 - A2 * A4 + (2.0 * A3 - A4) * R - A3 * A4 * RSQ - A5 * A6 * (ra6 * rinv) - A4 * A5 * ra6);
+    const double DR = R - RL;
+    const double cub = (R <= RL) ? 0.0 : C1;
+    const double Ei = E1 + cub * DR * DR * DR + C2 * DR + C3;
+    const double dEi = dE1 + 3.0 * cub * DR * DR + C2;
+    E3 = (R >= RR) ? Eo : Ei;
+    dE3 = (R >= RR) ? dEo : dEi;
 }
 
 // quantities shared by the VBEND / CBEND blocks
@@ -329,7 +324,7 @@ CRCL_HD __noinline__ inline void compact_terms(const double R[3], const Bend& c,
 
 // pote (egrad_h3.f:79-249): potential and dV/dR on the three distances
 // R = (r12, r13, r23).  warn gets CHGEOM's two conditions as bits (the reference prints).
-CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], int& warn)
+CRCL_HD __forceinline__ void pote(const double R[3], const double iR[3], double& V, double dV[3], int& warn)
 {
     // CHGEOM (egrad_h3.f:1432-1476)
     {
@@ -345,17 +340,18 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         double E1, dE1, E3, dE3;
-        singlet(R[i], E1, dE1);
-        triplet(R[i], E1, dE1, E3, dE3);
+        singlet(R[i], iR[i], E1, dE1);
+        triplet(R[i], iR[i], E1, dE1, E3, dE3);
         Q += 0.5 * (E1 + E3);
         J[i] = 0.5 * (E1 - E3);
         dQ[i] = 0.5 * (dE1 + dE3);
         dJ[i] = 0.5 * (dE1 - dE3);
     }
     const double d10 = J[1] - J[0], d21 = J[2] - J[1], d20 = J[2] - J[0];
-    const double rootjt = sqrt(0.5 * (d10 * d10 + d21 * d21 + d20 * d20) + 1.0e-12);
+    double rootjt, irootjt;
+    sqrt_rsqrt(0.5 * (d10 * d10 + d21 * d21 + d20 * d20) + 1.0e-12, rootjt, irootjt);
     V = Q - rootjt;
-    const double hr = 0.5 / rootjt;
+    const double hr = 0.5 * irootjt;
     dV[0] = dQ[0] - hr * (2.0 * J[0] - J[1] - J[2]) * dJ[0];
     dV[1] = dQ[1] - hr * (2.0 * J[1] - J[2] - J[0]) * dJ[1];
     dV[2] = dQ[2] - hr * (2.0 * J[2] - J[0] - J[1]) * dJ[2];
@@ -372,13 +368,14 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
                          AA5 = FL(-.1293180255E-06), AA6 = FL(0.5237179303E+00),
                          AA7 = FL(-.1112326215E-02);
         const double A2 = A * A, A3 = A2 * A, A4 = A3 * A, A5 = A4 * A;
-        const double EXP1 = exp(-AA1 * c.RSQ * c.R);
-        const double EXP6 = exp(-AA6 * c.R);
+        const double EXP1 = CRCL_EXP(-AA1 * c.RSQ * c.R);
+        const double EXP6 = CRCL_EXP(-AA6 * c.R);
+        const double iSR = CRCL_RCP(c.R);
         const double S = AA2 * A2 + AA3 * A3 + AA4 * A4 + AA5 * A5;
-        const double e6r = AA7 * EXP6 / c.R;
+        const double e6r = AA7 * EXP6 * iSR;
         V += S * EXP1 + A2 * e6r;
         const double dSdA = 2.0 * AA2 * A + 3.0 * AA3 * A2 + 4.0 * AA4 * A3 + 5.0 * AA5 * A4;
-        const double com = -3.0 * AA1 * c.RSQ * S * EXP1 - A2 * e6r / c.R - AA6 * A2 * e6r;
+        const double com = -3.0 * AA1 * c.RSQ * S * EXP1 - A2 * e6r * iSR - AA6 * A2 * e6r;
         const double cA = dSdA * EXP1 + 2.0 * A * e6r;
 #pragma unroll
         for (int i = 0; i < 3; i++) dV[i] += com + cA * DA[i];
@@ -388,7 +385,8 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
     const double R1 = R[0], R2 = R[1], R3 = R[2];
     const double s1 = R1 * R1, s2 = R2 * R2, s3 = R3 * R3;
     const double T1 = s1 - s2 - s3, T2 = s2 - s3 - s1, T3 = s3 - s1 - s2;
-    const double C1 = T1 / (-2.0 * R2 * R3), C2 = T2 / (-2.0 * R3 * R1), C3 = T3 / (-2.0 * R1 * R2);
+    const double i1 = iR[0], i2 = iR[1], i3 = iR[2];   // the reference divides; here one reciprocal per distance serves all quotients
+    const double C1 = -0.5 * T1 * (i2 * i3), C2 = -0.5 * T2 * (i3 * i1), C3 = -0.5 * T3 * (i1 * i2);
     const double SUM = C1 + C2 + C3;
     const double B1A = 1.0 - SUM;
     const double SUMB = (4.0 * C1 * C1 * C1 - 3.0 * C1) + (4.0 * C2 * C2 * C2 - 3.0 * C2) +
@@ -396,9 +394,9 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
     const double B1B = 1.0 - (Z58 * SUMB + Z38 * SUM);
     // dC_a/dR_b
     const double DC[3][3] = {
-        {-R1 / (R2 * R3), (T1 / s2 + 2.0) / (2.0 * R3), (T1 / s3 + 2.0) / (2.0 * R2)},
-        {(T2 / s1 + 2.0) / (2.0 * R3), -R2 / (R1 * R3), (T2 / s3 + 2.0) / (2.0 * R1)},
-        {(T3 / s1 + 2.0) / (2.0 * R2), (T3 / s2 + 2.0) / (2.0 * R1), -R3 / (R1 * R2)}};
+        {-R1 * (i2 * i3), (T1 * (i2 * i2) + 2.0) * (0.5 * i3), (T1 * (i3 * i3) + 2.0) * (0.5 * i2)},
+        {(T2 * (i1 * i1) + 2.0) * (0.5 * i3), -R2 * (i1 * i3), (T2 * (i3 * i3) + 2.0) * (0.5 * i1)},
+        {(T3 * (i1 * i1) + 2.0) * (0.5 * i2), (T3 * (i2 * i2) + 2.0) * (0.5 * i1), -R3 * (i1 * i2)}};
     const double D1 = 12.0 * C1 * C1 - 3.0, D2 = 12.0 * C2 * C2 - 3.0, D3 = 12.0 * C3 * C3 - 3.0;
     double DB1A[3], DB1B[3];
 #pragma unroll
@@ -407,22 +405,23 @@ CRCL_HD __forceinline__ void pote(const double R[3], double& V, double dV[3], in
         DB1A[i] = -sd;
         DB1B[i] = -Z58 * (D1 * DC[0][i] + D2 * DC[1][i] + D3 * DC[2][i]) - Z38 * sd;
     }
-    c.B2 = 1.0 / R1 + 1.0 / R2 + 1.0 / R3;
+    c.B2 = i1 + i2 + i3;
     c.B3 = (R2 - R1) * (R2 - R1) + (R3 - R2) * (R3 - R2) + (R1 - R3) * (R1 - R3);
-    c.B3B = sqrt(c.B3 + 1.0e-12);
-    c.DB2[0] = -1.0 / s1;
-    c.DB2[1] = -1.0 / s2;
-    c.DB2[2] = -1.0 / s3;
+    double iB3B;
+    sqrt_rsqrt(c.B3 + 1.0e-12, c.B3B, iB3B);
+    c.DB2[0] = -(i1 * i1);
+    c.DB2[1] = -(i2 * i2);
+    c.DB2[2] = -(i3 * i3);
     c.DB3[0] = 4.0 * R1 - 2.0 * R2 - 2.0 * R3;
     c.DB3[1] = 4.0 * R2 - 2.0 * R3 - 2.0 * R1;
     c.DB3[2] = 4.0 * R3 - 2.0 * R1 - 2.0 * R2;
-    const double hb = 0.5 / c.B3B;
+    const double hb = 0.5 * iB3B;
     c.DB3B[0] = hb * c.DB3[0];
     c.DB3B[1] = hb * c.DB3[1];
     c.DB3B[2] = hb * c.DB3[2];
-    c.EXP1 = exp(-BETA1 * c.R);
-    c.EXP2 = exp(-BETA2 * c.RSQ);
-    const double EXP7 = exp(-BETA3 * c.R);
+    c.EXP1 = CRCL_EXP(-BETA1 * c.R);
+    c.EXP2 = CRCL_EXP(-BETA2 * c.RSQ);
+    const double EXP7 = CRCL_EXP(-BETA3 * c.R);
     c.DEXP1 = -BETA1 * c.EXP1;
     c.DEXP2 = -2.0 * BETA2 * c.R * c.EXP2;
     const double DEXP7 = -BETA3 * EXP7;
@@ -464,13 +463,13 @@ struct PesH3 {
         const double ab[3] = {q[3] - q[0], q[4] - q[1], q[5] - q[2]};
         const double ac[3] = {q[0] - q[6], q[1] - q[7], q[2] - q[8]};
         const double bc[3] = {q[6] - q[3], q[7] - q[4], q[8] - q[5]};
-        double R[3], dV[3];
-        R[0] = sqrt(ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2]);
-        R[1] = sqrt(ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2]);
-        R[2] = sqrt(bc[0] * bc[0] + bc[1] * bc[1] + bc[2] * bc[2]);
+        double R[3], iR[3], dV[3];
+        sqrt_rsqrt(ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2], R[0], iR[0]);
+        sqrt_rsqrt(ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2], R[1], iR[1]);
+        sqrt_rsqrt(bc[0] * bc[0] + bc[1] * bc[1] + bc[2] * bc[2], R[2], iR[2]);
         int warn;
-        h3::pote(R, V, dV, warn);
-        const double f0 = dV[0] / R[0], f1 = dV[1] / R[1], f2 = dV[2] / R[2];
+        h3::pote(R, iR, V, dV, warn);
+        const double f0 = dV[0] * iR[0], f1 = dV[1] * iR[1], f2 = dV[2] * iR[2];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             g[d] = f1 * ac[d] - f0 * ab[d];

@@ -41,7 +41,7 @@ CRCL_HD __forceinline__ void v2(double r, double& v, double& dv)
     double bk = 1.0, sv = 0.0, sg = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const double ex = a[k] * exp(-alpha * bk * r2);
+        const double ex = a[k] * CRCL_EXP(-alpha * bk * r2);
         sv += ex;
         sg -= 2.0 * alpha * bk * r * ex;
         bk *= beta;
@@ -57,10 +57,10 @@ CRCL_HD __forceinline__ void disp(double R, double& e, double& de)
     const double r2r4 = (double)2.59361680f;   // r2r4(8): REAL*4 literal in the source
     const double c8 = 3.0 * c6 * r2r4 * r2r4;
     const double t = a1 * sqrt(c8 / c6) + a2, t2 = t * t, t6 = t2 * t2 * t2, t8 = t6 * t2;
-    const double r = R / autoang, q2 = r * r, q4 = q2 * q2, q6 = q4 * q2, q8 = q4 * q4;
-    const double i6 = 1.0 / (q6 + t6), i8 = 1.0 / (q8 + t8);
+    const double r = CRCL_DIV(R, autoang), q2 = r * r, q4 = q2 * q2, q6 = q4 * q2, q8 = q4 * q4;
+    const double i6 = CRCL_RCP(q6 + t6), i8 = CRCL_RCP(q8 + t8);
     e = (-c6 * i6 - s8 * c8 * i8) * autokcal;
-    de = (6.0 * c6 * q4 * r * i6 * i6 + 8.0 * s8 * c8 * q6 * r * i8 * i8) * autokcal / autoang;
+    de = (6.0 * c6 * q4 * r * i6 * i6 + 8.0 * s8 * c8 * q6 * r * i8 * i8) * CRCL_DIV(autokcal, autoang);
 }
 
 #define O3P0(k, x, y) const J p##k = mul(p##x, p##y);
@@ -82,8 +82,8 @@ CRCL_HD __forceinline__ void pes(const double (&R)[3], double& V, double (&dV)[3
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const double u = R[i] - RB;
-        m[i] = exp(-(R[i] - RA) / A - (u * u) / AB);
-        dm[i] = (-2.0 * u / AB - 1.0 / A) * m[i];
+        m[i] = CRCL_EXP(-CRCL_DIV(R[i] - RA, A) - CRCL_DIV(u * u, AB));
+        dm[i] = (CRCL_DIV(-2.0 * u, AB) - 1.0 / A) * m[i];
     }
     // monomials (EvMono): rm1 = ms(3), rm2 = ms(2), rm3 = ms(1); pair and triple products
     const J q1 = {m[2], 0.0, 0.0, dm[2]}, q2 = {m[1], 0.0, dm[1], 0.0}, q3 = {m[0], dm[0], 0.0, 0.0};
@@ -256,13 +256,14 @@ struct PesO3 {
             v13[d] = (q[d] - q[6 + d]) * Cconv;
             v23[d] = (q[3 + d] - q[6 + d]) * Cconv;
         }
-        const double R[3] = {sqrt(v12[0] * v12[0] + v12[1] * v12[1] + v12[2] * v12[2]),
-                             sqrt(v13[0] * v13[0] + v13[1] * v13[1] + v13[2] * v13[2]),
-                             sqrt(v23[0] * v23[0] + v23[1] * v23[1] + v23[2] * v23[2])};
+        double R[3], iR[3];
+        sqrt_rsqrt(v12[0] * v12[0] + v12[1] * v12[1] + v12[2] * v12[2], R[0], iR[0]);
+        sqrt_rsqrt(v13[0] * v13[0] + v13[1] * v13[1] + v13[2] * v13[2], R[1], iR[1]);
+        sqrt_rsqrt(v23[0] * v23[0] + v23[1] * v23[1] + v23[2] * v23[2], R[2], iR[2]);
         double vk, dV[3];
         o3::pes(R, vk, dV);
         V = vk * Econv + Eref;
-        const double f1 = dV[0] / R[0] * Gconv, f2 = dV[1] / R[1] * Gconv, f3 = dV[2] / R[2] * Gconv;
+        const double f1 = dV[0] * iR[0] * Gconv, f2 = dV[1] * iR[1] * Gconv, f3 = dV[2] * iR[2] * Gconv;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             g[d] = f1 * v12[d] + f2 * v13[d];

@@ -27,7 +27,7 @@ constexpr double ACON0 = 0.10, ACON1 = 0.009;
 
 CRCL_HD __forceinline__ void morse(double D, double B, double T, double r, double& V, double& dV)
 {
-    const double x = exp(-B * (r - T));
+    const double x = CRCL_EXP(-B * (r - T));
     const double u = 1.0 - x;
     V += D * u * u;
     dV += 2.0 * B * D * u * x;
@@ -52,7 +52,7 @@ CRCL_HD __forceinline__ void vh2o(double roha, double rohb, double rhh, double& 
             double omt, ms2;
             one_minus_tanh(X, omt, ms2);
             Q[i] = omt;
-            L[i] = 0.5 * GAM[i] * ms2 / omt;
+            L[i] = -0.5 * GAM[i] * (2.0 - omt);   // DQ/Q = -sech^2 / (1 - tanh) = -(1 + tanh)
         } else {  // reference sets Q=0 and leaves DEDR(I) stale; E is then exactly 0
             Q[i] = 0.0;
             L[i] = 0.0;
@@ -66,9 +66,10 @@ CRCL_HD __forceinline__ void vh2o(double roha, double rohb, double rhh, double& 
     const double DP3 = CON1 + CON3 * S3 + CON5 * S2 + CON6 * S1;
     V += E;
     // DEDR(1:3) before the swap is indexed like S: (r_OHa, r_HH, r_OHb)
-    const double p0 = (Q[0] == 0.0) ? D[0] : E * (L[0] + DP1 / P);
-    const double p1 = (Q[1] == 0.0) ? D[1] : E * (L[1] + DP2 / P);
-    const double p2 = (Q[2] == 0.0) ? D[2] : E * (L[2] + DP3 / P);
+    const double iP = CRCL_RCP(P);
+    const double p0 = (Q[0] == 0.0) ? D[0] : E * (L[0] + DP1 * iP);
+    const double p1 = (Q[1] == 0.0) ? D[1] : E * (L[1] + DP2 * iP);
+    const double p2 = (Q[2] == 0.0) ? D[2] : E * (L[2] + DP3 * iP);
     D[0] = p0;
     D[1] = p2;   // DEDR(2) <-> DEDR(3)
     D[2] = p1;
@@ -98,19 +99,20 @@ CRCL_HD __forceinline__ void pot(const double R[6], double& V, double dV[6])
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double DO4Z = de[i] / 4.0 / ZPO;
-            X[i] = exp(-be[i] * (r[i] - re[i]));
+            X[i] = CRCL_EXP(-be[i] * (r[i] - re[i]));
             E += DO4Z * (ZP3 * X[i] - TOP3Z) * X[i];
             EX[i] = DO4Z * (OP3Z * X[i] - TZP3) * X[i];
             S += EX[i];
         }
-        const double RAD = sqrt(sqr(EX[0] - EX[1]) + sqr(EX[1] - EX[2]) + sqr(EX[2] - EX[0]));
+        double RAD, iRAD;
+        sqrt_rsqrt(sqr(EX[0] - EX[1]) + sqr(EX[1] - EX[2]) + sqr(EX[2] - EX[0]), RAD, iRAD);
         constexpr double RS2 = 0.70710678118654752440;  // 1/sqrt(2)
         V += E - RAD * RS2;
         const int idx[3] = {1, 2, 5};
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             const double B = be[i] * (de[i] / 4.0 / ZPO) * 2.0;
-            DEDR[i] = B * X[i] * ((3.0 * EX[i] - S) * RS2 * (OP3Z * X[i] - ZP3) / RAD - ZP3 * X[i] + OP3Z);
+            DEDR[i] = B * X[i] * ((3.0 * EX[i] - S) * RS2 * (OP3Z * X[i] - ZP3) * iRAD - ZP3 * X[i] + OP3Z);
             dV[idx[i]] += DEDR[i];
         }
     }
@@ -119,9 +121,9 @@ CRCL_HD __forceinline__ void pot(const double R[6], double& V, double dV[6])
     // four-body term on (OH2, OH3, H1H2, H1H3)  (V4POT_oh3; A=ALP, C=CLAM, COF=ACON)
     {
         const double r[4] = {R[1], R[2], R[3], R[4]};
-        const double T1 = ACON0 * exp(-CLAM0 * (sqr(r[0] - ALP0) + sqr(r[1] - ALP0)) -
+        const double T1 = ACON0 * CRCL_EXP(-CLAM0 * (sqr(r[0] - ALP0) + sqr(r[1] - ALP0)) -
                                         CLAM2 * (sqr(r[2] - ALP2) + sqr(r[3] - ALP2)));
-        const double T2 = ACON1 * exp(-CLAM1 * (sqr(r[0] - ALP1) + sqr(r[1] - ALP1)) -
+        const double T2 = ACON1 * CRCL_EXP(-CLAM1 * (sqr(r[0] - ALP1) + sqr(r[1] - ALP1)) -
                                         CLAM3 * (sqr(r[2] - ALP3) + sqr(r[3] - ALP3)));
         V += T1 + T2;
         dV[1] += -2.0 * (T1 * CLAM0 * (r[0] - ALP0) + T2 * CLAM1 * (r[0] - ALP1));
@@ -154,19 +156,19 @@ struct PesOH3 {
     {
         constexpr int PA[6] = {0, 0, 0, 1, 1, 2};
         constexpr int PB[6] = {1, 2, 3, 2, 3, 3};
-        double vec[6][3], R[6], dV[6];
+        double vec[6][3], R[6], iR[6], dV[6];
 #pragma unroll
         for (int m = 0; m < 6; m++) {
 #pragma unroll
             for (int d = 0; d < 3; d++) vec[m][d] = q[3 * PB[m] + d] - q[3 * PA[m] + d];
-            R[m] = sqrt(vec[m][0] * vec[m][0] + vec[m][1] * vec[m][1] + vec[m][2] * vec[m][2]);
+            sqrt_rsqrt(vec[m][0] * vec[m][0] + vec[m][1] * vec[m][1] + vec[m][2] * vec[m][2], R[m], iR[m]);
         }
         oh3::pot(R, V, dV);
 #pragma unroll
         for (int d = 0; d < 12; d++) g[d] = 0.0;
 #pragma unroll
         for (int m = 0; m < 6; m++) {
-            const double f = dV[m] / R[m];
+            const double f = dV[m] * iR[m];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 g[3 * PB[m] + d] += f * vec[m][d];

@@ -15,7 +15,7 @@ typedef cudaError_t (*traj_launch_fn)(int nbeads, const TrajArgs& A, int bias_mo
 template <class PES, int KIND, int NB>
 static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, cudaStream_t s)
 {
-    using L = SmemLayout<PES::NATOMS, NB, PES::LANES>;
+    using L = SmemLayout<PES::NATOMS, NB, PES::LANES, coop_scratch<PES>::value>;
     constexpr int gpb = Group<NB, PES::LANES>::GPB, tpb = Group<NB, PES::LANES>::TPB;
     const int grid = (A.ntraj + gpb - 1) / gpb;
     const size_t smem = L::bytes();
@@ -83,5 +83,8 @@ CRCL_DECLARE_TRAJ(launch_ch4oh_recross);
 CRCL_DECLARE_TRAJ(launch_geh4oh_verlet);
 CRCL_DECLARE_TRAJ(launch_geh4oh_mdinit);
 CRCL_DECLARE_TRAJ(launch_geh4oh_recross);
+CRCL_DECLARE_TRAJ(launch_ch4cn_verlet);
+CRCL_DECLARE_TRAJ(launch_ch4cn_mdinit);
+CRCL_DECLARE_TRAJ(launch_ch4cn_recross);
 
 }  // namespace crcl

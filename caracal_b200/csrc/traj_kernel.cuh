@@ -196,8 +196,18 @@ struct Group {
     }
 };
 
-// shared-memory footprint (doubles) of one trajectory and of the block-wide part
-template <int NAT, int NB, int LANES>
+// doubles of lane-exchange scratch per thread a lane-split surface asks for (PES::COOP_SCRATCH), 0 if it has none
+template <class P, class = void>
+struct coop_scratch {
+    static constexpr int value = 0;
+};
+template <class P>
+struct coop_scratch<P, decltype((void)P::COOP_SCRATCH)> {
+    static constexpr int value = P::COOP_SCRATCH;
+};
+
+// shared-memory footprint (doubles) of one trajectory and of the block-wide part; SCR: coop_scratch of the surface
+template <int NAT, int NB, int LANES, int SCR = 0>
 struct SmemLayout {
     static constexpr int NC = 3 * NAT;
     // bead stride of the {p,q}[c][b] staging in double2 units: +1 when several lanes of a bead
@@ -207,12 +217,16 @@ struct SmemLayout {
     static constexpr int NH = NB / 2 + 1;
     static constexpr int SYM_STAGE = (NB > 1) ? 2 * NC * NH : 0;
     static constexpr int XI_SCR = (3 * NC + 2) & ~1;        // calc_xi_coop scratch (ds0, ds1, v, xi), even for double2 alignment
-    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE + XI_SCR;  // {p,q}[c][b], cen, dxi, add, ham, sym, xi scratch
+    static constexpr int COOP = SCR * NB * LANES;           // lane-exchange scratch of the surface, [bead][lane][SCR]
+    static constexpr int PER_GROUP = 2 * NC * NBP + 4 * NC + SYM_STAGE + XI_SCR + COOP;  // {p,q}[c][b], cen, dxi, add, ham, sym, xi scratch, lane exchange
     // free-RP kernels: for NB <= 32 the three N x N tables H[b][a] (symmetrisation folded in, see
     // load_fker), otherwise the three circulant kernels f[N]
     static constexpr bool HTAB = (NB > 1 && NB <= 32);
     static constexpr int FKER = HTAB ? 3 * NB * NB : 3 * NB;
-    static constexpr int BLOCK = (FKER + 32 * Group<NB, LANES>::RED_N + 1) & ~1;   // + reduction scratch: RED_N values for each of up to 32 warps (even: double2 alignment)
+    // after the tables and the reduction scratch (RED_N values for each of up to 32 warps): {mass, 1/mass}[lane][NOWN] (double2), see Traj::mt
+    static constexpr int MT_OFF = (FKER + 32 * Group<NB, LANES>::RED_N + 1) & ~1;
+    static constexpr int MT_MAX = 2 * 3 * XI_MAXAT + 16;         // >= 2 LANES NOWN for every surface (static_assert in load_fker)
+    static constexpr int BLOCK = MT_OFF + MT_MAX;   // even: double2 alignment of what follows
     static constexpr size_t bytes()
     {
         return sizeof(double) * (BLOCK + Group<NB, LANES>::GPB * PER_GROUP);
@@ -233,8 +247,8 @@ struct Traj {
     const TrajArgs& A;
     const Grp& G;
     double g[NO];   // forces of the owned components
-    double ms[NO];  // mass of the owned components' atoms
-    double ims[NO]; // and its reciprocal
+    const double2* mt;  // shared {mass, 1/mass} of the owned components' atoms, [lane][NO] (load_fker): re-read where it is
+                        // needed instead of 4 NO registers that would stay live across the surface
     int oc[NO];     // owned component numbers (-1: none)
     int ob[NO];     // their row offset in pq (component 0's row for unowned slots)
     unsigned mv;    // bit k: owned component k exists and its atom is movable
@@ -245,6 +259,7 @@ struct Traj {
     double* ham;    // shared hams force (umbrella.f90:144-174) [NC]
     double2* sq;    // shared bead-symmetrised sums {p,q}[c][b], b = 0..N/2 (free_rp, reference transform)
     double* xis;    // shared scratch of calc_xi_coop [3 NC]
+    double* coop;   // shared lane-exchange scratch of this thread's bead (surfaces with COOP_SCRATCH), else unused
     bool want_epot; // false: forces() skips the all-reduce of the bead energies (recrossing children)
     const double* fk;
     double xi_ideal, k_force, xi_real, epot;
@@ -254,8 +269,9 @@ struct Traj {
 
     __device__ __forceinline__ Traj(const TrajArgs& a, const Grp& grp, double* smem) : A(a), G(grp)
     {
-        using Lay = SmemLayout<NAT, NB, L>;
+        using Lay = SmemLayout<NAT, NB, L, coop_scratch<PES>::value>;
         fk = smem;
+        mt = reinterpret_cast<const double2*>(smem + Lay::MT_OFF) + grp.lane * NO;
         double* base = smem + Lay::BLOCK + grp.gib * Lay::PER_GROUP;
         pq = reinterpret_cast<double2*>(base);
         cen = base + 2 * NC * NBP;
@@ -264,6 +280,7 @@ struct Traj {
         ham = add + NC;
         sq = reinterpret_cast<double2*>(ham + NC);
         xis = ham + NC + Lay::SYM_STAGE;
+        coop = xis + Lay::XI_SCR + grp.bead * (L * coop_scratch<PES>::value);
         want_epot = true;
         status = 0;
         xi_real = 0.0;
@@ -277,8 +294,6 @@ struct Traj {
         for (int k = 0; k < NO; k++) {
             oc[k] = PES::owned(grp.lane, k);
             ob[k] = (oc[k] >= 0 ? oc[k] : 0) * NBP;
-            ms[k] = (oc[k] >= 0) ? A.mass[oc[k] / 3] : 1.0;
-            ims[k] = 1.0 / ms[k];
             if (oc[k] >= 0 && A.at_move[oc[k] / 3]) mv |= 1u << k;
             g[k] = 0.0;
         }
@@ -325,7 +340,7 @@ struct Traj {
         if (NB == 1) {
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (own(k)) Qk(k) = Qk(k) + Pk(k) * A.dt / ms[k];
+                if (own(k)) Qk(k) = Qk(k) + Pk(k) * A.dt / mt[k].x;
             return;
         }
         G.sync();
@@ -380,7 +395,7 @@ struct Traj {
             }
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
+                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(mt[k].x, aq[k], cp[k]), fma(mt[k].y, bp[k], cq[k]));
             return;
         }
         double cp[NO], aq[NO], bp[NO], cq[NO];
@@ -417,7 +432,7 @@ struct Traj {
             }
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
+                if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(mt[k].x, aq[k], cp[k]), fma(mt[k].y, bp[k], cq[k]));
             return;
         }
 #pragma unroll 2
@@ -436,7 +451,7 @@ struct Traj {
         G.sync();
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(ms[k], aq[k], cp[k]), fma(ims[k], bp[k], cq[k]));
+            if (own(k)) pq[ob[k] + G.bead] = make_double2(fma(mt[k].x, aq[k], cp[k]), fma(mt[k].y, bp[k], cq[k]));
     }
     // gradient.f90 -> egrad_<pes> for this bead; returns epot = sum over beads (verlet.f90:772-777)
     __device__ __forceinline__ double forces()
@@ -444,7 +459,11 @@ struct Traj {
         G.sync();
         double e;
         const double2* base = pq + G.bead;
-        const int w = PES::eval_coop([&](int c) { return base[c * NBP].y; }, G.lane, G.mask, e, g);
+        int w;
+        if constexpr (coop_scratch<PES>::value > 0)
+            w = PES::eval_coop([&](int c) { return base[c * NBP].y; }, G.lane, G.mask, e, g, coop);
+        else
+            w = PES::eval_coop([&](int c) { return base[c * NBP].y; }, G.lane, G.mask, e, g);
         if (w) status |= CRCL_TRAJ_PESWARN;
         return want_epot ? G.sum(e) : 0.0;
     }
@@ -511,7 +530,7 @@ struct Traj {
 #pragma unroll
         for (int k = 0; k < NO; k++)
             if (own(k)) {
-                Qk(k) = Qk(k) + coeff / ms[k] * dxi[oc[k]];
+                Qk(k) = Qk(k) + coeff / mt[k].x * dxi[oc[k]];
                 Pk(k) = Pk(k) + mult * dt / NB * dxi[oc[k]];
             }
         return 0;
@@ -522,7 +541,7 @@ struct Traj {
         double c1 = 0.0, c2 = 0.0;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (own(k)) c1 += dxi[oc[k]] * Pk(k) / ms[k];
+            if (own(k)) c1 += dxi[oc[k]] * Pk(k) / mt[k].x;
 #pragma unroll
         for (int j = 0; j < NAT; j++)
 #pragma unroll
@@ -544,7 +563,7 @@ struct Traj {
                 const int m = oc[k];
                 double z0, z1;
                 normal_pair(A.seed, tid, event, (uint32_t)G.bead, (uint32_t)(m >> 1), z0, z1);
-                Pk(k) = ((m & 1) ? z1 : z0) * sqrt(ms[k] / beta_n);
+                Pk(k) = ((m & 1) ? z1 : z0) * sqrt(mt[k].x / beta_n);
             }
         event++;
     }
@@ -561,7 +580,7 @@ struct Traj {
         double ek = 0.0;
 #pragma unroll
         for (int k = 0; k < NO; k++)
-            if (mov(k)) ek += Pk(k) * Pk(k) / (2.0 * ms[k]) / NB / NB;
+            if (mov(k)) ek += Pk(k) * Pk(k) / (2.0 * mt[k].x) / NB / NB;
         double eksum = G.sum(ek);
         double scale = 1.0, gn;
         const double nf = (double)nfree;
@@ -723,13 +742,29 @@ struct Traj {
         return 0;
     }
 
+    // NaN / Inf scan of the positions (verlet.f90:1256-1275)
+    __device__ __forceinline__ void nan_scan()
+    {
+        int nan = 0;
+#pragma unroll
+        for (int k = 0; k < NO; k++)
+            if (oc[k] >= 0) {
+                const double v = Q(oc[k]);
+                nan |= (v != v) || (v > 1.79769313486231570815e308);
+            }
+        if (G.any(nan)) status |= CRCL_TRAJ_NAN;
+    }
+
     // one verlet step (SURVEY.md 3.5 numbering)
     // check_nan: run the NaN / Inf scan of verlet.f90:1256-1275 in this step.  A NaN coordinate never
     // recovers, so the callers scan every 16th and the last step of a launch: same status, one
     // CTA-wide vote less per step.
+    // CM: the constrain mode as a compile-time constant (the recrossing children always run mode 2: their kernel then
+    // carries none of the thermostat / bias / SHAKE / rotation-removal code), or -99 to read it from the arguments.
+    template <int CM = -99>
     __device__ __forceinline__ void step(int istep, bool check_nan = true)
     {
-        const int c = A.constrain, th = A.thermostat;
+        const int c = (CM == -99) ? A.constrain : CM, th = A.thermostat;
         if (c != 2 && th == 2) nhc();                          // 1
         half_kick();                                           // 2,3
         free_rp();                                             // 4
@@ -753,16 +788,7 @@ struct Traj {
         if (c != 2 && th == 2) nhc();                          // 15
         if (c != 2 && th == 1 && A.andersen_step > 0 && (istep % A.andersen_step) == 0)
             andersen();                                        // 16
-        if (check_nan) {                                       // 18
-            int nan = 0;
-#pragma unroll
-            for (int k = 0; k < NO; k++)
-                if (oc[k] >= 0) {
-                    const double v = Q(oc[k]);
-                    nan |= (v != v) || (v > 1.79769313486231570815e308);
-                }
-            if (G.any(nan)) status |= CRCL_TRAJ_NAN;
-        }
+        if (check_nan) nan_scan();                             // 18
         if (c <= 0)                                            // 19
             if (transrot()) status |= CRCL_TRAJ_SINGULAR;
         // the drivers' rpmd_check right after verlet (rpmd_check.f90:88-116; calc_rate.f90:945,1575,1633,
@@ -819,9 +845,16 @@ struct LaunchCfg {
 //   H_x[b][a] = f_x((a-b) mod N)                          (CRCL_TRANSFORM_EXACT)
 //   H_x[b][a] = (f_x((a-b) mod N) + f_x((a+b) mod N)) / 2  (reference: Circ(f).(I+J)/2)
 // for x = c, a, b, so that the symmetrisation costs nothing per step; otherwise f_x[N] as they come.
-template <int NAT, int NB, int LANES>
+template <class PES, int NB>
 __device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
 {
+    constexpr int NAT = PES::NATOMS, LANES = PES::LANES;
+    static_assert(2 * LANES * PES::NOWN <= SmemLayout<NAT, NB, LANES>::MT_MAX, "enlarge MT_MAX");
+    for (int i = threadIdx.x; i < LANES * PES::NOWN; i += blockDim.x) {
+        const int oc = PES::owned(i / PES::NOWN, i % PES::NOWN);
+        const double m = (oc >= 0) ? A.mass[oc / 3] : 1.0;
+        reinterpret_cast<double2*>(smem + SmemLayout<NAT, NB, LANES>::MT_OFF)[i] = make_double2(m, 1.0 / m);
+    }
     if (SmemLayout<NAT, NB, LANES>::HTAB) {
         for (int i = threadIdx.x; i < 3 * NB * NB; i += blockDim.x) {
             const int x = i / (NB * NB), r = i - x * NB * NB, b = r / NB, a = r - b * NB;
@@ -842,7 +875,7 @@ verlet_kernel(const __grid_constant__ TrajArgs A)
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    load_fker<PES, NB>(A, smem);
     Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
@@ -919,7 +952,7 @@ mdinit_kernel(const __grid_constant__ TrajArgs A, const int bias_mode, const dou
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    load_fker<PES, NB>(A, smem);
     Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
@@ -979,7 +1012,7 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     extern __shared__ __align__(16) double smem[];
     constexpr int NC = 3 * PES::NATOMS, NO = PES::NOWN;
     using Grp = Group<NB, PES::LANES>;
-    load_fker<PES::NATOMS, NB, PES::LANES>(A, smem);
+    load_fker<PES, NB>(A, smem);
     Grp G(smem + SmemLayout<PES::NATOMS, NB, PES::LANES>::FKER);
     const int traj = blockIdx.x * Grp::GPB + G.gib;
     if (traj >= A.ntraj) return;
@@ -1003,7 +1036,7 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     double vs = 0.0, fs = 0.0;
 #pragma unroll
     for (int k = 0; k < NO; k++)
-        if (T.own(k)) vs += T.dxi[T.oc[k]] * T.Pk(k) / T.ms[k];
+        if (T.own(k)) vs += T.dxi[T.oc[k]] * T.Pk(k) / T.mt[k].x;
 #pragma unroll
     for (int c = 0; c < NC; c++) fs += T.dxi[c] * T.dxi[c] / A.mass[c / 3];
     vs = G.sum(vs) / NB;
@@ -1013,9 +1046,14 @@ recross_kernel(const __grid_constant__ TrajArgs A)
         A.weight[traj] = w;
         A.denom_part[traj] = (vs > 0) ? w : 0.0;
     }
+    // Tried and rejected on measurement (profiles/r2j_*): a child step arranged around two barriers instead of six (CTA
+    // re-alignment doubling as the staging barrier, centroid of q' from the staged sums through the column means of the
+    // tables, surface behind a warp-level fence): 13.8 against 12.6 ms per 1000 steps -- warps that meet at fewer barriers
+    // drift apart in the ~50 KB step body and stop sharing fetched instruction lines (no_instruction 0.59 -> 1.00 cycles
+    // per issue), and the second copy of the transform raised the spills.
     for (int l = 1; l <= A.nsteps; l++) {
         Grp::align_warps();
-        if (!(T.status & CRCL_TRAJ_NAN)) T.step(l, (l & 15) == 0 || l == A.nsteps);
+        if (!(T.status & CRCL_TRAJ_NAN)) T.template step<2>(l, (l & 15) == 0 || l == A.nsteps);   // A.constrain = 2 (api.cu)
         if (T.xi_writer()) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
     }
     if (G.tig == 0 && A.status) A.status[traj] = T.status;

@@ -66,6 +66,23 @@ def geh4oh_ts():
     return q / BOHR
 
 
+def ch4cn_ts():
+    """CH4 + CN near its (early) abstraction saddle region: tetrahedral CH4 (r0ch = 1.094 A, egrad_ch4cn.f:2078) with the
+    hydrogen in flight (atom 1) at 1.20 A, the carbon of CN 1.55 A beyond it, N at 1.172 A and 172 deg (the H-C-N
+    reference angle is 180 deg; off the axis so that the bend's cross product is not the zero vector).  Atom order
+    H, C, H, H, H, C(N), N."""
+    t = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]]) / np.sqrt(3)
+    q = np.zeros((7, 3))
+    q[0] = t[0] * 1.20
+    q[2], q[3], q[4] = t[1] * 1.094, t[2] * 1.094, t[3] * 1.094
+    q[5] = t[0] * (1.20 + 1.55)
+    e2 = t[1] - (t[1] @ t[0]) * t[0]
+    e2 /= np.linalg.norm(e2)
+    th = np.deg2rad(172.0)
+    q[6] = q[5] + 1.172 * (np.cos(th) * (-t[0]) + np.sin(th) * e2)
+    return q / BOHR
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -83,6 +100,8 @@ SYSTEMS = {
                   mecha=dict(bond_form=[[4, 6]], bond_break=[[2, 4]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
     "geh4oh": dict(pes="geh4oh", symbols=["H", "GE", "H", "H", "H", "O", "H"], ts=geh4oh_ts,
                    mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
+    "ch4cn": dict(pes="ch4cn", symbols=["H", "C", "H", "H", "H", "C", "N"], ts=ch4cn_ts,
+                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

@@ -39,6 +39,7 @@ extern "C" {
 #define CRCL_PES_O3 5    /* "o3"   egrad_o3.f   O3 1 1A" PIP surface (Varga, Paukku, Truhlar 2017), atoms O,O,O */
 #define CRCL_PES_CH4OH 6 /* "ch4oh" egrad_ch4oh.f Espinosa-Garcia/Corchado CH4 + OH, atoms H,C,H,H,H,O,H */
 #define CRCL_PES_GEH4OH 7 /* "geh4oh" egrad_geh4oh.f GeH4 + OH, atoms H,Ge,H,H,H,O,H */
+#define CRCL_PES_CH4CN 8 /* "ch4cn" egrad_ch4cn.f CH4 + CN (Espinosa-Garcia, Rangel, Suleimanov 2017), atoms H,C,H,H,H,C,N */
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
                              crcl_set_qmdff2, crcl_set_dgevb */

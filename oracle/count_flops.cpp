@@ -25,6 +25,12 @@ namespace cbe_geh4oh {
 #undef ipow
 }
 
+namespace cbe_ch4cn {
+#define ipow ipow_ch4cn
+#include "pes_ch4cn.c"
+#undef ipow
+}
+
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
 static void census(const char* name, egrad_fn fn, int nat, const double* ts, int n, bool last)
@@ -73,7 +79,12 @@ int main()
     const double t0 = 1.62 * s3 / b, t1 = 1.525 * s3 / b, to = 2.97 * s3 / b;
     const double geh4oh[21] = {t0, t0, t0, 0, 0, 0, t1, -t1, -t1, -t1, t1, -t1, -t1, -t1, t1, to, to, to,
                                to + 0.97 * 0.6650 / b, to - 0.97 * 0.6820 / b, to - 0.97 * 0.3040 / b};
-    census("geh4oh", cbe_geh4oh::oracle_egrad_geh4oh_real, 7, geh4oh, 2000, true);
+    census("geh4oh", cbe_geh4oh::oracle_egrad_geh4oh_real, 7, geh4oh, 2000, false);
+    // caracal_b200/systems.py ch4cn_ts
+    const double u0 = 1.20 * s3 / b, u1 = 1.094 * s3 / b, uc = 2.75 * s3 / b;
+    const double ch4cn[21] = {u0, u0, u0, 0, 0, 0, u1, -u1, -u1, -u1, u1, -u1, -u1, -u1, u1, uc, uc, uc,
+                              uc + 1.172 * 0.6385 / b, uc + 1.172 * 0.5384 / b, uc + 1.172 * 0.5384 / b};
+    census("ch4cn", cbe_ch4cn::oracle_egrad_ch4cn_real, 7, ch4cn, 2000, true);
     printf("}\n");
     return 0;
 }

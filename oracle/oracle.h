@@ -27,12 +27,15 @@ void oracle_ch4h_parts_real(const real *q18, real parts[3], real *V);
 void oracle_ch4h_parts_grad_real(const real *q18, real parts[3], real *gparts);
 void oracle_ch4oh_parts_grad_real(const real *q21, real parts[3], real *gparts);
 void oracle_geh4oh_parts_grad_real(const real *q21, real parts[3], real *gparts);
+void oracle_ch4cn_parts_grad_real(const real *q21, real parts[3], real *gparts);
 void oracle_egrad_brh2_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_egrad_o3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_egrad_ch4oh_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_ch4oh_parts_real(const real *q21, real parts[3], real *V);
 void oracle_egrad_geh4oh_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_geh4oh_parts_real(const real *q21, real parts[3], real *V);
+void oracle_egrad_ch4cn_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_ch4cn_parts_real(const real *q21, real parts[3], real *V);
 void oracle_brh2_pot_real(const real R[3], real *V, real dVdR[3], int *ierr);
 
 #ifdef __cplusplus

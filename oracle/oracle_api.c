@@ -37,6 +37,7 @@ void oracle_ch4h_parts(const double *q18, double parts[3], double *V)
 void oracle_ch4h_parts_grad(const double *q18, double parts[3], double *gparts) { oracle_ch4h_parts_grad_real(q18, parts, gparts); }
 void oracle_ch4oh_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_ch4oh_parts_grad_real(q21, parts, gparts); }
 void oracle_geh4oh_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_geh4oh_parts_grad_real(q21, parts, gparts); }
+void oracle_ch4cn_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_ch4cn_parts_grad_real(q21, parts, gparts); }
 void oracle_ch4oh_parts(const double *q21, double parts[3], double *V)
 {
     oracle_ch4oh_parts_real(q21, parts, V);
@@ -53,6 +54,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_O3: oracle_egrad_o3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_CH4OH: oracle_egrad_ch4oh_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_GEH4OH: oracle_egrad_geh4oh_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_CH4CN: oracle_egrad_ch4cn_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

@@ -34,6 +34,10 @@
  * With -DCBE_GEH4OH in addition (pes_geh4oh.c) they restate /root/reference/src/egrad_geh4oh.f (GeH4 + OH ->
  * GeH3 + H2O): the CH4 + OH file again with its own BLOCK DATA (:2002-2042), the in-plane reference angle built
  * on taugeh = 0.678 pi instead of pi/2 (:368, :382-440) and sphi evaluated at every distance (:1793-1804).
+ * With -DCBE_CH4CN in addition to CBE_CH4OH (pes_ch4cn.c) they restate /root/reference/src/egrad_ch4cn.f (CH4 + CN ->
+ * CH3 + HCN; Espinosa-Garcia, Rangel, Suleimanov, PCCP 19, 19341 (2017)): the CH4 + OH file with the abstracting atom
+ * the carbon of CN and the seventh atom its nitrogen, its own BLOCK DATA (:2074-2114), and the Morse term of the
+ * seventh atom on literal constants (:625-627, :659: r0 = 1.172, a = 0.80, D = 80.0 -- D is NOT scaled by fact1).
  */
 #include "oracle_real.h"
 #include "oracle.h"
@@ -146,6 +150,24 @@ static void ch4h_prepot(ch4h_par *p)
     p->bk = 50.7132;
     p->aa1 = 0.173746;
     p->aa3 = 2.166595;
+#endif
+#ifdef CBE_CH4CN
+    /* BLOCK DATA PTPACM_ch4cn (egrad_ch4cn.f:2074-2114): the entries that differ from CH4 + OH */
+    p->d3ch = 14.65328;
+    p->a1ch = 1.75000;
+    p->b1ch = 0.12000;
+    p->c1ch = 5.00000;
+    p->r0hh = 1.06497;
+    p->d1hh = 132.17000;
+    p->d3hh = 44.63017;
+    p->ahh = 1.70000;
+    p->r0cb = 1.72592;
+    p->d3cbi = 88.69509;
+    p->acb = 3.08688;
+    p->aa1 = 0.273746;
+    p->fkh2oeq = 0.2600000;
+    p->alph2o = 3.1080000;
+    p->anh2oeq = 180.0000000;
 #endif
     p->d3cbi = p->d3cbi * fact1;
     p->a3cb = p->a3cb * fact1;
@@ -413,10 +435,17 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
     vqcb = (e1 + e3) * 0.5;
     vjcb = (e1 - e3) * 0.5;
 #ifdef CBE_CH4OH
+#ifdef CBE_CH4CN
+    /* C-N Morse term on literal constants (egrad_ch4cn.f:625-627) */
+    dt = (s->rno - 1.172);
+    expterm = exp(-0.80 * dt);
+    vno = 80.0 * ((1.0 - expterm) * (1.0 - expterm));
+#else
     /* O-H Morse term (:616-621) */
     dt = (s->rno - r0hh);
     expterm = exp(-ahh * dt);
     vno = d1hh * ((1.0 - expterm) * (1.0 - expterm));
+#endif
 #endif
     for (i = 1; i <= 4; i++) {
         e1 = d1ch * (exp(-2.0 * ach * (rch[i] - r0ch)) - 2.0 * exp(-ach * (rch[i] - r0ch)));
@@ -435,7 +464,11 @@ static void ch4h_stretch(const ch4h_par *p, ch4h_state *s, real *vstr_out)
     }
 #ifdef CBE_CH4OH
     vstr = vstr + vno;                                      /* :646 */
+#ifdef CBE_CH4CN
+    deddt = 2.0 * 0.8 * 80.0 * (1.0 - expterm) * expterm;   /* egrad_ch4cn.f:659-660 */
+#else
     deddt = 2.0 * ahh * d1hh * (1.0 - expterm) * expterm;   /* :652-659 */
+#endif
     de = deddt / s->rno;
     for (i = 1; i <= 3; i++) ded[i] = de * s->tno[i];
 #endif
@@ -972,7 +1005,13 @@ static void ch4h_ipbend(const ch4h_par *p, ch4h_state *s, real *vip_out)
 #undef CBE_EGRAD
 #undef CBE_PARTS
 #undef CBE_PARTS_GRAD
-#if defined(CBE_GEH4OH)
+#if defined(CBE_CH4CN)
+#define CBE_NC 21   /* POT_ch4cn :161-293 */
+#define CBE_NAT 7
+#define CBE_EGRAD oracle_egrad_ch4cn_real
+#define CBE_PARTS oracle_ch4cn_parts_real
+#define CBE_PARTS_GRAD oracle_ch4cn_parts_grad_real
+#elif defined(CBE_GEH4OH)
 #define CBE_NC 21   /* pot_geh4oh :84-217 */
 #define CBE_NAT 7
 #define CBE_EGRAD oracle_egrad_geh4oh_real

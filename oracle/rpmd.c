@@ -257,6 +257,9 @@ void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g)
     case ORC_PES_GEH4OH:
         oracle_egrad_geh4oh_real(xyz, s->natoms, 1, e, g, &info);
         break;
+    case ORC_PES_CH4CN:
+        oracle_egrad_ch4cn_real(xyz, s->natoms, 1, e, g, &info);
+        break;
     default:
         *e = 0.0;
         memset(g, 0, sizeof(double) * 3 * s->natoms);

@@ -21,6 +21,7 @@
 #define ORC_PES_O3 5
 #define ORC_PES_CH4OH 6
 #define ORC_PES_GEH4OH 7
+#define ORC_PES_CH4CN 8
 
 #ifdef __cplusplus
 extern "C" {

@@ -11,7 +11,7 @@ TOL_EG = 1e-10   # energies / gradients per bead, relative
 TOL_QP = 1e-8    # positions / momenta after 100 steps
 
 
-from caracal_b200.systems import (SYSTEMS, brh2_ts, ch4oh_ts, ch5_ts, geh4oh_ts, h3_ts, masses, mechanism, o3_ts, oh3_ts,  # noqa: E402,F401
+from caracal_b200.systems import (SYSTEMS, brh2_ts, ch4cn_ts, ch4oh_ts, ch5_ts, geh4oh_ts, h3_ts, masses, mechanism, o3_ts, oh3_ts,  # noqa: E402,F401
                                   ring_polymer)
 
 

@@ -4,6 +4,9 @@
 #include "../../caracal_b200/csrc/pes_h3.cuh"
 #include "../../caracal_b200/csrc/pes_oh3.cuh"
 #include "../../caracal_b200/csrc/pes_ch4h.cuh"
+#include "../../caracal_b200/csrc/pes_brh2.cuh"
+#include "../../caracal_b200/csrc/pes_o3.cuh"
+#include "../../caracal_b200/csrc/pes_ch4oh.cuh"
 
 template <class PES>
 static int run(const double* q, int nimg, double* V, double* g)
@@ -20,6 +23,11 @@ extern "C" int hh_egrad(int pes, const double* q, int nimg, double* V, double* g
     case CRCL_PES_H3: return run<crcl::PesH3>(q, nimg, V, g);
     case CRCL_PES_OH3: return run<crcl::PesOH3>(q, nimg, V, g);
     case CRCL_PES_CH4H: return run<crcl::PesCH4H>(q, nimg, V, g);
+    case CRCL_PES_BRH2: return run<crcl::PesBrH2>(q, nimg, V, g);
+    case CRCL_PES_O3: return run<crcl::PesO3>(q, nimg, V, g);
+    case CRCL_PES_CH4OH: return run<crcl::PesCH4OH>(q, nimg, V, g);
+    case CRCL_PES_GEH4OH: return run<crcl::PesGeH4OH>(q, nimg, V, g);
+    case CRCL_PES_CH4CN: return run<crcl::PesCH4CN>(q, nimg, V, g);
     }
     return -1;
 }
@@ -57,3 +65,24 @@ extern "C" void hh_normal_pair(unsigned long long seed, unsigned traj, unsigned 
 {
     crcl::normal_pair(seed, traj, event, bead, pair, z[0], z[1]);
 }
+
+#ifdef CRCL_FM_ACTIVE
+// the branch-free elementary functions of crcl_common.cuh (namespace fm) with the host model of the MUFU seeds
+extern "C" void hh_fm(int func, const double* x, const double* y, int n, double* out)
+{
+    for (int i = 0; i < n; i++) {
+        switch (func) {
+        case 0: out[i] = crcl::fm::rcp(x[i]); break;
+        case 1: out[i] = crcl::fm::div(x[i], y[i]); break;
+        case 2: out[i] = crcl::fm::rsqrt(x[i]); break;
+        case 3: out[i] = crcl::fm::sqrt<>(x[i]); break;
+        case 4: out[i] = crcl::fm::exp(x[i]); break;
+        case 5: out[i] = crcl::fm::acos(x[i]); break;
+        case 6: { double s, is; crcl::sqrt_rsqrt(x[i], s, is); out[i] = s; } break;
+        case 7: out[i] = crcl::fm::log(x[i]); break;
+        case 8: out[i] = crcl::fm::pow(x[i], y[i]); break;
+        case 9: out[i] = crcl::fm::sqrt<true>(x[i]); break;
+        }
+    }
+}
+#endif

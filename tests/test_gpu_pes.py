@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
                                           ("oh3", 0.5, 30000), ("ch4h", 0.15, 100000), ("ch4h", 0.4, 30000),
                                           ("brh2", 0.15, 100000), ("brh2", 0.5, 30000), ("o3", 0.15, 100000), ("o3", 0.4, 30000),
                                           ("ch4oh", 0.15, 100000), ("ch4oh", 0.4, 30000),
-                                          ("geh4oh", 0.15, 100000), ("geh4oh", 0.4, 30000)])
+                                          ("geh4oh", 0.15, 100000), ("geh4oh", 0.4, 30000),
+                                          ("ch4cn", 0.15, 100000), ("ch4cn", 0.4, 30000)])
 def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, n, sigma, rng)
@@ -80,7 +81,28 @@ def test_h3_compact_branch_and_warning_bits(gpu, oracle):
     assert info == oinfo == 2
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn"])
+def test_egrad_far_apart_matches_oracle(gpu, oracle, name):
+    """reactants 8 ... 45 bohr apart, where the umbrella windows of a rate calculation go (DIST_INF): arguments far
+    outside the saddle-point clouds (BKMP2's H2 singlet curve calls exp(-2e12) at 30 bohr); the CPU twin of this test
+    (tests/test_host_harness.py::test_pes_functor_far_apart) explains the 35 bohr of Br + H2"""
+    rng = np.random.default_rng(17)
+    q = C.ts_cloud(name, 20000, 0.1, rng)
+    frag = [i - 1 for i in C.SYSTEMS[name]["mecha"]["reactants"][-1]]
+    rest = [i for i in range(q.shape[1]) if i not in frag]
+    d = q[:, frag].mean(axis=1) - q[:, rest].mean(axis=1)
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    far = 35.0 if name == "brh2" else 45.0
+    q[:, frag] += (d * rng.uniform(8.0, far, (len(q), 1)))[:, None, :]
+    Vo, go, _ = oracle.egrad(name, q)
+    Vd, gd, _ = gpu.egrad(name, q)
+    ok = np.isfinite(Vo) & np.isfinite(go.reshape(len(q), -1)).all(axis=1)
+    assert ok.mean() > 0.99 and np.isfinite(Vd[ok]).all() and np.isfinite(gd[ok]).all()
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+
+
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn"])
 def test_invariances_at_scale(gpu, name):
     """size-independent properties on 1e6 images: rigid motions and permutations of equivalent
     hydrogens leave E unchanged and rotate/permute the gradient."""
@@ -102,7 +124,7 @@ def test_invariances_at_scale(gpu, name):
     # net force and torque vanish
     assert np.abs(g.sum(axis=1)).max() < 1e-10
     perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5], "brh2": [2, 1, 0], "o3": [1, 2, 0],
-            "ch4oh": [3, 1, 2, 0, 4, 5, 6], "geh4oh": [0, 1, 3, 2, 4, 5, 6]}[name]
+            "ch4oh": [3, 1, 2, 0, 4, 5, 6], "geh4oh": [0, 1, 3, 2, 4, 5, 6], "ch4cn": [0, 1, 2, 4, 3, 5, 6]}[name]
     V3, g3, _ = gpu.egrad(name, q[:, perm])
     ok = np.ones(len(q), dtype=bool)
     if name == "brh2":

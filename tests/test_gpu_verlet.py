@@ -39,6 +39,8 @@ CASES = [
     ("ch4oh", 16, 2, 0, 0, 2, 0.98, 0.0, 3),      # child trajectories
     ("geh4oh", 8, 0, 1, 40, 2, 0.9, 15.0, 3),     # GeH4 + OH, umbrella window
     ("geh4oh", 16, 2, 0, 0, 2, 0.98, 0.0, 2),     # child trajectories
+    ("ch4cn", 8, 0, 1, 40, 2, 0.9, 15.0, 3),      # CH4 + CN, umbrella window
+    ("ch4cn", 16, 2, 0, 0, 2, 0.98, 0.0, 2),      # child trajectories
 ]
 
 

@@ -174,7 +174,7 @@ def test_rpmd_check_bits(oracle):
 
 
 # ---- CBE sub-terms by finite differences ------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["ch4h", "ch4oh", "geh4oh"])
+@pytest.mark.parametrize("name", ["ch4h", "ch4oh", "geh4oh", "ch4cn"])
 def test_cbe_subterm_gradients_by_finite_differences(oracle, name):
     """stretch / opbend / ipbend separately: the gradient each routine adds to pdot against central differences of
     the energy the same routine returns (egrad_ch4h.f:506,713,865 and the twins in egrad_ch4oh.f, egrad_geh4oh.f).

@@ -1,4 +1,5 @@
-"""CPU tests of the CH4 + OH and GeH4 + OH oracles (oracle/pes_ch4oh.c, pes_geh4oh.c <- egrad_ch4oh.f, egrad_geh4oh.f;
+"""CPU tests of the CH4 + OH, GeH4 + OH and CH4 + CN oracles (oracle/pes_ch4oh.c, pes_geh4oh.c, pes_ch4cn.c <- egrad_ch4oh.f,
+egrad_geh4oh.f, egrad_ch4cn.f;
 SURVEY.md 8f row N4).  The reference ships no
 outputs for this surface; what it does ship is the start structure of its own saddle search
 (examples/explore/ts_irc_ch4oh/ts_start.xyz), used here as the geometry the clouds are drawn around."""
@@ -17,7 +18,7 @@ def oracle():
     return O
 
 
-NAMES = ["ch4oh", "geh4oh"]
+NAMES = ["ch4oh", "geh4oh", "ch4cn"]
 
 
 def fd_gradient(O, q, h=1e-4, name="ch4oh"):
@@ -129,3 +130,41 @@ def test_bend_force_constant_is_the_water_value(oracle, name, rxh):
     x = water_far_from_xh3(name, rxh)
     _, g, _ = oracle.egrad(name, x[None])
     assert np.abs(g.reshape(7, 3)[6]).max() < 2e-5     # 0.52918 (POT) against 0.52917721 (the test) in r0hh
+
+
+def hcn_far_from_ch3(rch=1.06497, rcn=1.172, bend=0.0):
+    """products far apart (CH3 ... HCN, 12 A): H on the carbon of CN at rch, N at rcn, H-C-N opened by `bend` from 180 deg"""
+    t = np.array([[1, 1, 1], [1, -1, -1], [-1, 1, -1], [-1, -1, 1]]) / np.sqrt(3)
+    q = np.zeros((7, 3))
+    q[2], q[3], q[4] = t[1] * 2.05, t[2] * 2.05, t[3] * 2.05           # CH3
+    q[5] = t[0] * 12.0 / C.BOHR                                        # C of CN
+    q[0] = q[5] - t[0] * rch / C.BOHR                                  # H taken from CH4, now on that carbon
+    e2 = t[1] - (t[1] @ t[0]) * t[0]
+    e2 /= np.linalg.norm(e2)
+    q[6] = q[5] + rcn / C.BOHR * (np.cos(bend) * t[0] + np.sin(bend) * e2)
+    return q
+
+
+def test_ch4cn_product_fragment_is_hydrogen_cyanide(oracle):
+    """known answers for the constants egrad_ch4cn.f adds to the CH4 + OH template (BLOCK DATA :2084-2087, :2109-2111 and
+    the literals of :625-627): far from CH3 the H-C-N fragment relaxes to the experimental HCN geometry the constants
+    encode -- r(C-H) = r0hh = 1.06497 A (experiment 1.0655), r(C-N) = 1.172 A (the CN radical's 1.1718), linear -- and the
+    well of the H-CN bond is d1hh = 132.17 kcal/mol deep"""
+    from scipy.optimize import minimize
+    q = hcn_far_from_ch3(1.10, 1.20, 0.15)
+
+    def f(x):
+        V, g, _ = oracle.egrad("ch4cn", x.reshape(1, 7, 3))
+        return V[0], g.reshape(-1)
+    res = minimize(f, q.reshape(-1), jac=True, method="BFGS", options=dict(gtol=1e-7, maxiter=3000))
+    x = res.x.reshape(7, 3)
+    a, b = x[0] - x[5], x[6] - x[5]
+    assert abs(np.linalg.norm(a) * C.BOHR - 1.06497) < 2e-3
+    assert abs(np.linalg.norm(b) * C.BOHR - 1.172) < 2e-3
+    ang = np.degrees(np.arccos(a @ b / np.linalg.norm(a) / np.linalg.norm(b)))
+    assert ang > 179.0
+    # depth of the H-CN well: pull the hydrogen off along the axis
+    far = x.copy()
+    far[0] = x[5] + (x[0] - x[5]) / np.linalg.norm(a) * 14.0
+    dE = (oracle.egrad("ch4cn", far[None])[0][0] - res.fun) * KCAL
+    assert abs(dE - 132.17) < 1.5
