@@ -307,7 +307,7 @@ __device__ __forceinline__ int eliminate(double (&a)[3][3], int irow)
     const double pivot = a[ICOL][ICOL];
     a[ICOL][ICOL] = 1.0;
 #pragma unroll
-    for (int j = 0; j < 3; j++) a[ICOL][j] /= pivot;
+    for (int j = 0; j < 3; j++) a[ICOL][j] = CRCL_DIV(a[ICOL][j], pivot);
 #pragma unroll
     for (int j = 0; j < 3; j++)
         if (j != ICOL) {

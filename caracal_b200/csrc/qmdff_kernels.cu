@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <vector>
 #include "qmdff.cuh"
+#include "crcl_common.cuh"
 
 namespace crcl {
 
@@ -497,8 +498,10 @@ __device__ __forceinline__ void qm_pair_exact(const QmdffDev& D, const InterTabl
         image(vab[1], D.box[1]);
         image(vab[2], D.box[2]);
     }
-    const double r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2], r = sqrt(r2);
-    const double oner = 1.0 / r, oner2 = oner * oner;
+    const double r2 = vab[0] * vab[0] + vab[1] * vab[1] + vab[2] * vab[2];
+    double r, oner;
+    sqrt_rsqrt(r2, r, oner);   // branch-free (crcl_common.cuh, fm::): a pair is ~1/3 fewer instructions without the library's slow paths
+    const double oner2 = oner * oner;
     double dr = 0.0;
     ep = 0.0;
     if (!(per && r > D.vdw_cut)) {
@@ -507,13 +510,13 @@ __device__ __forceinline__ void qm_pair_exact(const QmdffDev& D, const InterTabl
         const double R0 = tb.r094[ti][tj];
         const double r4 = r2 * r2, r6 = r4 * r2, R02 = R0 * R0, r06 = R02 * R02 * R02;
         const double t6 = r6 + r06, t8 = r6 * r2 + r06 * R02;
-        const double it6 = 1.0 / t6, it8 = 1.0 / t8;
+        const double it6 = CRCL_RCP(t6), it8 = CRCL_RCP(t8);
         const double c6t6 = c6 * it6, t27 = tb.sr42[ti][tj] * (c6 * it8);
         ep -= c6t6 + t27;
         dr += c6t6 * 6.0 * r4 * it6 + 8.0 * t27 * r6 * it8;
         if (r < 25.0) {
             const double alpha = tb.r0ab[ti][tj];
-            const double tt = tb.zab[ti][tj] * exp(-alpha * r);
+            const double tt = tb.zab[ti][tj] * CRCL_EXP(-alpha * r);
             ep += tt * oner;
             dr -= tt * (alpha * r + 1.0) * oner * oner2;
         }

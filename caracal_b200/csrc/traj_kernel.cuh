@@ -316,6 +316,15 @@ struct Traj {
         for (int k = 0; k < NO; k++)
             if (own(k)) Pk(k) = mov(k) ? Pk(k) - h * g[k] : 0.0;
     }
+    // the second half kick of one step and the first of the next in one pass over the momenta (the same two operations in
+    // the same order, without the store and reload between them)
+    __device__ __forceinline__ void double_half_kick()
+    {
+        const double h = 0.5 * A.dt;
+#pragma unroll
+        for (int k = 0; k < NO; k++)
+            if (own(k)) Pk(k) = mov(k) ? (Pk(k) - h * g[k]) - h * g[k] : 0.0;
+    }
     __device__ __forceinline__ void mask_p()
     {
 #pragma unroll
@@ -650,7 +659,7 @@ struct Traj {
             if (oc[k] >= 0) {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
                 const double w = A.mass[j];
-                const double v = P(c) / w;
+                const double v = CRCL_DIV(P(c), w);
                 vk[k] = v;
                 const double qx = Q(3 * j), qy = Q(3 * j + 1), qz = Q(3 * j + 2);
                 s[d] += v * w;
@@ -682,8 +691,8 @@ struct Traj {
         double vtot[3], ctr[3], mang[3];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            vtot[d] = s[d] / totmass;
-            ctr[d] = s[3 + d] / totmass;
+            vtot[d] = CRCL_DIV(s[d], totmass);
+            ctr[d] = CRCL_DIV(s[3 + d], totmass);
         }
         mang[0] = s[6] - (ctr[1] * vtot[2] - ctr[2] * vtot[1]) * totmass;
         mang[1] = s[7] - (ctr[2] * vtot[0] - ctr[0] * vtot[2]) * totmass;
@@ -837,7 +846,7 @@ struct LaunchCfg {
     // lane-split surfaces on multi-warp trajectories: the CRCL_MINB_L4 x 64 threads of the single-wave tuning, whatever
     // the packing (7 CTAs of 64 threads or 4 of 128: a 128-register cap either way)
     static constexpr int MINB = WARP ? ((PES::LANES > 1) ? 2 : (CRCL_MINB_L1 * 32 / CRCL_WTPB > 0 ? CRCL_MINB_L1 * 32 / CRCL_WTPB : 1))
-                                     : ((PES::LANES > 1 && TPB <= 128) ? (CRCL_MINB_L4 * 64 / TPB > 0 ? (CRCL_MINB_L4 * 64 + TPB - 1) / TPB : 1)
+                                     : ((PES::LANES > 1 && (TPB <= 128 || Group<NB, PES::LANES>::GPB > 1)) ? (CRCL_MINB_L4 * 64 / TPB > 0 ? (CRCL_MINB_L4 * 64 + TPB - 1) / TPB : 1)
                                                                        : ((PES::LANES == 1 && TPB <= 128) ? CRCL_MINB_C1 : 1));
 };
 
@@ -1051,9 +1060,23 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     // tables, surface behind a warp-level fence): 13.8 against 12.6 ms per 1000 steps -- warps that meet at fewer barriers
     // drift apart in the ~50 KB step body and stop sharing fetched instruction lines (no_instruction 0.59 -> 1.00 cycles
     // per issue), and the second copy of the transform raised the spills.
+    // step() in mode 2 (A.constrain = 2, api.cu) written out, so that the second half kick of a step and the first of the
+    // next are one pass: kick, [free ring polymer, centroid, mask, forces, xi, kick + kick] ..., kick
+    if (A.nsteps > 0) T.half_kick();                           // 2,3 of the first step
     for (int l = 1; l <= A.nsteps; l++) {
         Grp::align_warps();
-        if (!(T.status & CRCL_TRAJ_NAN)) T.template step<2>(l, (l & 15) == 0 || l == A.nsteps);   // A.constrain = 2 (api.cu)
+        if (!(T.status & CRCL_TRAJ_NAN)) {
+            T.free_rp();                                       // 4
+            T.centroid();                                      // 6
+            T.mask_p();                                        // 7
+            T.epot = T.forces();                               // 10
+            T.umbrella(2);                                     // 12
+            if (l < A.nsteps)
+                T.double_half_kick();                          // 13 and 2,3 of the next step
+            else
+                T.half_kick();                                 // 13
+            if ((l & 15) == 0 || l == A.nsteps) T.nan_scan();  // 18
+        }
         if (T.xi_writer()) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
     }
     if (G.tig == 0 && A.status) A.status[traj] = T.status;

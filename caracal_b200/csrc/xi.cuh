@@ -176,14 +176,14 @@ CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double x
         if (i < M.break_num) {
             const int a1 = M.bb[i][0], a2 = M.bb[i][1];
             const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-            s1 += (sqrt(dx * dx + dy * dy + dz * dz) - M.bref[i]) * M.inv_break;
+            s1 += (CRCL_SQRT(dx * dx + dy * dy + dz * dz) - M.bref[i]) * M.inv_break;
         }
 #pragma unroll
     for (int i = 0; i < XI_MAXBOND; i++)
         if (i < M.form_num) {
             const int a1 = M.bf[i][0], a2 = M.bf[i][1];
             const double dx = x[3 * a1] - x[3 * a2], dy = x[3 * a1 + 1] - x[3 * a2 + 1], dz = x[3 * a1 + 2] - x[3 * a2 + 2];
-            s1 -= (sqrt(dx * dx + dy * dy + dz * dz) - M.fref[i]) * M.inv_form;
+            s1 -= (CRCL_SQRT(dx * dx + dy * dy + dz * dz) - M.fref[i]) * M.inv_form;
         }
     // calc_com.f90:36-58; atoms outside fragment k enter with weight 0 (same sums, same order)
     double com[XI_MAXREAC][3];
@@ -205,10 +205,10 @@ CRCL_HD __forceinline__ double xi_value(const Mech& M, const double* x, double x
         for (int j = i + 1; j < XI_MAXREAC; j++)
             if (j < M.sum_reacs) {
                 const double dx = com[j][0] - com[i][0], dy = com[j][1] - com[i][1], dz = com[j][2] - com[i][2];
-                s0 += M.R_inf - sqrt(dx * dx + dy * dy + dz * dz);
+                s0 += M.R_inf - CRCL_SQRT(dx * dx + dy * dy + dz * dz);
             }
     s0 = s0 * M.inv_pairs;
-    return (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    return (mode == 1) ? CRCL_DIV(s0, s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
 }
 
 // mode 1: xi = s0/(s0-s1) (umbrella form); mode 2: xi = xi_ideal*s1 + (1-xi_ideal)*s0.
