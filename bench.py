@@ -623,19 +623,26 @@ def main():
     # DRAM bytes of one launch of this kernel at this shape from an `ncu --set full` capture
     # (profiles/traffic_recross.json, written by profiles/ncu_traffic.py); null when not captured
     traffic = None
+    hardware = None   # the same capture's pipe utilisation: the hardware's view beside the census-based fraction
     try:
         with open(os.path.join(ROOT, "profiles", "traffic_recross.json")) as f:
             tr = json.load(f)
         if tr.get("child_steps") == CHILD_EVOL and tr.get("child_pairs") == local_pairs:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            if "fp64_pipe_active_pct" in tr:
+                hardware = {"fp64_pipe_active_frac": tr["fp64_pipe_active_pct"] / 100.0,
+                            "issue_active_frac": tr.get("issue_active_pct", 0.0) / 100.0,
+                            "warp_instructions_per_launch": tr.get("warp_instructions"),
+                            "source": "ncu --set full, profiles/" + tr.get("source", "traffic_recross.json")}
     except (OSError, ValueError, KeyError):
         pass
     roofline = {"bound": "fp64", "kernel": "recross_kernel<PesCH4H,16>", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": traffic,
                 "peak_source": "builder-measured: DFMA microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
-                "algorithmic_flops_per_launch": bead_steps_launch * fl_bs,
-                "note": "algorithmic flops = reference's own operation count (oracle census); the kernel executes "
-                        "fewer (re-derived PES), see DESIGN.md"}
+                "algorithmic_flops_per_launch": bead_steps_launch * fl_bs, "hardware": hardware,
+                "note": "algorithmic flops = reference's own operation count (oracle census: 411 libm calls, 1813 "
+                        "divisions per image as written); the kernel executes about a quarter of them (re-derived PES), "
+                        "so frac overstates the pipe utilisation -- that is hardware.fp64_pipe_active_frac (ncu)"}
     cpu_baseline = None
     if not args.no_cpu_baseline:
         from oracle import oracle as O

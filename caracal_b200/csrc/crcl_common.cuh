@@ -330,6 +330,25 @@ __device__ __forceinline__ void unswap(double (&a)[3][3], int r, int c)
         swap_cols<1, 2>(a);
 }
 }  // namespace inv3
+// Inverse of a SYMMETRIC 3x3 matrix by cofactors: straight-line code (21 multiply-adds and one reciprocal) where the
+// Gauss-Jordan form above is a tree of data-dependent pivot branches -- ~10 % of the stall samples and a good part of the
+// instruction footprint of every step that removes the net rotation (ncu, verlet_kernel<PesH3,16>,
+// profiles/r2m_verlet_h3_nb16.txt).  Differs from invert.f90's pivoted elimination by rounding only (relative error of
+// both ~ cond(A) eps; a ring polymer's inertia tensor has cond <= 1e4); singular (returns 1) iff the determinant is exactly
+// zero, which is what the elimination reports for the cases that occur -- a collinear arrangement on an axis.
+__device__ __forceinline__ int invert3_sym(double (&a)[3][3])
+{
+    const double p = a[0][0], q = a[0][1], r = a[0][2], u = a[1][1], v = a[1][2], w = a[2][2];
+    const double A = fma(u, w, -v * v), B = fma(r, v, -q * w), C = fma(q, v, -r * u);
+    const double D = fma(p, w, -r * r), E = fma(q, r, -p * v), F = fma(p, u, -q * q);
+    const double det = fma(p, A, fma(q, B, r * C));
+    if (det == 0.0) return 1;
+    const double id = CRCL_RCP(det);
+    a[0][0] = A * id, a[0][1] = B * id, a[0][2] = C * id;
+    a[1][0] = B * id, a[1][1] = D * id, a[1][2] = E * id;
+    a[2][0] = C * id, a[2][1] = E * id, a[2][2] = F * id;
+    return 0;
+}
 __device__ __forceinline__ int invert3(double (&a)[3][3])
 {
     int ip0 = 0, ip1 = 0, ip2 = 0;                 // ipivot(1:3)

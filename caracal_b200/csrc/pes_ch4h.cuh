@@ -655,18 +655,16 @@ struct PesCBE4 {
             __syncwarp();
             c[0][0] = co[0], c[0][1] = co[1], c[0][2] = co[2];
             rch[0] = rcho, irch[0] = ircho;
-            s3[0] = sw[4], ds3[0] = sw[5];
-            sphi[0] = sw[6], dsphi[0] = sw[7], sth[0] = sw[8], dsth[0] = sw[9];
+            s3[0] = sw[4], sphi[0] = sw[6], sth[0] = sw[8];
 #pragma unroll
             for (int t = 1; t < 4; t++) {
                 const double2* o = reinterpret_cast<const double2*>(scr + ((x + t) & 3) * COOP_SCRATCH);
                 nb[t - 1] = o;
-                const double2 v0 = o[0], v1 = o[1], v2 = o[2], v3 = o[3], v4 = o[4];
+                const double2 v0 = o[0], v1 = o[1], v2 = o[2];
                 c[t][0] = v0.x, c[t][1] = v0.y, c[t][2] = v1.x;
                 rch[t] = v1.y, irch[t] = v2.x;
-                s3[t] = v2.y, ds3[t] = v3.x;
-                sphi[t] = v3.y, dsphi[t] = v4.x, sth[t] = v4.y;
-                dsth[t] = reinterpret_cast<const double*>(o)[10];
+                s3[t] = v2.y;
+                sphi[t] = reinterpret_cast<const double*>(o)[7], sth[t] = reinterpret_cast<const double*>(o)[9];
             }
         }
         auto gather_inplane = [&]() {
@@ -674,15 +672,8 @@ struct PesCBE4 {
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 const double2* o = t ? nb[t - 1] : reinterpret_cast<const double2*>(scr + x * COOP_SCRATCH);
-                const double v5y = reinterpret_cast<const double*>(o)[11];
-                const double2 v6 = o[6];
-                const double v7x = reinterpret_cast<const double*>(o)[14];
-                s1[t] = v5y, ds1[t] = v6.x, s2[t] = v6.y, ds2[t] = v7x;
-                if (t < 3) {
-                    const double v7y = reinterpret_cast<const double*>(o)[15];
-                    const double2 v8 = o[8];
-                    f1[t] = v7y, df1c[t] = v8.x, df1h[t] = v8.y;
-                }
+                s1[t] = reinterpret_cast<const double*>(o)[11], s2[t] = reinterpret_cast<const double*>(o)[13];
+                if (t < 3) f1[t] = reinterpret_cast<const double*>(o)[15];
             }
         };
 #else
@@ -710,6 +701,30 @@ struct PesCBE4 {
             }
         }
         auto gather_inplane = [&]() {};
+#endif
+        // The derivatives of the switching functions are used once or twice each, late in their terms: 26 doubles that would
+        // be live (and spilled: ncu attributed 14 % of the kernel's stall samples to reloads in this function) from the
+        // gather to the end.  With the exchange block they are read where they are used, straight from the owner's slot
+        // (volatile: a load the compiler may neither hoist nor keep).
+#ifndef CRCL_CBE_SHFL_GATHER
+        const double* nbd[4] = {scr + x * COOP_SCRATCH, reinterpret_cast<const double*>(nb[0]),
+                                reinterpret_cast<const double*>(nb[1]), reinterpret_cast<const double*>(nb[2])};
+        auto LDV = [&](int t, int off) { return *reinterpret_cast<const volatile double*>(nbd[t] + off); };
+        auto DS3 = [&](int t) { return LDV(t, 6); };
+        auto DSPHI = [&](int t) { return LDV(t, 8); };
+        auto DSTH = [&](int t) { return LDV(t, 10); };
+        auto DS1 = [&](int t) { return LDV(t, 12); };
+        auto DS2 = [&](int t) { return LDV(t, 14); };
+        auto DF1C = [&](int t) { return LDV(t, 16); };
+        auto DF1H = [&](int t) { return LDV(t, 17); };
+#else
+        auto DS3 = [&](int t) { return ds3[t]; };
+        auto DSPHI = [&](int t) { return dsphi[t]; };
+        auto DSTH = [&](int t) { return dsth[t]; };
+        auto DS1 = [&](int t) { return ds1[t]; };
+        auto DS2 = [&](int t) { return ds2[t]; };
+        auto DF1C = [&](int t) { return df1c[t]; };
+        auto DF1H = [&](int t) { return df1h[t]; };
 #endif
         const double tau = TAU_TET;
         const double ta = tau - K::TAU_PLANAR * PI, tb = tau - 2.0 * PI / 3.0;
@@ -788,10 +803,10 @@ struct PesCBE4 {
                     gC[d] -= v;
                     G[d] += wu * (c[m][d] - um * nh[d]);
                 }
-                Dch[0] -= w * ta * dsphi[0] * sphi[m];
-                Dch[m] -= w * ta * sphi[0] * dsphi[m];
-                Dch[ca] -= w * tb * dsth[ca] * sth[cb2];
-                Dch[cb2] -= w * tb * sth[ca] * dsth[cb2];
+                Dch[0] -= w * ta * DSPHI(0) * sphi[m];
+                Dch[m] -= w * ta * sphi[0] * DSPHI(m);
+                Dch[ca] -= w * tb * DSTH(ca) * sth[cb2];
+                Dch[cb2] -= w * tb * sth[ca] * DSTH(cb2);
             }
             {
                 const double s = sg * inn;
@@ -807,10 +822,10 @@ struct PesCBE4 {
             }
             en += fd * sum2 + hd * sum4;
             const double fs = K::FCH3 * sum2 + K::HCH3 * sum4;
-            Dch[0] -= fs * ds3[0] * pj * pk * pl;
-            Dch[1] += fs * (1.0 - s3[0]) * ds3[1] * pk * pl;
-            Dch[2] += fs * (1.0 - s3[0]) * pj * ds3[2] * pl;
-            Dch[3] += fs * (1.0 - s3[0]) * pj * pk * ds3[3];
+            Dch[0] -= fs * DS3(0) * pj * pk * pl;
+            Dch[1] += fs * (1.0 - s3[0]) * DS3(1) * pk * pl;
+            Dch[2] += fs * (1.0 - s3[0]) * pj * DS3(2) * pl;
+            Dch[3] += fs * (1.0 - s3[0]) * pj * pk * DS3(3);
         }
         // ---- in-plane bending: pair local (0,1) on every lane, local (0,2) on lanes 0 and 1 ----
         gather_inplane();
@@ -838,12 +853,12 @@ struct PesCBE4 {
                     gC[d] -= vi + vj;
                 }
                 const double hd2 = 0.5 * del * del;
-                Dch[0] += -w * ta * dsphi[0] * sphi[j] + hd2 * (f0 * ds1[0] * s1[j] * ff + fk0 * df1c[0] * f1[j]);
-                Dch[j] += -w * ta * sphi[0] * dsphi[j] + hd2 * (f0 * s1[0] * ds1[j] * ff + fk0 * f1[0] * df1c[j]);
-                Dch[k] += -w * tb * dsth[k] * sth[l] + hd2 * (f0 - f2) * ds2[k] * s2[l] * ff;
-                Dch[l] += -w * tb * sth[k] * dsth[l] + hd2 * (f0 - f2) * s2[k] * ds2[l] * ff;
-                Dbh[0] += hd2 * fk0 * df1h[0] * f1[j];
-                Dbh[j] += hd2 * fk0 * f1[0] * df1h[j];
+                Dch[0] += -w * ta * DSPHI(0) * sphi[j] + hd2 * (f0 * DS1(0) * s1[j] * ff + fk0 * DF1C(0) * f1[j]);
+                Dch[j] += -w * ta * sphi[0] * DSPHI(j) + hd2 * (f0 * s1[0] * DS1(j) * ff + fk0 * f1[0] * DF1C(j));
+                Dch[k] += -w * tb * DSTH(k) * sth[l] + hd2 * (f0 - f2) * DS2(k) * s2[l] * ff;
+                Dch[l] += -w * tb * sth[k] * DSTH(l) + hd2 * (f0 - f2) * s2[k] * DS2(l) * ff;
+                Dbh[0] += hd2 * fk0 * DF1H(0) * f1[j];
+                Dbh[j] += hd2 * fk0 * f1[0] * DF1H(j);
             }
         }
         double gO[3] = {0, 0, 0}, gBx[3] = {0, 0, 0};   // explicit vector parts on H(O) and on the abstracting atom

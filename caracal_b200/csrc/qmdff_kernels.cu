@@ -89,7 +89,15 @@ __device__ __forceinline__ double block_sum_to(double v, double* dst)
 // that CTAs stay full; the energy then goes out with one atomic per term.
 __device__ __forceinline__ void term_index(int nterm, int nimg, int flat, int& t, int& img)
 {
-    if (flat) {
+    if (flat == 2) {
+        // term-major: the 32 threads of a warp evaluate the SAME term on 32 consecutive images -- one term type per warp
+        // (bonds, angles and torsions of a small molecule no longer share warps and serialise their three bodies) and the
+        // gradient reductions of a warp-instruction go to 32 different images instead of colliding on the few atoms of one
+        const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const size_t tt = gidx / (size_t)nimg;
+        t = (tt < (size_t)nterm) ? (int)tt : nterm;
+        img = (tt < (size_t)nterm) ? (int)(gidx - tt * nimg) : 0;
+    } else if (flat) {
         const size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         const size_t im = gidx / (size_t)nterm;
         t = (im < (size_t)nimg) ? (int)(gidx - im * nterm) : nterm;
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const 
         if (D.periodic) box_image(D, rb);
         const double r2 = dot3(rb, rb), r = sqrt(r2);
         const double rij = D.vbond[3 * t], kij = D.vbond[3 * t + 1], aai = D.vbond[3 * t + 2];
-        const double ph = pow(rij / r, 0.5 * aai), pf = ph * ph;   // (rij/r)^(a/2), (rij/r)^a
+        const double ph = CRCL_POW(CRCL_DIV(rij, r), 0.5 * aai), pf = ph * ph;   // (rij/r)^(a/2), (rij/r)^a
         e = kij * (1.0 + pf - 2.0 * ph);
         const double fac = aai * kij * (-pf + ph) / r2;
         double v[3] = {fac * rb[0], fac * rb[1], fac * rb[2]};
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const 
         const double al = sqrt(rab2), bl = sqrt(rcb2);
         double cosa = (al > 0.0 && bl > 0.0) ? dot3(vab, vcb) / (al * bl) : 0.0;
         cosa = fmin(1.0, fmax(-1.0, cosa));
-        const double theta = acos(cosa);
+        const double theta = CRCL_ACOS(cosa);
         double dij, d2ij, djk, d2jk;
         abdamp(D, D.type[i], D.type[j], rab2, dij, d2ij);
         abdamp(D, D.type[k], D.type[j], rcb2, djk, d2jk);
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(128) qm_bonded_kernel(const QmdffDev D, const 
             if (nan_ > 1.e-14) sn /= nan_;
             if (nbn > 1.e-14) sn /= nbn;
             if (fabs(fabs(sn) - 1.0) < 1.0e-14) sn = (sn >= 0.0) ? 1.0 : -1.0;
-            const double phi = acos(sn);
+            const double phi = CRCL_ACOS(sn);
             const double cosphi = cos(phi), sinphi = sin(phi);
             double dda[3] = {0, 0, 0}, ddb[3] = {0, 0, 0}, ddc[3] = {0, 0, 0}, ddd[3] = {0, 0, 0};
             const double nenner = nan_ * nbn * sinphi;
@@ -380,7 +388,7 @@ __device__ __forceinline__ double vdw_pair(const QmdffDev& D, int t1, int t2, do
     dr = eps * (c6t6 * 6.0 * r4 / t6 + 8.0 * t27 * r6 / t8);
     if (r < 25.0) {
         const double alpha = D.r0ab[t1][t2];
-        const double tt = D.zab[t1][t2] * exp(-alpha * r);
+        const double tt = D.zab[t1][t2] * CRCL_EXP(-alpha * r);
         const double oner = 1.0 / r;
         e += tt * oner * eps;
         dr -= eps * tt * (alpha * r + 1.0) * oner / r2;
@@ -1201,8 +1209,13 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         double* g = d_g + (size_t)i0 * 3 * D->n;
         double* V = d_V + i0;
         const int nterm = D->nbond + D->nangl + D->ntors;
+        // CRCL_QM_TERM_MAJOR=0 keeps the image-major forms (A/B)
+        static const bool tm_on = [] { const char* e = getenv("CRCL_QM_TERM_MAJOR"); return !(e && e[0] == '0'); }();
+        const bool term_major = tm_on && ni >= 512 && D->n <= 128;
         if (nterm > 0) {
-            if (nterm < 96)   // short lists: flat (image, term) index
+            if (term_major)   // many images of a small molecule: flat (term, image) index, see term_index
+                qm_bonded_kernel<<<(unsigned)(((size_t)nterm * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 2);
+            else if (nterm < 96)   // short lists: flat (image, term) index
                 qm_bonded_kernel<<<(unsigned)(((size_t)nterm * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 1);
             else
                 qm_bonded_kernel<<<dim3((nterm + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g, ni, 0);
@@ -1211,7 +1224,9 @@ cudaError_t qmdff_egrad(QmdffDev* D, const double* d_xyz, int nimg, double* d_V,
         // early returns: ff_nonb.f90:74 (nnci <= 1 and nmols == 0), ff_nonb_two.f90:48 (nnci_two <= 1)
         if (!(D->nnci <= 1 && (D->is_two || D->nmols == 0))) {
             if (D->nnci > 0) {
-                if (D->nnci < 96)
+                if (term_major)
+                    qm_nci_kernel<<<(unsigned)(((size_t)D->nnci * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 2);
+                else if (D->nnci < 96)
                     qm_nci_kernel<<<(unsigned)(((size_t)D->nnci * ni + 127) / 128), 128, 0, s>>>(*D, x, V, g, ni, 1);
                 else
                     qm_nci_kernel<<<dim3((D->nnci + 127) / 128, ni), 128, 0, s>>>(*D, x, V, g, ni, 0);

@@ -728,8 +728,12 @@ struct Traj {
             t[2][2] += 0.000001;
         }
         // every thread inverts its own copy of the tensor: the sums above are bit-identical on all threads of the
-        // trajectory and invert3 lives in registers, so this costs no barrier and nobody waits for a publishing thread
+        // trajectory and the inverse lives in registers, so this costs no barrier and nobody waits for a publishing thread
+#ifdef CRCL_TRANSROT_GAUSS_JORDAN   // invert.f90's pivoted elimination operation by operation (A/B builds; the split path uses it)
         if (invert3(t)) return 1;
+#else
+        if (invert3_sym(t)) return 1;
+#endif
         double vang[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) vang[i] = t[i][0] * mang[0] + t[i][1] * mang[1] + t[i][2] * mang[2];
@@ -1063,21 +1067,28 @@ recross_kernel(const __grid_constant__ TrajArgs A)
     // step() in mode 2 (A.constrain = 2, api.cu) written out, so that the second half kick of a step and the first of the
     // next are one pass: kick, [free ring polymer, centroid, mask, forces, xi, kick + kick] ..., kick
     if (A.nsteps > 0) T.half_kick();                           // 2,3 of the first step
-    for (int l = 1; l <= A.nsteps; l++) {
+    // loop state in registers (steps left, theta cursor): the kernel arguments live in the constant bank, and ncu showed the
+    // per-step reloads of nsteps / ntraj / theta behind `l < A.nsteps` among the top long-scoreboard lines
+    unsigned char* th = A.theta + traj;
+    const int ntraj = A.ntraj;
+    for (int l = 1, rem = A.nsteps; rem > 0; l++, rem--, th += ntraj) {
         Grp::align_warps();
         if (!(T.status & CRCL_TRAJ_NAN)) {
+            // (tried and rejected on measurement, profiles/r2o_*: the centroid of q' from the staged sums -- the centroid
+            // mode of a free ring polymer moves as a free particle -- on the warp that evaluates xi, without centroid()'s
+            // two barriers: 11.80 against 11.76 ms per 1000 steps)
             T.free_rp();                                       // 4
             T.centroid();                                      // 6
             T.mask_p();                                        // 7
             T.epot = T.forces();                               // 10
             T.umbrella(2);                                     // 12
-            if (l < A.nsteps)
+            if (rem > 1)
                 T.double_half_kick();                          // 13 and 2,3 of the next step
             else
                 T.half_kick();                                 // 13
-            if ((l & 15) == 0 || l == A.nsteps) T.nan_scan();  // 18
+            if ((l & 15) == 0 || rem == 1) T.nan_scan();       // 18
         }
-        if (T.xi_writer()) A.theta[(size_t)(l - 1) * A.ntraj + traj] = (T.xi_real > 0) ? 1 : 0;
+        if (T.xi_writer()) *th = (T.xi_real > 0) ? 1 : 0;
     }
     if (G.tig == 0 && A.status) A.status[traj] = T.status;
 }

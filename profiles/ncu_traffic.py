@@ -23,5 +23,12 @@ def b(key):
 out = dict(kernel=M["Kernel Name"][0], child_steps=steps, child_pairs=pairs, dram_bytes_read=b("dram__bytes_read.sum"),
            dram_bytes_write=b("dram__bytes_write.sum"), duration_us_under_ncu=float(M["gpu__time_duration.sum"][0]),
            source=os.path.basename(rep))
+# the hardware's view of the same launch, next to the census-based roofline fraction of bench.py
+for key, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
+                  ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
+                  ("smsp__inst_executed.sum", "warp_instructions"),
+                  ("sass__inst_executed_local_loads", "local_loads"), ("sass__inst_executed_local_stores", "local_stores")):
+    if key in M:
+        out[name] = float(M[key][0])
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic_recross.json"), "w"), indent=1)
 print(out)
