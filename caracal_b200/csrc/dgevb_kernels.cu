@@ -16,6 +16,7 @@
 #include <cmath>
 #include <vector>
 #include "dgevb.cuh"
+#include "crcl_common.cuh"
 
 namespace crcl {
 
@@ -31,14 +32,14 @@ __device__ double ic_eval(int ty, const double p[4][3])
 {
     if (ty == 1) {  // dist.f90
         const double dx = p[1][0] - p[0][0], dy = p[1][1] - p[0][1], dz = p[1][2] - p[0][2];
-        return sqrt(dx * dx + (dy * dy + dz * dz));
+        return CRCL_SQRT(dx * dx + (dy * dy + dz * dz));
     } else if (ty == 2) {  // ang.f90: angle at atom 2
         double a[3], b[3];
         for (int c = 0; c < 3; c++) {
             a[c] = p[0][c] - p[1][c];
             b[c] = p[2][c] - p[1][c];
         }
-        return acos(d3(a, b) / (sqrt(d3(a, a)) * sqrt(d3(b, b))));
+        return CRCL_ACOS(d3(a, b) * CRCL_RSQRT(d3(a, a)) * CRCL_RSQRT(d3(b, b)));
     } else if (ty == 3) {  // dihed.f90
         double u[3], v[3], w[3], uxw[3], vxw[3];
         for (int c = 0; c < 3; c++) {
@@ -46,18 +47,18 @@ __device__ double ic_eval(int ty, const double p[4][3])
             v[c] = p[3][c] - p[2][c];
             w[c] = p[2][c] - p[1][c];
         }
-        const double ul = sqrt(d3(u, u)), vl = sqrt(d3(v, v)), wl = sqrt(d3(w, w));
+        const double iul = CRCL_RSQRT(d3(u, u)), ivl = CRCL_RSQRT(d3(v, v)), iwl = CRCL_RSQRT(d3(w, w));
         for (int c = 0; c < 3; c++) {
-            u[c] = u[c] / ul;
-            v[c] = v[c] / vl;
-            w[c] = w[c] / wl;
+            u[c] = u[c] * iul;
+            v[c] = v[c] * ivl;
+            w[c] = w[c] * iwl;
         }
         c3(u, w, uxw);
         c3(v, w, vxw);
         const double uw = d3(u, w), vw = d3(v, w);
-        double cv = d3(uxw, vxw) / (sqrt(1.0 - uw * uw) * sqrt(1.0 - vw * vw));
+        double cv = d3(uxw, vxw) * CRCL_RSQRT(1.0 - uw * uw) * CRCL_RSQRT(1.0 - vw * vw);
         cv = (cv >= 1.0) ? 1.0 : ((cv <= -1.0) ? -1.0 : cv);
-        return acos(cv);
+        return CRCL_ACOS(cv);
     } else {  // oop.f90
         double v41[3], v42[3], v43[3], c12[3], c23[3], c31[3], nv[3];
         for (int c = 0; c < 3; c++) {
@@ -65,17 +66,17 @@ __device__ double ic_eval(int ty, const double p[4][3])
             v42[c] = p[3][c] - p[1][c];
             v43[c] = p[3][c] - p[2][c];
         }
-        const double l1 = sqrt(d3(v41, v41)), l2 = sqrt(d3(v42, v42)), l3 = sqrt(d3(v43, v43));
+        const double i1 = CRCL_RSQRT(d3(v41, v41)), i2 = CRCL_RSQRT(d3(v42, v42)), i3 = CRCL_RSQRT(d3(v43, v43));
         for (int c = 0; c < 3; c++) {
-            v41[c] = v41[c] / l1;
-            v42[c] = v42[c] / l2;
-            v43[c] = v43[c] / l3;
+            v41[c] = v41[c] * i1;
+            v42[c] = v42[c] * i2;
+            v43[c] = v43[c] * i3;
         }
         c3(v41, v42, c12);
         c3(v42, v43, c23);
         c3(v43, v41, c31);
         for (int c = 0; c < 3; c++) nv[c] = c12[c] + c23[c] + c31[c];
-        return d3(v41, c23) / sqrt(d3(nv, nv));
+        return d3(v41, c23) * CRCL_RSQRT(d3(nv, nv));
     }
 }
 __device__ __forceinline__ void ic_load(const DgevbDev& P, const double* x, int i, int& ty, int& nact, int at[4],
@@ -109,12 +110,11 @@ __global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int na
     const int nat6 = P.nat6, n3 = 3 * natoms, lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int img = blockIdx.x * (blockDim.x >> 5) + wib;
     if (img >= nimg) return;                                  // whole warps leave together
-    const int per = 4 * nat6 + n3;
+    const int per = 4 * nat6;
     double* internal = sm + (size_t)wib * per;   // [nat6]
     double* gq = internal + nat6;                // [nat6]
     double* qq = gq + nat6;                      // [nat6]
     double* Bq = qq + nat6;                      // [nat6]
-    double* gv = Bq + nat6;                      // [3n]
     const double* x = xyz + (size_t)img * n3;
     for (int i = lane; i < nat6; i += 32) {
         int ty, nact, at[4];
@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int na
         internal[i] = ic_eval(ty, p);
         gq[i] = 0.0;
     }
-    for (int c = lane; c < n3; c += 32) gv[c] = 0.0;
     __syncwarp();
     const int mode = P.mode;
     const int block = 1 + nat6 + nat6 * (nat6 + 1) / 2, first = 1 + nat6;
@@ -136,7 +135,7 @@ __global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int na
         __syncwarp();
         double d_p = 0.0;
         for (int k = 0; k < nat6; k++) d_p += qq[k] * qq[k];   // every lane: same order as dot_product
-        const double expo = exp(-0.5 * al * d_p);
+        const double expo = CRCL_EXP(-0.5 * al * d_p);
         if (!(expo < P.g_thres)) {
             // offsets of the coefficient blocks of point j (sum_v12.f90 / sum_dv12.f90 index arithmetic)
             const double b0 = (mode == 1) ? b[j] : (mode == 2 ? b[(j - 1) * nat6 + j] : b[(j - 1) * (block - 1) + j]);
@@ -166,7 +165,21 @@ __global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int na
         }
         __syncwarp();
     }
-    // ---- numeric Wilson B (calc_wilson.f90:114-178) contracted with gq: gv = B^T gq ----
+    // ---- mixing (gradient.f90:497-537) and the numeric Wilson B (calc_wilson.f90:114-178) contracted with gq ----
+    // g = 1/2 (g1 + g2 - [ediff (g1 - g2) + 2 B^T gq] / root2) is linear in the Wilson term: lane c first stores the part
+    // without it, then every finite-difference slot adds its share -(dq_i/dx_c) gq_i / root2 straight into g with a
+    // fire-and-forget FP64 reduction (RED.ADD at the L2).  The first version accumulated B^T gq in shared memory, where an
+    // FP64 atomicAdd is a compare-and-swap loop: 45 % of a DG-EVB step went there (profiles/r2q_launches_c4.csv).
+    const double e1 = V1[img], e2 = V2[img];
+    const double ediff = e1 - e2, off4 = 4.0 * V12;
+    const bool unset = (ediff * ediff + off4 < 0.0);
+    const double root2 = unset ? 1.0 : sqrt(ediff * ediff + off4);
+    const double iroot2 = unset ? 0.0 : 1.0 / root2;
+    const double* g1 = G1 + (size_t)img * n3;
+    const double* g2 = G2 + (size_t)img * n3;
+    double* g = G + (size_t)img * n3;
+    for (int c = lane; c < n3; c += 32) g[c] = 0.5 * (g1[c] + g2[c] - ediff * (g1[c] - g2[c]) * iroot2);
+    __syncwarp();   // the stores above are ordered before the reductions of the other lanes below
     for (int w = lane; w < nat6 * 12; w += 32) {
         const int i = w / 12, slot = w - 12 * i;
         int ty, nact, at[4];
@@ -175,27 +188,22 @@ __global__ void __launch_bounds__(128) dgevb_mix_kernel(const DgevbDev P, int na
         const int a = slot / 3, m = slot - 3 * a;
         if (a < nact) {
             const double shift = 0.001;
-            p[a][m] = p[a][m] - shift;
-            // an atom may appear once only in a coordinate definition, so perturbing slot a is
-            // perturbing atom at[a] as the reference does
-            const double lo = ic_eval(ty, p);
-            p[a][m] = p[a][m] + 2 * shift;
-            const double hi = ic_eval(ty, p);
-            atomicAdd(&gv[3 * at[a] + m], (hi - lo) / (2 * shift) * gq[i]);
+            // an atom may appear once only in a coordinate definition, so perturbing slot a is perturbing atom at[a] as the
+            // reference does: x - shift, then (x - shift) + 2 shift.  The slot is picked by selects, not by indexing p
+            // with the run-time (a, m), which would put the twelve coordinates in local memory.
+            double pl[4][3], ph[4][3];
+#pragma unroll
+            for (int aa = 0; aa < 4; aa++)
+#pragma unroll
+                for (int mm = 0; mm < 3; mm++) {
+                    const bool hit = (aa == a) && (mm == m);
+                    pl[aa][mm] = hit ? p[aa][mm] - shift : p[aa][mm];
+                    ph[aa][mm] = hit ? pl[aa][mm] + 2 * shift : p[aa][mm];
+                }
+            const double lo = ic_eval(ty, pl);
+            const double hi = ic_eval(ty, ph);
+            atomicAdd(&g[3 * at[a] + m], -((hi - lo) / (2 * shift) * gq[i]) * iroot2);
         }
-    }
-    __syncwarp();
-    const double e1 = V1[img], e2 = V2[img];
-    const double ediff = e1 - e2, off4 = 4.0 * V12;
-    const bool unset = (ediff * ediff + off4 < 0.0);
-    const double root2 = unset ? 1.0 : sqrt(ediff * ediff + off4);
-    const double* g1 = G1 + (size_t)img * n3;
-    const double* g2 = G2 + (size_t)img * n3;
-    double* g = G + (size_t)img * n3;
-    for (int c = lane; c < n3; c += 32) {
-        const double deldiscr = ediff * (g1[c] - g2[c]) + 2.0 * gv[c];
-        const double delsqrt = unset ? 0.0 : deldiscr / root2;
-        g[c] = 0.5 * (g1[c] + g2[c] - delsqrt);
     }
     if (lane == 0) {
         const double root = (0.5 * ediff) * (0.5 * ediff) + V12;
@@ -207,7 +215,7 @@ cudaError_t dgevb_mix(const DgevbDev* P, int natoms, const double* xyz, int nimg
                       const double* V2, const double* G2, double* V, double* G, cudaStream_t s)
 {
     if (nimg <= 0) return cudaSuccess;
-    const size_t per = sizeof(double) * (4 * (size_t)P->nat6 + 3 * (size_t)natoms);
+    const size_t per = sizeof(double) * 4 * (size_t)P->nat6;
     int wpb = 4;                                  // warps (images) per CTA
     while (wpb > 1 && per * wpb > 96 * 1024) wpb >>= 1;
     const size_t smem = per * wpb;
