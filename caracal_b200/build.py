@@ -59,7 +59,20 @@ def _compile(src):
 
 
 def build(force=False, verbose=False):
+    """Safe to call from every rank of a multi-process job at once: an exclusive file lock serialises the callers (the
+    first one compiles, the others find everything up to date), and the library is linked to a temporary name and
+    renamed into place, so a process that is loading it never sees a half-written file."""
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     srcs = _sources()
     if force:
         for s in srcs:
@@ -74,13 +87,15 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in srcs]
     if rebuilt or not os.path.exists(LIB):
         nvcc = os.environ.get("NVCC", "nvcc")
+        tmp = LIB + ".tmp.%d" % os.getpid()
         # cuFFT (the FFTW of ewald_recip.f90) from the toolkit; rpath so that the library also loads in a
         # process that has not imported torch's bundled copy first
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + \
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + \
               ["-lcufft", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+        os.replace(tmp, LIB)
         with open(os.path.join(HERE, "build.log"), "a" if not force else "w") as f:
             f.write("\n".join(l for l in logs if l))
     if verbose:

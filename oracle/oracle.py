@@ -15,7 +15,17 @@ PES = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7
 
 
 def build(force=False):
-    """Compile the C restatement (gcc; see oracle/Makefile)."""
+    """Compile the C restatement (gcc; see oracle/Makefile).  Serialised by a file lock: several ranks may call it."""
+    import fcntl
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force):
     need = force or not all(os.path.exists(os.path.join(HERE, f)) for f in ("liboracle.so", "liboracle_exact.so"))
     if not need:
         so = os.path.getmtime(os.path.join(HERE, "liboracle.so"))
