@@ -88,10 +88,8 @@ def _build_locked(force, verbose):
     if rebuilt or not os.path.exists(LIB):
         nvcc = os.environ.get("NVCC", "nvcc")
         tmp = LIB + ".tmp.%d" % os.getpid()
-        # cuFFT (the FFTW of ewald_recip.f90) from the toolkit; rpath so that the library also loads in a
-        # process that has not imported torch's bundled copy first
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs + \
-              ["-lcufft", "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
+        # no library besides the CUDA runtime: the FFT of ewald_recip.f90 is a kernel of this library too
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n" + res.stdout + res.stderr)

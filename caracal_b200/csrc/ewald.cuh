@@ -3,19 +3,24 @@
 // with the set-up quantities of set_periodic.f90:114-231 received as tables.
 #pragma once
 #include <cuda_runtime.h>
-#include <cufft.h>
 #include "../../include/caracal_gpu.h"
 
 namespace crcl {
+
+struct FftPlan {
+    int nfac;
+    int r[16];
+};
 
 struct EwaldDev {
     int nfft, bsorder;
     double box[3], a_ewald;
     double* bsmod;            // [3][nfft]
     // grow-only work space
-    cufftHandle plan;
-    int plan_batch;           // batch the plan was made for (0: none)
-    cufftDoubleComplex* grid; // [nimg][nfft][nfft][nfft], x fastest
+    FftPlan plan;             // factors of nfft, in the order the Stockham stages take them
+    int fft_L;                // lines per CTA of ew_fft_lines_kernel
+    double2* tw;              // [2][nfft]: e^{-2 pi i t/nfft} and conjugates
+    double2* grid;            // [nimg][nfft][nfft][nfft], x fastest
     size_t grid_cap;
     double* theta;            // [nimg*n][3][5][2]: B-spline values and first derivatives
     int* igrid;               // [nimg*n][3]

@@ -4,10 +4,11 @@
 //   1. ew_spread_kernel     fractional coordinates, order-5 B-splines (bsplgen.f90, values and first
 //                           derivatives) and charge spreading onto the nfft^3 grid (:110-330; the
 //                           chunk tables of setchunk.f90 / ewald_adjust.f90 reduce to one chunk)
-//   2. cuFFT Z2Z forward    dfftw_execute_dft(planf) (:369); cuFFT is a library FFT like FFTW there
+//   2. ew_fft_lines_kernel  dfftw_execute_dft(planf) (:369): the complex 3-D DFT as three sweeps of 1-D lines, each
+//                           line a mixed-radix Stockham transform in shared memory (below); no library FFT
 //   3. ew_influence_kernel  exp(-pi^2 h^2 / a^2) / (pi V h^2 B(m)) on every grid point but the
 //                           origin, energy = 1/2 sum expterm |S|^2 (:371-415)
-//   4. cuFFT Z2Z inverse    dfftw_execute_dft(planb) (:417), unnormalised like FFTW
+//   4. ew_fft_lines_kernel  dfftw_execute_dft(planb) (:417), sign +1, unnormalised like FFTW
 //   5. ew_gather_kernel     gradient of every site from the convolved grid (:419-468)
 // The reference never reaches this routine (ff_nonb.f90:337 sets ewald=.false.): it is
 // exported as its own entry point (crcl_ewald_recip) and validated against the oracle's restatement
@@ -68,7 +69,7 @@ __device__ __forceinline__ int wrap(int g0, int it, int nfft)
 
 __global__ void __launch_bounds__(128) ew_spread_kernel(int n, int natot, int nfft, double rx, double ry, double rz,
                                                         const double* __restrict__ xyz, const double* __restrict__ q,
-                                                        cufftDoubleComplex* __restrict__ grid,
+                                                        double2* __restrict__ grid,
                                                         double* __restrict__ theta, int* __restrict__ igrid)
 {
     const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(128) ew_spread_kernel(int n, int natot, int nf
         }
         const double term = (v0 * q[at]) * u0;
         const int k = wrap(g0[2], kz, nfft), j = wrap(g0[1], jy, nfft);
-        cufftDoubleComplex* row = grid + (((size_t)img * nfft + k) * nfft + j) * nfft;
+        double2* row = grid + (((size_t)img * nfft + k) * nfft + j) * nfft;
 #pragma unroll
         for (int i = 0; i < BSO; i++) atomicAdd(&row[wrap(g0[0], i, nfft)].x, term * th[0][i]);
     }
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128) ew_spread_kernel(int n, int natot, int nf
 __global__ void __launch_bounds__(256) ew_influence_kernel(int nfft, int nimg, double rx, double ry, double rz,
                                                            double pterm, double volterm,
                                                            const double* __restrict__ bsmod,
-                                                           cufftDoubleComplex* __restrict__ grid,
+                                                           double2* __restrict__ grid,
                                                            double* __restrict__ energy)
 {
     const size_t npoint = (size_t)nfft * nfft * nfft;
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(256) ew_influence_kernel(int nfft, int nimg, d
         const double hsq = h1 * h1 + h2 * h2 + h3 * h3;
         const double term = -pterm * hsq;
         double expterm = 0.0;
-        cufftDoubleComplex* p = grid + (size_t)img * npoint + t;
-        cufftDoubleComplex v = *p;
+        double2* p = grid + (size_t)img * npoint + t;
+        double2 v = *p;
         if (term > -50.0) {
             const double denom = volterm * hsq * bsmod[k1] * bsmod[nfft + k2] * bsmod[2 * nfft + k3];
             expterm = exp(term) / denom;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) ew_influence_kernel(int nfft, int nimg, d
 
 __global__ void __launch_bounds__(128) ew_gather_kernel(int n, int natot, int nfft, double rx, double ry, double rz,
                                                         const double* __restrict__ q,
-                                                        const cufftDoubleComplex* __restrict__ grid,
+                                                        const double2* __restrict__ grid,
                                                         const double* __restrict__ theta, const int* __restrict__ igrid,
                                                         double* __restrict__ grad)
 {
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(128) ew_gather_kernel(int n, int natot, int nf
         const int kz = lane / BSO, jy = lane - kz * BSO;
         const double t3 = t[(2 * BSO + kz) * 2], dt3 = dn * t[(2 * BSO + kz) * 2 + 1];
         const double t2 = t[(BSO + jy) * 2], dt2 = dn * t[(BSO + jy) * 2 + 1];
-        const cufftDoubleComplex* row =
+        const double2* row =
             grid + (((size_t)img * nfft + wrap(g0z, kz, nfft)) * nfft + wrap(g0y, jy, nfft)) * nfft;
 #pragma unroll
         for (int i = 0; i < BSO; i++) {
@@ -192,6 +193,113 @@ __global__ void __launch_bounds__(128) ew_gather_kernel(int n, int natot, int nf
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Complex 3-D DFT of the charge grid (the two dfftw_execute_dft calls, ewald_recip.f90:369,417): three sweeps, one
+// per axis; a CTA owns a tile of L lines that are adjacent in memory along x (for the y and z sweeps: L consecutive x
+// at one (z, img) or (y, img), so a global access covers L*16 contiguous bytes; for the x sweep: L consecutive
+// lines), keeps them in shared memory as sh[t*LP + line] and runs a decimation-in-frequency Stockham autosort
+// transform over the factors of nfft (any factorisation: a thread produces ONE output of a radix-r stage from its r
+// inputs, twiddles from a table of the nfft-th roots of unity computed in double on the host).  HBM traffic: one read
+// and one write of the grid per sweep.
+__global__ void __launch_bounds__(256) ew_fft_lines_kernel(double2* __restrict__ grid, int nf, int nimg, int dim, int L,
+                                                           int LP, const double2* __restrict__ tw_g, FftPlan plan)
+{
+    extern __shared__ double2 ew_sh[];
+    double2* tw = ew_sh;                       // [nf]
+    double2* x = ew_sh + nf;                   // [nf][LP]
+    double2* y = x + (size_t)nf * LP;          // [nf][LP]
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t nf2 = (size_t)nf * nf;
+    // tile -> first element and number of valid lines
+    size_t base, lstride, tstride;
+    int nl;
+    if (dim == 0) {
+        const size_t line0 = (size_t)blockIdx.x * L;          // lines of the whole batch are consecutive
+        const size_t nlines = nf2 * nimg;
+        if (line0 >= nlines) return;
+        nl = (int)((nlines - line0 < (size_t)L) ? nlines - line0 : L);
+        base = line0 * nf;
+        lstride = nf;
+        tstride = 1;
+    } else {
+        const int tiles_i = (nf + L - 1) / L;
+        const int i0 = (blockIdx.x % tiles_i) * L, o = blockIdx.x / tiles_i;   // o = z (dim 1) or y (dim 2)
+        nl = (nf - i0 < L) ? nf - i0 : L;
+        base = (dim == 1) ? (size_t)o * nf2 + i0 : (size_t)o * nf + i0;
+        lstride = 1;
+        tstride = (dim == 1) ? (size_t)nf : nf2;
+    }
+    if (dim != 0) base += (size_t)blockIdx.y * nf2 * nf;       // image
+    for (int t = tid; t < nf; t += nt) tw[t] = tw_g[t];
+    if (dim == 0) {
+        for (int e = tid; e < nl * nf; e += nt) {
+            const int line = e / nf, t = e - line * nf;
+            x[(size_t)t * LP + line] = grid[base + (size_t)line * lstride + t];
+        }
+    } else {
+        for (int e = tid; e < nl * nf; e += nt) {
+            const int t = e / nl, line = e - t * nl;
+            x[(size_t)t * LP + line] = grid[base + (size_t)t * tstride + line];
+        }
+    }
+    __syncthreads();
+    int n = nf, st = 1;
+    for (int f = 0; f < plan.nfac; f++) {
+        const int r = plan.r[f], m = n / r, wr = nf / r;
+        for (int e = tid; e < nl * nf; e += nt) {
+            const int o = e / nl, line = e - o * nl;
+            const int q = o % st, tt = o / st, j = tt % r, pp = tt / r;
+            double re = 0.0, im = 0.0;
+            int jk = 0;                                        // (j*k) mod r
+            for (int k = 0; k < r; k++) {
+                const double2 a = x[(size_t)(q + st * (pp + k * m)) * LP + line];
+                const double2 w = tw[jk * wr];
+                re += a.x * w.x - a.y * w.y;
+                im += a.x * w.y + a.y * w.x;
+                jk += j;
+                if (jk >= r) jk -= r;
+            }
+            const double2 w = tw[pp * j * st];                 // < nf: pp < m, j < r, m*r*st = nf
+            y[(size_t)o * LP + line] = make_double2(re * w.x - im * w.y, re * w.y + im * w.x);
+        }
+        __syncthreads();
+        double2* z = x;
+        x = y;
+        y = z;
+        n = m;
+        st *= r;
+    }
+    if (dim == 0) {
+        for (int e = tid; e < nl * nf; e += nt) {
+            const int line = e / nf, t = e - line * nf;
+            grid[base + (size_t)line * lstride + t] = x[(size_t)t * LP + line];
+        }
+    } else {
+        for (int e = tid; e < nl * nf; e += nt) {
+            const int t = e / nl, line = e - t * nl;
+            grid[base + (size_t)t * tstride + line] = x[(size_t)t * LP + line];
+        }
+    }
+}
+
+// one unnormalised 3-D transform of every image's grid; sgn = -1 (FFTW_FORWARD) or +1 (FFTW_BACKWARD)
+static int ew_fft3(EwaldDev* E, int nimg, int sgn, cudaStream_t s, long long* launches)
+{
+    const int nf = E->nfft;
+    const double2* tw = E->tw + (sgn < 0 ? 0 : nf);
+    for (int dim = 0; dim < 3; dim++) {
+        const int L = E->fft_L, LP = L | 1;
+        const size_t shm = ((size_t)nf + 2 * (size_t)nf * LP) * sizeof(double2);
+        // x sweep: the lines of the whole batch are consecutive; y / z sweeps: blockIdx.y is the image
+        const dim3 grid = (dim == 0) ? dim3((unsigned)(((size_t)nf * nf * nimg + L - 1) / L), 1)
+                                     : dim3((unsigned)(nf * ((nf + L - 1) / L)), nimg);
+        ew_fft_lines_kernel<<<grid, 256, shm, s>>>(E->grid, nf, nimg, dim, L, LP, tw, E->plan);
+        if (launches) *launches += 1;
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 1;
+}
+
 int ewald_recip(EwaldDev* E, int n, int nimg, const double* d_xyz, const double* d_q, double* d_energy, double* d_grad,
                 cudaStream_t s, long long* launches, const char** err)
 {
@@ -206,7 +314,7 @@ int ewald_recip(EwaldDev* E, int n, int nimg, const double* d_xyz, const double*
         if (E->grid) cudaFree(E->grid);
         E->grid = nullptr;
         E->grid_cap = 0;
-        if (cudaMalloc(&E->grid, npoint * nimg * sizeof(cufftDoubleComplex)) != cudaSuccess) {
+        if (cudaMalloc(&E->grid, npoint * nimg * sizeof(double2)) != cudaSuccess) {
             *err = "crcl_ewald_recip: grid allocation failed";
             return CRCL_ENOMEM;
         }
@@ -225,43 +333,28 @@ int ewald_recip(EwaldDev* E, int n, int nimg, const double* d_xyz, const double*
         }
         E->atom_cap = natot;
     }
-    if (E->plan_batch != nimg) {
-        if (E->plan_batch) cufftDestroy(E->plan);
-        E->plan_batch = 0;
-        int dims[3] = {nfft, nfft, nfft};
-        if (cufftPlanMany(&E->plan, 3, dims, nullptr, 1, (int)npoint, nullptr, 1, (int)npoint, CUFFT_Z2Z, nimg) !=
-            CUFFT_SUCCESS) {
-            *err = "crcl_ewald_recip: cufftPlanMany failed";
-            return CRCL_ECUDA;
-        }
-        E->plan_batch = nimg;
-    }
-    if (cufftSetStream(E->plan, s) != CUFFT_SUCCESS) {
-        *err = "crcl_ewald_recip: cufftSetStream failed";
-        return CRCL_ECUDA;
-    }
     const double volbox = E->box[0] * E->box[1] * E->box[2];
     // recip(1,1) = (br2*cr3)/volbox etc. (ewald_recip.f90:97-105): the division is kept as written
     const double rx = (E->box[1] * E->box[2]) / volbox, ry = (E->box[2] * E->box[0]) / volbox,
                  rz = (E->box[0] * E->box[1]) / volbox;
     const double PI = 3.1415926535897932384626433832795029;
     const double pterm = (PI / E->a_ewald) * (PI / E->a_ewald), volterm = PI * volbox;
-    cudaMemsetAsync(E->grid, 0, npoint * nimg * sizeof(cufftDoubleComplex), s);
+    cudaMemsetAsync(E->grid, 0, npoint * nimg * sizeof(double2), s);
     cudaMemsetAsync(d_energy, 0, nimg * sizeof(double), s);
     const unsigned wblocks = (unsigned)((natot * 32 + 127) / 128);
     ew_spread_kernel<<<wblocks, 128, 0, s>>>(n, (int)natot, nfft, rx, ry, rz, d_xyz, d_q, E->grid, E->theta, E->igrid);
-    if (cufftExecZ2Z(E->plan, E->grid, E->grid, CUFFT_FORWARD) != CUFFT_SUCCESS) {
-        *err = "crcl_ewald_recip: forward FFT failed";
+    if (ew_fft3(E, nimg, -1, s, launches)) {
+        *err = "crcl_ewald_recip: forward FFT launch failed";
         return CRCL_ECUDA;
     }
     ew_influence_kernel<<<dim3((unsigned)((npoint + 255) / 256), nimg), 256, 0, s>>>(nfft, nimg, rx, ry, rz, pterm, volterm,
                                                                                     E->bsmod, E->grid, d_energy);
-    if (cufftExecZ2Z(E->plan, E->grid, E->grid, CUFFT_INVERSE) != CUFFT_SUCCESS) {
-        *err = "crcl_ewald_recip: backward FFT failed";
+    if (ew_fft3(E, nimg, +1, s, launches)) {
+        *err = "crcl_ewald_recip: backward FFT launch failed";
         return CRCL_ECUDA;
     }
     ew_gather_kernel<<<wblocks, 128, 0, s>>>(n, (int)natot, nfft, rx, ry, rz, d_q, E->grid, E->theta, E->igrid, d_grad);
-    if (launches) *launches += 3;   // own kernels; the two FFTs are library launches
+    if (launches) *launches += 3;   // spread, influence, gather; ew_fft3 counts its six sweeps
     if (cudaGetLastError() != cudaSuccess) {
         *err = "crcl_ewald_recip: kernel launch failed";
         return CRCL_ECUDA;
@@ -299,6 +392,48 @@ int ewald_upload(const crcl_ewald_params* P, EwaldDev** out, const char** err)
         *err = "SPME: device allocation / upload failed";
         return CRCL_ENOMEM;
     }
+    // roots of unity e^{-2 pi i t / nfft} (forward) and their conjugates (backward), the factors of nfft (largest
+    // first: fewer stages), and the number of lines a CTA holds in its two shared-memory line buffers
+    {
+        const int nf = P->nfft;
+        const double PI = 3.1415926535897932384626433832795029;
+        std::vector<double2> tw(2 * (size_t)nf);
+        for (int t = 0; t < nf; t++) {
+            const double a = 2.0 * PI * (double)t / (double)nf;
+            tw[t] = make_double2(cos(a), -sin(a));
+            tw[nf + t] = make_double2(cos(a), sin(a));
+        }
+        int rest = nf, nfac = 0;
+        const int pref[4] = {5, 4, 3, 2};
+        for (int i = 0; i < 4; i++)
+            while (rest % pref[i] == 0 && nfac < 16) {
+                E->plan.r[nfac++] = pref[i];
+                rest /= pref[i];
+            }
+        for (int r = 7; rest > 1 && nfac < 16; r += 2)
+            while (rest % r == 0 && nfac < 16) {
+                E->plan.r[nfac++] = r;
+                rest /= r;
+            }
+        if (rest != 1) {
+            ewald_free(E);
+            *err = "SPME: nfft has more than 16 prime factors";
+            return CRCL_EINVAL;
+        }
+        E->plan.nfac = nfac;
+        int L = 8;
+        while (L > 1 && ((size_t)nf + 2 * (size_t)nf * (L | 1)) * sizeof(double2) > 200 * 1024) L >>= 1;
+        E->fft_L = L;
+        const size_t shm = ((size_t)nf + 2 * (size_t)nf * (L | 1)) * sizeof(double2);
+        if (cudaFuncSetAttribute(ew_fft_lines_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm) !=
+                cudaSuccess ||
+            cudaMalloc(&E->tw, tw.size() * sizeof(double2)) != cudaSuccess ||
+            cudaMemcpy(E->tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice) != cudaSuccess) {
+            ewald_free(E);
+            *err = "SPME: FFT set-up failed";
+            return CRCL_ENOMEM;
+        }
+    }
     *out = E;
     return CRCL_OK;
 }
@@ -306,8 +441,8 @@ int ewald_upload(const crcl_ewald_params* P, EwaldDev** out, const char** err)
 void ewald_free(EwaldDev* E)
 {
     if (!E) return;
-    if (E->plan_batch) cufftDestroy(E->plan);
     cudaFree(E->bsmod);
+    cudaFree(E->tw);
     cudaFree(E->grid);
     cudaFree(E->theta);
     cudaFree(E->igrid);
