@@ -83,6 +83,41 @@ def ch4cn_ts():
     return q / BOHR
 
 
+def _nh3_axes(theta_deg):
+    """three unit vectors with mutual angle theta, on a cone around +z"""
+    sa = np.sqrt((1.0 - np.cos(np.deg2rad(theta_deg))) / 1.5)
+    ca = np.sqrt(1.0 - sa * sa)
+    return np.array([[sa * np.cos(f), sa * np.sin(f), ca] for f in np.deg2rad([0.0, 120.0, 240.0])])
+
+
+def clnh3_ts():
+    """NH3 + Cl -> NH2 + HCl in its (late) saddle region: pyramidal NH3 (r = 1.014 A, H-N-H 107 deg) with the hydrogen in
+    flight (atom 1) at 1.33 A from N and the chlorine 1.40 A beyond it on the N-H axis.  Atom order H, N, H, H, Cl
+    (egrad_clnh3.f:85-91)."""
+    u = _nh3_axes(107.0)
+    q = np.zeros((5, 3))
+    q[0] = u[0] * 1.33
+    q[2], q[3] = u[1] * 1.014, u[2] * 1.014
+    q[4] = u[0] * (1.33 + 1.40)
+    return q / BOHR
+
+
+def nh3oh_ts():
+    """NH3 + OH -> NH2 + H2O in its (early) saddle region: pyramidal NH3 with the hydrogen in flight (atom 1) at 1.15 A,
+    the oxygen 1.30 A beyond it, the hydroxyl hydrogen at 0.97 A and 100 deg to the O-H' axis.  Atom order
+    H, N, H, H, O, H(O) (egrad_nh3oh.f BLOCK DATA: nnc = 2, nnb = 5, nnh = 1, 3, 4, nno = 6)."""
+    u = _nh3_axes(107.0)
+    q = np.zeros((6, 3))
+    q[0] = u[0] * 1.15
+    q[2], q[3] = u[1] * 1.014, u[2] * 1.014
+    q[4] = u[0] * (1.15 + 1.30)
+    e2 = np.cross(u[0], [0.0, 1.0, 0.0])
+    e2 /= np.linalg.norm(e2)
+    th = np.deg2rad(100.0)
+    q[5] = q[4] + 0.97 * (np.cos(th) * (-u[0]) + np.sin(th) * e2)
+    return q / BOHR
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -102,6 +137,10 @@ SYSTEMS = {
                    mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
     "ch4cn": dict(pes="ch4cn", symbols=["H", "C", "H", "H", "H", "C", "N"], ts=ch4cn_ts,
                   mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6, 7]], dist_inf=16.0)),
+    "clnh3": dict(pes="clnh3", symbols=["H", "N", "H", "H", "CL"], ts=clnh3_ts,
+                  mecha=dict(bond_form=[[1, 5]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4], [5]], dist_inf=16.0)),
+    "nh3oh": dict(pes="nh3oh", symbols=["H", "N", "H", "H", "O", "H"], ts=nh3oh_ts,
+                  mecha=dict(bond_form=[[1, 5]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4], [5, 6]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

@@ -36,6 +36,14 @@ void oracle_egrad_geh4oh_real(const real *q, int natoms, int nbeads, real *V, re
 void oracle_geh4oh_parts_real(const real *q21, real parts[3], real *V);
 void oracle_egrad_ch4cn_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_ch4cn_parts_real(const real *q21, real parts[3], real *V);
+void oracle_egrad_clnh3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_clnh3_parts_real(const real *q15, real parts[3], real *V);
+void oracle_clnh3_parts_grad_real(const real *q15, real parts[3], real *gparts);
+void clnh3_parts_frozen_real(const real *q15, double r0ch_frozen, real parts[3], real *V);
+void oracle_egrad_nh3oh_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_nh3oh_parts_real(const real *q18, real parts[3], real *V);
+void oracle_nh3oh_parts_grad_real(const real *q18, real parts[3], real *gparts);
+void nh3oh_parts_frozen_real(const real *q18, double r0ch_frozen, real parts[3], real *V);
 void oracle_brh2_pot_real(const real R[3], real *V, real dVdR[3], int *ierr);
 
 #ifdef __cplusplus

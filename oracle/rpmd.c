@@ -260,6 +260,12 @@ void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g)
     case ORC_PES_CH4CN:
         oracle_egrad_ch4cn_real(xyz, s->natoms, 1, e, g, &info);
         break;
+    case ORC_PES_CLNH3:
+        oracle_egrad_clnh3_real(xyz, s->natoms, 1, e, g, &info);
+        break;
+    case ORC_PES_NH3OH:
+        oracle_egrad_nh3oh_real(xyz, s->natoms, 1, e, g, &info);
+        break;
     default:
         *e = 0.0;
         memset(g, 0, sizeof(double) * 3 * s->natoms);

@@ -22,6 +22,8 @@
 #define ORC_PES_CH4OH 6
 #define ORC_PES_GEH4OH 7
 #define ORC_PES_CH4CN 8
+#define ORC_PES_CLNH3 9
+#define ORC_PES_NH3OH 13
 
 #ifdef __cplusplus
 extern "C" {
