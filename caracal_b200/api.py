@@ -459,7 +459,8 @@ class RPMD:
 _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"],
              _l.PES_BRH2: ["H", "BR", "H"], _l.PES_O3: ["O", "O", "O"],
              _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"], _l.PES_GEH4OH: ["H", "GE", "H", "H", "H", "O", "H"],
-             _l.PES_CH4CN: ["H", "C", "H", "H", "H", "C", "N"]}
+             _l.PES_CH4CN: ["H", "C", "H", "H", "H", "C", "N"],
+             _l.PES_CLNH3: ["H", "N", "H", "H", "CL"], _l.PES_NH3OH: ["H", "N", "H", "H", "O", "H"]}
 _egrad_handles = {}
 
 
@@ -502,6 +503,14 @@ def egrad_geh4oh(q, Natoms=7, Nbeads=None):
 
 def egrad_ch4cn(q, Natoms=7, Nbeads=None):
     return egrad(_l.PES_CH4CN, q, Natoms, Nbeads)
+
+
+def egrad_clnh3(q, Natoms=5, Nbeads=None):
+    return egrad(_l.PES_CLNH3, q, Natoms, Nbeads)
+
+
+def egrad_nh3oh(q, Natoms=6, Nbeads=None):
+    return egrad(_l.PES_NH3OH, q, Natoms, Nbeads)
 
 
 def egrad_ch4h(q, Natoms=6, Nbeads=None):

@@ -14,6 +14,7 @@
 #include "pes_ch4h.cuh"
 #include "pes_brh2.cuh"
 #include "pes_o3.cuh"
+#include "pes_nh3x.cuh"
 #include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
@@ -282,7 +283,7 @@ __global__ void reduce_kappa_kernel(const unsigned char* theta, const double* we
 // ---- dispatch --------------------------------------------------------------------------------
 static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode = 0)
 {
-    static const traj_launch_fn table[8][3] = {
+    static const traj_launch_fn table[10][3] = {
         {launch_h3_verlet, launch_h3_mdinit, launch_h3_recross},
         {launch_oh3_verlet, launch_oh3_mdinit, launch_oh3_recross},
         {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross},
@@ -290,7 +291,9 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
         {launch_o3_verlet, launch_o3_mdinit, launch_o3_recross},
         {launch_ch4oh_verlet, launch_ch4oh_mdinit, launch_ch4oh_recross},
         {launch_geh4oh_verlet, launch_geh4oh_mdinit, launch_geh4oh_recross},
-        {launch_ch4cn_verlet, launch_ch4cn_mdinit, launch_ch4cn_recross}};
+        {launch_ch4cn_verlet, launch_ch4cn_mdinit, launch_ch4cn_recross},
+        {launch_clnh3_verlet, launch_clnh3_mdinit, launch_clnh3_recross},
+        {launch_nh3oh_verlet, launch_nh3oh_mdinit, launch_nh3oh_recross}};
     int row;
     switch (h->pes) {
     case CRCL_PES_H3: row = 0; break;
@@ -301,6 +304,8 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
     case CRCL_PES_CH4OH: row = 5; break;
     case CRCL_PES_GEH4OH: row = 6; break;
     case CRCL_PES_CH4CN: row = 7; break;
+    case CRCL_PES_CLNH3: row = 8; break;
+    case CRCL_PES_NH3OH: row = 9; break;
     default: return fail(h, CRCL_ENOSUP, "no device trajectory kernel for this PES id");
     }
     if (A.ntraj <= 0) return CRCL_OK;
@@ -353,6 +358,8 @@ static int pes_natoms(int pes)
     case CRCL_PES_CH4OH: return 7;
     case CRCL_PES_GEH4OH: return 7;
     case CRCL_PES_CH4CN: return 7;
+    case CRCL_PES_CLNH3: return 5;
+    case CRCL_PES_NH3OH: return 6;
     }
     return -1;
 }
@@ -1431,6 +1438,8 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_CH4OH: egrad_kernel<PesCH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_GEH4OH: egrad_kernel<PesGeH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_CH4CN: egrad_kernel<PesCH4CN><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_CLNH3: egrad_kernel<PesClNH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_NH3OH: egrad_kernel<PesNH3OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     default: return fail(h, CRCL_ENOSUP, "unknown PES id");
     }
     if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);

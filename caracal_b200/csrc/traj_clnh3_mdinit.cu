@@ -1,0 +1,6 @@
+// traj_clnh3_mdinit.cu -- instantiates the mdinit trajectory kernels for the "clnh3" surface.
+#include "pes_nh3x.cuh"
+#include "traj_inst.cuh"
+namespace crcl {
+CRCL_DECLARE_TRAJ(launch_clnh3_mdinit) { return launch_traj_pes<PesClNH3, K_MDINIT>(nbeads, A, bias_mode, nose_q, s, nosup); }
+}  // namespace crcl

@@ -86,5 +86,11 @@ CRCL_DECLARE_TRAJ(launch_geh4oh_recross);
 CRCL_DECLARE_TRAJ(launch_ch4cn_verlet);
 CRCL_DECLARE_TRAJ(launch_ch4cn_mdinit);
 CRCL_DECLARE_TRAJ(launch_ch4cn_recross);
+CRCL_DECLARE_TRAJ(launch_clnh3_verlet);
+CRCL_DECLARE_TRAJ(launch_clnh3_mdinit);
+CRCL_DECLARE_TRAJ(launch_clnh3_recross);
+CRCL_DECLARE_TRAJ(launch_nh3oh_verlet);
+CRCL_DECLARE_TRAJ(launch_nh3oh_mdinit);
+CRCL_DECLARE_TRAJ(launch_nh3oh_recross);
 
 }  // namespace crcl

@@ -40,6 +40,9 @@ extern "C" {
 #define CRCL_PES_CH4OH 6 /* "ch4oh" egrad_ch4oh.f Espinosa-Garcia/Corchado CH4 + OH, atoms H,C,H,H,H,O,H */
 #define CRCL_PES_GEH4OH 7 /* "geh4oh" egrad_geh4oh.f GeH4 + OH, atoms H,Ge,H,H,H,O,H */
 #define CRCL_PES_CH4CN 8 /* "ch4cn" egrad_ch4cn.f CH4 + CN (Espinosa-Garcia, Rangel, Suleimanov 2017), atoms H,C,H,H,H,C,N */
+#define CRCL_PES_CLNH3 9 /* "clnh3" egrad_clnh3.f NH3 + Cl (Monge-Palacios, Rangel, Corchado, Espinosa-Garcia 2012), atoms H,N,H,H,Cl */
+#define CRCL_PES_NH3OH 13 /* "nh3oh" egrad_nh3oh.f NH3 + OH (Monge-Palacios, Rangel, Espinosa-Garcia 2013), atoms H,N,H,H,O,H; the gradient is the
+                             reference's own forward difference of the energy (POT_nh3oh :283-296) */
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
                              crcl_set_qmdff2, crcl_set_dgevb */

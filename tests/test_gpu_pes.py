@@ -18,7 +18,9 @@ pytestmark = pytest.mark.gpu
                                           ("brh2", 0.15, 100000), ("brh2", 0.5, 30000), ("o3", 0.15, 100000), ("o3", 0.4, 30000),
                                           ("ch4oh", 0.15, 100000), ("ch4oh", 0.4, 30000),
                                           ("geh4oh", 0.15, 100000), ("geh4oh", 0.4, 30000),
-                                          ("ch4cn", 0.15, 100000), ("ch4cn", 0.4, 30000)])
+                                          ("ch4cn", 0.15, 100000), ("ch4cn", 0.4, 30000),
+                                          ("clnh3", 0.15, 100000), ("clnh3", 0.4, 30000),
+                                          ("nh3oh", 0.15, 100000), ("nh3oh", 0.4, 30000)])
 def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, n, sigma, rng)
@@ -27,7 +29,7 @@ def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     ok = np.isfinite(Vo)
     assert ok.mean() > 0.999
     assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
-    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)      # 1e-10; nh3oh: see tests/common.py tol_grad
 
 
 def test_egrad_golden(gpu):
@@ -37,7 +39,7 @@ def test_egrad_golden(gpu):
         q = np.array(rec["q"])
         V, g, _ = gpu.egrad(name, q)
         assert C.rel_err_E(V, np.array(rec["V"])).max() < C.TOL_EG
-        assert C.rel_err_G(g, np.array(rec["g"])).max() < C.TOL_EG
+        assert C.rel_err_G(g, np.array(rec["g"])).max() < C.tol_grad(name)
 
 
 def test_reference_signature_wrappers(gpu, oracle):
@@ -81,7 +83,7 @@ def test_h3_compact_branch_and_warning_bits(gpu, oracle):
     assert info == oinfo == 2
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh"])
 def test_egrad_far_apart_matches_oracle(gpu, oracle, name):
     """reactants 8 ... 45 bohr apart, where the umbrella windows of a rate calculation go (DIST_INF): arguments far
     outside the saddle-point clouds (BKMP2's H2 singlet curve calls exp(-2e12) at 30 bohr); the CPU twin of this test
@@ -99,10 +101,12 @@ def test_egrad_far_apart_matches_oracle(gpu, oracle, name):
     ok = np.isfinite(Vo) & np.isfinite(go.reshape(len(q), -1)).all(axis=1)
     assert ok.mean() > 0.99 and np.isfinite(Vd[ok]).all() and np.isfinite(gd[ok]).all()
     assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
-    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn"])
+# nh3oh is not in this list: its gradient is a one-sided difference quotient (egrad_nh3oh.f:283-296), which is neither
+# rotation-covariant nor free of a net force beyond O(step); tests/test_oracle_clnh3.py checks what does hold for it
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3"])
 def test_invariances_at_scale(gpu, name):
     """size-independent properties on 1e6 images: rigid motions and permutations of equivalent
     hydrogens leave E unchanged and rotate/permute the gradient."""
@@ -124,7 +128,8 @@ def test_invariances_at_scale(gpu, name):
     # net force and torque vanish
     assert np.abs(g.sum(axis=1)).max() < 1e-10
     perm = {"h3": [1, 0, 2], "oh3": [0, 1, 3, 2], "ch4h": [0, 1, 3, 2, 4, 5], "brh2": [2, 1, 0], "o3": [1, 2, 0],
-            "ch4oh": [3, 1, 2, 0, 4, 5, 6], "geh4oh": [0, 1, 3, 2, 4, 5, 6], "ch4cn": [0, 1, 2, 4, 3, 5, 6]}[name]
+            "ch4oh": [3, 1, 2, 0, 4, 5, 6], "geh4oh": [0, 1, 3, 2, 4, 5, 6], "ch4cn": [0, 1, 2, 4, 3, 5, 6],
+            "clnh3": [2, 1, 0, 3, 4]}[name]
     V3, g3, _ = gpu.egrad(name, q[:, perm])
     ok = np.ones(len(q), dtype=bool)
     if name == "brh2":

@@ -41,6 +41,12 @@ CASES = [
     ("geh4oh", 16, 2, 0, 0, 2, 0.98, 0.0, 2),     # child trajectories
     ("ch4cn", 8, 0, 1, 40, 2, 0.9, 15.0, 3),      # CH4 + CN, umbrella window
     ("ch4cn", 16, 2, 0, 0, 2, 0.98, 0.0, 2),      # child trajectories
+    ("clnh3", 8, 0, 1, 40, 2, 0.9, 15.0, 3),      # NH3 + Cl (5 atoms), umbrella window
+    ("clnh3", 16, 1, 1, 31, 2, 0.98, 15.0, 2),    # constrained parent
+    ("clnh3", 32, 2, 0, 0, 2, 0.98, 0.0, 2),      # child trajectories
+    ("nh3oh", 8, 0, 1, 40, 2, 0.9, 15.0, 3),      # NH3 + OH (numeric gradient, four lanes per bead)
+    ("nh3oh", 16, 2, 0, 0, 2, 0.98, 0.0, 2),      # child trajectories
+    ("nh3oh", 1, 0, 1, 50, 2, 0.95, 15.0, 5),     # one bead
 ]
 
 

@@ -12,7 +12,7 @@ from tests import common as C
 
 dp = ctypes.POINTER(ctypes.c_double)
 ip = ctypes.POINTER(ctypes.c_int)
-PID = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8}
+PID = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8, "clnh3": 9, "nh3oh": 13}
 
 
 def hh_egrad(H, name, q):
@@ -26,7 +26,8 @@ def hh_egrad(H, name, q):
 @pytest.mark.parametrize("name,sigma", [("h3", 0.15), ("h3", 0.5), ("oh3", 0.15), ("oh3", 0.5),
                                         ("ch4h", 0.15), ("ch4h", 0.4), ("brh2", 0.15), ("brh2", 0.5), ("o3", 0.15), ("o3", 0.4),
                                         ("ch4oh", 0.15), ("ch4oh", 0.4), ("geh4oh", 0.15), ("geh4oh", 0.4),
-                                        ("ch4cn", 0.15), ("ch4cn", 0.4)])
+                                        ("ch4cn", 0.15), ("ch4cn", 0.4), ("clnh3", 0.15), ("clnh3", 0.4),
+                                        ("nh3oh", 0.15), ("nh3oh", 0.4)])
 def test_pes_functor_matches_oracle(oracle, host_harness, name, sigma):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, 20000, sigma, rng)
@@ -35,10 +36,10 @@ def test_pes_functor_matches_oracle(oracle, host_harness, name, sigma):
     ok = np.isfinite(Vo)
     assert ok.mean() > 0.999
     assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
-    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh"])
 def test_pes_functor_far_apart(oracle, host_harness, name):
     """reactants 8 ... 45 bohr apart (the umbrella windows of a rate calculation reach DIST_INF): the curves are evaluated
     far outside the region the saddle-point clouds sample -- BKMP2's H2 singlet curve, for one, calls exp(-2e12) at
@@ -59,7 +60,7 @@ def test_pes_functor_far_apart(oracle, host_harness, name):
     ok = np.isfinite(Vo) & np.isfinite(go.reshape(len(q), -1)).all(axis=1)
     assert ok.mean() > 0.99 and np.isfinite(Vd[ok]).all()
     assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
-    assert C.rel_err_G(gd[ok], go[ok]).max() < C.TOL_EG
+    assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 
 def test_h3_compact_geometries(oracle, host_harness):
