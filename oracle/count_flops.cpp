@@ -31,6 +31,16 @@ namespace cbe_ch4cn {
 #undef ipow
 }
 
+// the three-hydrogen members (pes_clnh3.c, and pes_nh3oh.c = the same source with CBE3_NH3OH; for nh3oh the census
+// counts the 19 energy evaluations of the difference quotient -- the analytic derivative code the reference still
+// runs 19 times and discards is not restated, so its operations are not in the figure)
+namespace cbe_clnh3 {
+#include "pes_clnh3.c"
+}
+namespace cbe_nh3oh {
+#include "pes_nh3oh.c"
+}
+
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
 static void census(const char* name, egrad_fn fn, int nat, const double* ts, int n, bool last)
@@ -84,7 +94,15 @@ int main()
     const double u0 = 1.20 * s3 / b, u1 = 1.094 * s3 / b, uc = 2.75 * s3 / b;
     const double ch4cn[21] = {u0, u0, u0, 0, 0, 0, u1, -u1, -u1, -u1, u1, -u1, -u1, -u1, u1, uc, uc, uc,
                               uc + 1.172 * 0.6385 / b, uc + 1.172 * 0.5384 / b, uc + 1.172 * 0.5384 / b};
-    census("ch4cn", cbe_ch4cn::oracle_egrad_ch4cn_real, 7, ch4cn, 2000, true);
+    census("ch4cn", cbe_ch4cn::oracle_egrad_ch4cn_real, 7, ch4cn, 2000, false);
+    // caracal_b200/systems.py clnh3_ts, nh3oh_ts
+    const double clnh3[15] = {2.3329132995, 0.0, 0.9350786638, 0.0, 0.0, 0.0, -0.8893135660, 1.5403362803, 0.7129095978,
+                              -0.8893135660, -1.5403362803, 0.7129095978, 4.7886115095, 0.0, 1.9193719941};
+    census("clnh3", cbe_clnh3::oracle_egrad_clnh3_real, 5, clnh3, 2000, false);
+    const double nh3oh[18] = {2.0171806725, 0.0, 0.8085266642, 0.0, 0.0, 0.0, -0.8893135660, 1.5403362803, 0.7129095978,
+                              -0.8893135660, -1.5403362803, 0.7129095978, 4.2974718675, 0.0, 1.7225133281,
+                              3.9213112830, 0.0, 3.5165362123};
+    census("nh3oh", cbe_nh3oh::oracle_egrad_nh3oh_real, 6, nh3oh, 2000, true);
     printf("}\n");
     return 0;
 }

@@ -730,8 +730,13 @@ void N3_PARTS(const real *qin, real parts[3], real *V)
 /* energy split with r0ch held at r0ch_frozen (<= 0: as in the source) */
 void N3(parts_frozen_real)(const real *qin, double r0ch_frozen, real parts[3], real *V)
 {
+    N3(par) par;
+    real R[N3_NC + 1], D[N3_NC + 1];
+    int i;
+    N3(prepot)(&par);
+    for (i = 0; i < N3_NC; i++) R[i + 1] = qin[i];
     N3(r0ch_frozen) = r0ch_frozen;
-    N3_PARTS(qin, parts, V);
+    N3(pot)(&par, R, V, D, parts, (real *)0);
     N3(r0ch_frozen) = -1.0;
 }
 

@@ -184,7 +184,7 @@ for nb, nsteps in ((1, 200), (8, 200)):
     g.close()
 
 # ---- N4: the 7-atom CBE-family surfaces (one-lane PesCBE1<K>), recrossing children at config 2's shape ----------
-for name in ("ch4oh", "geh4oh"):
+for name in ("ch4oh", "geh4oh", "clnh3", "nh3oh"):
     nb, npairs, evol = 16, 512, 500
     g, o = C.make_pair(name, nb)
     g.set_seed(C.SEED)
