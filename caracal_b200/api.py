@@ -454,6 +454,13 @@ class RPMD:
         """FP64 tensor-core (mma.sync.m8n8k4.f64) throughput of this device"""
         return float(self._lib.crcl_measure_dmma_tflops(self._h, int(iters)))
 
+    def bench_transform(self, nbeads, ntraj, reps):
+        """free ring-polymer step from shared memory, FMA form against DMMA form (include/caracal_gpu.h
+        crcl_bench_transform): dict(ms_dfma, ms_dmma, max_rel_diff, flops, max_dq)"""
+        out = np.zeros(5)
+        _l.check(self._lib.crcl_bench_transform(self._h, int(nbeads), int(ntraj), int(reps), _dp(out)), self._h, "crcl_bench_transform")
+        return dict(ms_dfma=out[0], ms_dmma=out[1], max_rel_diff=out[2], flops=out[3], max_dq=out[4])
+
 
 # ---- egrad_<pes>(q,Natoms,Nbeads,V,dVdq,info): the reference's PES plug-in signature ---------
 _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H: ["H", "C", "H", "H", "H", "H"],

@@ -15,6 +15,7 @@
 #include "pes_brh2.cuh"
 #include "pes_o3.cuh"
 #include "pes_nh3x.cuh"
+#include "transform_bench.cuh"
 #include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
 #include "split_kernels.cuh"
@@ -2154,6 +2155,92 @@ double crcl_measure_fp64_tflops(crcl_handle h, int iters)
         if (rep > 0 && tf > best) best = tf;
     }
     return best;
+}
+
+}  // extern "C" (templates below)
+
+template <int NB, int NC, int TPC, int MODE>
+static int run_transform_bench(crcl_handle h, const double* d_f, const double* d_m, double2* d_pq, int ntraj, int reps, float* ms)
+{
+    using B = TransformBench<NB, NC, TPC, MODE>;
+    auto kern = transform_bench_kernel<NB, NC, TPC, MODE>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::smem_bytes()) != cudaSuccess) return CRCL_ECUDA;
+    cudaEventRecord(h->ev0, h->stream);
+    kern<<<ntraj / TPC, B::THREADS, B::smem_bytes(), h->stream>>>(d_f, d_m, d_pq, reps);
+    cudaEventRecord(h->ev1, h->stream);
+    h->launches++;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess || cudaGetLastError() != cudaSuccess) return CRCL_ECUDA;
+    cudaEventElapsedTime(ms, h->ev0, h->ev1);
+    return CRCL_OK;
+}
+
+template <int NB, int NC, int TPC>
+static int transform_bench(crcl_handle h, int ntraj, int reps, double* out)
+{
+    ntraj = (ntraj / TPC) * TPC;
+    if (ntraj <= 0 || reps <= 0) return fail(h, CRCL_EINVAL, "crcl_bench_transform: ntraj >= 4 and reps >= 1");
+    std::vector<double> f, m(NC);
+    build_fker(NB, h->beta, h->dt, f);
+    for (int c = 0; c < NC; c++) m[c] = ((c / 3) == 1 ? 12.0 : 1.00782503207) * 1822.888486;   // one heavy atom among hydrogens
+    const size_t n = (size_t)ntraj * NC * NB;
+    std::vector<double2> x(n);
+    uint64_t sd = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < n; i++) {
+        sd = sd * 6364136223846793005ull + 1442695040888963407ull;
+        const double u = (double)(sd >> 11) / 9007199254740992.0 - 0.5;
+        sd = sd * 6364136223846793005ull + 1442695040888963407ull;
+        const double v = (double)(sd >> 11) / 9007199254740992.0 - 0.5;
+        x[i] = make_double2(10.0 * u, 2.0 * v);      // momenta ~ sqrt(m kT), positions ~ bohr
+    }
+    double *d_f, *d_m;
+    double2 *d_a, *d_b;
+    int rc;
+    if ((rc = scratch(h, 11, f.size(), &d_f)) || (rc = scratch(h, 12, m.size(), &d_m)) || (rc = scratch(h, 13, n, &d_a)) ||
+        (rc = scratch(h, 14, n, &d_b)))
+        return rc;
+    CK(cudaMemcpy(d_f, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_m, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // the two forms on the same input, three steps: they must agree to rounding
+    float ms;
+    CK(cudaMemcpy(d_a, x.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_b, x.data(), n * sizeof(double2), cudaMemcpyHostToDevice));
+    if ((rc = run_transform_bench<NB, NC, TPC, 0>(h, d_f, d_m, d_a, ntraj, 3, &ms))) return fail(h, rc, "transform bench (DFMA) failed");
+    if ((rc = run_transform_bench<NB, NC, TPC, 1>(h, d_f, d_m, d_b, ntraj, 3, &ms))) return fail(h, rc, "transform bench (DMMA) failed");
+    std::vector<double2> ya(n), yb(n);
+    CK(cudaMemcpy(ya.data(), d_a, n * sizeof(double2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(yb.data(), d_b, n * sizeof(double2), cudaMemcpyDeviceToHost));
+    double dmax = 0.0, pmax = 0.0, qmax = 0.0, moved = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        pmax = fmax(pmax, fabs(ya[i].x));
+        qmax = fmax(qmax, fabs(ya[i].y));
+        moved = fmax(moved, fabs(ya[i].y - x[i].y));
+    }
+    for (size_t i = 0; i < n; i++) dmax = fmax(dmax, fmax(fabs(ya[i].x - yb[i].x) / pmax, fabs(ya[i].y - yb[i].y) / qmax));
+    out[2] = dmax;
+    out[4] = moved;       // the transform did something (max |q' - q|)
+    for (int mode = 0; mode < 2; mode++) {
+        double best = 1e30;
+        for (int rep = 0; rep < 4; rep++) {
+            rc = mode ? run_transform_bench<NB, NC, TPC, 1>(h, d_f, d_m, d_b, ntraj, reps, &ms)
+                      : run_transform_bench<NB, NC, TPC, 0>(h, d_f, d_m, d_a, ntraj, reps, &ms);
+            if (rc) return fail(h, rc, "transform bench failed");
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out[mode] = best;
+    }
+    out[3] = (double)reps * ntraj * NC * 4.0 * 2.0 * NB * NB;
+    return CRCL_OK;
+}
+
+extern "C" {
+
+int crcl_bench_transform(crcl_handle h, int nbeads, int ntraj, int reps, double* out)
+{
+    if (!h || !out) return CRCL_EINVAL;
+    cudaSetDevice(h->device);
+    if (nbeads == 16) return transform_bench<16, 18, 4>(h, ntraj, reps, out);
+    if (nbeads == 64) return transform_bench<64, 12, 4>(h, ntraj, reps, out);
+    return fail(h, CRCL_ENOSUP, "crcl_bench_transform: 16 beads (6 atoms) or 64 beads (4 atoms)");
 }
 
 double crcl_measure_dmma_tflops(crcl_handle h, int iters)

@@ -126,6 +126,7 @@ SIGNATURES = {
     "crcl_bench_propagate": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, c_double_p]),
     "crcl_measure_fp64_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
     "crcl_measure_dmma_tflops": (ctypes.c_double, [_H, ctypes.c_int]),
+    "crcl_bench_transform": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p]),
 }
 
 

@@ -352,6 +352,13 @@ double crcl_measure_fp64_tflops(crcl_handle h, int iters);
 /* same for the FP64 tensor-core path (mma.sync.m8n8k4.f64): the evidence behind keeping the bead
  * transform on the DFMA pipe */
 double crcl_measure_dmma_tflops(crcl_handle h, int iters);
+/* the free ring-polymer step as a stand-alone shared-memory-resident kernel in its FMA form (the loop of the trajectory
+ * kernels) and in a DMMA form, on the same synthetic input (csrc/transform_bench.cuh): nbeads = 16 (6 atoms) or 64
+ * (4 atoms), ntraj trajectories, the step applied reps times per launch.  out[0] = ms per launch of the FMA form,
+ * out[1] = of the DMMA form (best of 3), out[2] = largest difference between the two results relative to the largest
+ * |p| / |q| after three steps, out[3] = flops per launch (4 NB x NB matrix-vector products per component),
+ * out[4] = largest |q' - q| (the step is not the identity).  Measurement helper, not on the reference's path. */
+int crcl_bench_transform(crcl_handle h, int nbeads, int ntraj, int reps, double *out);
 
 #ifdef __cplusplus
 }
