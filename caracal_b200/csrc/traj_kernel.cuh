@@ -196,6 +196,13 @@ struct Group {
     }
 };
 
+// Free ring-polymer step on the FP64 tensor cores (mma.sync.m8n8k4.f64) for the lane-split surfaces whose trajectories are
+// whole warps with dense tables (NB = 8, 16, 32 at four lanes per bead; Traj::free_rp_dmma).  -DCRCL_DMMA_TRANSFORM=0
+// restores the FMA loop (A/B builds: profiles/build_variant.py).
+#ifndef CRCL_DMMA_TRANSFORM
+#define CRCL_DMMA_TRANSFORM 1
+#endif
+
 // doubles of lane-exchange scratch per thread a lane-split surface asks for (PES::COOP_SCRATCH), 0 if it has none
 template <class P, class = void>
 struct coop_scratch {
@@ -226,7 +233,11 @@ struct SmemLayout {
     // after the tables and the reduction scratch (RED_N values for each of up to 32 warps): {mass, 1/mass}[lane][NOWN] (double2), see Traj::mt
     static constexpr int MT_OFF = (FKER + 32 * Group<NB, LANES>::RED_N + 1) & ~1;
     static constexpr int MT_MAX = 2 * 3 * XI_MAXAT + 16;         // >= 2 LANES NOWN for every surface (static_assert in load_fker)
-    static constexpr int BLOCK = MT_OFF + MT_MAX;   // even: double2 alignment of what follows
+    // {mass, 1/mass}[component] (double2) for the tensor-core form of the free ring-polymer step, whose accumulator
+    // fragments hold components the thread does not own
+    static constexpr bool DMMA = CRCL_DMMA_TRANSFORM && HTAB && LANES > 1 && (NB % 8 == 0) && ((NB * LANES) % 32 == 0);
+    static constexpr int MC_OFF = MT_OFF + MT_MAX;
+    static constexpr int BLOCK = MC_OFF + (DMMA ? 2 * NC : 0);   // even: double2 alignment of what follows
     static constexpr size_t bytes()
     {
         return sizeof(double) * (BLOCK + Group<NB, LANES>::GPB * PER_GROUP);
@@ -262,6 +273,7 @@ struct Traj {
     double* coop;   // shared lane-exchange scratch of this thread's bead (surfaces with COOP_SCRATCH), else unused
     bool want_epot; // false: forces() skips the all-reduce of the bead energies (recrossing children)
     const double* fk;
+    const double2* mc;  // shared {mass, 1/mass}[component] (SmemLayout::DMMA only)
     double xi_ideal, k_force, xi_real, epot;
     double vnh[4], qnh[4];
     int nfree, status;
@@ -271,6 +283,7 @@ struct Traj {
     {
         using Lay = SmemLayout<NAT, NB, L, coop_scratch<PES>::value>;
         fk = smem;
+        mc = reinterpret_cast<const double2*>(smem + Lay::MC_OFF);
         mt = reinterpret_cast<const double2*>(smem + Lay::MT_OFF) + grp.lane * NO;
         double* base = smem + Lay::BLOCK + grp.gib * Lay::PER_GROUP;
         pq = reinterpret_cast<double2*>(base);
@@ -342,6 +355,75 @@ struct Traj {
         }
         G.sync();
     }
+    // The same step on the FP64 tensor cores: out[a][c] = sum_b H[a][b] x[b][c] as m8n8k4 tiles -- 8 beads x 8 components
+    // per accumulator pair, A fragments = the three dense tables (stored in fragment order by load_fker: one conflict-free
+    // 8-byte load per fragment), B fragments = {p,q} of 4 source beads x 8 components (one 16-byte load yields the P and the
+    // Q fragment).  Warp w of the trajectory takes row tile w mod MT and every (T/32/MT)-th column tile; its A fragments
+    // are loaded once per step.  No staging of bead-symmetrised sums: the symmetrisation is in the table.
+    // Measured against the FMA loop on the transform alone (profiles/r2u_bench_transform.json): 2.2x at 16 beads.
+    __device__ __forceinline__ void free_rp_dmma()
+    {
+        constexpr int WPT = Grp::T / 32, MT = NB / 8, KS = NB / 4, NT = (NC + 7) / 8;
+        constexpr int WPM = (WPT >= MT) ? WPT / MT : 1;            // warps that share a row tile (split its column tiles)
+        static_assert(WPT % MT == 0 || MT % WPT == 0, "row tiles and warps of a trajectory must divide each other");
+        const int w = G.tig >> 5, lane = G.tig & 31, gr = lane >> 2, tg = lane & 3;
+        auto mma = [](double& c0, double& c1, double a, double b) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+        };
+        G.sync();
+        constexpr int RT = (MT >= WPT) ? MT / WPT : 1;             // row tiles per warp
+        constexpr int CT = (NT + WPM - 1) / WPM;                   // column tiles per warp
+        double2 res[RT][CT][2];
+#pragma unroll
+        for (int ir = 0; ir < RT; ir++) {
+            const int mt_ = (MT >= WPT) ? w + WPT * ir : w % MT;
+            double fc[KS], fa[KS], fb[KS];
+            const double* hf = fk + mt_ * (KS * 32) + lane;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+                fc[ks] = hf[ks * 32];
+                fa[ks] = hf[MT * KS * 32 + ks * 32];
+                fb[ks] = hf[2 * MT * KS * 32 + ks * 32];
+            }
+#pragma unroll
+            for (int ic = 0; ic < CT; ic++) {
+                const int nt = (WPT >= MT) ? (w / MT) + WPM * ic : ic;
+                const int c = nt * 8 + gr;
+                const double2* xb = pq + ((c < NC) ? c : NC - 1) * NBP + tg;   // padded columns: a copy of the last one
+                double cp[2] = {0.0, 0.0}, aq[2] = {0.0, 0.0}, bp[2] = {0.0, 0.0}, cq[2] = {0.0, 0.0};
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) {
+                    const double2 u = xb[ks * 4];
+                    mma(cp[0], cp[1], fc[ks], u.x);
+                    mma(aq[0], aq[1], fa[ks], u.y);
+                    mma(bp[0], bp[1], fb[ks], u.x);
+                    mma(cq[0], cq[1], fc[ks], u.y);
+                }
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = nt * 8 + 2 * tg + e;
+                    const double2 m = mc[(j < NC) ? j : NC - 1];
+                    res[ir][ic][e] = make_double2(fma(m.x, aq[e], cp[e]), fma(m.y, bp[e], cq[e]));
+                }
+            }
+        }
+        G.sync();   // every B fragment has been read
+#pragma unroll
+        for (int ir = 0; ir < RT; ir++) {
+            const int mt_ = (MT >= WPT) ? w + WPT * ir : w % MT;
+#pragma unroll
+            for (int ic = 0; ic < CT; ic++) {
+                const int nt = (WPT >= MT) ? (w / MT) + WPM * ic : ic;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int j = nt * 8 + 2 * tg + e;
+                    if (j < NC && nt < NT) pq[j * NBP + mt_ * 8 + gr] = res[ir][ic][e];
+                }
+            }
+        }
+        // the caller's next phase starts with G.sync() (centroid), which publishes these stores
+    }
     // free ring-polymer propagation (verlet.f90:353-357 for one bead, :377-463 otherwise):
     // p' = Fc p + m Fa q, q' = Fb p / m + Fc q with the circulant kernels of the header comment
     __device__ __forceinline__ void free_rp()
@@ -350,6 +432,10 @@ struct Traj {
 #pragma unroll
             for (int k = 0; k < NO; k++)
                 if (own(k)) Qk(k) = Qk(k) + Pk(k) * A.dt / mt[k].x;
+            return;
+        }
+        if constexpr (SmemLayout<NAT, NB, L>::DMMA) {
+            free_rp_dmma();
             return;
         }
         G.sync();
@@ -868,11 +954,25 @@ __device__ __forceinline__ void load_fker(const TrajArgs& A, double* smem)
         const double m = (oc >= 0) ? A.mass[oc / 3] : 1.0;
         reinterpret_cast<double2*>(smem + SmemLayout<NAT, NB, LANES>::MT_OFF)[i] = make_double2(m, 1.0 / m);
     }
+    if (SmemLayout<NAT, NB, LANES>::DMMA) {
+        for (int i = threadIdx.x; i < 3 * PES::NATOMS; i += blockDim.x) {
+            const double m = A.mass[i / 3];
+            reinterpret_cast<double2*>(smem + SmemLayout<NAT, NB, LANES>::MC_OFF)[i] = make_double2(m, 1.0 / m);
+        }
+    }
     if (SmemLayout<NAT, NB, LANES>::HTAB) {
         for (int i = threadIdx.x; i < 3 * NB * NB; i += blockDim.x) {
             const int x = i / (NB * NB), r = i - x * NB * NB, b = r / NB, a = r - b * NB;
             const double f1 = A.fker[x * NB + ((a - b) & (NB - 1))];
-            smem[i] = A.symmetrize ? 0.5 * (f1 + A.fker[x * NB + ((a + b) & (NB - 1))]) : f1;
+            const double v = A.symmetrize ? 0.5 * (f1 + A.fker[x * NB + ((a + b) & (NB - 1))]) : f1;
+            if (SmemLayout<NAT, NB, LANES>::DMMA) {
+                // A-fragment order of mma.m8n8k4 (row a = lane / 4, column b = lane % 4 of an 8 x 4 tile):
+                // [x][row tile a / 8][k step b / 4][lane]
+                constexpr int MT = NB / 8, KS = NB / 4;
+                smem[((x * MT + a / 8) * KS + b / 4) * 32 + (a % 8) * 4 + (b % 4)] = v;
+            } else {
+                smem[i] = v;
+            }
         }
     } else {
         for (int i = threadIdx.x; i < 3 * NB; i += blockDim.x) smem[i] = A.fker[i];

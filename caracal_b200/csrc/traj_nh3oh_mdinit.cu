@@ -1,4 +1,7 @@
 // traj_nh3oh_mdinit.cu -- instantiates the mdinit trajectory kernels for the "nh3oh" surface.
+// FMA form of the free ring-polymer step: the step of this surface is 19 energy evaluations, the transform does not show,
+// and nvcc 12.9 crashes on the tensor-core form in this unit
+#define CRCL_DMMA_TRANSFORM 0
 #include "pes_nh3x.cuh"
 #include "traj_inst.cuh"
 namespace crcl {
