@@ -167,20 +167,58 @@ static int ensure_fker(crcl_handle h)
 }
 
 // ---- small kernels ---------------------------------------------------------------------------
+// One thread per image.  The images of a CTA are contiguous in q and g ([image][atom][xyz]), so the CTA moves its tile
+// with coalesced 16-byte accesses through shared memory (row stride odd: conflict-free for the per-thread reads) instead
+// of every thread walking its own 3 NATOMS doubles with a stride of 24 NATOMS bytes between lanes: the light surfaces
+// (H3, OH3, O3, ClNH3: 70-200 B and a few hundred flops per image) sat at 1.0-2.6 TB/s behind those accesses
+// (profiles/r2t_bench_egrad.json, long_scoreboard / lg_throttle in profiles/r2t_egrad_clnh3_summary.txt).
+constexpr int EGRAD_TPB = 128;
 template <class PES>
-__global__ void egrad_kernel(const double* __restrict__ q, int nimg, double* __restrict__ V,
-                             double* __restrict__ g, int* __restrict__ info)
+__global__ void __launch_bounds__(EGRAD_TPB, (PES::NATOMS <= 5) ? 3 : 2)
+    egrad_kernel(const double* __restrict__ q, int nimg, double* __restrict__ V, double* __restrict__ g, int* __restrict__ info)
 {
-    constexpr int NC = 3 * PES::NATOMS;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nimg) return;
-    double x[NC], gr[NC], e;
+    constexpr int NC = 3 * PES::NATOMS, NCP = NC | 1;
+    __shared__ __align__(16) double tile[EGRAD_TPB * NCP];
+    const int i0 = blockIdx.x * EGRAD_TPB, tid = threadIdx.x;
+    const int nloc = (nimg - i0 < EGRAD_TPB) ? nimg - i0 : EGRAD_TPB;
+    const size_t base = (size_t)i0 * NC;           // EGRAD_TPB * NC * 8 bytes per CTA: a multiple of 16
+    const int nd = nloc * NC;
+    // 16-byte accesses need 16-byte aligned arrays (anything from cudaMalloc is; a caller's offset pointer may not be)
+    const bool vec = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+    if (!vec) {
+        for (int j = tid; j < nd; j += EGRAD_TPB) tile[(j / NC) * NCP + j % NC] = q[base + j];
+    } else {
+        const double2* q2 = reinterpret_cast<const double2*>(q + base);
+        for (int j = tid; j < nd / 2; j += EGRAD_TPB) {
+            const double2 v = q2[j];
+            const int e0 = 2 * j, e1 = 2 * j + 1;
+            tile[(e0 / NC) * NCP + e0 % NC] = v.x;
+            tile[(e1 / NC) * NCP + e1 % NC] = v.y;
+        }
+        if ((nd & 1) && tid == 0) tile[((nd - 1) / NC) * NCP + (nd - 1) % NC] = q[base + nd - 1];
+    }
+    __syncthreads();
+    double x[NC], gr[NC], e = 0.0;
+    int w = 0;
+    if (tid < nloc) {
 #pragma unroll
-    for (int c = 0; c < NC; c++) x[c] = q[(size_t)i * NC + c];
-    const int w = PES::eval(x, e, gr);
-    V[i] = e;
+        for (int c = 0; c < NC; c++) x[c] = tile[tid * NCP + c];
+        w = PES::eval(x, e, gr);
+        V[i0 + tid] = e;
 #pragma unroll
-    for (int c = 0; c < NC; c++) g[(size_t)i * NC + c] = gr[c];
+        for (int c = 0; c < NC; c++) tile[tid * NCP + c] = gr[c];   // own row: no barrier needed before this store
+    }
+    __syncthreads();
+    if (!vec) {
+        for (int j = tid; j < nd; j += EGRAD_TPB) g[base + j] = tile[(j / NC) * NCP + j % NC];
+    } else {
+        double2* g2 = reinterpret_cast<double2*>(g + base);
+        for (int j = tid; j < nd / 2; j += EGRAD_TPB) {
+            const int e0 = 2 * j, e1 = 2 * j + 1;
+            g2[j] = make_double2(tile[(e0 / NC) * NCP + e0 % NC], tile[(e1 / NC) * NCP + e1 % NC]);
+        }
+        if ((nd & 1) && tid == 0) g[base + nd - 1] = tile[((nd - 1) / NC) * NCP + (nd - 1) % NC];
+    }
     if (w && info) atomicOr(info, w);
 }
 
@@ -1424,7 +1462,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     if (pes_natoms(pes_id) != natoms) return fail(h, CRCL_EINVAL, "natoms does not match the PES");
     if (nimg == 0) return CRCL_OK;
     CK(cudaSetDevice(h->device));
-    const int tpb = 128, grid = (nimg + tpb - 1) / tpb;
+    const int tpb = EGRAD_TPB, grid = (nimg + tpb - 1) / tpb;
     if (d_info) CK(cudaMemsetAsync(d_info, 0, sizeof(int), h->stream));
     if (h->timed && !h->capturing) {
         next_event_pair(h);

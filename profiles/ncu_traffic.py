@@ -21,7 +21,7 @@ def b(key):
 
 
 out = dict(kernel=M["Kernel Name"][0], child_steps=steps, child_pairs=pairs, dram_bytes_read=b("dram__bytes_read.sum"),
-           dram_bytes_write=b("dram__bytes_write.sum"), duration_us_under_ncu=float(M["gpu__time_duration.sum"][0]),
+           dram_bytes_write=b("dram__bytes_write.sum"), duration_under_ncu=float(M["gpu__time_duration.sum"][0]), duration_unit=M["gpu__time_duration.sum"][1],
            source=os.path.basename(rep))
 # the hardware's view of the same launch, next to the census-based roofline fraction of bench.py
 for key, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
@@ -30,5 +30,7 @@ for key, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active
                   ("sass__inst_executed_local_loads", "local_loads"), ("sass__inst_executed_local_stores", "local_stores")):
     if key in M:
         out[name] = float(M[key][0])
+# every pipe the capture reports (the DMMA of the tensor-core transform is not part of sm__pipe_fp64_cycles_active)
+out["pipes"] = {k: M[k][0] + " " + M[k][1] for k in sorted(M) if ("pipe" in k and ("tensor" in k or "fp64" in k or "dmma" in k.lower()))}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic_recross.json"), "w"), indent=1)
 print(out)
