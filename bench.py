@@ -631,6 +631,9 @@ def main():
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             if "fp64_pipe_active_pct" in tr:
                 hardware = {"fp64_pipe_active_frac": tr["fp64_pipe_active_pct"] / 100.0,
+                            # the free ring-polymer step runs as mma.sync.m8n8k4.f64 on the tensor sub-pipe, which
+                            # sm__pipe_fp64_cycles_active does not count
+                            "dmma_pipe_active_frac": tr.get("dmma_pipe_active_pct", 0.0) / 100.0,
                             "issue_active_frac": tr.get("issue_active_pct", 0.0) / 100.0,
                             "warp_instructions_per_launch": tr.get("warp_instructions"),
                             "source": "ncu --set full, profiles/" + tr.get("source", "traffic_recross.json")}

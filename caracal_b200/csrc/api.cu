@@ -167,59 +167,40 @@ static int ensure_fker(crcl_handle h)
 }
 
 // ---- small kernels ---------------------------------------------------------------------------
-// One thread per image.  The images of a CTA are contiguous in q and g ([image][atom][xyz]), so the CTA moves its tile
-// with coalesced 16-byte accesses through shared memory (row stride odd: conflict-free for the per-thread reads) instead
-// of every thread walking its own 3 NATOMS doubles with a stride of 24 NATOMS bytes between lanes: the light surfaces
-// (H3, OH3, O3, ClNH3: 70-200 B and a few hundred flops per image) sat at 1.0-2.6 TB/s behind those accesses
-// (profiles/r2t_bench_egrad.json, long_scoreboard / lg_throttle in profiles/r2t_egrad_clnh3_summary.txt).
+// One thread per image, each walking its own 3 NATOMS doubles of q and g ([image][atom][xyz]).
+// Tried and rejected on measurement (profiles/r2x_bench_egrad.json against r2t_bench_egrad.json): the CTA's tile moved
+// with coalesced 16-byte accesses through shared memory -- every surface but one got slower (H3 0.157 -> 0.193 ms per 2^20
+// images, OH3 0.081 -> 0.101, CH4 + OH 0.58 -> 0.88): the per-thread accesses already hit full sectors through L1, and the
+// two barriers plus the tile's registers cost more than they save.  What that build did show: Br + H2 gains from three
+// resident CTAs (168 registers instead of 188: 0.418 -> 0.347 ms), hence the launch bound below for that surface.
+template <class PES>
+__device__ __forceinline__ void egrad_body(const double* __restrict__ q, int nimg, double* __restrict__ V,
+                                           double* __restrict__ g, int* __restrict__ info)
+{
+    constexpr int NC = 3 * PES::NATOMS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nimg) return;
+    double x[NC], gr[NC], e;
+#pragma unroll
+    for (int c = 0; c < NC; c++) x[c] = q[(size_t)i * NC + c];
+    const int w = PES::eval(x, e, gr);
+    V[i] = e;
+#pragma unroll
+    for (int c = 0; c < NC; c++) g[(size_t)i * NC + c] = gr[c];
+    if (w && info) atomicOr(info, w);
+}
+template <class PES>
+__global__ void egrad_kernel(const double* __restrict__ q, int nimg, double* __restrict__ V,
+                             double* __restrict__ g, int* __restrict__ info)
+{
+    egrad_body<PES>(q, nimg, V, g, info);
+}
 constexpr int EGRAD_TPB = 128;
 template <class PES>
-__global__ void __launch_bounds__(EGRAD_TPB, (PES::NATOMS <= 5) ? 3 : 2)
-    egrad_kernel(const double* __restrict__ q, int nimg, double* __restrict__ V, double* __restrict__ g, int* __restrict__ info)
+__global__ void __launch_bounds__(EGRAD_TPB, 3) egrad_kernel_mb3(const double* __restrict__ q, int nimg, double* __restrict__ V,
+                                                                 double* __restrict__ g, int* __restrict__ info)
 {
-    constexpr int NC = 3 * PES::NATOMS, NCP = NC | 1;
-    __shared__ __align__(16) double tile[EGRAD_TPB * NCP];
-    const int i0 = blockIdx.x * EGRAD_TPB, tid = threadIdx.x;
-    const int nloc = (nimg - i0 < EGRAD_TPB) ? nimg - i0 : EGRAD_TPB;
-    const size_t base = (size_t)i0 * NC;           // EGRAD_TPB * NC * 8 bytes per CTA: a multiple of 16
-    const int nd = nloc * NC;
-    // 16-byte accesses need 16-byte aligned arrays (anything from cudaMalloc is; a caller's offset pointer may not be)
-    const bool vec = ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
-    if (!vec) {
-        for (int j = tid; j < nd; j += EGRAD_TPB) tile[(j / NC) * NCP + j % NC] = q[base + j];
-    } else {
-        const double2* q2 = reinterpret_cast<const double2*>(q + base);
-        for (int j = tid; j < nd / 2; j += EGRAD_TPB) {
-            const double2 v = q2[j];
-            const int e0 = 2 * j, e1 = 2 * j + 1;
-            tile[(e0 / NC) * NCP + e0 % NC] = v.x;
-            tile[(e1 / NC) * NCP + e1 % NC] = v.y;
-        }
-        if ((nd & 1) && tid == 0) tile[((nd - 1) / NC) * NCP + (nd - 1) % NC] = q[base + nd - 1];
-    }
-    __syncthreads();
-    double x[NC], gr[NC], e = 0.0;
-    int w = 0;
-    if (tid < nloc) {
-#pragma unroll
-        for (int c = 0; c < NC; c++) x[c] = tile[tid * NCP + c];
-        w = PES::eval(x, e, gr);
-        V[i0 + tid] = e;
-#pragma unroll
-        for (int c = 0; c < NC; c++) tile[tid * NCP + c] = gr[c];   // own row: no barrier needed before this store
-    }
-    __syncthreads();
-    if (!vec) {
-        for (int j = tid; j < nd; j += EGRAD_TPB) g[base + j] = tile[(j / NC) * NCP + j % NC];
-    } else {
-        double2* g2 = reinterpret_cast<double2*>(g + base);
-        for (int j = tid; j < nd / 2; j += EGRAD_TPB) {
-            const int e0 = 2 * j, e1 = 2 * j + 1;
-            g2[j] = make_double2(tile[(e0 / NC) * NCP + e0 % NC], tile[(e1 / NC) * NCP + e1 % NC]);
-        }
-        if ((nd & 1) && tid == 0) g[base + nd - 1] = tile[((nd - 1) / NC) * NCP + (nd - 1) % NC];
-    }
-    if (w && info) atomicOr(info, w);
+    egrad_body<PES>(q, nimg, V, g, info);
 }
 
 template <int NAT>
@@ -1472,7 +1453,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_H3: egrad_kernel<PesH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_OH3: egrad_kernel<PesOH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_CH4H: egrad_kernel<PesCH4H><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
-    case CRCL_PES_BRH2: egrad_kernel<PesBrH2><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_BRH2: egrad_kernel_mb3<PesBrH2><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_O3: egrad_kernel<PesO3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_CH4OH: egrad_kernel<PesCH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_GEH4OH: egrad_kernel<PesGeH4OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;

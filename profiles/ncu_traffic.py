@@ -25,12 +25,17 @@ out = dict(kernel=M["Kernel Name"][0], child_steps=steps, child_pairs=pairs, dra
            source=os.path.basename(rep))
 # the hardware's view of the same launch, next to the census-based roofline fraction of bench.py
 for key, name in (("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
+                  ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "dmma_pipe_active_pct"),
                   ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                   ("smsp__inst_executed.sum", "warp_instructions"),
                   ("sass__inst_executed_local_loads", "local_loads"), ("sass__inst_executed_local_stores", "local_stores")):
     if key in M:
         out[name] = float(M[key][0])
 # every pipe the capture reports (the DMMA of the tensor-core transform is not part of sm__pipe_fp64_cycles_active)
-out["pipes"] = {k: M[k][0] + " " + M[k][1] for k in sorted(M) if ("pipe" in k and ("tensor" in k or "fp64" in k or "dmma" in k.lower()))}
+out["pipes"] = {k: M[k][0] + " " + M[k][1] for k in sorted(M)
+                if k in ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                         "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+                         "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+                         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")}
 json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic_recross.json"), "w"), indent=1)
 print(out)

@@ -5,6 +5,8 @@
   * ADVICE r1: Andersen stream continuity over single-step calls, host-callback PES in crcl_umbrella_windows;
   * the NCCL communicator behind the C-ABI on one rank (the multi-rank form runs under torchrun: tests/multi_gpu_comm.py).
 """
+import ctypes as _ct
+
 import numpy as np
 import pytest
 
@@ -271,3 +273,37 @@ def test_cell_sweep_equals_n2_sweep_and_oracle(gpu, oracle, nmol, nimg):
         assert C.rel_err_E(res["m3"][0], Vo).max() < C.TOL_EG
         tol = np.maximum(C.TOL_EG, 2e-17 / torsion_conditioning(T, x) ** 2)
         assert (C.rel_err_G(res["m3"][1].reshape(go.shape), go) < tol).all()
+
+
+@pytest.mark.parametrize("nb", [16, 64])
+def test_tensor_core_transform_equals_the_fma_transform(gpu, nb):
+    """crcl_bench_transform: the free ring-polymer step as mma.sync.m8n8k4.f64 tiles against the FMA loop of the
+    trajectory kernels on the same seeded trajectories, three steps: same numbers to rounding (different summation
+    order only), and the step is not the identity.  The fused form of the same tiles (Traj::free_rp_dmma) is covered by
+    every lane-split case of tests/test_gpu_verlet.py / test_gpu_recross.py against the oracle."""
+    g, _ = C.make_pair("ch4h", 16)
+    r = g.bench_transform(nb, 64, 2)
+    assert r["max_rel_diff"] < 1e-14
+    assert r["max_dq"] > 1e-3
+    assert r["ms_dfma"] > 0 and r["ms_dmma"] > 0
+
+
+def test_egrad_unaligned_device_arrays(gpu, oracle):
+    """crcl_egrad_dev on device arrays that are only 8-byte aligned (offset by one double into their allocations)"""
+    import torch
+    name = "clnh3"
+    q = C.ts_cloud(name, 333, 0.1, np.random.default_rng(4))
+    Vo, go, _ = oracle.egrad(name, q)
+    g, _ = C.make_pair(name, 1)
+    n = q.size
+    buf_q = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+    buf_g = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+    V = torch.zeros(len(q), dtype=torch.float64, device="cuda")
+    buf_q[1:] = torch.from_numpy(q.ravel()).cuda()
+    torch.cuda.synchronize()
+    rc = g._lib.crcl_egrad_dev(g._h, gpu.PES_CLNH3, _ct.c_void_p(buf_q.data_ptr() + 8), 5, len(q),
+                               _ct.c_void_p(V.data_ptr()), _ct.c_void_p(buf_g.data_ptr() + 8), None)
+    assert rc == 0
+    g.synchronize()
+    assert C.rel_err_E(V.cpu().numpy(), Vo).max() < C.TOL_EG
+    assert C.rel_err_G(buf_g[1:].cpu().numpy().reshape(go.shape), go).max() < C.TOL_EG
