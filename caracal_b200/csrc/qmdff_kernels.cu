@@ -13,13 +13,14 @@
 // The SPME/Ewald branch of ff_nonb is dead code in the reference (ewald=.false., :337) and has
 // no counterpart.
 //
-// Mapping: one thread per (image, term) for the lists, gradients accumulated with FP64
-// atomics (red.global.add.f64; a term touches 2-4 atoms, contention is negligible).  The
-// inter-molecular part is an all-pairs sweep: a CTA owns 128 atoms i of one image, streams all
-// atoms j through shared memory in tiles (positions, charge, type, molecule), every thread
-// accumulates the gradient of its own atom in registers -- each pair is visited from both sides,
-// so no atomics and fully coalesced traffic; energies are halved.  With the 10 A cut-offs of the
-// periodic case ~20 % of the pairs of a 27 A box survive the distance test.
+// Mapping: one thread per (image, term) for the lists -- term-major with the image running fastest when a
+// call carries many images of a small molecule --, gradients accumulated with FP64 atomics (red.global.add.f64; a term
+// touches 2-4 atoms).  The inter-molecular part visits every unordered pair once: qm_inter_kernel, a warp per
+// (image, atom i) sweeping j > i with an FP32 pre-filter on a packed copy and a per-warp queue of surviving pairs that is
+// evaluated 32 at a time by qm_pair_exact (exact box_image loop and cut-off tests in FP64); for periodic boxes of at least
+// 2.5 cut-offs, qm_cellsort_kernel + qm_inter_cell_kernel: atoms binned and sorted by cell, a CTA per home cell streaming
+// the half shell of neighbour cells as contiguous runs, the same exact stage.  The donor x acceptor search of ff_hb uses
+// the warp-queue scheme per (image, donor, 512-atom segment).
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
