@@ -29,6 +29,8 @@ CASES = [
     ("ch4h", 16, 1, 1, 31, 2, 0.97, 15.0, 3),     # config 2: parent
     ("ch4h", 16, 0, 1, 80, 2, 0.5, 15.0, 3),      # config 2: umbrella window
     ("ch4h", 2, -1, 0, 0, 0, 0.0, 0.0, 17),
+    ("ch4h", 32, 2, 0, 0, 2, 0.97, 0.0, 2),       # four warps per trajectory: tensor-core transform with 4 row tiles
+    ("ch4h", 8, 0, 1, 40, 2, 0.9, 15.0, 3),       # one warp per trajectory
     ("brh2", 16, 0, 1, 40, 2, 0.9, 15.0, 3),      # DIM-3C Br + H2, umbrella window
     ("brh2", 8, 1, 1, 31, 2, 0.98, 15.0, 2),      # constrained parent
     ("brh2", 32, 2, 0, 0, 2, 0.98, 0.0, 3),       # child trajectories
