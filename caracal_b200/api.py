@@ -467,7 +467,7 @@ _PES_MASS = {_l.PES_H3: ["H"] * 3, _l.PES_OH3: ["O", "H", "H", "H"], _l.PES_CH4H
              _l.PES_BRH2: ["H", "BR", "H"], _l.PES_O3: ["O", "O", "O"],
              _l.PES_CH4OH: ["H", "C", "H", "H", "H", "O", "H"], _l.PES_GEH4OH: ["H", "GE", "H", "H", "H", "O", "H"],
              _l.PES_CH4CN: ["H", "C", "H", "H", "H", "C", "N"],
-             _l.PES_CLNH3: ["H", "N", "H", "H", "CL"], _l.PES_NH3OH: ["H", "N", "H", "H", "O", "H"]}
+             _l.PES_CLNH3: ["H", "N", "H", "H", "CL"], _l.PES_NH3OH: ["H", "N", "H", "H", "O", "H"], _l.PES_H2CO: ["C", "O", "H", "H"]}
 _egrad_handles = {}
 
 
@@ -518,6 +518,11 @@ def egrad_clnh3(q, Natoms=5, Nbeads=None):
 
 def egrad_nh3oh(q, Natoms=6, Nbeads=None):
     return egrad(_l.PES_NH3OH, q, Natoms, Nbeads)
+
+
+def egrad_h2co(q, Natoms=4, Nbeads=None):
+    """egrad_h2co(cood,natoms,e_evb,pot_grad,info) of main_h2co.f90:3170 takes one structure; here a batch of images"""
+    return egrad(_l.PES_H2CO, q, Natoms, Nbeads)
 
 
 def egrad_ch4h(q, Natoms=6, Nbeads=None):

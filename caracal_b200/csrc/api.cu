@@ -15,6 +15,7 @@
 #include "pes_brh2.cuh"
 #include "pes_o3.cuh"
 #include "pes_nh3x.cuh"
+#include "pes_h2co.cuh"
 #include "transform_bench.cuh"
 #include "pes_ch4oh.cuh"
 #include "traj_inst.cuh"
@@ -303,7 +304,7 @@ __global__ void reduce_kappa_kernel(const unsigned char* theta, const double* we
 // ---- dispatch --------------------------------------------------------------------------------
 static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode = 0)
 {
-    static const traj_launch_fn table[10][3] = {
+    static const traj_launch_fn table[11][3] = {
         {launch_h3_verlet, launch_h3_mdinit, launch_h3_recross},
         {launch_oh3_verlet, launch_oh3_mdinit, launch_oh3_recross},
         {launch_ch4h_verlet, launch_ch4h_mdinit, launch_ch4h_recross},
@@ -313,7 +314,8 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
         {launch_geh4oh_verlet, launch_geh4oh_mdinit, launch_geh4oh_recross},
         {launch_ch4cn_verlet, launch_ch4cn_mdinit, launch_ch4cn_recross},
         {launch_clnh3_verlet, launch_clnh3_mdinit, launch_clnh3_recross},
-        {launch_nh3oh_verlet, launch_nh3oh_mdinit, launch_nh3oh_recross}};
+        {launch_nh3oh_verlet, launch_nh3oh_mdinit, launch_nh3oh_recross},
+        {launch_h2co_verlet, launch_h2co_mdinit, launch_h2co_recross}};
     int row;
     switch (h->pes) {
     case CRCL_PES_H3: row = 0; break;
@@ -326,6 +328,7 @@ static int launch_traj(crcl_handle h, int kind, const TrajArgs& A, int bias_mode
     case CRCL_PES_CH4CN: row = 7; break;
     case CRCL_PES_CLNH3: row = 8; break;
     case CRCL_PES_NH3OH: row = 9; break;
+    case CRCL_PES_H2CO: row = 10; break;
     default: return fail(h, CRCL_ENOSUP, "no device trajectory kernel for this PES id");
     }
     if (A.ntraj <= 0) return CRCL_OK;
@@ -380,6 +383,7 @@ static int pes_natoms(int pes)
     case CRCL_PES_CH4CN: return 7;
     case CRCL_PES_CLNH3: return 5;
     case CRCL_PES_NH3OH: return 6;
+    case CRCL_PES_H2CO: return 4;
     }
     return -1;
 }
@@ -1460,6 +1464,7 @@ int crcl_egrad_dev(crcl_handle h, int pes_id, const double* d_q, int natoms, int
     case CRCL_PES_CH4CN: egrad_kernel<PesCH4CN><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_CLNH3: egrad_kernel<PesClNH3><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     case CRCL_PES_NH3OH: egrad_kernel<PesNH3OH><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
+    case CRCL_PES_H2CO: egrad_kernel<PesH2CO><<<grid, tpb, 0, h->stream>>>(d_q, nimg, d_V, d_dVdq, d_info); break;
     default: return fail(h, CRCL_ENOSUP, "unknown PES id");
     }
     if (h->timed && !h->capturing) cudaEventRecord(h->ev1, h->stream);

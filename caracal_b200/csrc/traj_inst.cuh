@@ -92,5 +92,8 @@ CRCL_DECLARE_TRAJ(launch_clnh3_recross);
 CRCL_DECLARE_TRAJ(launch_nh3oh_verlet);
 CRCL_DECLARE_TRAJ(launch_nh3oh_mdinit);
 CRCL_DECLARE_TRAJ(launch_nh3oh_recross);
+CRCL_DECLARE_TRAJ(launch_h2co_verlet);
+CRCL_DECLARE_TRAJ(launch_h2co_mdinit);
+CRCL_DECLARE_TRAJ(launch_h2co_recross);
 
 }  // namespace crcl

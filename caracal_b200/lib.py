@@ -15,9 +15,9 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 c_u32_p = ctypes.POINTER(ctypes.c_uint32)
 
 PES_NONE, PES_H3, PES_OH3, PES_CH4H, PES_BRH2, PES_O3, PES_QMDFF, PES_DGEVB, PES_WATER, PES_HOSTCB = 0, 1, 2, 3, 4, 5, 10, 11, 12, 100
-PES_CH4OH, PES_GEH4OH, PES_CH4CN, PES_CLNH3, PES_NH3OH = 6, 7, 8, 9, 13
-PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H, "brh2": PES_BRH2, "o3": PES_O3, "ch4oh": PES_CH4OH, "geh4oh": PES_GEH4OH, "ch4cn": PES_CH4CN, "clnh3": PES_CLNH3, "nh3oh": PES_NH3OH}
-PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6, PES_BRH2: 3, PES_O3: 3, PES_CH4OH: 7, PES_GEH4OH: 7, PES_CH4CN: 7, PES_CLNH3: 5, PES_NH3OH: 6}
+PES_CH4OH, PES_GEH4OH, PES_CH4CN, PES_CLNH3, PES_NH3OH, PES_H2CO = 6, 7, 8, 9, 13, 14
+PES_IDS = {"h3": PES_H3, "oh3": PES_OH3, "ch4h": PES_CH4H, "brh2": PES_BRH2, "o3": PES_O3, "ch4oh": PES_CH4OH, "geh4oh": PES_GEH4OH, "ch4cn": PES_CH4CN, "clnh3": PES_CLNH3, "nh3oh": PES_NH3OH, "h2co": PES_H2CO}
+PES_NATOMS = {PES_H3: 3, PES_OH3: 4, PES_CH4H: 6, PES_BRH2: 3, PES_O3: 3, PES_CH4OH: 7, PES_GEH4OH: 7, PES_CH4CN: 7, PES_CLNH3: 5, PES_NH3OH: 6, PES_H2CO: 4}
 TRANSFORM_REFERENCE, TRANSFORM_EXACT = 0, 1
 PATH_AUTO, PATH_FUSED, PATH_SPLIT = 0, 1, 2
 ERRORS = {0: "CRCL_OK", -1: "CRCL_ENODEV", -2: "CRCL_EINVAL", -3: "CRCL_ENOMEM", -4: "CRCL_ECUDA",

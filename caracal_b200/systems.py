@@ -118,6 +118,14 @@ def nh3oh_ts():
     return q / BOHR
 
 
+def h2co_ts():
+    """formaldehyde on its way to H2 + CO (molecular channel): planar, both hydrogens swung to one side of the C-O axis,
+    C-H 1.10 / 1.60 A, H-H 1.25 A.  Atom order C, O, H, H (main_h2co.f90:3182)."""
+    q = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 1.17], [1.05, 0.0, -0.33], [1.30, 0.0, -0.93]])
+    q[3] = q[2] + (q[3] - q[2]) / np.linalg.norm(q[3] - q[2]) * 1.25
+    return q / BOHR
+
+
 SYSTEMS = {
     "h3": dict(pes="h3", symbols=["H", "H", "H"], ts=h3_ts,
                # examples/calc_rate/h+h2/rate.key: reactant1 1 2, reactant2 3, bond_form 2-3, bond_break 1-2
@@ -141,6 +149,9 @@ SYSTEMS = {
                   mecha=dict(bond_form=[[1, 5]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4], [5]], dist_inf=16.0)),
     "nh3oh": dict(pes="nh3oh", symbols=["H", "N", "H", "H", "O", "H"], ts=nh3oh_ts,
                   mecha=dict(bond_form=[[1, 5]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4], [5, 6]], dist_inf=16.0)),
+    # H2 + CO -> H2CO read as an association: both C-H bonds form, the H-H bond breaks
+    "h2co": dict(pes="h2co", symbols=["C", "O", "H", "H"], ts=h2co_ts,
+                 mecha=dict(bond_form=[[1, 3], [1, 4]], bond_break=[[3, 4]], reactants=[[1, 2], [3, 4]], dist_inf=16.0)),
     "ch4h": dict(pes="ch4h", symbols=["H", "C", "H", "H", "H", "H"], ts=ch5_ts,
                  # reactant1 1 2 3 4 5, reactant2 6, bond_form 1-6, bond_break 2-1
                  mecha=dict(bond_form=[[1, 6]], bond_break=[[2, 1]], reactants=[[1, 2, 3, 4, 5], [6]], dist_inf=16.0)),

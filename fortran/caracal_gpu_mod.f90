@@ -12,7 +12,7 @@ implicit none
 
 integer(c_int), parameter :: CRCL_PES_H3 = 1, CRCL_PES_OH3 = 2, CRCL_PES_CH4H = 3, CRCL_PES_BRH2 = 4, CRCL_PES_O3 = 5, &
                              CRCL_PES_CH4OH = 6, CRCL_PES_GEH4OH = 7, CRCL_PES_CH4CN = 8, CRCL_PES_CLNH3 = 9, &
-                             CRCL_PES_NH3OH = 13, CRCL_PES_WATER = 12
+                             CRCL_PES_NH3OH = 13, CRCL_PES_H2CO = 14, CRCL_PES_WATER = 12
 integer(c_int), parameter :: CRCL_PES_QMDFF = 10, CRCL_PES_DGEVB = 11, CRCL_PES_HOSTCB = 100
 type(c_ptr), save :: crcl_h = c_null_ptr        ! one handle per MPI rank / GPU
 !     per-trajectory status bits (include/caracal_gpu.h): SHAKE_FAIL 1, NAN 2, SINGULAR 4, ENERGY 8, PESWARN 16,

@@ -43,6 +43,9 @@ extern "C" {
 #define CRCL_PES_CLNH3 9 /* "clnh3" egrad_clnh3.f NH3 + Cl (Monge-Palacios, Rangel, Corchado, Espinosa-Garcia 2012), atoms H,N,H,H,Cl */
 #define CRCL_PES_NH3OH 13 /* "nh3oh" egrad_nh3oh.f NH3 + OH (Monge-Palacios, Rangel, Espinosa-Garcia 2013), atoms H,N,H,H,O,H; the gradient is the
                              reference's own forward difference of the energy (POT_nh3oh :283-296) */
+#define CRCL_PES_H2CO 14 /* "h2co" main_h2co.f90 egrad_h2co: H2CO fit in Morse variables, atoms C,O,H,H; the gradient is the reference's
+                            own central difference (step 0.001 bohr); info / status bit 1 where the reference leaves the fit
+                            (r(H-H) >= 8 bohr: hcopot needs a parameter file the reference does not ship) */
 #define CRCL_PES_QMDFF 10 /* one QMDFF (gradient.f90:341-362): ff_eg + ff_nonb, tables via crcl_set_qmdff */
 #define CRCL_PES_DGEVB 11 /* two QMDFFs + DG-EVB coupling (gradient.f90:365-537): crcl_set_qmdff,
                              crcl_set_qmdff2, crcl_set_dgevb */

@@ -41,6 +41,8 @@ namespace cbe_nh3oh {
 #include "pes_nh3oh.c"
 }
 
+#include "pes_h2co.c"
+
 typedef void (*egrad_fn)(const real*, int, int, real*, real*, int*);
 
 static void census(const char* name, egrad_fn fn, int nat, const double* ts, int n, bool last)
@@ -102,7 +104,11 @@ int main()
     const double nh3oh[18] = {2.0171806725, 0.0, 0.8085266642, 0.0, 0.0, 0.0, -0.8893135660, 1.5403362803, 0.7129095978,
                               -0.8893135660, -1.5403362803, 0.7129095978, 4.2974718675, 0.0, 1.7225133281,
                               3.9213112830, 0.0, 3.5165362123};
-    census("nh3oh", cbe_nh3oh::oracle_egrad_nh3oh_real, 6, nh3oh, 2000, true);
+    census("nh3oh", cbe_nh3oh::oracle_egrad_nh3oh_real, 6, nh3oh, 2000, false);
+    // caracal_b200/systems.py h2co_ts
+    const double h2co[12] = {0.0, 0.0, 0.0, 0.0, 0.0, 1.17 / b, 1.05 / b, 0.0, -0.33 / b,
+                             (1.05 + 1.25 * 0.384615) / b, 0.0, (-0.33 - 1.25 * 0.923077) / b};
+    census("h2co", oracle_egrad_h2co_real, 4, h2co, 50, true);
     printf("}\n");
     return 0;
 }

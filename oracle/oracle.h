@@ -36,6 +36,8 @@ void oracle_egrad_geh4oh_real(const real *q, int natoms, int nbeads, real *V, re
 void oracle_geh4oh_parts_real(const real *q21, real parts[3], real *V);
 void oracle_egrad_ch4cn_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_ch4cn_parts_real(const real *q21, real parts[3], real *V);
+void oracle_egrad_h2co_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
+void oracle_h2co_energy_real(const real *q12, real *V, int *far);
 void oracle_egrad_clnh3_real(const real *q, int natoms, int nbeads, real *V, real *dVdq, int *info);
 void oracle_clnh3_parts_real(const real *q15, real parts[3], real *V);
 void oracle_clnh3_parts_grad_real(const real *q15, real parts[3], real *gparts);

@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 dp = ctypes.POINTER(ctypes.c_double)
 ip = ctypes.POINTER(ctypes.c_int)
-PES = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8, "clnh3": 9, "nh3oh": 13}
+PES = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8, "clnh3": 9, "nh3oh": 13, "h2co": 14}
 
 
 def build(force=False):
@@ -105,7 +105,7 @@ def egrad(pes, q, exact=False):
     """Oracle of egrad_<pes> on [nimg][natoms][3]; loops images the way gradient.f90 does."""
     q = np.ascontiguousarray(q, dtype=np.float64)
     pid = PES[pes] if isinstance(pes, str) else pes
-    nat = {1: 3, 2: 4, 3: 6, 4: 3, 5: 3, 6: 7, 7: 7, 8: 7, 9: 5, 13: 6}[pid]
+    nat = {1: 3, 2: 4, 3: 6, 4: 3, 5: 3, 6: 7, 7: 7, 8: 7, 9: 5, 13: 6, 14: 4}[pid]
     qq = q.reshape(-1, nat, 3)
     V = np.zeros(qq.shape[0])
     g = np.zeros_like(qq)

@@ -40,6 +40,7 @@ void oracle_geh4oh_parts_grad(const double *q21, double parts[3], double *gparts
 void oracle_clnh3_parts(const double *q15, double parts[3], double *V) { oracle_clnh3_parts_real(q15, parts, V); }
 void oracle_clnh3_parts_grad(const double *q15, double parts[3], double *gparts) { oracle_clnh3_parts_grad_real(q15, parts, gparts); }
 void oracle_clnh3_parts_frozen(const double *q15, double r0, double parts[3], double *V) { clnh3_parts_frozen_real(q15, r0, parts, V); }
+void oracle_h2co_energy(const double *q12, double *V, int *far) { oracle_h2co_energy_real(q12, V, far); }
 void oracle_nh3oh_parts(const double *q18, double parts[3], double *V) { oracle_nh3oh_parts_real(q18, parts, V); }
 void oracle_ch4cn_parts_grad(const double *q21, double parts[3], double *gparts) { oracle_ch4cn_parts_grad_real(q21, parts, gparts); }
 void oracle_ch4oh_parts(const double *q21, double parts[3], double *V)
@@ -61,6 +62,7 @@ int oracle_egrad(int pes, const double *q, int natoms, int nimg, double *V, doub
     case ORC_PES_CH4CN: oracle_egrad_ch4cn_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_CLNH3: oracle_egrad_clnh3_real(q, natoms, nimg, V, dVdq, &info); break;
     case ORC_PES_NH3OH: oracle_egrad_nh3oh_real(q, natoms, nimg, V, dVdq, &info); break;
+    case ORC_PES_H2CO: oracle_egrad_h2co_real(q, natoms, nimg, V, dVdq, &info); break;
     default: return -1;
     }
     return info;

@@ -266,6 +266,9 @@ void orc_gradient(orc_sys *s, const double *xyz, double *e, double *g)
     case ORC_PES_NH3OH:
         oracle_egrad_nh3oh_real(xyz, s->natoms, 1, e, g, &info);
         break;
+    case ORC_PES_H2CO:
+        oracle_egrad_h2co_real(xyz, s->natoms, 1, e, g, &info);
+        break;
     default:
         *e = 0.0;
         memset(g, 0, sizeof(double) * 3 * s->natoms);

@@ -24,6 +24,7 @@
 #define ORC_PES_CH4CN 8
 #define ORC_PES_CLNH3 9
 #define ORC_PES_NH3OH 13
+#define ORC_PES_H2CO 14
 
 #ifdef __cplusplus
 extern "C" {

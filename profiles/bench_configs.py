@@ -184,8 +184,8 @@ for nb, nsteps in ((1, 200), (8, 200)):
     g.close()
 
 # ---- N4: the 7-atom CBE-family surfaces (one-lane PesCBE1<K>), recrossing children at config 2's shape ----------
-for name in ("ch4oh", "geh4oh", "clnh3", "nh3oh"):
-    nb, npairs, evol = 16, 512, 500
+for name in ("ch4oh", "geh4oh", "clnh3", "nh3oh", "h2co"):
+    nb, npairs, evol = 16, 512, (100 if name == "h2co" else 500)
     g, o = C.make_pair(name, nb)
     g.set_seed(C.SEED)
     qp = np.array([C.ring_polymer(name, nb, rng, 0.01) for _ in range(8)])

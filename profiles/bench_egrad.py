@@ -17,7 +17,7 @@ census = json.load(open(os.path.join(ROOT, "oracle", "flop_census.json")))
 rows = []
 rng = np.random.default_rng(0)
 peak = dmma = None
-for name in ("h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh"):
+for name in ("h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh", "h2co"):
     g, _ = C.make_pair(name, 1)
     if peak is None:
         peak, dmma = g.measure_fp64_tflops(16384), g.measure_dmma_tflops(16384)

@@ -47,7 +47,20 @@ def tol_grad(name):
     Eh/bohr, and two correct evaluations of the energy differ by tens of ulps (different libm / FMA contraction), so the
     parity bar of THAT gradient is 5e-9 relative (gradients are ~0.1 Eh/bohr: ~80 ulps of the energy); the energy itself
     is held to TOL_EG like every other surface."""
+    if name == "h2co":
+        # egrad_h2co: central differences of step 1e-3 bohr (main_h2co.f90:3231-3304) of an ill-conditioned sum, see tol_energy:
+        # 5e-13 Eh / 2e-3 bohr = 2.5e-10 Eh/bohr on gradients of ~0.05-0.1 Eh/bohr; observed 3e-9 - 6e-9 relative
+        return 5e-8
     return 5e-9 if name == "nh3oh" else TOL_EG
+
+
+def tol_energy(name):
+    """Energy tolerance per image, relative to max(|E|, 1e-3 Eh).  The H2CO fit is a sum of 1561 terms with sum |c_k B_k| ~ 9e3 Eh
+    for a value of ~0.1 Eh (main_h2co.f90:3220-3225): the reference raises its variables to REAL powers with libm pow, any other
+    correct evaluation of the same powers differs in last bits of terms of up to 250 Eh, i.e. by ~5e-13 Eh in the sum (observed
+    4e-13 - 5e-13).  That is 1e-10 relative for |E| >= 5e-3 Eh; close to the fit's zero (its formaldehyde minimum) it is not,
+    hence 1e-9 against the 1e-3 Eh floor for this surface."""
+    return 1e-9 if name == "h2co" else TOL_EG
 
 
 def rel_err_E(a, ref, floor=1e-3):

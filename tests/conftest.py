@@ -28,7 +28,7 @@ def host_harness():
     so = os.path.join(d, "libpes_host.so")
     src = os.path.join(d, "pes_host.cu")
     deps = [src] + [os.path.join(ROOT, "caracal_b200", "csrc", f)
-                    for f in ("pes_h3.cuh", "pes_oh3.cuh", "pes_ch4h.cuh", "pes_brh2.cuh", "pes_o3.cuh", "pes_ch4oh.cuh", "pes_nh3x.cuh", "xi.cuh", "rng.cuh",
+                    for f in ("pes_h3.cuh", "pes_oh3.cuh", "pes_ch4h.cuh", "pes_brh2.cuh", "pes_o3.cuh", "pes_ch4oh.cuh", "pes_nh3x.cuh", "pes_h2co.cuh", "pes_h2co_tables.cuh", "xi.cuh", "rng.cuh",
                               "crcl_common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
         subprocess.run(["nvcc", "-x", "cu", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",

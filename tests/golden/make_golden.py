@@ -32,7 +32,7 @@ def main():
         q = np.concatenate([C.SYSTEMS[name]["ts"]()[None], C.ts_cloud(name, 15, 0.15, r2)])
         V, g, _ = O.egrad(name, q)
         pes[name] = dict(q=q.tolist(), V=V.tolist(), g=g.tolist())
-    for k, name in enumerate(("clnh3", "nh3oh")):
+    for k, name in enumerate(("clnh3", "nh3oh", "h2co")):
         r2 = np.random.default_rng(C.SEED + 200 + k)
         q = np.concatenate([C.SYSTEMS[name]["ts"]()[None], C.ts_cloud(name, 15, 0.15, r2)])
         V, g, _ = O.egrad(name, q)

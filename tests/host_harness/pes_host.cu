@@ -8,6 +8,7 @@
 #include "../../caracal_b200/csrc/pes_o3.cuh"
 #include "../../caracal_b200/csrc/pes_ch4oh.cuh"
 #include "../../caracal_b200/csrc/pes_nh3x.cuh"
+#include "../../caracal_b200/csrc/pes_h2co.cuh"
 
 template <class PES>
 static int run(const double* q, int nimg, double* V, double* g)
@@ -31,6 +32,7 @@ extern "C" int hh_egrad(int pes, const double* q, int nimg, double* V, double* g
     case CRCL_PES_CH4CN: return run<crcl::PesCH4CN>(q, nimg, V, g);
     case CRCL_PES_CLNH3: return run<crcl::PesClNH3>(q, nimg, V, g);
     case CRCL_PES_NH3OH: return run<crcl::PesNH3OH>(q, nimg, V, g);
+    case CRCL_PES_H2CO: return run<crcl::PesH2CO>(q, nimg, V, g);
     }
     return -1;
 }

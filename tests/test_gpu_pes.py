@@ -20,7 +20,8 @@ pytestmark = pytest.mark.gpu
                                           ("geh4oh", 0.15, 100000), ("geh4oh", 0.4, 30000),
                                           ("ch4cn", 0.15, 100000), ("ch4cn", 0.4, 30000),
                                           ("clnh3", 0.15, 100000), ("clnh3", 0.4, 30000),
-                                          ("nh3oh", 0.15, 100000), ("nh3oh", 0.4, 30000)])
+                                          ("nh3oh", 0.15, 100000), ("nh3oh", 0.4, 30000),
+                                          ("h2co", 0.1, 400), ("h2co", 0.3, 400)])   # h2co: 8 ms per oracle gradient
 def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     rng = np.random.default_rng(C.SEED)
     q = C.ts_cloud(name, n, sigma, rng)
@@ -28,7 +29,7 @@ def test_egrad_matches_oracle(gpu, oracle, name, sigma, n):
     Vd, gd, info = gpu.egrad(name, q)
     ok = np.isfinite(Vo)
     assert ok.mean() > 0.999
-    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.tol_energy(name)
     assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)      # 1e-10; nh3oh: see tests/common.py tol_grad
 
 
@@ -38,7 +39,7 @@ def test_egrad_golden(gpu):
     for name, rec in G.items():
         q = np.array(rec["q"])
         V, g, _ = gpu.egrad(name, q)
-        assert C.rel_err_E(V, np.array(rec["V"])).max() < C.TOL_EG
+        assert C.rel_err_E(V, np.array(rec["V"])).max() < C.tol_energy(name)
         assert C.rel_err_G(g, np.array(rec["g"])).max() < C.tol_grad(name)
 
 
@@ -83,13 +84,13 @@ def test_h3_compact_branch_and_warning_bits(gpu, oracle):
     assert info == oinfo == 2
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh", "h2co"])
 def test_egrad_far_apart_matches_oracle(gpu, oracle, name):
     """reactants 8 ... 45 bohr apart, where the umbrella windows of a rate calculation go (DIST_INF): arguments far
     outside the saddle-point clouds (BKMP2's H2 singlet curve calls exp(-2e12) at 30 bohr); the CPU twin of this test
     (tests/test_host_harness.py::test_pes_functor_far_apart) explains the 35 bohr of Br + H2"""
     rng = np.random.default_rng(17)
-    q = C.ts_cloud(name, 20000, 0.1, rng)
+    q = C.ts_cloud(name, 300 if name == "h2co" else 20000, 0.1, rng)
     frag = [i - 1 for i in C.SYSTEMS[name]["mecha"]["reactants"][-1]]
     rest = [i for i in range(q.shape[1]) if i not in frag]
     d = q[:, frag].mean(axis=1) - q[:, rest].mean(axis=1)
@@ -100,7 +101,7 @@ def test_egrad_far_apart_matches_oracle(gpu, oracle, name):
     Vd, gd, _ = gpu.egrad(name, q)
     ok = np.isfinite(Vo) & np.isfinite(go.reshape(len(q), -1)).all(axis=1)
     assert ok.mean() > 0.99 and np.isfinite(Vd[ok]).all() and np.isfinite(gd[ok]).all()
-    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.tol_energy(name)
     assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 

@@ -21,7 +21,7 @@ def parents(g, name, nb, nparent, xi_dag, steps=40, seed=5):
 
 @pytest.mark.parametrize("name,nb,npairs,evol", [("h3", 8, 12, 120), ("ch4h", 16, 6, 80), ("oh3", 64, 2, 40),
                                                  ("h3", 1, 7, 50), ("brh2", 16, 5, 60), ("ch4oh", 8, 4, 60), ("geh4oh", 8, 3, 50), ("ch4cn", 8, 3, 50),
-                                                 ("clnh3", 8, 3, 50), ("nh3oh", 8, 3, 50)])
+                                                 ("clnh3", 8, 3, 50), ("nh3oh", 8, 3, 50), ("h2co", 4, 2, 30)])
 def test_kappa_sums_match_oracle(gpu, oracle, name, nb, npairs, evol):
     g, o = C.make_pair(name, nb)
     g.set_seed(C.SEED)

@@ -49,6 +49,8 @@ CASES = [
     ("nh3oh", 8, 0, 1, 40, 2, 0.9, 15.0, 3),      # NH3 + OH (numeric gradient, four lanes per bead)
     ("nh3oh", 16, 2, 0, 0, 2, 0.98, 0.0, 2),      # child trajectories
     ("nh3oh", 1, 0, 1, 50, 2, 0.95, 15.0, 5),     # one bead
+    ("h2co", 8, 0, 1, 40, 2, 0.9, 15.0, 2),       # H2CO fit (central-difference gradient, four lanes per bead)
+    ("h2co", 4, 2, 0, 0, 2, 0.98, 0.0, 2),        # child trajectories
 ]
 
 

@@ -12,7 +12,7 @@ from tests import common as C
 
 dp = ctypes.POINTER(ctypes.c_double)
 ip = ctypes.POINTER(ctypes.c_int)
-PID = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8, "clnh3": 9, "nh3oh": 13}
+PID = {"h3": 1, "oh3": 2, "ch4h": 3, "brh2": 4, "o3": 5, "ch4oh": 6, "geh4oh": 7, "ch4cn": 8, "clnh3": 9, "nh3oh": 13, "h2co": 14}
 
 
 def hh_egrad(H, name, q):
@@ -27,25 +27,25 @@ def hh_egrad(H, name, q):
                                         ("ch4h", 0.15), ("ch4h", 0.4), ("brh2", 0.15), ("brh2", 0.5), ("o3", 0.15), ("o3", 0.4),
                                         ("ch4oh", 0.15), ("ch4oh", 0.4), ("geh4oh", 0.15), ("geh4oh", 0.4),
                                         ("ch4cn", 0.15), ("ch4cn", 0.4), ("clnh3", 0.15), ("clnh3", 0.4),
-                                        ("nh3oh", 0.15), ("nh3oh", 0.4)])
+                                        ("nh3oh", 0.15), ("nh3oh", 0.4), ("h2co", 0.1), ("h2co", 0.3)])
 def test_pes_functor_matches_oracle(oracle, host_harness, name, sigma):
     rng = np.random.default_rng(C.SEED)
-    q = C.ts_cloud(name, 20000, sigma, rng)
+    q = C.ts_cloud(name, 300 if name == "h2co" else 20000, sigma, rng)   # h2co: 390 000 libm pow calls per oracle gradient
     Vo, go, _ = oracle.egrad(name, q)
     Vd, gd = hh_egrad(host_harness, name, q)
     ok = np.isfinite(Vo)
     assert ok.mean() > 0.999
-    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.tol_energy(name)
     assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 
-@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh"])
+@pytest.mark.parametrize("name", ["h3", "oh3", "ch4h", "brh2", "o3", "ch4oh", "geh4oh", "ch4cn", "clnh3", "nh3oh", "h2co"])
 def test_pes_functor_far_apart(oracle, host_harness, name):
     """reactants 8 ... 45 bohr apart (the umbrella windows of a rate calculation reach DIST_INF): the curves are evaluated
     far outside the region the saddle-point clouds sample -- BKMP2's H2 singlet curve, for one, calls exp(-2e12) at
     30 bohr, which the branch-free exp of the device code has to survive"""
     rng = np.random.default_rng(17)
-    q = C.ts_cloud(name, 4000, 0.1, rng)
+    q = C.ts_cloud(name, 200 if name == "h2co" else 4000, 0.1, rng)
     frag = [i - 1 for i in C.SYSTEMS[name]["mecha"]["reactants"][-1]]
     rest = [i for i in range(q.shape[1]) if i not in frag]
     d = q[:, frag].mean(axis=1) - q[:, rest].mean(axis=1)
@@ -59,7 +59,7 @@ def test_pes_functor_far_apart(oracle, host_harness, name):
     Vd, gd = hh_egrad(host_harness, name, q)
     ok = np.isfinite(Vo) & np.isfinite(go.reshape(len(q), -1)).all(axis=1)
     assert ok.mean() > 0.99 and np.isfinite(Vd[ok]).all()
-    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.TOL_EG
+    assert C.rel_err_E(Vd[ok], Vo[ok]).max() < C.tol_energy(name)
     assert C.rel_err_G(gd[ok], go[ok]).max() < C.tol_grad(name)
 
 
