@@ -3,6 +3,8 @@
 set -x
 O=gpurun_out/r2ab
 mkdir -p $O
+# NOTE (found afterwards): there is no comm.cu -- this removed nothing, no unit was stale in this capture; r2ad repeats it
+# with a stamp that exists
 rm -f caracal_b200/build/comm.o.sha
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 $TR --nproc-per-node 2 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > $O/bench_n2.json 2> $O/bench_n2.err

@@ -4,6 +4,8 @@
 set -x
 O=gpurun_out/r2z
 mkdir -p $O
+# NOTE (found afterwards): there is no comm.cu -- this removed nothing, no unit was stale in this capture; r2ad repeats it
+# with a stamp that exists
 rm -f caracal_b200/build/comm.o.sha
 for i in 1 2 3 4 5 6; do
   (python -c "import caracal_b200; caracal_b200.build_if_needed(); caracal_b200.load(); print('rank-like process $i: library loaded')" > $O/lock_$i.log 2>&1 &)

@@ -59,3 +59,23 @@ def test_fails_loudly_without_gpu():
         caracal_b200.RPMD("h3", 16, [1837.0] * 3, 1000.0, 4.0)
     with pytest.raises(caracal_b200.CaracalGpuError):
         caracal_b200.egrad_h3([[0, 0, 0], [0, 0, 1.4], [0, 0, 4.0]])
+
+
+def test_concurrent_builds_do_not_corrupt_the_library():
+    """N ranks of a torchrun job all call build_if_needed(); with a stale translation unit they used to compile and link over
+    each other and a rank would dlopen a half-written file (capture r2s: 'invalid ELF header' at N = 8).  Now a file lock
+    serialises them and the link goes to a temporary name that is renamed into place: five processes, one stale unit."""
+    import subprocess
+    import sys
+    from caracal_b200 import build as B
+    B.build()
+    stamp = os.path.join(B.OBJ, "water_kernels.o.sha")     # a unit that compiles in seconds
+    assert os.path.exists(stamp)
+    os.remove(stamp)
+    code = "import caracal_b200, ctypes; caracal_b200.build_if_needed(); ctypes.CDLL(caracal_b200.LIB_PATH); print('ok')"
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for _ in range(5)]
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 and o[0].strip() == "ok" for p, o in zip(procs, outs)), [o[1][-300:] for o in outs]
+    assert os.path.exists(stamp)
+    assert not [f for f in os.listdir(B.HERE) if ".so.tmp." in f]
