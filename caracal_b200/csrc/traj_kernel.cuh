@@ -274,6 +274,7 @@ struct Traj {
     bool want_epot; // false: forces() skips the all-reduce of the bead energies (recrossing children)
     const double* fk;
     const double2* mc;  // shared {mass, 1/mass}[component] (SmemLayout::DMMA only)
+    double mass_sum;    // sum of the atomic masses in atom order (transrot.f90:87-92)
     double xi_ideal, k_force, xi_real, epot;
     double vnh[4], qnh[4];
     int nfree, status;
@@ -295,6 +296,9 @@ struct Traj {
         xis = ham + NC + Lay::SYM_STAGE;
         coop = xis + Lay::XI_SCR + grp.bead * (L * coop_scratch<PES>::value);
         want_epot = true;
+        mass_sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < NAT; j++) mass_sum += A.mass[j];
         status = 0;
         xi_real = 0.0;
         epot = 0.0;
@@ -735,16 +739,16 @@ struct Traj {
         double s[15];
 #pragma unroll
         for (int i = 0; i < 15; i++) s[i] = 0.0;
-        double mt = 0.0;
-#pragma unroll
-        for (int j = 0; j < NAT; j++) mt += A.mass[j];
+        // masses from the shared {mass, 1/mass} table of the owned components and their sum taken once per kernel: the
+        // global loads of the mass array (6 + 3 NO per step, dependent) were long-scoreboard stalls of the biased step
+        const double msum = mass_sum;
         double vk[NO];   // velocity of the owned components, p / m as the reference divides it (kept for the last loop)
 #pragma unroll
         for (int k = 0; k < NO; k++) {
             vk[k] = 0.0;
             if (oc[k] >= 0) {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
-                const double w = A.mass[j];
+                const double w = mt[k].x;
                 const double v = CRCL_DIV(P(c), w);
                 vk[k] = v;
                 const double qx = Q(3 * j), qy = Q(3 * j + 1), qz = Q(3 * j + 2);
@@ -773,7 +777,7 @@ struct Traj {
 #pragma unroll
             for (int i = 0; i < 9; i++) s[i] = s9[i];
         }
-        const double totmass = (mt * NB) * NB;
+        const double totmass = (msum * NB) * NB;
         double vtot[3], ctr[3], mang[3];
 #pragma unroll
         for (int d = 0; d < 3; d++) {
@@ -788,7 +792,7 @@ struct Traj {
         for (int k = 0; k < NO; k++)
             if (oc[k] >= 0 && (oc[k] % 3) == 0) {
                 const int j = oc[k] / 3;
-                const double w = A.mass[j];
+                const double w = mt[k].x;
                 const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
                 xx += xd * xd * w;
                 xy += xd * yd * w;
@@ -827,7 +831,7 @@ struct Traj {
         for (int k = 0; k < NO; k++)
             if (oc[k] >= 0) {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
-                const double w = A.mass[j];
+                const double w = mt[k].x;
                 const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
                 double v = vk[k] - vtot[d];
                 if (d == 0)
