@@ -40,13 +40,54 @@ static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, c
     return cudaGetLastError();
 }
 
+// A one-lane surface spread over L threads per bead for SMALL batches of one-bead trajectories: the start-structure chain
+// of a rate calculation (calc_rate.f90:651-1148) is 111 one-bead trajectories one after the other, i.e. a single thread
+// of the GPU at 4 400 instructions per step, 42 % of them the serial form of xi and its Hessian products, 30 % the
+// per-component loops of the step (profiles/r2ai_chain_h3_source.txt).  With L >= 3 NATOMS every lane owns ONE
+// component: the cooperative xi (calc_xi_coop) applies, the loops over the owned components have one trip, Andersen
+// draws its pairs in parallel; the surface itself is evaluated by every lane on the same structure (the same
+// instructions the one thread issued), lane 0 reports the energy.  Batches above CRCL_SPREAD_MAX_TRAJ keep one thread
+// per trajectory: there the throughput of the packed form wins.
+#ifndef CRCL_SPREAD_MAX_TRAJ
+#define CRCL_SPREAD_MAX_TRAJ 1024
+#endif
+template <class P, int L>
+struct PesSpread {
+    static_assert(P::LANES == 1 && 3 * P::NATOMS <= L, "one lane per component");
+    static constexpr int NATOMS = P::NATOMS;
+    static constexpr int ID = P::ID;
+    static constexpr int LANES = L;
+    static constexpr int NOWN = 1;
+    CRCL_HD static __forceinline__ int owned(int lane, int k) { return (k == 0 && lane < 3 * NATOMS) ? lane : -1; }
+    template <class QF>
+    CRCL_HD static __forceinline__ int eval_coop(QF qf, int lane, unsigned, double& V, double* gown)
+    {
+        constexpr int NC = 3 * NATOMS;
+        double x[NC], g[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) x[c] = qf(c);
+        double e;
+        const int w = P::eval(x, e, g);
+        V = (lane == 0) ? e : 0.0;
+        double own = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; c++) own = (c == lane) ? g[c] : own;
+        gown[0] = own;
+        return w;
+    }
+};
+
 template <class PES, int KIND>
 static cudaError_t launch_traj_pes(int nbeads, const TrajArgs& A, int bias_mode, double nose_q,
                                    cudaStream_t s, int* nosup)
 {
     *nosup = 0;
     switch (nbeads) {
-    case 1: return launch_one<PES, KIND, 1>(A, bias_mode, nose_q, s);
+    case 1:
+        if constexpr (PES::LANES == 1 && 3 * PES::NATOMS <= 16) {
+            if (A.ntraj <= CRCL_SPREAD_MAX_TRAJ) return launch_one<PesSpread<PES, 16>, KIND, 1>(A, bias_mode, nose_q, s);
+        }
+        return launch_one<PES, KIND, 1>(A, bias_mode, nose_q, s);
     case 2: return launch_one<PES, KIND, 2>(A, bias_mode, nose_q, s);
     case 4: return launch_one<PES, KIND, 4>(A, bias_mode, nose_q, s);
     case 8: return launch_one<PES, KIND, 8>(A, bias_mode, nose_q, s);

@@ -435,7 +435,7 @@ struct Traj {
         if (NB == 1) {
 #pragma unroll
             for (int k = 0; k < NO; k++)
-                if (own(k)) Qk(k) = Qk(k) + Pk(k) * A.dt / mt[k].x;
+                if (own(k)) Qk(k) = Qk(k) + CRCL_DIV(Pk(k) * A.dt, mt[k].x);   // branch-free quotient: the nine overlap
             return;
         }
         if constexpr (SmemLayout<NAT, NB, L>::DMMA) {

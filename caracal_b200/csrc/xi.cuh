@@ -227,7 +227,9 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
     }
     double Rf[XI_MAXBOND][3], Rb[XI_MAXBOND][3], fi[XI_MAXBOND], bi[XI_MAXBOND];
     double s1 = 0.0, s0u = 0.0;   // s0u: s0 of the unimolecular mechanisms (reactant bond references)
-    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+    // 1/n of the bond and pair counts from the mechanism (exact for 1, 2, 4; one ulp beside the reference's quotient
+    // otherwise): a product instead of a quotient per term
+    const double ifnum = M.inv_form, ibnum = M.inv_break, iterms = M.inv_pairs;
     // ATOM_SHIFT has no bond terms, the unimolecular mechanisms no fragment terms
     const int nform = (M.type == 2) ? 0 : M.form_num, nbreak = (M.type == 2) ? 0 : M.break_num;
     const int nreac = (M.type == 0) ? M.sum_reacs : 0;
@@ -235,13 +237,13 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         const int a1 = M.bb[i][0], a2 = M.bb[i][1];
 #pragma unroll
         for (int d = 0; d < 3; d++) Rb[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
-        const double r = sqrt(Rb[i][0] * Rb[i][0] + Rb[i][1] * Rb[i][1] + Rb[i][2] * Rb[i][2]);
-        bi[i] = 1.0 / r;
-        s1 += (r - M.bref[i]) / bnum;
-        s0u += (r - M.breac[i]) / bnum;
+        double r;
+        sqrt_rsqrt(Rb[i][0] * Rb[i][0] + Rb[i][1] * Rb[i][1] + Rb[i][2] * Rb[i][2], r, bi[i]);
+        s1 += (r - M.bref[i]) * ibnum;
+        s0u += (r - M.breac[i]) * ibnum;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            const double v = Rb[i][d] * bi[i] / bnum;
+            const double v = Rb[i][d] * bi[i] * ibnum;
             ds1[3 * a1 + d] += v;
             ds1[3 * a2 + d] -= v;
         }
@@ -250,13 +252,13 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         const int a1 = M.bf[i][0], a2 = M.bf[i][1];
 #pragma unroll
         for (int d = 0; d < 3; d++) Rf[i][d] = x[3 * a1 + d] - x[3 * a2 + d];
-        const double r = sqrt(Rf[i][0] * Rf[i][0] + Rf[i][1] * Rf[i][1] + Rf[i][2] * Rf[i][2]);
-        fi[i] = 1.0 / r;
-        s1 -= (r - M.fref[i]) / fnum;
-        s0u -= (r - M.freac[i]) / fnum;
+        double r;
+        sqrt_rsqrt(Rf[i][0] * Rf[i][0] + Rf[i][1] * Rf[i][1] + Rf[i][2] * Rf[i][2], r, fi[i]);
+        s1 -= (r - M.fref[i]) * ifnum;
+        s0u -= (r - M.freac[i]) * ifnum;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            const double v = Rf[i][d] * fi[i] / fnum;
+            const double v = Rf[i][d] * fi[i] * ifnum;
             ds1[3 * a1 + d] -= v;
             ds1[3 * a2 + d] += v;
         }
@@ -273,8 +275,6 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
             for (int d = 0; d < 3; d++) com[k][d] += M.wfrag[a] * x[3 * a + d];
         }
     }
-    const int nterms = (M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2;
-    const double fterms = (double)nterms;
     double s0 = 0.0;
     double Red[XI_MAXREAC * (XI_MAXREAC - 1) / 2][3], ri[XI_MAXREAC * (XI_MAXREAC - 1) / 2];
     int np = 0;
@@ -282,22 +282,21 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         for (int j = i + 1; j < nreac; j++, np++) {
 #pragma unroll
             for (int d = 0; d < 3; d++) Red[np][d] = com[j][d] - com[i][d];
-            const double r =
-                sqrt(Red[np][0] * Red[np][0] + Red[np][1] * Red[np][1] + Red[np][2] * Red[np][2]);
-            ri[np] = 1.0 / r;
+            double r;
+            sqrt_rsqrt(Red[np][0] * Red[np][0] + Red[np][1] * Red[np][1] + Red[np][2] * Red[np][2], r, ri[np]);
             s0 += M.R_inf - r;
 #pragma unroll
             for (int a = 0; a < NAT; a++) {
                 const int k = M.frag[a];
                 if (k == i || k == j) {
                     const double sg = (k == i) ? 1.0 : -1.0;
-                    const double w = sg * ri[np] * M.wfrag[a] / fterms;
+                    const double w = sg * ri[np] * M.wfrag[a] * iterms;
 #pragma unroll
                     for (int d = 0; d < 3; d++) ds0[3 * a + d] += Red[np][d] * w;
                 }
             }
         }
-    s0 = s0 / fterms;
+    s0 = s0 * iterms;
     if (M.type == 1) {          // calc_xi.f90:722-728, :765 (ds0 = ds1)
         s0 = s0u;
 #pragma unroll
@@ -314,8 +313,9 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
 
     if (mode == 1) {
         const double D = s0 - s1;
-        xi = s0 / D;
-        const double iD2 = 1.0 / (D * D);
+        const double iD = CRCL_RCP(D);
+        xi = s0 * iD;
+        const double iD2 = iD * iD;
 #pragma unroll
         for (int t = 0; t < 3 * NAT; t++) dxi[t] = (s0 * ds1[t] - s1 * ds0[t]) * iD2;
     } else {
@@ -333,7 +333,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             const int t = 3 * a + d;
-            v[t] = dxi[t] / mass[a];
+            v[t] = CRCL_DIV(dxi[t], mass[a]);
             fs2 += dxi[t] * v[t];
             d1v += ds1[t] * v[t];
             d0v += ds0[t] * v[t];
@@ -348,8 +348,8 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         proj(Rf[i], fi[i], w, o);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            H1v[3 * a1 + d] -= o[d] / fnum;
-            H1v[3 * a2 + d] += o[d] / fnum;
+            H1v[3 * a1 + d] -= o[d] * ifnum;
+            H1v[3 * a2 + d] += o[d] * ifnum;
         }
     }
     for (int i = 0; i < nbreak; i++) {  // breaking bonds: block = +(r^2 I - r r^T)/r^3
@@ -360,8 +360,8 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         proj(Rb[i], bi[i], w, o);
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            H1v[3 * a1 + d] += o[d] / bnum;
-            H1v[3 * a2 + d] -= o[d] / bnum;
+            H1v[3 * a1 + d] += o[d] * ibnum;
+            H1v[3 * a2 + d] -= o[d] * ibnum;
         }
     }
     np = 0;
@@ -384,7 +384,7 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
                 const int k = M.frag[a];
                 if (k == i || k == j) {
                     const double sg = (k == i) ? 1.0 : -1.0;
-                    const double w = -sg * M.wfrag[a] / fterms;
+                    const double w = -sg * M.wfrag[a] * iterms;
 #pragma unroll
                     for (int d = 0; d < 3; d++) H0v[3 * a + d] += w * o[d];
                 }
@@ -395,10 +395,10 @@ CRCL_HD __forceinline__ void calc_xi(const Mech& M, const double* mass, const do
         for (int t = 0; t < 3 * NAT; t++) H0v[t] = H1v[t];
     }
     const double coeff1 = 2.0 * PI_UMBR * beta;
-    fs2 = fs2 / coeff1;
-    const double pref = (-1.0 / beta) / (coeff1 * fs2);
+    fs2 = CRCL_DIV(fs2, coeff1);
+    const double pref = CRCL_DIV(-1.0, beta * (coeff1 * fs2));
     const double D = s0 - s1;
-    const double iD3 = 1.0 / (D * D * D);
+    const double iD3 = CRCL_RCP(D * D * D);
     const double cross2 = 2.0 * (s0 * d1v - s1 * d0v);
 #pragma unroll
     for (int t = 0; t < 3 * NAT; t++) {
@@ -449,10 +449,11 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
     double* s_ds0 = scr;
     double* s_ds1 = scr + NC;
     double* s_v = scr + 2 * NC;
-    const double fnum = (double)M.form_num, bnum = (double)M.break_num;
+    // 1/n of the bond and pair counts from the mechanism (exact for 1, 2, 4; one ulp beside the reference's quotient
+    // otherwise): a product instead of a quotient per term
+    const double ifnum = M.inv_form, ibnum = M.inv_break, iterms = M.inv_pairs;
     const int nform = (M.type == 2) ? 0 : M.form_num, nbreak = (M.type == 2) ? 0 : M.break_num;
     const int nreac = (M.type == 0) ? M.sum_reacs : 0;
-    const double fterms = (double)((M.sum_reacs * M.sum_reacs - M.sum_reacs) / 2);
     auto sel = [](const double (&r)[3], int d) { return d == 0 ? r[0] : (d == 1 ? r[1] : r[2]); };
     // warps of a CTA-wide trajectory that own no component skip the work and pick xi up from shared memory
     const bool work = (T <= 32) || ((tig & ~31) < NC);
@@ -481,20 +482,22 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
         for (int i = 0; i < nbreak; i++) {
             const int a1 = M.bb[i][0], a2 = M.bb[i][1];
             const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
-            const double r = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]), ri = 1.0 / r;
-            s1 += (r - M.bref[i]) / bnum;
-            s0u += (r - M.breac[i]) / bnum;
-            const double v = sel(R, d) * ri / bnum;
+            double r, ri;
+            sqrt_rsqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2], r, ri);
+            s1 += (r - M.bref[i]) * ibnum;
+            s0u += (r - M.breac[i]) * ibnum;
+            const double v = sel(R, d) * ri * ibnum;
             if (a == a1) ds1 += v;
             if (a == a2) ds1 -= v;
         }
         for (int i = 0; i < nform; i++) {
             const int a1 = M.bf[i][0], a2 = M.bf[i][1];
             const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
-            const double r = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]), ri = 1.0 / r;
-            s1 -= (r - M.fref[i]) / fnum;
-            s0u -= (r - M.freac[i]) / fnum;
-            const double v = sel(R, d) * ri / fnum;
+            double r, ri;
+            sqrt_rsqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2], r, ri);
+            s1 -= (r - M.fref[i]) * ifnum;
+            s0u -= (r - M.freac[i]) * ifnum;
+            const double v = sel(R, d) * ri * ifnum;
             if (a == a1) ds1 -= v;
             if (a == a2) ds1 += v;
         }
@@ -507,14 +510,15 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             for (int j = i + 1; j < XI_MAXREAC; j++)
                 if (j < nreac) {
                     const double Red[3] = {com[j][0] - com[i][0], com[j][1] - com[i][1], com[j][2] - com[i][2]};
-                    const double r = sqrt(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2]), ri = 1.0 / r;
+                    double r, ri;
+                    sqrt_rsqrt(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2], r, ri);
                     s0 += M.R_inf - r;
                     if (ka == i || ka == j) {
                         const double sg = (ka == i) ? 1.0 : -1.0;
-                        ds0 += sel(Red, d) * (sg * ri * wa / fterms);
+                        ds0 += sel(Red, d) * (sg * ri * wa * iterms);
                     }
                 }
-        s0 = s0 / fterms;
+        s0 = s0 * iterms;
         if (M.type == 1) {
             s0 = s0u;
             ds0 = ds1;
@@ -527,7 +531,8 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
         double dx;
         if (mode == 1) {
             const double D = s0 - s1;
-            dx = (s0 * ds1 - s1 * ds0) * (1.0 / (D * D));
+            const double iD = CRCL_RCP(D);
+            dx = (s0 * ds1 - s1 * ds0) * (iD * iD);
         } else {
             dx = xi_ideal * ds1 + (1 - xi_ideal) * ds0;
         }
@@ -535,10 +540,10 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             dxi_sh[t] = dx;
             s_ds0[t] = ds0;
             s_ds1[t] = ds1;
-            s_v[t] = dx / mass[a];
+            s_v[t] = CRCL_DIV(dx, mass[a]);
         }
     }
-    double xi = (mode == 1) ? s0 / (s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
+    double xi = (mode == 1) ? s0 * CRCL_RCP(s0 - s1) : xi_ideal * s1 + (1 - xi_ideal) * s0;
     if (T > 32 && tig == 0) scr[3 * NC] = xi;
     if (T > 32 || want_hams) sync();
     if (!work) xi = scr[3 * NC];
@@ -552,10 +557,10 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
         d0v += s_ds0[t] * v;
     }
     const double coeff1 = 2.0 * PI_UMBR * beta;
-    fs2 = fs2 / coeff1;
-    const double pref = (-1.0 / beta) / (coeff1 * fs2);
+    fs2 = CRCL_DIV(fs2, coeff1);
+    const double pref = CRCL_DIV(-1.0, beta * (coeff1 * fs2));
     const double D = s0 - s1;
-    const double iD3 = 1.0 / (D * D * D);
+    const double iD3 = CRCL_RCP(D * D * D);
     const double cross2 = 2.0 * (s0 * d1v - s1 * d0v);
 #pragma unroll
     for (int p = 0; p < NPASS; p++) {
@@ -567,11 +572,11 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             const int a1 = M.bf[i][0], a2 = M.bf[i][1];
             if (a == a1 || a == a2) {
                 const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
-                const double ri = 1.0 / sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+                const double ri = CRCL_RSQRT(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
                 const double w[3] = {s_v[3 * a1] - s_v[3 * a2], s_v[3 * a1 + 1] - s_v[3 * a2 + 1], s_v[3 * a1 + 2] - s_v[3 * a2 + 2]};
                 double o[3];
                 proj(R, ri, w, o);
-                const double od = sel(o, d) / fnum;
+                const double od = sel(o, d) * ifnum;
                 if (a == a1) H1 -= od;
                 if (a == a2) H1 += od;
             }
@@ -580,11 +585,11 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             const int a1 = M.bb[i][0], a2 = M.bb[i][1];
             if (a == a1 || a == a2) {
                 const double R[3] = {x[3 * a1] - x[3 * a2], x[3 * a1 + 1] - x[3 * a2 + 1], x[3 * a1 + 2] - x[3 * a2 + 2]};
-                const double ri = 1.0 / sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+                const double ri = CRCL_RSQRT(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
                 const double w[3] = {s_v[3 * a1] - s_v[3 * a2], s_v[3 * a1 + 1] - s_v[3 * a2 + 1], s_v[3 * a1 + 2] - s_v[3 * a2 + 2]};
                 double o[3];
                 proj(R, ri, w, o);
-                const double od = sel(o, d) / bnum;
+                const double od = sel(o, d) * ibnum;
                 if (a == a1) H1 += od;
                 if (a == a2) H1 -= od;
             }
@@ -597,7 +602,7 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
             for (int j = i + 1; j < XI_MAXREAC; j++)
                 if (j < nreac && (ka == i || ka == j)) {
                     const double Red[3] = {com[j][0] - com[i][0], com[j][1] - com[i][1], com[j][2] - com[i][2]};
-                    const double ri = 1.0 / sqrt(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2]);
+                    const double ri = CRCL_RSQRT(Red[0] * Red[0] + Red[1] * Red[1] + Red[2] * Red[2]);
                     double W[3] = {0, 0, 0}, o[3];
 #pragma unroll
                     for (int b = 0; b < NAT; b++) {
@@ -610,7 +615,7 @@ __device__ __forceinline__ double calc_xi_coop(const Mech& M, const double* mass
                     }
                     proj(Red, ri, W, o);
                     const double sg = (ka == i) ? 1.0 : -1.0;
-                    H0 += (-sg * wa / fterms) * sel(o, d);
+                    H0 += (-sg * wa * iterms) * sel(o, d);
                 }
         if (M.type == 1) H0 = H1;
         const double ds0 = s_ds0[tt], ds1 = s_ds1[tt];
