@@ -324,7 +324,13 @@ CRCL_HD __noinline__ inline void compact_terms(const double R[3], const Bend& c,
 
 // pote (egrad_h3.f:79-249): potential and dV/dR on the three distances
 // R = (r12, r13, r23).  warn gets CHGEOM's two conditions as bits (the reference prints).
-CRCL_HD __forceinline__ void pote(const double R[3], const double iR[3], double& V, double dV[3], int& warn)
+// SPLIT > 0 (device only): the SPLIT lanes of a trajectory segment evaluate the surface together on the same structure
+// (PesSpread, traj_inst.cuh) -- the three pair curves of the London term, 40 % of the instructions of an evaluation, are
+// then ONE pass with lane % 3 choosing the distance, the four numbers per distance handed round by shuffles from the
+// first three lanes of the segment; Q is summed in the order of the loop (the same bits).
+template <int SPLIT = 0>
+CRCL_HD __forceinline__ void pote(const double R[3], const double iR[3], double& V, double dV[3], int& warn, int lane = 0,
+                                  unsigned mask = 0u)
 {
     // CHGEOM (egrad_h3.f:1432-1476)
     {
@@ -337,15 +343,36 @@ CRCL_HD __forceinline__ void pote(const double R[3], const double iR[3], double&
     }
     // ---- London term (H3LOND95, :419-480) ----
     double Q = 0.0, J[3], dQ[3], dJ[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
+#ifdef __CUDA_ARCH__
+    if constexpr (SPLIT > 0) {
+        const int i = lane % 3;
+        const double Ri = (i == 0) ? R[0] : ((i == 1) ? R[1] : R[2]);
+        const double iRi = (i == 0) ? iR[0] : ((i == 1) ? iR[1] : iR[2]);
         double E1, dE1, E3, dE3;
-        singlet(R[i], iR[i], E1, dE1);
-        triplet(R[i], iR[i], E1, dE1, E3, dE3);
-        Q += 0.5 * (E1 + E3);
-        J[i] = 0.5 * (E1 - E3);
-        dQ[i] = 0.5 * (dE1 + dE3);
-        dJ[i] = 0.5 * (dE1 - dE3);
+        singlet(Ri, iRi, E1, dE1);
+        triplet(Ri, iRi, E1, dE1, E3, dE3);
+        const double q = 0.5 * (E1 + E3), j = 0.5 * (E1 - E3), dq = 0.5 * (dE1 + dE3), dj = 0.5 * (dE1 - dE3);
+        const int first = (int)(threadIdx.x & 31u) - lane;   // lane 0 of this trajectory's segment of the warp
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            Q += __shfl_sync(mask, q, first + k);
+            J[k] = __shfl_sync(mask, j, first + k);
+            dQ[k] = __shfl_sync(mask, dq, first + k);
+            dJ[k] = __shfl_sync(mask, dj, first + k);
+        }
+    } else
+#endif
+    {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            double E1, dE1, E3, dE3;
+            singlet(R[i], iR[i], E1, dE1);
+            triplet(R[i], iR[i], E1, dE1, E3, dE3);
+            Q += 0.5 * (E1 + E3);
+            J[i] = 0.5 * (E1 - E3);
+            dQ[i] = 0.5 * (dE1 + dE3);
+            dJ[i] = 0.5 * (dE1 - dE3);
+        }
     }
     const double d10 = J[1] - J[0], d21 = J[2] - J[1], d20 = J[2] - J[0];
     double rootjt, irootjt;
@@ -434,7 +461,19 @@ CRCL_HD __forceinline__ void pote(const double R[3], const double iR[3], double&
         for (int i = 0; i < 3; i++) dV[i] += dVa[i] + dVb[i];
     }
     // ---- compact-geometry corrections (COMPAC95 :576-609 decides) ----
-    if (R1 < 1.15 || R2 < 1.15 || R3 < 1.15) compact_terms(R, c, B1A, B1B, DB1A, DB1B, A, DA, V, dV);
+    // The rare branch works on COPIES: compact_terms is not inlined, so whatever it receives by address lives on the
+    // stack -- handed the originals, every evaluation stored c, R, DB1A, DB1B, DA, V and dV there (74 local stores and
+    // 20 reloads per step of a one-bead trajectory, profiles/r2ak_chain_h3_source.txt) whether or not the branch ran.
+    if (R1 < 1.15 || R2 < 1.15 || R3 < 1.15) {
+        const Bend cc = c;
+        const double Rc[3] = {R[0], R[1], R[2]}, DAc[3] = {DA[0], DA[1], DA[2]};
+        const double DB1Ac[3] = {DB1A[0], DB1A[1], DB1A[2]}, DB1Bc[3] = {DB1B[0], DB1B[1], DB1B[2]};
+        double Vc = V, dVc[3] = {dV[0], dV[1], dV[2]};
+        compact_terms(Rc, cc, B1A, B1B, DB1Ac, DB1Bc, A, DAc, Vc, dVc);
+        V = Vc;
+#pragma unroll
+        for (int i = 0; i < 3; i++) dV[i] = dVc[i];
+    }
 }
 
 }  // namespace h3
@@ -459,6 +498,14 @@ struct PesH3 {
     CRCL_HD static __forceinline__ int eval(const double* __restrict__ q, double& V,
                                                double* __restrict__ g)
     {
+        return eval_split<0>(q, 0, 0u, V, g);
+    }
+    // the same with the SPLIT lanes of a trajectory segment sharing the London term (pote<SPLIT>; PesSpread)
+    static constexpr bool SPLIT_OK = true;
+    template <int SPLIT>
+    CRCL_HD static __forceinline__ int eval_split(const double* __restrict__ q, int lane, unsigned mask, double& V,
+                                                  double* __restrict__ g)
+    {
         // R(1)=|q2-q1|, R(2)=|q1-q3|, R(3)=|q3-q2|  (egrad_h3.f:44-63)
         const double ab[3] = {q[3] - q[0], q[4] - q[1], q[5] - q[2]};
         const double ac[3] = {q[0] - q[6], q[1] - q[7], q[2] - q[8]};
@@ -468,7 +515,7 @@ struct PesH3 {
         sqrt_rsqrt(ac[0] * ac[0] + ac[1] * ac[1] + ac[2] * ac[2], R[1], iR[1]);
         sqrt_rsqrt(bc[0] * bc[0] + bc[1] * bc[1] + bc[2] * bc[2], R[2], iR[2]);
         int warn;
-        h3::pote(R, iR, V, dV, warn);
+        h3::pote<SPLIT>(R, iR, V, dV, warn, lane, mask);
         const double f0 = dV[0] * iR[0], f1 = dV[1] * iR[1], f2 = dV[2] * iR[2];
 #pragma unroll
         for (int d = 0; d < 3; d++) {

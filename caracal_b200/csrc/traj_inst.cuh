@@ -51,6 +51,15 @@ static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, c
 #ifndef CRCL_SPREAD_MAX_TRAJ
 #define CRCL_SPREAD_MAX_TRAJ 1024
 #endif
+// surfaces with a lane-split evaluation for the spread form (P::eval_split<L>, P::SPLIT_OK)
+template <class P, class = void>
+struct has_split {
+    static constexpr bool value = false;
+};
+template <class P>
+struct has_split<P, decltype((void)P::SPLIT_OK)> {
+    static constexpr bool value = true;
+};
 template <class P, int L>
 struct PesSpread {
     static_assert(P::LANES == 1 && 3 * P::NATOMS <= L, "one lane per component");
@@ -60,14 +69,18 @@ struct PesSpread {
     static constexpr int NOWN = 1;
     CRCL_HD static __forceinline__ int owned(int lane, int k) { return (k == 0 && lane < 3 * NATOMS) ? lane : -1; }
     template <class QF>
-    CRCL_HD static __forceinline__ int eval_coop(QF qf, int lane, unsigned, double& V, double* gown)
+    CRCL_HD static __forceinline__ int eval_coop(QF qf, int lane, unsigned mask, double& V, double* gown)
     {
         constexpr int NC = 3 * NATOMS;
         double x[NC], g[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) x[c] = qf(c);
         double e;
-        const int w = P::eval(x, e, g);
+        int w;
+        if constexpr (has_split<P>::value)
+            w = P::template eval_split<L>(x, lane, mask, e, g);
+        else
+            w = P::eval(x, e, g);
         V = (lane == 0) ? e : 0.0;
         double own = 0.0;
 #pragma unroll

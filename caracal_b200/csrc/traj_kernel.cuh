@@ -752,7 +752,12 @@ struct Traj {
                 const double v = CRCL_DIV(P(c), w);
                 vk[k] = v;
                 const double qx = Q(3 * j), qy = Q(3 * j + 1), qz = Q(3 * j + 2);
-                s[d] += v * w;
+                // s[d] += v w without a run-time index (d is one when a lane owns a single component, PesSpread: s would
+                // move to local memory); adding 0.0 changes no bits
+                const double vw = v * w;
+                s[0] += (d == 0) ? vw : 0.0;
+                s[1] += (d == 1) ? vw : 0.0;
+                s[2] += (d == 2) ? vw : 0.0;
                 // (q x e_d) v w
                 if (d == 0) {
                     s[7] += qz * v * w;
@@ -833,7 +838,7 @@ struct Traj {
                 const int c = oc[k], j = c / 3, d = c - 3 * j;
                 const double w = mt[k].x;
                 const double xd = Q(3 * j) - ctr[0], yd = Q(3 * j + 1) - ctr[1], zd = Q(3 * j + 2) - ctr[2];
-                double v = vk[k] - vtot[d];
+                double v = vk[k] - ((d == 0) ? vtot[0] : ((d == 1) ? vtot[1] : vtot[2]));
                 if (d == 0)
                     v = v - vang[1] * zd + vang[2] * yd;
                 else if (d == 1)
