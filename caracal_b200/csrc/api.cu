@@ -33,6 +33,7 @@ struct crcl_handle_s {
     int device = 0, natoms = 0, nbeads = 0, pes = 0;
     double beta = 0, dt = 0, kelvin = 0, nose_q = 0;
     int thermostat = 0, andersen_step = 0, transform = CRCL_TRANSFORM_REFERENCE;
+    int spread_max = CRCL_SPREAD_MAX_TRAJ;   // crcl_set_spread_max_traj
     uint64_t seed = 0;
     std::vector<double> mass;
     std::vector<int> at_move;
@@ -358,6 +359,7 @@ static void fill_args(crcl_handle h, TrajArgs& A)
     A.thermostat = h->thermostat;
     A.andersen_step = h->andersen_step;
     A.symmetrize = (h->transform == CRCL_TRANSFORM_REFERENCE) ? 1 : 0;
+    A.spread_max = h->spread_max;
     for (int i = 0; i < h->natoms && i < TRAJ_MAXNAT; i++) {
         A.mass[i] = h->mass[i];
         A.at_move[i] = h->at_move[i];
@@ -1005,6 +1007,13 @@ int crcl_set_transform(crcl_handle h, int mode)
 {
     if (!h || (mode != CRCL_TRANSFORM_REFERENCE && mode != CRCL_TRANSFORM_EXACT)) return CRCL_EINVAL;
     h->transform = mode;
+    return CRCL_OK;
+}
+
+int crcl_set_spread_max_traj(crcl_handle h, int max_traj)
+{
+    if (!h || max_traj < 0) return CRCL_EINVAL;
+    h->spread_max = max_traj;
     return CRCL_OK;
 }
 

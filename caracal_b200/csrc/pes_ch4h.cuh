@@ -525,6 +525,7 @@ struct PesCBE4 {
     static constexpr int ID = K::ID;
     static constexpr int LANES = 4;
     static constexpr int NOWN = K::HAS_OH ? 6 : 5;  // components owned per lane (5,5,4,4 of 18; 6,5,5,5 of 21)
+    static constexpr bool SPREAD_OK = true;          // one-bead trajectories may run as eight quads (PesSpreadQ, traj_inst.cuh)
 #ifndef CRCL_CBE_SHFL_GATHER
     // per-hydrogen quantities travel between the four lanes of a bead through shared memory: 18 doubles per lane,
     // written as nine 16-byte stores and read back as 16-byte loads per neighbour (instead of the 102 SHFL of the 51

@@ -46,8 +46,8 @@ static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, c
 // per-component loops of the step (profiles/r2ai_chain_h3_source.txt).  With L >= 3 NATOMS every lane owns ONE
 // component: the cooperative xi (calc_xi_coop) applies, the loops over the owned components have one trip, Andersen
 // draws its pairs in parallel; the surface itself is evaluated by every lane on the same structure (the same
-// instructions the one thread issued), lane 0 reports the energy.  Batches above CRCL_SPREAD_MAX_TRAJ keep one thread
-// per trajectory: there the throughput of the packed form wins.
+// instructions the one thread issued), lane 0 reports the energy.  Batches above the handle's spread_max (default
+// CRCL_SPREAD_MAX_TRAJ, crcl_set_spread_max_traj) keep one thread per trajectory: there the throughput of the packed form wins.
 #ifndef CRCL_SPREAD_MAX_TRAJ
 #define CRCL_SPREAD_MAX_TRAJ 1024
 #endif
@@ -58,6 +58,14 @@ struct has_split {
 };
 template <class P>
 struct has_split<P, decltype((void)P::SPLIT_OK)> {
+    static constexpr bool value = true;
+};
+template <class P, class = void>
+struct has_spread_q {
+    static constexpr bool value = false;
+};
+template <class P>
+struct has_spread_q<P, decltype((void)P::SPREAD_OK)> {
     static constexpr bool value = true;
 };
 template <class P, int L>
@@ -90,6 +98,42 @@ struct PesSpread {
     }
 };
 
+// The same for a surface that is already split over four lanes per bead (PesCBE4 and its family): R quads of one warp
+// evaluate it on the same structure -- quad r, surface lane x owns the ONE component P::owned(x, r) -- so that a
+// one-bead trajectory has 4 R >= 3 NATOMS threads and the cooperative xi applies (with the four threads of a bead alone
+// every thread ran the serial form over all 18 or 21 components).  Each quad keeps its own block of the surface's
+// lane-exchange scratch; quad 0 reports the energy.
+template <class P, int R>
+struct PesSpreadQ {
+    static_assert(P::LANES == 4 && P::NOWN <= R && 4 * R <= 32, "one quad per owned slot, within a warp");
+    static constexpr int NATOMS = P::NATOMS;
+    static constexpr int ID = P::ID;
+    static constexpr int LANES = 4 * R;
+    static constexpr int NOWN = 1;
+    static constexpr int COOP_SCRATCH = coop_scratch<P>::value;   // per thread: [quad][surface lane][scratch]
+    __device__ static __forceinline__ int owned(int lane, int k)
+    {
+        return (k == 0 && (lane >> 2) < P::NOWN) ? P::owned(lane & 3, lane >> 2) : -1;
+    }
+    template <class QF>
+    __device__ static __forceinline__ int eval_coop(QF qf, int lane, unsigned mask, double& V, double* gown,
+                                                   double* scr = nullptr)
+    {
+        double e, g[P::NOWN];
+        int w;
+        if constexpr (coop_scratch<P>::value > 0)
+            w = P::eval_coop(qf, lane & 3, mask, e, g, scr + (lane >> 2) * 4 * coop_scratch<P>::value);
+        else
+            w = P::eval_coop(qf, lane & 3, mask, e, g);
+        V = ((lane >> 2) == 0) ? e : 0.0;
+        double own = 0.0;
+#pragma unroll
+        for (int k = 0; k < P::NOWN; k++) own = (k == (lane >> 2)) ? g[k] : own;
+        gown[0] = own;
+        return w;
+    }
+};
+
 template <class PES, int KIND>
 static cudaError_t launch_traj_pes(int nbeads, const TrajArgs& A, int bias_mode, double nose_q,
                                    cudaStream_t s, int* nosup)
@@ -98,7 +142,9 @@ static cudaError_t launch_traj_pes(int nbeads, const TrajArgs& A, int bias_mode,
     switch (nbeads) {
     case 1:
         if constexpr (PES::LANES == 1 && 3 * PES::NATOMS <= 16) {
-            if (A.ntraj <= CRCL_SPREAD_MAX_TRAJ) return launch_one<PesSpread<PES, 16>, KIND, 1>(A, bias_mode, nose_q, s);
+            if (A.ntraj <= A.spread_max) return launch_one<PesSpread<PES, 16>, KIND, 1>(A, bias_mode, nose_q, s);
+        } else if constexpr (PES::LANES == 4 && 3 * PES::NATOMS <= 32 && has_spread_q<PES>::value) {
+            if (A.ntraj <= A.spread_max) return launch_one<PesSpreadQ<PES, 8>, KIND, 1>(A, bias_mode, nose_q, s);
         }
         return launch_one<PES, KIND, 1>(A, bias_mode, nose_q, s);
     case 2: return launch_one<PES, KIND, 2>(A, bias_mode, nose_q, s);

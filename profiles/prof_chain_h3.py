@@ -1,7 +1,7 @@
 """Small driver for ncu: one link of the start-structure chain of calc_rate (calc_rate.f90:651-1148) -- ONE
 one-bead H + H2 trajectory, mdinit(bias) + biased steps at a window (rate.py generate_start_structures).
   ncu --set full --clock-control none --import-source on -k regex:verlet_kernel -c 1 \
-      -o gpurun_out/prof_chain_h3 python profiles/prof_chain_h3.py [steps] [constrain] [pes]"""
+      -o gpurun_out/prof_chain_h3 python profiles/prof_chain_h3.py [steps] [constrain] [pes] [spread_max]"""
 import os
 import sys
 import time
@@ -23,6 +23,8 @@ g1 = caracal_b200.RPMD(name, 1, m, beta, dt)
 g1.set_mechanism(mech)
 g1.set_seed(C.SEED)
 g1.set_thermostat(1, 70, kelvin)
+if len(sys.argv) > 4:
+    g1.set_spread_max_traj(int(sys.argv[4]))   # 0: the one-thread-per-trajectory form
 ts = C.h3_ts() if name == "h3" else C.ring_polymer(name, 1, np.random.default_rng(1), 0.0)
 q = np.array(ts, dtype=np.float64).reshape(1, 1, len(m), 3).copy()
 tid = np.array([7], dtype=np.uint32)
@@ -33,4 +35,4 @@ for it in range(3):
     ep, xr, st = g1.verlet(q, p, d, nsteps=steps, constrain=constrain, xi_ideal=xi0, k_force=kf, dxi=dxi,
                            traj_id=tid, event=ev)
     sec = time.perf_counter() - t0
-    print("pass %d: %.3f us per step (wall, mdinit + %d steps)  xi %.4f  status %d" % (it, 1e6 * sec / steps, steps, xr[0], st[0]))
+    print("%s spread_max %s pass %d: %.3f us per step (wall, mdinit + %d steps)  xi %.4f  status %d" % (name, sys.argv[4] if len(sys.argv) > 4 else "default", it, 1e6 * sec / steps, steps, xr[0], st[0]))
