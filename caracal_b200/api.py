@@ -140,9 +140,9 @@ class RPMD:
     def set_transform(self, mode):
         self._ck(self._lib.crcl_set_transform(self._h, int(mode)), "crcl_set_transform")
 
-    def set_spread_max_traj(self, max_traj):
-        """Largest batch of one-bead trajectories that runs with a trajectory spread over 16 / 32 lanes (0: never)."""
-        self._ck(self._lib.crcl_set_spread_max_traj(self._h, int(max_traj)), "crcl_set_spread_max_traj")
+    def set_spread_max_beads(self, max_beads):
+        """Largest batch (trajectories x beads) of few-bead trajectories that runs spread over 16 / 32 lanes (0: never)."""
+        self._ck(self._lib.crcl_set_spread_max_beads(self._h, int(max_beads)), "crcl_set_spread_max_beads")
 
     def set_path(self, path):
         self._ck(self._lib.crcl_set_path(self._h, int(path)), "crcl_set_path")

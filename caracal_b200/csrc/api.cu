@@ -33,7 +33,7 @@ struct crcl_handle_s {
     int device = 0, natoms = 0, nbeads = 0, pes = 0;
     double beta = 0, dt = 0, kelvin = 0, nose_q = 0;
     int thermostat = 0, andersen_step = 0, transform = CRCL_TRANSFORM_REFERENCE;
-    int spread_max = CRCL_SPREAD_MAX_TRAJ;   // crcl_set_spread_max_traj
+    int spread_max = CRCL_SPREAD_MAX_BEADS;   // crcl_set_spread_max_beads
     uint64_t seed = 0;
     std::vector<double> mass;
     std::vector<int> at_move;
@@ -1010,10 +1010,10 @@ int crcl_set_transform(crcl_handle h, int mode)
     return CRCL_OK;
 }
 
-int crcl_set_spread_max_traj(crcl_handle h, int max_traj)
+int crcl_set_spread_max_beads(crcl_handle h, int max_beads)
 {
-    if (!h || max_traj < 0) return CRCL_EINVAL;
-    h->spread_max = max_traj;
+    if (!h || max_beads < 0) return CRCL_EINVAL;
+    h->spread_max = max_beads;
     return CRCL_OK;
 }
 

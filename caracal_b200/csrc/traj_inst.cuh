@@ -46,10 +46,12 @@ static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, c
 // per-component loops of the step (profiles/r2ai_chain_h3_source.txt).  With L >= 3 NATOMS every lane owns ONE
 // component: the cooperative xi (calc_xi_coop) applies, the loops over the owned components have one trip, Andersen
 // draws its pairs in parallel; the surface itself is evaluated by every lane on the same structure (the same
-// instructions the one thread issued), lane 0 reports the energy.  Batches above the handle's spread_max (default
-// CRCL_SPREAD_MAX_TRAJ, crcl_set_spread_max_traj) keep one thread per trajectory: there the throughput of the packed form wins.
-#ifndef CRCL_SPREAD_MAX_TRAJ
-#define CRCL_SPREAD_MAX_TRAJ 1024
+// instructions the one thread issued), lane 0 reports the energy.  Batches of more than spread_max trajectories x beads
+// (default CRCL_SPREAD_MAX_BEADS, crcl_set_spread_max_beads) keep the packed form: the spread forms are for batches that
+// leave most SMs with at most one warp, where nothing but the latency of a step counts -- measured (r2an): the 1100 8-bead
+// trajectories of the H + H2 umbrella phase ran 0.45 -> 0.97 s when they were spread two lanes per bead.
+#ifndef CRCL_SPREAD_MAX_BEADS
+#define CRCL_SPREAD_MAX_BEADS 256
 #endif
 // surfaces with a lane-split evaluation for the spread form (P::eval_split<L>, P::SPLIT_OK)
 template <class P, class = void>
@@ -68,14 +70,21 @@ template <class P>
 struct has_spread_q<P, decltype((void)P::SPREAD_OK)> {
     static constexpr bool value = true;
 };
+// The same with L lanes per bead for trajectories of 2, 4 or 8 beads, which have fewer threads than components in the
+// packed form too (the constrained recrossing parent of the H + H2 example is ONE 8-bead trajectory of 150 000 steps):
+// lane x of a bead owns the components x NOWN ... x NOWN + NOWN - 1, NOWN = ceil(3 NATOMS / L).
 template <class P, int L>
 struct PesSpread {
-    static_assert(P::LANES == 1 && 3 * P::NATOMS <= L, "one lane per component");
+    static_assert(P::LANES == 1 && L >= 2 && L <= 32, "spreads a one-lane surface");
     static constexpr int NATOMS = P::NATOMS;
     static constexpr int ID = P::ID;
     static constexpr int LANES = L;
-    static constexpr int NOWN = 1;
-    CRCL_HD static __forceinline__ int owned(int lane, int k) { return (k == 0 && lane < 3 * NATOMS) ? lane : -1; }
+    static constexpr int NOWN = (3 * P::NATOMS + L - 1) / L;
+    CRCL_HD static __forceinline__ int owned(int lane, int k)
+    {
+        const int c = lane * NOWN + k;
+        return (k < NOWN && c < 3 * NATOMS) ? c : -1;
+    }
     template <class QF>
     CRCL_HD static __forceinline__ int eval_coop(QF qf, int lane, unsigned mask, double& V, double* gown)
     {
@@ -85,15 +94,18 @@ struct PesSpread {
         for (int c = 0; c < NC; c++) x[c] = qf(c);
         double e;
         int w;
-        if constexpr (has_split<P>::value)
+        if constexpr (has_split<P>::value && L >= 4)
             w = P::template eval_split<L>(x, lane, mask, e, g);
         else
             w = P::eval(x, e, g);
         V = (lane == 0) ? e : 0.0;
-        double own = 0.0;
 #pragma unroll
-        for (int c = 0; c < NC; c++) own = (c == lane) ? g[c] : own;
-        gown[0] = own;
+        for (int k = 0; k < NOWN; k++) {
+            double own = 0.0;
+#pragma unroll
+            for (int c = k; c < NC; c++) own = (c == lane * NOWN + k) ? g[c] : own;
+            gown[k] = own;
+        }
         return w;
     }
 };
@@ -147,9 +159,21 @@ static cudaError_t launch_traj_pes(int nbeads, const TrajArgs& A, int bias_mode,
             if (A.ntraj <= A.spread_max) return launch_one<PesSpreadQ<PES, 8>, KIND, 1>(A, bias_mode, nose_q, s);
         }
         return launch_one<PES, KIND, 1>(A, bias_mode, nose_q, s);
-    case 2: return launch_one<PES, KIND, 2>(A, bias_mode, nose_q, s);
-    case 4: return launch_one<PES, KIND, 4>(A, bias_mode, nose_q, s);
-    case 8: return launch_one<PES, KIND, 8>(A, bias_mode, nose_q, s);
+    case 2:
+        if constexpr (PES::LANES == 1 && 3 * PES::NATOMS <= 16) {
+            if (2 * A.ntraj <= A.spread_max) return launch_one<PesSpread<PES, 8>, KIND, 2>(A, bias_mode, nose_q, s);
+        }
+        return launch_one<PES, KIND, 2>(A, bias_mode, nose_q, s);
+    case 4:
+        if constexpr (PES::LANES == 1 && 3 * PES::NATOMS <= 16) {
+            if (4 * A.ntraj <= A.spread_max) return launch_one<PesSpread<PES, 4>, KIND, 4>(A, bias_mode, nose_q, s);
+        }
+        return launch_one<PES, KIND, 4>(A, bias_mode, nose_q, s);
+    case 8:
+        if constexpr (PES::LANES == 1 && 3 * PES::NATOMS <= 16 && 3 * PES::NATOMS > 8) {
+            if (8 * A.ntraj <= A.spread_max) return launch_one<PesSpread<PES, 2>, KIND, 8>(A, bias_mode, nose_q, s);
+        }
+        return launch_one<PES, KIND, 8>(A, bias_mode, nose_q, s);
     case 16: return launch_one<PES, KIND, 16>(A, bias_mode, nose_q, s);
     case 32: return launch_one<PES, KIND, 32>(A, bias_mode, nose_q, s);
     case 64: return launch_one<PES, KIND, 64>(A, bias_mode, nose_q, s);

@@ -34,7 +34,7 @@ constexpr int TRAJ_MAXNAT = XI_MAXAT;
 
 struct TrajArgs {
     int ntraj, nsteps, istep0, constrain, thermostat, andersen_step, symmetrize, nbeads;
-    int spread_max;   // host side only: largest batch of one-bead trajectories that runs in the spread form (traj_inst.cuh)
+    int spread_max;   // host side only: largest batch (trajectories x beads) that runs in the spread forms (traj_inst.cuh)
     double beta, dt, kelvin;
     double mass[TRAJ_MAXNAT];
     int at_move[TRAJ_MAXNAT];

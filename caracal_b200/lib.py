@@ -71,7 +71,7 @@ SIGNATURES = {
     "crcl_synchronize": (ctypes.c_int, [_H]),
     "crcl_set_beta_dt": (ctypes.c_int, [_H, ctypes.c_double, ctypes.c_double]),
     "crcl_set_transform": (ctypes.c_int, [_H, ctypes.c_int]),
-    "crcl_set_spread_max_traj": (ctypes.c_int, [_H, ctypes.c_int]),
+    "crcl_set_spread_max_beads": (ctypes.c_int, [_H, ctypes.c_int]),
     "crcl_set_host_gradient_cb": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p]),
     "crcl_set_qmdff": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),
     "crcl_set_qmdff2": (ctypes.c_int, [_H, ctypes.POINTER(QmdffTables)]),

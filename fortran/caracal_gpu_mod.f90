@@ -274,13 +274,13 @@ interface
       integer(c_int), value :: mode
       integer(c_int) :: crcl_set_transform
    end function crcl_set_transform
-   ! largest batch of one-bead trajectories run in the spread (low-latency) form; 0 = never
-   function crcl_set_spread_max_traj(h, max_traj) bind(C, name="crcl_set_spread_max_traj")
+   ! largest batch (trajectories x beads) of few-bead trajectories run in the spread (low-latency) form; 0 = never
+   function crcl_set_spread_max_beads(h, max_beads) bind(C, name="crcl_set_spread_max_beads")
       import :: c_ptr, c_int
       type(c_ptr), value :: h
-      integer(c_int), value :: max_traj
-      integer(c_int) :: crcl_set_spread_max_traj
-   end function crcl_set_spread_max_traj
+      integer(c_int), value :: max_beads
+      integer(c_int) :: crcl_set_spread_max_beads
+   end function crcl_set_spread_max_beads
    ! 0 automatic, 1 fused in-register kernels, 2 HBM-resident path
    function crcl_set_path(h, path) bind(C, name="crcl_set_path")
       import :: c_ptr, c_int

@@ -107,13 +107,14 @@ int crcl_synchronize(crcl_handle h);
 /* beta, dt, nbeads are mutated mid-run by the drivers (calc_rate.f90:651,1253) */
 int crcl_set_beta_dt(crcl_handle h, double beta, double dt);
 int crcl_set_transform(crcl_handle h, int mode);
-/* One-bead trajectories (the start-structure chain of calc_rate.f90:651-1148 runs 111 of them one after the other):
- * batches of at most max_traj trajectories run with the components of a trajectory spread over the lanes of a
- * half-warp or warp (a third of the step latency of the one-thread-per-trajectory form, which larger batches keep
- * for its throughput).  Default 1024; 0 = always one thread (four for the lane-split surfaces) per trajectory.  Both
- * forms follow the same operations; sums over components differ in their order (last bits).  No counterpart in the
- * reference. */
-int crcl_set_spread_max_traj(crcl_handle h, int max_traj);
+/* Trajectories with fewer threads than components in the packed form -- one bead of anything, up to eight beads of a
+ * three- or four-atom system: the start-structure chain of calc_rate.f90:651-1148 is 111 one-bead trajectories one after
+ * the other, the constrained recrossing parent (recross.f90:228-330) ONE trajectory of 150 000 steps.  Batches of at most
+ * max_beads trajectories x beads run with the components of a trajectory spread over the lanes of a half-warp or warp
+ * (0.6-0.75 of the step latency of the packed form, which larger batches keep for its throughput).  Default 256;
+ * 0 = always the packed form.  Both forms follow the same operations; sums over components differ in their order (last
+ * bits).  No counterpart in the reference. */
+int crcl_set_spread_max_beads(crcl_handle h, int max_beads);
 int crcl_set_host_gradient_cb(crcl_handle h, crcl_host_grad_fn fn, void *user);
 int crcl_set_path(crcl_handle h, int path);
 /* Split path only: steps 2..nsteps of one crcl_verlet / work-unit call are replayed from a CUDA graph of the

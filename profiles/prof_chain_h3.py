@@ -24,7 +24,7 @@ g1.set_mechanism(mech)
 g1.set_seed(C.SEED)
 g1.set_thermostat(1, 70, kelvin)
 if len(sys.argv) > 4:
-    g1.set_spread_max_traj(int(sys.argv[4]))   # 0: the one-thread-per-trajectory form
+    g1.set_spread_max_beads(int(sys.argv[4]))   # 0: the one-thread-per-trajectory form
 ts = C.h3_ts() if name == "h3" else C.ring_polymer(name, 1, np.random.default_rng(1), 0.0)
 q = np.array(ts, dtype=np.float64).reshape(1, 1, len(m), 3).copy()
 tid = np.array([7], dtype=np.uint32)

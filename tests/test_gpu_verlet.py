@@ -53,6 +53,9 @@ CASES = [
     ("ch4h", 1, 1, 1, 31, 2, 0.98, 15.0, 3),      # the same under SHAKE / RATTLE
     ("ch4oh", 1, 0, 1, 50, 2, 0.9, 15.0, 3),      # 7 atoms: six owned slots per surface lane
     ("oh3", 1, 0, 1, 50, 2, 0.9, 15.0, 5),        # one bead, 12 components on 16 lanes (PesSpread)
+    ("h3", 2, 0, 1, 50, 2, 0.9, 15.0, 3),         # two beads x eight lanes
+    ("oh3", 4, 1, 1, 31, 2, 0.95, 15.0, 3),       # four beads x four lanes, SHAKE / RATTLE
+    ("brh2", 4, 0, 1, 40, 2, 0.9, 15.0, 3),       # four beads x four lanes
     ("h2co", 8, 0, 1, 40, 2, 0.9, 15.0, 2),       # H2CO fit (central-difference gradient, four lanes per bead)
     ("h2co", 4, 2, 0, 0, 2, 0.98, 0.0, 2),        # child trajectories
 ]
@@ -63,7 +66,7 @@ def run_case(gpu, oracle, name, nb, constrain, thermo, astep, bias_mode, xi_idea
     rng = np.random.default_rng(abs(hash((name, nb, constrain, thermo))) % 2 ** 31)
     g, _ = C.make_pair(name, nb)
     if spread_max is not None:
-        g.set_spread_max_traj(spread_max)
+        g.set_spread_max_beads(spread_max)
     g.set_seed(C.SEED)
     g.set_thermostat(thermo, astep, 300.0, 100.0)
     q0 = np.array([C.ring_polymer(name, nb, rng, 0.03) for _ in range(ntraj)])
@@ -106,11 +109,12 @@ def test_100_steps_match_oracle(gpu, oracle, case):
     assert wp < C.TOL_QP, "momenta differ by %g (relative to max |p|)" % wp
 
 
-@pytest.mark.parametrize("name", ["h3", "ch4h", "brh2"])
-def test_one_bead_packed_form_matches_oracle(gpu, oracle, name):
-    """Small one-bead batches run spread over 16 / 32 lanes by default (crcl_set_spread_max_traj); the
-    one-thread-per-trajectory form that large batches keep is held to the same bar."""
-    wq, wp = run_case(gpu, oracle, name, 1, 0, 1, 50, 2, 0.95, 15.0, 5, spread_max=0)
+@pytest.mark.parametrize("name,nb,constrain", [("h3", 1, 0), ("ch4h", 1, 0), ("brh2", 1, 0), ("h3", 8, 0), ("h3", 8, 1),
+                                               ("oh3", 4, 0), ("o3", 2, 0)])
+def test_packed_form_of_few_bead_trajectories_matches_oracle(gpu, oracle, name, nb, constrain):
+    """Small batches of trajectories with fewer threads than components run spread over 16 / 32 lanes by default
+    (crcl_set_spread_max_beads); the packed form that large batches keep is held to the same bar."""
+    wq, wp = run_case(gpu, oracle, name, nb, constrain, 1, 31 if constrain == 1 else 50, 2, 0.95, 15.0, 4, spread_max=0)
     assert wq < C.TOL_QP and wp < C.TOL_QP, (wq, wp)
 
 
