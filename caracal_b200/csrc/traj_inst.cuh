@@ -40,16 +40,11 @@ static cudaError_t launch_one(const TrajArgs& A, int bias_mode, double nose_q, c
     return cudaGetLastError();
 }
 
-// A one-lane surface spread over L threads per bead for SMALL batches of one-bead trajectories: the start-structure chain
-// of a rate calculation (calc_rate.f90:651-1148) is 111 one-bead trajectories one after the other, i.e. a single thread
-// of the GPU at 4 400 instructions per step, 42 % of them the serial form of xi and its Hessian products, 30 % the
-// per-component loops of the step (profiles/r2ai_chain_h3_source.txt).  With L >= 3 NATOMS every lane owns ONE
-// component: the cooperative xi (calc_xi_coop) applies, the loops over the owned components have one trip, Andersen
-// draws its pairs in parallel; the surface itself is evaluated by every lane on the same structure (the same
-// instructions the one thread issued), lane 0 reports the energy.  Batches of more than spread_max trajectories x beads
-// (default CRCL_SPREAD_MAX_BEADS, crcl_set_spread_max_beads) keep the packed form: the spread forms are for batches that
-// leave most SMs with at most one warp, where nothing but the latency of a step counts -- measured (r2an): the 1100 8-bead
-// trajectories of the H + H2 umbrella phase ran 0.45 -> 0.97 s when they were spread two lanes per bead.
+// ---- spread forms: SMALL batches of trajectories that have fewer threads than components in the packed form ------------
+// Batches of more than spread_max trajectories x beads (default CRCL_SPREAD_MAX_BEADS, crcl_set_spread_max_beads) keep the
+// packed form: the spread forms are for batches that leave most SMs with at most one warp, where nothing but the latency
+// of a step counts -- measured (r2an): the 1100 8-bead trajectories of the H + H2 umbrella phase ran 0.45 -> 0.97 s when
+// they were spread two lanes per bead.
 #ifndef CRCL_SPREAD_MAX_BEADS
 #define CRCL_SPREAD_MAX_BEADS 256
 #endif
@@ -70,9 +65,16 @@ template <class P>
 struct has_spread_q<P, decltype((void)P::SPREAD_OK)> {
     static constexpr bool value = true;
 };
-// The same with L lanes per bead for trajectories of 2, 4 or 8 beads, which have fewer threads than components in the
-// packed form too (the constrained recrossing parent of the H + H2 example is ONE 8-bead trajectory of 150 000 steps):
-// lane x of a bead owns the components x NOWN ... x NOWN + NOWN - 1, NOWN = ceil(3 NATOMS / L).
+// A one-lane surface spread over L threads per bead.  The start-structure chain of a rate calculation
+// (calc_rate.f90:651-1148) is 111 one-bead trajectories one after the other, i.e. a single thread of the GPU at 4 400
+// instructions per step, 42 % of them the serial form of xi and its Hessian products, 30 % the per-component loops of the
+// step (profiles/r2ai_chain_h3_source.txt).  With L = 16 >= 3 NATOMS lanes every lane owns ONE component: the cooperative
+// xi (calc_xi_coop) applies, the loops over the owned components have one trip, Andersen draws its pairs in parallel; the
+// surface itself is evaluated by every lane on the same structure (the same instructions the one thread issued, or fewer
+// where the surface shares work between the lanes: P::eval_split), lane 0 reports the energy.
+// The same with 8, 4 or 2 lanes per bead for trajectories of 2, 4 or 8 beads (the constrained recrossing parent of the
+// H + H2 example is ONE 8-bead trajectory of 150 000 steps): lane x of a bead owns the components x NOWN ...
+// x NOWN + NOWN - 1, NOWN = ceil(3 NATOMS / L).
 template <class P, int L>
 struct PesSpread {
     static_assert(P::LANES == 1 && L >= 2 && L <= 32, "spreads a one-lane surface");
