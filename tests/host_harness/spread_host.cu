@@ -1,0 +1,26 @@
+// spread_host.cu -- the ownership map of the spread trajectory forms (PesSpread, csrc/traj_inst.cuh) callable on the CPU:
+// which component (atom * 3 + xyz) lane x of a bead owns in slot k, -1 for none.  Test infrastructure.
+#include "../../include/caracal_gpu.h"
+#include "../../caracal_b200/csrc/pes_h3.cuh"
+#include "../../caracal_b200/csrc/pes_oh3.cuh"
+#include "../../caracal_b200/csrc/traj_inst.cuh"
+
+template <class P>
+static int owned_of(int L, int lane, int k, int* nown)
+{
+    using namespace crcl;
+    switch (L) {
+    case 16: *nown = PesSpread<P, 16>::NOWN; return PesSpread<P, 16>::owned(lane, k);
+    case 8: *nown = PesSpread<P, 8>::NOWN; return PesSpread<P, 8>::owned(lane, k);
+    case 4: *nown = PesSpread<P, 4>::NOWN; return PesSpread<P, 4>::owned(lane, k);
+    case 2: *nown = PesSpread<P, 2>::NOWN; return PesSpread<P, 2>::owned(lane, k);
+    }
+    return -2;
+}
+
+extern "C" int hh_spread_owned(int pes, int L, int lane, int k, int* nown)
+{
+    if (pes == CRCL_PES_H3) return owned_of<crcl::PesH3>(L, lane, k, nown);
+    if (pes == CRCL_PES_OH3) return owned_of<crcl::PesOH3>(L, lane, k, nown);
+    return -2;
+}
